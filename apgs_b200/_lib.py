@@ -1,0 +1,72 @@
+"""ctypes binding of the C ABI in include/apgs_b200.h (the drop-in boundary).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an
+exception is raised.  Build with `python -c "import __graft_entry__ as g; g.build()"` or
+`apgs_b200/csrc/build.sh`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libapgs_b200.so")
+
+MAX_LATENTS = 8
+SYSTEMATIC, MULTINOMIAL = 0, 1
+CDF_AUTO, CDF_EXACT, CDF_BLOCKED = 0, 1, 2
+
+
+class ApgsError(RuntimeError):
+    pass
+
+
+class Latent(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("inner_bytes", C.c_int64)]
+
+
+_p, _i64, _int, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "apgs_version": (_int, []),
+    "apgs_last_error": (C.c_char_p, []),
+    "apgs_weight_stats_f32": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "apgs_local_weight_stats_f32": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
+    "apgs_ancestors_workspace_bytes": (_sz, [_i64, _i64]),
+    "apgs_sample_ancestors_f32": (_int, [_p, _p, _i64, _i64, _int, _p, _i64, _i64, _int,
+                                         _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "apgs_gather_ancestors": (_int, [_p, _p, _i64, _i64, C.POINTER(Latent), _int, _p]),
+    "apgs_resample_workspace_bytes": (_sz, [_i64, _i64]),
+    "apgs_resample_f32": (_int, [_p, _p, _i64, _i64, _int, _p, _i64, _i64, _int,
+                                 C.POINTER(Latent), _int, _p, _p, _p, _p, _p, _sz, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library handle.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ApgsError(
+            "apgs_b200: %s not found -- the CUDA extension has not been built "
+            "(run apgs_b200/csrc/build.sh).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().apgs_last_error()
+        raise ApgsError("%s failed (%d): %s" % (what, code, msg.decode() if msg else ""))
+
+
+def ptr(t):
+    """device pointer of a tensor, or NULL"""
+    return None if t is None else C.c_void_p(t.data_ptr())

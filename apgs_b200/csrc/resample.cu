@@ -1,0 +1,538 @@
+// Resampling kernels for sm_100a: weight normalisation / ESS / log-sum-exp (W1), CDF + ancestor
+// search (R2 systematic, R3 multinomial), ancestor gather (R4) and the fused entry (R5).
+//
+// Replaces apgs/resampler.py:22-54 and the per-model resample_variables (see include/apgs_b200.h).
+// All HBM-bound: no tensor cores.  Layout facts used:
+//   * log_w is (S,B) with B innermost, so a warp reading 32 consecutive instances of one particle
+//     row is one 128 B transaction;
+//   * a latent is (S,B,inner): the output of the gather is a dense stream, the input is B chunks of
+//     `inner` bytes per output row.
+#include "common.cuh"
+
+namespace apgs {
+
+// =============================================================================================
+// K_anc: one CTA owns TB adjacent instances (columns) and ALL S particles of them.
+//   phase 1  load the column tile (coalesced), column max
+//   phase 2  e = exp(x - max), column sum
+//   phase 3  w = e / sum  (optionally stored), sum of squares -> ess, lse
+//   phase 4  CDF over the particle axis (EXACT: one sequential chain per column; BLOCKED: strips)
+//   phase 5  normalise by the last entry
+//   phase 6  ancestor = lower_bound(ncdf, position)  (binary search, coalesced index stores)
+// The tile lives in shared memory (S*TB*4 B) or, for very long particle axes, in a global
+// workspace with the same (row, column) addressing.
+// =============================================================================================
+struct AncArgs {
+    const float* log_w;
+    const float* w_norm;
+    const float* u_sys;        // [B]
+    const double* u_mult;      // strided
+    long long us, ub;
+    long long S, B;
+    int strategy;              // APGS_SYSTEMATIC / APGS_MULTINOMIAL / -1 (stats only)
+    int blocked;               // CDF mode
+    int tile_in_smem;
+    float* ws;                 // global tile (S,B) when !tile_in_smem
+    long long* anc64;
+    int* anc32;
+    float* w_out;
+    float* ess;
+    float* lse;
+};
+
+template <int TB, typename T, typename Op>
+__device__ __forceinline__ T col_reduce(T v, Op op, T* scratch, int col) {
+    // reduce over all threads of the CTA that share `col` (= tid % TB)
+    if (TB < 32) {
+#pragma unroll
+        for (int o = TB; o < 32; o <<= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    if (lane < TB) scratch[warp * TB + lane] = v;
+    __syncthreads();
+    T r = scratch[col];
+    for (int w = 1; w < nwarp; ++w) r = op(r, scratch[w * TB + col]);
+    __syncthreads();
+    return r;
+}
+
+template <int TB>
+__global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* dscr = reinterpret_cast<double*>(smem_raw);                 // blockDim.x doubles
+    float* stile = reinterpret_cast<float*>(smem_raw + (size_t)blockDim.x * sizeof(double));
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int col = tid % TB, rg = tid / TB, R = nthr / TB;
+    const long long b0 = (long long)blockIdx.x * TB;
+    const long long b = b0 + col;
+    const bool colok = b < a.B;
+    const long long S = a.S, B = a.B;
+
+    float* tile;
+    long long ts;
+    if (a.tile_in_smem) { tile = stile + col; ts = TB; }
+    else                { tile = a.ws + b; ts = B; }
+    // in global mode out-of-range columns never touch memory
+    const bool touch = a.tile_in_smem || colok;
+
+    float cmax = 0.f, csum = 1.f;
+    if (a.w_norm == nullptr) {
+        // ---- phase 1
+        float m = -INFINITY;
+        for (long long i = rg; i < S; i += R) {
+            float x = colok ? __ldg(a.log_w + i * B + b) : 0.f;
+            if (touch) tile[i * ts] = x;
+            m = fmaxf(m, x);
+        }
+        cmax = col_reduce<TB>(m, [](float p, float q) { return fmaxf(p, q); },
+                              reinterpret_cast<float*>(dscr), col);
+        // ---- phase 2
+        float ps = 0.f;
+        if (touch)
+            for (long long i = rg; i < S; i += R) {
+                float e = expf(tile[i * ts] - cmax);
+                tile[i * ts] = e;
+                ps += e;
+            }
+        double dsum = col_reduce<TB>((double)ps, [](double p, double q) { return p + q; }, dscr, col);
+        csum = (float)dsum;
+        // ---- phase 3
+        float pq = 0.f;
+        if (touch)
+            for (long long i = rg; i < S; i += R) {
+                float w = __fdiv_rn(tile[i * ts], csum);
+                tile[i * ts] = w;
+                if (a.w_out != nullptr && colok) a.w_out[i * B + b] = w;
+                pq = fmaf(w, w, pq);
+            }
+        if (a.ess != nullptr || a.lse != nullptr) {
+            double dsq = col_reduce<TB>((double)pq, [](double p, double q) { return p + q; }, dscr, col);
+            if (rg == 0 && colok) {
+                if (a.ess != nullptr) a.ess[b] = __fdiv_rn(1.f, (float)dsq);
+                if (a.lse != nullptr) a.lse[b] = cmax + logf(csum);
+            }
+        }
+        if (a.strategy == APGS_MULTINOMIAL) {
+            // Categorical(probs) renormalises once more before torch.multinomial
+            // (torch/distributions/categorical.py:70, reached from apgs/resampler.py:41)
+            float pw = 0.f;
+            if (touch)
+                for (long long i = rg; i < S; i += R) pw += tile[i * ts];
+            const float sw = (float)col_reduce<TB>((double)pw, [](double p, double q) { return p + q; }, dscr, col);
+            if (touch)
+                for (long long i = rg; i < S; i += R) tile[i * ts] = __fdiv_rn(tile[i * ts], sw);
+        }
+    } else {
+        for (long long i = rg; i < S; i += R) {
+            float w = colok ? __ldg(a.w_norm + i * B + b) : 0.f;
+            if (touch) tile[i * ts] = w;
+        }
+    }
+    if (a.strategy < 0) return;
+    __syncthreads();
+
+    // ---- phase 4: CDF
+    if (!a.blocked) {
+        if (rg == 0 && touch) {
+            if (a.strategy == APGS_SYSTEMATIC) {
+                double acc = 0.0;                          // == ATen CPU cumsum<float> (double acc)
+                for (long long i = 0; i < S; ++i) {
+                    acc += (double)tile[i * ts];
+                    tile[i * ts] = (float)acc;
+                }
+            } else {
+                float acc = 0.f;                           // == ATen CPU multinomial running sum
+                for (long long i = 0; i < S; ++i) {
+                    acc = __fadd_rn(acc, tile[i * ts]);
+                    tile[i * ts] = acc;
+                }
+            }
+        }
+    } else {
+        const long long L = (S + R - 1) / R;
+        const long long i0 = (long long)rg * L, i1 = (i0 + L < S) ? (i0 + L) : S;
+        double loc = 0.0;
+        if (touch)
+            for (long long i = i0; i < i1; ++i) loc += (double)tile[i * ts];
+        dscr[rg * TB + col] = loc;
+        __syncthreads();
+        if (rg == 0) {
+            double run = 0.0;
+            for (int r = 0; r < R; ++r) {
+                double v = dscr[r * TB + col];
+                dscr[r * TB + col] = run;
+                run += v;
+            }
+        }
+        __syncthreads();
+        double acc = dscr[rg * TB + col];
+        if (touch)
+            for (long long i = i0; i < i1; ++i) {
+                acc += (double)tile[i * ts];
+                tile[i * ts] = (float)acc;
+            }
+    }
+    __syncthreads();
+
+    // ---- phase 5: normalise by the last CDF entry (the row max of a monotone CDF; resampler.py:32-33)
+    const float norm = touch ? tile[(S - 1) * ts] : 1.f;
+    __syncthreads();
+    if (touch)
+        for (long long i = rg; i < S; i += R) tile[i * ts] = __fdiv_rn(tile[i * ts], norm);
+    __syncthreads();
+
+    // ---- phase 6: ancestors
+    if (!colok) return;
+    const float fS = (float)S;
+    const float u = (a.strategy == APGS_SYSTEMATIC) ? __ldg(a.u_sys + b) : 0.f;
+    for (long long i = rg; i < S; i += R) {
+        long long lo = 0, hi = S;
+        if (a.strategy == APGS_SYSTEMATIC) {
+            const float pos = __fdiv_rn(__fadd_rn(u, (float)i), fS);          // resampler.py:28
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if (tile[mid * ts] < pos) lo = mid + 1; else hi = mid;
+            }
+        } else {
+            const double ud = __ldg(a.u_mult + i * a.us + b * a.ub);
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if ((double)tile[mid * ts] < ud) lo = mid + 1; else hi = mid;
+            }
+        }
+        if (lo > S - 1) lo = S - 1;                        // memory safety on NaN / degenerate weights
+        if (a.anc32 != nullptr) a.anc32[i * B + b] = (int)lo;
+        if (a.anc64 != nullptr) a.anc64[i * B + b] = lo;
+    }
+}
+
+static const size_t kSmemTileBudget = 200 * 1024;
+
+struct AncPlan { int TB; int nthr; int tile_in_smem; size_t smem; int grid; };
+
+static AncPlan plan_ancestors(long long S, long long B) {
+    AncPlan p;
+    int TB = 32;
+    while (TB > 1 && (size_t)S * TB * 4 > kSmemTileBudget) TB >>= 1;
+    p.tile_in_smem = ((size_t)S * TB * 4 <= kSmemTileBudget) ? 1 : 0;
+    if (p.tile_in_smem) {
+        // spread over the 148 SMs: shrink the column tile while the grid is under ~2 CTAs/SM
+        while (TB > 4 && (B + TB - 1) / TB < 2 * sm_count()) TB >>= 1;
+    } else {
+        TB = 8;
+    }
+    while (TB > 1 && TB / 2 >= B) TB >>= 1;               // do not waste lanes on tiny B
+    long long want = (S * TB + 7) / 8;
+    int nthr = 128;
+    while (nthr < 1024 && nthr < want) nthr <<= 1;
+    if (!p.tile_in_smem) nthr = 1024;
+    p.TB = TB;
+    p.nthr = nthr;
+    p.smem = (size_t)nthr * sizeof(double) + (p.tile_in_smem ? (size_t)S * TB * 4 : 0);
+    p.grid = (int)((B + TB - 1) / TB);
+    return p;
+}
+
+template <int TB>
+static int launch_anc_tb(const AncArgs& a, const AncPlan& p, cudaStream_t st) {
+    if (p.smem > 48 * 1024)
+        APGS_CUDA_OK(cudaFuncSetAttribute(k_ancestors<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)p.smem), "cudaFuncSetAttribute(k_ancestors)");
+    k_ancestors<TB><<<p.grid, p.nthr, p.smem, st>>>(a);
+    APGS_LAUNCH_OK("k_ancestors launch");
+    return 0;
+}
+
+static int launch_ancestors(AncArgs a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    AncPlan p = plan_ancestors(a.S, a.B);
+    a.tile_in_smem = p.tile_in_smem;
+    if (!p.tile_in_smem) {
+        size_t need = (size_t)a.S * a.B * sizeof(float);
+        if (workspace == nullptr || workspace_bytes < need)
+            return fail(APGS_E_WORKSPACE, "ancestors: workspace of %zu bytes required (S=%lld B=%lld), got %zu",
+                        need, a.S, a.B, workspace_bytes);
+        a.ws = reinterpret_cast<float*>(workspace);
+    }
+    switch (p.TB) {
+        case 32: return launch_anc_tb<32>(a, p, st);
+        case 16: return launch_anc_tb<16>(a, p, st);
+        case 8:  return launch_anc_tb<8>(a, p, st);
+        case 4:  return launch_anc_tb<4>(a, p, st);
+        case 2:  return launch_anc_tb<2>(a, p, st);
+        default: return launch_anc_tb<1>(a, p, st);
+    }
+}
+
+// =============================================================================================
+// K_gather: dst_l[s,b,:] = src_l[anc[s,b], b, :] for up to 8 latents in one launch.
+// Output-stationary: consecutive threads own consecutive 16/8/4-byte vectors of the dense output,
+// so stores are perfectly coalesced and each source chunk is read with full-width vectors.  The
+// int64 gather index the reference materialises (apgs/resampler.py:48,53) never exists.
+// =============================================================================================
+struct GLat {
+    const char* src;
+    char* dst;
+    unsigned int vlog;         // log2(vector bytes)
+    unsigned int vpr;          // vectors per (s,b) row
+    unsigned int Bv;           // vectors per particle row  (= B * vpr)
+    unsigned int rows_per_blk; // >1: block covers whole rows;  1: row split into chunks
+    unsigned int chunks;       // chunks per row when rows_per_blk == 1
+    unsigned int blk_begin;    // first block of this latent
+    FastDiv d_vpr, d_Bv, d_chunks;
+};
+struct GatherArgs {
+    GLat lat[APGS_MAX_LATENTS];
+    int n;
+    const int* anc32;
+    const long long* anc64;
+    long long S, B;
+};
+
+constexpr int kGThreads = 256;
+constexpr int kGUnroll = 8;
+constexpr int kGTile = kGThreads * kGUnroll;   // vectors per block
+
+template <typename V>
+__device__ __forceinline__ void gather_block(const GLat& L, const GatherArgs& g, unsigned int lb) {
+    const V* __restrict__ src = reinterpret_cast<const V*>(L.src);
+    V* __restrict__ dst = reinterpret_cast<V*>(L.dst);
+    long long s0;
+    unsigned int t0, tend;          // block covers row-local vector range [t0, tend) starting at row s0
+    unsigned int nrows;
+    if (L.rows_per_blk > 1) {
+        s0 = (long long)lb * L.rows_per_blk;
+        long long left = g.S - s0;
+        nrows = left < (long long)L.rows_per_blk ? (unsigned int)left : L.rows_per_blk;
+        t0 = 0;
+        tend = nrows * L.Bv;
+    } else {
+        unsigned int row = fastdiv(lb, L.d_chunks);
+        unsigned int ch = lb - row * L.chunks;
+        s0 = row;
+        t0 = ch * kGTile;
+        tend = min(t0 + (unsigned int)kGTile, L.Bv);
+        nrows = 1;
+    }
+    const long long Bv = L.Bv;
+    V val[kGUnroll];
+    long long so[kGUnroll];
+#pragma unroll
+    for (int k = 0; k < kGUnroll; ++k) {
+        unsigned int t = t0 + k * kGThreads + threadIdx.x;
+        so[k] = -1;
+        if (t < tend) {
+            unsigned int ds = (L.rows_per_blk > 1) ? fastdiv(t, L.d_Bv) : 0u;
+            unsigned int v = t - ds * L.Bv;                   // vector within the particle row
+            unsigned int bcol = fastdiv(v, L.d_vpr);
+            long long s = s0 + ds;
+            long long anc = g.anc32 ? (long long)__ldg(g.anc32 + s * g.B + bcol)
+                                    : __ldg(g.anc64 + s * g.B + bcol);
+            so[k] = anc * Bv + v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kGUnroll; ++k)
+        if (so[k] >= 0) val[k] = __ldcs(src + so[k]);
+#pragma unroll
+    for (int k = 0; k < kGUnroll; ++k) {
+        unsigned int t = t0 + k * kGThreads + threadIdx.x;
+        if (so[k] >= 0) __stcs(dst + (s0 * Bv + t), val[k]);
+    }
+}
+
+__global__ void __launch_bounds__(kGThreads) k_gather(const __grid_constant__ GatherArgs g) {
+    int l = 0;
+#pragma unroll 1
+    for (int i = 1; i < g.n; ++i)
+        if (blockIdx.x >= g.lat[i].blk_begin) l = i;
+    const GLat& L = g.lat[l];
+    const unsigned int lb = blockIdx.x - L.blk_begin;
+    switch (L.vlog) {
+        case 4: gather_block<uint4>(L, g, lb); break;
+        case 3: gather_block<uint2>(L, g, lb); break;
+        case 2: gather_block<unsigned int>(L, g, lb); break;
+        case 1: gather_block<unsigned short>(L, g, lb); break;
+        default: gather_block<unsigned char>(L, g, lb); break;
+    }
+}
+
+static int launch_gather(const int* anc32, const long long* anc64, long long S, long long B,
+                         const apgs_latent_t* lat, int n, cudaStream_t st) {
+    if (n < 0 || n > APGS_MAX_LATENTS) return fail(APGS_E_BADARG, "gather: n_latents=%d out of [0,%d]", n, APGS_MAX_LATENTS);
+    if ((anc32 == nullptr) == (anc64 == nullptr)) return fail(APGS_E_BADARG, "gather: exactly one of anc32/anc64 must be given");
+    if (n == 0 || S == 0 || B == 0) return 0;
+    GatherArgs g;
+    g.n = n; g.anc32 = anc32; g.anc64 = anc64; g.S = S; g.B = B;
+    unsigned long long blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        const apgs_latent_t& a = lat[i];
+        if (a.src == nullptr || a.dst == nullptr || a.inner_bytes <= 0)
+            return fail(APGS_E_BADARG, "gather: latent %d has null pointer or inner_bytes<=0", i);
+        unsigned int vlog = 4;
+        while (vlog > 0 && ((a.inner_bytes & ((1ll << vlog) - 1)) != 0 ||
+                            !aligned(a.src, 1u << vlog) || !aligned(a.dst, 1u << vlog))) --vlog;
+        long long vpr = a.inner_bytes >> vlog;
+        long long Bv = B * vpr;
+        if (Bv >= (1ll << 31) - kGTile) return fail(APGS_E_SHAPE, "gather: latent %d row of %lld vectors too long", i, Bv);
+        GLat& L = g.lat[i];
+        L.src = reinterpret_cast<const char*>(a.src);
+        L.dst = reinterpret_cast<char*>(a.dst);
+        L.vlog = vlog; L.vpr = (unsigned int)vpr; L.Bv = (unsigned int)Bv;
+        L.d_vpr = make_fastdiv(L.vpr); L.d_Bv = make_fastdiv(L.Bv);
+        unsigned long long nb;
+        if (Bv * 2 <= kGTile) {
+            L.rows_per_blk = (unsigned int)(kGTile / Bv);
+            L.chunks = 1;
+            nb = (unsigned long long)((S + L.rows_per_blk - 1) / L.rows_per_blk);
+        } else {
+            L.rows_per_blk = 1;
+            L.chunks = (unsigned int)((Bv + kGTile - 1) / kGTile);
+            nb = (unsigned long long)S * L.chunks;
+        }
+        L.d_chunks = make_fastdiv(L.chunks);
+        if (blocks + nb >= (1ull << 31)) return fail(APGS_E_SHAPE, "gather: grid too large");
+        L.blk_begin = (unsigned int)blocks;
+        blocks += nb;
+    }
+    k_gather<<<(unsigned int)blocks, kGThreads, 0, st>>>(g);
+    APGS_LAUNCH_OK("k_gather launch");
+    return 0;
+}
+
+// =============================================================================================
+// W2: softmax over S for every (b, n) column of log_w_local (S,B,N) + sum over n.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_local_sum(const float* __restrict__ lwl, long long rows, int N,
+                                                   float* __restrict__ out) {
+    // one warp per (s,b) row of N contiguous floats
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int n = lane; n < N; n += 32) acc += (double)__ldg(lwl + row * N + n);
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = (float)acc;
+}
+
+__global__ void __launch_bounds__(256) k_local_softmax(const float* __restrict__ lwl, long long S, long long C,
+                                                       float* __restrict__ w) {
+    // C = B*N columns, softmax over S; thread per column, lanes along the contiguous axis
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float m = -INFINITY;
+    for (long long s = 0; s < S; ++s) m = fmaxf(m, __ldg(lwl + s * C + c));
+    float sum = 0.f;
+    for (long long s = 0; s < S; ++s) sum += expf(__ldg(lwl + s * C + c) - m);
+    for (long long s = 0; s < S; ++s) w[s * C + c] = __fdiv_rn(expf(__ldg(lwl + s * C + c) - m), sum);
+}
+
+}  // namespace apgs
+
+using namespace apgs;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+static int check_sb(long long S, long long B, const char* who) {
+    if (S <= 0 || B <= 0) return fail(APGS_E_SHAPE, "%s: S=%lld B=%lld must be positive", who, S, B);
+    if (S >= (1ll << 31) || B >= (1ll << 31)) return fail(APGS_E_SHAPE, "%s: S=%lld B=%lld too large", who, S, B);
+    return 0;
+}
+
+extern "C" size_t apgs_ancestors_workspace_bytes(int64_t S, int64_t B) {
+    if (S <= 0 || B <= 0) return 0;
+    if ((size_t)S * 4 <= kSmemTileBudget) return 0;
+    return (size_t)S * (size_t)B * sizeof(float);
+}
+
+extern "C" size_t apgs_resample_workspace_bytes(int64_t S, int64_t B) {
+    if (S <= 0 || B <= 0) return 0;
+    size_t idx = ((size_t)S * (size_t)B * sizeof(int32_t) + 255) & ~(size_t)255;
+    return idx + apgs_ancestors_workspace_bytes(S, B);
+}
+
+extern "C" int apgs_weight_stats_f32(const float* log_w, int64_t S, int64_t B, float* w_out, float* ess,
+                                     float* lse, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int e = check_sb(S, B, "weight_stats")) return e;
+    if (log_w == nullptr) return fail(APGS_E_BADARG, "weight_stats: log_w is NULL");
+    AncArgs a = {};
+    a.log_w = log_w; a.S = S; a.B = B; a.strategy = -1;
+    a.w_out = w_out; a.ess = ess; a.lse = lse;
+    return launch_ancestors(a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int apgs_sample_ancestors_f32(const float* log_w, const float* w_norm, int64_t S, int64_t B,
+                                         int strategy, const void* uniforms, int64_t u_stride_s,
+                                         int64_t u_stride_b, int cdf_mode, int64_t* anc64, int32_t* anc32,
+                                         float* w_out, float* ess, float* lse, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+    if (int e = check_sb(S, B, "sample_ancestors")) return e;
+    if ((log_w == nullptr) == (w_norm == nullptr))
+        return fail(APGS_E_BADARG, "sample_ancestors: exactly one of log_w / w_norm must be given");
+    if (strategy != APGS_SYSTEMATIC && strategy != APGS_MULTINOMIAL)
+        return fail(APGS_E_BADARG, "sample_ancestors: unknown strategy %d", strategy);
+    if (uniforms == nullptr) return fail(APGS_E_BADARG, "sample_ancestors: uniforms is NULL");
+    if (cdf_mode < APGS_CDF_AUTO || cdf_mode > APGS_CDF_BLOCKED)
+        return fail(APGS_E_BADARG, "sample_ancestors: unknown cdf_mode %d", cdf_mode);
+    if (anc64 == nullptr && anc32 == nullptr)
+        return fail(APGS_E_BADARG, "sample_ancestors: no ancestor output given");
+    AncArgs a = {};
+    a.log_w = log_w; a.w_norm = w_norm; a.S = S; a.B = B; a.strategy = strategy;
+    if (strategy == APGS_SYSTEMATIC) a.u_sys = reinterpret_cast<const float*>(uniforms);
+    else { a.u_mult = reinterpret_cast<const double*>(uniforms); a.us = u_stride_s; a.ub = u_stride_b; }
+    a.blocked = (cdf_mode == APGS_CDF_BLOCKED) || (cdf_mode == APGS_CDF_AUTO && S > 8192);
+    a.anc64 = reinterpret_cast<long long*>(anc64); a.anc32 = anc32;
+    a.w_out = w_out; a.ess = ess; a.lse = lse;
+    return launch_ancestors(a, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int apgs_gather_ancestors(const int32_t* anc32, const int64_t* anc64, int64_t S, int64_t B,
+                                     const apgs_latent_t* latents, int n_latents, void* stream) {
+    if (int e = check_sb(S, B, "gather_ancestors")) return e;
+    if (latents == nullptr && n_latents > 0) return fail(APGS_E_BADARG, "gather_ancestors: latents is NULL");
+    return launch_gather(anc32, reinterpret_cast<const long long*>(anc64), S, B, latents, n_latents,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int apgs_resample_f32(const float* log_w, const float* w_norm, int64_t S, int64_t B, int strategy,
+                                 const void* uniforms, int64_t u_stride_s, int64_t u_stride_b, int cdf_mode,
+                                 const apgs_latent_t* latents, int n_latents, int64_t* anc64, float* w_out,
+                                 float* ess, float* lse, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (int e = check_sb(S, B, "resample")) return e;
+    size_t need = apgs_resample_workspace_bytes(S, B);
+    if (workspace == nullptr || workspace_bytes < need)
+        return fail(APGS_E_WORKSPACE, "resample: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+    if (!aligned(workspace, 256)) return fail(APGS_E_ALIGN, "resample: workspace must be 256-byte aligned");
+    size_t idx_bytes = ((size_t)S * (size_t)B * sizeof(int32_t) + 255) & ~(size_t)255;
+    int32_t* anc32 = reinterpret_cast<int32_t*>(workspace);
+    char* rest = reinterpret_cast<char*>(workspace) + idx_bytes;
+    int e = apgs_sample_ancestors_f32(log_w, w_norm, S, B, strategy, uniforms, u_stride_s, u_stride_b, cdf_mode,
+                                      anc64, anc32, w_out, ess, lse, rest, workspace_bytes - idx_bytes, stream);
+    if (e) return e;
+    return apgs_gather_ancestors(anc32, nullptr, S, B, latents, n_latents, stream);
+}
+
+extern "C" int apgs_local_weight_stats_f32(const float* log_w_local, int64_t S, int64_t B, int64_t N,
+                                           float* w_local_out, float* log_w_out, void* stream) {
+    if (int e = check_sb(S, B, "local_weight_stats")) return e;
+    if (N <= 0 || N >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: N=%lld", (long long)N);
+    if (log_w_local == nullptr) return fail(APGS_E_BADARG, "local_weight_stats: input is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (log_w_out != nullptr) {
+        long long rows = (long long)S * B;
+        long long blocks = (rows + 7) / 8;
+        if (blocks >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: too many rows");
+        k_local_sum<<<(unsigned int)blocks, 256, 0, st>>>(log_w_local, rows, (int)N, log_w_out);
+        APGS_LAUNCH_OK("k_local_sum launch");
+    }
+    if (w_local_out != nullptr) {
+        long long C = (long long)B * N;
+        long long blocks = (C + 255) / 256;
+        if (blocks >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: too many columns");
+        k_local_softmax<<<(unsigned int)blocks, 256, 0, st>>>(log_w_local, S, C, w_local_out);
+        APGS_LAUNCH_OK("k_local_softmax launch");
+    }
+    return 0;
+}

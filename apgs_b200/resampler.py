@@ -1,0 +1,82 @@
+"""Drop-in for apgs/resampler.py:7-54 on top of the sm_100a kernels.
+
+Same constructor, same method names and argument meaning:
+    Resampler(strategy, sample_size, CUDA, device)
+    .sample_ancestral_index(log_weights: f32[S,B]) -> i64[S,B]      (apgs/resampler.py:22-44)
+    .resample_4dims(var, ancestral_index) / .resample_5dims(...)     (apgs/resampler.py:46-54)
+plus one fused entry the reference lacks:
+    .resample(latents, log_weights) -> list of resampled latents     (= resample_variables)
+
+Random numbers stay in PyTorch (north_star): systematic draws torch.rand(B, 1) -- exactly what
+Uniform(0,1).sample((B,)) with shape-[1] parameters consumes (quirk Q5); multinomial draws
+float64 uniforms and inverts the CDF, which is what ATen's CPU multinomial does internally.
+"""
+import torch
+
+from . import _lib, ops
+
+
+class Resampler():
+    def __init__(self, strategy, sample_size, CUDA=True, device=None, generator=None):
+        if strategy not in ("systematic", "multinomial"):
+            # the reference's assert at apgs/resampler.py:11 is always true; its else-branch prints
+            raise ValueError("ERROR! specify resampling strategy as either systematic or multinomial.")
+        if not CUDA:
+            raise _lib.ApgsError("apgs_b200.Resampler runs on CUDA only (no CPU fallback)")
+        _lib.load()
+        self.strategy = strategy
+        self.S = int(sample_size)
+        self.CUDA = CUDA
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        self.generator = generator
+        self.cdf_mode = _lib.CDF_AUTO
+
+    # ------------------------------------------------------------------ uniforms (host RNG)
+    def draw_uniforms(self, S, B, device):
+        if self.strategy == "systematic":
+            return torch.rand(B, 1, device=device, generator=self.generator)
+        return torch.rand(S, B, dtype=torch.float64, device=device, generator=self.generator)
+
+    def _check(self, log_weights):
+        if log_weights.dim() != 2:
+            raise ValueError("log_weights must be (S, B)")
+        if self.strategy == "systematic" and log_weights.shape[0] != self.S:
+            raise ValueError("log_weights has %d particles but the resampler was built for sample_size=%d"
+                             % (log_weights.shape[0], self.S))
+
+    # ------------------------------------------------------------------ reference surface
+    def sample_ancestral_index(self, log_weights, uniforms=None):
+        """sample ancestral indices"""
+        self._check(log_weights)
+        S, B = log_weights.shape
+        if uniforms is None:
+            uniforms = self.draw_uniforms(S, B, log_weights.device)
+        return ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms,
+                                    cdf_mode=self.cdf_mode)
+
+    def resample_4dims(self, var, ancestral_index):
+        if var.dim() != 4:
+            raise ValueError("resample_4dims expects a 4-D tensor")
+        return ops.gather_ancestors([var], ancestral_index)[0]
+
+    def resample_5dims(self, var, ancestral_index):
+        if var.dim() != 5:
+            raise ValueError("resample_5dims expects a 5-D tensor")
+        return ops.gather_ancestors([var], ancestral_index)[0]
+
+    # ------------------------------------------------------------------ fused entry
+    def resample(self, latents, log_weights, uniforms=None, want_stats=False, want_index=False):
+        """One ancestor draw + gather of every latent (2 launches, no int64 index tensor).
+        Returns the list of resampled latents (and (w, ess, lse) / ancestors when asked)."""
+        self._check(log_weights)
+        S, B = log_weights.shape
+        if uniforms is None:
+            uniforms = self.draw_uniforms(S, B, log_weights.device)
+        outs, anc, stats = ops.resample(latents, log_w=log_weights, strategy=self.strategy,
+                                        uniforms=uniforms, cdf_mode=self.cdf_mode,
+                                        want_index=want_index, want_stats=want_stats)
+        if want_stats or want_index:
+            return outs, anc, stats
+        return outs

@@ -1,0 +1,125 @@
+/*
+ * apgs_b200 -- C ABI of the B200 (sm_100a) kernels behind the APG reweight -> resample hot path.
+ *
+ * The reference (hao-w/apgs) is pure Python/PyTorch and has NO FFI boundary:
+ * the path sits behind plain Python objects.  Each entry point below names the reference
+ * interface it replaces (file:line, relative to the reference tree); the Python binding a
+ * maintainer would add (ctypes) is shown in INTEGRATION.md and implemented in apgs_b200/_lib.py.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated; tensors are dense row-major fp32 in the
+ *     reference layout (S, B, ...) -- S particles, B instances;
+ *   - no allocation, no ownership transfer, no global mutable state; every call is asynchronous
+ *     on `stream` (a cudaStream_t passed as void*) and re-entrant from any host thread;
+ *   - return value: 0 ok, < 0 bad argument (APGS_E_*), > 0 a cudaError_t;
+ *     apgs_last_error() returns a thread-local message for the last non-zero return;
+ *   - nothing throws across the ABI.
+ */
+#ifndef APGS_B200_H
+#define APGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APGS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define APGS_API __attribute__((visibility("default")))
+#else
+#define APGS_API
+#endif
+
+#define APGS_E_BADARG   (-1)
+#define APGS_E_SHAPE    (-2)
+#define APGS_E_ALIGN    (-3)
+#define APGS_E_WORKSPACE (-4)
+#define APGS_E_UNSUPPORTED (-5)
+
+/* resampling strategy (apgs/resampler.py:8-11) */
+#define APGS_SYSTEMATIC  0
+#define APGS_MULTINOMIAL 1
+
+/* how the CDF over the particle axis is accumulated (DESIGN.md "index exactness")
+ *   AUTO    : EXACT when S <= 8192, BLOCKED otherwise
+ *   EXACT   : one sequential chain per instance -- systematic: fp64 running sum rounded to fp32
+ *             per element (== ATen CPU cumsum, apgs/resampler.py:31); multinomial: sequential
+ *             fp32 running sum (== ATen CPU multinomial_with_replacement, apgs/resampler.py:41)
+ *   BLOCKED : strip-parallel fp64 scan (bit-equal to EXACT-systematic except where fp64
+ *             re-association moves a prefix across an fp32 rounding boundary, ~2^-29 / element) */
+#define APGS_CDF_AUTO    0
+#define APGS_CDF_EXACT   1
+#define APGS_CDF_BLOCKED 2
+
+APGS_API int         apgs_version(void);
+APGS_API const char* apgs_last_error(void);
+
+/* ----------------------------------------------------------------------------------------------
+ * W1  weight normalisation + ESS + log-sum-exp over the particle axis.
+ * replaces: F.softmax(log_w, 0) / 1/(w**2).sum(0)   apgs/gmm/objectives.py:93,98,141,146,181,186;
+ *           apgs/dmm/objectives.py:94,100,137,143; apgs/bmnist/objectives.py:150,156,207,242,248.
+ *   log_w (S,B) in;  w_out (S,B), ess (B), lse (B) out -- each output may be NULL.
+ * workspace: apgs_ancestors_workspace_bytes(S, B) bytes (may be 0 -> NULL allowed).           */
+APGS_API int apgs_weight_stats_f32(const float* log_w, int64_t S, int64_t B,
+                          float* w_out, float* ess, float* lse,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* W2  per-point weights: w_local = softmax over S of log_w_local (S,B,N); log_w = sum_n.
+ * replaces: apgs/gmm/objectives.py:216-218, apgs/dmm/objectives.py:173-175.
+ *   w_local_out (S,B,N) and log_w_out (S,B) may each be NULL.                                  */
+APGS_API int apgs_local_weight_stats_f32(const float* log_w_local, int64_t S, int64_t B, int64_t N,
+                                float* w_local_out, float* log_w_out, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * R2/R3  ancestor sampling.   replaces Resampler.sample_ancestral_index, apgs/resampler.py:22-44.
+ *   exactly one of log_w / w_norm is non-NULL ((S,B) fp32).  With log_w the kernel normalises
+ *   itself (and can emit w_out/ess/lse like W1, so the reference's duplicated softmax is done
+ *   once); with w_norm (already-normalised weights) ancestors are bit-exact with the reference
+ *   run on CPU given the same uniforms.
+ *   strategy APGS_SYSTEMATIC : uniforms = float32[B], one per instance (apgs/resampler.py:28);
+ *                              u_stride_* ignored.
+ *   strategy APGS_MULTINOMIAL: uniforms = float64, element (s,b) at uniforms[s*u_stride_s +
+ *                              b*u_stride_b] (the reference's generator order is (B,S):
+ *                              u_stride_s = 1, u_stride_b = S).
+ *   anc64 (S,B) int64 and/or anc32 (S,B) int32 receive the ancestors (either may be NULL).   */
+APGS_API size_t apgs_ancestors_workspace_bytes(int64_t S, int64_t B);
+APGS_API int apgs_sample_ancestors_f32(const float* log_w, const float* w_norm, int64_t S, int64_t B,
+                              int strategy, const void* uniforms,
+                              int64_t u_stride_s, int64_t u_stride_b, int cdf_mode,
+                              int64_t* anc64, int32_t* anc32,
+                              float* w_out, float* ess, float* lse,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * R4  ancestor gather.  replaces Resampler.resample_4dims / resample_5dims,
+ *     apgs/resampler.py:46-54 (no materialised int64 gather index).
+ *   for every latent l:  dst_l[s, b, :] = src_l[anc[s, b], b, :]   with inner_bytes_l bytes per
+ *   (s,b) row; src/dst dense, non-overlapping.  Exactly one of anc32 / anc64 is non-NULL.
+ *   Up to APGS_MAX_LATENTS latents are gathered by ONE launch.                                 */
+#define APGS_MAX_LATENTS 8
+typedef struct apgs_latent {
+    const void* src;
+    void*       dst;
+    int64_t     inner_bytes;
+} apgs_latent_t;   /* HOST array */
+
+APGS_API int apgs_gather_ancestors(const int32_t* anc32, const int64_t* anc64, int64_t S, int64_t B,
+                          const apgs_latent_t* latents, int n_latents, void* stream);
+
+/* R5  fused resample = R2/R3 + R4.  replaces resample_variables,
+ *     apgs/gmm/objectives.py:229-234, apgs/dmm/objectives.py:190-195, apgs/bmnist/objectives.py:5-9.
+ *   workspace: apgs_resample_workspace_bytes(S,B) (holds the int32 ancestors + CDF scratch).  */
+APGS_API size_t apgs_resample_workspace_bytes(int64_t S, int64_t B);
+APGS_API int apgs_resample_f32(const float* log_w, const float* w_norm, int64_t S, int64_t B,
+                      int strategy, const void* uniforms, int64_t u_stride_s, int64_t u_stride_b,
+                      int cdf_mode, const apgs_latent_t* latents, int n_latents,
+                      int64_t* anc64, float* w_out, float* ess, float* lse,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APGS_B200_H */
