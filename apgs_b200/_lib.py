@@ -23,7 +23,21 @@ class Latent(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("inner_bytes", C.c_int64)]
 
 
+class GmmPrior(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("alpha", "beta", "mu", "nu", "pi")]
+
+
+class GmmPost(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("alpha", "beta", "mu", "nu")]
+
+
+class GmmOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b",
+                                          "log_w_local", "log_q_local")]
+
+
 _p, _i64, _int, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
+_PR, _PO, _OUT = C.POINTER(GmmPrior), C.POINTER(GmmPost), C.POINTER(GmmOut)
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
@@ -38,6 +52,12 @@ SIGNATURES = {
     "apgs_resample_workspace_bytes": (_sz, [_i64, _i64]),
     "apgs_resample_f32": (_int, [_p, _p, _i64, _i64, _int, _p, _i64, _i64, _int,
                                  C.POINTER(Latent), _int, _p, _p, _p, _p, _p, _sz, _p]),
+    "apgs_gmm_nss_posterior_f32": (_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "apgs_gmm_logw_oneshot_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_gmm_logw_eta_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_gmm_logw_z_f32": (_int, [_p, _p, _p, _p, _PR, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_gmm_logw_joint_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _p, _p, _p,
+                                       _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
 }
 
 _lib = None

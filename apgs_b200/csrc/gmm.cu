@@ -1,0 +1,484 @@
+// GMM reweighting kernels for sm_100a.
+//
+//   k_gmm_nss_posterior  G1: neural sufficient statistics -> Normal-Gamma posterior parameters
+//                            (apgs/gmm/kls_gmm.py:92-119, quirks Q1/Q2)
+//   k_gmm_weights        G2/G3/G4: log importance weights of the eta step, the z step, the joint
+//                            step and the one-shot (apgs/gmm/objectives.py:74-227,
+//                            apgs/gmm/models.py:139-185; torch.distributions formulas restated)
+//
+// Both are HBM-bound streams over particles r = s*B + b whose rows are contiguous in memory.
+// A CTA owns a tile of P consecutive particles: the large per-particle rows (z one-hot, q_probs,
+// gamma, x') are staged into shared memory by the bulk-copy engine (tile.cuh) while the threads
+// evaluate the small (K,D) terms; LANES lanes then split the N points of each particle.
+// fp32 arithmetic in the reference's operation order; N-sums are accumulated in fp64.
+#include "tile.cuh"
+
+namespace apgs {
+
+#define LOG_SQRT_2PI_F 0.918938533204672741780329736406f
+#define FLT_EPS_F 1.1920928955078125e-07f
+
+__device__ __forceinline__ float xlogy_f(float a, float b) { return a == 0.f ? 0.f : __fmul_rn(a, logf(b)); }
+
+// torch/distributions/gamma.py:89-98
+__device__ __forceinline__ float gamma_lp(float v, float c, float r) {
+    float t = __fadd_rn(xlogy_f(c, r), xlogy_f(__fsub_rn(c, 1.f), v));
+    t = __fsub_rn(t, __fmul_rn(r, v));
+    return __fsub_rn(t, lgammaf(c));
+}
+// torch/distributions/normal.py:87-101
+__device__ __forceinline__ float normal_lp(float v, float loc, float scale) {
+    const float var = __fmul_rn(scale, scale);
+    const float d = __fsub_rn(v, loc);
+    float t = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var));
+    t = __fsub_rn(t, logf(scale));
+    return __fsub_rn(t, LOG_SQRT_2PI_F);
+}
+// 1 / sqrt(v)  as the reference writes it (models.py:34,74,147,177): IEEE sqrt then IEEE divide
+__device__ __forceinline__ float inv_sqrt_ref(float v) { return __fdiv_rn(1.f, __fsqrt_rn(v)); }
+
+template <int LANES, typename T>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ============================================================================================
+// G1
+// ============================================================================================
+struct NssArgs {
+    const float* xp;      // (R, N, D)
+    const float* gamma;   // (R, N, K)
+    const float *ra, *rb, *rm, *rn;   // prior alpha, beta, mu, nu  (K, D)
+    float *oa, *ob, *om, *on;         // posterior (R, K, D)
+    long long R;
+    int N;
+};
+
+template <int K, int D, int P, int LANES>
+__global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long bar;
+    const int N = a.N;
+    float* s_g = reinterpret_cast<float*>(smem);                 // P*N*K
+    float* s_x = s_g + (size_t)P * N * K;                        // P*N*D
+    const long long r0 = (long long)blockIdx.x * P;
+    const int rows = (int)min((long long)P, a.R - r0);
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    StageReq req[2] = {{s_g, a.gamma + r0 * N * K, (unsigned int)(rows * N * K * 4)},
+                       {s_x, a.xp + r0 * N * D, (unsigned int)(rows * N * D * 4)}};
+    stage_issue(req, 2, &bar);
+    const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
+    const bool valid = p < rows;
+    stage_wait(&bar, 0);
+
+    double s1[K], s2[K][D], s3[K][D];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        s1[k] = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { s2[k][d] = 0.0; s3[k][d] = 0.0; }
+    }
+    if (valid) {
+        const float* g = s_g + (size_t)p * N * K;
+        const float* x = s_x + (size_t)p * N * D;
+        for (int n = j; n < N; n += LANES) {
+            float xv[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) xv[d] = x[n * D + d];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float gk = g[n * K + k];
+                s1[k] += (double)gk;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float gx = __fmul_rn(gk, xv[d]);                 // z_expand * ob_expand
+                    s2[k][d] += (double)gx;
+                    s3[k][d] += (double)__fmul_rn(gk, __fmul_rn(xv[d], xv[d]));   // z_expand * ob_expand**2
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        s1[k] = group_sum<LANES>(s1[k]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) { s2[k][d] = group_sum<LANES>(s2[k][d]); s3[k][d] = group_sum<LANES>(s3[k][d]); }
+    }
+    if (!valid) return;
+    // lanes 0..K*D-1 finish one (k,d) element each (kls_gmm.py:110-118, fp32, reference order)
+    for (int e = j; e < K * D; e += LANES) {
+        const int k = e / D, d = e % D;
+        float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd)
+                if (kk == k && dd == d) { c1 = (float)s1[kk]; c2 = (float)s2[kk][dd]; c3 = (float)s3[kk][dd]; }
+        const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
+        const float cnt = (c1 == 0.f) ? 1.f : c1;                                   // Q1
+        const float x_bar = __fdiv_rn(c2, cnt);
+        const float alpha = __fadd_rn(a0, __fdiv_rn(cnt, 2.f));
+        const float nu = __fadd_rn(n0, cnt);
+        const float cn = __fadd_rn(cnt, n0);
+        const float mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), c2), cn);
+        const float t1 = __fdiv_rn(__fsub_rn(c3, __fdiv_rn(__fmul_rn(c2, c2), cnt)), 2.f);
+        const float dx = __fsub_rn(x_bar, n0);                                       // Q2: prior_nu
+        const float t2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
+        const float beta = __fadd_rn(__fadd_rn(b0, t1), t2);
+        const long long o = (r0 + p) * (K * D) + e;
+        a.oa[o] = alpha; a.ob[o] = beta; a.om[o] = mu; a.on[o] = nu;
+    }
+}
+
+// ============================================================================================
+// G2 / G3 / G4
+// ============================================================================================
+enum { STEP_ONESHOT = 0, STEP_ETA = 1, STEP_Z = 2, STEP_JOINT = 3 };
+
+struct GmmWArgs {
+    const float* x;                   // (B, N, D)   -- read once per instance, not S-replicated (F9)
+    const float* z_f;                 // (R, N, K) assignment of the forward term
+    const float* z_b;                 // (R, N, K) assignment of the backward term (== z_f for ETA)
+    const float* q;                   // (R, N, K) q_probs or null
+    const float *pa, *pb, *pm, *pn;   // posterior (R, K, D) or null
+    const float *ra, *rb, *rm, *rn;   // prior (K, D)
+    const float* rpi;                 // prior pi (K)
+    const float *tau_f, *mu_f, *tau_b, *mu_b;   // (R, K, D)
+    long long R;
+    int B, N, step;
+    float *log_w, *log_q_f, *dens, *log_w_f, *log_w_b;   // (R), each optional
+    float *lw_local, *lq_local;                           // (R, N), optional (Z step)
+};
+
+template <int K, int D, int P, int LANES>
+__global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long bar;
+    constexpr int KD = K * D;
+    const int N = a.N, step = a.step;
+    const bool has_eta = step != STEP_Z, has_z = step != STEP_ETA, has_bwd = step != STEP_ONESHOT;
+    const bool zb_distinct = has_bwd && (a.z_b != a.z_f);
+    const size_t tile_f = (size_t)P * N * K;
+    float* s_zf = reinterpret_cast<float*>(smem);
+    float* s_zb = zb_distinct ? s_zf + tile_f : s_zf;
+    float* s_q = s_zf + tile_f * (zb_distinct ? 2 : 1);
+    float* s_tab = s_q + (has_z ? tile_f : 0);          // [P][2][KD][3]: mu, 1/(2 var), log sigma + c
+    const long long r0 = (long long)blockIdx.x * P;
+    const int rows = (int)min((long long)P, a.R - r0);
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    const unsigned int tb = (unsigned int)(rows * N * K * 4);
+    StageReq req[3] = {{s_zf, a.z_f + r0 * N * K, tb},
+                       {s_zb, a.z_b + r0 * N * K, zb_distinct ? tb : 0u},
+                       {s_q, a.q + r0 * N * K, has_z ? tb : 0u}};
+    stage_issue(req, 3, &bar);
+
+    // ---- while the tile is in flight: the (K,D) terms of this particle
+    const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
+    const bool valid = p < rows;
+    const long long r = r0 + p;
+    float lq_mu_f = 0.f, lq_tau_f = 0.f, lp_mu_f = 0.f, lp_tau_f = 0.f;
+    float lq_mu_b = 0.f, lq_tau_b = 0.f, lp_mu_b = 0.f, lp_tau_b = 0.f;
+    if (valid) {
+        float* tab = s_tab + (size_t)p * (2 * KD * 3);
+        for (int e = j; e < KD; e += LANES) {
+            const float tf = __ldg(a.tau_f + r * KD + e), mf = __ldg(a.mu_f + r * KD + e);
+            float tbk = tf, mbk = mf;
+            if (has_bwd) { tbk = __ldg(a.tau_b + r * KD + e); mbk = __ldg(a.mu_b + r * KD + e); }
+            {   // likelihood tables: sigma = 1/sqrt(tau) (models.py:177)
+                const float sg = inv_sqrt_ref(tf);
+                tab[e * 3 + 0] = mf;
+                tab[e * 3 + 1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sg, sg)));
+                tab[e * 3 + 2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
+                const float sb = inv_sqrt_ref(tbk);
+                tab[(KD + e) * 3 + 0] = mbk;
+                tab[(KD + e) * 3 + 1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sb, sb)));
+                tab[(KD + e) * 3 + 2] = __fadd_rn(logf(sb), LOG_SQRT_2PI_F);
+            }
+            if (has_eta) {
+                const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
+                const float qa = __ldg(a.pa + r * KD + e), qb = __ldg(a.pb + r * KD + e);
+                const float qm = __ldg(a.pm + r * KD + e), qn = __ldg(a.pn + r * KD + e);
+                lq_tau_f += gamma_lp(tf, qa, qb);
+                lq_mu_f += normal_lp(mf, qm, inv_sqrt_ref(__fmul_rn(qn, tf)));
+                lp_tau_f += gamma_lp(tf, a0, b0);
+                lp_mu_f += normal_lp(mf, m0, inv_sqrt_ref(__fmul_rn(n0, tf)));
+                if (has_bwd) {
+                    lq_tau_b += gamma_lp(tbk, qa, qb);
+                    lq_mu_b += normal_lp(mbk, qm, inv_sqrt_ref(__fmul_rn(qn, tbk)));
+                    lp_tau_b += gamma_lp(tbk, a0, b0);
+                    lp_mu_b += normal_lp(mbk, m0, inv_sqrt_ref(__fmul_rn(n0, tbk)));
+                }
+            }
+        }
+    }
+    // log q / log p of eta: means.sum + precisions.sum (objectives.py:167-168)
+    const float lq_eta_f = __fadd_rn(group_sum<LANES>(lq_mu_f), group_sum<LANES>(lq_tau_f));
+    const float lp_eta_f = __fadd_rn(group_sum<LANES>(lp_mu_f), group_sum<LANES>(lp_tau_f));
+    const float lq_eta_b = __fadd_rn(group_sum<LANES>(lq_mu_b), group_sum<LANES>(lq_tau_b));
+    const float lp_eta_b = __fadd_rn(group_sum<LANES>(lp_mu_b), group_sum<LANES>(lp_tau_b));
+
+    // log pi of the (renormalised, clamped) prior (models.py:167-170, quirk Q4)
+    float logpi[K];
+    {
+        float sp = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) sp = __fadd_rn(sp, __ldg(a.rpi + k));
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            logpi[k] = logf(fminf(fmaxf(__fdiv_rn(__ldg(a.rpi + k), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
+    }
+
+    stage_wait(&bar, 0);           // tile + tables visible
+
+    double A_llf = 0, A_llb = 0, A_lpzf = 0, A_lpzb = 0, A_lqzf = 0, A_lqzb = 0, A_loc = 0;
+    if (valid) {
+        const float* zf = s_zf + (size_t)p * N * K;
+        const float* zb = s_zb + (size_t)p * N * K;
+        const float* qq = s_q + (size_t)p * N * K;
+        const float* tab = s_tab + (size_t)p * (2 * KD * 3);
+        const float* xb = a.x + (size_t)(r % a.B) * N * D;
+        for (int n = j; n < N; n += LANES) {
+            // labels = argmax over K (first maximum; models.py:178)
+            int lf = 0, lb = 0;
+            {
+                float best = zf[n * K];
+#pragma unroll
+                for (int k = 1; k < K; ++k) { const float v = zf[n * K + k]; if (v > best) { best = v; lf = k; } }
+            }
+            if (zb_distinct) {
+                float best = zb[n * K];
+#pragma unroll
+                for (int k = 1; k < K; ++k) { const float v = zb[n * K + k]; if (v > best) { best = v; lb = k; } }
+            } else {
+                lb = lf;
+            }
+            float llf = 0.f, llb = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float xv = __ldg(xb + n * D + d);
+                const float* tf = tab + (lf * D + d) * 3;
+                const float df = __fsub_rn(xv, tf[0]);
+                llf = __fadd_rn(llf, __fsub_rn(-__fmul_rn(__fmul_rn(df, df), tf[1]), tf[2]));
+                if (has_bwd) {
+                    const float* tbp = tab + (KD + lb * D + d) * 3;
+                    const float db = __fsub_rn(xv, tbp[0]);
+                    llb = __fadd_rn(llb, __fsub_rn(-__fmul_rn(__fmul_rn(db, db), tbp[1]), tbp[2]));
+                }
+            }
+            A_llf += (double)llf;
+            A_llb += (double)llb;
+            if (has_z) {
+                float sq = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, qq[n * K + k]);
+                const float lqf = logf(fminf(fmaxf(__fdiv_rn(qq[n * K + lf], sq), FLT_EPS_F), 1.f - FLT_EPS_F));
+                float lpf = logpi[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) if (lf == k) lpf = logpi[k];
+                A_lqzf += (double)lqf;
+                A_lpzf += (double)lpf;
+                float lqb = 0.f, lpb = 0.f;
+                if (has_bwd) {
+                    lqb = logf(fminf(fmaxf(__fdiv_rn(qq[n * K + lb], sq), FLT_EPS_F), 1.f - FLT_EPS_F));
+                    lpb = logpi[0];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) if (lb == k) lpb = logpi[k];
+                    A_lqzb += (double)lqb;
+                    A_lpzb += (double)lpb;
+                }
+                if (step == STEP_Z) {
+                    // objectives.py:206,215-216: (ll_f + log_p_f - log_q_f) - (ll_b + log_p_b - log_q_b)
+                    const float wf = __fsub_rn(__fadd_rn(llf, lpf), lqf);
+                    const float wb = __fsub_rn(__fadd_rn(llb, lpb), lqb);
+                    const float loc = __fsub_rn(wf, wb);
+                    A_loc += (double)loc;
+                    if (a.lw_local != nullptr) a.lw_local[r * N + n] = loc;
+                    if (a.lq_local != nullptr) a.lq_local[r * N + n] = lqf;
+                }
+            }
+        }
+    }
+    A_llf = group_sum<LANES>(A_llf);
+    A_llb = group_sum<LANES>(A_llb);
+    A_lpzf = group_sum<LANES>(A_lpzf);
+    A_lpzb = group_sum<LANES>(A_lpzb);
+    A_lqzf = group_sum<LANES>(A_lqzf);
+    A_lqzb = group_sum<LANES>(A_lqzb);
+    A_loc = group_sum<LANES>(A_loc);
+    if (!valid || j != 0) return;
+
+    const float ll_f = (float)A_llf, ll_b = (float)A_llb;
+    const float lpz_f = (float)A_lpzf, lpz_b = (float)A_lpzb, lqz_f = (float)A_lqzf, lqz_b = (float)A_lqzb;
+    float lw, lwf = 0.f, lwb = 0.f, lqf, dens;
+    if (step == STEP_ETA) {                 // objectives.py:172,179-180,194
+        lwf = __fsub_rn(__fadd_rn(ll_f, lp_eta_f), lq_eta_f);
+        lwb = __fsub_rn(__fadd_rn(ll_b, lp_eta_b), lq_eta_b);
+        lw = __fsub_rn(lwf, lwb);
+        lqf = lq_eta_f;
+        dens = lp_eta_f;
+    } else if (step == STEP_Z) {            // objectives.py:216-218,226
+        lw = (float)A_loc;
+        lwf = __fsub_rn(__fadd_rn(ll_f, lpz_f), lqz_f);
+        lwb = __fsub_rn(__fadd_rn(ll_b, lpz_b), lqz_b);
+        lqf = lqz_f;
+        dens = __fadd_rn(ll_f, lpz_f);
+    } else if (step == STEP_ONESHOT) {      // objectives.py:89-92,108
+        const float lp = __fadd_rn(__fadd_rn(ll_f, lp_eta_f), lpz_f);
+        lqf = __fadd_rn(lq_eta_f, lqz_f);
+        lw = __fsub_rn(lp, lqf);
+        lwf = lw;
+        dens = lp;
+    } else {                                // joint: objectives.py:128,139-140,156
+        lwf = __fadd_rn(__fsub_rn(__fsub_rn(__fadd_rn(ll_f, lp_eta_f), lq_eta_f), lqz_f), lpz_f);
+        lwb = __fsub_rn(__fadd_rn(__fsub_rn(__fadd_rn(ll_b, lp_eta_b), lq_eta_b), lpz_b), lqz_b);
+        lw = __fsub_rn(lwf, lwb);
+        lqf = __fadd_rn(lq_eta_f, lqz_f);
+        dens = __fadd_rn(__fadd_rn(ll_f, lp_eta_f), lpz_f);
+    }
+    if (a.log_w != nullptr) a.log_w[r] = lw;
+    if (a.log_q_f != nullptr) a.log_q_f[r] = lqf;
+    if (a.dens != nullptr) a.dens[r] = dens;
+    if (a.log_w_f != nullptr) a.log_w_f[r] = lwf;
+    if (a.log_w_b != nullptr) a.log_w_b[r] = lwb;
+}
+
+// ----------------------------------------------------------------------------------- launchers
+constexpr int kP = 32, kLanes = 8;
+
+template <int K, int D>
+static int launch_nss(const NssArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)kP * a.N * (K + D) * 4;
+    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_nss_posterior: N=%d too large for one tile", a.N);
+    auto kern = k_gmm_nss_posterior<K, D, kP, kLanes>;
+    if (smem > 48 * 1024)
+        APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    const long long grid = (a.R + kP - 1) / kP;
+    kern<<<(unsigned int)grid, kP * kLanes, smem, st>>>(a);
+    APGS_LAUNCH_OK("k_gmm_nss_posterior launch");
+    return 0;
+}
+
+template <int K, int D>
+static int launch_weights(const GmmWArgs& a, cudaStream_t st) {
+    const bool has_z = a.step != STEP_ETA, has_bwd = a.step != STEP_ONESHOT;
+    const int ntile = 1 + ((has_bwd && a.z_b != a.z_f) ? 1 : 0) + (has_z ? 1 : 0);
+    const size_t smem = (size_t)kP * a.N * K * 4 * ntile + (size_t)kP * 2 * K * D * 3 * 4;
+    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_logw: N=%d too large for one tile", a.N);
+    auto kern = k_gmm_weights<K, D, kP, kLanes>;
+    if (smem > 48 * 1024)
+        APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    const long long grid = (a.R + kP - 1) / kP;
+    kern<<<(unsigned int)grid, kP * kLanes, smem, st>>>(a);
+    APGS_LAUNCH_OK("k_gmm_weights launch");
+    return 0;
+}
+
+#define APGS_KD_DISPATCH(K_, D_, FN)                                              \
+    do {                                                                          \
+        if (K_ == 3 && D_ == 2) return FN<3, 2>(a, st);                           \
+        if (K_ == 2 && D_ == 2) return FN<2, 2>(a, st);                           \
+        if (K_ == 4 && D_ == 2) return FN<4, 2>(a, st);                           \
+        if (K_ == 5 && D_ == 2) return FN<5, 2>(a, st);                           \
+        if (K_ == 3 && D_ == 3) return FN<3, 3>(a, st);                           \
+        if (K_ == 4 && D_ == 3) return FN<4, 3>(a, st);                           \
+        if (K_ == 3 && D_ == 1) return FN<3, 1>(a, st);                           \
+    } while (0)
+
+}  // namespace apgs
+
+using namespace apgs;
+
+static int check_gmm_dims(int64_t S, int64_t B, int64_t N, int64_t K, int64_t D, const char* who) {
+    if (S <= 0 || B <= 0 || N <= 0) return fail(APGS_E_SHAPE, "%s: S=%lld B=%lld N=%lld must be positive", who,
+                                                (long long)S, (long long)B, (long long)N);
+    if (S * B >= (1ll << 40) || N >= (1 << 20)) return fail(APGS_E_SHAPE, "%s: problem too large", who);
+    (void)K; (void)D;
+    return 0;
+}
+
+extern "C" int apgs_gmm_nss_posterior_f32(const float* xp, const float* gamma, int64_t S, int64_t B, int64_t N,
+                                          int64_t K, int64_t D, const float* prior_alpha, const float* prior_beta,
+                                          const float* prior_mu, const float* prior_nu, float* post_alpha,
+                                          float* post_beta, float* post_mu, float* post_nu, void* stream) {
+    if (int e = check_gmm_dims(S, B, N, K, D, "gmm_nss_posterior")) return e;
+    if (!xp || !gamma || !prior_alpha || !prior_beta || !prior_mu || !prior_nu || !post_alpha || !post_beta ||
+        !post_mu || !post_nu)
+        return fail(APGS_E_BADARG, "gmm_nss_posterior: NULL pointer");
+    NssArgs a = {xp, gamma, prior_alpha, prior_beta, prior_mu, prior_nu, post_alpha, post_beta, post_mu, post_nu,
+                 (long long)S * B, (int)N};
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_nss);
+    return fail(APGS_E_UNSUPPORTED, "gmm_nss_posterior: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
+}
+
+static int gmm_logw(int step, const float* x, const float* z_f, const float* z_b, const float* q,
+                    const apgs_gmm_post_t* postp, const apgs_gmm_prior_t* priorp, const float* tau_f,
+                    const float* mu_f, const float* tau_b, const float* mu_b, int64_t S, int64_t B, int64_t N,
+                    int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream) {
+    if (!priorp || !out) return fail(APGS_E_BADARG, "gmm_logw: NULL prior/out struct");
+    const float* prior[4] = {priorp->alpha, priorp->beta, priorp->mu, priorp->nu};
+    const float* prior_pi = priorp->pi;
+    const float* postv[4] = {postp ? postp->alpha : nullptr, postp ? postp->beta : nullptr,
+                             postp ? postp->mu : nullptr, postp ? postp->nu : nullptr};
+    const float* const* post = postp ? postv : nullptr;
+    float *log_w = out->log_w, *log_q_f = out->log_q_f, *dens = out->density, *log_w_f = out->log_w_f,
+          *log_w_b = out->log_w_b, *lw_local = out->log_w_local, *lq_local = out->log_q_local;
+    if (int e = check_gmm_dims(S, B, N, K, D, "gmm_logw")) return e;
+    const bool has_eta = step != STEP_Z, has_z = step != STEP_ETA, has_bwd = step != STEP_ONESHOT;
+    if (!x || !z_f || !tau_f || !mu_f || !prior || !prior_pi) return fail(APGS_E_BADARG, "gmm_logw: NULL input");
+    for (int i = 0; i < 4; ++i)
+        if (!prior[i]) return fail(APGS_E_BADARG, "gmm_logw: NULL prior");
+    if (has_eta) {
+        if (!post) return fail(APGS_E_BADARG, "gmm_logw: posterior parameters required");
+        for (int i = 0; i < 4; ++i)
+            if (!post[i]) return fail(APGS_E_BADARG, "gmm_logw: NULL posterior parameter");
+    }
+    if (has_z && !q) return fail(APGS_E_BADARG, "gmm_logw: q_probs required");
+    if (has_bwd && (!z_b || !tau_b || !mu_b)) return fail(APGS_E_BADARG, "gmm_logw: backward inputs required");
+    GmmWArgs a = {};
+    a.x = x; a.z_f = z_f; a.z_b = has_bwd ? z_b : z_f; a.q = has_z ? q : z_f;
+    if (has_eta) { a.pa = post[0]; a.pb = post[1]; a.pm = post[2]; a.pn = post[3]; }
+    a.ra = prior[0]; a.rb = prior[1]; a.rm = prior[2]; a.rn = prior[3]; a.rpi = prior_pi;
+    a.tau_f = tau_f; a.mu_f = mu_f; a.tau_b = has_bwd ? tau_b : tau_f; a.mu_b = has_bwd ? mu_b : mu_f;
+    a.R = (long long)S * B; a.B = (int)B; a.N = (int)N; a.step = step;
+    a.log_w = log_w; a.log_q_f = log_q_f; a.dens = dens; a.log_w_f = log_w_f; a.log_w_b = log_w_b;
+    a.lw_local = lw_local; a.lq_local = lq_local;
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_weights);
+    return fail(APGS_E_UNSUPPORTED, "gmm_logw: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
+}
+
+extern "C" int apgs_gmm_logw_oneshot_f32(const float* x, const apgs_gmm_post_t* post, const apgs_gmm_prior_t* prior,
+                                         const float* tau, const float* mu, const float* q_probs, const float* z,
+                                         int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                         const apgs_gmm_out_t* out, void* stream) {
+    return gmm_logw(STEP_ONESHOT, x, z, nullptr, q_probs, post, prior, tau, mu, nullptr, nullptr, S, B, N, K, D, out,
+                    stream);
+}
+
+extern "C" int apgs_gmm_logw_eta_f32(const float* x, const float* z, const apgs_gmm_post_t* post,
+                                     const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
+                                     const float* tau_old, const float* mu_old, int64_t S, int64_t B, int64_t N,
+                                     int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream) {
+    return gmm_logw(STEP_ETA, x, z, z, nullptr, post, prior, tau, mu, tau_old, mu_old, S, B, N, K, D, out, stream);
+}
+
+extern "C" int apgs_gmm_logw_z_f32(const float* x, const float* tau, const float* mu, const float* q_probs,
+                                   const apgs_gmm_prior_t* prior, const float* z, const float* z_old, int64_t S,
+                                   int64_t B, int64_t N, int64_t K, int64_t D, const apgs_gmm_out_t* out,
+                                   void* stream) {
+    return gmm_logw(STEP_Z, x, z, z_old, q_probs, nullptr, prior, tau, mu, tau, mu, S, B, N, K, D, out, stream);
+}
+
+extern "C" int apgs_gmm_logw_joint_f32(const float* x, const apgs_gmm_post_t* post, const apgs_gmm_prior_t* prior,
+                                       const float* tau, const float* mu, const float* tau_old, const float* mu_old,
+                                       const float* q_probs, const float* z, const float* z_old, int64_t S,
+                                       int64_t B, int64_t N, int64_t K, int64_t D, const apgs_gmm_out_t* out,
+                                       void* stream) {
+    return gmm_logw(STEP_JOINT, x, z, z_old, q_probs, post, prior, tau, mu, tau_old, mu_old, S, B, N, K, D, out,
+                    stream);
+}

@@ -32,6 +32,7 @@ struct AncArgs {
     int strategy;              // APGS_SYSTEMATIC / APGS_MULTINOMIAL / -1 (stats only)
     int blocked;               // CDF mode
     int tile_in_smem;
+    int dbl;                   // exact systematic CDF kept in a shared fp64 tile (no conversions on the chain)
     float* ws;                 // global tile (S,B) when !tile_in_smem
     long long* anc64;
     int* anc32;
@@ -56,7 +57,85 @@ __device__ __forceinline__ T col_reduce(T v, Op op, T* scratch, int col) {
     return r;
 }
 
+// Tile accessors: shared memory (compile-time stride TB, LDS/STS with immediate offsets) or the
+// global workspace (stride B).
+template <int TB, bool SMEM>
+struct Tile {
+    float* p;
+    long long gs;
+    __device__ __forceinline__ float ld(int i) const { return SMEM ? p[i * TB] : p[(long long)i * gs]; }
+    __device__ __forceinline__ void st(int i, float v) const {
+        if (SMEM) p[i * TB] = v; else p[(long long)i * gs] = v;
+    }
+};
+
+// One sequential chain per column (bit-exact with ATen's CPU loops).  Only the adds are dependent:
+// values are fetched / converted / stored in register batches of CH so the chain costs one DADD
+// (or FADD) latency per particle instead of a shared-memory round trip.
+template <int TB, bool SMEM, typename ACC>
+__device__ __forceinline__ void cdf_chain(const Tile<TB, SMEM>& t, int S) {
+    constexpr int CH = 16;
+    ACC acc = (ACC)0;
+    const int Sfull = S - (S % CH);
+    float v[CH];
+    if (Sfull > 0) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = t.ld(k);
+    }
+    for (int i0 = 0; i0 < Sfull; i0 += CH) {
+        float nx[CH];
+        if (i0 + CH < Sfull) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) nx[k] = t.ld(i0 + CH + k);
+        }
+        float c[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            if (sizeof(ACC) == 8) acc = (ACC)((double)acc + (double)v[k]);
+            else acc = (ACC)__fadd_rn((float)acc, v[k]);
+            c[k] = (float)acc;
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) t.st(i0 + k, c[k]);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = nx[k];
+    }
+    for (int i = Sfull; i < S; ++i) {
+        if (sizeof(ACC) == 8) acc = (ACC)((double)acc + (double)t.ld(i));
+        else acc = (ACC)__fadd_rn((float)acc, t.ld(i));
+        t.st(i, (float)acc);
+    }
+}
+
+// Exact systematic chain on an fp64 shared tile: the serial path is LDS.64 -> DADD -> STS.64 only
+// (fp32<->fp64 conversions are quarter-rate and were 2/3 of the chain when done inline).
 template <int TB>
+__device__ __forceinline__ void cdf_chain_f64(double* t, int S) {
+    constexpr int CH = 8;
+    double acc = 0.0;
+    const int Sfull = S - (S % CH);
+    double v[CH];
+    if (Sfull > 0) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = t[k * TB];
+    }
+    for (int i0 = 0; i0 < Sfull; i0 += CH) {
+        double nx[CH];
+        if (i0 + CH < Sfull) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) nx[k] = t[(i0 + CH + k) * TB];
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) { acc += v[k]; v[k] = acc; }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) t[(i0 + k) * TB] = v[k];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v[k] = nx[k];
+    }
+    for (int i = Sfull; i < S; ++i) { acc += t[i * TB]; t[i * TB] = acc; }
+}
+
+template <int TB, bool SMEM>
 __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* dscr = reinterpret_cast<double*>(smem_raw);                 // blockDim.x doubles
@@ -67,22 +146,26 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
     const long long b0 = (long long)blockIdx.x * TB;
     const long long b = b0 + col;
     const bool colok = b < a.B;
-    const long long S = a.S, B = a.B;
+    const int S = (int)a.S;
+    const long long B = a.B;
 
-    float* tile;
-    long long ts;
-    if (a.tile_in_smem) { tile = stile + col; ts = TB; }
-    else                { tile = a.ws + b; ts = B; }
+    // fp64 CDF tile (only when a.dbl): S*TB doubles after the fp32 tile, 8-byte aligned
+    double* dt = reinterpret_cast<double*>(stile + (((size_t)S * TB + 1) & ~(size_t)1)) + col;
+    const bool dbl = SMEM && a.dbl;
+
+    Tile<TB, SMEM> tile;
+    if (SMEM) { tile.p = stile + col; tile.gs = TB; }
+    else      { tile.p = a.ws + b; tile.gs = B; }
     // in global mode out-of-range columns never touch memory
-    const bool touch = a.tile_in_smem || colok;
+    const bool touch = SMEM || colok;
 
     float cmax = 0.f, csum = 1.f;
     if (a.w_norm == nullptr) {
         // ---- phase 1
         float m = -INFINITY;
-        for (long long i = rg; i < S; i += R) {
-            float x = colok ? __ldg(a.log_w + i * B + b) : 0.f;
-            if (touch) tile[i * ts] = x;
+        for (int i = rg; i < S; i += R) {
+            float x = colok ? __ldg(a.log_w + (long long)i * B + b) : 0.f;
+            if (touch) tile.st(i, x);
             m = fmaxf(m, x);
         }
         cmax = col_reduce<TB>(m, [](float p, float q) { return fmaxf(p, q); },
@@ -90,9 +173,9 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
         // ---- phase 2
         float ps = 0.f;
         if (touch)
-            for (long long i = rg; i < S; i += R) {
-                float e = expf(tile[i * ts] - cmax);
-                tile[i * ts] = e;
+            for (int i = rg; i < S; i += R) {
+                float e = expf(tile.ld(i) - cmax);
+                tile.st(i, e);
                 ps += e;
             }
         double dsum = col_reduce<TB>((double)ps, [](double p, double q) { return p + q; }, dscr, col);
@@ -100,10 +183,10 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
         // ---- phase 3
         float pq = 0.f;
         if (touch)
-            for (long long i = rg; i < S; i += R) {
-                float w = __fdiv_rn(tile[i * ts], csum);
-                tile[i * ts] = w;
-                if (a.w_out != nullptr && colok) a.w_out[i * B + b] = w;
+            for (int i = rg; i < S; i += R) {
+                float w = __fdiv_rn(tile.ld(i), csum);
+                if (dbl) dt[i * TB] = (double)w; else tile.st(i, w);
+                if (a.w_out != nullptr && colok) a.w_out[(long long)i * B + b] = w;
                 pq = fmaf(w, w, pq);
             }
         if (a.ess != nullptr || a.lse != nullptr) {
@@ -118,15 +201,15 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
             // (torch/distributions/categorical.py:70, reached from apgs/resampler.py:41)
             float pw = 0.f;
             if (touch)
-                for (long long i = rg; i < S; i += R) pw += tile[i * ts];
+                for (int i = rg; i < S; i += R) pw += tile.ld(i);
             const float sw = (float)col_reduce<TB>((double)pw, [](double p, double q) { return p + q; }, dscr, col);
             if (touch)
-                for (long long i = rg; i < S; i += R) tile[i * ts] = __fdiv_rn(tile[i * ts], sw);
+                for (int i = rg; i < S; i += R) tile.st(i, __fdiv_rn(tile.ld(i), sw));
         }
     } else {
-        for (long long i = rg; i < S; i += R) {
-            float w = colok ? __ldg(a.w_norm + i * B + b) : 0.f;
-            if (touch) tile[i * ts] = w;
+        for (int i = rg; i < S; i += R) {
+            float w = colok ? __ldg(a.w_norm + (long long)i * B + b) : 0.f;
+            if (dbl) dt[i * TB] = (double)w; else if (touch) tile.st(i, w);
         }
     }
     if (a.strategy < 0) return;
@@ -135,26 +218,16 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
     // ---- phase 4: CDF
     if (!a.blocked) {
         if (rg == 0 && touch) {
-            if (a.strategy == APGS_SYSTEMATIC) {
-                double acc = 0.0;                          // == ATen CPU cumsum<float> (double acc)
-                for (long long i = 0; i < S; ++i) {
-                    acc += (double)tile[i * ts];
-                    tile[i * ts] = (float)acc;
-                }
-            } else {
-                float acc = 0.f;                           // == ATen CPU multinomial running sum
-                for (long long i = 0; i < S; ++i) {
-                    acc = __fadd_rn(acc, tile[i * ts]);
-                    tile[i * ts] = acc;
-                }
-            }
+            if (dbl)                                cdf_chain_f64<TB>(dt, S);               // ATen CPU cumsum<float>
+            else if (a.strategy == APGS_SYSTEMATIC) cdf_chain<TB, SMEM, double>(tile, S);
+            else                               cdf_chain<TB, SMEM, float>(tile, S);    // ATen CPU multinomial
         }
     } else {
-        const long long L = (S + R - 1) / R;
-        const long long i0 = (long long)rg * L, i1 = (i0 + L < S) ? (i0 + L) : S;
+        const int L = (S + R - 1) / R;
+        const int i0 = min(rg * L, S), i1 = min(i0 + L, S);
         double loc = 0.0;
         if (touch)
-            for (long long i = i0; i < i1; ++i) loc += (double)tile[i * ts];
+            for (int i = i0; i < i1; ++i) loc += (double)tile.ld(i);
         dscr[rg * TB + col] = loc;
         __syncthreads();
         if (rg == 0) {
@@ -168,54 +241,61 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
         __syncthreads();
         double acc = dscr[rg * TB + col];
         if (touch)
-            for (long long i = i0; i < i1; ++i) {
-                acc += (double)tile[i * ts];
-                tile[i * ts] = (float)acc;
+            for (int i = i0; i < i1; ++i) {
+                acc += (double)tile.ld(i);
+                tile.st(i, (float)acc);
             }
     }
     __syncthreads();
 
     // ---- phase 5: normalise by the last CDF entry (the row max of a monotone CDF; resampler.py:32-33)
-    const float norm = touch ? tile[(S - 1) * ts] : 1.f;
-    __syncthreads();
-    if (touch)
-        for (long long i = rg; i < S; i += R) tile[i * ts] = __fdiv_rn(tile[i * ts], norm);
+    if (dbl) {
+        const float norm = (float)dt[(S - 1) * TB];
+        for (int i = rg; i < S; i += R) tile.st(i, __fdiv_rn((float)dt[i * TB], norm));
+    } else {
+        const float norm = touch ? tile.ld(S - 1) : 1.f;
+        __syncthreads();
+        if (touch)
+            for (int i = rg; i < S; i += R) tile.st(i, __fdiv_rn(tile.ld(i), norm));
+    }
     __syncthreads();
 
     // ---- phase 6: ancestors
     if (!colok) return;
     const float fS = (float)S;
     const float u = (a.strategy == APGS_SYSTEMATIC) ? __ldg(a.u_sys + b) : 0.f;
-    for (long long i = rg; i < S; i += R) {
-        long long lo = 0, hi = S;
+    for (int i = rg; i < S; i += R) {
+        int lo = 0, hi = S;
         if (a.strategy == APGS_SYSTEMATIC) {
             const float pos = __fdiv_rn(__fadd_rn(u, (float)i), fS);          // resampler.py:28
             while (lo < hi) {
-                long long mid = (lo + hi) >> 1;
-                if (tile[mid * ts] < pos) lo = mid + 1; else hi = mid;
+                int mid = (lo + hi) >> 1;
+                if (tile.ld(mid) < pos) lo = mid + 1; else hi = mid;
             }
         } else {
-            const double ud = __ldg(a.u_mult + i * a.us + b * a.ub);
+            const double ud = __ldg(a.u_mult + (long long)i * a.us + b * a.ub);
             while (lo < hi) {
-                long long mid = (lo + hi) >> 1;
-                if ((double)tile[mid * ts] < ud) lo = mid + 1; else hi = mid;
+                int mid = (lo + hi) >> 1;
+                if ((double)tile.ld(mid) < ud) lo = mid + 1; else hi = mid;
             }
         }
         if (lo > S - 1) lo = S - 1;                        // memory safety on NaN / degenerate weights
-        if (a.anc32 != nullptr) a.anc32[i * B + b] = (int)lo;
-        if (a.anc64 != nullptr) a.anc64[i * B + b] = lo;
+        if (a.anc32 != nullptr) a.anc32[(long long)i * B + b] = lo;
+        if (a.anc64 != nullptr) a.anc64[(long long)i * B + b] = lo;
     }
 }
 
 static const size_t kSmemTileBudget = 200 * 1024;
 
-struct AncPlan { int TB; int nthr; int tile_in_smem; size_t smem; int grid; };
+struct AncPlan { int TB; int nthr; int tile_in_smem; int dbl; size_t smem; int grid; };
 
-static AncPlan plan_ancestors(long long S, long long B) {
+static AncPlan plan_ancestors(long long S, long long B, bool want_dbl) {
     AncPlan p;
     int TB = 32;
-    while (TB > 1 && (size_t)S * TB * 4 > kSmemTileBudget) TB >>= 1;
-    p.tile_in_smem = ((size_t)S * TB * 4 <= kSmemTileBudget) ? 1 : 0;
+    const size_t per = want_dbl ? 12 : 4;       // bytes of shared memory per (particle, column)
+    while (TB > 1 && ((size_t)S * TB + 2) * per > kSmemTileBudget) TB >>= 1;
+    p.tile_in_smem = (((size_t)S * TB + 2) * per <= kSmemTileBudget) ? 1 : 0;
+    p.dbl = (want_dbl && p.tile_in_smem) ? 1 : 0;
     if (p.tile_in_smem) {
         // spread over the 148 SMs: shrink the column tile while the grid is under ~2 CTAs/SM
         while (TB > 4 && (B + TB - 1) / TB < 2 * sm_count()) TB >>= 1;
@@ -229,24 +309,29 @@ static AncPlan plan_ancestors(long long S, long long B) {
     if (!p.tile_in_smem) nthr = 1024;
     p.TB = TB;
     p.nthr = nthr;
-    p.smem = (size_t)nthr * sizeof(double) + (p.tile_in_smem ? (size_t)S * TB * 4 : 0);
+    p.smem = (size_t)nthr * sizeof(double) + (p.tile_in_smem ? ((size_t)S * TB + 2) * (p.dbl ? 12 : 4) : 0);
     p.grid = (int)((B + TB - 1) / TB);
     return p;
 }
 
 template <int TB>
 static int launch_anc_tb(const AncArgs& a, const AncPlan& p, cudaStream_t st) {
-    if (p.smem > 48 * 1024)
-        APGS_CUDA_OK(cudaFuncSetAttribute(k_ancestors<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)p.smem), "cudaFuncSetAttribute(k_ancestors)");
-    k_ancestors<TB><<<p.grid, p.nthr, p.smem, st>>>(a);
+    if (p.tile_in_smem) {
+        if (p.smem > 48 * 1024)
+            APGS_CUDA_OK(cudaFuncSetAttribute(k_ancestors<TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)p.smem), "cudaFuncSetAttribute(k_ancestors)");
+        k_ancestors<TB, true><<<p.grid, p.nthr, p.smem, st>>>(a);
+    } else {
+        k_ancestors<TB, false><<<p.grid, p.nthr, p.smem, st>>>(a);
+    }
     APGS_LAUNCH_OK("k_ancestors launch");
     return 0;
 }
 
 static int launch_ancestors(AncArgs a, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    AncPlan p = plan_ancestors(a.S, a.B);
+    AncPlan p = plan_ancestors(a.S, a.B, a.strategy == APGS_SYSTEMATIC && !a.blocked);
     a.tile_in_smem = p.tile_in_smem;
+    a.dbl = p.dbl;
     if (!p.tile_in_smem) {
         size_t need = (size_t)a.S * a.B * sizeof(float);
         if (workspace == nullptr || workspace_bytes < need)
@@ -442,7 +527,7 @@ static int check_sb(long long S, long long B, const char* who) {
 
 extern "C" size_t apgs_ancestors_workspace_bytes(int64_t S, int64_t B) {
     if (S <= 0 || B <= 0) return 0;
-    if ((size_t)S * 4 <= kSmemTileBudget) return 0;
+    if (((size_t)S + 2) * 12 <= kSmemTileBudget) return 0;      // CDF tile fits in shared memory
     return (size_t)S * (size_t)B * sizeof(float);
 }
 

@@ -1,0 +1,132 @@
+"""Host wrappers of the GMM reweighting kernels (apgs_b200/csrc/gmm.cu) -- SURVEY.md G1-G4."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import GmmOut, GmmPost, GmmPrior, check, ptr
+from ..ops import _call, _req, _stream
+
+
+def _prior_struct(prior):
+    """prior: object with prior_alpha/beta/mu/nu (K,D) and prior_pi (K) CUDA tensors (Generative)."""
+    t = [_req(getattr(prior, "prior_" + n), "prior_" + n) for n in ("alpha", "beta", "mu", "nu", "pi")]
+    s = GmmPrior(*[v.data_ptr() for v in t])
+    return s, t
+
+
+def _post_struct(post):
+    t = [_req(v, "posterior parameter") for v in post]
+    return GmmPost(*[v.data_ptr() for v in t]), t
+
+
+def _x3(x):
+    """the kernels read ONE copy of the data per instance: accept (B,N,D) or the reference's
+    S-replicated (S,B,N,D) (apgs/gmm/apg_training.py:19) and use its first slice."""
+    if x.dim() == 4:
+        x = x[0]
+    return _req(x, "x", ndim=3)
+
+
+def nss_posterior(xp, gamma, prior):
+    """G1: data_to_stats + posterior_eta (apgs/gmm/kls_gmm.py:92-119) -> alpha, beta, mu, nu (S,B,K,D)."""
+    lib = _lib.load()
+    xp, gamma = _req(xp, "xp", ndim=4), _req(gamma, "gamma", ndim=4)
+    S, B, N, D = xp.shape
+    K = gamma.shape[-1]
+    if tuple(gamma.shape[:3]) != (S, B, N):
+        raise ValueError("xp %s and gamma %s disagree" % (tuple(xp.shape), tuple(gamma.shape)))
+    pr = [_req(getattr(prior, "prior_" + n), "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
+    outs = [torch.empty(S, B, K, D, dtype=torch.float32, device=xp.device) for _ in range(4)]
+    with torch.cuda.device(xp.device), _call("gmm_nss_posterior", 1, 4 * S * B * (N * (K + D) + 4 * K * D)):
+        check(lib.apgs_gmm_nss_posterior_f32(ptr(xp), ptr(gamma), S, B, N, K, D, *[ptr(v) for v in pr],
+                                             *[ptr(v) for v in outs], _stream()), "apgs_gmm_nss_posterior_f32")
+    return tuple(outs)
+
+
+class Weights(object):
+    """outputs of one reweighting step (all (S,B) unless noted; None when not requested)."""
+    __slots__ = ("log_w", "log_q_f", "density", "log_w_f", "log_w_b", "log_w_local", "log_q_local")
+
+
+def _outs(S, B, N, dev, parts, local):
+    w = Weights()
+    o = GmmOut()
+    keep = []
+    for name in Weights.__slots__:
+        t = None
+        if name in ("log_w", "log_q_f", "density") or (parts and name in ("log_w_f", "log_w_b")):
+            t = torch.empty(S, B, dtype=torch.float32, device=dev)
+        elif local and name in ("log_w_local", "log_q_local"):
+            t = torch.empty(S, B, N, dtype=torch.float32, device=dev)
+        setattr(w, name, t)
+        setattr(o, name, None if t is None else t.data_ptr())
+        keep.append(t)
+    return w, o
+
+
+def logw_oneshot(x, post, prior, tau, mu, q_probs, z, parts=False):
+    """G4a: oneshot weights (apgs/gmm/objectives.py:74-110)."""
+    lib = _lib.load()
+    x = _x3(x)
+    z, q_probs, tau, mu = _req(z, "z", ndim=4), _req(q_probs, "q_probs", ndim=4), _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    ps, pk = _post_struct(post)
+    rs, rk = _prior_struct(prior)
+    w, o = _outs(S, B, N, z.device, parts, False)
+    with torch.cuda.device(z.device), _call("gmm_logw_oneshot", 1, 4 * S * B * (2 * N * K + 6 * K * D + 3)):
+        check(lib.apgs_gmm_logw_oneshot_f32(ptr(x), C.byref(ps), C.byref(rs), ptr(tau), ptr(mu), ptr(q_probs), ptr(z),
+                                            S, B, N, K, D, C.byref(o), _stream()), "apgs_gmm_logw_oneshot_f32")
+    return w
+
+
+def logw_eta(x, z, post, prior, tau, mu, tau_old, mu_old, parts=False):
+    """G2: eta-step weights (apgs/gmm/objectives.py:161-195)."""
+    lib = _lib.load()
+    x = _x3(x)
+    z = _req(z, "z", ndim=4)
+    tau, mu, tau_old, mu_old = [_req(v, "tau/mu", ndim=4) for v in (tau, mu, tau_old, mu_old)]
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    ps, pk = _post_struct(post)
+    rs, rk = _prior_struct(prior)
+    w, o = _outs(S, B, N, z.device, parts, False)
+    with torch.cuda.device(z.device), _call("gmm_logw_eta", 1, 4 * S * B * (N * K + 8 * K * D + 3)):
+        check(lib.apgs_gmm_logw_eta_f32(ptr(x), ptr(z), C.byref(ps), C.byref(rs), ptr(tau), ptr(mu), ptr(tau_old),
+                                        ptr(mu_old), S, B, N, K, D, C.byref(o), _stream()), "apgs_gmm_logw_eta_f32")
+    return w
+
+
+def logw_z(x, tau, mu, q_probs, prior, z, z_old, parts=False, local=False):
+    """G3 (+W2): z-step weights (apgs/gmm/objectives.py:197-227)."""
+    lib = _lib.load()
+    x = _x3(x)
+    z, z_old, q_probs = _req(z, "z", ndim=4), _req(z_old, "z_old", ndim=4), _req(q_probs, "q_probs", ndim=4)
+    tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    rs, rk = _prior_struct(prior)
+    w, o = _outs(S, B, N, z.device, parts, local)
+    with torch.cuda.device(z.device), _call("gmm_logw_z", 1, 4 * S * B * (3 * N * K + 2 * K * D + 3 + (2 * N if local else 0))):
+        check(lib.apgs_gmm_logw_z_f32(ptr(x), ptr(tau), ptr(mu), ptr(q_probs), C.byref(rs), ptr(z), ptr(z_old),
+                                      S, B, N, K, D, C.byref(o), _stream()), "apgs_gmm_logw_z_f32")
+    return w
+
+
+def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, parts=False):
+    """G4b: joint-step weights (apgs/gmm/objectives.py:112-158)."""
+    lib = _lib.load()
+    x = _x3(x)
+    z, z_old, q_probs = _req(z, "z", ndim=4), _req(z_old, "z_old", ndim=4), _req(q_probs, "q_probs", ndim=4)
+    tau, mu, tau_old, mu_old = [_req(v, "tau/mu", ndim=4) for v in (tau, mu, tau_old, mu_old)]
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    ps, pk = _post_struct(post)
+    rs, rk = _prior_struct(prior)
+    w, o = _outs(S, B, N, z.device, parts, False)
+    with torch.cuda.device(z.device), _call("gmm_logw_joint", 1, 4 * S * B * (3 * N * K + 8 * K * D + 3)):
+        check(lib.apgs_gmm_logw_joint_f32(ptr(x), C.byref(ps), C.byref(rs), ptr(tau), ptr(mu), ptr(tau_old),
+                                          ptr(mu_old), ptr(q_probs), ptr(z), ptr(z_old), S, B, N, K, D,
+                                          C.byref(o), _stream()), "apgs_gmm_logw_joint_f32")
+    return w

@@ -1,0 +1,194 @@
+"""GMM proposals and generative model: same classes, constructor arguments, parameter names
+(state_dict keys) and forward() contract as apgs/gmm/models.py, with the arithmetic after the
+Linear layers done by the sm_100a kernels.
+
+    Enc_rws_eta   apgs/gmm/models.py:10-48      Enc_apg_eta  :50-88
+    Enc_apg_z     apgs/gmm/models.py:91-115     Generative   :117-185
+
+The nn.Linear layers and the random draws stay in PyTorch (north_star).  Each encoder has a
+`params(...)` method returning the proposal parameters (what the fused log-weight kernels eat)
+and the reference's `forward(...)` returning a Trace of nodes {value, dist, log_prob}.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.distributions.gamma import Gamma
+from torch.distributions.normal import Normal
+from torch.distributions.one_hot_categorical import OneHotCategorical as cat
+
+from ..trace import Trace
+from . import kernels
+
+
+def _x_inst(ob):
+    """(S,B,N,D) S-replicated data (apgs/gmm/apg_training.py:19) or (B,N,D) -> (B,N,D)."""
+    return ob[0] if ob.dim() == 4 else ob
+
+
+class _PriorNG(object):
+    def __init__(self, prior_ng):
+        self.prior_alpha, self.prior_beta, self.prior_mu, self.prior_nu = prior_ng
+
+
+def _eta_trace(post, sampled, tau_old, mu_old):
+    q_alpha, q_beta, q_mu, q_nu = post
+    q = Trace()
+    if sampled:
+        tau = Gamma(q_alpha, q_beta).sample()
+        q.gamma(q_alpha, q_beta, value=tau, name='precisions')
+        mu = Normal(q_mu, 1. / (q_nu * tau).sqrt()).sample()
+        q.normal(q_mu, 1. / (q_nu * tau).sqrt(), value=mu, name='means')
+    else:
+        q.gamma(q_alpha, q_beta, value=tau_old, name='precisions')
+        q.normal(q_mu, 1. / (q_nu * tau_old).sqrt(), value=mu_old, name='means')
+    q.post = post            # (alpha, beta, mu, nu): inputs of the fused log-weight kernels
+    return q
+
+
+class Enc_rws_eta(nn.Module):
+    """One-shot (i.e. RWS) encoder of {mean, precision}, apgs/gmm/models.py:10-48."""
+
+    def __init__(self, K, D):
+        super(self.__class__, self).__init__()
+        self.gamma = nn.Sequential(nn.Linear(D, K), nn.Softmax(-1))
+        self.ob = nn.Sequential(nn.Linear(D, D))
+
+    def params(self, ob, prior_ng, S=None):
+        x = _x_inst(ob)
+        S = ob.shape[0] if ob.dim() == 4 else S
+        # the heads depend on the data only: evaluate once per instance, not once per particle
+        xp, gam = self.ob(x), self.gamma(x)                               # (B,N,D), (B,N,K)
+        post = kernels.nss_posterior(xp.unsqueeze(0), gam.unsqueeze(0), _PriorNG(prior_ng))   # (1,B,K,D)
+        return tuple(v.expand(S, -1, -1, -1).contiguous() for v in post)
+
+    def forward(self, ob, prior_ng, sampled=True, tau_old=None, mu_old=None):
+        return _eta_trace(self.params(ob, prior_ng), sampled, tau_old, mu_old)
+
+
+class Enc_apg_eta(nn.Module):
+    """Conditional proposal of {mean, precision} given z, apgs/gmm/models.py:50-88."""
+
+    def __init__(self, K, D):
+        super(self.__class__, self).__init__()
+        self.gamma = nn.Sequential(nn.Linear(K + D, K), nn.Softmax(-1))
+        self.ob = nn.Sequential(nn.Linear(K + D, D))
+
+    def heads(self, ob, z):
+        """Linear(cat(ob, z)) without materialising the S-replicated concatenation:
+        W [x; z] + b = (W_x x + b) (per instance) + W_z z (per particle)."""
+        x = _x_inst(ob)
+        D = x.shape[-1]
+        Wg, bg = self.gamma[0].weight, self.gamma[0].bias
+        Wo, bo = self.ob[0].weight, self.ob[0].bias
+        gam = F.softmax(F.linear(z, Wg[:, D:]) + F.linear(x, Wg[:, :D], bg), -1)
+        xp = F.linear(z, Wo[:, D:]) + F.linear(x, Wo[:, :D], bo)
+        return xp, gam
+
+    def params(self, ob, z, prior_ng):
+        xp, gam = self.heads(ob, z)
+        return kernels.nss_posterior(xp, gam, _PriorNG(prior_ng))
+
+    def forward(self, ob, z, prior_ng, sampled=True, tau_old=None, mu_old=None):
+        return _eta_trace(self.params(ob, z, prior_ng), sampled, tau_old, mu_old)
+
+
+class Enc_apg_z(nn.Module):
+    """Conditional proposal of the assignments z, apgs/gmm/models.py:91-115."""
+    chunk_elems = 1 << 28          # bound on the (s,b,n,k,h) activation held at once (floats)
+
+    def __init__(self, K, D, num_hidden):
+        super(self.__class__, self).__init__()
+        self.pi_log_prob = nn.Sequential(nn.Linear(3 * D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, 1))
+
+    def probs(self, ob, tau, mu):
+        """q_probs (S,B,N,K) = softmax_k MLP(cat(x_n, mu_k, tau_k)).  The first Linear is split
+        into its x / mu / tau column blocks so that nothing is replicated over N or S."""
+        x = _x_inst(ob)
+        D = x.shape[-1]
+        W1, b1 = self.pi_log_prob[0].weight, self.pi_log_prob[0].bias
+        W2, b2 = self.pi_log_prob[2].weight, self.pi_log_prob[2].bias
+        hx = F.linear(x, W1[:, :D])                                          # (B,N,H)
+        he = F.linear(mu, W1[:, D:2 * D]) + F.linear(tau, W1[:, 2 * D:], b1)  # (S,B,K,H)
+        S, B, K, H = he.shape
+        N = x.shape[-2]
+        step = max(1, int(self.chunk_elems // max(1, B * N * K * H)))
+        outs = []
+        for s0 in range(0, S, step):
+            h = torch.tanh(hx[None, :, :, None, :] + he[s0:s0 + step, :, None, :, :])   # (s,B,N,K,H)
+            outs.append(F.linear(h, W2, b2).squeeze(-1))
+        logits = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return F.softmax(logits, -1)
+
+    def forward(self, ob, tau, mu, sampled=True, z_old=None):
+        q = Trace()
+        q_probs = self.probs(ob, tau, mu)
+        if sampled:
+            z = cat(q_probs).sample()
+            _ = q.variable(cat, probs=q_probs, value=z, name='states')
+        else:
+            _ = q.variable(cat, probs=q_probs, value=z_old, name='states')
+        q.q_probs = q_probs
+        return q
+
+
+class Generative():
+    """The generative model of GMM, apgs/gmm/models.py:117-185."""
+
+    def __init__(self, K, D, CUDA, device):
+        super().__init__()
+        self.K = K
+        dev = torch.device(device) if CUDA else torch.device("cpu")
+        self.prior_mu = torch.zeros((K, D), device=dev)
+        self.prior_nu = torch.ones((K, D), device=dev) * 0.1
+        self.prior_alpha = torch.ones((K, D), device=dev) * 2
+        self.prior_beta = torch.ones((K, D), device=dev) * 2
+        self.prior_pi = torch.ones(K, device=dev) * (1. / K)
+        self.prior_ng = (self.prior_alpha, self.prior_beta, self.prior_mu, self.prior_nu)
+
+    def eta_prior(self, q):
+        p = Trace()
+        p.gamma(self.prior_alpha, self.prior_beta, value=q['precisions'], name='precisions')
+        p.normal(self.prior_mu, 1. / (self.prior_nu * p['precisions'].value).sqrt(), value=q['means'], name='means')
+        return p
+
+    def z_prior(self, q):
+        p = Trace()
+        _ = p.variable(cat, probs=self.prior_pi, value=q['states'], name='states')
+        return p
+
+    def log_prob(self, ob, z, tau, mu, aggregate=False):
+        """log p(x | z, tau, mu): (S,B,N), or (S,B) when aggregate -- via the z-step kernel's
+        likelihood path would need q_probs, so the un-fused form is evaluated with torch ops here;
+        the sweep objectives never call this (they use the fused kernels)."""
+        if ob.dim() == 3:
+            ob = ob.unsqueeze(0).expand(z.shape[0], -1, -1, -1)
+        sigma = 1. / tau.sqrt()
+        labels = z.argmax(-1).unsqueeze(-1).expand(-1, -1, -1, ob.shape[-1])
+        ll = Normal(torch.gather(mu, 2, labels), torch.gather(sigma, 2, labels)).log_prob(ob).sum(-1)
+        return ll.sum(-1) if aggregate else ll
+
+
+def init_apg_models(K, D, num_hidden_z, CUDA, device, load_version=None, lr=None):
+    """apgs/gmm/apg_training.py:70-99 (same construction order -> same weights under a seed)."""
+    enc_rws_eta = Enc_rws_eta(K, D)
+    enc_apg_z = Enc_apg_z(K, D, num_hidden_z)
+    enc_apg_eta = Enc_apg_eta(K, D)
+    generative = Generative(K, D, CUDA, device)
+    if CUDA:
+        enc_rws_eta.to(device)
+        enc_apg_z.to(device)
+        enc_apg_eta.to(device)
+    if load_version is not None:
+        weights = torch.load("weights/cp-%s" % load_version)
+        enc_rws_eta.load_state_dict(weights['enc-rws-eta'])
+        enc_apg_z.load_state_dict(weights['enc-apg-z'])
+        enc_apg_eta.load_state_dict(weights['enc-apg-eta'])
+    if lr is not None:
+        assert isinstance(lr, float)
+        optimizer = torch.optim.Adam(list(enc_rws_eta.parameters()) + list(enc_apg_z.parameters())
+                                     + list(enc_apg_eta.parameters()), lr=lr, betas=(0.9, 0.99))
+        return (enc_rws_eta, enc_apg_z, enc_apg_eta, generative), optimizer
+    for m in (enc_rws_eta, enc_apg_z, enc_apg_eta):
+        for p in m.parameters():
+            p.requires_grad = False
+    return (enc_rws_eta, enc_apg_z, enc_apg_eta, generative)

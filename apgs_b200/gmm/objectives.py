@@ -1,0 +1,141 @@
+"""APG sweep for the GMM task: drop-in for the hot-path functions of apgs/gmm/objectives.py
+(apg_objective :9-53, oneshot :74-110, apg_update_joint :112-158, apg_update_eta :161-195,
+apg_update_z :197-227, resample_variables :229-234).
+
+Differences a caller can observe: none in names, argument meaning or returned shapes.
+Differences in how the work is done:
+  * each block update evaluates its encoder ONCE and scores both the new and the old values
+    against the same proposal parameters (the reference re-runs the encoder with identical
+    inputs for the backward kernel, objectives.py:174,210,131,135);
+  * every log-density, the N-sums and the f - b difference are one fused kernel (csrc/gmm.cu);
+  * softmax / ESS over S is one kernel (W1); resampling is ancestors + one gather launch for
+    (tau, mu, z) with no int64 index expansion;
+  * `x` may be passed as (B,N,D); the reference's S-replicated (S,B,N,D) is accepted and only
+    its first slice is read.
+Gradients: this module is the evaluation path (the reference's budget_analysis flags,
+apgs/gmm/evaluation.py:127).  `loss_required` returns forward values only.
+"""
+import torch
+from torch.distributions.gamma import Gamma
+from torch.distributions.normal import Normal
+from torch.distributions.one_hot_categorical import OneHotCategorical as cat
+
+from .. import ops
+from . import kernels
+
+
+def _sample_eta(post):
+    q_alpha, q_beta, q_mu, q_nu = post
+    tau = Gamma(q_alpha, q_beta).sample()
+    mu = Normal(q_mu, 1. / (q_nu * tau).sqrt()).sample()
+    return tau, mu
+
+
+def _book(trace, result_flags, log_w, log_q_f, density, append=True):
+    """loss / ess / density bookkeeping shared by the steps (objectives.py:93-109,181-194)."""
+    if result_flags['loss_required'] or result_flags['ess_required']:
+        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        if result_flags['loss_required']:
+            trace['loss'].append((w * (-log_q_f)).sum(0).mean().unsqueeze(0))
+        if result_flags['ess_required']:
+            trace['ess'].append(ess.unsqueeze(0))
+    if result_flags['density_required']:
+        trace['density'].append(density.unsqueeze(0))
+
+
+def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
+    """Amortized Population Gibbs objective in the GMM problem (objectives.py:9-53)."""
+    trace = {'loss': [], 'ess': [], 'E_tau': [], 'E_mu': [], 'E_z': [], 'density': []}
+    (enc_rws_eta, enc_apg_z, enc_apg_eta, generative) = models
+    if x.dim() == 3:
+        x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)       # stride-0 S axis; never materialised
+    log_w, tau, mu, z, trace = oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags)
+    tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
+    for m in range(num_sweeps - 1):
+        if block == 'decomposed':
+            log_w_eta, tau, mu, trace = apg_update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags)
+            tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_eta)
+            log_w_z, z, trace = apg_update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags)
+            tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_z)
+        elif block == 'joint':
+            log_w, tau, mu, z, trace = apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z, tau, mu, trace, result_flags)
+            tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
+        else:
+            raise ValueError
+    if result_flags['loss_required']:
+        trace['loss'] = torch.cat(trace['loss'], 0)
+    if result_flags['ess_required']:
+        trace['ess'] = torch.cat(trace['ess'], 0)
+    if result_flags['mode_required']:
+        trace['E_tau'] = torch.cat(trace['E_tau'], 0)
+        trace['E_mu'] = torch.cat(trace['E_mu'], 0)
+        trace['E_z'] = torch.cat(trace['E_z'], 0)
+    if result_flags['density_required']:
+        trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
+    """One-shot for eta and z, like a normal RWS (objectives.py:74-110)."""
+    post = enc_rws_eta.params(x, generative.prior_ng)
+    tau, mu = _sample_eta(post)
+    q_probs = enc_rws_z.probs(x, tau, mu)
+    z = cat(q_probs).sample()
+    w = kernels.logw_oneshot(x, post, generative, tau, mu, q_probs, z)
+    _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
+    if result_flags['mode_required']:
+        trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
+        trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
+        trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
+    return w.log_w, tau, mu, z, trace
+
+
+def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old, trace, result_flags):
+    """Jointly update all the variables (objectives.py:112-158)."""
+    post = enc_apg_eta.params(x, z_old, generative.prior_ng)
+    tau, mu = _sample_eta(post)
+    q_probs = enc_apg_z.probs(x, tau, mu)
+    z = cat(q_probs).sample()
+    w = kernels.logw_joint(x, post, generative, tau, mu, tau_old, mu_old, q_probs, z, z_old)
+    _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
+    if result_flags['mode_required']:
+        # the reference's branch (objectives.py:149-155) reads an undefined name; emit what it intends
+        trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
+        trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
+        trace['E_z'].append(z.unsqueeze(0))
+    return w.log_w, tau, mu, z, trace
+
+
+def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags):
+    """Given local variable z, update global variables eta := {mu, tau} (objectives.py:161-195)."""
+    post = enc_apg_eta.params(x, z, generative.prior_ng)
+    tau, mu = _sample_eta(post)
+    w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
+    _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
+    if result_flags['mode_required']:
+        trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
+        trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
+    return w.log_w, tau, mu, trace
+
+
+def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
+    """Given the current samples of eta, update the assignments z (objectives.py:197-227)."""
+    q_probs = enc_apg_z.probs(x, tau, mu)
+    z = cat(q_probs).sample()
+    need_local = bool(result_flags['loss_required'])
+    w = kernels.logw_z(x, tau, mu, q_probs, generative, z, z_old, local=need_local)
+    if result_flags['loss_required']:
+        w_local, _ = ops.local_weight_stats(w.log_w_local, want_w=True, want_sum=False)
+        loss = (w_local * (-w.log_q_local)).sum(0).sum(-1).mean()
+        trace['loss'][-1] = trace['loss'][-1] + loss.unsqueeze(0)
+    if result_flags['mode_required']:
+        trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
+    if result_flags['density_required']:
+        trace['density'][-1] = trace['density'][-1] + w.density.unsqueeze(0)
+    return w.log_w, z, trace
+
+
+def resample_variables(resampler, tau, mu, z, log_weights):
+    """objectives.py:229-234: one ancestor draw, one gather launch for the three latents."""
+    tau, mu, z = resampler.resample([tau, mu, z], log_weights)
+    return tau, mu, z

@@ -12,6 +12,57 @@ from ._lib import Latent, check, ptr
 STRATEGIES = {"systematic": _lib.SYSTEMATIC, "multinomial": _lib.MULTINOMIAL}
 
 
+class _Profile(object):
+    """Optional per-call accounting used by bench.py: counts the kernels this package launches and,
+    when `events` is on, brackets every C-ABI call with CUDA events on the launching stream."""
+
+    def __init__(self):
+        self.launches = 0
+        self.events = False
+        self.records = []          # (name, start_event, end_event, algorithmic_bytes)
+
+    def reset(self, events=False):
+        self.launches, self.events, self.records = 0, events, []
+
+    def summary(self):
+        """name -> dict(calls, ms_total, ms_avg, bytes_per_call, gbs) (call after a synchronize)."""
+        out = {}
+        for name, e0, e1, nbytes in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms_total": 0.0, "bytes": 0})
+            d["calls"] += 1
+            d["ms_total"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+        for d in out.values():
+            d["ms_avg"] = d["ms_total"] / d["calls"]
+            d["bytes_per_call"] = d["bytes"] / d["calls"]
+            d["gbs"] = d["bytes"] / max(d["ms_total"], 1e-9) / 1e6
+        return out
+
+
+PROFILE = _Profile()
+
+
+class _call(object):
+    __slots__ = ("name", "n", "nbytes", "e0")
+
+    def __init__(self, name, n_launches, nbytes=0):
+        self.name, self.n, self.nbytes = name, n_launches, nbytes
+
+    def __enter__(self):
+        PROFILE.launches += self.n
+        if PROFILE.events:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE.events and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.records.append((self.name, self.e0, e1, self.nbytes))
+        return False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -46,7 +97,7 @@ def weight_stats(log_w, want_w=True):
     lse = torch.empty(B, dtype=torch.float32, device=log_w.device)
     nws = lib.apgs_ancestors_workspace_bytes(S, B)
     ws = _workspace(nws, log_w.device)
-    with torch.cuda.device(log_w.device):
+    with torch.cuda.device(log_w.device), _call("weight_stats", 1, 4 * S * B * (2 if want_w else 1)):
         check(lib.apgs_weight_stats_f32(ptr(log_w), S, B, ptr(w), ptr(ess), ptr(lse), ptr(ws), nws, _stream()),
               "apgs_weight_stats_f32")
     return w, ess, lse
@@ -59,7 +110,8 @@ def local_weight_stats(log_w_local, want_w=True, want_sum=True):
     S, B, N = x.shape
     w = torch.empty_like(x) if want_w else None
     lw = torch.empty(S, B, dtype=torch.float32, device=x.device) if want_sum else None
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _call("local_weight_stats", int(want_w) + int(want_sum),
+                                            4 * S * B * N * (int(want_sum) + 2 * int(want_w))):
         check(lib.apgs_local_weight_stats_f32(ptr(x), S, B, N, ptr(w), ptr(lw), _stream()),
               "apgs_local_weight_stats_f32")
     return w, lw
@@ -112,7 +164,7 @@ def sample_ancestors(log_w=None, w_norm=None, strategy="systematic", uniforms=No
         lse = torch.empty(B, dtype=torch.float32, device=dev)
     nws = lib.apgs_ancestors_workspace_bytes(S, B)
     ws = _workspace(nws, dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _call("sample_ancestors", 1, S * B * (4 + anc.element_size())):
         check(lib.apgs_sample_ancestors_f32(
             ptr(src) if log_w is not None else None, ptr(src) if w_norm is not None else None,
             S, B, STRATEGIES[strategy], ptr(u), us, ub, cdf_mode, ptr(a64), ptr(a32),
@@ -149,7 +201,8 @@ def gather_ancestors(latents, anc):
     arr, srcs, outs = _latent_array(latents, S, B)
     a32 = anc if anc.dtype == torch.int32 else None
     a64 = anc if anc.dtype == torch.int64 else None
-    with torch.cuda.device(anc.device):
+    nbytes = S * B * (anc.element_size() + 2 * sum(int(a.inner_bytes) for a in arr[:len(latents)]))
+    with torch.cuda.device(anc.device), _call("gather_ancestors", 1, nbytes):
         check(lib.apgs_gather_ancestors(ptr(a32), ptr(a64), S, B, arr, len(latents), _stream()),
               "apgs_gather_ancestors")
     return outs
@@ -180,7 +233,8 @@ def resample(latents, log_w=None, w_norm=None, strategy="systematic", uniforms=N
         lse = torch.empty(B, dtype=torch.float32, device=dev)
     nws = lib.apgs_resample_workspace_bytes(S, B)
     ws = _workspace(nws, dev)
-    with torch.cuda.device(dev):
+    nbytes = S * B * (4 + 2 * sum(int(a.inner_bytes) for a in arr[:len(latents)]))
+    with torch.cuda.device(dev), _call("resample", 2, nbytes):
         check(lib.apgs_resample_f32(
             ptr(src) if log_w is not None else None, ptr(src) if w_norm is not None else None,
             S, B, STRATEGIES[strategy], ptr(u), us, ub, cdf_mode, arr, len(latents),

@@ -74,6 +74,11 @@ class Resampler():
         S, B = log_weights.shape
         if uniforms is None:
             uniforms = self.draw_uniforms(S, B, log_weights.device)
+        if ops.PROFILE.events and not (want_stats or want_index):
+            # bench.py roofline accounting: same two kernels, timed separately
+            anc32 = ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms,
+                                         cdf_mode=self.cdf_mode, index_dtype=torch.int32)
+            return ops.gather_ancestors(latents, anc32)
         outs, anc, stats = ops.resample(latents, log_w=log_weights, strategy=self.strategy,
                                         uniforms=uniforms, cdf_mode=self.cdf_mode,
                                         want_index=want_index, want_stats=want_stats)

@@ -119,6 +119,68 @@ APGS_API int apgs_resample_f32(const float* log_w, const float* w_norm, int64_t 
                       int64_t* anc64, float* w_out, float* ess, float* lse,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ==============================================================================================
+ * GMM reweighting.  K clusters, D data dims, N points.
+ * Instantiated (K,D): (3,2) (2,2) (4,2) (5,2) (3,3) (4,3) (3,1); anything else -> APGS_E_UNSUPPORTED.
+ * ============================================================================================== */
+
+/* G1  neural sufficient statistics -> Normal-Gamma posterior parameters.
+ * replaces data_to_stats + posterior_eta, apgs/gmm/kls_gmm.py:92-119 (called from
+ * Enc_rws_eta.forward apgs/gmm/models.py:27 and Enc_apg_eta.forward :66), incl. quirks Q1/Q2.
+ *   xp (S,B,N,D) = Linear(ob|z), gamma (S,B,N,K) = softmax(Linear(ob|z)); prior_* (K,D);
+ *   post_* (S,B,K,D) out.  No (S,B,N,K,D) temporaries are built.                              */
+APGS_API int apgs_gmm_nss_posterior_f32(const float* xp, const float* gamma,
+                               int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                               const float* prior_alpha, const float* prior_beta,
+                               const float* prior_mu, const float* prior_nu,
+                               float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
+                               void* stream);
+
+typedef struct apgs_gmm_prior {       /* HOST struct of DEVICE pointers; apgs/gmm/models.py:124-128 */
+    const float *alpha, *beta, *mu, *nu;   /* (K,D) each */
+    const float *pi;                       /* (K)        */
+} apgs_gmm_prior_t;
+typedef struct apgs_gmm_post {        /* proposal parameters from G1, (S,B,K,D) each */
+    const float *alpha, *beta, *mu, *nu;
+} apgs_gmm_post_t;
+typedef struct apgs_gmm_out {         /* every field optional (NULL = not wanted) */
+    float *log_w;        /* (S,B)   log importance weight of the step                               */
+    float *log_q_f;      /* (S,B)   forward proposal log-density (the loss term)                    */
+    float *density;      /* (S,B)   the step's contribution to trace['density']                     */
+    float *log_w_f;      /* (S,B)   forward / backward halves of log_w (parity checks)              */
+    float *log_w_b;
+    float *log_w_local;  /* (S,B,N) z step only: per-point weight (objectives.py:216)                */
+    float *log_q_local;  /* (S,B,N) z step only: per-point forward log q(z_n)                       */
+} apgs_gmm_out_t;
+
+/* x is (B,N,D): ONE copy per instance -- the reference's S-fold replication (apg_training.py:19)
+ * is not needed.  z tensors are one-hot fp32 (S,B,N,K); tau/mu (S,B,K,D); q_probs (S,B,N,K).       */
+
+/* G4a one-shot weight.  replaces the arithmetic of oneshot, apgs/gmm/objectives.py:74-110.         */
+APGS_API int apgs_gmm_logw_oneshot_f32(const float* x, const apgs_gmm_post_t* post, const apgs_gmm_prior_t* prior,
+                              const float* tau, const float* mu, const float* q_probs, const float* z,
+                              int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              const apgs_gmm_out_t* out, void* stream);
+/* G2  eta step.  replaces apg_update_eta arithmetic, apgs/gmm/objectives.py:161-195
+ *     (+ Generative.eta_prior models.py:139-150, Generative.log_prob(aggregate=True) :172-185).    */
+APGS_API int apgs_gmm_logw_eta_f32(const float* x, const float* z, const apgs_gmm_post_t* post,
+                          const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
+                          const float* tau_old, const float* mu_old,
+                          int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                          const apgs_gmm_out_t* out, void* stream);
+/* G3  z step (+W2 sum over points).  replaces apg_update_z arithmetic, objectives.py:197-227
+ *     (+ z_prior models.py:167-170, log_prob(aggregate=False)), eps-clamped categorical (Q4).      */
+APGS_API int apgs_gmm_logw_z_f32(const float* x, const float* tau, const float* mu, const float* q_probs,
+                        const apgs_gmm_prior_t* prior, const float* z, const float* z_old,
+                        int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                        const apgs_gmm_out_t* out, void* stream);
+/* G4b joint step.  replaces apg_update_joint arithmetic, objectives.py:112-158.                    */
+APGS_API int apgs_gmm_logw_joint_f32(const float* x, const apgs_gmm_post_t* post, const apgs_gmm_prior_t* prior,
+                            const float* tau, const float* mu, const float* tau_old, const float* mu_old,
+                            const float* q_probs, const float* z, const float* z_old,
+                            int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                            const apgs_gmm_out_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

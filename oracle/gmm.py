@@ -140,7 +140,7 @@ def z_log_prior(z, prior):
 
 
 # --------------------------------------------------- G2 / G3 / G4: importance weights
-def eta_step_weights(x, z, post, prior, tau, mu, tau_old, mu_old):
+def eta_step_weights(x, z, post, prior, tau, mu, tau_old, mu_old, parts=False):
     """objectives.py:161-195 given the posterior parameters and the draws.
     Returns log_w, log_q_f, log_p_f (the 'density' increment), ll_f   -- all (S,B)."""
     log_q_f = eta_log_q(tau, mu, post)
@@ -151,10 +151,12 @@ def eta_step_weights(x, z, post, prior, tau, mu, tau_old, mu_old):
     log_p_b = eta_log_prior(tau_old, mu_old, prior)
     ll_b = log_likelihood(x, z, tau_old, mu_old, True)
     log_w_b = ll_b + log_p_b - log_q_b
+    if parts:
+        return log_w_f - log_w_b, log_q_f, log_p_f, ll_f, log_w_f, log_w_b
     return log_w_f - log_w_b, log_q_f, log_p_f, ll_f
 
 
-def z_step_weights(x, tau, mu, q_probs, prior, z, z_old):
+def z_step_weights(x, tau, mu, q_probs, prior, z, z_old, parts=False):
     """objectives.py:197-227 given q_probs and the draws.
     Returns log_w_local (S,B,N), log_w (S,B), log_q_f (S,B,N), ll_f + log_p_f (S,B,N)."""
     log_q_f = z_log_q(z, q_probs)
@@ -166,6 +168,8 @@ def z_step_weights(x, tau, mu, q_probs, prior, z, z_old):
     ll_b = log_likelihood(x, z_old, tau, mu, False)
     log_w_b = ll_b + log_p_b - log_q_b
     log_w_local = log_w_f - log_w_b
+    if parts:
+        return log_w_local, log_w_local.sum(-1), log_q_f, ll_f + log_p_f, log_w_f.sum(-1), log_w_b.sum(-1)
     return log_w_local, log_w_local.sum(-1), log_q_f, ll_f + log_p_f
 
 
@@ -181,7 +185,7 @@ def oneshot_weights(x, post, prior, tau, mu, q_probs, z):
     return log_p - log_q, log_q, log_p
 
 
-def joint_step_weights(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old):
+def joint_step_weights(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, parts=False):
     """objectives.py:112-158 given parameters and draws.  q_probs is evaluated at the
     NEW (tau, mu) for both the forward and the backward z-term (:123,:131)."""
     log_q_f_eta = eta_log_q(tau, mu, post)
@@ -196,6 +200,8 @@ def joint_step_weights(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_o
     log_p_b_eta = eta_log_prior(tau_old, mu_old, prior)
     ll_b = log_likelihood(x, z_old, tau_old, mu_old, True)
     log_w_b = ll_b + log_p_b_eta - log_q_b_eta + log_p_b_z - log_q_b_z
+    if parts:
+        return (log_w_f - log_w_b, log_q_f_eta + log_q_f_z, ll_f + log_p_f_eta + log_p_f_z, log_w_f, log_w_b)
     return (log_w_f - log_w_b, log_q_f_eta + log_q_f_z, ll_f + log_p_f_eta + log_p_f_z)
 
 

@@ -36,6 +36,7 @@ def test_version_and_pure_host_queries():
     assert lib.apgs_version() == 1
     assert lib.apgs_ancestors_workspace_bytes(1000, 1024) == 0            # CDF tile lives in smem
     assert lib.apgs_ancestors_workspace_bytes(100000, 10) == 100000 * 10 * 4
+    assert lib.apgs_ancestors_workspace_bytes(8192, 7) == 0
     assert lib.apgs_resample_workspace_bytes(1000, 1024) >= 1000 * 1024 * 4
 
 

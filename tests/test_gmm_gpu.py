@@ -1,0 +1,305 @@
+"""GPU parity: GMM reweighting kernels (G1-G4) and the sweep, through the C ABI, against the
+oracle and the reference-generated golden fixtures.
+
+Tolerances (north_star: 1e-5 relative, fp32):
+  * every log-density sum (log_w_f, log_w_b, log_q_f, density): rtol 1e-5;
+  * log_w = log_w_f - log_w_b is a difference of large sums: atol = 1e-5 * (|f| + |b|);
+  * posterior beta contains s3 - s2^2/cnt, a cancellation the reference itself evaluates in fp32:
+    atol = 4e-6 * (|s3| + s2^2/cnt) on top of rtol 1e-5 (the kernel is checked to be at least as
+    close to an fp64 evaluation as the reference is).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gmm as og
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RT = 1e-5
+
+
+def _t(g, k):
+    return torch.from_numpy(g[k])
+
+
+def _params(g):
+    P = {}
+    for k in g.files:
+        if k.startswith("P/"):
+            _, mod, name = k.split("/", 2)
+            P.setdefault(mod, {})[name] = torch.from_numpy(g[k])
+    return P
+
+
+class _Gen:
+    def __init__(self, K=3, D=2):
+        pr = og.make_prior(K, D)
+        self.prior_alpha, self.prior_beta = pr["alpha"].to(DEV), pr["beta"].to(DEV)
+        self.prior_mu, self.prior_nu, self.prior_pi = pr["mu"].to(DEV), pr["nu"].to(DEV), pr["pi"].to(DEV)
+        self.prior_ng = (self.prior_alpha, self.prior_beta, self.prior_mu, self.prior_nu)
+
+
+def _close(a, b, rtol=RT, atol=0.0, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    atol_t = atol if torch.is_tensor(atol) else torch.full_like(b, atol)
+    err = (a - b).abs() - (atol_t.cpu().double() + rtol * b.abs())
+    assert float(err.max()) <= 0, "%s: worst excess %g (max abs diff %g)" % (what, float(err.max()), float((a - b).abs().max()))
+
+
+def _dev(*ts):
+    return [t.to(DEV) for t in ts]
+
+
+def _eta_mag(tau, mu, post):
+    """sum over (K,D) of the magnitudes of the terms a Normal-Gamma log-density adds up: the
+    1e-5 relative bound applies to this scale, not to the (possibly cancelling) total."""
+    from oracle import dists
+    al, be, mq, nq = post
+    sc = 1. / (nq * tau).sqrt()
+    m = (torch.xlogy(al, be).abs() + torch.xlogy(al - 1, tau).abs() + (be * tau).abs() + torch.lgamma(al).abs()
+         + ((mu - mq) ** 2 / (2 * sc ** 2)).abs() + sc.log().abs() + dists.LOG_SQRT_2PI)
+    return m.sum(-1).sum(-1)
+
+
+# --------------------------------------------------------------------------------------- G1
+def _nss_check(xp, gamma, ref_post):
+    from apgs_b200.gmm import kernels
+    a, b, m, n = kernels.nss_posterior(xp.to(DEV), gamma.to(DEV), _Gen(gamma.shape[-1], xp.shape[-1]))
+    ra, rb, rm, rn = ref_post
+    _close(a, ra, what="alpha")
+    _close(n, rn, what="nu")
+    g5, x5 = gamma.double().unsqueeze(-1), xp.double().unsqueeze(-2)
+    s2a, s3 = (g5 * x5.abs()).sum(2), (g5 * x5 ** 2).sum(2)       # magnitudes entering the fp32 sums
+    cnt = gamma.double().sum(2).unsqueeze(-1).expand_as(s3).clone()
+    cnt[cnt == 0] = 1
+    cond = s3.abs() + s2a ** 2 / cnt
+    _close(m, rm, atol=2e-6 * s2a / cnt, what="mu")
+    _close(b, rb, atol=4e-6 * cond, what="beta")
+    # at least as accurate as the reference w.r.t. an fp64 evaluation of the same formula
+    pr = {k: v.double() for k, v in og.make_prior(gamma.shape[-1], xp.shape[-1]).items()}
+    ea = og.nss_posterior(xp.double(), gamma.double(), pr)
+    err_k = (b.cpu().double() - ea[1]).abs().max()
+    err_r = (rb.double() - ea[1]).abs().max()
+    assert float(err_k) <= float(err_r) * 1.5 + 1e-6 * float(ea[1].abs().max())
+
+
+def test_G1_nss_posterior_vs_reference_golden(golden):
+    g = golden("gmm")
+    for tag in ("soft", "hard"):       # "hard" has an empty cluster -> quirk Q1
+        _nss_check(_t(g, "g1_xp"), _t(g, "g1_%s_gamma" % tag),
+                   [_t(g, "g1_%s_%s" % (tag, n)) for n in ("alpha", "beta", "mu", "nu")])
+
+
+@pytest.mark.parametrize("S,B,N,K,D", [(7, 5, 60, 3, 2), (33, 31, 17, 4, 2), (1, 1, 3, 3, 3), (64, 16, 200, 4, 2), (3, 2, 61, 5, 2)])
+def test_G1_nss_posterior_vs_oracle(S, B, N, K, D):
+    torch.manual_seed(S * 7 + N)
+    xp = torch.randn(S, B, N, D) * 3 + 2
+    gamma = torch.softmax(torch.randn(S, B, N, K) * 3, -1)
+    _nss_check(xp, gamma, og.nss_posterior(xp, gamma, og.make_prior(K, D)))
+
+
+# ------------------------------------------------------------------------------ G2 / G3 / G4
+def test_G2_eta_step_vs_reference_golden(golden):
+    from apgs_b200.gmm import kernels
+    g = golden("gmm")
+    P, prior = _params(g), og.make_prior()
+    S = g["eta_z"].shape[0]
+    x = _t(g, "x")
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    post = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, _t(g, "eta_z"), prior)
+    ref = og.eta_step_weights(xs, _t(g, "eta_z"), post, prior, _t(g, "eta_tau"), _t(g, "eta_mu"),
+                              _t(g, "eta_tau_old"), _t(g, "eta_mu_old"), parts=True)
+    assert torch.equal(ref[0], _t(g, "eta_log_w"))            # oracle == reference (bit exact on CPU)
+    w = kernels.logw_eta(x.to(DEV), _t(g, "eta_z").to(DEV), _dev(*post), _Gen(), *_dev(_t(g, "eta_tau"), _t(g, "eta_mu"),
+                         _t(g, "eta_tau_old"), _t(g, "eta_mu_old")), parts=True)
+    _close(w.log_w_f, ref[4], what="log_w_f")
+    _close(w.log_w_b, ref[5], what="log_w_b")
+    _close(w.log_q_f, ref[1], rtol=0, atol=RT * _eta_mag(_t(g, "eta_tau"), _t(g, "eta_mu"), post), what="log_q_f")
+    _close(w.density, _t(g, "eta_density")[0], what="density")
+    _close(w.log_w, _t(g, "eta_log_w"), rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="log_w")
+    # the S-replicated layout the reference passes gives the same numbers
+    w2 = kernels.logw_eta(xs.to(DEV), _t(g, "eta_z").to(DEV), _dev(*post), _Gen(), *_dev(_t(g, "eta_tau"), _t(g, "eta_mu"),
+                          _t(g, "eta_tau_old"), _t(g, "eta_mu_old")))
+    assert torch.equal(w2.log_w, w.log_w)
+
+
+def test_G3_z_step_vs_reference_golden(golden):
+    from apgs_b200.gmm import kernels
+    from apgs_b200 import ops
+    g = golden("gmm")
+    P, prior = _params(g), og.make_prior()
+    S = g["z_old"].shape[0]
+    x = _t(g, "x")
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    q_probs = og.enc_apg_z_probs(P["enc_apg_z"], xs, _t(g, "z_tau"), _t(g, "z_mu"))
+    ref = og.z_step_weights(xs, _t(g, "z_tau"), _t(g, "z_mu"), q_probs, prior, _t(g, "z_new"), _t(g, "z_old"), parts=True)
+    assert torch.equal(ref[1], _t(g, "z_log_w"))
+    w = kernels.logw_z(x.to(DEV), *_dev(_t(g, "z_tau"), _t(g, "z_mu"), q_probs), _Gen(), *_dev(_t(g, "z_new"), _t(g, "z_old")),
+                       parts=True, local=True)
+    _close(w.log_w_f, ref[4], what="sum log_w_f")
+    _close(w.log_w_b, ref[5], what="sum log_w_b")
+    _close(w.density, _t(g, "z_density")[0], what="density")
+    _close(w.log_q_local, ref[2], atol=1e-6, what="log_q_local")
+    # per-point weights: f - b per point, each term O(1..10)
+    _close(w.log_w_local, ref[0], rtol=RT, atol=2e-5, what="log_w_local")
+    _close(w.log_w, _t(g, "z_log_w"), rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="log_w")
+    # W2 + loss term as the reference computes it (objectives.py:217,220)
+    w_local, _ = ops.local_weight_stats(w.log_w_local, want_sum=False)
+    loss = (w_local * (-w.log_q_local)).sum(0).sum(-1).mean()
+    np.testing.assert_allclose(float(loss), float(_t(g, "z_loss")[0]), rtol=2e-5)
+
+
+def test_G4_oneshot_and_joint_vs_reference_golden(golden):
+    from apgs_b200.gmm import kernels
+    g = golden("gmm")
+    P, prior = _params(g), og.make_prior()
+    S = g["os_z"].shape[0]
+    x = _t(g, "x")
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    post = og.enc_rws_eta_posterior(P["enc_rws_eta"], xs, prior)
+    q_probs = og.enc_apg_z_probs(P["enc_apg_z"], xs, _t(g, "os_tau"), _t(g, "os_mu"))
+    lw, lq, lp = og.oneshot_weights(xs, post, prior, _t(g, "os_tau"), _t(g, "os_mu"), q_probs, _t(g, "os_z"))
+    w = kernels.logw_oneshot(x.to(DEV), _dev(*post), _Gen(), *_dev(_t(g, "os_tau"), _t(g, "os_mu"), q_probs, _t(g, "os_z")))
+    _close(w.density, _t(g, "os_density")[0], what="oneshot log_p")
+    _close(w.log_q_f, lq, rtol=RT, atol=RT * _eta_mag(_t(g, "os_tau"), _t(g, "os_mu"), post), what="oneshot log_q")
+    _close(w.log_w, _t(g, "os_log_w"), rtol=0, atol=RT * (lp.abs() + lq.abs()), what="oneshot log_w")
+    # joint
+    post = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, _t(g, "j_z_old"), prior)
+    q_probs = og.enc_apg_z_probs(P["enc_apg_z"], xs, _t(g, "j_tau"), _t(g, "j_mu"))
+    ref = og.joint_step_weights(xs, post, prior, _t(g, "j_tau"), _t(g, "j_mu"), _t(g, "j_tau_old"), _t(g, "j_mu_old"),
+                                q_probs, _t(g, "j_z"), _t(g, "j_z_old"), parts=True)
+    assert torch.equal(ref[0], _t(g, "j_log_w"))
+    w = kernels.logw_joint(x.to(DEV), _dev(*post), _Gen(), *_dev(_t(g, "j_tau"), _t(g, "j_mu"), _t(g, "j_tau_old"),
+                           _t(g, "j_mu_old"), q_probs, _t(g, "j_z"), _t(g, "j_z_old")), parts=True)
+    _close(w.log_w_f, ref[3], what="joint log_w_f")
+    _close(w.log_w_b, ref[4], what="joint log_w_b")
+    _close(w.density, _t(g, "j_density")[0], what="joint density")
+    _close(w.log_w, _t(g, "j_log_w"), rtol=0, atol=RT * (ref[3].abs() + ref[4].abs()), what="joint log_w")
+
+
+@pytest.mark.parametrize("S,B,N,K,D", [(5, 3, 60, 3, 2), (37, 9, 41, 4, 2), (2, 1, 7, 3, 3), (100, 20, 60, 3, 2)])
+def test_steps_vs_oracle_random_shapes(S, B, N, K, D):
+    """ragged tiles (S*B not a multiple of the 32-particle tile), other (K,D), -inf-free random inputs."""
+    from apgs_b200.gmm import kernels
+    torch.manual_seed(S + N + K)
+    prior = og.make_prior(K, D)
+    x = torch.randn(B, N, D) * 2
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    one_hot = lambda: torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    z, z_old = one_hot(), one_hot()
+    tau, tau_old = torch.rand(S, B, K, D) * 3 + 0.1, torch.rand(S, B, K, D) * 3 + 0.1
+    mu, mu_old = torch.randn(S, B, K, D) * 2, torch.randn(S, B, K, D) * 2
+    post = (torch.rand(S, B, K, D) * 20 + 1, torch.rand(S, B, K, D) * 20 + 0.5, torch.randn(S, B, K, D), torch.rand(S, B, K, D) * 20 + 0.1)
+    q_probs = torch.softmax(torch.randn(S, B, N, K) * 3, -1)
+    q_probs[0, 0, 0] = torch.tensor([1.0] + [0.0] * (K - 1))           # exercises the eps clamp (Q4)
+    gen = _Gen(K, D)
+    # random proposal parameters make the three summands of log_w_f huge and cancelling: the bound
+    # is relative to the magnitudes that are added (|ll| + |log p| + |log q|), as in SURVEY.md H2
+    mag_f = (og.log_likelihood(xs, z, tau, mu, True).abs() + og.eta_log_prior(tau, mu, prior).abs()
+             + og.eta_log_q(tau, mu, post).abs())
+    mag_b = (og.log_likelihood(xs, z, tau_old, mu_old, True).abs() + og.eta_log_prior(tau_old, mu_old, prior).abs()
+             + og.eta_log_q(tau_old, mu_old, post).abs())
+    ref = og.eta_step_weights(xs, z, post, prior, tau, mu, tau_old, mu_old, parts=True)
+    w = kernels.logw_eta(x.to(DEV), z.to(DEV), _dev(*post), gen, *_dev(tau, mu, tau_old, mu_old), parts=True)
+    _close(w.log_w_f, ref[4], rtol=0, atol=RT * mag_f, what="eta f")
+    _close(w.log_w_b, ref[5], rtol=0, atol=RT * mag_b, what="eta b")
+    _close(w.log_w, ref[0], rtol=0, atol=RT * (mag_f + mag_b), what="eta log_w")
+    ref = og.z_step_weights(xs, tau, mu, q_probs, prior, z, z_old, parts=True)
+    w = kernels.logw_z(x.to(DEV), *_dev(tau, mu, q_probs), gen, *_dev(z, z_old), parts=True, local=True)
+    _close(w.log_w_f, ref[4], what="z f")
+    _close(w.log_w_b, ref[5], what="z b")
+    _close(w.log_w, ref[1], rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="z log_w")
+    _close(w.log_w_local, ref[0], rtol=RT, atol=1e-4, what="z local")
+    ref = og.joint_step_weights(xs, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, parts=True)
+    w = kernels.logw_joint(x.to(DEV), _dev(*post), gen, *_dev(tau, mu, tau_old, mu_old, q_probs, z, z_old), parts=True)
+    mag_zf = og.z_log_q(z, q_probs).sum(-1).abs() + og.z_log_prior(z, prior).sum(-1).abs()
+    mag_zb = og.z_log_q(z_old, q_probs).sum(-1).abs() + og.z_log_prior(z_old, prior).sum(-1).abs()
+    mag_bj = (og.log_likelihood(xs, z_old, tau_old, mu_old, True).abs() + og.eta_log_prior(tau_old, mu_old, prior).abs()
+              + og.eta_log_q(tau_old, mu_old, post).abs())
+    _close(w.log_w_f, ref[3], rtol=0, atol=RT * (mag_f + mag_zf), what="joint f")
+    _close(w.log_w_b, ref[4], rtol=0, atol=RT * (mag_bj + mag_zb), what="joint b")
+    lw, lq, lp = og.oneshot_weights(xs, post, prior, tau, mu, q_probs, z)
+    w = kernels.logw_oneshot(x.to(DEV), _dev(*post), gen, *_dev(tau, mu, q_probs, z))
+    _close(w.density, lp, rtol=0, atol=RT * (mag_f + mag_zf), what="oneshot p")
+    _close(w.log_q_f, lq, rtol=RT, atol=RT * (_eta_mag(tau, mu, post) + mag_zf), what="oneshot q")
+
+
+# ------------------------------------------------------------------------- encoders + sweep
+def _models_from_params(P, K=3, D=2, H=32):
+    from apgs_b200.gmm import models as M
+    ms = M.init_apg_models(K, D, H, True, DEV)
+    for m, key in zip(ms[:3], ("enc_rws_eta", "enc_apg_z", "enc_apg_eta")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})     # same state_dict keys as the reference
+    return ms
+
+
+def test_encoder_parameters_match_oracle(golden):
+    g = golden("gmm")
+    P, prior = _params(g), og.make_prior()
+    enc_rws_eta, enc_apg_z, enc_apg_eta, gen = _models_from_params(P)
+    S = g["eta_z"].shape[0]
+    x = _t(g, "x")
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    with torch.no_grad():
+        post = enc_apg_eta.params(xs.to(DEV), _t(g, "eta_z").to(DEV), gen.prior_ng)
+        ref = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, _t(g, "eta_z"), prior)
+        for a, b, nm in zip(post, ref, ("alpha", "beta", "mu", "nu")):
+            _close(a, b, rtol=2e-5, atol=2e-5, what="enc_apg_eta " + nm)
+        post = enc_rws_eta.params(xs.to(DEV), gen.prior_ng)
+        ref = og.enc_rws_eta_posterior(P["enc_rws_eta"], xs, prior)
+        for a, b, nm in zip(post, ref, ("alpha", "beta", "mu", "nu")):
+            _close(a, b, rtol=2e-5, atol=2e-5, what="enc_rws_eta " + nm)
+        qp = enc_apg_z.probs(x.to(DEV), _t(g, "z_tau").to(DEV), _t(g, "z_mu").to(DEV))
+        _close(qp, og.enc_apg_z_probs(P["enc_apg_z"], xs, _t(g, "z_tau"), _t(g, "z_mu")), rtol=2e-5, atol=1e-7, what="q_probs")
+        # reference forward() contract: Trace nodes with value / dist / log_prob
+        q = enc_apg_eta(xs.to(DEV), z=_t(g, "eta_z").to(DEV), prior_ng=gen.prior_ng, sampled=False,
+                        tau_old=_t(g, "eta_tau").to(DEV), mu_old=_t(g, "eta_mu").to(DEV))
+        _close(q["precisions"].dist.concentration, _t(g, "eta_alpha"), rtol=2e-5, what="trace alpha")
+        _close(q["means"].dist.scale, _t(g, "eta_scale_q"), rtol=2e-5, what="trace scale")
+        assert q["means"].log_prob.shape == (S, x.shape[0], 3, 2)
+
+
+@pytest.mark.parametrize("block", ["decomposed", "joint"])
+def test_sweep_statistics_match_oracle(block):
+    """End-to-end: CPU and CUDA generators differ, so the comparison is statistical:
+    mean ESS and mean log-joint of the last sweep over many instances, within 5 standard errors."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B, sweeps = 40, 300, 4
+    torch.manual_seed(0)
+    P = og.make_params()
+    torch.manual_seed(1)
+    x = og.simulate(B)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    torch.manual_seed(2)
+    ref = og.apg_objective(P, og.make_prior(), x.repeat(S, 1, 1, 1), flags, sweeps, block, "systematic")
+    models = _models_from_params(P)
+    torch.manual_seed(3)
+    with torch.no_grad():
+        tr = O.apg_objective(models, x.to(DEV), flags, sweeps, block, Resampler("systematic", S, True, DEV))
+    for k in ("loss", "ess", "density"):
+        assert tuple(tr[k].shape) == tuple(ref[k].shape), k
+        assert bool(torch.isfinite(tr[k]).all()), k
+    for k in ("ess", "density"):
+        a = tr[k][-1].cpu().reshape(-1, B).mean(0) if k == "density" else tr[k][-1].cpu()
+        b = ref[k][-1].reshape(-1, B).mean(0) if k == "density" else ref[k][-1]
+        se = (a.var() / B + b.var() / B).sqrt()
+        assert abs(float(a.mean() - b.mean())) < 5 * float(se), (k, float(a.mean()), float(b.mean()), float(se))
+
+
+def test_full_size_sweep_runs():
+    """BASELINE.json configs[1] shape (S=1000, B=1024), 2 sweeps: finite, ESS in [1,S]."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B = 1000, 1024
+    torch.manual_seed(0)
+    models = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    flags = {"loss_required": False, "ess_required": True, "mode_required": False, "density_required": True}
+    with torch.no_grad():
+        tr = O.apg_objective(models, x, flags, 2, "decomposed", Resampler("systematic", S, True, DEV))
+    assert tuple(tr["ess"].shape) == (2, B) and tuple(tr["density"].shape) == (2, S, B)
+    assert bool(torch.isfinite(tr["density"]).all())
+    assert float(tr["ess"].min()) >= 1 - 1e-3 and float(tr["ess"].max()) <= S + 1e-1
