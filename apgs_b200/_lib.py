@@ -58,6 +58,10 @@ SIGNATURES = {
     "apgs_gmm_logw_z_f32": (_int, [_p, _p, _p, _p, _PR, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_logw_joint_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _p, _p, _p,
                                        _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_gmm_eta_posterior_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64,
+                                                _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "apgs_gmm_z_step_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p, _p,
+                                         _i64, _i64, _i64, _i64, _i64, _p, _p, _OUT, _p]),
 }
 
 _lib = None

@@ -11,45 +11,21 @@
 // gamma, x') are staged into shared memory by the bulk-copy engine (tile.cuh) while the threads
 // evaluate the small (K,D) terms; LANES lanes then split the N points of each particle.
 // fp32 arithmetic in the reference's operation order; N-sums are accumulated in fp64.
-#include "tile.cuh"
+#include "gmm_common.cuh"
 
 namespace apgs {
-
-#define LOG_SQRT_2PI_F 0.918938533204672741780329736406f
-#define FLT_EPS_F 1.1920928955078125e-07f
-
-__device__ __forceinline__ float xlogy_f(float a, float b) { return a == 0.f ? 0.f : __fmul_rn(a, logf(b)); }
-
-// torch/distributions/gamma.py:89-98
-__device__ __forceinline__ float gamma_lp(float v, float c, float r) {
-    float t = __fadd_rn(xlogy_f(c, r), xlogy_f(__fsub_rn(c, 1.f), v));
-    t = __fsub_rn(t, __fmul_rn(r, v));
-    return __fsub_rn(t, lgammaf(c));
-}
-// torch/distributions/normal.py:87-101
-__device__ __forceinline__ float normal_lp(float v, float loc, float scale) {
-    const float var = __fmul_rn(scale, scale);
-    const float d = __fsub_rn(v, loc);
-    float t = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var));
-    t = __fsub_rn(t, logf(scale));
-    return __fsub_rn(t, LOG_SQRT_2PI_F);
-}
-// 1 / sqrt(v)  as the reference writes it (models.py:34,74,147,177): IEEE sqrt then IEEE divide
-__device__ __forceinline__ float inv_sqrt_ref(float v) { return __fdiv_rn(1.f, __fsqrt_rn(v)); }
-
-template <int LANES, typename T>
-__device__ __forceinline__ T group_sum(T v) {
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // ============================================================================================
 // G1
 // ============================================================================================
 struct NssArgs {
-    const float* xp;      // (R, N, D)
+    const float* xp;      // (R, N, D)          (un-fused: outputs of the two Linear heads)
     const float* gamma;   // (R, N, K)
+    // fused heads (gamma == nullptr): gamma = softmax(Wg [x;z] + bg), xp = Wo [x;z] + bo computed in-kernel
+    const float* x;       // (B, N, D)
+    const float* z;       // (R, N, K) or nullptr (Enc_rws_eta: heads see x only)
+    const float *Wg, *bg, *Wo, *bo;   // (K, D[+K]), (K), (D, D[+K]), (D)
+    int B;
     const float *ra, *rb, *rm, *rn;   // prior alpha, beta, mu, nu  (K, D)
     float *oa, *ob, *om, *on;         // posterior (R, K, D)
     long long R;
@@ -60,74 +36,124 @@ template <int K, int D, int P, int LANES>
 __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
+    __shared__ float s_wg[K * (D + K) + K], s_wo[D * (D + K) + D];
     const int N = a.N;
-    float* s_g = reinterpret_cast<float*>(smem);                 // P*N*K
-    float* s_x = s_g + (size_t)P * N * K;                        // P*N*D
+    const bool fused = a.gamma == nullptr;
+    const bool has_z = a.z != nullptr;
+    const int IN = D + (has_z ? K : 0);                          // input width of the heads
+    float* s_g = reinterpret_cast<float*>(smem);                 // P*N*K  (gamma, or z when fused)
+    float* s_x = s_g + (size_t)P * N * K;                        // P*N*D  (xp; unused when fused)
     const long long r0 = (long long)blockIdx.x * P;
     const int rows = (int)min((long long)P, a.R - r0);
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
-    StageReq req[2] = {{s_g, a.gamma + r0 * N * K, (unsigned int)(rows * N * K * 4)},
-                       {s_x, a.xp + r0 * N * D, (unsigned int)(rows * N * D * 4)}};
+    StageReq req[2] = {{s_g, (fused ? (has_z ? a.z : a.x) : a.gamma) + ((fused && !has_z) ? 0 : r0 * N * K),
+                        (fused && !has_z) ? 0u : (unsigned int)(rows * N * K * 4)},
+                       {s_x, (fused ? a.x : a.xp) + (fused ? 0 : r0 * N * D), fused ? 0u : (unsigned int)(rows * N * D * 4)}};
     stage_issue(req, 2, &bar);
+    if (fused) {
+        for (int i = threadIdx.x; i < K * IN; i += blockDim.x) s_wg[i] = __ldg(a.Wg + i);
+        for (int i = threadIdx.x; i < K; i += blockDim.x) s_wg[K * (D + K) + i] = __ldg(a.bg + i);
+        for (int i = threadIdx.x; i < D * IN; i += blockDim.x) s_wo[i] = __ldg(a.Wo + i);
+        for (int i = threadIdx.x; i < D; i += blockDim.x) s_wo[D * (D + K) + i] = __ldg(a.bo + i);
+    }
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
     const bool valid = p < rows;
     stage_wait(&bar, 0);
 
-    double s1[K], s2[K][D], s3[K][D];
+    // per-lane partial sums (<= ceil(N/LANES) terms) in fp32, combined across lanes in fp64: fewer roundings than
+    // the reference's own fp32 reduction over all N terms, and no fp64 converts per point
+    float s1[K], s2[K][D], s3[K][D];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        s1[k] = 0.0;
+        s1[k] = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) { s2[k][d] = 0.0; s3[k][d] = 0.0; }
+        for (int d = 0; d < D; ++d) { s2[k][d] = 0.f; s3[k][d] = 0.f; }
     }
     if (valid) {
         const float* g = s_g + (size_t)p * N * K;
         const float* x = s_x + (size_t)p * N * D;
+        const float* xb = fused ? a.x + (size_t)((r0 + p) % a.B) * N * D : nullptr;
         for (int n = j; n < N; n += LANES) {
-            float xv[D];
+            float xv[D], gv[K];
+            if (!fused) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) xv[d] = x[n * D + d];
+                for (int d = 0; d < D; ++d) xv[d] = x[n * D + d];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float gk = g[n * K + k];
-                s1[k] += (double)gk;
+                for (int k = 0; k < K; ++k) gv[k] = g[n * K + k];
+            } else {
+                // the two Linear heads on cat(x_n, z_n) (models.py:17-22,56-65) and the softmax over k
+                float in[D + K];
+#pragma unroll
+                for (int d = 0; d < D; ++d) in[d] = __ldg(xb + n * D + d);
+#pragma unroll
+                for (int k = 0; k < K; ++k) in[D + k] = has_z ? g[n * K + k] : 0.f;
+                float lg[K], mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float acc = s_wg[K * (D + K) + k];
+#pragma unroll
+                    for (int i = 0; i < D + K; ++i) if (i < IN) acc = fmaf(s_wg[k * IN + i], in[i], acc);
+                    lg[k] = acc;
+                    mx = fmaxf(mx, acc);
+                }
+                float se = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { lg[k] = ex2_ftz((lg[k] - mx) * 1.4426950408889634f); se += lg[k]; }
+                const float rse = rcp_ftz(se);
+#pragma unroll
+                for (int k = 0; k < K; ++k) gv[k] = lg[k] * rse;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    const float gx = __fmul_rn(gk, xv[d]);                 // z_expand * ob_expand
-                    s2[k][d] += (double)gx;
-                    s3[k][d] += (double)__fmul_rn(gk, __fmul_rn(xv[d], xv[d]));   // z_expand * ob_expand**2
+                    float acc = s_wo[D * (D + K) + d];
+#pragma unroll
+                    for (int i = 0; i < D + K; ++i) if (i < IN) acc = fmaf(s_wo[d * IN + i], in[i], acc);
+                    xv[d] = acc;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float gk = gv[k];
+                s1[k] = __fadd_rn(s1[k], gk);
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    s2[k][d] = __fadd_rn(s2[k][d], __fmul_rn(gk, xv[d]));                      // z_expand * ob_expand
+                    s3[k][d] = __fadd_rn(s3[k][d], __fmul_rn(gk, __fmul_rn(xv[d], xv[d])));    // z_expand * ob_expand**2
                 }
             }
         }
     }
+    double t1[K], t2[K][D], t3[K][D];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        s1[k] = group_sum<LANES>(s1[k]);
+        t1[k] = group_sum<LANES>((double)s1[k]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) { s2[k][d] = group_sum<LANES>(s2[k][d]); s3[k][d] = group_sum<LANES>(s3[k][d]); }
+        for (int d = 0; d < D; ++d) {
+            t2[k][d] = group_sum<LANES>((double)s2[k][d]);
+            t3[k][d] = group_sum<LANES>((double)s3[k][d]);
+        }
     }
     if (!valid) return;
     // lanes 0..K*D-1 finish one (k,d) element each (kls_gmm.py:110-118, fp32, reference order)
     for (int e = j; e < K * D; e += LANES) {
         const int k = e / D, d = e % D;
-        float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        float n1 = 0.f, n2 = 0.f, n3 = 0.f;
 #pragma unroll
         for (int kk = 0; kk < K; ++kk)
 #pragma unroll
             for (int dd = 0; dd < D; ++dd)
-                if (kk == k && dd == d) { c1 = (float)s1[kk]; c2 = (float)s2[kk][dd]; c3 = (float)s3[kk][dd]; }
+                if (kk == k && dd == d) { n1 = (float)t1[kk]; n2 = (float)t2[kk][dd]; n3 = (float)t3[kk][dd]; }
         const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
-        const float cnt = (c1 == 0.f) ? 1.f : c1;                                   // Q1
-        const float x_bar = __fdiv_rn(c2, cnt);
+        const float cnt = (n1 == 0.f) ? 1.f : n1;                                   // Q1
+        const float x_bar = __fdiv_rn(n2, cnt);
         const float alpha = __fadd_rn(a0, __fdiv_rn(cnt, 2.f));
         const float nu = __fadd_rn(n0, cnt);
         const float cn = __fadd_rn(cnt, n0);
-        const float mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), c2), cn);
-        const float t1 = __fdiv_rn(__fsub_rn(c3, __fdiv_rn(__fmul_rn(c2, c2), cnt)), 2.f);
+        const float mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), n2), cn);
+        const float u1 = __fdiv_rn(__fsub_rn(n3, __fdiv_rn(__fmul_rn(n2, n2), cnt)), 2.f);
         const float dx = __fsub_rn(x_bar, n0);                                       // Q2: prior_nu
-        const float t2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
-        const float beta = __fadd_rn(__fadd_rn(b0, t1), t2);
+        const float u2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
+        const float beta = __fadd_rn(__fadd_rn(b0, u1), u2);
         const long long o = (r0 + p) * (K * D) + e;
         a.oa[o] = alpha; a.ob[o] = beta; a.om[o] = mu; a.on[o] = nu;
     }
@@ -234,7 +260,7 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
 
     stage_wait(&bar, 0);           // tile + tables visible
 
-    double A_llf = 0, A_llb = 0, A_lpzf = 0, A_lpzb = 0, A_lqzf = 0, A_lqzb = 0, A_loc = 0;
+    KahanF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;
     if (valid) {
         const float* zf = s_zf + (size_t)p * N * K;
         const float* zb = s_zb + (size_t)p * N * K;
@@ -269,8 +295,8 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
                     llb = __fadd_rn(llb, __fsub_rn(-__fmul_rn(__fmul_rn(db, db), tbp[1]), tbp[2]));
                 }
             }
-            A_llf += (double)llf;
-            A_llb += (double)llb;
+            A_llf.add(llf);
+            A_llb.add(llb);
             if (has_z) {
                 float sq = 0.f;
 #pragma unroll
@@ -279,40 +305,37 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
                 float lpf = logpi[0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) if (lf == k) lpf = logpi[k];
-                A_lqzf += (double)lqf;
-                A_lpzf += (double)lpf;
+                A_lqzf.add(lqf);
+                A_lpzf.add(lpf);
                 float lqb = 0.f, lpb = 0.f;
                 if (has_bwd) {
                     lqb = logf(fminf(fmaxf(__fdiv_rn(qq[n * K + lb], sq), FLT_EPS_F), 1.f - FLT_EPS_F));
                     lpb = logpi[0];
 #pragma unroll
                     for (int k = 1; k < K; ++k) if (lb == k) lpb = logpi[k];
-                    A_lqzb += (double)lqb;
-                    A_lpzb += (double)lpb;
+                    A_lqzb.add(lqb);
+                    A_lpzb.add(lpb);
                 }
                 if (step == STEP_Z) {
                     // objectives.py:206,215-216: (ll_f + log_p_f - log_q_f) - (ll_b + log_p_b - log_q_b)
                     const float wf = __fsub_rn(__fadd_rn(llf, lpf), lqf);
                     const float wb = __fsub_rn(__fadd_rn(llb, lpb), lqb);
                     const float loc = __fsub_rn(wf, wb);
-                    A_loc += (double)loc;
+                    A_loc.add(loc);
                     if (a.lw_local != nullptr) a.lw_local[r * N + n] = loc;
                     if (a.lq_local != nullptr) a.lq_local[r * N + n] = lqf;
                 }
             }
         }
     }
-    A_llf = group_sum<LANES>(A_llf);
-    A_llb = group_sum<LANES>(A_llb);
-    A_lpzf = group_sum<LANES>(A_lpzf);
-    A_lpzb = group_sum<LANES>(A_lpzb);
-    A_lqzf = group_sum<LANES>(A_lqzf);
-    A_lqzb = group_sum<LANES>(A_lqzb);
-    A_loc = group_sum<LANES>(A_loc);
+    const double S_llf = group_sum<LANES>(A_llf.value()), S_llb = group_sum<LANES>(A_llb.value());
+    const double S_lpzf = group_sum<LANES>(A_lpzf.value()), S_lpzb = group_sum<LANES>(A_lpzb.value());
+    const double S_lqzf = group_sum<LANES>(A_lqzf.value()), S_lqzb = group_sum<LANES>(A_lqzb.value());
+    const double S_loc = group_sum<LANES>(A_loc.value());
     if (!valid || j != 0) return;
 
-    const float ll_f = (float)A_llf, ll_b = (float)A_llb;
-    const float lpz_f = (float)A_lpzf, lpz_b = (float)A_lpzb, lqz_f = (float)A_lqzf, lqz_b = (float)A_lqzb;
+    const float ll_f = (float)S_llf, ll_b = (float)S_llb;
+    const float lpz_f = (float)S_lpzf, lpz_b = (float)S_lpzb, lqz_f = (float)S_lqzf, lqz_b = (float)S_lqzb;
     float lw, lwf = 0.f, lwb = 0.f, lqf, dens;
     if (step == STEP_ETA) {                 // objectives.py:172,179-180,194
         lwf = __fsub_rn(__fadd_rn(ll_f, lp_eta_f), lq_eta_f);
@@ -321,7 +344,7 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
         lqf = lq_eta_f;
         dens = lp_eta_f;
     } else if (step == STEP_Z) {            // objectives.py:216-218,226
-        lw = (float)A_loc;
+        lw = (float)S_loc;
         lwf = __fsub_rn(__fadd_rn(ll_f, lpz_f), lqz_f);
         lwb = __fsub_rn(__fadd_rn(ll_b, lpz_b), lqz_b);
         lqf = lqz_f;
@@ -351,7 +374,7 @@ constexpr int kP = 32, kLanes = 8;
 
 template <int K, int D>
 static int launch_nss(const NssArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)kP * a.N * (K + D) * 4;
+    const size_t smem = (size_t)kP * a.N * (K + D) * 4;       // (the fused variant only uses the first K part)
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_nss_posterior: N=%d too large for one tile", a.N);
     auto kern = k_gmm_nss_posterior<K, D, kP, kLanes>;
     if (smem > 48 * 1024)
@@ -408,8 +431,11 @@ extern "C" int apgs_gmm_nss_posterior_f32(const float* xp, const float* gamma, i
     if (!xp || !gamma || !prior_alpha || !prior_beta || !prior_mu || !prior_nu || !post_alpha || !post_beta ||
         !post_mu || !post_nu)
         return fail(APGS_E_BADARG, "gmm_nss_posterior: NULL pointer");
-    NssArgs a = {xp, gamma, prior_alpha, prior_beta, prior_mu, prior_nu, post_alpha, post_beta, post_mu, post_nu,
-                 (long long)S * B, (int)N};
+    NssArgs a = {};
+    a.xp = xp; a.gamma = gamma;
+    a.ra = prior_alpha; a.rb = prior_beta; a.rm = prior_mu; a.rn = prior_nu;
+    a.oa = post_alpha; a.ob = post_beta; a.om = post_mu; a.on = post_nu;
+    a.R = (long long)S * B; a.N = (int)N; a.B = (int)B;
     cudaStream_t st = (cudaStream_t)stream;
     APGS_KD_DISPATCH(K, D, launch_nss);
     return fail(APGS_E_UNSUPPORTED, "gmm_nss_posterior: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
@@ -481,4 +507,24 @@ extern "C" int apgs_gmm_logw_joint_f32(const float* x, const apgs_gmm_post_t* po
                                        void* stream) {
     return gmm_logw(STEP_JOINT, x, z, z_old, q_probs, post, prior, tau, mu, tau_old, mu_old, S, B, N, K, D, out,
                     stream);
+}
+
+extern "C" int apgs_gmm_eta_posterior_fused_f32(const float* x, const float* z, const float* Wg, const float* bg,
+                                                const float* Wo, const float* bo, int64_t S, int64_t B, int64_t N,
+                                                int64_t K, int64_t D, const float* prior_alpha, const float* prior_beta,
+                                                const float* prior_mu, const float* prior_nu, float* post_alpha,
+                                                float* post_beta, float* post_mu, float* post_nu, void* stream) {
+    if (int e = check_gmm_dims(S, B, N, K, D, "gmm_eta_posterior_fused")) return e;
+    if (!x || !Wg || !bg || !Wo || !bo || !prior_alpha || !prior_beta || !prior_mu || !prior_nu || !post_alpha ||
+        !post_beta || !post_mu || !post_nu)
+        return fail(APGS_E_BADARG, "gmm_eta_posterior_fused: NULL pointer");
+    NssArgs a = {};
+    a.x = x; a.z = z; a.Wg = Wg; a.bg = bg; a.Wo = Wo; a.bo = bo;
+    a.ra = prior_alpha; a.rb = prior_beta; a.rm = prior_mu; a.rn = prior_nu;
+    a.oa = post_alpha; a.ob = post_beta; a.om = post_mu; a.on = post_nu;
+    a.R = (long long)S * B; a.N = (int)N; a.B = (int)B;
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_nss);
+    return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_fused: (K=%lld, D=%lld) not instantiated", (long long)K,
+                (long long)D);
 }

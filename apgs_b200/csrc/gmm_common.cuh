@@ -1,0 +1,71 @@
+// Device helpers shared by the GMM kernels: torch.distributions log-densities restated in fp32
+// with the library's operation order (no FMA contraction on the reference-order paths).
+#pragma once
+#include "tile.cuh"
+
+namespace apgs {
+
+#define LOG_SQRT_2PI_F 0.918938533204672741780329736406f
+#define FLT_EPS_F 1.1920928955078125e-07f
+
+__device__ __forceinline__ float xlogy_f(float a, float b) { return a == 0.f ? 0.f : __fmul_rn(a, logf(b)); }
+
+// torch/distributions/gamma.py:89-98
+__device__ __forceinline__ float gamma_lp(float v, float c, float r) {
+    float t = __fadd_rn(xlogy_f(c, r), xlogy_f(__fsub_rn(c, 1.f), v));
+    t = __fsub_rn(t, __fmul_rn(r, v));
+    return __fsub_rn(t, lgammaf(c));
+}
+// torch/distributions/normal.py:87-101
+__device__ __forceinline__ float normal_lp(float v, float loc, float scale) {
+    const float var = __fmul_rn(scale, scale);
+    const float d = __fsub_rn(v, loc);
+    float t = __fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var));
+    t = __fsub_rn(t, logf(scale));
+    return __fsub_rn(t, LOG_SQRT_2PI_F);
+}
+// 1 / sqrt(v)  as the reference writes it (models.py:34,74,147,177): IEEE sqrt then IEEE divide
+__device__ __forceinline__ float inv_sqrt_ref(float v) { return __fdiv_rn(1.f, __fsqrt_rn(v)); }
+
+template <int LANES, typename T>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+
+// Compensated fp32 accumulation (Kahan): a lane adds <= ceil(N/LANES) terms; the pair (sum, comp) is
+// widened to fp64 only when lanes are combined.  No FMA contraction may touch these four operations.
+__device__ __forceinline__ void kahan_add(float& s, float& c, float v) {
+    const float y = __fsub_rn(v, c);
+    const float t = __fadd_rn(s, y);
+    c = __fsub_rn(__fsub_rn(t, s), y);
+    s = t;
+}
+struct KahanF {
+    float s, c;
+    __device__ __forceinline__ KahanF() : s(0.f), c(0.f) {}
+    __device__ __forceinline__ void add(float v) { kahan_add(s, c, v); }
+    __device__ __forceinline__ double value() const { return (double)s - (double)c; }
+};
+
+// tanh with ~1e-7 absolute error from a PRE-SCALED argument a = 2*log2(e)*x:
+//   tanh(x) = 1 - 2 / (2^a + 1)      -> MUFU.EX2, FADD, MUFU.RCP, FFMA  (flush-to-zero forms: no denormal
+// fix-up code; 2^a underflowing to 0 gives -1 and overflowing to +inf gives +1, the correct saturations)
+#define TANH_PRESCALE 2.885390081777926814719849f
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_prescaled(float a) {
+    return fmaf(rcp_ftz(ex2_ftz(a) + 1.f), -2.f, 1.f);
+}
+
+}  // namespace apgs

@@ -84,6 +84,30 @@ __device__ __forceinline__ void stage_issue(const StageReq (&req)[NREQ], int nre
         }
     }
 }
+// shared -> global bulk store of a finished tile.  Called by ALL threads after they wrote `src_smem`
+// with ordinary stores; one thread hands the slice to the bulk-copy engine (UBLKCP) when it is
+// 16-byte sized/aligned, otherwise the CTA stores it cooperatively.
+__device__ __forceinline__ void tile_store(void* dst_gmem, const void* src_smem, unsigned int bytes) {
+    const bool bulk = ((bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dst_gmem) & 15u) == 0);
+    if (bulk) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+        __syncthreads();
+        if (threadIdx.x == 0 && bytes > 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                         "r"(smem_u32(src_smem)), "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released at exit
+        }
+    } else {
+        __syncthreads();
+        const unsigned int nw = bytes >> 2;
+        const float* s = reinterpret_cast<const float*>(src_smem);
+        float* d = reinterpret_cast<float*>(dst_gmem);
+        for (unsigned int j = threadIdx.x; j < nw; j += blockDim.x) d[j] = s[j];
+    }
+}
+
 __device__ __forceinline__ void stage_wait(unsigned long long* bar, unsigned int parity) {
     mbar_wait(bar, parity);
     __syncthreads();                                  // also publishes the cooperative copies

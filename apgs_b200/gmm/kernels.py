@@ -130,3 +130,64 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
                                           ptr(mu_old), ptr(q_probs), ptr(z), ptr(z_old), S, B, N, K, D,
                                           C.byref(o), _stream()), "apgs_gmm_logw_joint_f32")
     return w
+
+
+def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
+                 parts=False, local=False):
+    """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
+    mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights)."""
+    lib = _lib.load()
+    x = _x3(x)
+    tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
+    S, B, K, D = tau.shape
+    N = x.shape[-2]
+    W1, b1, W2, b2 = [_req(v, "mlp weight") for v in mlp]
+    H = W1.shape[0]
+    if tuple(W1.shape) != (H, 3 * D) or W2.numel() != H or b1.numel() != H or b2.numel() != 1:
+        raise ValueError("unexpected Enc_apg_z weight shapes")
+    dev = tau.device
+    if z_old is not None:
+        z_old = _req(z_old, "z_old", ndim=4)
+    if z_forced is not None:
+        z_forced = _req(z_forced, "z_forced", ndim=4)
+    elif uniforms is None:
+        uniforms = torch.rand(S, B, N, device=dev)
+    if uniforms is not None:
+        uniforms = _req(uniforms, "uniforms", ndim=3)
+    z_new = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
+    q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
+    rs, rk = _prior_struct(prior)
+    w, o = _outs(S, B, N, dev, parts, local)
+    nbytes = 4 * S * B * (N * K * (2 if z_old is not None else 1) + N + 2 * K * D + 3 + (N * K if want_q else 0))
+    with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes):
+        check(lib.apgs_gmm_z_step_fused_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
+                                            C.byref(rs), ptr(z_old), ptr(z_forced), ptr(uniforms), S, B, N, K, D,
+                                            ptr(z_new), ptr(q), C.byref(o), _stream()), "apgs_gmm_z_step_fused_f32")
+    return z_new, q, w
+
+
+def eta_posterior_fused(x, z, heads, prior):
+    """N1b+G1: Linear heads of Enc_apg_eta (z given) / Enc_rws_eta (z None) + softmax + NSS posterior.
+    heads = (Wg, bg, Wo, bo).  Returns alpha, beta, mu, nu of shape (S,B,K,D) ((1,B,K,D) when z is None)."""
+    lib = _lib.load()
+    x = _x3(x)
+    B, N, D = x.shape
+    Wg, bg, Wo, bo = [_req(v, "head weight") for v in heads]
+    K = Wg.shape[0]
+    if z is not None:
+        z = _req(z, "z", ndim=4)
+        S = z.shape[0]
+        if tuple(z.shape) != (S, B, N, K):
+            raise ValueError("z has shape %s, expected (S,%d,%d,%d)" % (tuple(z.shape), B, N, K))
+    else:
+        S = 1
+    IN = D + (K if z is not None else 0)
+    if tuple(Wg.shape) != (K, IN) or tuple(Wo.shape) != (D, IN):
+        raise ValueError("unexpected head weight shapes %s %s" % (tuple(Wg.shape), tuple(Wo.shape)))
+    pr = [_req(getattr(prior, "prior_" + n), "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
+    outs = [torch.empty(S, B, K, D, dtype=torch.float32, device=x.device) for _ in range(4)]
+    with torch.cuda.device(x.device), _call("gmm_eta_posterior_fused", 1, 4 * S * B * (N * K + 4 * K * D)):
+        check(lib.apgs_gmm_eta_posterior_fused_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
+                                                   *[ptr(v) for v in pr], *[ptr(v) for v in outs], _stream()),
+              "apgs_gmm_eta_posterior_fused_f32")
+    return tuple(outs)

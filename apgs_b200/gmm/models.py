@@ -53,12 +53,18 @@ class Enc_rws_eta(nn.Module):
         self.gamma = nn.Sequential(nn.Linear(D, K), nn.Softmax(-1))
         self.ob = nn.Sequential(nn.Linear(D, D))
 
+    fused = True
+
     def params(self, ob, prior_ng, S=None):
         x = _x_inst(ob)
         S = ob.shape[0] if ob.dim() == 4 else S
         # the heads depend on the data only: evaluate once per instance, not once per particle
-        xp, gam = self.ob(x), self.gamma(x)                               # (B,N,D), (B,N,K)
-        post = kernels.nss_posterior(xp.unsqueeze(0), gam.unsqueeze(0), _PriorNG(prior_ng))   # (1,B,K,D)
+        if self.fused and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            post = kernels.eta_posterior_fused(x, None, (self.gamma[0].weight, self.gamma[0].bias,
+                                                         self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng))
+        else:
+            xp, gam = self.ob(x), self.gamma(x)                               # (B,N,D), (B,N,K)
+            post = kernels.nss_posterior(xp.unsqueeze(0), gam.unsqueeze(0), _PriorNG(prior_ng))   # (1,B,K,D)
         return tuple(v.expand(S, -1, -1, -1).contiguous() for v in post)
 
     def forward(self, ob, prior_ng, sampled=True, tau_old=None, mu_old=None):
@@ -84,7 +90,12 @@ class Enc_apg_eta(nn.Module):
         xp = F.linear(z, Wo[:, D:]) + F.linear(x, Wo[:, :D], bo)
         return xp, gam
 
+    fused = True
+
     def params(self, ob, z, prior_ng):
+        if self.fused and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            return kernels.eta_posterior_fused(ob, z, (self.gamma[0].weight, self.gamma[0].bias,
+                                                       self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng))
         xp, gam = self.heads(ob, z)
         return kernels.nss_posterior(xp, gam, _PriorNG(prior_ng))
 
@@ -95,6 +106,7 @@ class Enc_apg_eta(nn.Module):
 class Enc_apg_z(nn.Module):
     """Conditional proposal of the assignments z, apgs/gmm/models.py:91-115."""
     chunk_elems = 1 << 28          # bound on the (s,b,n,k,h) activation held at once (floats)
+    fused = True                   # evaluation path: MLP + softmax + draw fused with the weights (csrc/gmm_fused.cu)
 
     def __init__(self, K, D, num_hidden):
         super(self.__class__, self).__init__()
@@ -118,6 +130,20 @@ class Enc_apg_z(nn.Module):
             outs.append(F.linear(h, W2, b2).squeeze(-1))
         logits = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return F.softmax(logits, -1)
+
+    def mlp(self):
+        return (self.pi_log_prob[0].weight, self.pi_log_prob[0].bias, self.pi_log_prob[2].weight, self.pi_log_prob[2].bias)
+
+    def can_fuse(self, need_grad=False):
+        """the fused kernel is forward-only: use it unless gradients w.r.t. the MLP are needed."""
+        if not self.fused:
+            return False
+        return not (need_grad and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
+
+    def sample_fused(self, ob, tau, mu, generative, want_q=True):
+        """z ~ q(z | x, tau, mu) and q_probs from the fused kernel (sample-only mode)."""
+        z, q_probs, _ = kernels.z_step_fused(ob, tau, mu, self.mlp(), generative, want_q=want_q)
+        return z, q_probs
 
     def forward(self, ob, tau, mu, sampled=True, z_old=None):
         q = Trace()

@@ -26,8 +26,10 @@ from . import kernels
 
 def _sample_eta(post):
     q_alpha, q_beta, q_mu, q_nu = post
-    tau = Gamma(q_alpha, q_beta).sample()
-    mu = Normal(q_mu, 1. / (q_nu * tau).sqrt()).sample()
+    # validate_args=False: the default argument validation calls .item() on the device (a host sync per
+    # distribution); it carries no arithmetic
+    tau = Gamma(q_alpha, q_beta, validate_args=False).sample()
+    mu = Normal(q_mu, 1. / (q_nu * tau).sqrt(), validate_args=False).sample()
     return tau, mu
 
 
@@ -79,8 +81,11 @@ def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
     """One-shot for eta and z, like a normal RWS (objectives.py:74-110)."""
     post = enc_rws_eta.params(x, generative.prior_ng)
     tau, mu = _sample_eta(post)
-    q_probs = enc_rws_z.probs(x, tau, mu)
-    z = cat(q_probs).sample()
+    if enc_rws_z.can_fuse(result_flags['loss_required']):
+        z, q_probs = enc_rws_z.sample_fused(x, tau, mu, generative)
+    else:
+        q_probs = enc_rws_z.probs(x, tau, mu)
+        z = cat(q_probs, validate_args=False).sample()
     w = kernels.logw_oneshot(x, post, generative, tau, mu, q_probs, z)
     _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
     if result_flags['mode_required']:
@@ -94,8 +99,11 @@ def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_o
     """Jointly update all the variables (objectives.py:112-158)."""
     post = enc_apg_eta.params(x, z_old, generative.prior_ng)
     tau, mu = _sample_eta(post)
-    q_probs = enc_apg_z.probs(x, tau, mu)
-    z = cat(q_probs).sample()
+    if enc_apg_z.can_fuse(result_flags['loss_required']):
+        z, q_probs = enc_apg_z.sample_fused(x, tau, mu, generative)
+    else:
+        q_probs = enc_apg_z.probs(x, tau, mu)
+        z = cat(q_probs, validate_args=False).sample()
     w = kernels.logw_joint(x, post, generative, tau, mu, tau_old, mu_old, q_probs, z, z_old)
     _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
     if result_flags['mode_required']:
@@ -120,10 +128,15 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
 
 def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
     """Given the current samples of eta, update the assignments z (objectives.py:197-227)."""
-    q_probs = enc_apg_z.probs(x, tau, mu)
-    z = cat(q_probs).sample()
     need_local = bool(result_flags['loss_required'])
-    w = kernels.logw_z(x, tau, mu, q_probs, generative, z, z_old, local=need_local)
+    if enc_apg_z.can_fuse(result_flags['loss_required']):
+        # N1: MLP + softmax + draw + weights in one kernel; q_probs only materialised when asked for
+        z, q_probs, w = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
+                                             want_q=bool(result_flags['mode_required']), local=need_local)
+    else:
+        q_probs = enc_apg_z.probs(x, tau, mu)
+        z = cat(q_probs, validate_args=False).sample()
+        w = kernels.logw_z(x, tau, mu, q_probs, generative, z, z_old, local=need_local)
     if result_flags['loss_required']:
         w_local, _ = ops.local_weight_stats(w.log_w_local, want_w=True, want_sum=False)
         loss = (w_local * (-w.log_q_local)).sum(0).sum(-1).mean()

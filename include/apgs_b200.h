@@ -181,6 +181,33 @@ APGS_API int apgs_gmm_logw_joint_f32(const float* x, const apgs_gmm_post_t* post
                             int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
                             const apgs_gmm_out_t* out, void* stream);
 
+/* N1+G3  fused z step: Enc_apg_z.forward (apgs/gmm/models.py:102-115: per-(n,k)
+ *     MLP 3D -> H -> 1 with tanh, softmax over k) + categorical draw by inverse CDF from the supplied
+ *     uniforms + the z-step weight of G3, in one pass (no (S,B,N,K,H) activations, no q_probs round trip).
+ *   W1 (H,3D) b1 (H) W2 (H) b2 (1): pi_log_prob.{0,2}.{weight,bias} of the reference module.
+ *   z_old    (S,B,N,K) one-hot or NULL (NULL: sample-only mode, used by the one-shot / joint steps).
+ *   z_forced (S,B,N,K) one-hot or NULL (teacher forcing for parity tests: use instead of sampling).
+ *   uniforms (S,B,N) fp32 in [0,1) (required unless z_forced): z_n = #{k : cdf_k <= u_n * sum_k q_nk}.
+ *   z_new    (S,B,N,K) out;  q_probs (S,B,N,K) out or NULL;  out: as G3 (may be NULL).             */
+APGS_API int apgs_gmm_z_step_fused_f32(const float* x, const float* tau, const float* mu,
+                              const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
+                              const apgs_gmm_prior_t* prior, const float* z_old, const float* z_forced,
+                              const float* uniforms,
+                              int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              float* z_new, float* q_probs, const apgs_gmm_out_t* out, void* stream);
+
+/* N1b+G1  fused eta heads: the two Linear layers of Enc_apg_eta / Enc_rws_eta (apgs/gmm/models.py:17-22,56-65),
+ *     the softmax over k and G1 in one pass over z -- cat(ob, z), gamma and x' never touch HBM.
+ *   Wg (K, D+K) bg (K) Wo (D, D+K) bo (D) = gamma.0.{weight,bias}, ob.0.{weight,bias};
+ *   z (S,B,N,K) or NULL (Enc_rws_eta: the heads see x only; then Wg is (K,D), Wo (D,D)).        */
+APGS_API int apgs_gmm_eta_posterior_fused_f32(const float* x, const float* z,
+                                     const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                     int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                     const float* prior_alpha, const float* prior_beta,
+                                     const float* prior_mu, const float* prior_nu,
+                                     float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
+                                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

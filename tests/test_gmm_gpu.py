@@ -250,6 +250,14 @@ def test_encoder_parameters_match_oracle(golden):
         ref = og.enc_rws_eta_posterior(P["enc_rws_eta"], xs, prior)
         for a, b, nm in zip(post, ref, ("alpha", "beta", "mu", "nu")):
             _close(a, b, rtol=2e-5, atol=2e-5, what="enc_rws_eta " + nm)
+        for fused in (True, False):          # fused heads (csrc) and the PyTorch Linear heads give the same parameters
+            enc_apg_eta.fused = enc_rws_eta.fused = fused
+            post = enc_apg_eta.params(xs.to(DEV), _t(g, "eta_z").to(DEV), gen.prior_ng)
+            for a, b, nm in zip(post, og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, _t(g, "eta_z"), prior), "abmn"):
+                _close(a, b, rtol=2e-5, atol=2e-5, what="enc_apg_eta fused=%s %s" % (fused, nm))
+            post = enc_rws_eta.params(x.to(DEV), gen.prior_ng, S=S)
+            for a, b, nm in zip(post, og.enc_rws_eta_posterior(P["enc_rws_eta"], xs, prior), "abmn"):
+                _close(a, b, rtol=2e-5, atol=2e-5, what="enc_rws_eta fused=%s %s" % (fused, nm))
         qp = enc_apg_z.probs(x.to(DEV), _t(g, "z_tau").to(DEV), _t(g, "z_mu").to(DEV))
         _close(qp, og.enc_apg_z_probs(P["enc_apg_z"], xs, _t(g, "z_tau"), _t(g, "z_mu")), rtol=2e-5, atol=1e-7, what="q_probs")
         # reference forward() contract: Trace nodes with value / dist / log_prob
@@ -303,3 +311,80 @@ def test_full_size_sweep_runs():
     assert tuple(tr["ess"].shape) == (2, B) and tuple(tr["density"].shape) == (2, S, B)
     assert bool(torch.isfinite(tr["density"]).all())
     assert float(tr["ess"].min()) >= 1 - 1e-3 and float(tr["ess"].max()) <= S + 1e-1
+
+
+# ------------------------------------------------------------------ N1: fused z step
+def _mlp(P):
+    p = P["enc_apg_z"]
+    return [p[k].to(DEV) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+
+
+def test_N1_fused_z_step_teacher_forced_vs_reference_golden(golden):
+    """the fused kernel (MLP + softmax + weights) given the reference's own draw z_new."""
+    from apgs_b200.gmm import kernels
+    g = golden("gmm")
+    P, prior = _params(g), og.make_prior()
+    S = g["z_old"].shape[0]
+    x = _t(g, "x")
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    q_ref = og.enc_apg_z_probs(P["enc_apg_z"], xs, _t(g, "z_tau"), _t(g, "z_mu"))
+    ref = og.z_step_weights(xs, _t(g, "z_tau"), _t(g, "z_mu"), q_ref, prior, _t(g, "z_new"), _t(g, "z_old"), parts=True)
+    z_new, q, w = kernels.z_step_fused(x.to(DEV), _t(g, "z_tau").to(DEV), _t(g, "z_mu").to(DEV), _mlp(P), _Gen(),
+                                       z_old=_t(g, "z_old").to(DEV), z_forced=_t(g, "z_new").to(DEV),
+                                       want_q=True, parts=True, local=True)
+    assert torch.equal(z_new.cpu(), _t(g, "z_new"))
+    _close(q, q_ref, rtol=2e-5, atol=1e-7, what="q_probs")
+    _close(w.log_w_f, ref[4], what="sum log_w_f")
+    _close(w.log_w_b, ref[5], what="sum log_w_b")
+    _close(w.density, _t(g, "z_density")[0], what="density")
+    _close(w.log_q_local, ref[2], rtol=2e-5, atol=2e-6, what="log_q_local")
+    _close(w.log_w_local, ref[0], rtol=RT, atol=3e-5, what="log_w_local")
+    _close(w.log_w, _t(g, "z_log_w"), rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="log_w")
+
+
+@pytest.mark.parametrize("S,B,N,K,D,H", [(6, 5, 60, 3, 2, 32), (37, 3, 41, 4, 2, 16), (33, 2, 9, 3, 3, 48)])
+def test_N1_fused_sampling_is_inverse_cdf_of_oracle_probs(S, B, N, K, D, H):
+    from apgs_b200.gmm import kernels
+    torch.manual_seed(S + H)
+    P, prior = og.make_params(K, D, H), og.make_prior(K, D)
+    x = torch.randn(B, N, D) * 2
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    tau, mu = torch.rand(S, B, K, D) * 3 + 0.1, torch.randn(S, B, K, D) * 2
+    u = torch.rand(S, B, N)
+    q_ref = og.enc_apg_z_probs(P["enc_apg_z"], xs, tau, mu)
+    z_new, q, _ = kernels.z_step_fused(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), _Gen(K, D), uniforms=u.to(DEV), want_q=True)
+    _close(q, q_ref, rtol=2e-5, atol=1e-7, what="q_probs")
+    z_new = z_new.cpu()
+    assert bool(((z_new == 0) | (z_new == 1)).all()) and bool((z_new.sum(-1) == 1).all()), "one-hot"
+    cdf = torch.cumsum(q_ref, -1)
+    lab_ref = (u.unsqueeze(-1) * cdf[..., -1:] >= cdf[..., :-1]).sum(-1)
+    bad = (z_new.argmax(-1) != lab_ref)
+    # a label may differ only where u sits on a CDF boundary (q differs by ~1e-6 relative)
+    assert float(bad.float().mean()) <= 1e-3
+    gap = (u.unsqueeze(-1) * cdf[..., -1:] - cdf[..., :-1]).abs().min(-1).values
+    assert bool((gap[bad] < 1e-5).all())
+
+
+def test_sweep_statistics_torch_encoder_path():
+    """the un-fused Enc_apg_z path (PyTorch MLP + torch categorical draw) stays available and agrees statistically."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B, sweeps = 40, 300, 3
+    torch.manual_seed(0)
+    P = og.make_params()
+    torch.manual_seed(1)
+    x = og.simulate(B)
+    flags = {"loss_required": False, "ess_required": True, "mode_required": True, "density_required": True}
+    out = {}
+    for fused in (True, False):
+        models = _models_from_params(P)
+        models[0].fused = models[1].fused = models[2].fused = fused
+        torch.manual_seed(3)
+        with torch.no_grad():
+            out[fused] = O.apg_objective(models, x.to(DEV), flags, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
+    for k in ("ess", "density"):
+        a = out[True][k][-1].reshape(-1, B).mean(0).cpu()
+        b = out[False][k][-1].reshape(-1, B).mean(0).cpu()
+        se = (a.var() / B + b.var() / B).sqrt()
+        assert abs(float(a.mean() - b.mean())) < 5 * float(se), k
+    assert tuple(out[True]["E_z"].shape) == tuple(out[False]["E_z"].shape)
