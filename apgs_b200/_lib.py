@@ -58,6 +58,11 @@ SIGNATURES = {
     "apgs_gmm_logw_z_f32": (_int, [_p, _p, _p, _p, _PR, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_logw_joint_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _p, _p, _p,
                                        _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_bmnist_crop_f32": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_bmnist_paste_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_bmnist_paste_ll_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "apgs_bmnist_logw_where_f32": (_int, [_p] * 11 + [_i64] * 4 + [_p] * 6),
+    "apgs_bmnist_logw_what_f32": (_int, [_p] * 8 + [_i64] * 5 + [_p] * 5),
     "apgs_gmm_eta_posterior_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64,
                                                 _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "apgs_gmm_z_step_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p, _p,

@@ -1,0 +1,48 @@
+"""Drop-in for apgs/bmnist/affine_transformer.py:24-65 on the sm_100a crop / paste kernels.
+
+Same constructor and methods:
+    Affine_Transformer(frame_pixels, digit_pixels, CUDA, DEVICE)
+    .digit_to_frame(digit[S,B,K,DP,DP], z_where[S,B,T,K,2]) -> [S,B,T,K,FP,FP]
+    .frame_to_digit(frames[S,B,T,FP,FP], z_where[S,B,T,K,2]) -> [S,B,T,K,DP,DP]
+Nearest sampling with align_corners=True, exactly as the reference; z_where is not modified.
+`frames` may also be (B,T,FP,FP) or carry a stride-0 particle axis.
+"""
+import torch
+
+from .. import _lib
+from . import kernels
+
+
+class Affine_Transformer():
+    def __init__(self, frame_pixels, digit_pixels, CUDA=True, DEVICE=None):
+        super().__init__()
+        if not CUDA:
+            raise _lib.ApgsError("apgs_b200 Affine_Transformer runs on CUDA only (no CPU fallback)")
+        _lib.load()
+        self.digit_pixels = digit_pixels
+        self.frame_pixels = frame_pixels
+        self.translation_dtof = (self.frame_pixels - self.digit_pixels) / self.digit_pixels
+        self.translation_ftod = (self.frame_pixels - self.digit_pixels) / self.frame_pixels
+        self.scale_dtof = torch.FloatTensor([[self.frame_pixels / self.digit_pixels, 0], [0, self.frame_pixels / self.digit_pixels]])
+        self.scale_ftod = torch.FloatTensor([[self.digit_pixels / self.frame_pixels, 0], [0, self.digit_pixels / self.frame_pixels]])
+        dev = torch.device("cuda", torch.cuda.current_device()) if DEVICE is None else torch.device(DEVICE)
+        self.device = dev
+        # affine_grid's base axes, computed by the same CPU linspace the reference's affine_grid uses
+        self.lin_fp = torch.linspace(-1, 1, frame_pixels).to(dev)
+        self.lin_dp = torch.linspace(-1, 1, digit_pixels).to(dev)
+        self.scale_dtof = self.scale_dtof.to(dev)
+        self.scale_ftod = self.scale_ftod.to(dev)
+
+    def digit_to_frame(self, digit, z_where):
+        """transfer the digits to the frame
+        [digit: S * B * K * DP * DP, z_where: S * B * T * K * 2 ===> frame: S * B * T * K * FP * FP]"""
+        return kernels.paste(digit, z_where, self.lin_fp, self.frame_pixels)
+
+    def frame_to_digit(self, frames, z_where):
+        """transfer the frames to the digits
+        [frame: S * B * T * FP * FP, z_where: S * B * T * K * 2 ===> digit: S * B * T * K * DP * DP]"""
+        return kernels.crop(frames, z_where, self.lin_dp, self.digit_pixels)
+
+    # fused tail of Dec_digit.forward (apgs/bmnist/models.py:148-154) -- the reference has no such entry
+    def reconstruct_ll(self, digit, z_where, frames, want_recon=False):
+        return kernels.paste_ll(digit, z_where, frames, self.lin_fp, want_recon=want_recon)

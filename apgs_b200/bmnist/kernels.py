@@ -1,0 +1,110 @@
+"""Host wrappers of the bouncing-MNIST kernels (apgs_b200/csrc/bmnist.cu) -- SURVEY.md B1-B4."""
+import torch
+
+from .. import _lib
+from .._lib import check, ptr
+from ..ops import _call, _req, _stream
+
+
+def _frames_view(frames, S):
+    """frames as (S,B,T,FP,FP) with arbitrary (possibly zero) strides over s, b, t and dense pixels."""
+    if frames.dim() == 4:
+        frames = frames.unsqueeze(0).expand(S, -1, -1, -1, -1)
+    if not frames.is_cuda or frames.dtype != torch.float32:
+        raise _lib.ApgsError("frames must be a float32 CUDA tensor (no CPU fallback)")
+    if frames.stride(-1) != 1 or frames.stride(-2) != frames.shape[-1]:
+        frames = frames.contiguous()
+    return frames.detach()
+
+
+def crop(frames, z_where, lin_dp, DP):
+    """B1: (S,B,T,FP,FP) x (S,B,T,K,2) -> (S,B,T,K,DP,DP)."""
+    lib = _lib.load()
+    z = _req(z_where, "z_where", ndim=5)
+    S, B, T, K, _ = z.shape
+    fr = _frames_view(frames, S)
+    FP = fr.shape[-1]
+    out = torch.empty(S, B, T, K, DP, DP, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device), _call("bmnist_crop", 1, 8 * S * B * T * K * DP * DP):
+        check(lib.apgs_bmnist_crop_f32(ptr(fr), fr.stride(0), fr.stride(1), fr.stride(2), ptr(z), ptr(lin_dp),
+                                       S, B, T, K, FP, DP, ptr(out), _stream()), "apgs_bmnist_crop_f32")
+    return out
+
+
+def paste(digits, z_where, lin_fp, FP):
+    """B2: (S,B,K,DP,DP) x (S,B,T,K,2) -> (S,B,T,K,FP,FP)."""
+    lib = _lib.load()
+    z = _req(z_where, "z_where", ndim=5)
+    d = _req(digits, "digit", ndim=5)
+    S, B, T, K, _ = z.shape
+    DP = d.shape[-1]
+    out = torch.empty(S, B, T, K, FP, FP, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device), _call("bmnist_paste", 1, 4 * S * B * (K * DP * DP + T * K * FP * FP)):
+        check(lib.apgs_bmnist_paste_f32(ptr(d), ptr(z), ptr(lin_fp), S, B, T, K, FP, DP, ptr(out), _stream()),
+              "apgs_bmnist_paste_f32")
+    return out
+
+
+def paste_ll(digits, z_where, frames, lin_fp, want_recon=False):
+    """B2+B3: -> ll (S,B,T), recon (S,B,T,FP,FP) or None."""
+    lib = _lib.load()
+    z = _req(z_where, "z_where", ndim=5)
+    d = _req(digits, "digit", ndim=5)
+    S, B, T, K, _ = z.shape
+    DP = d.shape[-1]
+    fr = _frames_view(frames, S)
+    FP = fr.shape[-1]
+    ll = torch.empty(S, B, T, dtype=torch.float32, device=z.device)
+    recon = torch.empty(S, B, T, FP, FP, dtype=torch.float32, device=z.device) if want_recon else None
+    uniq = (1 if fr.stride(0) == 0 else S)
+    nbytes = 4 * (uniq * B * T * FP * FP + S * B * K * DP * DP + S * B * T * (1 + (FP * FP if want_recon else 0)))
+    with torch.cuda.device(z.device), _call("bmnist_paste_ll", 1, nbytes):
+        check(lib.apgs_bmnist_paste_ll_f32(ptr(d), ptr(z), ptr(lin_fp), ptr(fr), fr.stride(0), fr.stride(1), fr.stride(2),
+                                           S, B, T, K, FP, DP, ptr(ll), ptr(recon), _stream()), "apgs_bmnist_paste_ll_f32")
+    return ll, recon
+
+
+def logw_where(q_mean, q_std, z_new, z_prev, z_old, z_old_prev, dec_coor, ll_f=None, ll_b=None, want_w=True,
+               want_b=False):
+    """B4a: per-frame z_where log-densities and weight -> (log_w or None, log_q_f, log_p_f), each (S,B);
+    with want_b also (log_q_b, log_p_b)."""
+    lib = _lib.load()
+    q_mean, q_std, z_new = _req(q_mean, "q_mean", ndim=4), _req(q_std, "q_std", ndim=4), _req(z_new, "z_new", ndim=4)
+    S, B, K, D = z_new.shape
+    opt = [None if v is None else _req(v, "z", ndim=4) for v in (z_prev, z_old, z_old_prev)]
+    lls = [None if v is None else _req(v, "ll", ndim=2) for v in (ll_f, ll_b)]
+    pr = [_req(getattr(dec_coor, n), n) for n in ("prior_mu0", "prior_Sigma0", "prior_Sigmat")]
+    dev = z_new.device
+    lw = torch.empty(S, B, dtype=torch.float32, device=dev) if want_w else None
+    lq = torch.empty(S, B, dtype=torch.float32, device=dev)
+    lp = torch.empty(S, B, dtype=torch.float32, device=dev)
+    lqb = torch.empty(S, B, dtype=torch.float32, device=dev) if want_b else None
+    lpb = torch.empty(S, B, dtype=torch.float32, device=dev) if want_b else None
+    with torch.cuda.device(dev), _call("bmnist_logw_where", 1, 4 * S * B * (6 * K * D + 5)):
+        check(lib.apgs_bmnist_logw_where_f32(ptr(q_mean), ptr(q_std), ptr(z_new), *[ptr(v) for v in opt],
+                                             *[ptr(v) for v in pr], *[ptr(v) for v in lls], S, B, K, D,
+                                             ptr(lw), ptr(lq), ptr(lp), ptr(lqb), ptr(lpb), _stream()),
+              "apgs_bmnist_logw_where_f32")
+    if want_b:
+        return lw, lq, lp, lqb, lpb
+    return lw, lq, lp
+
+
+def logw_what(q_mu, q_std, z_new, z_old, ll_f, ll_b=None, extra_log_p=None, extra_log_q=None):
+    """B4b: z_what step / one-shot -> (log_w, log_q_f, density, ll_sum), each (S,B)."""
+    lib = _lib.load()
+    q_mu, q_std, z_new = _req(q_mu, "q_mu", ndim=4), _req(q_std, "q_std", ndim=4), _req(z_new, "z_what", ndim=4)
+    S, B, K, Z = z_new.shape
+    z_old = None if z_old is None else _req(z_old, "z_what_old", ndim=4)
+    ll_f = _req(ll_f, "ll_f", ndim=3)
+    T = ll_f.shape[-1]
+    ll_b = None if ll_b is None else _req(ll_b, "ll_b", ndim=3)
+    ep = None if extra_log_p is None else _req(extra_log_p, "extra_log_p", ndim=2)
+    eq = None if extra_log_q is None else _req(extra_log_q, "extra_log_q", ndim=2)
+    dev = z_new.device
+    outs = [torch.empty(S, B, dtype=torch.float32, device=dev) for _ in range(4)]
+    with torch.cuda.device(dev), _call("bmnist_logw_what", 1, 4 * S * B * (4 * K * Z + 2 * T + 6)):
+        check(lib.apgs_bmnist_logw_what_f32(ptr(q_mu), ptr(q_std), ptr(z_new), ptr(z_old), ptr(ll_f), ptr(ll_b), ptr(ep),
+                                            ptr(eq), S, B, K, Z, T, *[ptr(v) for v in outs], _stream()),
+              "apgs_bmnist_logw_what_f32")
+    return tuple(outs)

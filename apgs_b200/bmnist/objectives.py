@@ -1,0 +1,191 @@
+"""APG sweep for bouncing MNIST: drop-in for the hot-path functions of apgs/bmnist/objectives.py
+(resample_variables :5-9, apg_objective :11-58, propose_one_movement :60-107, oneshot :109-165,
+apg_where :167-225, apg_what :228-257).
+
+The template-matching conv2d + softmax and the MLPs stay in PyTorch; crop, paste,
+paste+sum+clamp+log-likelihood, every Normal log-density, the step weights, softmax/ESS and the per-frame
+resampling run in the sm_100a kernels.  Reference behaviours that change numbers are kept:
+  * the one-shot counts the t = 0 terms of log p / log q(z_where) twice (objectives.py:124-139);
+  * apg_where resamples a local z_what at every frame but returns only z_where, so apg_what scores the new
+    z_what against the caller's un-resampled z_what (objectives.py:212,225,45);
+  * frame t+1 is proposed from the un-resampled z_where_t (objectives.py:189).
+Forward / evaluation path only (gradients: SURVEY.md row N2).
+"""
+import torch
+import torch.nn.functional as F
+from torch.distributions.normal import Normal
+
+from .. import ops
+from . import kernels
+
+
+def resample_variables(resampler, z_where, z_what, log_weights):
+    z_where, z_what = resampler.resample([z_where, z_what], log_weights)
+    return z_where, z_what
+
+
+def _frames5(frames, S):
+    return frames if frames.dim() == 5 else frames.unsqueeze(0).expand(S, -1, -1, -1, -1)
+
+
+def apg_objective(models, AT, frames, K, result_flags, num_sweeps, resampler, mnist_mean):
+    """Amortized Population Gibbs objective in the bouncing MNIST problem (objectives.py:11-58)."""
+    trace = {'loss_phi': [], 'loss_theta': [], 'ess': [], 'E_where': [], 'E_what': [], 'E_recon': [], 'density': []}
+    frames = _frames5(frames, resampler.S)
+    (enc_coor, dec_coor, enc_digit, dec_digit) = models
+    log_w, z_where, z_what, trace = oneshot(enc_coor, dec_coor, enc_digit, dec_digit, AT, frames, mnist_mean, trace, result_flags)
+    z_where, z_what = resample_variables(resampler, z_where, z_what, log_weights=log_w)
+    for m in range(num_sweeps - 1):
+        z_where, trace = apg_where(enc_coor, dec_coor, dec_digit, AT, resampler, frames, z_what, z_where, trace, result_flags)
+        log_w, z_what, trace = apg_what(enc_digit, dec_digit, AT, frames, z_where, z_what, trace, result_flags)
+        z_where, z_what = resample_variables(resampler, z_where, z_what, log_weights=log_w)
+    if result_flags['loss_required']:
+        trace['loss_phi'] = torch.cat(trace['loss_phi'], 0)
+        trace['loss_theta'] = torch.cat(trace['loss_theta'], 0)
+    if result_flags['ess_required']:
+        trace['ess'] = torch.cat(trace['ess'], 0)
+    if result_flags['mode_required']:
+        trace['E_where'] = torch.cat(trace['E_where'], 0)
+        trace['E_what'] = torch.cat(trace['E_what'], 0)
+        trace['E_recon'] = torch.cat(trace['E_recon'], 0).cpu()
+    if result_flags['density_required']:
+        trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def propose_one_movement(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t, z_where_old_t_1):
+    """objectives.py:60-107: K sequential template matches; returns the reference's tuple."""
+    return _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t, z_where_old_t_1)[0]
+
+
+def _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t, z_where_old_t_1):
+    """-> (the reference's tuple, (q_mean, q_std)) -- the proposal parameters feed the caller's weight kernel."""
+    FP = frame.shape[-1]
+    S, B, K, DP, _ = template.shape
+    zs, means, stds = [], [], []
+    frame_left = frame
+    for k in range(K):
+        template_k = template[:, :, k, :, :]
+        conved_k = F.conv2d(frame_left.reshape(S * B, FP, FP).unsqueeze(0), template_k.reshape(S * B, DP, DP).unsqueeze(1), groups=int(S * B))
+        CP = conved_k.shape[-1]
+        conved_k = F.softmax(conved_k.squeeze(0).view(S, B, CP * CP), -1)
+        q_mean, q_std = enc_coor.params(conved_k)
+        z_where_k = Normal(q_mean, q_std, validate_args=False).sample()
+        zs.append(z_where_k.unsqueeze(2)); means.append(q_mean.unsqueeze(2)); stds.append(q_std.unsqueeze(2))
+        recon_k = AT.digit_to_frame(template_k.unsqueeze(2), z_where_k.unsqueeze(2).unsqueeze(2)).squeeze(2).squeeze(2)
+        frame_left = frame_left - recon_k
+    z_where = torch.cat(zs, 2)
+    q_mean, q_std = torch.cat(means, 2), torch.cat(stds, 2)
+    # every Normal log-density of this frame (all K digits, forward and backward) in one kernel (B4a)
+    E_where = q_mean
+    if z_where_old_t is not None:
+        _, log_q_f, log_p_f, log_q_b, log_p_b = kernels.logw_where(q_mean, q_std, z_where, z_where_t_1, z_where_old_t,
+                                                                   z_where_old_t_1, dec_coor, want_w=False, want_b=True)
+        return (log_p_f, log_q_f, log_p_b, log_q_b, z_where, E_where), (q_mean, q_std)
+    _, log_q_f, log_p_f = kernels.logw_where(q_mean, q_std, z_where, z_where_t_1, None, None, dec_coor, want_w=False)
+    return (log_p_f, log_q_f, z_where, E_where), (q_mean, q_std)
+
+
+def oneshot(enc_coor, dec_coor, enc_digit, dec_digit, AT, frames, digit, trace, result_flags):
+    """objectives.py:109-165."""
+    T = frames.shape[2]
+    S, B, K, DP, DP = digit.shape
+    z_where, E_where = [], []
+    z_where_t = None
+    for t in range(T):
+        log_p_where_t, log_q_where_t, z_where_t, E_where_t = propose_one_movement(
+            enc_coor, dec_coor, AT, frames[:, :, t, :, :], digit, z_where_t, None, None)
+        if t == 0:
+            log_p_where, log_q_where = log_p_where_t, log_q_where_t
+        log_q_where = log_q_where + log_q_where_t          # t = 0 is counted twice, as in the reference
+        log_p_where = log_p_where + log_p_where_t
+        z_where.append(z_where_t.unsqueeze(2))
+        E_where.append(E_where_t.unsqueeze(2))
+    z_where = torch.cat(z_where, 2)
+    E_where = torch.cat(E_where, 2)
+    cropped = AT.frame_to_digit(frames=frames, z_where=z_where).view(S, B, T, K, DP * DP)
+    q_mu, q_std = enc_digit.params(cropped)
+    z_what = Normal(q_mu, q_std, validate_args=False).sample()
+    ll, recon = AT.reconstruct_ll(dec_digit.templates(z_what), z_where, frames, want_recon=bool(result_flags['mode_required']))
+    log_w, log_q, log_p, ll_sum = kernels.logw_what(q_mu, q_std, z_what, None, ll, None, extra_log_p=log_p_where, extra_log_q=log_q_where)
+    if result_flags['loss_required'] or result_flags['ess_required']:
+        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        if result_flags['loss_required']:
+            trace['loss_phi'].append((w * (-log_q)).sum(0).mean().unsqueeze(0))
+            trace['loss_theta'].append((w * (-ll_sum)).sum(0).mean().unsqueeze(0))
+        if result_flags['ess_required']:
+            trace['ess'].append(ess.unsqueeze(0))
+    if result_flags['mode_required']:
+        trace['E_where'].append(E_where.mean(0).unsqueeze(0))
+        trace['E_what'].append(q_mu.mean(0).unsqueeze(0))
+        trace['E_recon'].append(recon.mean(0).unsqueeze(0))
+    if result_flags['density_required']:
+        trace['density'].append(log_p.unsqueeze(0))
+    return log_w, z_where, z_what, trace
+
+
+def apg_where(enc_coor, dec_coor, dec_digit, AT, resampler, frames, z_what, z_where_old, trace, result_flags):
+    """objectives.py:167-225: per-frame propose -> reweight -> resample of the growing z_where[:, :, :t+1]."""
+    T = frames.shape[2]
+    template = dec_digit.templates(z_what)
+    E_where, LOSS_phi, LOSS_theta = [], [], []
+    log_prior = 0.0
+    z_where_t = None
+    z_where = None
+    for t in range(T):
+        frame_t = frames[:, :, t, :, :]
+        z_old_t = z_where_old[:, :, t, :, :]
+        z_old_t_1 = None if t == 0 else z_where_old[:, :, t - 1, :, :]
+        z_prev = z_where_t
+        (log_p_f, log_q_f, log_p_b, log_q_b, z_where_t, E_where_t), (q_mean, q_std) = _propose(
+            enc_coor, dec_coor, AT, frame_t, template, z_where_t, z_old_t, z_old_t_1)
+        if result_flags['density_required']:
+            log_prior = log_prior + log_p_f
+        if result_flags['mode_required']:
+            E_where.append(E_where_t.unsqueeze(2))
+        digit = dec_digit.templates(z_what)
+        ll_f, _ = AT.reconstruct_ll(digit, z_where_t.unsqueeze(2), frames[:, :, t:t + 1])
+        ll_b, _ = AT.reconstruct_ll(digit, z_old_t.unsqueeze(2), frames[:, :, t:t + 1])
+        # objectives.py:198-206 in one kernel: (log_p_f - log_q_f) - (log_p_b - log_q_b) + ll_f - ll_b
+        log_w, _, _ = kernels.logw_where(q_mean, q_std, z_where_t, z_prev, z_old_t, z_old_t_1, dec_coor,
+                                         ll_f=ll_f.squeeze(-1), ll_b=ll_b.squeeze(-1))
+        z_where = z_where_t.unsqueeze(2) if t == 0 else torch.cat((z_where, z_where_t.unsqueeze(2)), 2)
+        if result_flags['loss_required']:
+            w, _, _ = ops.weight_stats(log_w)
+            LOSS_phi.append((w * (-log_q_f)).sum(0).mean().unsqueeze(-1))
+            LOSS_theta.append((w * (-ll_f.squeeze(-1))).sum(0).mean().unsqueeze(-1))
+        z_where, z_what = resample_variables(resampler, z_where, z_what, log_weights=log_w)
+    if result_flags['mode_required']:
+        trace['E_where'].append(torch.cat(E_where, 2).mean(0).unsqueeze(0))
+    if result_flags['loss_required']:
+        trace['loss_phi'].append(torch.cat(LOSS_phi, -1).sum(-1).unsqueeze(0))
+        trace['loss_theta'].append(torch.cat(LOSS_theta, -1).sum(-1).unsqueeze(0))
+    if result_flags['density_required']:
+        trace['density'].append(log_prior.unsqueeze(0))
+    return z_where, trace
+
+
+def apg_what(enc_digit, dec_digit, AT, frames, z_where, z_what_old, trace, result_flags):
+    """objectives.py:228-257."""
+    S, B, T, K, _ = z_where.shape
+    cropped = AT.frame_to_digit(frames=frames, z_where=z_where)
+    DP = cropped.shape[-1]
+    q_mu, q_std = enc_digit.params(cropped.view(S, B, T, K, int(DP * DP)))
+    z_what = Normal(q_mu, q_std, validate_args=False).sample()
+    want_recon = bool(result_flags['mode_required'])
+    ll_f, recon = AT.reconstruct_ll(dec_digit.templates(z_what), z_where, frames, want_recon=want_recon)
+    ll_b, _ = AT.reconstruct_ll(dec_digit.templates(z_what_old), z_where, frames)
+    log_w, log_q_f, dens, ll_sum = kernels.logw_what(q_mu, q_std, z_what, z_what_old, ll_f, ll_b)
+    if result_flags['loss_required'] or result_flags['ess_required']:
+        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        if result_flags['loss_required']:
+            trace['loss_phi'][-1] = trace['loss_phi'][-1] + (w * (-log_q_f)).sum(0).mean().unsqueeze(0)
+            trace['loss_theta'][-1] = trace['loss_theta'][-1] + (w * (-ll_sum)).sum(0).mean().unsqueeze(0)
+        if result_flags['ess_required']:
+            trace['ess'].append(ess.unsqueeze(0))
+    if result_flags['mode_required']:
+        trace['E_what'].append(q_mu.mean(0).unsqueeze(0))
+        trace['E_recon'].append(recon.mean(0).unsqueeze(0))
+    if result_flags['density_required']:
+        trace['density'][-1] = trace['density'][-1] + dens.unsqueeze(0)
+    return log_w, z_what, trace

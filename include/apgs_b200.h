@@ -208,6 +208,53 @@ APGS_API int apgs_gmm_eta_posterior_fused_f32(const float* x, const float* z,
                                      float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
                                      void* stream);
 
+/* ==============================================================================================
+ * Bouncing-MNIST.  FP frame pixels (96), DP digit pixels (28), K digits,
+ * T frames.  The transformer is the reference's: nearest sampling, align_corners=True, diagonal theta
+ * (SURVEY.md F5).  lin_* = torch.linspace(-1, 1, n) (affine_grid's base axis) on the device.
+ * ============================================================================================== */
+
+/* B1  crop.  replaces Affine_Transformer.frame_to_digit, apgs/bmnist/affine_transformer.py:54-65.
+ *   frames: element (s,b,t,i,j) at frames[s*stride_s + b*stride_b + t*stride_t + i*FP + j] -- stride_s may be 0
+ *   (the reference's S-fold repeat, apgs/bmnist/apg_training.py:25, is not needed);
+ *   z_where (S,B,T,K,2) (not modified); lin_dp (DP); digits_out (S,B,T,K,DP,DP).                   */
+APGS_API int apgs_bmnist_crop_f32(const float* frames, int64_t stride_s, int64_t stride_b, int64_t stride_t,
+                         const float* z_where, const float* lin_dp,
+                         int64_t S, int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP,
+                         float* digits_out, void* stream);
+/* B2  paste.  replaces Affine_Transformer.digit_to_frame, affine_transformer.py:41-52.
+ *   digits (S,B,K,DP,DP); lin_fp (FP); frames_out (S,B,T,K,FP,FP) (zero outside the digit).         */
+APGS_API int apgs_bmnist_paste_f32(const float* digits, const float* z_where, const float* lin_fp,
+                          int64_t S, int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP,
+                          float* frames_out, void* stream);
+/* B2+B3  paste + sum over digits + clamp + Bernoulli-like pixel log-likelihood, fused.
+ * replaces the tail of Dec_digit.forward, apgs/bmnist/models.py:148-154, and MBern_log_prob :156-162.
+ *   ll_out (S,B,T); recon_out (S,B,T,FP,FP) or NULL.  The (S,B,T,K,FP,FP) pasted tensor never exists.  */
+APGS_API int apgs_bmnist_paste_ll_f32(const float* digits, const float* z_where, const float* lin_fp,
+                             const float* frames, int64_t stride_s, int64_t stride_b, int64_t stride_t,
+                             int64_t S, int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP,
+                             float* ll_out, float* recon_out, void* stream);
+/* B4a  z_where step of one frame.  replaces the log-density bookkeeping of propose_one_movement,
+ * apgs/bmnist/objectives.py:60-107 (+ Dec_coor.forward, apgs/bmnist/models.py:97-104) and the weight at
+ * objectives.py:198-206.   q_mean/q_std/z_new (S,B,K,D) of frame t; z_prev = z_new of frame t-1 or NULL (t=0);
+ * z_old / z_old_prev: the old trajectory at t and t-1 (NULL: no backward term / t=0); prior_* (D);
+ * ll_f / ll_b (S,B) or NULL.  Outputs (S,B), each optional: log_w, log_q_f, log_p_f, log_q_b, log_p_b. */
+APGS_API int apgs_bmnist_logw_where_f32(const float* q_mean, const float* q_std, const float* z_new,
+                               const float* z_prev, const float* z_old, const float* z_old_prev,
+                               const float* prior_mu0, const float* prior_sigma0, const float* prior_sigmat,
+                               const float* ll_f, const float* ll_b,
+                               int64_t S, int64_t B, int64_t K, int64_t D,
+                               float* log_w, float* log_q_f, float* log_p_f, float* log_q_b, float* log_p_b,
+                               void* stream);
+/* B4b  z_what step / one-shot.  replaces objectives.py:241 (apg_what) and :147-149 (oneshot).
+ *   q_mu/q_std/z_new (S,B,K,Z); z_old or NULL; ll_f/ll_b (S,B,T); extra_log_p / extra_log_q (S,B) or NULL
+ *   (the one-shot's accumulated log p / log q of z_where).  Outputs (S,B), each optional.           */
+APGS_API int apgs_bmnist_logw_what_f32(const float* q_mu, const float* q_std, const float* z_new, const float* z_old,
+                              const float* ll_f, const float* ll_b,
+                              const float* extra_log_p, const float* extra_log_q,
+                              int64_t S, int64_t B, int64_t K, int64_t Z, int64_t T,
+                              float* log_w, float* log_q_f, float* density, float* ll_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -169,7 +169,104 @@ def section_gmm():
     save("gmm", **out)
 
 
-SECTIONS = {"resampler": section_resampler, "gmm": section_gmm}
+# ------------------------------------------------------------------------------------- STN
+def section_stn():
+    from apgs.bmnist.affine_transformer import Affine_Transformer
+    from apgs.bmnist.models import MBern_log_prob
+    FP, DP = 96, 28
+    AT = Affine_Transformer(FP, DP, False, None)
+    torch.manual_seed(11)
+    S, B, T, K = 2, 2, 3, 3
+    z = torch.randn(S, B, T, K, 2) * 0.6
+    z[0, 0, 0, 0] = torch.tensor([1.4, -1.3])       # partly outside the frame
+    z[1, 1, 2, 2] = torch.tensor([-2.5, 0.2])       # completely outside along x
+    z[0, 1, 1, 1] = torch.tensor([0.0, 0.0])
+    digit = torch.rand(S, B, K, DP, DP)
+    frames = torch.rand(S, B, T, FP, FP)
+    z_in = z.clone()
+    pasted = AT.digit_to_frame(digit, z)
+    cropped = AT.frame_to_digit(frames, z)
+    assert torch.equal(z, z_in)                     # the reference does not mutate z_where
+    recon = torch.clamp(pasted.sum(-3), min=0.0, max=1.0)
+    ll = MBern_log_prob(recon, frames)
+    save("stn", z_where=z, digit=digit, frames=frames, pasted=pasted, cropped=cropped, recon=recon, ll=ll)
+
+
+# ---------------------------------------------------------------------------------- bmnist
+def section_bmnist():
+    """Reference apg_objective (bmnist) under fixed seeds: whole traces + every per-step log-weight (captured by
+    wrapping the reference's resample_variables) + the oracle's step records, which are asserted to reproduce them."""
+    from apgs.resampler import Resampler
+    from apgs.bmnist.apg_training import init_models
+    import apgs.bmnist.objectives as O
+    from apgs.bmnist.affine_transformer import Affine_Transformer
+    from oracle import bmnist as ob
+    FP, DP, K = 96, 28, 3
+    S, B, T, sweeps = 4, 3, 3, 3
+    out = {"dims": np.array([S, B, T, K, sweeps, FP, DP])}
+    torch.manual_seed(0)
+    models = init_models(FP, DP, 400, 400, 2, 10, False, None, None, None)
+    torch.manual_seed(0)
+    P = ob.make_params()
+    torch.manual_seed(1)
+    frames1 = ob.simulate(B, T, K)
+    frames = frames1.repeat(S, 1, 1, 1, 1)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, DP), torch.linspace(-1, 1, DP), indexing="ij")
+    tmpl = torch.exp(-(xx ** 2 + yy ** 2) * 3).clamp(0, 1)
+    mm = tmpl.repeat(S, B, K, 1, 1)
+    out["frames"], out["template"] = frames1, tmpl
+    AT = Affine_Transformer(FP, DP, False, None)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    ref_lw = []
+    orig = O.resample_variables
+
+    def rec(resampler, z_where, z_what, log_weights):
+        ref_lw.append(log_weights.clone())
+        return orig(resampler, z_where, z_what, log_weights)
+    for strategy in ("systematic", "multinomial"):
+        del ref_lw[:]
+        O.resample_variables = rec
+        with torch.no_grad():
+            torch.manual_seed(2)
+            tr = O.apg_objective(models, AT, frames, K, flags, sweeps, Resampler(strategy, S, False, None), mm)
+            O.resample_variables = orig
+            torch.manual_seed(2)
+            recd = []
+            mine = ob.apg_objective(P, ob.make_prior(), frames, K, flags, sweeps, mm, strategy, record=recd)
+        for k in ("loss_phi", "loss_theta", "ess", "density"):
+            assert torch.equal(tr[k], mine[k]), (strategy, k)
+            out["full_%s_%s" % (strategy, k)] = tr[k]
+        assert len(ref_lw) == len(recd)
+        for i, (a, r) in enumerate(zip(ref_lw, recd)):
+            assert torch.equal(a, r["log_w"]), (strategy, i)
+        if strategy != "systematic":
+            continue
+        # step fixtures (inputs from the oracle's record, log-weights from the reference itself)
+        ws = [i for i, r in enumerate(recd) if r["step"] == "where"]
+        for tag, i in (("w0", ws[0]), ("w1", ws[1]), ("w5", ws[-1])):
+            r = recd[i]
+            pm = r["pm"]
+            out.update({tag + "_q_mean": pm["q_mean"], tag + "_q_std": pm["q_std"], tag + "_z_new": pm["z_where"],
+                        tag + "_z_old": r["z_old_t"], tag + "_ll_f": r["ll_f"], tag + "_ll_b": r["ll_b"],
+                        tag + "_log_w": ref_lw[i], tag + "_log_q_f": pm["log_q_f"], tag + "_log_p_f": pm["log_p_f"],
+                        tag + "_z_what": r["z_what"]})
+            if r["z_old_t_1"] is not None:
+                out[tag + "_z_old_prev"] = r["z_old_t_1"]
+                prev = recd[i - 1]["pm"]["z_where"]
+                out[tag + "_z_prev"] = prev
+        i = [i for i, r in enumerate(recd) if r["step"] == "what"][0]
+        r = recd[i]
+        out.update({"wh_q_mu": r["q_mu"], "wh_q_std": r["q_std"], "wh_z_what": r["z_what"], "wh_z_what_old": r["z_what_old"],
+                    "wh_ll_f": r["ll_f"], "wh_ll_b": r["ll_b"], "wh_log_w": ref_lw[i], "wh_log_q_f": r["log_q_f"],
+                    "wh_dens": r["dens"], "wh_z_where": r["z_where"]})
+        r = recd[0]
+        out.update({"os_z_where": r["z_where"], "os_z_what": r["z_what"], "os_q_mu": r["q_mu"], "os_q_std": r["q_std"],
+                    "os_ll": r["ll"], "os_log_p_where": r["log_p_where"], "os_log_q_where": r["log_q_where"],
+                    "os_log_w": ref_lw[0], "os_log_p": r["log_p"], "os_log_q": r["log_q"]})
+    save("bmnist", **out)
+
+
+SECTIONS = {"resampler": section_resampler, "gmm": section_gmm, "stn": section_stn, "bmnist": section_bmnist}
 
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(SECTIONS)

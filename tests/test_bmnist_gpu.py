@@ -1,0 +1,153 @@
+"""GPU parity: spatial-transformer crop / paste (bit-exact: pure gathers) and the fused paste + Bernoulli
+log-likelihood, z_where / z_what step weights, against the reference-generated golden fixtures and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bmnist as ob
+from oracle import stn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(g, k):
+    return torch.from_numpy(g[k])
+
+
+def _AT():
+    from apgs_b200.bmnist.affine_transformer import Affine_Transformer
+    return Affine_Transformer(96, 28, True, DEV)
+
+
+def test_B1_B2_crop_paste_bit_exact_vs_reference_golden(golden):
+    g = golden("stn")
+    AT = _AT()
+    z = _t(g, "z_where").to(DEV)
+    z_in = z.clone()
+    pasted = AT.digit_to_frame(_t(g, "digit").to(DEV), z)
+    cropped = AT.frame_to_digit(_t(g, "frames").to(DEV), z)
+    assert torch.equal(z, z_in), "z_where must not be modified"
+    assert tuple(pasted.shape) == g["pasted"].shape and tuple(cropped.shape) == g["cropped"].shape
+    assert np.array_equal(pasted.cpu().numpy(), g["pasted"])
+    assert np.array_equal(cropped.cpu().numpy(), g["cropped"])
+
+
+def test_B3_paste_ll_vs_reference_golden(golden):
+    g = golden("stn")
+    AT = _AT()
+    ll, recon = AT.reconstruct_ll(_t(g, "digit").to(DEV), _t(g, "z_where").to(DEV), _t(g, "frames").to(DEV), want_recon=True)
+    assert np.array_equal(recon.cpu().numpy(), g["recon"])          # sums of <= 3 gathered values + clamp: exact
+    np.testing.assert_allclose(ll.cpu().numpy(), g["ll"], rtol=1e-5)
+    ll2, none = AT.reconstruct_ll(_t(g, "digit").to(DEV), _t(g, "z_where").to(DEV), _t(g, "frames").to(DEV))
+    assert none is None and torch.equal(ll, ll2)
+
+
+@pytest.mark.parametrize("S,B,T,K", [(1, 1, 1, 1), (3, 2, 5, 3), (10, 4, 2, 2)])
+def test_stn_random_vs_oracle_incl_shared_frames(S, B, T, K):
+    """frames given once per instance ((B,T,FP,FP) / stride-0 particle axis) and single-frame views."""
+    AT = _AT()
+    torch.manual_seed(S * 10 + T)
+    z = torch.randn(S, B, T, K, 2) * 0.9
+    digit = torch.rand(S, B, K, 28, 28)
+    fr = torch.rand(B, T, 96, 96)
+    frs = fr.unsqueeze(0).expand(S, -1, -1, -1, -1)
+    ref_c = stn.frame_to_digit(frs.numpy(), z.numpy())
+    assert np.array_equal(AT.frame_to_digit(fr.to(DEV), z.to(DEV)).cpu().numpy(), ref_c)
+    assert np.array_equal(AT.frame_to_digit(fr.to(DEV).unsqueeze(0).expand(S, -1, -1, -1, -1), z.to(DEV)).cpu().numpy(), ref_c)
+    assert np.array_equal(AT.digit_to_frame(digit.to(DEV), z.to(DEV)).cpu().numpy(), stn.digit_to_frame(digit.numpy(), z.numpy()))
+    recon, ll = stn.recon_and_ll(digit.numpy(), z.numpy(), frs.numpy())
+    ll_g, rec_g = AT.reconstruct_ll(digit.to(DEV), z.to(DEV), fr.to(DEV), want_recon=True)
+    assert np.array_equal(rec_g.cpu().numpy(), recon.numpy())
+    np.testing.assert_allclose(ll_g.cpu().numpy(), ll.numpy(), rtol=1e-5)
+    # one frame of a (S,B,T,..) tensor as a strided view, as apg_where uses it (objectives.py:204)
+    t = T - 1
+    ll_t, _ = AT.reconstruct_ll(digit.to(DEV), z[:, :, t:t + 1].contiguous().to(DEV), frs.to(DEV)[:, :, t:t + 1])
+    np.testing.assert_allclose(ll_t.cpu().numpy()[..., 0], ll.numpy()[..., t], rtol=1e-5)
+
+
+def test_B4_where_and_what_weights_vs_reference_golden(golden):
+    from apgs_b200.bmnist import kernels
+    from apgs_b200.bmnist.models import Dec_coor
+    g = golden("bmnist")
+    dc = Dec_coor(2, True, DEV)
+    for tag in ("w0", "w1", "w5"):
+        opt = lambda n: _t(g, tag + n).to(DEV) if (tag + n) in g.files else None
+        lw, lq, lp = kernels.logw_where(_t(g, tag + "_q_mean").to(DEV), _t(g, tag + "_q_std").to(DEV), _t(g, tag + "_z_new").to(DEV),
+                                        opt("_z_prev"), _t(g, tag + "_z_old").to(DEV), opt("_z_old_prev"), dc,
+                                        ll_f=_t(g, tag + "_ll_f").squeeze(-1).to(DEV), ll_b=_t(g, tag + "_ll_b").squeeze(-1).to(DEV))
+        np.testing.assert_allclose(lq.cpu().numpy(), g[tag + "_log_q_f"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(lp.cpu().numpy(), g[tag + "_log_p_f"], rtol=1e-5, atol=1e-5)
+        mag = np.abs(g[tag + "_ll_f"]).squeeze(-1) + np.abs(g[tag + "_ll_b"]).squeeze(-1) + np.abs(g[tag + "_log_q_f"]) + np.abs(g[tag + "_log_p_f"])
+        assert (np.abs(lw.cpu().numpy() - g[tag + "_log_w"]) <= 1e-5 * mag + 1e-4).all(), tag
+    lw, lq, dens, lls = kernels.logw_what(_t(g, "wh_q_mu").to(DEV), _t(g, "wh_q_std").to(DEV), _t(g, "wh_z_what").to(DEV),
+                                          _t(g, "wh_z_what_old").to(DEV), _t(g, "wh_ll_f").to(DEV), _t(g, "wh_ll_b").to(DEV))
+    np.testing.assert_allclose(lq.cpu().numpy(), g["wh_log_q_f"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dens.cpu().numpy(), g["wh_dens"], rtol=1e-5)
+    mag = np.abs(g["wh_ll_f"]).sum(-1) + np.abs(g["wh_ll_b"]).sum(-1)
+    assert (np.abs(lw.cpu().numpy() - g["wh_log_w"]) <= 1e-5 * mag + 1e-4).all()
+    # one-shot: log p - log q with the accumulated z_where terms
+    lw, lq, dens, _ = kernels.logw_what(_t(g, "os_q_mu").to(DEV), _t(g, "os_q_std").to(DEV), _t(g, "os_z_what").to(DEV), None,
+                                        _t(g, "os_ll").to(DEV), None, extra_log_p=_t(g, "os_log_p_where").to(DEV),
+                                        extra_log_q=_t(g, "os_log_q_where").to(DEV))
+    np.testing.assert_allclose(dens.cpu().numpy(), g["os_log_p"], rtol=1e-5)
+    np.testing.assert_allclose(lq.cpu().numpy(), g["os_log_q"], rtol=1e-5, atol=1e-5)
+    assert (np.abs(lw.cpu().numpy() - g["os_log_w"]) <= 1e-5 * (np.abs(g["os_log_p"]) + np.abs(g["os_log_q"]))).all()
+
+
+def _models(seed=0):
+    from apgs_b200.bmnist import models as M
+    torch.manual_seed(seed)
+    P = ob.make_params()
+    ms = M.init_models(96, 28, 400, 400, 2, 10, True, DEV)
+    for m, key in ((ms[0], "enc_coor"), (ms[2], "enc_digit"), (ms[3], "dec_digit")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})     # same state_dict keys as the reference
+    return P, ms
+
+
+def test_bmnist_sweep_runs_and_matches_oracle_statistics(golden):
+    """End to end on the golden instance set (CPU/CUDA generators differ -> shapes, finiteness, and the log-joint of
+    the one-shot, whose proposal does not depend on earlier draws of other particles, within Monte-Carlo error)."""
+    from apgs_b200.bmnist import objectives as O
+    from apgs_b200.resampler import Resampler
+    g = golden("bmnist")
+    K, FP, DP = 3, 96, 28
+    S, B, T, sweeps = 12, 3, 3, 3
+    P, models = _models()
+    frames = _t(g, "frames")
+    tmpl = _t(g, "template")
+    flags = {"loss_required": True, "ess_required": True, "mode_required": True, "density_required": True}
+    torch.manual_seed(5)
+    with torch.no_grad():
+        ref = ob.apg_objective(P, ob.make_prior(), frames.repeat(S, 1, 1, 1, 1), K, flags, sweeps, tmpl.repeat(S, B, K, 1, 1))
+        tr = O.apg_objective(models, _AT(), frames.to(DEV).repeat(S, 1, 1, 1, 1), K, flags, sweeps,
+                             Resampler("systematic", S, True, DEV), tmpl.to(DEV).repeat(S, B, K, 1, 1))
+    for k in ("loss_phi", "loss_theta", "ess", "density"):
+        assert tuple(tr[k].shape) == tuple(ref[k].shape), k
+        assert bool(torch.isfinite(tr[k]).all()), k
+    assert tuple(tr["E_where"].shape) == (sweeps, B, T, K, 2) and tuple(tr["E_recon"].shape) == (sweeps, B, T, FP, FP)
+    a, b = tr["density"][0].cpu().mean(0), ref["density"][0].mean(0)
+    assert bool(((a - b).abs() < 0.15 * b.abs()).all()), (a, b)
+
+
+def test_bmnist_teacher_forced_step_vs_oracle(golden):
+    """One apg_what step with the draw forced: crop -> Enc_digit -> Dec_digit -> paste/ll -> weight, against the oracle."""
+    from apgs_b200.bmnist import kernels
+    g = golden("bmnist")
+    K = 3
+    S, B, T = [int(v) for v in g["dims"][:3]]
+    P, models = _models()
+    enc_digit, dec_digit = models[2], models[3]
+    AT = _AT()
+    frames = _t(g, "frames")
+    frs = frames.repeat(S, 1, 1, 1, 1)
+    z_where, z_new, z_old = _t(g, "wh_z_where"), _t(g, "wh_z_what"), _t(g, "wh_z_what_old")
+    with torch.no_grad():
+        cropped = AT.frame_to_digit(frames.to(DEV), z_where.to(DEV))
+        assert torch.equal(cropped.cpu(), ob.frame_to_digit(frs, z_where))
+        q_mu, q_std = enc_digit.params(cropped.view(S, B, T, K, 784))
+        np.testing.assert_allclose(q_mu.cpu().numpy(), g["wh_q_mu"], rtol=2e-4, atol=2e-5)
+        ll_f, _ = AT.reconstruct_ll(dec_digit.templates(z_new.to(DEV)), z_where.to(DEV), frames.to(DEV))
+        ll_b, _ = AT.reconstruct_ll(dec_digit.templates(z_old.to(DEV)), z_where.to(DEV), frames.to(DEV))
+        np.testing.assert_allclose(ll_f.cpu().numpy(), g["wh_ll_f"], rtol=2e-5)
+        np.testing.assert_allclose(ll_b.cpu().numpy(), g["wh_ll_b"], rtol=2e-5)

@@ -140,3 +140,56 @@ def test_gmm_full_objective_reproduces_reference_trace(golden, block, strategy):
         ref = _t(g, "full_%s_%s_%s" % (block, strategy, k))
         assert tr[k].shape == ref.shape
         torch.testing.assert_close(tr[k], ref, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------ STN / bmnist
+def test_stn_closed_form_bit_exact(golden):
+    from oracle import stn
+    g = golden("stn")
+    assert np.array_equal(stn.digit_to_frame(g["digit"], g["z_where"]), g["pasted"])
+    assert np.array_equal(stn.frame_to_digit(g["frames"], g["z_where"]), g["cropped"])
+    recon, ll = stn.recon_and_ll(g["digit"], g["z_where"], g["frames"])
+    assert np.array_equal(recon.numpy(), g["recon"]) and np.array_equal(ll.numpy(), g["ll"])
+    # the torch-vectorised restatement used by the sweep oracle agrees bit for bit
+    from oracle import bmnist as ob
+    assert torch.equal(ob.digit_to_frame(_t(g, "digit"), _t(g, "z_where")), _t(g, "pasted"))
+    assert torch.equal(ob.frame_to_digit(_t(g, "frames"), _t(g, "z_where")), _t(g, "cropped"))
+
+
+def test_bmnist_step_weights(golden):
+    from oracle import bmnist as ob
+    g = golden("bmnist")
+    prior = ob.make_prior()
+    for tag in ("w0", "w1", "w5"):
+        pm = {"log_q_f": _t(g, tag + "_log_q_f"), "log_p_f": _t(g, tag + "_log_p_f")}
+        z_old = _t(g, tag + "_z_old")
+        has_prev = (tag + "_z_old_prev") in g.files
+        lqb = sum(ob.dists.normal_log_prob(z_old[:, :, k], _t(g, tag + "_q_mean")[:, :, k], _t(g, tag + "_q_std")[:, :, k]).sum(-1).unsqueeze(-1)
+                  for k in range(3))
+        lpb = torch.cat([ob.coor_log_prior(prior, z_old[:, :, k], _t(g, tag + "_z_old_prev")[:, :, k] if has_prev else None).unsqueeze(-1)
+                         for k in range(3)], -1).sum(-1)
+        lqb = torch.cat([ob.dists.normal_log_prob(z_old[:, :, k], _t(g, tag + "_q_mean")[:, :, k], _t(g, tag + "_q_std")[:, :, k]).sum(-1).unsqueeze(-1)
+                         for k in range(3)], -1).sum(-1)
+        pm["log_q_b"], pm["log_p_b"] = lqb, lpb
+        lw = ob.where_step_weight(pm, _t(g, tag + "_ll_f").squeeze(-1), _t(g, tag + "_ll_b").squeeze(-1))
+        assert torch.equal(lw, _t(g, tag + "_log_w")), tag
+    lw, lq, dens = ob.what_step_weight(_t(g, "wh_q_mu"), _t(g, "wh_q_std"), _t(g, "wh_z_what"), _t(g, "wh_z_what_old"),
+                                       _t(g, "wh_ll_f"), _t(g, "wh_ll_b"))
+    assert torch.equal(lw, _t(g, "wh_log_w")) and torch.equal(dens, _t(g, "wh_dens"))
+
+
+@pytest.mark.parametrize("strategy", ["systematic", "multinomial"])
+def test_bmnist_full_objective_reproduces_reference_trace(golden, strategy):
+    from oracle import bmnist as ob
+    g = golden("bmnist")
+    S, B, T, K, sweeps, FP, DP = [int(v) for v in g["dims"]]
+    torch.manual_seed(0)
+    P = ob.make_params()
+    frames = _t(g, "frames").repeat(S, 1, 1, 1, 1)
+    mm = _t(g, "template").repeat(S, B, K, 1, 1)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    torch.manual_seed(2)
+    with torch.no_grad():
+        tr = ob.apg_objective(P, ob.make_prior(), frames, K, flags, sweeps, mm, strategy)
+    for k in ("loss_phi", "loss_theta", "ess", "density"):
+        torch.testing.assert_close(tr[k], _t(g, "full_%s_%s" % (strategy, k)), rtol=1e-5, atol=1e-3)
