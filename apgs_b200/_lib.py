@@ -36,8 +36,18 @@ class GmmOut(C.Structure):
                                           "log_w_local", "log_q_local")]
 
 
+class DmmPrior(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mu_mu", "mu_sigma", "pi", "con1", "con0", "radi", "recon_sigma")]
+
+
+class DmmOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("log_w", "log_q_f", "density", "ll_f", "log_w_f", "log_w_b",
+                                          "log_w_local", "log_q_local", "ll_local")]
+
+
 _p, _i64, _int, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
 _PR, _PO, _OUT = C.POINTER(GmmPrior), C.POINTER(GmmPost), C.POINTER(GmmOut)
+_DPR, _DOUT = C.POINTER(DmmPrior), C.POINTER(DmmOut)
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
@@ -58,6 +68,10 @@ SIGNATURES = {
     "apgs_gmm_logw_z_f32": (_int, [_p, _p, _p, _p, _PR, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_logw_joint_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _p, _p, _p,
                                        _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_dmm_nss_pool_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_dmm_logw_mu_f32": (_int, [_p] * 7 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
+    "apgs_dmm_logw_local_f32": (_int, [_p] * 13 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
+    "apgs_dmm_logw_oneshot_f32": (_int, [_p] * 10 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
     "apgs_bmnist_crop_f32": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_bmnist_paste_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_bmnist_paste_ll_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),

@@ -1,0 +1,113 @@
+"""Host wrappers of the DMM kernels (apgs_b200/csrc/dmm.cu) -- SURVEY.md D1-D3."""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import DmmOut, DmmPrior, check, ptr
+from ..ops import _call, _req, _stream
+
+
+def _x3(x):
+    if x.dim() == 4:
+        x = x[0]
+    return _req(x, "x", ndim=3)
+
+
+def _prior(dec):
+    """dec: object with prior_mu_mu, prior_mu_sigma (D), prior_pi (K), prior_con1/con0 (1), radi (1), recon_sigma (1)."""
+    t = [_req(getattr(dec, n), n) for n in ("prior_mu_mu", "prior_mu_sigma", "prior_pi", "prior_con1", "prior_con0",
+                                             "radi", "recon_sigma")]
+    return DmmPrior(*[v.data_ptr() for v in t]), t
+
+
+class Weights(object):
+    __slots__ = ("log_w", "log_q_f", "density", "ll_f", "log_w_f", "log_w_b", "log_w_local", "log_q_local", "ll_local")
+
+
+def _outs(S, B, N, dev, parts, local):
+    w, o = Weights(), DmmOut()
+    for name in Weights.__slots__:
+        t = None
+        if name in ("log_w", "log_q_f", "density", "ll_f") or (parts and name in ("log_w_f", "log_w_b")):
+            t = torch.empty(S, B, dtype=torch.float32, device=dev)
+        elif local and name in ("log_w_local", "log_q_local", "ll_local"):
+            t = torch.empty(S, B, N, dtype=torch.float32, device=dev)
+        setattr(w, name, t)
+        setattr(o, name, None if t is None else t.data_ptr())
+    return w, o
+
+
+def nss_pool(nss1, nss2, prior_mu_mu, prior_mu_sigma):
+    """D1 -> (S,B,K,J+2D)."""
+    lib = _lib.load()
+    nss1, nss2 = _req(nss1, "nss1", ndim=4), _req(nss2, "nss2", ndim=4)
+    S, B, N, J = nss1.shape
+    K = nss2.shape[-1]
+    pm, ps = _req(prior_mu_mu, "prior_mu_mu"), _req(prior_mu_sigma, "prior_mu_sigma")
+    D = pm.numel()
+    out = torch.empty(S, B, K, J + 2 * D, dtype=torch.float32, device=nss1.device)
+    with torch.cuda.device(nss1.device), _call("dmm_nss_pool", 1, 4 * S * B * (N * (J + K) + K * (J + 2 * D))):
+        check(lib.apgs_dmm_nss_pool_f32(ptr(nss1), ptr(nss2), ptr(pm), ptr(ps), S, B, N, K, J, D, ptr(out), _stream()),
+              "apgs_dmm_nss_pool_f32")
+    return out
+
+
+def _flat(t, name):
+    """(S,B,N,1) or (S,B,N) -> contiguous tensor read as (S,B,N)."""
+    t = _req(t, name)
+    return t
+
+
+def logw_mu(x, z, hidden2, q_mu, q_sigma, mu, mu_old, dec, parts=False):
+    """D2: mu-step weights (apgs/dmm/objectives.py:116-151)."""
+    lib = _lib.load()
+    x = _x3(x)
+    z, hidden2 = _req(z, "z", ndim=4), _req(hidden2, "hidden2", ndim=4)
+    q_mu, q_sigma, mu, mu_old = [_req(v, "mu params", ndim=4) for v in (q_mu, q_sigma, mu, mu_old)]
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    ps, keep = _prior(dec)
+    w, o = _outs(S, B, N, z.device, parts, False)
+    with torch.cuda.device(z.device), _call("dmm_logw_mu", 1, 4 * S * B * (N * (K + D) + 4 * K * D + 4)):
+        check(lib.apgs_dmm_logw_mu_f32(ptr(x), ptr(z), ptr(hidden2), ptr(q_mu), ptr(q_sigma), ptr(mu), ptr(mu_old),
+                                       C.byref(ps), S, B, N, K, D, C.byref(o), _stream()), "apgs_dmm_logw_mu_f32")
+    return w
+
+
+def logw_local(x, mu, q_probs, z, beta, con1, con0, hidden2, z_old, beta_old, con1_old, con0_old, hidden2_old, dec,
+               parts=False, local=False):
+    """D3: local-step weights (apgs/dmm/objectives.py:153-188)."""
+    lib = _lib.load()
+    x = _x3(x)
+    mu = _req(mu, "mu", ndim=4)
+    q_probs, z, z_old = [_req(v, "z/q", ndim=4) for v in (q_probs, z, z_old)]
+    hidden2, hidden2_old = _req(hidden2, "hidden2", ndim=4), _req(hidden2_old, "hidden2_old", ndim=4)
+    b = [_flat(v, "beta/con") for v in (beta, con1, con0, beta_old, con1_old, con0_old)]
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    ps, keep = _prior(dec)
+    w, o = _outs(S, B, N, z.device, parts, local)
+    with torch.cuda.device(z.device), _call("dmm_logw_local", 1, 4 * S * B * (N * (3 * K + 2 * D + 6) + K * D + 3)):
+        check(lib.apgs_dmm_logw_local_f32(ptr(x), ptr(mu), ptr(q_probs), ptr(z), ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(hidden2),
+                                          ptr(z_old), ptr(b[3]), ptr(b[4]), ptr(b[5]), ptr(hidden2_old), C.byref(ps),
+                                          S, B, N, K, D, C.byref(o), _stream()), "apgs_dmm_logw_local_f32")
+    return w
+
+
+def logw_oneshot(x, q_mu, q_sigma, mu, q_probs, z, beta, con1, con0, hidden2, dec, local=False):
+    """one-shot weights (apgs/dmm/objectives.py:80-114)."""
+    lib = _lib.load()
+    x = _x3(x)
+    q_mu, q_sigma, mu = [_req(v, "mu params", ndim=4) for v in (q_mu, q_sigma, mu)]
+    q_probs, z, hidden2 = [_req(v, "z/q/h", ndim=4) for v in (q_probs, z, hidden2)]
+    b = [_flat(v, "beta/con") for v in (beta, con1, con0)]
+    S, B, N, K = z.shape
+    D = x.shape[-1]
+    ps, keep = _prior(dec)
+    w, o = _outs(S, B, N, z.device, False, local)
+    with torch.cuda.device(z.device), _call("dmm_logw_oneshot", 1, 4 * S * B * (N * (2 * K + D + 3) + 3 * K * D + 4)):
+        check(lib.apgs_dmm_logw_oneshot_f32(ptr(x), ptr(q_mu), ptr(q_sigma), ptr(mu), ptr(q_probs), ptr(z), ptr(b[0]), ptr(b[1]),
+                                            ptr(b[2]), ptr(hidden2), C.byref(ps), S, B, N, K, D, C.byref(o), _stream()),
+              "apgs_dmm_logw_oneshot_f32")
+    return w

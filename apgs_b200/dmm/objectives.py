@@ -1,0 +1,119 @@
+"""APG sweep for the DMM ring-mixture task: drop-in for the hot-path functions of apgs/dmm/objectives.py
+(apg_objective :9-56, oneshot :80-114, apg_update_mu :116-151, apg_update_local :153-188,
+resample_variables :190-195).
+
+Each block update evaluates its encoder once (the reference re-runs it with identical inputs for the backward
+kernel, and the decoder MLP twice although only mu moves in the mu step); log-densities, likelihood, the N-sums
+and the f - b difference are one kernel (csrc/dmm.cu).  Forward / evaluation path (gradients: SURVEY.md row N2).
+"""
+import torch
+from torch.distributions.beta import Beta
+from torch.distributions.normal import Normal
+from torch.distributions.one_hot_categorical import OneHotCategorical as cat
+
+from .. import ops
+from . import kernels
+
+
+def _book(trace, result_flags, log_w, log_q, ll, density):
+    if result_flags['loss_required'] or result_flags['ess_required']:
+        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        if result_flags['loss_required']:
+            trace['loss_phi'].append((w * (-log_q)).sum(0).mean().unsqueeze(0))
+            trace['loss_theta'].append((w * (-ll)).sum(0).mean().unsqueeze(0))
+        if result_flags['ess_required']:
+            trace['ess'].append(ess.unsqueeze(0))
+    if result_flags['density_required']:
+        trace['density'].append(density.unsqueeze(0))
+
+
+def apg_objective(models, x, K, result_flags, num_sweeps, resampler):
+    """Amortized Population Gibbs objective in the DMM problem (objectives.py:9-56)."""
+    trace = {'loss_phi': [], 'loss_theta': [], 'ess': [], 'E_mu': [], 'E_z': [], 'E_recon': [], 'density': []}
+    (enc_rws_mu, enc_apg_local, enc_apg_mu, dec) = models
+    if x.dim() == 3:
+        x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)
+    log_w, mu, z, beta, trace = oneshot(enc_rws_mu, enc_apg_local, dec, x, K, trace, result_flags)
+    mu, z, beta = resample_variables(resampler, mu, z, beta, log_weights=log_w)
+    for m in range(num_sweeps - 1):
+        log_w_mu, mu, trace = apg_update_mu(enc_apg_mu, dec, x, z, beta, mu, K, trace, result_flags)
+        mu, z, beta = resample_variables(resampler, mu, z, beta, log_weights=log_w_mu)
+        log_w_z, z, beta, trace = apg_update_local(enc_apg_local, dec, x, mu, z, beta, K, trace, result_flags)
+        mu, z, beta = resample_variables(resampler, mu, z, beta, log_weights=log_w_z)
+    if result_flags['loss_required']:
+        trace['loss_phi'] = torch.cat(trace['loss_phi'], 0)
+        trace['loss_theta'] = torch.cat(trace['loss_theta'], 0)
+    if result_flags['ess_required']:
+        trace['ess'] = torch.cat(trace['ess'], 0)
+    if result_flags['mode_required']:
+        trace['E_mu'] = torch.cat(trace['E_mu'], 0)
+        trace['E_z'] = torch.cat(trace['E_z'], 0)
+        trace['E_recon'] = torch.cat(trace['E_recon'], 0)
+    if result_flags['density_required']:
+        trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def _sample_local(enc_local, x, mu, K):
+    q_probs = enc_local.probs(x, mu, K)
+    z = cat(q_probs, validate_args=False).sample()
+    con1, con0 = enc_local.cons(x, mu, z)
+    beta = Beta(con1, con0, validate_args=False).sample()
+    return q_probs, z, con1, con0, beta
+
+
+def _E_recon(dec, mu, z, h2):
+    mu_expand = torch.gather(mu, -2, z.argmax(-1).unsqueeze(-1).expand(-1, -1, -1, mu.shape[-1]))
+    return (h2 * dec.radi + mu_expand).mean(0).unsqueeze(0)
+
+
+def oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
+    """One-shot predicts mu, z and beta like a normal RWS (objectives.py:80-114)."""
+    q_mu, q_sigma = enc_rws_mu.params(x, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+    mu = Normal(q_mu, q_sigma, validate_args=False).sample()
+    q_probs, z, con1, con0, beta = _sample_local(enc_rws_local, x, mu, K)
+    h2 = dec.hidden2(beta)
+    w = kernels.logw_oneshot(x, q_mu, q_sigma, mu, q_probs, z, beta, con1, con0, h2, dec)
+    _book(trace, result_flags, w.log_w, w.log_q_f, w.ll_f, w.density)
+    if result_flags['mode_required']:
+        trace['E_mu'].append(q_mu.mean(0).unsqueeze(0))
+        trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
+        trace['E_recon'].append(_E_recon(dec, mu, z, h2))
+    return w.log_w, mu, z, beta, trace
+
+
+def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags):
+    """Given local variables {z, beta}, update the centres mu (objectives.py:116-151)."""
+    q_mu, q_sigma = enc_apg_mu.params(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+    mu = Normal(q_mu, q_sigma, validate_args=False).sample()
+    h2 = dec.hidden2(beta)                 # the decoder sees beta only: one evaluation serves f and b
+    w = kernels.logw_mu(x, z, h2, q_mu, q_sigma, mu, mu_old, dec)
+    _book(trace, result_flags, w.log_w, w.log_q_f, w.ll_f, w.density)
+    if result_flags['mode_required']:
+        trace['E_mu'].append(q_mu.mean(0).unsqueeze(0))
+    return w.log_w, mu, trace
+
+
+def apg_update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_flags):
+    """Given mu, update the local variables {z, beta} (objectives.py:153-188)."""
+    q_probs, z, con1, con0, beta = _sample_local(enc_apg_local, x, mu, K)
+    con1_b, con0_b = enc_apg_local.cons(x, mu, z_old)
+    h2, h2_old = dec.hidden2(beta), dec.hidden2(beta_old)
+    need_local = bool(result_flags['loss_required'])
+    w = kernels.logw_local(x, mu, q_probs, z, beta, con1, con0, h2, z_old, beta_old, con1_b, con0_b, h2_old, dec,
+                           local=need_local)
+    if result_flags['loss_required']:
+        w_local, _ = ops.local_weight_stats(w.log_w_local, want_w=True, want_sum=False)
+        trace['loss_phi'][-1] = trace['loss_phi'][-1] + (w_local * (-w.log_q_local)).sum(0).sum(-1).mean().unsqueeze(0)
+        trace['loss_theta'][-1] = trace['loss_theta'][-1] + (w_local * (-w.ll_local)).sum(0).sum(-1).mean().unsqueeze(0)
+    if result_flags['mode_required']:
+        trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
+        trace['E_recon'].append(_E_recon(dec, mu, z, h2))
+    if result_flags['density_required']:
+        trace['density'][-1] = trace['density'][-1] + w.density.unsqueeze(0)
+    return w.log_w, z, beta, trace
+
+
+def resample_variables(resampler, mu, z, beta, log_weights):
+    mu, z, beta = resampler.resample([mu, z, beta], log_weights)
+    return mu, z, beta

@@ -255,6 +255,57 @@ APGS_API int apgs_bmnist_logw_what_f32(const float* q_mu, const float* q_std, co
                               int64_t S, int64_t B, int64_t K, int64_t Z, int64_t T,
                               float* log_w, float* log_q_f, float* density, float* ll_sum, void* stream);
 
+/* ==============================================================================================
+ * DMM ring mixture.  K <= 16 clusters, D <= 8 data dims, N points.
+ * ============================================================================================== */
+
+/* D1  NSS pooling.  replaces apgs/dmm/models.py:134-139 (Enc_apg_mu) and :38-43 (Enc_rws_mu):
+ *   out[s,b,k,:J] = sum_n nss1[s,b,n,:] * nss2[s,b,n,k] / (sum_n nss2[s,b,n,k] + 1e-8),
+ *   out[s,b,k,J:] = cat(prior_mu_mu, prior_mu_sigma);   nss1 (S,B,N,J), nss2 (S,B,N,K), out (S,B,K,J+2D).
+ *   No (S,B,N,K,J) temporaries.                                                                     */
+APGS_API int apgs_dmm_nss_pool_f32(const float* nss1, const float* nss2,
+                          const float* prior_mu_mu, const float* prior_mu_sigma,
+                          int64_t S, int64_t B, int64_t N, int64_t K, int64_t J, int64_t D,
+                          float* out, void* stream);
+
+typedef struct apgs_dmm_prior {       /* HOST struct of DEVICE pointers; apgs/dmm/models.py:163-172 */
+    const float *mu_mu, *mu_sigma;    /* (D)  prior of the centres                    */
+    const float *pi;                  /* (K)  prior of the assignments                */
+    const float *con1, *con0;         /* (1)  Beta prior of the angles                */
+    const float *radi;                /* (1)  decoder radius parameter                */
+    const float *recon_sigma;         /* (1)  likelihood scale                        */
+} apgs_dmm_prior_t;
+typedef struct apgs_dmm_out {         /* every field optional */
+    float *log_w, *log_q_f, *density, *ll_f, *log_w_f, *log_w_b;     /* (S,B)   */
+    float *log_w_local, *log_q_local, *ll_local;                      /* (S,B,N) */
+} apgs_dmm_out_t;
+
+/* x (B,N,D) one copy per instance; z one-hot (S,B,N,K); hidden2 (S,B,N,D) = unit-normalised decoder MLP
+ * output (apgs/dmm/models.py:202-203); beta / con1 / con0 (S,B,N[,1]); mu / q_mu / q_sigma (S,B,K,D).      */
+
+/* D2  mu step.  replaces the arithmetic of apg_update_mu, apgs/dmm/objectives.py:116-151.          */
+APGS_API int apgs_dmm_logw_mu_f32(const float* x, const float* z, const float* hidden2,
+                         const float* q_mu, const float* q_sigma, const float* mu, const float* mu_old,
+                         const apgs_dmm_prior_t* prior,
+                         int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                         const apgs_dmm_out_t* out, void* stream);
+/* D3  {z, beta} step per point (+ sum over points).  replaces apg_update_local, objectives.py:153-188.  */
+APGS_API int apgs_dmm_logw_local_f32(const float* x, const float* mu, const float* q_probs,
+                            const float* z, const float* beta, const float* con1, const float* con0,
+                            const float* hidden2,
+                            const float* z_old, const float* beta_old, const float* con1_old,
+                            const float* con0_old, const float* hidden2_old,
+                            const apgs_dmm_prior_t* prior,
+                            int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                            const apgs_dmm_out_t* out, void* stream);
+/* one-shot weight.  replaces the arithmetic of oneshot, objectives.py:80-114.                       */
+APGS_API int apgs_dmm_logw_oneshot_f32(const float* x, const float* q_mu, const float* q_sigma, const float* mu,
+                              const float* q_probs, const float* z, const float* beta,
+                              const float* con1, const float* con0, const float* hidden2,
+                              const apgs_dmm_prior_t* prior,
+                              int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              const apgs_dmm_out_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

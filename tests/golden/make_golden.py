@@ -266,7 +266,64 @@ def section_bmnist():
     save("bmnist", **out)
 
 
-SECTIONS = {"resampler": section_resampler, "gmm": section_gmm, "stn": section_stn, "bmnist": section_bmnist}
+# ------------------------------------------------------------------------------------- DMM
+def section_dmm():
+    """Reference DMM apg_objective under fixed seeds: whole traces, every per-step log-weight (captured by wrapping the
+    reference's resample_variables) and the oracle's step records, asserted to reproduce them bit for bit."""
+    from apgs.resampler import Resampler
+    from apgs.dmm.apg_training import init_apg_models
+    import apgs.dmm.objectives as O
+    from oracle import dmm as od
+    K, D, N = 4, 2, 60
+    S, B, sweeps = 6, 5, 3
+    out = {"dims": np.array([S, B, N, K, D, sweeps])}
+    torch.manual_seed(0)
+    models = init_apg_models(K, D, 32, 8, 32, 32, 0.5, False, None)
+    torch.manual_seed(0)
+    P = od.make_params(K, D)
+    for mod in P:
+        for k, v in P[mod].items():
+            out["P/%s/%s" % (mod, k)] = v
+    torch.manual_seed(1)
+    x1 = od.simulate(B, N, K, D)
+    x = x1.repeat(S, 1, 1, 1)
+    out["x"] = x1
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    ref_lw = []
+    orig = O.resample_variables
+
+    def rec(resampler, mu, z, beta, log_weights):
+        ref_lw.append(log_weights.clone())
+        return orig(resampler, mu, z, beta, log_weights)
+    for strategy in ("systematic", "multinomial"):
+        del ref_lw[:]
+        O.resample_variables = rec
+        with torch.no_grad():
+            torch.manual_seed(2)
+            tr = O.apg_objective(models, x, K, flags, sweeps, Resampler(strategy, S, False, None))
+            O.resample_variables = orig
+            torch.manual_seed(2)
+            recd = []
+            mine = od.apg_objective(P, od.make_prior(K, D), x, K, flags, sweeps, strategy, record=recd)
+        for k in ("loss_phi", "loss_theta", "ess", "density"):
+            assert torch.equal(tr[k], mine[k]), (strategy, k)
+            out["full_%s_%s" % (strategy, k)] = tr[k]
+        assert len(ref_lw) == len(recd)
+        for i, (a, r) in enumerate(zip(ref_lw, recd)):
+            assert torch.equal(a, r["log_w"]), (strategy, i)
+        if strategy != "systematic":
+            continue
+        for tag, step in (("os", "oneshot"), ("mu", "mu"), ("lo", "local")):
+            i = [j for j, r in enumerate(recd) if r["step"] == step][0]
+            for k, v in recd[i].items():
+                if torch.is_tensor(v):
+                    out["%s_%s" % (tag, k)] = v
+            out["%s_ref_log_w" % tag] = ref_lw[i]
+    save("dmm", **out)
+
+
+SECTIONS = {"resampler": section_resampler, "gmm": section_gmm, "stn": section_stn, "bmnist": section_bmnist,
+            "dmm": section_dmm}
 
 if __name__ == "__main__":
     todo = sys.argv[1:] or list(SECTIONS)

@@ -193,3 +193,54 @@ def test_bmnist_full_objective_reproduces_reference_trace(golden, strategy):
         tr = ob.apg_objective(P, ob.make_prior(), frames, K, flags, sweeps, mm, strategy)
     for k in ("loss_phi", "loss_theta", "ess", "density"):
         torch.testing.assert_close(tr[k], _t(g, "full_%s_%s" % (strategy, k)), rtol=1e-5, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------- DMM
+def _dmm_params(g):
+    P = {}
+    for k in g.files:
+        if k.startswith("P/"):
+            _, mod, name = k.split("/", 2)
+            P.setdefault(mod, {})[name] = torch.from_numpy(g[k])
+    return P
+
+
+def test_dmm_step_weights_teacher_forced(golden):
+    from oracle import dmm as od
+    g = golden("dmm")
+    S, B, N, K, D, sweeps = [int(v) for v in g["dims"]]
+    P, prior = _dmm_params(g), od.make_prior(K, D)
+    x = _t(g, "x").unsqueeze(0).repeat(S, 1, 1, 1)
+    lw = od.mu_step_weights(prior, P["dec"], x, _t(g, "mu_z"), _t(g, "mu_hidden2"), _t(g, "mu_q_mu"), _t(g, "mu_q_sigma"),
+                            _t(g, "mu_mu"), _t(g, "mu_mu_old"))[0]
+    assert torch.equal(lw, _t(g, "mu_ref_log_w"))
+    lw = od.local_step_weights(prior, P["dec"], x, _t(g, "lo_mu"), _t(g, "lo_q_probs"), _t(g, "lo_z"), _t(g, "lo_beta"),
+                               _t(g, "lo_con1"), _t(g, "lo_con0"), _t(g, "lo_hidden2"), _t(g, "lo_z_old"), _t(g, "lo_beta_old"),
+                               _t(g, "lo_con1_old"), _t(g, "lo_con0_old"), _t(g, "lo_hidden2_old"))[1]
+    assert torch.equal(lw, _t(g, "lo_ref_log_w"))
+    lw = od.oneshot_weights(prior, P["dec"], x, _t(g, "os_q_mu"), _t(g, "os_q_sigma"), _t(g, "os_mu"), _t(g, "os_q_probs"),
+                            _t(g, "os_z"), _t(g, "os_beta"), _t(g, "os_con1"), _t(g, "os_con0"), _t(g, "os_hidden2"))[0]
+    assert torch.equal(lw, _t(g, "os_ref_log_w"))
+    # encoders reproduce the recorded proposal parameters from the stored weights
+    q_mu, q_sigma = od.enc_mu_params(P["enc_apg_mu"], torch.cat((x, _t(g, "mu_z")), -1), prior)
+    assert torch.equal(q_mu, _t(g, "mu_q_mu")) and torch.equal(q_sigma, _t(g, "mu_q_sigma"))
+    assert torch.equal(od.enc_local_probs(P["enc_apg_local"], x, _t(g, "lo_mu"), K), _t(g, "lo_q_probs"))
+
+
+@pytest.mark.parametrize("strategy", ["systematic", "multinomial"])
+def test_dmm_full_objective_reproduces_reference_trace(golden, strategy):
+    from oracle import dmm as od
+    g = golden("dmm")
+    S, B, N, K, D, sweeps = [int(v) for v in g["dims"]]
+    torch.manual_seed(0)
+    P = od.make_params(K, D)
+    for mod in P:
+        for k in P[mod]:
+            assert torch.equal(P[mod][k], _dmm_params(g)[mod][k])
+    x = _t(g, "x").repeat(S, 1, 1, 1)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    torch.manual_seed(2)
+    with torch.no_grad():
+        tr = od.apg_objective(P, od.make_prior(K, D), x, K, flags, sweeps, strategy)
+    for k in ("loss_phi", "loss_theta", "ess", "density"):
+        torch.testing.assert_close(tr[k], _t(g, "full_%s_%s" % (strategy, k)), rtol=1e-6, atol=1e-5)
