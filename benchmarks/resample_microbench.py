@@ -69,8 +69,9 @@ def main():
     rows = []
     if a.gmm or True:
         for strat in ("systematic", "multinomial"):
-            rows.append(run_case(1000, 1024, [24, 24, 720], strat, 2.0, flush))
-            print(json.dumps(rows[-1]), flush=True)
+            for sigma in (0.1, 2.0, 10.0):            # ESS ~ S, ~ S/50, ~ 1: distinct ancestors read from HBM vary
+                rows.append(run_case(1000, 1024, [24, 24, 720], strat, sigma, flush))
+                print(json.dumps(rows[-1]), flush=True)
         rows.append(run_case(100, 256, [32, 3200, 800], "systematic", 2.0, flush))   # DMM C3
         print(json.dumps(rows[-1]), flush=True)
     if not a.gmm:

@@ -258,3 +258,21 @@ def test_multinomial_distribution_chi2():
     counts = torch.zeros(S, B, device=DEV).scatter_add_(0, a, torch.ones(S, B, device=DEV))
     chi2 = (((counts - S * w) ** 2) / (S * w)).sum(0)           # dof = S-1, sd = sqrt(2(S-1))
     assert bool(((chi2 - (S - 1)).abs() < 6 * (2 * (S - 1)) ** 0.5).all()), chi2
+
+
+@pytest.mark.parametrize("S,B,shape", [(203, 67, (60, 3)), (50, 33, (200, 4)), (1000, 13, (50, 4)), (77, 129, (64,))])
+def test_gather_large_rows(S, B, shape):
+    """> 8 MB latents with 720 B / 3200 B / 800 B / 256 B rows next to a 24 B latent in the same launch:
+    ragged last chunk, int32 and int64 ancestors."""
+    ops = _ops()
+    torch.manual_seed(S + B)
+    reps = max(1, int(9e6 // (S * B * int(np.prod(shape)) * 4)) + 1)
+    Sx = S * reps                                           # grow S until the latent is > 8 MB
+    anc = torch.randint(0, Sx, (Sx, B), device=DEV)
+    v = torch.randn(Sx, B, *shape, device=DEV)
+    small = torch.randn(Sx, B, 3, 2, device=DEV)
+    for dt in (torch.int64, torch.int32):
+        o, o2 = ops.gather_ancestors([v, small], anc.to(dt))
+        idx = anc.view(Sx, B, *([1] * len(shape))).expand_as(v)
+        assert torch.equal(o, torch.gather(v, 0, idx))
+        assert torch.equal(o2, torch.gather(small, 0, anc.view(Sx, B, 1, 1).expand_as(small)))
