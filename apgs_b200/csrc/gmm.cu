@@ -209,34 +209,44 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
     float lq_mu_f = 0.f, lq_tau_f = 0.f, lp_mu_f = 0.f, lp_tau_f = 0.f;
     float lq_mu_b = 0.f, lq_tau_b = 0.f, lp_mu_b = 0.f, lp_tau_b = 0.f;
     if (valid) {
+        // One (k,d) element per lane.  The log-densities are written with the logs shared between the terms that
+        // need them:  log(1/sqrt(nu*tau)) = -(log nu + log tau)/2,  (1/sqrt(nu*tau))^2 = 1/(nu*tau),  sigma^2 = 1/tau.
+        // These identities move individual terms by a few ulp relative to the reference's operation order
+        // (1/sqrt then square then log again, quirk Q3) -- two orders of magnitude inside the 1e-5 budget -- and
+        // cut the per-particle transcendental count from 20 to 5 per element.
         float* tab = s_tab + (size_t)p * (2 * KD * 3);
         for (int e = j; e < KD; e += LANES) {
             const float tf = __ldg(a.tau_f + r * KD + e), mf = __ldg(a.mu_f + r * KD + e);
             float tbk = tf, mbk = mf;
             if (has_bwd) { tbk = __ldg(a.tau_b + r * KD + e); mbk = __ldg(a.mu_b + r * KD + e); }
-            {   // likelihood tables: sigma = 1/sqrt(tau) (models.py:177)
-                const float sg = inv_sqrt_ref(tf);
-                tab[e * 3 + 0] = mf;
-                tab[e * 3 + 1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sg, sg)));
-                tab[e * 3 + 2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
-                const float sb = inv_sqrt_ref(tbk);
-                tab[(KD + e) * 3 + 0] = mbk;
-                tab[(KD + e) * 3 + 1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sb, sb)));
-                tab[(KD + e) * 3 + 2] = __fadd_rn(logf(sb), LOG_SQRT_2PI_F);
-            }
+            const float Ltf = logf(tf), Ltb = has_bwd ? logf(tbk) : Ltf;
+            tab[e * 3 + 0] = mf;
+            tab[e * 3 + 1] = 0.5f * tf;                                   // 1 / (2 sigma^2)
+            tab[e * 3 + 2] = fmaf(-0.5f, Ltf, LOG_SQRT_2PI_F);            // log sigma + c
+            tab[(KD + e) * 3 + 0] = mbk;
+            tab[(KD + e) * 3 + 1] = 0.5f * tbk;
+            tab[(KD + e) * 3 + 2] = fmaf(-0.5f, Ltb, LOG_SQRT_2PI_F);
             if (has_eta) {
                 const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
                 const float qa = __ldg(a.pa + r * KD + e), qb = __ldg(a.pb + r * KD + e);
                 const float qm = __ldg(a.pm + r * KD + e), qn = __ldg(a.pn + r * KD + e);
-                lq_tau_f += gamma_lp(tf, qa, qb);
-                lq_mu_f += normal_lp(mf, qm, inv_sqrt_ref(__fmul_rn(qn, tf)));
-                lp_tau_f += gamma_lp(tf, a0, b0);
-                lp_mu_f += normal_lp(mf, m0, inv_sqrt_ref(__fmul_rn(n0, tf)));
+                // Gamma(c, r).log_prob(t) = c log r + (c-1) log t - r t - lgamma(c)      (gamma.py:89-98)
+                const float gq = fmaf(qa, logf(qb), -lgammaf(qa)), gp = fmaf(a0, logf(b0), -lgammaf(a0));
+                // Normal(m, 1/sqrt(n t)).log_prob(v) = -(v-m)^2 n t / 2 + (log n + log t)/2 - c   (normal.py:87-101)
+                const float Lqn = logf(qn), Ln0 = logf(n0);
+                {
+                    const float dq = mf - qm, dp = mf - m0;
+                    lq_tau_f += fmaf(qa - 1.f, Ltf, gq) - qb * tf;
+                    lp_tau_f += fmaf(a0 - 1.f, Ltf, gp) - b0 * tf;
+                    lq_mu_f += fmaf(-0.5f * dq * dq, qn * tf, 0.5f * (Lqn + Ltf)) - LOG_SQRT_2PI_F;
+                    lp_mu_f += fmaf(-0.5f * dp * dp, n0 * tf, 0.5f * (Ln0 + Ltf)) - LOG_SQRT_2PI_F;
+                }
                 if (has_bwd) {
-                    lq_tau_b += gamma_lp(tbk, qa, qb);
-                    lq_mu_b += normal_lp(mbk, qm, inv_sqrt_ref(__fmul_rn(qn, tbk)));
-                    lp_tau_b += gamma_lp(tbk, a0, b0);
-                    lp_mu_b += normal_lp(mbk, m0, inv_sqrt_ref(__fmul_rn(n0, tbk)));
+                    const float dq = mbk - qm, dp = mbk - m0;
+                    lq_tau_b += fmaf(qa - 1.f, Ltb, gq) - qb * tbk;
+                    lp_tau_b += fmaf(a0 - 1.f, Ltb, gp) - b0 * tbk;
+                    lq_mu_b += fmaf(-0.5f * dq * dq, qn * tbk, 0.5f * (Lqn + Ltb)) - LOG_SQRT_2PI_F;
+                    lp_mu_b += fmaf(-0.5f * dp * dp, n0 * tbk, 0.5f * (Ln0 + Ltb)) - LOG_SQRT_2PI_F;
                 }
             }
         }
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
 
     stage_wait(&bar, 0);           // tile + tables visible
 
-    KahanF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;
+    PlainF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;      // <= ceil(N/LANES) terms per lane
     if (valid) {
         const float* zf = s_zf + (size_t)p * N * K;
         const float* zb = s_zb + (size_t)p * N * K;
@@ -301,7 +311,8 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
                 float sq = 0.f;
 #pragma unroll
                 for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, qq[n * K + k]);
-                const float lqf = logf(fminf(fmaxf(__fdiv_rn(qq[n * K + lf], sq), FLT_EPS_F), 1.f - FLT_EPS_F));
+                const float rsq = rcp_ftz(sq);
+                const float lqf = log_fast(fminf(fmaxf(qq[n * K + lf] * rsq, FLT_EPS_F), 1.f - FLT_EPS_F));
                 float lpf = logpi[0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) if (lf == k) lpf = logpi[k];
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
                 A_lpzf.add(lpf);
                 float lqb = 0.f, lpb = 0.f;
                 if (has_bwd) {
-                    lqb = logf(fminf(fmaxf(__fdiv_rn(qq[n * K + lb], sq), FLT_EPS_F), 1.f - FLT_EPS_F));
+                    lqb = log_fast(fminf(fmaxf(qq[n * K + lb] * rsq, FLT_EPS_F), 1.f - FLT_EPS_F));
                     lpb = logpi[0];
 #pragma unroll
                     for (int k = 1; k < K; ++k) if (lb == k) lpb = logpi[k];

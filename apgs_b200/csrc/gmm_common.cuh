@@ -50,6 +50,14 @@ struct KahanF {
     __device__ __forceinline__ double value() const { return (double)s - (double)c; }
 };
 
+// plain fp32 partial sum of a handful of terms (same interface as KahanF)
+struct PlainF {
+    float s;
+    __device__ __forceinline__ PlainF() : s(0.f) {}
+    __device__ __forceinline__ void add(float v) { s = __fadd_rn(s, v); }
+    __device__ __forceinline__ double value() const { return (double)s; }
+};
+
 // tanh with ~1e-7 absolute error from a PRE-SCALED argument a = 2*log2(e)*x:
 //   tanh(x) = 1 - 2 / (2^a + 1)      -> MUFU.EX2, FADD, MUFU.RCP, FFMA  (flush-to-zero forms: no denormal
 // fix-up code; 2^a underflowing to 0 gives -1 and overflowing to +inf gives +1, the correct saturations)
@@ -63,6 +71,13 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// log with the SFU (lg2.approx, abs error ~2^-22 * ln 2 on the result): used for log q of a categorical, whose
+// magnitude is <= 16 (eps clamp), so the error is ~1e-7 relative to the sums it enters
+__device__ __forceinline__ float log_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.693147180559945309417f;
 }
 __device__ __forceinline__ float tanh_prescaled(float a) {
     return fmaf(rcp_ftz(ex2_ftz(a) + 1.f), -2.f, 1.f);

@@ -67,18 +67,17 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         float tk[KD], mk[KD];
 #pragma unroll
         for (int e = 0; e < KD; ++e) { tk[e] = __ldg(a.tau + r * KD + e); mk[e] = __ldg(a.mu + r * KD + e); }
-        for (int i = j; i < K * H; i += LANES) {                 // e[k][h] = b1 + W1m mu_k + W1t tau_k
-            const int k = i / H, h = i % H;
-            float acc = __ldg(a.b1 + h);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                float mkd = 0.f, tkd = 0.f;
+        for (int k = 0; k < K; ++k) {                              // e[k][h] = b1 + W1m mu_k + W1t tau_k
+            for (int h = j; h < H; h += LANES) {
+                float acc = __ldg(a.b1 + h);
 #pragma unroll
-                for (int kk = 0; kk < K; ++kk) if (kk == k) { mkd = mk[kk * D + d]; tkd = tk[kk * D + d]; }
-                acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mkd, acc);
-                acc = fmaf(__ldg(a.W1 + h * 3 * D + 2 * D + d), tkd, acc);
+                for (int d = 0; d < D; ++d) {
+                    acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mk[k * D + d], acc);
+                    acc = fmaf(__ldg(a.W1 + h * 3 * D + 2 * D + d), tk[k * D + d], acc);
+                }
+                s_e[p * EP + k * H + h] = TANH_PRESCALE * acc;
             }
-            s_e[p * EP + i] = TANH_PRESCALE * acc;
         }
         float* tab = s_tab + (size_t)p * (KD * 3);
         for (int e = j; e < KD; e += LANES) {
@@ -102,7 +101,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     }
     stage_wait(&bar, 0);
 
-    KahanF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;
+    PlainF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;     // <= ceil(N/LANES) terms per lane
     if (valid) {
         const float* zo = s_zo + (size_t)p * N * K;
         float* zn = s_zn + (size_t)p * N * K;
@@ -133,8 +132,23 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float e = ev[k * H + h];
+                    if (PB == 4) {
+                        // tanh = 1 - 2 / (2^a + 1) for four points with ONE reciprocal (batch inversion): the SFU
+                        // does 1.25 instead of 2 operations per tanh.  a is clamped at 30 so the product of the four
+                        // denominators stays below 2^121; 2 / (2^30 + 1) < eps/2, i.e. tanh is already 1.0f there.
+                        float y[4];
 #pragma unroll
-                    for (int q = 0; q < PB; ++q) logit[q][k] = fmaf(w2, tanh_prescaled(xh[q] + e), logit[q][k]);
+                        for (int q = 0; q < 4; ++q) y[q] = ex2_ftz(fminf(xh[q] + e, 30.f)) + 1.f;
+                        const float p01 = y[0] * y[1], p23 = y[2] * y[3];
+                        const float r = rcp_ftz(p01 * p23);
+                        const float r01 = r * p23, r23 = r * p01;
+                        const float inv[4] = {r01 * y[1], r01 * y[0], r23 * y[3], r23 * y[2]};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) logit[q][k] = fmaf(w2, fmaf(inv[q], -2.f, 1.f), logit[q][k]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) logit[q][k] = fmaf(w2, tanh_prescaled(xh[q] + e), logit[q][k]);
+                    }
                 }
             }
             // ---- per point: softmax, draw, log-densities
@@ -147,12 +161,14 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 for (int k = 1; k < K; ++k) mx = fmaxf(mx, logit[q][k]);
                 float pr[K], se = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) { pr[k] = expf(logit[q][k] - mx); se += pr[k]; }
+                for (int k = 0; k < K; ++k) { pr[k] = ex2_ftz((logit[q][k] - mx) * 1.4426950408889634f); se += pr[k]; }
+                const float rse = rcp_ftz(se);
 #pragma unroll
-                for (int k = 0; k < K; ++k) pr[k] = __fdiv_rn(pr[k], se);        // F.softmax(., -1)
+                for (int k = 0; k < K; ++k) pr[k] *= rse;                         // F.softmax(., -1)
                 float sq = 0.f;
 #pragma unroll
                 for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, pr[k]);            // Categorical renormalisation
+                const float rsq = rcp_ftz(sq);
                 if (a.q_probs != nullptr) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) a.q_probs[(r * N + n) * K + k] = pr[k];
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 float plf = pr[0], lpf = logpi[0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) if (lf == k) { plf = pr[k]; lpf = logpi[k]; }
-                const float lqf = logf(fminf(fmaxf(__fdiv_rn(plf, sq), FLT_EPS_F), 1.f - FLT_EPS_F));
+                const float lqf = log_fast(fminf(fmaxf(plf * rsq, FLT_EPS_F), 1.f - FLT_EPS_F));
                 float llf = 0.f;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                     float plb = pr[0], lpb = logpi[0];
 #pragma unroll
                     for (int k = 1; k < K; ++k) if (lb == k) { plb = pr[k]; lpb = logpi[k]; }
-                    const float lqb = logf(fminf(fmaxf(__fdiv_rn(plb, sq), FLT_EPS_F), 1.f - FLT_EPS_F));
+                    const float lqb = log_fast(fminf(fmaxf(plb * rsq, FLT_EPS_F), 1.f - FLT_EPS_F));
                     float llb = 0.f;
 #pragma unroll
                     for (int d = 0; d < D; ++d) {

@@ -20,9 +20,10 @@ class _Profile(object):
         self.launches = 0
         self.events = False
         self.records = []          # (name, start_event, end_event, algorithmic_bytes)
+        self.notes = {}            # name -> list of device scalars recorded by callers (read after a synchronize)
 
     def reset(self, events=False):
-        self.launches, self.events, self.records = 0, events, []
+        self.launches, self.events, self.records, self.notes = 0, events, [], {}
 
     def summary(self):
         """name -> dict(calls, ms_total, ms_avg, bytes_per_call, gbs) (call after a synchronize)."""

@@ -78,6 +78,10 @@ class Resampler():
             # bench.py roofline accounting: same two kernels, timed separately
             anc32 = ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms,
                                          cdf_mode=self.cdf_mode, index_dtype=torch.int32)
+            # fraction of source rows that are actually read (distinct ancestors): the rest is served by L2
+            srt = anc32 if self.strategy == "systematic" else anc32.sort(0).values
+            distinct = ((srt[1:] != srt[:-1]).sum() + B).float() / float(S * B)
+            ops.PROFILE.notes.setdefault("distinct_ancestor_frac", []).append(distinct)
             return ops.gather_ancestors(latents, anc32)
         outs, anc, stats = ops.resample(latents, log_w=log_weights, strategy=self.strategy,
                                         uniforms=uniforms, cdf_mode=self.cdf_mode,

@@ -193,7 +193,11 @@ def run_ours(args):
         step(x_dev)
         torch.cuda.synchronize()
         prof = ops.PROFILE.summary()
+        dfr = ops.PROFILE.notes.get("distinct_ancestor_frac", [])
+        distinct_frac = float(torch.stack(dfr).mean()) if dfr else None
         ops.PROFILE.reset(events=False)
+        # ---- the same resample step on near-uniform weights (all ancestors distinct: every source row is read from HBM)
+        probe = resample_probe(S, B, dev)
         final = step(x_dev)
 
     work = world * S * B * sweeps * args.steps
@@ -203,12 +207,25 @@ def run_ours(args):
     g = prof.get("gather_ancestors", None)
     roof = None
     if g:
-        roof = {"kernel": "k_gather (ancestor gather of tau, mu, z; apgs_gather_ancestors)", "bound": "hbm",
-                "achieved": g["gbs"], "peak": peak, "unit": "GB/s", "frac": g["gbs"] / peak, "traffic": None,
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_bench_traffic.json")))["k_gather"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        inner = 2 * (K_CL * D_X * 4) + N_PTS * K_CL * 4
+        uniq = None if distinct_frac is None else S * B * (4 + inner * (1 + distinct_frac))
+        roof = {"kernel": "k_gather (ancestor gather of tau, mu, z; the dominant kernel of the resample step)", "bound": "hbm",
+                "achieved": g["gbs"], "peak": peak, "unit": "GB/s", "frac": g["gbs"] / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": g["bytes_per_call"],
                 "avg_launch_ms": g["ms_avg"], "launches_timed": g["calls"],
-                "note": "CUDA events on the launching stream around each launch inside a profiled step; "
-                        "traffic from ncu is recorded in profiles/"}
+                "distinct_ancestor_frac": distinct_frac,
+                "achieved_unique_bytes": None if uniq is None else uniq / g["ms_avg"] / 1e6,
+                "all_distinct_probe": probe,
+                "note": "achieved = SURVEY 8d bytes (4 + 2*768 B per particle, index read + every row read and written once) / "
+                        "CUDA-event time of each launch on the launching stream.  With random-init encoders the weights are "
+                        "degenerate (ESS ~ 1): almost all particles copy the same few ancestors, the reads hit L2 and the kernel is "
+                        "write-bound, so achieved exceeds the copy peak; achieved_unique_bytes counts each distinct source row once, "
+                        "and all_distinct_probe times the same step on near-uniform weights where every row comes from HBM."}
     if rank == 0:
         line = {"metric": "particle-sweeps/sec", "value": value, "unit": "particle-sweeps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -228,6 +245,39 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def resample_probe(S, B, dev, iters=10):
+    """resample step (ancestors + gather of tau, mu, z) on log-weights ~ N(0, 0.1^2): ESS ~ S, so the gather reads
+    every source row once -- algorithmic bytes == DRAM traffic."""
+    from apgs_b200 import ops
+    from apgs_b200.resampler import Resampler
+    peak, _ = peaks()
+    torch.manual_seed(123)
+    lw = torch.randn(S, B, device=dev) * 0.1
+    lat = [torch.randn(S, B, K_CL, D_X, device=dev), torch.randn(S, B, K_CL, D_X, device=dev),
+           torch.randn(S, B, N_PTS, K_CL, device=dev)]
+    r = Resampler('systematic', S, True, dev)
+    u = r.draw_uniforms(S, B, dev)
+    anc = ops.sample_ancestors(log_w=lw, strategy='systematic', uniforms=u, index_dtype=torch.int32)
+
+    def med(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+    t_g = med(lambda: ops.gather_ancestors(lat, anc))
+    t_r = med(lambda: ops.resample(lat, log_w=lw, strategy='systematic', uniforms=u))
+    nbytes = S * B * (4 + 2 * (2 * K_CL * D_X * 4 + N_PTS * K_CL * 4))
+    return {"gather_ms": t_g, "gather_GBs": nbytes / t_g / 1e6, "gather_frac": nbytes / t_g / 1e6 / peak,
+            "resample_step_ms": t_r, "resample_step_GBs": nbytes / t_r / 1e6, "resample_step_frac": nbytes / t_r / 1e6 / peak}
 
 
 def main():
