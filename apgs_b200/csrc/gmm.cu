@@ -32,15 +32,14 @@ struct NssArgs {
     int N;
 };
 
-template <int K, int D, int P, int LANES>
+template <int K, int D, int P, int LANES, bool FUSED, bool HAS_Z>
 __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
     __shared__ float s_wg[K * (D + K) + K], s_wo[D * (D + K) + D];
     const int N = a.N;
-    const bool fused = a.gamma == nullptr;
-    const bool has_z = a.z != nullptr;
-    const int IN = D + (has_z ? K : 0);                          // input width of the heads
+    constexpr bool fused = FUSED, has_z = HAS_Z;
+    constexpr int IN = D + (HAS_Z ? K : 0);                      // input width of the heads
     float* s_g = reinterpret_cast<float*>(smem);                 // P*N*K  (gamma, or z when fused)
     float* s_x = s_g + (size_t)P * N * K;                        // P*N*D  (xp; unused when fused)
     const long long r0 = (long long)blockIdx.x * P;
@@ -83,17 +82,19 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
                 for (int k = 0; k < K; ++k) gv[k] = g[n * K + k];
             } else {
                 // the two Linear heads on cat(x_n, z_n) (models.py:17-22,56-65) and the softmax over k
-                float in[D + K];
+                float in[IN];
 #pragma unroll
                 for (int d = 0; d < D; ++d) in[d] = __ldg(xb + n * D + d);
+                if (HAS_Z) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) in[D + k] = has_z ? g[n * K + k] : 0.f;
+                    for (int k = 0; k < K; ++k) in[D + (HAS_Z ? k : 0)] = g[n * K + k];
+                }
                 float lg[K], mx = -INFINITY;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     float acc = s_wg[K * (D + K) + k];
 #pragma unroll
-                    for (int i = 0; i < D + K; ++i) if (i < IN) acc = fmaf(s_wg[k * IN + i], in[i], acc);
+                    for (int i = 0; i < IN; ++i) acc = fmaf(s_wg[k * IN + i], in[i], acc);
                     lg[k] = acc;
                     mx = fmaxf(mx, acc);
                 }
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
                 for (int d = 0; d < D; ++d) {
                     float acc = s_wo[D * (D + K) + d];
 #pragma unroll
-                    for (int i = 0; i < D + K; ++i) if (i < IN) acc = fmaf(s_wo[d * IN + i], in[i], acc);
+                    for (int i = 0; i < IN; ++i) acc = fmaf(s_wo[d * IN + i], in[i], acc);
                     xv[d] = acc;
                 }
             }
@@ -179,13 +180,14 @@ struct GmmWArgs {
     float *lw_local, *lq_local;                           // (R, N), optional (Z step)
 };
 
-template <int K, int D, int P, int LANES>
+template <int K, int D, int P, int LANES, int STEP>
 __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
     constexpr int KD = K * D;
-    const int N = a.N, step = a.step;
-    const bool has_eta = step != STEP_Z, has_z = step != STEP_ETA, has_bwd = step != STEP_ONESHOT;
+    const int N = a.N;
+    constexpr int step = STEP;
+    constexpr bool has_eta = step != STEP_Z, has_z = step != STEP_ETA, has_bwd = step != STEP_ONESHOT;
     const bool zb_distinct = has_bwd && (a.z_b != a.z_f);
     const size_t tile_f = (size_t)P * N * K;
     float* s_zf = reinterpret_cast<float*>(smem);
@@ -387,7 +389,9 @@ template <int K, int D>
 static int launch_nss(const NssArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)kP * a.N * (K + D) * 4;       // (the fused variant only uses the first K part)
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_nss_posterior: N=%d too large for one tile", a.N);
-    auto kern = k_gmm_nss_posterior<K, D, kP, kLanes>;
+    void (*kern)(NssArgs) = k_gmm_nss_posterior<K, D, kP, kLanes, false, false>;
+    if (a.gamma == nullptr) kern = a.z != nullptr ? k_gmm_nss_posterior<K, D, kP, kLanes, true, true>
+                                                  : k_gmm_nss_posterior<K, D, kP, kLanes, true, false>;
     if (smem > 48 * 1024)
         APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     const long long grid = (a.R + kP - 1) / kP;
@@ -402,7 +406,10 @@ static int launch_weights(const GmmWArgs& a, cudaStream_t st) {
     const int ntile = 1 + ((has_bwd && a.z_b != a.z_f) ? 1 : 0) + (has_z ? 1 : 0);
     const size_t smem = (size_t)kP * a.N * K * 4 * ntile + (size_t)kP * 2 * K * D * 3 * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_logw: N=%d too large for one tile", a.N);
-    auto kern = k_gmm_weights<K, D, kP, kLanes>;
+    void (*kern)(GmmWArgs) = k_gmm_weights<K, D, kP, kLanes, STEP_ONESHOT>;
+    if (a.step == STEP_ETA) kern = k_gmm_weights<K, D, kP, kLanes, STEP_ETA>;
+    if (a.step == STEP_Z) kern = k_gmm_weights<K, D, kP, kLanes, STEP_Z>;
+    if (a.step == STEP_JOINT) kern = k_gmm_weights<K, D, kP, kLanes, STEP_JOINT>;
     if (smem > 48 * 1024)
         APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     const long long grid = (a.R + kP - 1) / kP;

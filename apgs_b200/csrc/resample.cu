@@ -354,9 +354,12 @@ static int launch_ancestors(AncArgs a, void* workspace, size_t workspace_bytes, 
 // Output-stationary: consecutive threads own consecutive 16/8/4-byte vectors of the dense output,
 // so stores are perfectly coalesced and each source chunk is read with full-width vectors.  The
 // int64 gather index the reference materialises (apgs/resampler.py:48,53) never exists.
-// (A cp.async.bulk / TMA variant -- one bulk load per 720 B source row into a shared-memory ring, one bulk
-// store per output tile -- was measured at 3.8 TB/s against 5.7-6.4 TB/s for this kernel: the copy engine
-// spends ~120 cycles per sub-KB request, so row-granular gathers stay on LDG.128/STG.128; DESIGN.md.)
+// Variants measured on B200 at the GMM shape (ms for all-distinct / sigma=2 / degenerate weights):
+//   this flat output-stationary mapping, 8 x 16 B per thread ......... 0.278 / 0.245 / 0.194
+//   row-stationary (G lanes per row, 4 rows in flight per thread) .... 0.298 / 0.232 / 0.173
+//   warp-span (32 rows per warp, source offsets by shuffle) .......... 0.320 / 0.258 / 0.227
+//   cp.async.bulk (TMA) row loads into a shared ring + bulk store ..... 0.417 (copy engine ~120 cycles / sub-KB request)
+// The flat mapping wins where it matters (every row read from HBM), so it is the one kept.
 // =============================================================================================
 struct GLat {
     const char* src;
@@ -450,14 +453,13 @@ static int launch_gather(const int* anc32, const long long* anc64, long long S, 
     if (n < 0 || n > APGS_MAX_LATENTS) return fail(APGS_E_BADARG, "gather: n_latents=%d out of [0,%d]", n, APGS_MAX_LATENTS);
     if ((anc32 == nullptr) == (anc64 == nullptr)) return fail(APGS_E_BADARG, "gather: exactly one of anc32/anc64 must be given");
     if (n == 0 || S == 0 || B == 0) return 0;
-    for (int i = 0; i < n; ++i)
-        if (lat[i].src == nullptr || lat[i].dst == nullptr || lat[i].inner_bytes <= 0)
-            return fail(APGS_E_BADARG, "gather: latent %d has null pointer or inner_bytes<=0", i);
     GatherArgs g;
     g.n = n; g.anc32 = anc32; g.anc64 = anc64; g.S = S; g.B = B;
     unsigned long long blocks = 0;
     for (int i = 0; i < n; ++i) {
         const apgs_latent_t& a = lat[i];
+        if (a.src == nullptr || a.dst == nullptr || a.inner_bytes <= 0)
+            return fail(APGS_E_BADARG, "gather: latent %d has null pointer or inner_bytes<=0", i);
         unsigned int vlog = 4;
         while (vlog > 0 && ((a.inner_bytes & ((1ll << vlog) - 1)) != 0 ||
                             !aligned(a.src, 1u << vlog) || !aligned(a.dst, 1u << vlog))) --vlog;
