@@ -25,6 +25,35 @@ def _x_inst(ob):
     return ob[0] if ob.dim() == 4 else ob
 
 
+def needs_grad(*modules):
+    """True when autograd is recording and any parameter of the given encoders requires grad (training)."""
+    return torch.is_grad_enabled() and any(p.requires_grad for m in modules for p in m.parameters())
+
+
+def posterior_eta_torch(xp, gamma, prior_ng):
+    """Differentiable PyTorch form of G1 (apgs/gmm/kls_gmm.py:92-119, quirks Q1/Q2 included) used ONLY to build the
+    autograd graph of log q in training mode; the forward numbers of the sweep come from the kernels."""
+    prior_alpha, prior_beta, prior_mu, prior_nu = prior_ng
+    s1 = gamma.sum(2).unsqueeze(-1)
+    s2 = torch.einsum('sbnk,sbnd->sbkd', gamma, xp)
+    s3 = torch.einsum('sbnk,sbnd->sbkd', gamma, xp ** 2)
+    cnt = s1.expand_as(s2)
+    cnt = torch.where(cnt == 0.0, torch.ones_like(cnt), cnt)                       # Q1
+    x_bar = s2 / cnt
+    alpha = prior_alpha + cnt / 2
+    nu = prior_nu + cnt
+    mu = (prior_mu * prior_nu + s2) / (cnt + prior_nu)
+    beta = prior_beta + (s3 - (s2 ** 2) / cnt) / 2. + (cnt * prior_nu / (cnt + prior_nu)) * ((x_bar - prior_nu) ** 2) / 2.   # Q2
+    return alpha, beta, mu, nu
+
+
+def eta_log_q_torch(post, tau, mu):
+    """differentiable log q(tau, mu) summed over (K, D) (apgs/gmm/objectives.py:167)."""
+    alpha, beta, mu_q, nu_q = post
+    lq = Gamma(alpha, beta, validate_args=False).log_prob(tau).sum(-1).sum(-1)
+    return lq + Normal(mu_q, 1. / (nu_q * tau).sqrt(), validate_args=False).log_prob(mu).sum(-1).sum(-1)
+
+
 class _PriorNG(object):
     def __init__(self, prior_ng):
         self.prior_alpha, self.prior_beta, self.prior_mu, self.prior_nu = prior_ng
@@ -59,13 +88,20 @@ class Enc_rws_eta(nn.Module):
         x = _x_inst(ob)
         S = ob.shape[0] if ob.dim() == 4 else S
         # the heads depend on the data only: evaluate once per instance, not once per particle
-        if self.fused and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+        if self.fused:
             post = kernels.eta_posterior_fused(x, None, (self.gamma[0].weight, self.gamma[0].bias,
                                                          self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng))
         else:
             xp, gam = self.ob(x), self.gamma(x)                               # (B,N,D), (B,N,K)
             post = kernels.nss_posterior(xp.unsqueeze(0), gam.unsqueeze(0), _PriorNG(prior_ng))   # (1,B,K,D)
         return tuple(v.expand(S, -1, -1, -1).contiguous() for v in post)
+
+    def params_torch(self, ob, prior_ng, S=None):
+        """same parameters through PyTorch ops only (autograd graph for training)."""
+        x = _x_inst(ob)
+        S = ob.shape[0] if ob.dim() == 4 else S
+        post = posterior_eta_torch(self.ob(x).unsqueeze(0), self.gamma(x).unsqueeze(0), prior_ng)
+        return tuple(v.expand(S, -1, -1, -1) for v in post)
 
     def forward(self, ob, prior_ng, sampled=True, tau_old=None, mu_old=None):
         return _eta_trace(self.params(ob, prior_ng), sampled, tau_old, mu_old)
@@ -93,11 +129,16 @@ class Enc_apg_eta(nn.Module):
     fused = True
 
     def params(self, ob, z, prior_ng):
-        if self.fused and not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+        if self.fused:
             return kernels.eta_posterior_fused(ob, z, (self.gamma[0].weight, self.gamma[0].bias,
                                                        self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng))
         xp, gam = self.heads(ob, z)
         return kernels.nss_posterior(xp, gam, _PriorNG(prior_ng))
+
+    def params_torch(self, ob, z, prior_ng):
+        """same parameters through PyTorch ops only (autograd graph for training)."""
+        xp, gam = self.heads(ob, z)
+        return posterior_eta_torch(xp, gam, prior_ng)
 
     def forward(self, ob, z, prior_ng, sampled=True, tau_old=None, mu_old=None):
         return _eta_trace(self.params(ob, z, prior_ng), sampled, tau_old, mu_old)

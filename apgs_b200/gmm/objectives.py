@@ -12,8 +12,11 @@ Differences in how the work is done:
     (tau, mu, z) with no int64 index expansion;
   * `x` may be passed as (B,N,D); the reference's S-replicated (S,B,N,D) is accepted and only
     its first slice is read.
-Gradients: this module is the evaluation path (the reference's budget_analysis flags,
-apgs/gmm/evaluation.py:127).  `loss_required` returns forward values only.
+Gradients: the kernels are forward-only.  The APG loss is  sum_s w_s.detach() * (-log q_s), so the
+only graph autograd needs is that of the FORWARD proposal log-density; when `loss_required` is set and the encoder
+parameters require grad, that term is rebuilt with PyTorch ops (models.posterior_eta_torch / eta_log_q_torch / the
+un-fused Enc_apg_z MLP) and multiplied by the detached kernel weights -- the reference's train() works unchanged and
+gets the reference's gradients, while every forward quantity still comes from the kernels.
 """
 import torch
 from torch.distributions.gamma import Gamma
@@ -22,6 +25,7 @@ from torch.distributions.one_hot_categorical import OneHotCategorical as cat
 
 from .. import ops
 from . import kernels
+from .models import eta_log_q_torch, needs_grad
 
 
 def _sample_eta(post):
@@ -87,11 +91,15 @@ def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
         q_probs = enc_rws_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()
     w = kernels.logw_oneshot(x, post, generative, tau, mu, q_probs, z)
-    _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
+    log_q = w.log_q_f
+    if result_flags['loss_required'] and needs_grad(enc_rws_eta, enc_rws_z):
+        log_q = (eta_log_q_torch(enc_rws_eta.params_torch(x, generative.prior_ng), tau, mu)
+                 + cat(q_probs, validate_args=False).log_prob(z).sum(-1))
+    _book(trace, result_flags, w.log_w, log_q, w.density)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
         trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
-        trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
+        trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0).detach())
     return w.log_w, tau, mu, z, trace
 
 
@@ -105,7 +113,11 @@ def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_o
         q_probs = enc_apg_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()
     w = kernels.logw_joint(x, post, generative, tau, mu, tau_old, mu_old, q_probs, z, z_old)
-    _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
+    log_q_f = w.log_q_f
+    if result_flags['loss_required'] and needs_grad(enc_apg_eta, enc_apg_z):
+        log_q_f = (eta_log_q_torch(enc_apg_eta.params_torch(x, z_old, generative.prior_ng), tau, mu)
+                   + cat(q_probs, validate_args=False).log_prob(z).sum(-1))
+    _book(trace, result_flags, w.log_w, log_q_f, w.density)
     if result_flags['mode_required']:
         # the reference's branch (objectives.py:149-155) reads an undefined name; emit what it intends
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
@@ -119,7 +131,10 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
     post = enc_apg_eta.params(x, z, generative.prior_ng)
     tau, mu = _sample_eta(post)
     w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
-    _book(trace, result_flags, w.log_w, w.log_q_f, w.density)
+    log_q_f = w.log_q_f
+    if result_flags['loss_required'] and needs_grad(enc_apg_eta):
+        log_q_f = eta_log_q_torch(enc_apg_eta.params_torch(x, z, generative.prior_ng), tau, mu)
+    _book(trace, result_flags, w.log_w, log_q_f, w.density)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
         trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
@@ -139,7 +154,10 @@ def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
         w = kernels.logw_z(x, tau, mu, q_probs, generative, z, z_old, local=need_local)
     if result_flags['loss_required']:
         w_local, _ = ops.local_weight_stats(w.log_w_local, want_w=True, want_sum=False)
-        loss = (w_local * (-w.log_q_local)).sum(0).sum(-1).mean()
+        log_q_local = w.log_q_local
+        if needs_grad(enc_apg_z):
+            log_q_local = cat(q_probs, validate_args=False).log_prob(z)       # q_probs from the PyTorch MLP: has a graph
+        loss = (w_local * (-log_q_local)).sum(0).sum(-1).mean()
         trace['loss'][-1] = trace['loss'][-1] + loss.unsqueeze(0)
     if result_flags['mode_required']:
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))

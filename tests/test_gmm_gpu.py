@@ -388,3 +388,82 @@ def test_sweep_statistics_torch_encoder_path():
         se = (a.var() / B + b.var() / B).sqrt()
         assert abs(float(a.mean() - b.mean())) < 5 * float(se), k
     assert tuple(out[True]["E_z"].shape) == tuple(out[False]["E_z"].shape)
+
+
+# ------------------------------------------------------------------ N2: training mode
+def _train_models(P):
+    from apgs_b200.gmm import models as M
+    ms, opt = M.init_apg_models(3, 2, 32, True, DEV, lr=1e-3)
+    for m, key in zip(ms[:3], ("enc_rws_eta", "enc_apg_z", "enc_apg_eta")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})
+    return ms, opt
+
+
+def test_N2_eta_and_z_step_gradients_match_oracle_autograd():
+    """loss.backward() through the drop-in steps gives the gradients autograd gives the oracle (= the reference's
+    computation) for the same draws: the kernels supply the detached weights, PyTorch the graph of log q."""
+    from apgs_b200.gmm import objectives as O
+    S, B, N, K, D = 8, 6, 60, 3, 2
+    torch.manual_seed(0)
+    P, prior = og.make_params(), og.make_prior()
+    x = og.simulate(B)
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    tau_old, mu_old = torch.rand(S, B, K, D) + 0.5, torch.randn(S, B, K, D)
+    (enc_rws_eta, enc_apg_z, enc_apg_eta, gen), _ = _train_models(P)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    # ---- eta step
+    trace = {"loss": [], "ess": [], "E_tau": [], "E_mu": [], "E_z": [], "density": []}
+    torch.manual_seed(1)
+    log_w, tau, mu, trace = O.apg_update_eta(enc_apg_eta, gen, x.to(DEV), z.to(DEV), tau_old.to(DEV), mu_old.to(DEV), trace, flags)
+    trace["loss"][0].sum().backward()
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P["enc_apg_eta"].items()}
+    post = og.enc_apg_eta_posterior(Pg, xs, z, prior)
+    lw, lq, _, _ = og.eta_step_weights(xs, z, post, prior, tau.cpu(), mu.cpu(), tau_old, mu_old)
+    loss_ref = (torch.softmax(lw.detach(), 0) * (-lq)).sum(0).mean()
+    loss_ref.backward()
+    np.testing.assert_allclose(float(trace["loss"][0].detach()), float(loss_ref.detach()), rtol=2e-4)
+    for name, p in enc_apg_eta.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), Pg[name].grad.numpy(), rtol=2e-3, atol=2e-5 * float(Pg[name].grad.abs().max()) + 1e-7)
+    # ---- z step
+    trace = {"loss": [torch.zeros(1, device=DEV)], "ess": [], "E_tau": [], "E_mu": [], "E_z": [], "density": [torch.zeros(1, S, B, device=DEV)]}
+    log_w, z_new, trace = O.apg_update_z(enc_apg_z, gen, x.to(DEV), tau, mu, z.to(DEV), trace, flags)
+    trace["loss"][0].sum().backward()
+    Pz = {k: v.clone().requires_grad_(True) for k, v in P["enc_apg_z"].items()}
+    q_probs = og.enc_apg_z_probs(Pz, xs, tau.cpu(), mu.cpu())
+    lwl, _, lqf, _ = og.z_step_weights(xs, tau.cpu(), mu.cpu(), q_probs, prior, z_new.cpu(), z)
+    loss_ref = (torch.softmax(lwl.detach(), 0) * (-lqf)).sum(0).sum(-1).mean()
+    loss_ref.backward()
+    np.testing.assert_allclose(float(trace["loss"][0].detach()), float(loss_ref.detach()), rtol=2e-4)
+    scale = max(float(v.grad.abs().max()) for v in Pz.values())     # the shared output bias has an exactly-zero gradient
+    for name, p in enc_apg_z.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), Pz[name].grad.numpy(), rtol=5e-3, atol=1e-4 * scale)
+
+
+def test_N2_training_loop_runs_like_reference_train():
+    """the reference's train() inner loop (apgs/gmm/apg_training.py:17-27) on the drop-in: finite loss, every encoder
+    parameter receives a gradient, Adam steps change the weights."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B, sweeps = 10, 20, 5                       # BASELINE.json configs[0]
+    torch.manual_seed(0)
+    P = og.make_params()
+    models, opt = _train_models(P)
+    torch.manual_seed(1)
+    data = og.simulate(B).to(DEV)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    rs = Resampler("systematic", S, True, DEV)
+    before = [p.detach().clone() for m in models[:3] for p in m.parameters()]
+    for it in range(3):
+        opt.zero_grad()
+        x = data.repeat(S, 1, 1, 1)
+        trace = O.apg_objective(models, x, flags, sweeps, "decomposed", rs)
+        loss = trace["loss"].sum()
+        loss.backward()
+        assert bool(torch.isfinite(loss))
+        for m in models[:3]:
+            for p in m.parameters():
+                assert p.grad is not None and bool(torch.isfinite(p.grad).all())
+        opt.step()
+    after = [p.detach() for m in models[:3] for p in m.parameters()]
+    assert all(not torch.equal(a, b) for a, b in zip(before, after))
