@@ -50,6 +50,28 @@ struct KahanF {
     __device__ __forceinline__ double value() const { return (double)s - (double)c; }
 };
 
+// Packed fp32x2 arithmetic (sm_100: SASS FFMA2 / FMUL2): two fp32 lanes per issue slot.  The fused z step is bound by
+// instruction issue, not by the FMA pipe, so halving the number of FMA-pipe instructions is a direct win.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // plain fp32 partial sum of a handful of terms (same interface as KahanF)
 struct PlainF {
     float s;

@@ -124,40 +124,65 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 for (int k = 0; k < K; ++k) logit[q][k] = b2;
             }
             // ---- the MLP: hidden unit h for PB points x K clusters at a time
-            for (int h = 0; h < H; ++h) {
-                float xh[PB];
+            if (PB == 4) {
+                // points are paired as (0,2) and (1,3) in packed fp32x2 registers: y02 = Ex02 * Ee + 1 etc.
+                f32x2 L02[K], L13[K];
 #pragma unroll
-                for (int q = 0; q < PB; ++q) {
-                    float acc = 0.f;
+                for (int k = 0; k < K; ++k) { L02[k] = pack2(b2, b2); L13[k] = L02[k]; }
+                f32x2 xd02[D], xd13[D];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) acc = fmaf(s_w1x[h * D + d], xv[q][d], acc);
-                    xh[q] = acc;
-                }
-                const float w2 = s_w2[h];                                 // -2 * W2[h]
-                float ex[PB];
+                for (int d = 0; d < D; ++d) { xd02[d] = pack2(xv[0][d], xv[2][d]); xd13[d] = pack2(xv[1][d], xv[3][d]); }
+                const f32x2 one2 = pack2(1.f, 1.f), zero2 = pack2(0.f, 0.f);
+                for (int h = 0; h < H; ++h) {
+                    f32x2 xh02 = zero2, xh13 = zero2;
 #pragma unroll
-                for (int q = 0; q < PB; ++q) ex[q] = ex2_ftz(xh[q]);     // Ex_n[h]; 0 / +inf at the extremes are fine:
-                                                                          // Ee is clamped to [2^-80, 2^80], so no 0 * inf
+                    for (int d = 0; d < D; ++d) {
+                        const float w = s_w1x[h * D + d];
+                        const f32x2 w2p = pack2(w, w);
+                        xh02 = fma2(w2p, xd02[d], xh02);
+                        xh13 = fma2(w2p, xd13[d], xh13);
+                    }
+                    float x0, x1, x2, x3;
+                    unpack2(xh02, x0, x2);
+                    unpack2(xh13, x1, x3);
+                    // Ex_n[h] = 2^xh'; 0 / +inf at the extremes are fine: Ee is clamped to [2^-80, 2^80], so no 0 * inf
+                    const f32x2 ex02 = pack2(ex2_ftz(x0), ex2_ftz(x2)), ex13 = pack2(ex2_ftz(x1), ex2_ftz(x3));
+                    const float wm2 = s_w2[h];                                // -2 * W2[h]
+                    const f32x2 wm2p = pack2(wm2, wm2);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float ee = ev[k * H + h];                       // Ee_k[h]
-                    if (PB == 4) {
+                    for (int k = 0; k < K; ++k) {
+                        const float ee = ev[k * H + h];                       // Ee_k[h]
+                        const f32x2 eep = pack2(ee, ee);
                         // 1/y for four points with ONE reciprocal (batch inversion).  y is clamped at 2^30 so the
                         // product of four stays below 2^121; 2/(2^30+1) < eps/2, i.e. tanh is already 1.0f there.
-                        float y[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) y[q] = fminf(fmaf(ex[q], ee, 1.f), 1073741824.f);
-                        const float p01 = y[0] * y[1], p23 = y[2] * y[3];
+                        float y0, y1, y2, y3;
+                        unpack2(fma2(ex02, eep, one2), y0, y2);
+                        unpack2(fma2(ex13, eep, one2), y1, y3);
+                        y0 = fminf(y0, 1073741824.f); y1 = fminf(y1, 1073741824.f);
+                        y2 = fminf(y2, 1073741824.f); y3 = fminf(y3, 1073741824.f);
+                        const f32x2 yA = pack2(y0, y2), yB = pack2(y1, y3);
+                        float p01, p23;
+                        unpack2(mul2(yA, yB), p01, p23);
                         const float r = rcp_ftz(p01 * p23);
-                        const float r01 = r * p23, r23 = r * p01;
-                        logit[0][k] = fmaf(w2, r01 * y[1], logit[0][k]);
-                        logit[1][k] = fmaf(w2, r01 * y[0], logit[1][k]);
-                        logit[2][k] = fmaf(w2, r23 * y[3], logit[2][k]);
-                        logit[3][k] = fmaf(w2, r23 * y[2], logit[3][k]);
-                    } else {
+                        const f32x2 rr = pack2(r * p23, r * p01);             // (1/(y0 y1), 1/(y2 y3))
+                        L02[k] = fma2(wm2p, mul2(rr, yB), L02[k]);            // 1/y0 = y1/(y0 y1), 1/y2 = y3/(y2 y3)
+                        L13[k] = fma2(wm2p, mul2(rr, yA), L13[k]);
+                    }
+                }
 #pragma unroll
-                        for (int q = 0; q < PB; ++q)
-                            logit[q][k] = fmaf(w2, rcp_ftz(fminf(fmaf(ex[q], ee, 1.f), 1073741824.f)), logit[q][k]);
+                for (int k = 0; k < K; ++k) { unpack2(L02[k], logit[0][k], logit[2][k]); unpack2(L13[k], logit[1][k], logit[3][k]); }
+            } else {
+                for (int h = 0; h < H; ++h) {
+                    const float wm2 = s_w2[h];
+#pragma unroll
+                    for (int q = 0; q < PB; ++q) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc = fmaf(s_w1x[h * D + d], xv[q][d], acc);
+                        const float ex = ex2_ftz(acc);
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            logit[q][k] = fmaf(wm2, rcp_ftz(fminf(fmaf(ex, ev[k * H + h], 1.f), 1073741824.f)), logit[q][k]);
                     }
                 }
             }
