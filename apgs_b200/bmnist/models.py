@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 from torch.distributions.normal import Normal
 
+from ..rng import normal_sample
 from ..trace import Trace
 
 
@@ -31,7 +32,7 @@ class Enc_coor(nn.Module):
         q = Trace()
         q_mean, q_std = self.params(conved)
         if sampled:
-            z_where = Normal(q_mean, q_std, validate_args=False).sample()
+            z_where = normal_sample(q_mean, q_std)
             q.normal(loc=q_mean, scale=q_std, value=z_where, name='z_where')
         else:
             q.normal(loc=q_mean, scale=q_std, value=z_where_old, name='z_where')
@@ -56,7 +57,7 @@ class Enc_digit(nn.Module):
         q = Trace()
         q_mu, q_std = self.params(cropped)
         if sampled:
-            z_what = Normal(q_mu, q_std, validate_args=False).sample()
+            z_what = normal_sample(q_mu, q_std)
             q.normal(loc=q_mu, scale=q_std, value=z_what, name='z_what')
         else:
             q.normal(loc=q_mu, scale=q_std, value=z_what_old, name='z_what')

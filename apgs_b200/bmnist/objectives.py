@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from torch.distributions.normal import Normal
 
 from .. import ops
+from ..rng import normal_sample
 from . import kernels
 
 
@@ -70,7 +71,7 @@ def _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t
         CP = conved_k.shape[-1]
         conved_k = F.softmax(conved_k.squeeze(0).view(S, B, CP * CP), -1)
         q_mean, q_std = enc_coor.params(conved_k)
-        z_where_k = Normal(q_mean, q_std, validate_args=False).sample()
+        z_where_k = normal_sample(q_mean, q_std)
         zs.append(z_where_k.unsqueeze(2)); means.append(q_mean.unsqueeze(2)); stds.append(q_std.unsqueeze(2))
         recon_k = AT.digit_to_frame(template_k.unsqueeze(2), z_where_k.unsqueeze(2).unsqueeze(2)).squeeze(2).squeeze(2)
         frame_left = frame_left - recon_k
@@ -105,7 +106,7 @@ def oneshot(enc_coor, dec_coor, enc_digit, dec_digit, AT, frames, digit, trace, 
     E_where = torch.cat(E_where, 2)
     cropped = AT.frame_to_digit(frames=frames, z_where=z_where).view(S, B, T, K, DP * DP)
     q_mu, q_std = enc_digit.params(cropped)
-    z_what = Normal(q_mu, q_std, validate_args=False).sample()
+    z_what = normal_sample(q_mu, q_std)
     ll, recon = AT.reconstruct_ll(dec_digit.templates(z_what), z_where, frames, want_recon=bool(result_flags['mode_required']))
     log_w, log_q, log_p, ll_sum = kernels.logw_what(q_mu, q_std, z_what, None, ll, None, extra_log_p=log_p_where, extra_log_q=log_q_where)
     if result_flags['loss_required'] or result_flags['ess_required']:
@@ -171,7 +172,7 @@ def apg_what(enc_digit, dec_digit, AT, frames, z_where, z_what_old, trace, resul
     cropped = AT.frame_to_digit(frames=frames, z_where=z_where)
     DP = cropped.shape[-1]
     q_mu, q_std = enc_digit.params(cropped.view(S, B, T, K, int(DP * DP)))
-    z_what = Normal(q_mu, q_std, validate_args=False).sample()
+    z_what = normal_sample(q_mu, q_std)
     want_recon = bool(result_flags['mode_required'])
     ll_f, recon = AT.reconstruct_ll(dec_digit.templates(z_what), z_where, frames, want_recon=want_recon)
     ll_b, _ = AT.reconstruct_ll(dec_digit.templates(z_what_old), z_where, frames)

@@ -1,5 +1,6 @@
 // Library-level entry points: version, thread-local error string, device properties.
 #include "common.cuh"
+#include <mutex>
 
 namespace apgs {
 
@@ -19,6 +20,28 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    struct Entry { const void* f; int dev; size_t bytes; };
+    static Entry table[256];
+    static int n = 0;
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n; ++i)
+        if (table[i].f == func && table[i].dev == dev) {
+            if (table[i].bytes >= bytes) return cudaSuccess;
+            e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e == cudaSuccess) table[i].bytes = bytes;
+            return e;
+        }
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && n < 256) table[n++] = {func, dev, bytes};
+    return e;
 }
 
 }  // namespace apgs

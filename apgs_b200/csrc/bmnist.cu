@@ -271,12 +271,10 @@ static int launch_paste(bool with_ll, const float* digits, const float* z_where,
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "bmnist_paste: K*DP*DP too large for shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     if (with_ll) {
-        if (smem > 48 * 1024)
-            APGS_CUDA_OK(cudaFuncSetAttribute(k_stn_paste<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_stn_paste<true>), smem), "smem attr");
         k_stn_paste<true><<<(unsigned int)(S * B * T), 256, smem, st>>>(a);
     } else {
-        if (smem > 48 * 1024)
-            APGS_CUDA_OK(cudaFuncSetAttribute(k_stn_paste<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_stn_paste<false>), smem), "smem attr");
         k_stn_paste<false><<<(unsigned int)(S * B * T), 256, smem, st>>>(a);
     }
     APGS_LAUNCH_OK("k_stn_paste launch");

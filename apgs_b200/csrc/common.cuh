@@ -32,6 +32,10 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 // B200: 148 SMs; cached per device at first use.
 int sm_count();
 
+// Opt a kernel into > 48 KB of dynamic shared memory.  The attribute is set once per (function, device, size high-water
+// mark) and remembered, so steady-state calls -- and CUDA-graph capture -- issue nothing but the launch itself.
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // ---- exact division by an invariant for numerators < 2^31 (Granlund-Montgomery) -------------

@@ -392,8 +392,7 @@ static int launch_nss(const NssArgs& a, cudaStream_t st) {
     void (*kern)(NssArgs) = k_gmm_nss_posterior<K, D, kP, kLanes, false, false>;
     if (a.gamma == nullptr) kern = a.z != nullptr ? k_gmm_nss_posterior<K, D, kP, kLanes, true, true>
                                                   : k_gmm_nss_posterior<K, D, kP, kLanes, true, false>;
-    if (smem > 48 * 1024)
-        APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (a.R + kP - 1) / kP;
     kern<<<(unsigned int)grid, kP * kLanes, smem, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_nss_posterior launch");
@@ -410,8 +409,7 @@ static int launch_weights(const GmmWArgs& a, cudaStream_t st) {
     if (a.step == STEP_ETA) kern = k_gmm_weights<K, D, kP, kLanes, STEP_ETA>;
     if (a.step == STEP_Z) kern = k_gmm_weights<K, D, kP, kLanes, STEP_Z>;
     if (a.step == STEP_JOINT) kern = k_gmm_weights<K, D, kP, kLanes, STEP_JOINT>;
-    if (smem > 48 * 1024)
-        APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (a.R + kP - 1) / kP;
     kern<<<(unsigned int)grid, kP * kLanes, smem, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_weights launch");

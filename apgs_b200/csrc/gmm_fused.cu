@@ -286,8 +286,7 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
                          (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     auto kern = k_gmm_z_fused<K, D, kFP, kFLanes, kFPB>;
-    if (smem > 48 * 1024)
-        APGS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (a.R + kFP - 1) / kFP;
     kern<<<(unsigned int)grid, kFP * kFLanes, smem, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_z_fused launch");

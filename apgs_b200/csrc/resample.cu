@@ -317,9 +317,8 @@ static AncPlan plan_ancestors(long long S, long long B, bool want_dbl) {
 template <int TB>
 static int launch_anc_tb(const AncArgs& a, const AncPlan& p, cudaStream_t st) {
     if (p.tile_in_smem) {
-        if (p.smem > 48 * 1024)
-            APGS_CUDA_OK(cudaFuncSetAttribute(k_ancestors<TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)p.smem), "cudaFuncSetAttribute(k_ancestors)");
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_ancestors<TB, true>), p.smem),
+                     "cudaFuncSetAttribute(k_ancestors)");
         k_ancestors<TB, true><<<p.grid, p.nthr, p.smem, st>>>(a);
     } else {
         k_ancestors<TB, false><<<p.grid, p.nthr, p.smem, st>>>(a);

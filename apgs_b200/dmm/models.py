@@ -12,6 +12,7 @@ from torch.distributions.beta import Beta
 from torch.distributions.normal import Normal
 from torch.distributions.one_hot_categorical import OneHotCategorical as cat
 
+from ..rng import normal_sample
 from ..trace import Trace
 from . import kernels
 
@@ -41,7 +42,7 @@ class _EncMu(nn.Module):
     def _trace(q_mu_mu, q_mu_sigma, sampled, mu_old):
         q = Trace()
         if sampled:
-            mu = Normal(q_mu_mu, q_mu_sigma, validate_args=False).sample()
+            mu = normal_sample(q_mu_mu, q_mu_sigma)
             q.normal(q_mu_mu, q_mu_sigma, value=mu, name='means')
         else:
             q.normal(q_mu_mu, q_mu_sigma, value=mu_old, name='means')

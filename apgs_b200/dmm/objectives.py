@@ -12,6 +12,7 @@ from torch.distributions.normal import Normal
 from torch.distributions.one_hot_categorical import OneHotCategorical as cat
 
 from .. import ops
+from ..rng import normal_sample
 from . import kernels
 
 
@@ -70,7 +71,7 @@ def _E_recon(dec, mu, z, h2):
 def oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
     """One-shot predicts mu, z and beta like a normal RWS (objectives.py:80-114)."""
     q_mu, q_sigma = enc_rws_mu.params(x, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
-    mu = Normal(q_mu, q_sigma, validate_args=False).sample()
+    mu = normal_sample(q_mu, q_sigma)
     q_probs, z, con1, con0, beta = _sample_local(enc_rws_local, x, mu, K)
     h2 = dec.hidden2(beta)
     w = kernels.logw_oneshot(x, q_mu, q_sigma, mu, q_probs, z, beta, con1, con0, h2, dec)
@@ -85,7 +86,7 @@ def oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
 def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags):
     """Given local variables {z, beta}, update the centres mu (objectives.py:116-151)."""
     q_mu, q_sigma = enc_apg_mu.params(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
-    mu = Normal(q_mu, q_sigma, validate_args=False).sample()
+    mu = normal_sample(q_mu, q_sigma)
     h2 = dec.hidden2(beta)                 # the decoder sees beta only: one evaluation serves f and b
     w = kernels.logw_mu(x, z, h2, q_mu, q_sigma, mu, mu_old, dec)
     _book(trace, result_flags, w.log_w, w.log_q_f, w.ll_f, w.density)

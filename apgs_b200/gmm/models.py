@@ -16,6 +16,7 @@ from torch.distributions.gamma import Gamma
 from torch.distributions.normal import Normal
 from torch.distributions.one_hot_categorical import OneHotCategorical as cat
 
+from ..rng import normal_sample
 from ..trace import Trace
 from . import kernels
 
@@ -63,9 +64,9 @@ def _eta_trace(post, sampled, tau_old, mu_old):
     q_alpha, q_beta, q_mu, q_nu = post
     q = Trace()
     if sampled:
-        tau = Gamma(q_alpha, q_beta).sample()
+        tau = Gamma(q_alpha, q_beta, validate_args=False).sample()
         q.gamma(q_alpha, q_beta, value=tau, name='precisions')
-        mu = Normal(q_mu, 1. / (q_nu * tau).sqrt()).sample()
+        mu = normal_sample(q_mu, 1. / (q_nu * tau).sqrt())
         q.normal(q_mu, 1. / (q_nu * tau).sqrt(), value=mu, name='means')
     else:
         q.gamma(q_alpha, q_beta, value=tau_old, name='precisions')

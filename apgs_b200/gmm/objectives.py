@@ -24,6 +24,7 @@ from torch.distributions.normal import Normal
 from torch.distributions.one_hot_categorical import OneHotCategorical as cat
 
 from .. import ops
+from ..rng import normal_sample
 from . import kernels
 from .models import eta_log_q_torch, needs_grad
 
@@ -33,7 +34,7 @@ def _sample_eta(post):
     # validate_args=False: the default argument validation calls .item() on the device (a host sync per
     # distribution); it carries no arithmetic
     tau = Gamma(q_alpha, q_beta, validate_args=False).sample()
-    mu = Normal(q_mu, 1. / (q_nu * tau).sqrt(), validate_args=False).sample()
+    mu = normal_sample(q_mu, 1. / (q_nu * tau).sqrt())
     return tau, mu
 
 
