@@ -36,7 +36,7 @@ int sm_count();
 // mark) and remembered, so steady-state calls -- and CUDA-graph capture -- issue nothing but the launch itself.
 cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
 
-inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+__host__ __device__ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // ---- exact division by an invariant for numerators < 2^31 (Granlund-Montgomery) -------------
 struct FastDiv {

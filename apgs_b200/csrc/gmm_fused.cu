@@ -24,65 +24,220 @@ struct ZFusedArgs {
     const float* z_forced;          // (R, N, K) one-hot to use instead of sampling, or null
     const float* u;                 // (R, N) uniforms in [0,1), required unless z_forced
     const float* rpi;               // (K)
-    long long R;
-    int B, N, H;
+    int S, B, N, H;
     float* z_new;                   // (R, N, K) out
     float* q_probs;                 // (R, N, K) out, optional
     float *log_w, *log_q_f, *dens, *log_w_f, *log_w_b;   // (R), optional
     float *lw_local, *lq_local;                           // (R, N), optional
 };
 
+// ---- tile mapping -----------------------------------------------------------------------------------------------
+// A CTA owns ONE instance b and P particles s0..s0+P-1 of it (rows r = s*B + b: P separate N*K*4-byte rows, each
+// moved by its own bulk copy).  Everything that depends only on the data is then shared by the whole CTA:
+// Ex_n[h] = 2^(W1x x_n)' is tabulated ONCE per CTA in shared memory (N*H ex2 instead of P*N*H), which takes the
+// exponentials out of the inner loop altogether -- per hidden unit a thread issues two LDS.128 (Ex of its four
+// points; Ee of the K clusters + the output weight) and, per cluster, 11 packed-fp32 instructions and one MUFU.RCP.
+//
+// Range contract of the factorised loop.  The batch inversion multiplies four y = Ex*Ee + 1 >= 1; everything is
+// carried scaled by 2^-31 (y' = Ex * (2^-31 Ee) + 2^-31, the 2^-31 folded into the Ee table and the output weight),
+// so y in [1, 2^62] keeps the product of four y' inside [2^-124, 2^124] and no clamp is needed.  A particle may
+// run this loop iff  (a) every e'_k[h] is in [-80, 80],  (b) XM[h] = max_n xh'_n[h] <= 126 (Ex finite), and
+// (c) max_h (XM[h] + max_k e'_k[h]) <= 61.  XM is per CTA, the e' test per particle; both are evaluated in the
+// prologue.  Any other particle (saturating pre-activations far beyond anything a trained encoder produces, or
+// NaN/inf inputs) runs the plain loop  y = 2^(xh' + e') + 1, 1/y by MUFU.RCP per element  -- exact for every
+// input, ~3x slower, and in practice never taken.
+
+template <int K, int KP>
+__device__ __forceinline__ void mlp_quad_fast(const unsigned char* ex_ptr, int ex_stride_b, const unsigned char* ev_ptr,
+                                              int H, f32x2 (&L02)[K], f32x2 (&L13)[K]) {
+    const f32x2 c2 = pack2(4.656612873077393e-10f, 4.656612873077393e-10f);   // 2^-31
+#pragma unroll 2
+    for (int h = 0; h < H; ++h) {
+        const ulonglong2 exq = *reinterpret_cast<const ulonglong2*>(ex_ptr + (size_t)h * ex_stride_b);
+        const f32x2 ex02 = exq.x, ex13 = exq.y;                       // (Ex[q0], Ex[q2]), (Ex[q1], Ex[q3])
+        float ev[KP];
+#pragma unroll
+        for (int i = 0; i < KP / 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(ev_ptr + ((size_t)h * KP + i * 4) * 4);
+            ev[i * 4 + 0] = v.x; ev[i * 4 + 1] = v.y; ev[i * 4 + 2] = v.z; ev[i * 4 + 3] = v.w;
+        }
+        const f32x2 wm2p = pack2(ev[K], ev[K]);                       // -2 * W2[h] * 2^-31
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const f32x2 eep = pack2(ev[k], ev[k]);                    // 2^-31 Ee_k[h]
+            // 1/y' for four points with ONE reciprocal (batch inversion)
+            const f32x2 yA = fma2(ex02, eep, c2), yB = fma2(ex13, eep, c2);
+            float p01, p23;
+            unpack2(mul2(yA, yB), p01, p23);
+            const float r = rcp_ftz(p01 * p23);
+            const f32x2 rr = pack2(r * p23, r * p01);                 // (1/(y0 y1), 1/(y2 y3))
+            L02[k] = fma2(wm2p, mul2(rr, yB), L02[k]);                // 1/y0 = y1/(y0 y1), 1/y2 = y3/(y2 y3)
+            L13[k] = fma2(wm2p, mul2(rr, yA), L13[k]);
+        }
+    }
+}
+
+// the plain loop: ev holds the raw e'_k[h] and -2 W2[h]; xh' is recomputed exactly as the Ex table does
+template <int K, int KP, int D, int PB>
+__device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv)[PB][D], const float* ev, int H,
+                                               float (&logit)[PB][K]) {
+    for (int h = 0; h < H; ++h) {
+        const float wm2 = ev[h * KP + K];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc = fmaf(TANH_PRESCALE * __ldg(W1 + h * (3 * D) + d), xv[q][d], acc);
+#pragma unroll
+            for (int k = 0; k < K; ++k)      // 2^a = +inf gives 1/y = 0 (tanh = 1), 2^a = 0 gives 1/y = 1 (tanh = -1)
+                logit[q][k] = fmaf(wm2, rcp_ftz(ex2_ftz(acc + ev[h * KP + k]) + 1.f), logit[q][k]);
+        }
+    }
+}
+
 template <int K, int D, int P, int LANES, int PB>
 __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
+    static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
+    __shared__ float s_misc[1 + K];
     constexpr int KD = K * D;
+    constexpr int KP = ((K + 1) + 3) / 4 * 4;                  // Ee_0..Ee_{K-1}, -2 W2[h], padding
     const int N = a.N, H = a.H;
-    const int EP = K * H + 1;                                  // padded per-particle stride of e
+    const int NK = N * K;
+    const int nIt = (N + LANES * PB - 1) / (LANES * PB);       // passes of 32 points
+    const int EXS = nIt * LANES * PB;                          // floats of Ex per hidden unit
+    const int EPs = H * KP + 4;                                // per-particle stride of the Ee table (floats)
     const bool has_bwd = a.z_old != nullptr;
     const bool forced = a.z_forced != nullptr;
-    const size_t tile_f = (size_t)P * N * K;
-    float* s_zo = reinterpret_cast<float*>(smem);              // z_old tile (or z_forced when !has_bwd)
-    float* s_zn = s_zo + tile_f;                               // z_new tile (staged in from z_forced, out to z_new)
-    float* s_w1x = s_zn + tile_f;                              // H*D
-    float* s_w2 = s_w1x + H * D;                               // H
-    float* s_e = s_w2 + H;                                     // P * EP
-    float* s_tab = s_e + (size_t)P * EP;                       // P * KD * 3: mu, 1/(2 var), log sigma + c
-    const long long r0 = (long long)blockIdx.x * P;
-    const int rows = (int)min((long long)P, a.R - r0);
+    const size_t tile_f = ((size_t)P * NK + 3) / 4 * 4;
+    float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
+    float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
+    float* s_ex = s_zn + tile_f;                               // H * EXS, slot order inside a quad: q0 q2 q1 q3
+    float* s_e = s_ex + (size_t)H * EXS;                       // P * EPs
+    float* s_xm = s_e + (size_t)P * EPs;                       // H
+    float* s_tab = s_xm + (H + 3) / 4 * 4;                     // P * KD * 3: mu, 1/(2 var), log sigma + c
+    const int b = (int)(blockIdx.x % (unsigned int)a.B);
+    const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
+    const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool valid = s0 + p < a.S;
+    const long long r = (long long)(s0 + p) * a.B + b;
+    const int rows = min(P, a.S - s0);
+    const unsigned int rb = (unsigned int)NK * 4u;
+    // a row goes through the bulk-copy engine when its size keeps every row 16-byte aligned
+    const bool bulk_in = (rb & 15u) == 0 && (!has_bwd || aligned(a.z_old, 16)) && (!forced || aligned(a.z_forced, 16));
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
-    const unsigned int tb = (unsigned int)(rows * N * K * 4);
-    StageReq req[2] = {{s_zo, (has_bwd ? a.z_old : a.x) + (has_bwd ? r0 * N * K : 0), has_bwd ? tb : 0u},
-                       {s_zn, (forced ? a.z_forced : a.x) + (forced ? r0 * N * K : 0), forced ? tb : 0u}};
-    stage_issue(req, 2, &bar);
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows * ((has_bwd ? 1u : 0u) + (forced ? 1u : 0u)) : 0u);
+    if (valid) {
+        if (bulk_in) {
+            if (j == 0) {
+                if (has_bwd) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + r * NK, rb, &bar);
+                if (forced) bulk_g2s(s_zn + (size_t)p * NK, a.z_forced + r * NK, rb, &bar);
+            }
+        } else {
+            for (int i = j; i < NK; i += LANES) {
+                if (has_bwd) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + r * NK + i);
+                if (forced) s_zn[(size_t)p * NK + i] = __ldg(a.z_forced + r * NK + i);
+            }
+        }
+    }
 
-    // ---- weights and the per-particle pieces, while the tiles are in flight
-    // W1x and e are stored pre-multiplied by 2*log2(e): the tanh argument needs no further scaling
-    for (int i = threadIdx.x; i < H * D; i += blockDim.x)
-        s_w1x[i] = TANH_PRESCALE * __ldg(a.W1 + (i / D) * (3 * D) + (i % D));
-    // tanh = 1 - 2/y  =>  sum_h w2_h tanh_h = (sum_h w2_h) - sum_h (2 w2_h) / y_h : the loop accumulates the second sum
-    for (int i = threadIdx.x; i < H; i += blockDim.x) s_w2[i] = -2.f * __ldg(a.W2 + i);
-    float b2 = __ldg(a.b2);
-    for (int i = 0; i < H; ++i) b2 += __ldg(a.W2 + i);
-    const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
-    const bool valid = p < rows;
-    const long long r = r0 + p;
+    // ---- per-CTA table Ex_n[h] = 2^(2 log2(e) W1x x_n) and its per-unit maximum exponent, while the rows are in flight
+    const float* xb = a.x + (size_t)b * N * D;
+    {
+        constexpr int XS = 2;                                       // slots per lane kept in registers (N <= 64)
+        float xr[XS][D];
+#pragma unroll
+        for (int si = 0; si < XS; ++si) {
+            const int slot = lane + 32 * si, qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);   // slot order q0 q2 q1 q3
+            const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
+#pragma unroll
+            for (int d = 0; d < D; ++d) xr[si][d] = (slot < EXS && n < N) ? __ldg(xb + n * D + d) : NAN;
+        }
+        for (int h = warp; h < H; h += (P * LANES) / 32) {
+            float w[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) w[d] = TANH_PRESCALE * __ldg(a.W1 + h * (3 * D) + d);
+            float mx = -INFINITY;
+            bool bad = false;
+#pragma unroll
+            for (int si = 0; si < XS; ++si) {
+                const int slot = lane + 32 * si;
+                if (slot < EXS) {
+                    const int qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);
+                    const bool in = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2) < N;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) acc = fmaf(w[d], xr[si][d], acc);
+                    if (in) { mx = fmaxf(mx, acc); bad |= !(acc == acc); }
+                    // an underflow to 0 is exact enough (the sum of exponents is then < -46); overflow is caught via XM
+                    s_ex[(size_t)h * EXS + slot] = in ? ex2_ftz(acc) : 0.f;
+                }
+            }
+            for (int slot = lane + 32 * XS; slot < EXS; slot += 32) {
+                const int qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);
+                const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
+                float acc = 0.f;
+                if (n < N) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) acc = fmaf(w[d], __ldg(xb + n * D + d), acc);
+                    mx = fmaxf(mx, acc);
+                    bad |= !(acc == acc);
+                }
+                s_ex[(size_t)h * EXS + slot] = (n < N) ? ex2_ftz(acc) : 0.f;
+            }
+            mx = warp_max(bad ? INFINITY : mx);
+            if (lane == 0) s_xm[h] = (mx <= 126.f) ? mx : INFINITY;     // +inf: the CTA takes the plain loop
+        }
+    }
+    // per-CTA scalars, once: b2' = b2 + sum_h W2[h]  (tanh = 1 - 2/y  =>  sum_h w2_h tanh_h = sum_h w2_h - sum_h 2 w2_h / y_h,
+    // the loops accumulate the second sum) and the clamped log prior of the assignments
+    if (warp == 0) {
+        float part = 0.f;
+        for (int i = lane; i < H; i += 32) part += __ldg(a.W2 + i);
+        part = warp_sum(part);
+        if (lane == 0) s_misc[0] = __ldg(a.b2) + part;
+        if (lane < K) {
+            float sp = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) sp = __fadd_rn(sp, __ldg(a.rpi + k));
+            s_misc[1 + lane] = logf(fminf(fmaxf(__fdiv_rn(__ldg(a.rpi + lane), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
+        }
+    }
+    __syncthreads();                                               // s_xm, s_misc
+    const float b2 = s_misc[0];
+    float logpi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) logpi[k] = s_misc[1 + k];
+
+    // ---- per-particle pieces: e'_k[h] = 2 log2(e) (b1 + W1m mu_k + W1t tau_k), the range test, Normal tables
+    float bound = -INFINITY, elo = INFINITY, ehi = -INFINITY;
+    float* ep = s_e + (size_t)p * EPs;
     if (valid) {
         float tk[KD], mk[KD];
 #pragma unroll
         for (int e = 0; e < KD; ++e) { tk[e] = __ldg(a.tau + r * KD + e); mk[e] = __ldg(a.mu + r * KD + e); }
+        for (int h = j; h < H; h += LANES) {
+            const float bh = __ldg(a.b1 + h);
+            float emax = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {                              // e[k][h] = b1 + W1m mu_k + W1t tau_k
-            for (int h = j; h < H; h += LANES) {
-                float acc = __ldg(a.b1 + h);
+            for (int k = 0; k < K; ++k) {
+                float acc = bh;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mk[k * D + d], acc);
                     acc = fmaf(__ldg(a.W1 + h * 3 * D + 2 * D + d), tk[k * D + d], acc);
                 }
-                s_e[p * EP + k * H + h] = ex2_ftz(fminf(fmaxf(TANH_PRESCALE * acc, -80.f), 80.f));   // Ee_k[h]
+                const float ee = TANH_PRESCALE * acc;
+                emax = fmaxf(emax, ee);
+                elo = fminf(elo, ee);
+                ep[h * KP + k] = ee;
+                if (!(ee == ee)) ehi = INFINITY;                               // NaN: fmaxf/fminf would drop it
             }
+            ehi = fmaxf(ehi, emax);
+            bound = fmaxf(bound, s_xm[h] + emax);
         }
         float* tab = s_tab + (size_t)p * (KD * 3);
         for (int e = j; e < KD; e += LANES) {
@@ -95,96 +250,57 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             tab[e * 3 + 2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
         }
     }
-    float logpi[K];
-    {
-        float sp = 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) sp = __fadd_rn(sp, __ldg(a.rpi + k));
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-            logpi[k] = logf(fminf(fmaxf(__fdiv_rn(__ldg(a.rpi + k), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        ehi = fmaxf(ehi, __shfl_xor_sync(0xffffffffu, ehi, o));
+        elo = fminf(elo, __shfl_xor_sync(0xffffffffu, elo, o));
     }
-    stage_wait(&bar, 0);
+    const bool fast = (bound <= 61.f) && (ehi <= 80.f) && (elo >= -80.f);
+    if (valid) {                                  // each lane converts the entries it wrote itself
+        for (int h = j; h < H; h += LANES) {
+            const float w2 = -2.f * __ldg(a.W2 + h);
+            if (fast) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) ep[h * KP + k] = ex2_ftz(ep[h * KP + k] - 31.f);    // 2^-31 Ee_k[h]
+                ep[h * KP + K] = w2 * 4.656612873077393e-10f;
+            } else {
+                ep[h * KP + K] = w2;
+            }
+        }
+    }
+    stage_wait(&bar, 0);                                           // rows landed; also publishes s_e / s_tab
 
     PlainF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;     // <= ceil(N/LANES) terms per lane
     if (valid) {
-        const float* zo = s_zo + (size_t)p * N * K;
-        float* zn = s_zn + (size_t)p * N * K;
-        const float* ev = s_e + p * EP;
+        const float* zo = s_zo + (size_t)p * NK;
+        float* zn = s_zn + (size_t)p * NK;
         const float* tab = s_tab + (size_t)p * (KD * 3);
-        const float* xb = a.x + (size_t)(r % a.B) * N * D;
-        for (int n0 = j; n0 < N; n0 += LANES * PB) {
-            float xv[PB][D], logit[PB][K];
+        for (int it = 0; it < nIt; ++it) {
+            const int n0 = it * (LANES * PB) + j;
+            float xv[PB][D], logit[PB][K], uq[PB];
 #pragma unroll
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
 #pragma unroll
                 for (int d = 0; d < D; ++d) xv[q][d] = (n < N) ? __ldg(xb + n * D + d) : 0.f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) logit[q][k] = b2;
+                uq[q] = (n < N && !forced) ? __ldg(a.u + r * N + n) : 0.f;      // in flight during the MLP
             }
-            // ---- the MLP: hidden unit h for PB points x K clusters at a time
-            if (PB == 4) {
-                // points are paired as (0,2) and (1,3) in packed fp32x2 registers: y02 = Ex02 * Ee + 1 etc.
+            // ---- the MLP: hidden unit h for 4 points x K clusters at a time; points are paired as (0,2) and (1,3)
+            if (fast) {
                 f32x2 L02[K], L13[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) { L02[k] = pack2(b2, b2); L13[k] = L02[k]; }
-                f32x2 xd02[D], xd13[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) { xd02[d] = pack2(xv[0][d], xv[2][d]); xd13[d] = pack2(xv[1][d], xv[3][d]); }
-                const f32x2 one2 = pack2(1.f, 1.f), zero2 = pack2(0.f, 0.f);
-                for (int h = 0; h < H; ++h) {
-                    f32x2 xh02 = zero2, xh13 = zero2;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const float w = s_w1x[h * D + d];
-                        const f32x2 w2p = pack2(w, w);
-                        xh02 = fma2(w2p, xd02[d], xh02);
-                        xh13 = fma2(w2p, xd13[d], xh13);
-                    }
-                    float x0, x1, x2, x3;
-                    unpack2(xh02, x0, x2);
-                    unpack2(xh13, x1, x3);
-                    // Ex_n[h] = 2^xh'; 0 / +inf at the extremes are fine: Ee is clamped to [2^-80, 2^80], so no 0 * inf
-                    const f32x2 ex02 = pack2(ex2_ftz(x0), ex2_ftz(x2)), ex13 = pack2(ex2_ftz(x1), ex2_ftz(x3));
-                    const float wm2 = s_w2[h];                                // -2 * W2[h]
-                    const f32x2 wm2p = pack2(wm2, wm2);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float ee = ev[k * H + h];                       // Ee_k[h]
-                        const f32x2 eep = pack2(ee, ee);
-                        // 1/y for four points with ONE reciprocal (batch inversion).  y is clamped at 2^30 so the
-                        // product of four stays below 2^121; 2/(2^30+1) < eps/2, i.e. tanh is already 1.0f there.
-                        float y0, y1, y2, y3;
-                        unpack2(fma2(ex02, eep, one2), y0, y2);
-                        unpack2(fma2(ex13, eep, one2), y1, y3);
-                        y0 = fminf(y0, 1073741824.f); y1 = fminf(y1, 1073741824.f);
-                        y2 = fminf(y2, 1073741824.f); y3 = fminf(y3, 1073741824.f);
-                        const f32x2 yA = pack2(y0, y2), yB = pack2(y1, y3);
-                        float p01, p23;
-                        unpack2(mul2(yA, yB), p01, p23);
-                        const float r = rcp_ftz(p01 * p23);
-                        const f32x2 rr = pack2(r * p23, r * p01);             // (1/(y0 y1), 1/(y2 y3))
-                        L02[k] = fma2(wm2p, mul2(rr, yB), L02[k]);            // 1/y0 = y1/(y0 y1), 1/y2 = y3/(y2 y3)
-                        L13[k] = fma2(wm2p, mul2(rr, yA), L13[k]);
-                    }
-                }
+                const unsigned char* exb = reinterpret_cast<const unsigned char*>(s_ex + (size_t)(it * LANES + j) * PB);
+                mlp_quad_fast<K, KP>(exb, EXS * 4, reinterpret_cast<const unsigned char*>(ep), H, L02, L13);
 #pragma unroll
                 for (int k = 0; k < K; ++k) { unpack2(L02[k], logit[0][k], logit[2][k]); unpack2(L13[k], logit[1][k], logit[3][k]); }
             } else {
-                for (int h = 0; h < H; ++h) {
-                    const float wm2 = s_w2[h];
 #pragma unroll
-                    for (int q = 0; q < PB; ++q) {
-                        float acc = 0.f;
+                for (int q = 0; q < PB; ++q)
 #pragma unroll
-                        for (int d = 0; d < D; ++d) acc = fmaf(s_w1x[h * D + d], xv[q][d], acc);
-                        const float ex = ex2_ftz(acc);
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-                            logit[q][k] = fmaf(wm2, rcp_ftz(fminf(fmaf(ex, ev[k * H + h], 1.f), 1073741824.f)), logit[q][k]);
-                    }
-                }
+                    for (int k = 0; k < K; ++k) logit[q][k] = b2;
+                mlp_quad_plain<K, KP, D, PB>(a.W1, xv, ep, H, logit);
             }
             // ---- per point: softmax, draw, log-densities
 #pragma unroll
@@ -215,7 +331,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                     for (int k = 1; k < K; ++k) { const float v = zn[n * K + k]; if (v > best) { best = v; lf = k; } }
                 } else {
                     // inverse CDF on the (unnormalised) probabilities: label = #{k : cdf_k <= u * sum}
-                    const float t = __fmul_rn(__ldg(a.u + r * N + n), sq);
+                    const float t = __fmul_rn(uq[q], sq);
                     float c = 0.f;
 #pragma unroll
                     for (int k = 0; k < K - 1; ++k) { c = __fadd_rn(c, pr[k]); lf += (t >= c) ? 1 : 0; }
@@ -274,20 +390,39 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         if (a.log_q_f != nullptr) a.log_q_f[r] = lqz_f;
         if (a.dens != nullptr) a.dens[r] = __fadd_rn(ll_f, lpz_f);
     }
-    // ---- z_new tile out (one bulk store per CTA)
-    tile_store(a.z_new + r0 * N * K, s_zn, tb);
+    // ---- z_new rows out (one bulk store per particle row)
+    const bool bulk_out = (rb & 15u) == 0 && aligned(a.z_new, 16);
+    if (bulk_out) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+        __syncthreads();
+        if (valid && j == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.z_new + r * NK),
+                         "r"(smem_u32(s_zn + (size_t)p * NK)), "r"(rb)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released at exit
+        }
+    } else {
+        __syncthreads();
+        if (valid)
+            for (int i = j; i < NK; i += LANES) a.z_new[r * NK + i] = s_zn[(size_t)p * NK + i];
+    }
 }
 
 constexpr int kFP = 32, kFLanes = 8, kFPB = 4;
 
 template <int K, int D>
 static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
-    const size_t smem = ((size_t)kFP * a.N * K * 2 + (size_t)a.H * (D + 1) + (size_t)kFP * (K * a.H + 1) +
-                         (size_t)kFP * K * D * 3) * 4;
+    constexpr int KP = ((K + 1) + 3) / 4 * 4;
+    const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
+    const size_t tile_f = ((size_t)kFP * a.N * K + 3) / 4 * 4;
+    const size_t smem = (2 * tile_f + (size_t)a.H * nIt * kFLanes * kFPB + (size_t)kFP * (a.H * KP + 4) +
+                         (size_t)(a.H + 3) / 4 * 4 + (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     auto kern = k_gmm_z_fused<K, D, kFP, kFLanes, kFPB>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
-    const long long grid = (a.R + kFP - 1) / kFP;
+    const long long grid = (long long)a.B * ((a.S + kFP - 1) / kFP);
+    if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_z_fused: S*B too large for one launch");
     kern<<<(unsigned int)grid, kFP * kFLanes, smem, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_z_fused launch");
     return 0;
@@ -311,7 +446,7 @@ extern "C" int apgs_gmm_z_step_fused_f32(const float* x, const float* tau, const
     ZFusedArgs a = {};
     a.x = x; a.tau = tau; a.mu = mu; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
     a.z_old = z_old; a.z_forced = z_forced; a.u = uniforms; a.rpi = prior->pi;
-    a.R = (long long)S * B; a.B = (int)B; a.N = (int)N; a.H = (int)H;
+    a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
     a.z_new = z_new; a.q_probs = q_probs;
     if (out) {
         a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;

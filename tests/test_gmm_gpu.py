@@ -365,6 +365,31 @@ def test_N1_fused_sampling_is_inverse_cdf_of_oracle_probs(S, B, N, K, D, H):
     assert bool((gap[bad] < 1e-5).all())
 
 
+@pytest.mark.parametrize("xs_scale,w_scale", [(12.0, 4.0), (40.0, 10.0), (300.0, 30.0)])
+def test_N1_fused_saturating_preactivations_take_the_plain_loop(xs_scale, w_scale):
+    """pre-activations far beyond the tanh saturation point (exponents > 2^30, up to +-inf in the Ex table) must
+    fail the range test of the factorised loop, run the plain loop and still reproduce the reference probabilities."""
+    from apgs_b200.gmm import kernels
+    S, B, N, K, D, H = 35, 4, 60, 3, 2, 32
+    torch.manual_seed(int(xs_scale))
+    P, prior = og.make_params(K, D, H), og.make_prior(K, D)
+    enc = {k: v.clone() for k, v in P["enc_apg_z"].items()}
+    enc["pi_log_prob.0.weight"] = enc["pi_log_prob.0.weight"] * w_scale
+    x = torch.randn(B, N, D) * xs_scale
+    x[1] = torch.randn(N, D) * 0.5                      # one instance stays in the clamp-free regime
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    tau, mu = torch.rand(S, B, K, D) * 3 + 0.1, torch.randn(S, B, K, D) * xs_scale
+    mu[:, 1] = torch.randn(S, K, D) * 0.5
+    u = torch.rand(S, B, N)
+    q_ref = og.enc_apg_z_probs(enc, xs, tau, mu)
+    mlp = [enc[k].to(DEV) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+    z_new, q, _ = kernels.z_step_fused(x.to(DEV), tau.to(DEV), mu.to(DEV), mlp, _Gen(K, D), uniforms=u.to(DEV), want_q=True)
+    assert bool(torch.isfinite(q).all())
+    _close(q, q_ref, rtol=3e-5, atol=2e-7, what="q_probs (saturating)")
+    z_new = z_new.cpu()
+    assert bool((z_new.sum(-1) == 1).all())
+
+
 def test_sweep_statistics_torch_encoder_path():
     """the un-fused Enc_apg_z path (PyTorch MLP + torch categorical draw) stays available and agrees statistically."""
     from apgs_b200.gmm import objectives as O
