@@ -30,10 +30,16 @@ struct NssArgs {
     float *oa, *ob, *om, *on;         // posterior (R, K, D)
     long long R;
     int N;
+    // STATS: also emit the plain one-hot statistics of z centred at `center` (R, K, D):
+    //   stats[r][k] = { sum_n z_nk,  sum_n z_nk (x_nd - c_kd)  (d < D),  sum_n z_nk (x_nd - c_kd)^2  (d < D) }
+    // from which the eta-step log-likelihoods follow in O(K D) per particle (k_gmm_eta_weights_stats)
+    const float* center;
+    float* stats;         // (R, K, 1 + 2 D)
 };
 
-template <int K, int D, int P, int LANES, bool FUSED, bool HAS_Z>
-__global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
+template <int K, int D, int P, int LANES, bool FUSED, bool HAS_Z, bool STATS = false>
+__global__ void __launch_bounds__(P* LANES, STATS ? 4 : 1) k_gmm_nss_posterior(NssArgs a) {
+    static_assert(!STATS || (FUSED && HAS_Z), "plain statistics need the raw x and z");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
     __shared__ float s_wg[K * (D + K) + K], s_wo[D * (D + K) + D];
@@ -69,6 +75,21 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
 #pragma unroll
         for (int d = 0; d < D; ++d) { s2[k][d] = 0.f; s3[k][d] = 0.f; }
     }
+    float c1[STATS ? K : 1], c2[STATS ? K : 1][D], c3[STATS ? K : 1][D], cen[STATS ? K : 1][D];
+    f32x2 c2p[STATS ? K : 1], c3p[STATS ? K : 1], ncen2[STATS ? K : 1];       // D == 2: (d0, d1) pairs
+    if (STATS) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c1[k] = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                c2[k][d] = 0.f; c3[k][d] = 0.f;
+                cen[k][d] = valid ? __ldg(a.center + (r0 + p) * (K * D) + k * D + d) : 0.f;
+            }
+            c2p[k] = pack2(0.f, 0.f); c3p[k] = c2p[k];
+            ncen2[k] = pack2(-cen[k][0], -cen[k][D - 1]);
+        }
+    }
     if (valid) {
         const float* g = s_g + (size_t)p * N * K;
         const float* x = s_x + (size_t)p * N * D;
@@ -88,6 +109,39 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
                 if (HAS_Z) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) in[D + (HAS_Z ? k : 0)] = g[n * K + k];
+                }
+                if (STATS) {
+                    // indicator of the label the reference scores (first maximum, models.py:178), the point centred
+                    // at ITS cluster's centre, then K masked accumulations (packed fp32x2 when D == 2)
+                    int lab = 0;
+                    float best = in[D];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) { const float v = in[D + (HAS_Z ? k : 0)]; if (v > best) { best = v; lab = k; } }
+                    float ind[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { ind[k] = (lab == k) ? 1.f : 0.f; c1[k] += ind[k]; }
+                    if (D == 2) {
+                        f32x2 t = pack2(in[0], in[1]);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) t = fma2(pack2(ind[k], ind[k]), ncen2[k], t);      // x - c_lab
+                        const f32x2 t2 = mul2(t, t);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const f32x2 ik = pack2(ind[k], ind[k]);
+                            c2p[k] = fma2(ik, t, c2p[k]);
+                            c3p[k] = fma2(ik, t2, c3p[k]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            float c = 0.f;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) c = fmaf(ind[k], cen[k][d], c);
+                            const float t = in[d] - c, t2 = t * t;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { c2[k][d] = fmaf(ind[k], t, c2[k][d]); c3[k][d] = fmaf(ind[k], t2, c3[k][d]); }
+                        }
+                    }
                 }
                 float lg[K], mx = -INFINITY;
 #pragma unroll
@@ -132,6 +186,30 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_nss_posterior(NssArgs a) {
         for (int d = 0; d < D; ++d) {
             t2[k][d] = group_sum<LANES>((double)s2[k][d]);
             t3[k][d] = group_sum<LANES>((double)s3[k][d]);
+        }
+    }
+    if (STATS) {
+        // <= ceil(N/LANES) fp32 terms per lane, centred; the LANES partials of a particle meet in shared memory
+        constexpr int ST = 1 + 2 * D, NS = K * ST, NSP = NS | 1;
+        __syncthreads();                                      // every warp is done with the z tile: reuse its memory
+        float* s_red = reinterpret_cast<float*>(smem);        // [P * LANES][NSP] (the launcher sizes for it)
+        float* mine = s_red + (size_t)threadIdx.x * NSP;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (D == 2) { unpack2(c2p[k], c2[k][0], c2[k][D - 1]); unpack2(c3p[k], c3[k][0], c3[k][D - 1]); }
+            mine[k * ST] = c1[k];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { mine[k * ST + 1 + d] = c2[k][d]; mine[k * ST + 1 + D + d] = c3[k][d]; }
+        }
+        __syncwarp();
+        if (valid) {
+            float* so = a.stats + (r0 + p) * NS;
+            for (int e = j; e < NS; e += LANES) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < LANES; ++i) v += s_red[(size_t)(p * LANES + i) * NSP + e];
+                so[e] = v;
+            }
         }
     }
     if (!valid) return;
@@ -382,15 +460,104 @@ __global__ void __launch_bounds__(P* LANES) k_gmm_weights(GmmWArgs a) {
     if (a.log_w_b != nullptr) a.log_w_b[r] = lwb;
 }
 
+// ============================================================================================
+// G2 from statistics: the eta step scores the SAME assignment z under the new and the old (tau, mu)
+// (objectives.py:163-180), so both log-likelihoods are functions of the one-hot statistics of z that
+// k_gmm_nss_posterior<STATS> already accumulated while it read z:
+//   sum_n z_nk log N(x_nd | mu, 1/sqrt(tau)) = -(S2c - 2 dl S1c + cnt dl^2) tau / 2 - cnt (c - log(tau)/2),  dl = mu - c_kd
+// The statistics are centred at c (the old mu), so there is no cancellation for the backward term and only
+// O(|mu_new - mu_old|) of it for the forward term.  O(K D) work and ~300 bytes per particle instead of a second
+// pass over the 720-byte z row and all N points.
+// ============================================================================================
+struct EtaStatsArgs {
+    const float *stats, *center;      // (R, K, 1+2D), (R, K, D)
+    const float *pa, *pb, *pm, *pn;   // posterior (R, K, D)
+    const float *ra, *rb, *rm, *rn;   // prior (K, D)
+    const float *tau_f, *mu_f, *tau_b, *mu_b;
+    long long R;
+    float *log_w, *log_q_f, *dens, *log_w_f, *log_w_b;
+};
+
+template <int K, int D, int LANES>
+__global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
+    constexpr int KD = K * D, ST = 1 + 2 * D;
+    // per (k,d) constants of the prior, once per CTA: a0, b0, m0, n0, a0 log b0 - lgamma(a0), log n0
+    __shared__ float s_pr[KD][6];
+    if (threadIdx.x < KD) {
+        const int e = threadIdx.x;
+        const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), n0 = __ldg(a.rn + e);
+        s_pr[e][0] = a0; s_pr[e][1] = b0; s_pr[e][2] = __ldg(a.rm + e); s_pr[e][3] = n0;
+        s_pr[e][4] = fmaf(a0, logf(b0), -lgammaf(a0));
+        s_pr[e][5] = logf(n0);
+    }
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * (256 / LANES) + threadIdx.x / LANES;
+    const int j = threadIdx.x % LANES;
+    const bool valid = r < a.R;
+    float lq_f = 0.f, lp_f = 0.f, lq_b = 0.f, lp_b = 0.f, ll_f = 0.f, ll_b = 0.f;
+    if (valid) {
+        for (int e = j; e < KD; e += LANES) {
+            const int k = e / D, d = e % D;
+            const float tf = __ldg(a.tau_f + r * KD + e), mf = __ldg(a.mu_f + r * KD + e);
+            const float tbk = __ldg(a.tau_b + r * KD + e), mbk = __ldg(a.mu_b + r * KD + e);
+            const float a0 = s_pr[e][0], b0 = s_pr[e][1], m0 = s_pr[e][2], n0 = s_pr[e][3], gp = s_pr[e][4], Ln0 = s_pr[e][5];
+            const float qa = __ldg(a.pa + r * KD + e), qb = __ldg(a.pb + r * KD + e);
+            const float qm = __ldg(a.pm + r * KD + e), qn = __ldg(a.pn + r * KD + e);
+            const float* sp = a.stats + r * (K * ST) + k * ST;
+            const float cnt = __ldg(sp), S1 = __ldg(sp + 1 + d), S2 = __ldg(sp + 1 + D + d);
+            const float cen = __ldg(a.center + r * KD + e);
+            // SFU logs (abs error ~1e-7 |log|) and the Stirling lgamma: each enters the sums with a factor <= alpha, i.e.
+            // ~1e-7 relative to the magnitudes summed.  Same shared-log forms as k_gmm_weights (see the note there).
+            const float Ltf = log_fast(tf), Ltb = log_fast(tbk);
+            const float gq = fmaf(qa, log_fast(qb), -lgamma_pos(qa));
+            const float Lqn = log_fast(qn);
+            {
+                const float dq = mf - qm, dp = mf - m0, dl = mf - cen;
+                lq_f += (fmaf(qa - 1.f, Ltf, gq) - qb * tf) + (fmaf(-0.5f * dq * dq, qn * tf, 0.5f * (Lqn + Ltf)) - LOG_SQRT_2PI_F);
+                lp_f += (fmaf(a0 - 1.f, Ltf, gp) - b0 * tf) + (fmaf(-0.5f * dp * dp, n0 * tf, 0.5f * (Ln0 + Ltf)) - LOG_SQRT_2PI_F);
+                const float ss = fmaf(dl, fmaf(cnt, dl, -2.f * S1), S2);          // sum z (x - mu)^2
+                ll_f += fmaf(-0.5f * tf, ss, -cnt * fmaf(-0.5f, Ltf, LOG_SQRT_2PI_F));
+            }
+            {
+                const float dq = mbk - qm, dp = mbk - m0, dl = mbk - cen;
+                lq_b += (fmaf(qa - 1.f, Ltb, gq) - qb * tbk) + (fmaf(-0.5f * dq * dq, qn * tbk, 0.5f * (Lqn + Ltb)) - LOG_SQRT_2PI_F);
+                lp_b += (fmaf(a0 - 1.f, Ltb, gp) - b0 * tbk) + (fmaf(-0.5f * dp * dp, n0 * tbk, 0.5f * (Ln0 + Ltb)) - LOG_SQRT_2PI_F);
+                const float ss = fmaf(dl, fmaf(cnt, dl, -2.f * S1), S2);
+                ll_b += fmaf(-0.5f * tbk, ss, -cnt * fmaf(-0.5f, Ltb, LOG_SQRT_2PI_F));
+            }
+        }
+    }
+    lq_f = group_sum<LANES>(lq_f); lp_f = group_sum<LANES>(lp_f); ll_f = group_sum<LANES>(ll_f);
+    lq_b = group_sum<LANES>(lq_b); lp_b = group_sum<LANES>(lp_b); ll_b = group_sum<LANES>(ll_b);
+    if (!valid || j != 0) return;
+    const float lwf = __fsub_rn(__fadd_rn(ll_f, lp_f), lq_f);                     // objectives.py:172,179-180,194
+    const float lwb = __fsub_rn(__fadd_rn(ll_b, lp_b), lq_b);
+    if (a.log_w != nullptr) a.log_w[r] = __fsub_rn(lwf, lwb);
+    if (a.log_q_f != nullptr) a.log_q_f[r] = lq_f;
+    if (a.dens != nullptr) a.dens[r] = lp_f;
+    if (a.log_w_f != nullptr) a.log_w_f[r] = lwf;
+    if (a.log_w_b != nullptr) a.log_w_b[r] = lwb;
+}
+
+template <int K, int D>
+static int launch_eta_stats(const EtaStatsArgs& a, cudaStream_t st) {
+    const long long grid = (a.R + 31) / 32;
+    k_gmm_eta_weights_stats<K, D, 8><<<(unsigned int)grid, 256, 0, st>>>(a);
+    APGS_LAUNCH_OK("k_gmm_eta_weights_stats launch");
+    return 0;
+}
+
 // ----------------------------------------------------------------------------------- launchers
 constexpr int kP = 32, kLanes = 8;
 
 template <int K, int D>
 static int launch_nss(const NssArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)kP * a.N * (K + D) * 4;       // (the fused variant only uses the first K part)
+    size_t smem = (size_t)kP * a.N * (a.gamma == nullptr ? K : K + D) * 4;   // the fused variants only stage z
+    if (a.stats != nullptr) smem = max(smem, (size_t)kP * kLanes * ((K * (1 + 2 * D)) | 1) * 4);
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_nss_posterior: N=%d too large for one tile", a.N);
     void (*kern)(NssArgs) = k_gmm_nss_posterior<K, D, kP, kLanes, false, false>;
-    if (a.gamma == nullptr) kern = a.z != nullptr ? k_gmm_nss_posterior<K, D, kP, kLanes, true, true>
+    if (a.gamma == nullptr) kern = a.z != nullptr ? (a.stats != nullptr ? k_gmm_nss_posterior<K, D, kP, kLanes, true, true, true>
+                                                                        : k_gmm_nss_posterior<K, D, kP, kLanes, true, true>)
                                                   : k_gmm_nss_posterior<K, D, kP, kLanes, true, false>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (a.R + kP - 1) / kP;
@@ -543,4 +710,49 @@ extern "C" int apgs_gmm_eta_posterior_fused_f32(const float* x, const float* z, 
     APGS_KD_DISPATCH(K, D, launch_nss);
     return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_fused: (K=%lld, D=%lld) not instantiated", (long long)K,
                 (long long)D);
+}
+
+extern "C" int apgs_gmm_eta_posterior_stats_f32(const float* x, const float* z, const float* Wg, const float* bg,
+                                                const float* Wo, const float* bo, int64_t S, int64_t B, int64_t N,
+                                                int64_t K, int64_t D, const float* prior_alpha, const float* prior_beta,
+                                                const float* prior_mu, const float* prior_nu, float* post_alpha,
+                                                float* post_beta, float* post_mu, float* post_nu, const float* center,
+                                                float* stats, void* stream) {
+    if (int e = check_gmm_dims(S, B, N, K, D, "gmm_eta_posterior_stats")) return e;
+    if (!x || !z || !Wg || !bg || !Wo || !bo || !prior_alpha || !prior_beta || !prior_mu || !prior_nu || !post_alpha ||
+        !post_beta || !post_mu || !post_nu || !center || !stats)
+        return fail(APGS_E_BADARG, "gmm_eta_posterior_stats: NULL pointer");
+    NssArgs a = {};
+    a.x = x; a.z = z; a.Wg = Wg; a.bg = bg; a.Wo = Wo; a.bo = bo;
+    a.ra = prior_alpha; a.rb = prior_beta; a.rm = prior_mu; a.rn = prior_nu;
+    a.oa = post_alpha; a.ob = post_beta; a.om = post_mu; a.on = post_nu;
+    a.center = center; a.stats = stats;
+    a.R = (long long)S * B; a.N = (int)N; a.B = (int)B;
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_nss);
+    return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats: (K=%lld, D=%lld) not instantiated", (long long)K,
+                (long long)D);
+}
+
+extern "C" int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                           const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
+                                           const float* tau_old, const float* mu_old, int64_t S, int64_t B, int64_t K,
+                                           int64_t D, const apgs_gmm_out_t* out, void* stream) {
+    if (S <= 0 || B <= 0 || S * B >= (1ll << 36))
+        return fail(APGS_E_SHAPE, "gmm_logw_eta_stats: bad sizes S=%lld B=%lld", (long long)S, (long long)B);
+    if (!stats || !center || !post || !prior || !out || !tau || !mu || !tau_old || !mu_old)
+        return fail(APGS_E_BADARG, "gmm_logw_eta_stats: NULL input");
+    if (!post->alpha || !post->beta || !post->mu || !post->nu || !prior->alpha || !prior->beta || !prior->mu || !prior->nu)
+        return fail(APGS_E_BADARG, "gmm_logw_eta_stats: NULL prior / posterior parameter");
+    EtaStatsArgs a = {};
+    a.stats = stats; a.center = center;
+    a.pa = post->alpha; a.pb = post->beta; a.pm = post->mu; a.pn = post->nu;
+    a.ra = prior->alpha; a.rb = prior->beta; a.rm = prior->mu; a.rn = prior->nu;
+    a.tau_f = tau; a.mu_f = mu; a.tau_b = tau_old; a.mu_b = mu_old;
+    a.R = (long long)S * B;
+    a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;
+    a.log_w_b = out->log_w_b;
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_eta_stats);
+    return fail(APGS_E_UNSUPPORTED, "gmm_logw_eta_stats: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
 }

@@ -101,6 +101,18 @@ __device__ __forceinline__ float log_fast(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y * 0.693147180559945309417f;
 }
+// lgamma(x), x > 0, for the Gamma normaliser of the eta step: shift up by four (lgamma(x) = lgamma(x+4) - log(x(x+1)(x+2)(x+3)))
+// and Stirling's series at y = x + 4 >= 4 (first omitted term 1/(1680 y^7) < 4e-8).  ~25 instructions and two SFU logs
+// instead of the ~100 of lgammaf(); absolute error ~3e-7 |lgamma| + 1e-6, the same order as lgammaf's own (a few ulp).
+__device__ __forceinline__ float lgamma_pos(float x) {
+    const bool big = x > 1.0e8f;                        // the shift is irrelevant there and x^4 would overflow
+    const float y = big ? x : x + 4.f;
+    const float ry = rcp_ftz(y), ry2 = ry * ry;
+    const float series = ry * fmaf(ry2, fmaf(ry2, 7.9365079365e-4f, -2.7777777778e-3f), 8.3333333333e-2f);
+    const float st = fmaf(y - 0.5f, log_fast(y), -y) + (0.918938533204672742f + series);
+    const float prod = (x * (x + 1.f)) * ((x + 2.f) * (x + 3.f));
+    return big ? st : st - log_fast(prod);
+}
 __device__ __forceinline__ float tanh_prescaled(float a) {
     return fmaf(rcp_ftz(ex2_ftz(a) + 1.f), -2.f, 1.f);
 }

@@ -98,6 +98,28 @@ def logw_eta(x, z, post, prior, tau, mu, tau_old, mu_old, parts=False):
     return w
 
 
+def logw_eta_stats(stats, center, post, prior, tau, mu, tau_old, mu_old, parts=False):
+    """G2 evaluated from the centred one-hot statistics of z (eta_posterior_fused(..., center=)): same outputs as
+    logw_eta without a second pass over z (apgs/gmm/objectives.py:161-195)."""
+    lib = _lib.load()
+    stats, center = _req(stats, "stats", ndim=4), _req(center, "center", ndim=4)
+    tau, mu, tau_old, mu_old = [_req(v, "tau/mu", ndim=4) for v in (tau, mu, tau_old, mu_old)]
+    S, B, K, D = tau.shape
+    if tuple(stats.shape) != (S, B, K, 1 + 2 * D) or tuple(center.shape) != (S, B, K, D):
+        raise ValueError("stats/center have shapes %s %s" % (tuple(stats.shape), tuple(center.shape)))
+    for v in (mu, tau_old, mu_old):
+        if tuple(v.shape) != (S, B, K, D):
+            raise ValueError("tau/mu shapes differ")
+    ps, pk = _post_struct(post)
+    rs, rk = _prior_struct(prior)
+    w, o = _outs(S, B, 1, tau.device, parts, False)
+    with torch.cuda.device(tau.device), _call("gmm_logw_eta_stats", 1, 4 * S * B * (K * (1 + 2 * D) + 9 * K * D + 3)):
+        check(lib.apgs_gmm_logw_eta_stats_f32(ptr(stats), ptr(center), C.byref(ps), C.byref(rs), ptr(tau), ptr(mu),
+                                              ptr(tau_old), ptr(mu_old), S, B, K, D, C.byref(o), _stream()),
+              "apgs_gmm_logw_eta_stats_f32")
+    return w
+
+
 def logw_z(x, tau, mu, q_probs, prior, z, z_old, parts=False, local=False):
     """G3 (+W2): z-step weights (apgs/gmm/objectives.py:197-227)."""
     lib = _lib.load()
@@ -166,9 +188,11 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     return z_new, q, w
 
 
-def eta_posterior_fused(x, z, heads, prior):
+def eta_posterior_fused(x, z, heads, prior, center=None):
     """N1b+G1: Linear heads of Enc_apg_eta (z given) / Enc_rws_eta (z None) + softmax + NSS posterior.
-    heads = (Wg, bg, Wo, bo).  Returns alpha, beta, mu, nu of shape (S,B,K,D) ((1,B,K,D) when z is None)."""
+    heads = (Wg, bg, Wo, bo).  Returns alpha, beta, mu, nu of shape (S,B,K,D) ((1,B,K,D) when z is None).
+    With `center` (S,B,K,D; the old mu) the same pass also returns the centred one-hot statistics of z,
+    (S,B,K,1+2D), as a fifth tensor -- the input of logw_eta_stats."""
     lib = _lib.load()
     x = _x3(x)
     B, N, D = x.shape
@@ -186,6 +210,18 @@ def eta_posterior_fused(x, z, heads, prior):
         raise ValueError("unexpected head weight shapes %s %s" % (tuple(Wg.shape), tuple(Wo.shape)))
     pr = [_req(getattr(prior, "prior_" + n), "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
     outs = [torch.empty(S, B, K, D, dtype=torch.float32, device=x.device) for _ in range(4)]
+    if center is not None:
+        if z is None:
+            raise ValueError("centred statistics need z")
+        center = _req(center, "center", ndim=4)
+        if tuple(center.shape) != (S, B, K, D):
+            raise ValueError("center has shape %s, expected %s" % (tuple(center.shape), (S, B, K, D)))
+        stats = torch.empty(S, B, K, 1 + 2 * D, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device), _call("gmm_eta_posterior_stats", 1, 4 * S * B * (N * K + 6 * K * D + K * (1 + 2 * D))):
+            check(lib.apgs_gmm_eta_posterior_stats_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
+                                                       *[ptr(v) for v in pr], *[ptr(v) for v in outs], ptr(center),
+                                                       ptr(stats), _stream()), "apgs_gmm_eta_posterior_stats_f32")
+        return tuple(outs) + (stats,)
     with torch.cuda.device(x.device), _call("gmm_eta_posterior_fused", 1, 4 * S * B * (N * K + 4 * K * D)):
         check(lib.apgs_gmm_eta_posterior_fused_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
                                                    *[ptr(v) for v in pr], *[ptr(v) for v in outs], _stream()),

@@ -129,10 +129,13 @@ class Enc_apg_eta(nn.Module):
 
     fused = True
 
-    def params(self, ob, z, prior_ng):
+    def params(self, ob, z, prior_ng, center=None):
+        """posterior parameters (alpha, beta, mu, nu); with `center` (the old mu) the fused kernel's pass over z also
+        returns the centred one-hot statistics of z as a fifth tensor (see kernels.logw_eta_stats)."""
         if self.fused:
             return kernels.eta_posterior_fused(ob, z, (self.gamma[0].weight, self.gamma[0].bias,
-                                                       self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng))
+                                                       self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng),
+                                               center=center)
         xp, gam = self.heads(ob, z)
         return kernels.nss_posterior(xp, gam, _PriorNG(prior_ng))
 

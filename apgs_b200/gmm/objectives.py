@@ -129,9 +129,16 @@ def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_o
 
 def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags):
     """Given local variable z, update global variables eta := {mu, tau} (objectives.py:161-195)."""
-    post = enc_apg_eta.params(x, z, generative.prior_ng)
-    tau, mu = _sample_eta(post)
-    w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
+    if getattr(enc_apg_eta, 'fused', False):
+        # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of
+        *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old)
+        post = tuple(post)
+        tau, mu = _sample_eta(post)
+        w = kernels.logw_eta_stats(stats, mu_old, post, generative, tau, mu, tau_old, mu_old)
+    else:
+        post = enc_apg_eta.params(x, z, generative.prior_ng)
+        tau, mu = _sample_eta(post)
+        w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
     log_q_f = w.log_q_f
     if result_flags['loss_required'] and needs_grad(enc_apg_eta):
         log_q_f = eta_log_q_torch(enc_apg_eta.params_torch(x, z, generative.prior_ng), tau, mu)

@@ -208,6 +208,27 @@ APGS_API int apgs_gmm_eta_posterior_fused_f32(const float* x, const float* z,
                                      float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
                                      void* stream);
 
+/* G1+G2 from statistics.  The eta step scores the SAME assignment z under the new and the old (tau, mu)
+ *     (apgs/gmm/objectives.py:163-180), so its two log-likelihoods (apgs/gmm/models.py:172-185) are functions
+ *     of the one-hot statistics of z.  apgs_gmm_eta_posterior_stats_f32 is apgs_gmm_eta_posterior_fused_f32
+ *     that also writes, from the same pass over z,
+ *       stats (S,B,K,1+2D):  [k] = { sum_n z_nk,  sum_n z_nk (x_nd - c_kd) (d<D),  sum_n z_nk (x_nd - c_kd)^2 (d<D) }
+ *     centred at `center` (S,B,K,D) -- pass the OLD mu, which makes the backward term cancellation-free;
+ *     apgs_gmm_logw_eta_stats_f32 is apgs_gmm_logw_eta_f32 evaluated from those statistics: O(K D) work and
+ *     ~300 bytes per particle, no second pass over z.                                                 */
+APGS_API int apgs_gmm_eta_posterior_stats_f32(const float* x, const float* z,
+                                     const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                     int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                     const float* prior_alpha, const float* prior_beta,
+                                     const float* prior_mu, const float* prior_nu,
+                                     float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
+                                     const float* center, float* stats, void* stream);
+APGS_API int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
+                                const float* tau_old, const float* mu_old,
+                                int64_t S, int64_t B, int64_t K, int64_t D,
+                                const apgs_gmm_out_t* out, void* stream);
+
 /* ==============================================================================================
  * Bouncing-MNIST.  FP frame pixels (96), DP digit pixels (28), K digits,
  * T frames.  The transformer is the reference's: nearest sampling, align_corners=True, diagonal theta

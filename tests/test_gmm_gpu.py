@@ -124,6 +124,87 @@ def test_G2_eta_step_vs_reference_golden(golden):
     assert torch.equal(w2.log_w, w.log_w)
 
 
+def _heads(P):
+    p = P["enc_apg_eta"]
+    return [p[k].to(DEV) for k in ("gamma.0.weight", "gamma.0.bias", "ob.0.weight", "ob.0.bias")]
+
+
+def _stats_ref(x, z, center):
+    """centred one-hot statistics of z in fp64: (S,B,K,1+2D)."""
+    zz, t = z.double().unsqueeze(-1), x.double().unsqueeze(0).unsqueeze(-2) - center.double().unsqueeze(2)   # (S,B,N,K,D)
+    return torch.cat([z.double().sum(2).unsqueeze(-1), (zz * t).sum(2), (zz * t * t).sum(2)], -1)
+
+
+def test_G2_eta_step_from_statistics_vs_reference_golden(golden):
+    """the product's eta step: one pass over z (posterior + centred statistics), weights from the statistics."""
+    from apgs_b200.gmm import kernels
+    g = golden("gmm")
+    P, prior = _params(g), og.make_prior()
+    S = g["eta_z"].shape[0]
+    x, z, mu_old = _t(g, "x"), _t(g, "eta_z"), _t(g, "eta_mu_old")
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    post = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, z, prior)
+    ref = og.eta_step_weights(xs, z, post, prior, _t(g, "eta_tau"), _t(g, "eta_mu"), _t(g, "eta_tau_old"), mu_old, parts=True)
+    *post_k, stats = kernels.eta_posterior_fused(x.to(DEV), z.to(DEV), _heads(P), _Gen(), center=mu_old.to(DEV))
+    post_plain = kernels.eta_posterior_fused(x.to(DEV), z.to(DEV), _heads(P), _Gen())
+    for a, b in zip(post_k, post_plain):
+        assert torch.equal(a, b)                                   # the extra output does not change the posterior
+    sr = _stats_ref(x, z, mu_old)
+    assert torch.equal(stats[..., 0].cpu().double(), sr[..., 0])   # counts are exact
+    mag = _stats_ref(x.abs(), z, -mu_old.abs())                    # magnitudes entering the sums
+    _close(stats, sr, rtol=0, atol=2e-6 * mag + 1e-30, what="centred statistics")
+    w = kernels.logw_eta_stats(stats, mu_old.to(DEV), tuple(post_k), _Gen(), *_dev(_t(g, "eta_tau"), _t(g, "eta_mu"),
+                               _t(g, "eta_tau_old"), mu_old), parts=True)
+    _close(w.log_w_f, ref[4], what="log_w_f")
+    _close(w.log_w_b, ref[5], what="log_w_b")
+    _close(w.log_q_f, ref[1], rtol=0, atol=RT * _eta_mag(_t(g, "eta_tau"), _t(g, "eta_mu"), post), what="log_q_f")
+    _close(w.density, _t(g, "eta_density")[0], what="density")
+    _close(w.log_w, _t(g, "eta_log_w"), rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="log_w")
+
+
+@pytest.mark.parametrize("S,B,N,K,D,spread,tau_scale", [(5, 3, 60, 3, 2, 2.0, 3.0), (37, 9, 41, 4, 2, 2.0, 3.0), (2, 1, 7, 3, 3, 2.0, 3.0),
+                                                       (40, 6, 60, 3, 2, 0.05, 400.0), (33, 5, 200, 4, 2, 10.0, 0.05)])
+def test_G2_eta_step_from_statistics_random_shapes(S, B, N, K, D, spread, tau_scale):
+    """statistics route vs the oracle's pointwise sums: ragged tiles, other (K,D), and tight clusters far from the
+    origin (tau ~ 400, |x| ~ 10), where un-centred statistics would cancel catastrophically."""
+    from apgs_b200.gmm import kernels
+    torch.manual_seed(S + N + K)
+    prior, gen = og.make_prior(K, D), _Gen(K, D)
+    lab = torch.randint(0, K, (S, B, N))
+    z = torch.nn.functional.one_hot(lab, K).float()
+    if S > 4:
+        z[1, 0] = torch.nn.functional.one_hot(torch.zeros(N, dtype=torch.long), K).float()    # empty clusters
+    centres = torch.randn(B, K, D) * 10
+    x = centres[:, torch.randint(0, K, (N,))][torch.arange(B), :, :] + torch.randn(B, N, D) * spread
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    mu_old = centres.unsqueeze(0) + torch.randn(S, B, K, D) * spread
+    mu = mu_old + torch.randn(S, B, K, D) * spread * 0.5
+    tau, tau_old = (torch.rand(S, B, K, D) + 0.1) * tau_scale, (torch.rand(S, B, K, D) + 0.1) * tau_scale
+    post = (torch.rand(S, B, K, D) * 20 + 1, torch.rand(S, B, K, D) * 20 + 0.5, mu_old + torch.randn(S, B, K, D) * spread,
+            torch.rand(S, B, K, D) * 20 + 0.1)
+    heads = [torch.randn(K, D + K), torch.randn(K), torch.randn(D, D + K), torch.randn(D)]
+    out = kernels.eta_posterior_fused(x.to(DEV), z.to(DEV), [h.to(DEV) for h in heads], gen, center=mu_old.to(DEV))
+    stats = out[4]
+    w = kernels.logw_eta_stats(stats, mu_old.to(DEV), _dev(*post), gen, *_dev(tau, mu, tau_old, mu_old), parts=True)
+    # fp64 truth and the magnitudes that are added (|ll| + |log p| + |log q|), as in SURVEY.md H2
+    d = lambda t: t.double()
+    pr64 = {k: d(v) for k, v in prior.items()}
+    p64 = tuple(d(v) for v in post)
+    ref = og.eta_step_weights(d(xs), d(z), p64, pr64, d(tau), d(mu), d(tau_old), d(mu_old), parts=True)
+    ref32 = og.eta_step_weights(xs, z, post, prior, tau, mu, tau_old, mu_old, parts=True)
+    ll_mag = lambda t, m: (d(z).unsqueeze(-1) * (0.5 * d(t).unsqueeze(2) * (d(xs).unsqueeze(-2) - d(m).unsqueeze(2)) ** 2
+                                                 + (0.5 * d(t).log().abs() + 0.9189385).unsqueeze(2))).sum((2, 3, 4))
+    mag_f = ll_mag(tau, mu) + og.eta_log_prior(d(tau), d(mu), pr64).abs() + og.eta_log_q(d(tau), d(mu), p64).abs()
+    mag_b = ll_mag(tau_old, mu_old) + og.eta_log_prior(d(tau_old), d(mu_old), pr64).abs() + og.eta_log_q(d(tau_old), d(mu_old), p64).abs()
+    _close(w.log_w_f, ref[4], rtol=0, atol=RT * mag_f, what="eta f (stats)")
+    _close(w.log_w_b, ref[5], rtol=0, atol=RT * mag_b, what="eta b (stats)")
+    _close(w.log_w, ref[0], rtol=0, atol=RT * (mag_f + mag_b), what="eta log_w (stats)")
+    # and at least as close to the fp64 truth as the reference's own fp32 arithmetic is
+    err_k = (w.log_w.cpu().double() - ref[0]).abs().max()
+    err_r = (ref32[0].double() - ref[0]).abs().max()
+    assert float(err_k) <= 2.0 * float(err_r) + 1e-6 * float((mag_f + mag_b).max())
+
+
 def test_G3_z_step_vs_reference_golden(golden):
     from apgs_b200.gmm import kernels
     from apgs_b200 import ops
