@@ -40,6 +40,11 @@ class DmmPrior(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("mu_mu", "mu_sigma", "pi", "con1", "con0", "radi", "recon_sigma")]
 
 
+class DmmMlp(C.Structure):
+    """nn.Sequential(Linear, act, Linear): .0.weight, .0.bias, .2.weight, .2.bias (device pointers)."""
+    _fields_ = [(n, C.c_void_p) for n in ("W0", "b0", "W2", "b2")]
+
+
 class DmmOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("log_w", "log_q_f", "density", "ll_f", "log_w_f", "log_w_b",
                                           "log_w_local", "log_q_local", "ll_local")]
@@ -47,7 +52,7 @@ class DmmOut(C.Structure):
 
 _p, _i64, _int, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
 _PR, _PO, _OUT = C.POINTER(GmmPrior), C.POINTER(GmmPost), C.POINTER(GmmOut)
-_DPR, _DOUT = C.POINTER(DmmPrior), C.POINTER(DmmOut)
+_DPR, _DOUT, _DMLP = C.POINTER(DmmPrior), C.POINTER(DmmOut), C.POINTER(DmmMlp)
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
@@ -69,6 +74,9 @@ SIGNATURES = {
     "apgs_gmm_logw_joint_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _p, _p, _p,
                                        _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_dmm_nss_pool_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_dmm_nss_pool_onehot_f32": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_dmm_local_encoder_fused_f32": (_int, [_p, _p, _DMLP, _DMLP, _DMLP, _i64, _p, _p, _p] + [_i64] * 5 + [_p] * 7),
+    "apgs_dmm_decoder_hidden2_f32": (_int, [_p, _DMLP, _i64, _i64, _i64, _p, _p]),
     "apgs_dmm_logw_mu_f32": (_int, [_p] * 7 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
     "apgs_dmm_logw_local_f32": (_int, [_p] * 13 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
     "apgs_dmm_logw_oneshot_f32": (_int, [_p] * 10 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),

@@ -4,7 +4,7 @@ import ctypes as C
 import torch
 
 from .. import _lib
-from .._lib import DmmOut, DmmPrior, check, ptr
+from .._lib import DmmMlp, DmmOut, DmmPrior, check, ptr
 from ..ops import _call, _req, _stream
 
 
@@ -111,3 +111,83 @@ def logw_oneshot(x, q_mu, q_sigma, mu, q_probs, z, beta, con1, con0, hidden2, de
                                             ptr(b[2]), ptr(hidden2), C.byref(ps), S, B, N, K, D, C.byref(o), _stream()),
               "apgs_dmm_logw_oneshot_f32")
     return w
+
+
+# ------------------------------------------------------------------------------ fused encoders / decoder (N1)
+def _mlp_struct(seq, name):
+    """seq: nn.Sequential(Linear, act, Linear) -> (DmmMlp, tensors kept alive, H)."""
+    t = [_req(v, name) for v in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
+    return DmmMlp(*[v.data_ptr() for v in t]), t, seq[0].weight.shape[0]
+
+
+def nss_pool_onehot(tab1, tab2, z, prior_mu_mu, prior_mu_sigma):
+    """D1 for one-hot z from per-instance label tables: tab1 (B,N,K,J) = nss1(cat(x_n, e_l)), tab2 (B,N,K,K) =
+    softmax(nss2(cat(x_n, e_l))) -> (S,B,K,J+2D)  (apgs/dmm/models.py:129-139)."""
+    lib = _lib.load()
+    tab1, tab2, z = _req(tab1, "tab1", ndim=4), _req(tab2, "tab2", ndim=4), _req(z, "z", ndim=4)
+    S, B, N, K = z.shape
+    J = tab1.shape[-1]
+    if tuple(tab1.shape) != (B, N, K, J) or tuple(tab2.shape) != (B, N, K, K):
+        raise ValueError("label tables have shapes %s %s, expected (%d,%d,%d,J) and (%d,%d,%d,%d)"
+                         % (tuple(tab1.shape), tuple(tab2.shape), B, N, K, B, N, K, K))
+    pm, ps = _req(prior_mu_mu, "prior_mu_mu"), _req(prior_mu_sigma, "prior_mu_sigma")
+    D = pm.numel()
+    out = torch.empty(S, B, K, J + 2 * D, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device), _call("dmm_nss_pool_onehot", 1, 4 * (S * B * (N * K + K * (J + 2 * D)) + B * N * K * (J + K))):
+        check(lib.apgs_dmm_nss_pool_onehot_f32(ptr(tab1), ptr(tab2), ptr(z), ptr(pm), ptr(ps), S, B, N, K, J, D, ptr(out),
+                                               _stream()), "apgs_dmm_nss_pool_onehot_f32")
+    return out
+
+
+def local_encoder_fused(x, mu, enc, uniforms=None, z_forced=None, z_old=None):
+    """Enc_apg_local in one kernel (apgs/dmm/models.py:76-101).  enc: module with pi_log_prob, angle_log_con1,
+    angle_log_con0.  Returns q_probs (S,B,N,K), z (S,B,N,K), con1, con0 (S,B,N,1) and, when z_old is given,
+    con1_old, con0_old (S,B,N,1) (else None, None)."""
+    lib = _lib.load()
+    x = _x3(x)
+    mu = _req(mu, "mu", ndim=4)
+    S, B, K, D = mu.shape
+    N = x.shape[1]
+    if tuple(x.shape) != (B, N, D):
+        raise ValueError("x has shape %s, expected (%d,N,%d)" % (tuple(x.shape), B, D))
+    pi, k1, H = _mlp_struct(enc.pi_log_prob, "pi_log_prob")
+    c1, k2, H1 = _mlp_struct(enc.angle_log_con1, "angle_log_con1")
+    c0, k3, H0 = _mlp_struct(enc.angle_log_con0, "angle_log_con0")
+    if not (H == H1 == H0):
+        raise ValueError("the three local MLPs must share num_hidden")
+    dev = mu.device
+    if uniforms is None and z_forced is None:
+        uniforms = torch.rand(S, B, N, dtype=torch.float32, device=dev)
+    for name, t, shp in (("uniforms", uniforms, (S, B, N)), ("z_forced", z_forced, (S, B, N, K)), ("z_old", z_old, (S, B, N, K))):
+        if t is not None:
+            _req(t, name)
+            if tuple(t.shape) != shp:
+                raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), shp))
+    q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
+    z = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
+    con = [torch.empty(S, B, N, 1, dtype=torch.float32, device=dev) for _ in range(4 if z_old is not None else 2)]
+    co = con + [None, None] if z_old is None else con
+    nbytes = 4 * S * B * (N * (2 * K + 1 + len(con) + (K if z_old is not None else 0)) + K * D)
+    with torch.cuda.device(dev), _call("dmm_local_encoder_fused", 1, nbytes):
+        check(lib.apgs_dmm_local_encoder_fused_f32(ptr(x), ptr(mu), C.byref(pi), C.byref(c1), C.byref(c0), H, ptr(uniforms),
+                                                   ptr(z_forced), ptr(z_old), S, B, N, K, D, ptr(q), ptr(z), ptr(co[0]),
+                                                   ptr(co[1]), ptr(co[2]), ptr(co[3]), _stream()),
+              "apgs_dmm_local_encoder_fused_f32")
+    return q, z, co[0], co[1], co[2], co[3]
+
+
+def decoder_hidden2(beta, recon_mu):
+    """unit-normalised decoder output (apgs/dmm/models.py:202-203): beta (...,1) -> (...,D)."""
+    lib = _lib.load()
+    beta = _req(beta, "beta")
+    net, keep, H = _mlp_struct(recon_mu, "recon_mu")
+    D = recon_mu[2].weight.shape[0]
+    if recon_mu[0].weight.shape[1] != 1:
+        raise ValueError("recon_mu must map 1 -> H -> D")
+    M = beta.numel()
+    shape = tuple(beta.shape[:-1]) if beta.shape[-1] == 1 else tuple(beta.shape)
+    out = torch.empty(shape + (D,), dtype=torch.float32, device=beta.device)
+    with torch.cuda.device(beta.device), _call("dmm_decoder_hidden2", 1, 4 * M * (1 + D)):
+        check(lib.apgs_dmm_decoder_hidden2_f32(ptr(beta), C.byref(net), H, D, M, ptr(out), _stream()),
+              "apgs_dmm_decoder_hidden2_f32")
+    return out

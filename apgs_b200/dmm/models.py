@@ -69,8 +69,23 @@ class Enc_apg_mu(_EncMu):
         super(self.__class__, self).__init__()
         self._build(D + K, K, D, num_hidden, num_nss)
 
+    fused = True          # evaluation path: per-instance label tables + csrc/dmm_fused.cu (z must be one-hot)
+
+    def label_tables(self, x):
+        """nss1 / softmax(nss2) of cat(x_n, e_l) for every label l: (B,N,K,J), (B,N,K,K).  z is one-hot, so these are
+        ALL the values the per-point MLPs can take -- computed once per instance instead of once per particle."""
+        B, N, D = x.shape
+        K = self.nss1[0].weight.shape[1] - D
+        eye = torch.eye(K, dtype=x.dtype, device=x.device)
+        inp = torch.cat((x.unsqueeze(2).expand(B, N, K, D), eye.expand(B, N, K, K)), -1)
+        return self.nss1(inp).contiguous(), self.nss2(inp).contiguous()
+
     def params(self, ob, z, beta, K, priors):
         x = _x_inst(ob)
+        if self.fused and not any(p.requires_grad for p in self.parameters()):
+            tab1, tab2 = self.label_tables(x)
+            nss_prior = kernels.nss_pool_onehot(tab1, tab2, z, priors[0], priors[1])
+            return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
         h1 = torch.tanh(_split_linear(self.nss1[0], x, z))
         h2 = torch.tanh(_split_linear(self.nss2[0], x, z))
         return self._heads(self.nss1[2](h1), F.softmax(self.nss2[2](h2), -1), priors)
@@ -85,6 +100,16 @@ class Enc_apg_local(nn.Module):
         self.pi_log_prob = nn.Sequential(nn.Linear(D, num_hidden), nn.ReLU(), nn.Linear(num_hidden, 1))
         self.angle_log_con1 = nn.Sequential(nn.Linear(D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, 1))
         self.angle_log_con0 = nn.Sequential(nn.Linear(D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, 1))
+
+    fused = True          # evaluation path: csrc/dmm_fused.cu
+
+    def can_fuse(self):
+        return self.fused and not any(p.requires_grad for p in self.parameters())
+
+    def sample_fused(self, ob, mu, z_old=None, uniforms=None, z_forced=None):
+        """probs + categorical draw + Beta concentrations (for z and, when given, for z_old) in one kernel:
+        q_probs, z, con1, con0, con1_old, con0_old."""
+        return kernels.local_encoder_fused(_x_inst(ob), mu, self, uniforms=uniforms, z_forced=z_forced, z_old=z_old)
 
     def probs(self, ob, mu, K):
         """q_probs (S,B,N,K): MLP on x_n - mu_k (models.py:78-79); W (x - mu) + b = (W x + b) - W mu."""
@@ -132,8 +157,12 @@ class Decoder(nn.Module):
         self.recon_sigma = torch.ones(1, device=dev) * recon_sigma
         self.radi = nn.Parameter(torch.ones(1, device=dev))
 
+    fused = True          # evaluation path: csrc/dmm_fused.cu
+
     def hidden2(self, beta):
         """unit-normalised decoder output (models.py:202-203)."""
+        if self.fused and beta.is_cuda and not any(p.requires_grad for p in self.recon_mu.parameters()):
+            return kernels.decoder_hidden2(beta, self.recon_mu)
         hidden = self.recon_mu(beta * 2 * math.pi)
         return hidden / (hidden ** 2).sum(-1).unsqueeze(-1).sqrt()
 

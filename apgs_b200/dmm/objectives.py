@@ -55,7 +55,15 @@ def apg_objective(models, x, K, result_flags, num_sweeps, resampler):
     return trace
 
 
-def _sample_local(enc_local, x, mu, K):
+def _sample_local(enc_local, x, mu, K, z_old=None):
+    """q_probs, z, con1, con0, beta (+ the concentrations at z_old for the backward kernel when z_old is given)."""
+    if enc_local.can_fuse():
+        q_probs, z, con1, con0, con1_b, con0_b = enc_local.sample_fused(x, mu, z_old=z_old)
+        beta = Beta(con1, con0, validate_args=False).sample()
+        return (q_probs, z, con1, con0, beta) if z_old is None else (q_probs, z, con1, con0, beta, con1_b, con0_b)
+    if z_old is not None:
+        out = _sample_local(enc_local, x, mu, K)
+        return out + tuple(enc_local.cons(x, mu, z_old))
     q_probs = enc_local.probs(x, mu, K)
     z = cat(q_probs, validate_args=False).sample()
     con1, con0 = enc_local.cons(x, mu, z)
@@ -97,8 +105,7 @@ def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags):
 
 def apg_update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_flags):
     """Given mu, update the local variables {z, beta} (objectives.py:153-188)."""
-    q_probs, z, con1, con0, beta = _sample_local(enc_apg_local, x, mu, K)
-    con1_b, con0_b = enc_apg_local.cons(x, mu, z_old)
+    q_probs, z, con1, con0, beta, con1_b, con0_b = _sample_local(enc_apg_local, x, mu, K, z_old=z_old)
     h2, h2_old = dec.hidden2(beta), dec.hidden2(beta_old)
     need_local = bool(result_flags['loss_required'])
     w = kernels.logw_local(x, mu, q_probs, z, beta, con1, con0, h2, z_old, beta_old, con1_b, con0_b, h2_old, dec,

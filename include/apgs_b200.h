@@ -327,6 +327,39 @@ APGS_API int apgs_dmm_logw_oneshot_f32(const float* x, const float* q_mu, const 
                               int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
                               const apgs_dmm_out_t* out, void* stream);
 
+/* ---- fused DMM encoders / decoder ("the analogous Enc_apg_local") -------------- */
+typedef struct apgs_dmm_mlp {         /* HOST struct of DEVICE pointers: nn.Sequential(Linear(i,H), act, Linear(H,o)) */
+    const float *W0, *b0;             /* (H, i), (H)   = <name>.0.weight / .0.bias   */
+    const float *W2, *b2;             /* (o, H), (o)   = <name>.2.weight / .2.bias   */
+} apgs_dmm_mlp_t;
+
+/* D1 for Enc_apg_mu with one-hot z (apgs/dmm/models.py:129-139).  z is one-hot, so nss1/nss2 of cat(x_n, z_n)
+ *   take K distinct values per data point; the caller tabulates them once per INSTANCE,
+ *     tab1 (B,N,K,J) = nss1(cat(x_n, e_l)),  tab2 (B,N,K,K) = softmax(nss2(cat(x_n, e_l))),  l = label,
+ *   and this entry pools them over the labels argmax(z) (first maximum): out (S,B,K,J+2D) as apgs_dmm_nss_pool_f32. */
+APGS_API int apgs_dmm_nss_pool_onehot_f32(const float* tab1, const float* tab2, const float* z,
+                                 const float* prior_mu_mu, const float* prior_mu_sigma,
+                                 int64_t S, int64_t B, int64_t N, int64_t K, int64_t J, int64_t D,
+                                 float* out, void* stream);
+
+/* Enc_apg_local.forward (apgs/dmm/models.py:76-101) in one pass:
+ *   q_probs (S,B,N,K) = softmax_k pi_log_prob(x_n - mu_k)                               [:78-79]
+ *   z       (S,B,N,K) = z_forced, or the inverse-CDF draw of q_probs at uniforms (S,B,N) [:81]
+ *   con1, con0 (S,B,N) = exp(angle_log_con{1,0}(x_n - mu_{z_n}))                         [:86-88]
+ *   con1_old, con0_old = the same at z_old (S,B,N,K), when given (backward kernel)       [:99-101]
+ *   nets: pi (D->H->ReLU->1), con1 / con0 (D->H->tanh->1), all with the same H.                              */
+APGS_API int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
+                                 const apgs_dmm_mlp_t* pi, const apgs_dmm_mlp_t* con1_net, const apgs_dmm_mlp_t* con0_net,
+                                 int64_t H, const float* uniforms, const float* z_forced, const float* z_old,
+                                 int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                 float* q_probs, float* z, float* con1, float* con0,
+                                 float* con1_old, float* con0_old, void* stream);
+
+/* Decoder.recon_mu + unit normalisation (apgs/dmm/models.py:202-203): hidden2 (M,D) from beta (M), M = S*B*N;
+ *   net = recon_mu (1->H->tanh->D).                                                                          */
+APGS_API int apgs_dmm_decoder_hidden2_f32(const float* beta, const apgs_dmm_mlp_t* net, int64_t H, int64_t D,
+                                 int64_t M, float* hidden2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,130 @@ def test_dmm_encoder_parameters_match_oracle(golden):
         assert set(p.keys()) == {"means", "states", "angles", "likelihood"} and p["likelihood"].log_prob.shape == (S, B, N, D)
 
 
+# ------------------------------------------------------------------------ N1: fused encoders / decoder
+def _mods(K, D, H, NSS=8, seed=0):
+    from apgs_b200.dmm import models as M
+    torch.manual_seed(seed)
+    P = od.make_params(K, D, H, NSS, H, H)
+    ms = M.init_apg_models(K, D, H, NSS, H, H, 0.5, True, DEV)
+    for m, key in zip(ms, ("enc_rws_mu", "enc_apg_local", "enc_apg_mu", "dec")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})
+    return P, ms
+
+
+@pytest.mark.parametrize("S,B,N,K,D,H", [(5, 3, 200, 4, 2, 32), (19, 2, 37, 3, 2, 16), (9, 1, 65, 4, 3, 33), (2, 2, 5, 5, 2, 8)])
+def test_N1_enc_apg_mu_label_tables_vs_oracle(S, B, N, K, D, H):
+    """Enc_apg_mu through per-instance label tables + the one-hot pooling kernel == the oracle's per-particle MLPs."""
+    P, (_, _, enc_apg_mu, dec) = _mods(K, D, H, seed=S + N)
+    prior = od.make_prior(K, D)
+    x = torch.randn(B, N, D) * 2
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    if S > 2:
+        z[1, 0] = torch.nn.functional.one_hot(torch.zeros(N, dtype=torch.long), K).float()      # empty clusters
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    inp = torch.cat((xs, z), -1)
+    p = P["enc_apg_mu"]
+    nss_ref = od.nss_pool(od._mlp2(p, "nss1", inp, torch.tanh), torch.softmax(od._mlp2(p, "nss2", inp, torch.tanh), -1), prior)
+    q_mu_ref, q_sigma_ref = od.enc_mu_params(p, inp, prior)
+    from apgs_b200.dmm import kernels
+    with torch.no_grad():
+        tab1, tab2 = enc_apg_mu.label_tables(x.to(DEV))
+        nss = kernels.nss_pool_onehot(tab1, tab2, z.to(DEV), dec.prior_mu_mu, dec.prior_mu_sigma)
+        q_mu, q_sigma = enc_apg_mu.params(x.to(DEV), z.to(DEV), None, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+    _close(nss, nss_ref, 2e-5 * nss_ref.abs() + 2e-6, "pooled nss")
+    _close(q_mu, q_mu_ref, 2e-5 * q_mu_ref.abs() + 2e-6, "q_mu")
+    _close(q_sigma, q_sigma_ref, 2e-5 * q_sigma_ref.abs() + 1e-7, "q_sigma")
+    enc_apg_mu.fused = False                                   # the PyTorch per-particle path agrees too
+    try:
+        with torch.no_grad():
+            q_mu2, _ = enc_apg_mu.params(x.to(DEV), z.to(DEV), None, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+    finally:
+        type(enc_apg_mu).fused = True
+        del enc_apg_mu.fused
+    _close(q_mu2, q_mu_ref, 2e-5 * q_mu_ref.abs() + 2e-6, "q_mu (unfused)")
+
+
+@pytest.mark.parametrize("S,B,N,K,D,H", [(5, 3, 200, 4, 2, 32), (19, 2, 37, 3, 2, 16), (9, 1, 65, 4, 3, 33), (2, 2, 5, 5, 2, 8)])
+def test_N1_enc_apg_local_fused_vs_oracle(S, B, N, K, D, H):
+    from apgs_b200.dmm import kernels
+    P, (_, enc_local, _, _) = _mods(K, D, H, seed=S + N + 1)
+    p = P["enc_apg_local"]
+    x = torch.randn(B, N, D) * 2
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    mu = torch.randn(S, B, K, D) * 3
+    one_hot = lambda: torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    z_f, z_old = one_hot(), one_hot()
+    q_ref = od.enc_local_probs(p, xs, mu, K)
+    c1_ref, c0_ref = od.enc_local_cons(p, xs, mu, z_f)
+    c1b_ref, c0b_ref = od.enc_local_cons(p, xs, mu, z_old)
+    # teacher-forced: the given assignment, concentrations for it and for z_old
+    q, z, c1, c0, c1b, c0b = kernels.local_encoder_fused(x.to(DEV), mu.to(DEV), enc_local, z_forced=z_f.to(DEV), z_old=z_old.to(DEV))
+    assert torch.equal(z.cpu(), z_f)
+    _close(q, q_ref, 2e-5 * q_ref + 1e-7, "q_probs")
+    for a, b, w in ((c1, c1_ref, "con1"), (c0, c0_ref, "con0"), (c1b, c1b_ref, "con1_old"), (c0b, c0b_ref, "con0_old")):
+        assert tuple(a.shape) == (S, B, N, 1)
+        _close(a, b, 2e-5 * b.abs(), w)
+    # sampling: inverse CDF of the oracle's probabilities at the supplied uniforms
+    u = torch.rand(S, B, N)
+    q2, z2, c1s, c0s, n1, n0 = kernels.local_encoder_fused(x.to(DEV), mu.to(DEV), enc_local, uniforms=u.to(DEV))
+    assert n1 is None and n0 is None
+    z2 = z2.cpu()
+    assert bool(((z2 == 0) | (z2 == 1)).all()) and bool((z2.sum(-1) == 1).all())
+    cdf = torch.cumsum(q_ref, -1)
+    lab_ref = (u.unsqueeze(-1) * cdf[..., -1:] >= cdf[..., :-1]).sum(-1)
+    bad = z2.argmax(-1) != lab_ref
+    assert float(bad.float().mean()) <= 2e-3
+    gap = (u.unsqueeze(-1) * cdf[..., -1:] - cdf[..., :-1]).abs().min(-1).values
+    assert bool((gap[bad] < 1e-5).all())
+    c1s_ref, c0s_ref = od.enc_local_cons(p, xs, mu, z2)            # concentrations belong to the DRAWN assignment
+    _close(c1s, c1s_ref, 2e-5 * c1s_ref.abs(), "con1 at the draw")
+    _close(c0s, c0s_ref, 2e-5 * c0s_ref.abs(), "con0 at the draw")
+
+
+def test_N1_local_encoder_saturating_inputs():
+    """|x - mu| far beyond the tanh saturation point: finite outputs that still match the oracle."""
+    from apgs_b200.dmm import kernels
+    S, B, N, K, D, H = 4, 2, 50, 4, 2, 32
+    P, (_, enc_local, _, _) = _mods(K, D, H, seed=7)
+    p = P["enc_apg_local"]
+    x = torch.randn(B, N, D) * 300
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    mu = torch.randn(S, B, K, D) * 300
+    z_f = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    q, z, c1, c0, _, _ = kernels.local_encoder_fused(x.to(DEV), mu.to(DEV), enc_local, z_forced=z_f.to(DEV))
+    c1_ref, c0_ref = od.enc_local_cons(p, xs, mu, z_f)
+    assert bool(torch.isfinite(q).all()) and bool(torch.isfinite(c1).all())
+    _close(c1, c1_ref, 3e-5 * c1_ref.abs(), "con1")
+    _close(c0, c0_ref, 3e-5 * c0_ref.abs(), "con0")
+    q_ref = od.enc_local_probs(p, xs, mu, K)
+    _close(q, q_ref, 1e-4 * q_ref + 1e-6, "q_probs")          # logits of O(100): fp32 rounding of the split first layer
+
+
+@pytest.mark.parametrize("shape,D,H", [((7, 3, 200, 1), 2, 32), ((1000,), 2, 16), ((3, 5, 1), 3, 40)])
+def test_N1_decoder_hidden2_vs_oracle(shape, D, H):
+    from apgs_b200.dmm import kernels
+    P, (_, _, _, dec) = _mods(4, D, H, seed=H)
+    beta = torch.rand(*shape)
+    ref = od.dec_hidden2(P["dec"], beta if shape[-1] == 1 else beta.unsqueeze(-1))
+    out = kernels.decoder_hidden2(beta.to(DEV), dec.recon_mu)
+    assert tuple(out.shape) == tuple(ref.shape)
+    _close(out, ref, 2e-5 * ref.abs() + 2e-6, "hidden2")
+    assert float(((out ** 2).sum(-1) - 1).abs().max()) < 1e-5
+
+
+def test_N1_dmm_golden_through_fused_encoders(golden):
+    g = golden("dmm")
+    S, B, N, K, D, sweeps = [int(v) for v in g["dims"]]
+    P = _params(g)
+    _, enc_apg_local, _, _ = _models(P, K, D)
+    x = _t(g, "x")
+    q, z, c1, c0, c1b, c0b = enc_apg_local.sample_fused(x.to(DEV), _t(g, "lo_mu").to(DEV), z_forced=_t(g, "lo_z").to(DEV),
+                                                        z_old=_t(g, "lo_z_old").to(DEV))
+    np.testing.assert_allclose(q.cpu().numpy(), g["lo_q_probs"], rtol=2e-5, atol=1e-7)
+    for a, k in ((c1, "lo_con1"), (c0, "lo_con0"), (c1b, "lo_con1_old"), (c0b, "lo_con0_old")):
+        np.testing.assert_allclose(a.cpu().numpy(), g[k], rtol=2e-5)
+
+
 def test_dmm_sweep_statistics_match_oracle():
     """BASELINE.json configs[2] structure (K=4 rings, N=200) at reduced S,B: end to end, statistical (RNG differs)."""
     from apgs_b200.dmm import objectives as O
