@@ -26,6 +26,17 @@ __device__ __forceinline__ float beta_lp(float v, float c1, float c0) {
     const float s = __fadd_rn(a, b);
     return __fsub_rn(__fadd_rn(s, lgammaf(__fadd_rn(c1, c0))), __fadd_rn(lgammaf(c1), lgammaf(c0)));
 }
+// the same with the two logs supplied (they are shared by the proposal and the prior term of a point) and the
+// normaliser through the Stirling lgamma of gmm_common.cuh (~1e-6 absolute; the sums these enter are O(1..100))
+__device__ __forceinline__ float beta_norm(float c1, float c0) {
+    return __fsub_rn(lgamma_pos(__fadd_rn(c1, c0)), __fadd_rn(lgamma_pos(c1), lgamma_pos(c0)));
+}
+__device__ __forceinline__ float beta_lp_logs(float c1, float c0, float lv, float l1v, float norm) {
+    const float e1 = __fsub_rn(c1, 1.f), e0 = __fsub_rn(c0, 1.f);
+    const float a = e1 == 0.f ? 0.f : __fmul_rn(e1, lv);
+    const float b = e0 == 0.f ? 0.f : __fmul_rn(e0, l1v);
+    return __fadd_rn(__fadd_rn(a, b), norm);
+}
 __device__ __forceinline__ float cat_lp(float p_l, float sum_p) {     // quirk Q4: eps-clamped categorical
     return logf(fminf(fmaxf(__fdiv_rn(p_l, sum_p), FLT_EPS_F), 1.f - FLT_EPS_F));
 }
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_dmm_step(DmmArgs a) {
         for (int k = 0; k < K; ++k) logpi[k] = cat_lp(__ldg(a.prior_pi + k), spi);
     }
     const float pc1 = local ? __ldg(a.prior_con1) : 1.f, pc0 = local ? __ldg(a.prior_con0) : 1.f;
+    const float pnorm = local ? __fsub_rn(lgammaf(__fadd_rn(pc1, pc0)), __fadd_rn(lgammaf(pc1), lgammaf(pc0))) : 0.f;
     const float* xb = a.x + (size_t)(r % a.B) * N * D;
     KahanF A_llf, A_llb, A_lqf, A_lqb, A_lpf, A_lpb, A_loc, A_lqz, A_lqbeta, A_lpz, A_lpbeta;
     for (int n = lane; n < N; n += 32) {
@@ -152,8 +164,10 @@ __global__ void __launch_bounds__(kWarps * 32) k_dmm_step(DmmArgs a) {
             for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, __ldg(a.q_probs + pn * K + k));
             const float bf = __ldg(a.beta + pn);
             const float lqz = cat_lp(__ldg(a.q_probs + pn * K + lf), sq);
-            const float lqbeta = beta_lp(bf, __ldg(a.con1 + pn), __ldg(a.con0 + pn));
-            const float lpz = logpi[lf], lpbeta = beta_lp(bf, pc1, pc0);
+            const float lvf = logf(bf), l1vf = logf(__fsub_rn(1.f, bf));
+            const float c1f = __ldg(a.con1 + pn), c0f = __ldg(a.con0 + pn);
+            const float lqbeta = beta_lp_logs(c1f, c0f, lvf, l1vf, beta_norm(c1f, c0f));
+            const float lpz = logpi[lf], lpbeta = beta_lp_logs(pc1, pc0, lvf, l1vf, pnorm);
             const float lqf = __fadd_rn(lqz, lqbeta);                                  // objectives.py:162
             const float lpf = __fadd_rn(__fadd_rn(llf, lpz), lpbeta);                  // :164
             A_lqf.add(lqf); A_lpf.add(lpf);
@@ -162,9 +176,11 @@ __global__ void __launch_bounds__(kWarps * 32) k_dmm_step(DmmArgs a) {
             if (a.ll_local) a.ll_local[pn] = llf;
             if (mode == 1) {
                 const float bb = __ldg(a.beta_old + pn);
+                const float lvb = logf(bb), l1vb = logf(__fsub_rn(1.f, bb));
+                const float c1b = __ldg(a.con1_old + pn), c0b = __ldg(a.con0_old + pn);
                 const float lqb = __fadd_rn(cat_lp(__ldg(a.q_probs + pn * K + lb), sq),
-                                            beta_lp(bb, __ldg(a.con1_old + pn), __ldg(a.con0_old + pn)));
-                const float lpb = __fadd_rn(__fadd_rn(llb, logpi[lb]), beta_lp(bb, pc1, pc0));
+                                            beta_lp_logs(c1b, c0b, lvb, l1vb, beta_norm(c1b, c0b)));
+                const float lpb = __fadd_rn(__fadd_rn(llb, logpi[lb]), beta_lp_logs(pc1, pc0, lvb, l1vb, pnorm));
                 A_lqb.add(lqb); A_lpb.add(lpb);
                 const float loc = __fsub_rn(__fsub_rn(lpf, lqf), __fsub_rn(lpb, lqb));  // :165,171-172
                 A_loc.add(loc);

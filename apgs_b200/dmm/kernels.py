@@ -165,7 +165,10 @@ def local_encoder_fused(x, mu, enc, uniforms=None, z_forced=None, z_old=None):
                 raise ValueError("%s has shape %s, expected %s" % (name, tuple(t.shape), shp))
     q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
     z = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
-    con = [torch.empty(S, B, N, 1, dtype=torch.float32, device=dev) for _ in range(4 if z_old is not None else 2)]
+    # con1 / con0 are the two halves of one buffer so that beta_sample() can draw both Gammas in one launch
+    cbuf = torch.empty(2, S, B, N, 1, dtype=torch.float32, device=dev)
+    con = [cbuf[0], cbuf[1]] + ([torch.empty(S, B, N, 1, dtype=torch.float32, device=dev) for _ in range(2)]
+                                if z_old is not None else [])
     co = con + [None, None] if z_old is None else con
     nbytes = 4 * S * B * (N * (2 * K + 1 + len(con) + (K if z_old is not None else 0)) + K * D)
     with torch.cuda.device(dev), _call("dmm_local_encoder_fused", 1, nbytes):
@@ -191,3 +194,19 @@ def decoder_hidden2(beta, recon_mu):
         check(lib.apgs_dmm_decoder_hidden2_f32(ptr(beta), C.byref(net), H, D, M, ptr(out), _stream()),
               "apgs_dmm_decoder_hidden2_f32")
     return out
+
+
+def beta_sample(con1, con0):
+    """Beta(con1, con0).sample() as torch.distributions draws it (Dirichlet on [con1, con0]: two standard Gammas,
+    normalise, clamp to [tiny, 1 - eps]) without the stack / cat / select copies: when con1 and con0 are adjacent
+    halves of one buffer (local_encoder_fused) both Gammas come from ONE launch."""
+    n = con1.numel()
+    if (con1.is_contiguous() and con0.is_contiguous() and con1.dtype == con0.dtype and con1.shape == con0.shape
+            and con1.untyped_storage().data_ptr() == con0.untyped_storage().data_ptr()
+            and con0.storage_offset() == con1.storage_offset() + n):
+        both = con1.as_strided((2,) + tuple(con1.shape), (n,) + tuple(con1.stride()))
+    else:
+        both = torch.stack((con1, con0), 0)
+    g = torch._standard_gamma(both)
+    fi = torch.finfo(g.dtype)
+    return (g[0] / (g[0] + g[1])).clamp_(fi.tiny, 1.0 - fi.eps)

@@ -34,13 +34,16 @@ def apg_objective(models, x, K, result_flags, num_sweeps, resampler):
     (enc_rws_mu, enc_apg_local, enc_apg_mu, dec) = models
     if x.dim() == 3:
         x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)
-    log_w, mu, z, beta, trace = oneshot(enc_rws_mu, enc_apg_local, dec, x, K, trace, result_flags)
-    mu, z, beta = resample_variables(resampler, mu, z, beta, log_weights=log_w)
+    # the decoder output h2 is a function of beta alone, so it travels with beta through the resampling steps
+    # (one more 8-byte-per-point latent in the same gather launch) instead of being re-evaluated from the gathered
+    # beta: one decoder evaluation per sweep instead of three
+    log_w, mu, z, beta, h2, trace = _oneshot(enc_rws_mu, enc_apg_local, dec, x, K, trace, result_flags)
+    mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w)
     for m in range(num_sweeps - 1):
-        log_w_mu, mu, trace = apg_update_mu(enc_apg_mu, dec, x, z, beta, mu, K, trace, result_flags)
-        mu, z, beta = resample_variables(resampler, mu, z, beta, log_weights=log_w_mu)
-        log_w_z, z, beta, trace = apg_update_local(enc_apg_local, dec, x, mu, z, beta, K, trace, result_flags)
-        mu, z, beta = resample_variables(resampler, mu, z, beta, log_weights=log_w_z)
+        log_w_mu, mu, trace = apg_update_mu(enc_apg_mu, dec, x, z, beta, mu, K, trace, result_flags, h2=h2)
+        mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w_mu)
+        log_w_z, z, beta, h2, trace = _update_local(enc_apg_local, dec, x, mu, z, beta, K, trace, result_flags, h2_old=h2)
+        mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w_z)
     if result_flags['loss_required']:
         trace['loss_phi'] = torch.cat(trace['loss_phi'], 0)
         trace['loss_theta'] = torch.cat(trace['loss_theta'], 0)
@@ -59,7 +62,7 @@ def _sample_local(enc_local, x, mu, K, z_old=None):
     """q_probs, z, con1, con0, beta (+ the concentrations at z_old for the backward kernel when z_old is given)."""
     if enc_local.can_fuse():
         q_probs, z, con1, con0, con1_b, con0_b = enc_local.sample_fused(x, mu, z_old=z_old)
-        beta = Beta(con1, con0, validate_args=False).sample()
+        beta = kernels.beta_sample(con1, con0)
         return (q_probs, z, con1, con0, beta) if z_old is None else (q_probs, z, con1, con0, beta, con1_b, con0_b)
     if z_old is not None:
         out = _sample_local(enc_local, x, mu, K)
@@ -78,6 +81,12 @@ def _E_recon(dec, mu, z, h2):
 
 def oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
     """One-shot predicts mu, z and beta like a normal RWS (objectives.py:80-114)."""
+    log_w, mu, z, beta, _, trace = _oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags)
+    return log_w, mu, z, beta, trace
+
+
+def _oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
+    """oneshot that also returns the decoder output h2 of the new beta."""
     q_mu, q_sigma = enc_rws_mu.params(x, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
     mu = normal_sample(q_mu, q_sigma)
     q_probs, z, con1, con0, beta = _sample_local(enc_rws_local, x, mu, K)
@@ -88,14 +97,16 @@ def oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
         trace['E_mu'].append(q_mu.mean(0).unsqueeze(0))
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
         trace['E_recon'].append(_E_recon(dec, mu, z, h2))
-    return w.log_w, mu, z, beta, trace
+    return w.log_w, mu, z, beta, h2, trace
 
 
-def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags):
-    """Given local variables {z, beta}, update the centres mu (objectives.py:116-151)."""
+def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags, h2=None):
+    """Given local variables {z, beta}, update the centres mu (objectives.py:116-151).  h2: the decoder output of
+    beta when the caller already holds it."""
     q_mu, q_sigma = enc_apg_mu.params(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
     mu = normal_sample(q_mu, q_sigma)
-    h2 = dec.hidden2(beta)                 # the decoder sees beta only: one evaluation serves f and b
+    if h2 is None:
+        h2 = dec.hidden2(beta)             # the decoder sees beta only: one evaluation serves f and b
     w = kernels.logw_mu(x, z, h2, q_mu, q_sigma, mu, mu_old, dec)
     _book(trace, result_flags, w.log_w, w.log_q_f, w.ll_f, w.density)
     if result_flags['mode_required']:
@@ -105,8 +116,16 @@ def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags):
 
 def apg_update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_flags):
     """Given mu, update the local variables {z, beta} (objectives.py:153-188)."""
+    log_w, z, beta, _, trace = _update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_flags)
+    return log_w, z, beta, trace
+
+
+def _update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_flags, h2_old=None):
+    """apg_update_local that takes the decoder output of beta_old when the caller holds it and returns the new one."""
     q_probs, z, con1, con0, beta, con1_b, con0_b = _sample_local(enc_apg_local, x, mu, K, z_old=z_old)
-    h2, h2_old = dec.hidden2(beta), dec.hidden2(beta_old)
+    h2 = dec.hidden2(beta)
+    if h2_old is None:
+        h2_old = dec.hidden2(beta_old)
     need_local = bool(result_flags['loss_required'])
     w = kernels.logw_local(x, mu, q_probs, z, beta, con1, con0, h2, z_old, beta_old, con1_b, con0_b, h2_old, dec,
                            local=need_local)
@@ -119,7 +138,7 @@ def apg_update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, resul
         trace['E_recon'].append(_E_recon(dec, mu, z, h2))
     if result_flags['density_required']:
         trace['density'][-1] = trace['density'][-1] + w.density.unsqueeze(0)
-    return w.log_w, z, beta, trace
+    return w.log_w, z, beta, h2, trace
 
 
 def resample_variables(resampler, mu, z, beta, log_weights):

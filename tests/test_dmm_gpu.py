@@ -291,3 +291,17 @@ def test_dmm_full_size_runs():
     with torch.no_grad():
         tr = O.apg_objective(models, x, K, flags, 3, Resampler("systematic", S, True, DEV))
     assert tuple(tr["ess"].shape) == (3, B) and bool(torch.isfinite(tr["density"]).all())
+
+
+def test_beta_sample_matches_torch_distribution():
+    """beta_sample draws Beta(con1, con0) like torch.distributions (moments + support), from adjacent or separate buffers."""
+    from apgs_b200.dmm import kernels
+    torch.manual_seed(0)
+    buf = torch.empty(2, 400000, 1, device=DEV)
+    buf[0], buf[1] = 2.5, 0.7
+    for c1, c0 in ((buf[0], buf[1]), (buf[0].clone(), buf[1].clone())):
+        b = kernels.beta_sample(c1, c0)
+        assert tuple(b.shape) == tuple(c1.shape) and float(b.min()) > 0 and float(b.max()) < 1
+        m, v = 2.5 / 3.2, 2.5 * 0.7 / (3.2 ** 2 * 4.2)
+        assert abs(float(b.mean()) - m) < 5 * (v / b.numel()) ** 0.5
+        assert abs(float(b.var()) - v) < 0.02 * v
