@@ -108,3 +108,33 @@ def logw_what(q_mu, q_std, z_new, z_old, ll_f, ll_b=None, extra_log_p=None, extr
                                             ptr(eq), S, B, K, Z, T, *[ptr(v) for v in outs], _stream()),
               "apgs_bmnist_logw_what_f32")
     return tuple(outs)
+
+
+def _dense_images(t, name):
+    """(S,B,H,W) float32 CUDA tensor with dense H x W images and arbitrary non-negative (possibly zero) s / b strides."""
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise _lib.ApgsError("%s must be a float32 CUDA tensor (no CPU fallback)" % name)
+    if t.dim() != 4:
+        raise ValueError("%s must be (S,B,H,W), got %s" % (name, tuple(t.shape)))
+    if t.stride(-1) != 1 or t.stride(-2) != t.shape[-1] or t.stride(0) < 0 or t.stride(1) < 0:
+        t = t.contiguous()
+    return t.detach()
+
+
+def template_match(frame, template, softmax=True):
+    """N3: per-(s,b) cross-correlation of frame (S,B,FP,FP) with template (S,B,DP,DP) -> (S,B,CP*CP), CP = FP-DP+1,
+    followed by the softmax over the scores (apgs/bmnist/objectives.py:72-74).  Strided views (frames[:, :, t],
+    template[:, :, k], S-expanded frames) are read in place."""
+    lib = _lib.load()
+    f, t = _dense_images(frame, "frame"), _dense_images(template, "template")
+    S, B, FP, _ = f.shape
+    DP = t.shape[-1]
+    if tuple(t.shape) != (S, B, DP, DP) or f.shape[-2] != FP or DP > FP:
+        raise ValueError("frame %s / template %s shapes do not match" % (tuple(f.shape), tuple(t.shape)))
+    CP = FP - DP + 1
+    out = torch.empty(S, B, CP * CP, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device), _call("bmnist_template_match", 1, 4 * S * B * (FP * FP + DP * DP + CP * CP)):
+        check(lib.apgs_bmnist_template_match_f32(ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),
+                                                 S, B, FP, DP, 1 if softmax else 0, ptr(out), _stream()),
+              "apgs_bmnist_template_match_f32")
+    return out

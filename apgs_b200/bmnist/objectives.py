@@ -2,7 +2,7 @@
 (resample_variables :5-9, apg_objective :11-58, propose_one_movement :60-107, oneshot :109-165,
 apg_where :167-225, apg_what :228-257).
 
-The template-matching conv2d + softmax and the MLPs stay in PyTorch; crop, paste,
+The MLPs stay in PyTorch; the template matching (grouped conv2d + softmax), crop, paste,
 paste+sum+clamp+log-likelihood, every Normal log-density, the step weights, softmax/ESS and the per-frame
 resampling run in the sm_100a kernels.  Reference behaviours that change numbers are kept:
   * the one-shot counts the t = 0 terms of log p / log q(z_where) twice (objectives.py:124-139);
@@ -12,7 +12,6 @@ resampling run in the sm_100a kernels.  Reference behaviours that change numbers
 Forward / evaluation path only (gradients: SURVEY.md row N2).
 """
 import torch
-import torch.nn.functional as F
 from torch.distributions.normal import Normal
 
 from .. import ops
@@ -67,9 +66,7 @@ def _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t
     frame_left = frame
     for k in range(K):
         template_k = template[:, :, k, :, :]
-        conved_k = F.conv2d(frame_left.reshape(S * B, FP, FP).unsqueeze(0), template_k.reshape(S * B, DP, DP).unsqueeze(1), groups=int(S * B))
-        CP = conved_k.shape[-1]
-        conved_k = F.softmax(conved_k.squeeze(0).view(S, B, CP * CP), -1)
+        conved_k = kernels.template_match(frame_left, template_k)          # conv2d(groups=S*B) + softmax (:72-74)
         q_mean, q_std = enc_coor.params(conved_k)
         z_where_k = normal_sample(q_mean, q_std)
         zs.append(z_where_k.unsqueeze(2)); means.append(q_mean.unsqueeze(2)); stds.append(q_std.unsqueeze(2))

@@ -1,0 +1,161 @@
+// Bouncing-MNIST template matching for sm_100a:
+//   conved = conv2d(frame_left (1, S*B, FP, FP), template_k (S*B, 1, DP, DP), groups = S*B)   apgs/bmnist/objectives.py:72-73
+//   conved = softmax(conved.view(S, B, CP*CP), -1),  CP = FP - DP + 1                          :74
+// i.e. for every particle-instance pair ONE image is cross-correlated with ITS OWN template -- M = S*B independent
+// 2-D correlations, 3.7 MFMA each at 96/28; no operand is shared between problems, so this is FMA-pipe work (a GEMM view
+// would have N = 1).  PyTorch's depthwise kernel reaches ~2.5 TFMA/s on it and was 74 % of the bmnist sweep.
+//
+// One CTA per image.  The image sits in shared memory with a padded row stride (FP + 1: lanes of a warp own different
+// rows of the same column segment, so their window loads hit 32 different banks), the template is read as broadcast
+// LDS.128.  A thread owns SEG = 23 consecutive output columns of one output row (69 = 3 x 23): for each template row u
+// it loads the 50-element image row window and the 28 template values into registers once and issues 23 x 28 = 644
+// FMAs on them -- 12 FMAs per shared-memory load, 23 independent accumulation chains.  The softmax over the 4761
+// scores of the image is fused behind it (block max / sum), so the raw score map never reaches HBM.
+#include "common.cuh"
+
+namespace apgs {
+
+struct MatchArgs {
+    const float* frame;        // image (s,b) at frame + s*fs + b*fb, FP*FP dense row-major
+    long long fs, fb;
+    const float* tmpl;         // template (s,b) at tmpl + s*ts + b*tb, DP*DP dense
+    long long ts, tb;
+    float* out;                // (S*B, CP*CP)
+    int S, B, FP, DP, softmax;
+};
+
+__device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();                               // s_red may still be read from the previous reduction
+    if (lane == 0) s_red[w] = v;
+    __syncthreads();
+    float r = s_red[0];
+    for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, s_red[i]) : r + s_red[i];
+    return r;
+}
+
+template <int FP, int DP, int SEG>
+__global__ void __launch_bounds__(224, 2) k_template_match(MatchArgs a) {
+    constexpr int CP = FP - DP + 1, NSEG = CP / SEG, FS = FP + 1, WIN = SEG + DP - 1;
+    static_assert(CP % SEG == 0 && DP % 4 == 0, "tile shape");
+    static_assert(CP * NSEG <= 224, "one thread per (output row, column segment)");
+    extern __shared__ __align__(16) float s_m[];
+    float* s_t = s_m;                              // DP*DP (16-byte aligned rows)
+    float* s_f = s_m + DP * DP;                    // FP x (FP+1)
+    __shared__ float s_red[8];
+    const int img = blockIdx.x, s = img / a.B, b = img % a.B;
+    const float* f = a.frame + s * a.fs + b * a.fb;
+    const float* t = a.tmpl + s * a.ts + b * a.tb;
+    for (int i = threadIdx.x; i < FP * FP; i += blockDim.x) s_f[(i / FP) * FS + (i % FP)] = __ldg(f + i);
+    for (int i = threadIdx.x; i < DP * DP; i += blockDim.x) s_t[i] = __ldg(t + i);
+    __syncthreads();
+    const bool live = threadIdx.x < CP * NSEG;
+    const int i0 = live ? threadIdx.x % CP : 0, seg = live ? threadIdx.x / CP : 0;
+    float acc[SEG];
+#pragma unroll
+    for (int c = 0; c < SEG; ++c) acc[c] = 0.f;
+    if (live) {
+#pragma unroll 1
+        for (int u = 0; u < DP; ++u) {
+            const float* row = s_f + (i0 + u) * FS + seg * SEG;
+            float w[WIN], tr[DP];
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) w[q] = row[q];
+#pragma unroll
+            for (int q = 0; q < DP / 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(s_t + u * DP + q * 4);
+                tr[q * 4] = v.x; tr[q * 4 + 1] = v.y; tr[q * 4 + 2] = v.z; tr[q * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int v = 0; v < DP; ++v)
+#pragma unroll
+                for (int c = 0; c < SEG; ++c) acc[c] = fmaf(tr[v], w[v + c], acc[c]);
+        }
+    }
+    float* o = a.out + (size_t)img * CP * CP + i0 * CP + seg * SEG;
+    if (a.softmax) {
+        float mx = -INFINITY;
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < SEG; ++c) mx = fmaxf(mx, acc[c]);
+        }
+        mx = block_reduce(mx, s_red, true);
+        float se = 0.f;
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < SEG; ++c) { acc[c] = expf(acc[c] - mx); se += acc[c]; }
+        }
+        se = block_reduce(se, s_red, false);
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < SEG; ++c) o[c] = __fdiv_rn(acc[c], se);
+        }
+    } else if (live) {
+#pragma unroll
+        for (int c = 0; c < SEG; ++c) o[c] = acc[c];
+    }
+}
+
+// any other (FP, DP): one thread per score, operands in shared memory.  Correct, not tuned.
+__global__ void __launch_bounds__(256) k_template_match_generic(MatchArgs a) {
+    extern __shared__ __align__(16) float s_m[];
+    __shared__ float s_red[8];
+    const int FP = a.FP, DP = a.DP, CP = FP - DP + 1;
+    float* s_t = s_m;
+    float* s_f = s_m + DP * DP;
+    const int img = blockIdx.x, s = img / a.B, b = img % a.B;
+    const float* f = a.frame + s * a.fs + b * a.fb;
+    const float* t = a.tmpl + s * a.ts + b * a.tb;
+    for (int i = threadIdx.x; i < FP * FP; i += blockDim.x) s_f[i] = __ldg(f + i);
+    for (int i = threadIdx.x; i < DP * DP; i += blockDim.x) s_t[i] = __ldg(t + i);
+    __syncthreads();
+    float* o = a.out + (size_t)img * CP * CP;
+    float mx = -INFINITY;
+    for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
+        const int i = e / CP, j = e % CP;
+        float acc = 0.f;
+        for (int u = 0; u < DP; ++u)
+            for (int v = 0; v < DP; ++v) acc = fmaf(s_t[u * DP + v], s_f[(i + u) * FP + j + v], acc);
+        o[e] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    if (!a.softmax) return;
+    mx = block_reduce(mx, s_red, true);
+    float se = 0.f;
+    for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) { const float v = expf(o[e] - mx); o[e] = v; se += v; }
+    se = block_reduce(se, s_red, false);
+    for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) o[e] = __fdiv_rn(o[e], se);
+}
+
+}  // namespace apgs
+
+using namespace apgs;
+
+extern "C" int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                              const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                              int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax, float* out,
+                                              void* stream) {
+    if (S <= 0 || B <= 0 || FP <= 0 || DP <= 0 || DP > FP || S * B > 0x7fffffffLL)
+        return fail(APGS_E_SHAPE, "bmnist_template_match: bad sizes S=%lld B=%lld FP=%lld DP=%lld", (long long)S,
+                    (long long)B, (long long)FP, (long long)DP);
+    if (!frame || !tmpl || !out) return fail(APGS_E_BADARG, "bmnist_template_match: NULL pointer");
+    if (frame_stride_s < 0 || frame_stride_b < 0 || tmpl_stride_s < 0 || tmpl_stride_b < 0)
+        return fail(APGS_E_BADARG, "bmnist_template_match: negative stride");
+    MatchArgs a = {frame, (long long)frame_stride_s, (long long)frame_stride_b, tmpl, (long long)tmpl_stride_s,
+                   (long long)tmpl_stride_b, out, (int)S, (int)B, (int)FP, (int)DP, softmax};
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned int grid = (unsigned int)(S * B);
+    if (FP == 96 && DP == 28) {
+        const size_t smem = (size_t)(28 * 28 + 96 * 97) * 4;
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_template_match<96, 28, 23>), smem), "smem attr");
+        k_template_match<96, 28, 23><<<grid, 224, smem, st>>>(a);
+    } else {
+        const size_t smem = (size_t)(DP * DP + FP * FP) * 4;
+        if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "bmnist_template_match: FP=%lld too large", (long long)FP);
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_template_match_generic), smem), "smem attr");
+        k_template_match_generic<<<grid, 256, smem, st>>>(a);
+    }
+    APGS_LAUNCH_OK("k_template_match launch");
+    return 0;
+}

@@ -360,6 +360,16 @@ APGS_API int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
 APGS_API int apgs_dmm_decoder_hidden2_f32(const float* beta, const apgs_dmm_mlp_t* net, int64_t H, int64_t D,
                                  int64_t M, float* hidden2, void* stream);
 
+/* N3  bmnist template matching (apgs/bmnist/objectives.py:72-74):
+ *     conv2d(frame_left (1, S*B, FP, FP), template_k (S*B, 1, DP, DP), groups = S*B) -> (S, B, CP*CP), CP = FP-DP+1,
+ *     i.e. image (s,b) cross-correlated with ITS OWN template, optionally followed by the softmax over the CP*CP scores.
+ *   image (s,b) at frame + s*frame_stride_s + b*frame_stride_b (FP*FP dense; stride 0 allowed for S-shared frames),
+ *   template (s,b) at tmpl + s*tmpl_stride_s + b*tmpl_stride_b (DP*DP dense), strides in elements.              */
+APGS_API int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                   const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                   int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax,
+                                   float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,3 +151,39 @@ def test_bmnist_teacher_forced_step_vs_oracle(golden):
         ll_b, _ = AT.reconstruct_ll(dec_digit.templates(z_old.to(DEV)), z_where.to(DEV), frames.to(DEV))
         np.testing.assert_allclose(ll_f.cpu().numpy(), g["wh_ll_f"], rtol=2e-5)
         np.testing.assert_allclose(ll_b.cpu().numpy(), g["wh_ll_b"], rtol=2e-5)
+
+
+# ------------------------------------------------------------------------------ N3: template matching
+def _match_ref(frame, template, softmax):
+    """the reference's expression (apgs/bmnist/objectives.py:72-74) on CPU."""
+    import torch.nn.functional as F
+    S, B, FP, _ = frame.shape
+    DP = template.shape[-1]
+    c = F.conv2d(frame.reshape(S * B, FP, FP).unsqueeze(0), template.reshape(S * B, DP, DP).unsqueeze(1), groups=S * B)
+    CP = c.shape[-1]
+    c = c.squeeze(0).view(S, B, CP * CP)
+    return F.softmax(c, -1) if softmax else c
+
+
+@pytest.mark.parametrize("S,B,FP,DP", [(3, 5, 96, 28), (2, 2, 32, 8), (1, 3, 40, 28)])
+def test_N3_template_match_vs_reference_expression(S, B, FP, DP):
+    from apgs_b200.bmnist import kernels
+    torch.manual_seed(FP + S)
+    T, K = 4, 3
+    frames = torch.rand(B, T, FP, FP) * (torch.rand(B, T, FP, FP) > 0.7)
+    frames5 = frames.unsqueeze(0).expand(S, -1, -1, -1, -1)                 # S-shared frames: stride 0 over s
+    tmpl = torch.rand(S, B, K, DP, DP)
+    fd, td = frames.to(DEV).unsqueeze(0).expand(S, -1, -1, -1, -1), tmpl.to(DEV)
+    for t, k in ((0, 0), (3, 2)):
+        ref_raw = _match_ref(frames5[:, :, t].contiguous(), tmpl[:, :, k].contiguous(), False)
+        raw = kernels.template_match(fd[:, :, t], td[:, :, k], softmax=False)       # strided views, read in place
+        mag = _match_ref(frames5[:, :, t].contiguous().abs(), tmpl[:, :, k].contiguous().abs(), False)
+        assert float(((raw.cpu() - ref_raw).abs() - 2e-6 * mag).max()) <= 0
+        ref = _match_ref(frames5[:, :, t].contiguous(), tmpl[:, :, k].contiguous(), True)
+        out = kernels.template_match(fd[:, :, t], td[:, :, k])
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=3e-4, atol=1e-12)
+        np.testing.assert_allclose(out.sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
+    # a residual frame (negative pixels after subtracting a reconstruction) and a dense (S,B,FP,FP) input
+    left = (frames5[:, :, 1] - torch.rand(S, B, FP, FP) * 0.5).contiguous()
+    out = kernels.template_match(left.to(DEV), td[:, :, 1])
+    np.testing.assert_allclose(out.cpu().numpy(), _match_ref(left, tmpl[:, :, 1].contiguous(), True).numpy(), rtol=3e-4, atol=1e-12)
