@@ -21,6 +21,11 @@ def _x_inst(ob):
     return ob[0] if ob.dim() == 4 else ob
 
 
+def needs_grad(*modules):
+    """True when any parameter of the given modules takes part in autograd (training mode)."""
+    return torch.is_grad_enabled() and any(p.requires_grad for m in modules for p in m.parameters())
+
+
 def _split_linear(lin, x, z):
     """Linear(cat(x, z)) = Linear_x(x) (per instance, broadcast over S) + Linear_z(z), without the S-replicated cat."""
     D = x.shape[-1]
@@ -36,6 +41,14 @@ class _EncMu(nn.Module):
 
     def _heads(self, nss1, nss2, priors):
         nss_prior = kernels.nss_pool(nss1, nss2, priors[0], priors[1])          # D1
+        return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
+
+    def _heads_torch(self, nss1, nss2, priors, EPS=1e-8):
+        """D1 + heads with PyTorch ops only (autograd graph for training; models.py:134-139)."""
+        num = torch.einsum('sbnj,sbnk->sbkj', nss1, nss2)
+        nss = num / (nss2.sum(2).unsqueeze(-1) + EPS)
+        S, B, K, _ = nss.shape
+        nss_prior = torch.cat((nss, priors[0].expand(S, B, K, -1), priors[1].expand(S, B, K, -1)), -1)
         return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
 
     @staticmethod
@@ -60,6 +73,13 @@ class Enc_rws_mu(_EncMu):
         q_mu, q_sigma = self._heads(self.nss1(x).unsqueeze(0), self.nss2(x).unsqueeze(0), priors)   # data only: once per instance
         return q_mu.expand(S, -1, -1, -1).contiguous(), q_sigma.expand(S, -1, -1, -1).contiguous()
 
+    def params_torch(self, ob, K, priors, S=None):
+        """same parameters through PyTorch ops only (autograd graph for training)."""
+        x = _x_inst(ob)
+        S = ob.shape[0] if ob.dim() == 4 else S
+        q_mu, q_sigma = self._heads_torch(self.nss1(x).unsqueeze(0), self.nss2(x).unsqueeze(0), priors)
+        return q_mu.expand(S, -1, -1, -1), q_sigma.expand(S, -1, -1, -1)
+
     def forward(self, ob, K, priors, sampled=True, mu_old=None, EPS=1e-8):
         return self._trace(*self.params(ob, K, priors), sampled, mu_old)
 
@@ -82,13 +102,22 @@ class Enc_apg_mu(_EncMu):
 
     def params(self, ob, z, beta, K, priors):
         x = _x_inst(ob)
-        if self.fused and not any(p.requires_grad for p in self.parameters()):
-            tab1, tab2 = self.label_tables(x)
-            nss_prior = kernels.nss_pool_onehot(tab1, tab2, z, priors[0], priors[1])
-            return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
+        if self.fused:
+            # forward values only (the draws carry no gradient); training rebuilds log q through params_torch()
+            with torch.no_grad():
+                tab1, tab2 = self.label_tables(x)
+                nss_prior = kernels.nss_pool_onehot(tab1, tab2, z, priors[0], priors[1])
+                return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
         h1 = torch.tanh(_split_linear(self.nss1[0], x, z))
         h2 = torch.tanh(_split_linear(self.nss2[0], x, z))
         return self._heads(self.nss1[2](h1), F.softmax(self.nss2[2](h2), -1), priors)
+
+    def params_torch(self, ob, z, beta, K, priors):
+        """same parameters through PyTorch ops only (autograd graph for training)."""
+        x = _x_inst(ob)
+        h1 = torch.tanh(_split_linear(self.nss1[0], x, z))
+        h2 = torch.tanh(_split_linear(self.nss2[0], x, z))
+        return self._heads_torch(self.nss1[2](h1), F.softmax(self.nss2[2](h2), -1), priors)
 
     def forward(self, ob, z, beta, K, priors, sampled=True, mu_old=None, EPS=1e-8):
         return self._trace(*self.params(ob, z, beta, K, priors), sampled, mu_old)
@@ -104,7 +133,7 @@ class Enc_apg_local(nn.Module):
     fused = True          # evaluation path: csrc/dmm_fused.cu
 
     def can_fuse(self):
-        return self.fused and not any(p.requires_grad for p in self.parameters())
+        return self.fused
 
     def sample_fused(self, ob, mu, z_old=None, uniforms=None, z_forced=None):
         """probs + categorical draw + Beta concentrations (for z and, when given, for z_old) in one kernel:
@@ -161,10 +190,22 @@ class Decoder(nn.Module):
 
     def hidden2(self, beta):
         """unit-normalised decoder output (models.py:202-203)."""
-        if self.fused and beta.is_cuda and not any(p.requires_grad for p in self.recon_mu.parameters()):
-            return kernels.decoder_hidden2(beta, self.recon_mu)
+        if self.fused and beta.is_cuda:
+            return kernels.decoder_hidden2(beta, self.recon_mu)      # forward values; the graph: log_likelihood_torch()
+        return self.hidden2_torch(beta)
+
+    def hidden2_torch(self, beta):
         hidden = self.recon_mu(beta * 2 * math.pi)
         return hidden / (hidden ** 2).sum(-1).unsqueeze(-1).sqrt()
+
+    def log_likelihood_torch(self, ob, mu, z, beta):
+        """Normal(hidden2 * radi + mu[z], recon_sigma).log_prob(ob) summed over D -> (S,B,N), PyTorch ops only
+        (autograd graph of the decoder for loss_theta; models.py:202-209)."""
+        x = _x_inst(ob)
+        D = x.shape[-1]
+        mu_expand = torch.gather(mu, -2, z.argmax(-1).unsqueeze(-1).expand(-1, -1, -1, D))
+        recon_mu = self.hidden2_torch(beta) * self.radi + mu_expand
+        return Normal(recon_mu, self.recon_sigma, validate_args=False).log_prob(x.unsqueeze(0)).sum(-1)
 
     def forward(self, ob, mu, z, beta):
         p = Trace()

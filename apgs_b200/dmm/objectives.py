@@ -4,7 +4,13 @@ resample_variables :190-195).
 
 Each block update evaluates its encoder once (the reference re-runs it with identical inputs for the backward
 kernel, and the decoder MLP twice although only mu moves in the mu step); log-densities, likelihood, the N-sums
-and the f - b difference are one kernel (csrc/dmm.cu).  Forward / evaluation path (gradients: SURVEY.md row N2).
+and the f - b difference are one kernel (csrc/dmm.cu).
+Gradients: the kernels are forward-only.  The APG losses are  loss_phi = sum_s w_s.detach() (-log q_s)
+and  loss_theta = sum_s w_s.detach() (-ll_s), so autograd only needs the graphs of the FORWARD proposal log-density and of
+the forward log-likelihood.  When `loss_required` is set and the encoder (decoder) parameters require grad, those two
+terms are rebuilt with PyTorch ops on the kernels' draws and multiplied by the detached kernel weights -- the reference's
+train() works unchanged and gets the reference's gradients, while weights, ESS, densities and resampling still come
+from the kernels.
 """
 import torch
 from torch.distributions.beta import Beta
@@ -14,6 +20,7 @@ from torch.distributions.one_hot_categorical import OneHotCategorical as cat
 from .. import ops
 from ..rng import normal_sample
 from . import kernels
+from .models import needs_grad
 
 
 def _book(trace, result_flags, log_w, log_q, ll, density):
@@ -92,7 +99,17 @@ def _oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
     q_probs, z, con1, con0, beta = _sample_local(enc_rws_local, x, mu, K)
     h2 = dec.hidden2(beta)
     w = kernels.logw_oneshot(x, q_mu, q_sigma, mu, q_probs, z, beta, con1, con0, h2, dec)
-    _book(trace, result_flags, w.log_w, w.log_q_f, w.ll_f, w.density)
+    log_q, ll = w.log_q_f, w.ll_f
+    if result_flags['loss_required']:
+        if needs_grad(enc_rws_mu, enc_rws_local):            # objectives.py:88-91 with a graph
+            q_mu_t, q_sigma_t = enc_rws_mu.params_torch(x, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+            c1_t, c0_t = enc_rws_local.cons(x, mu, z)
+            log_q = (Normal(q_mu_t, q_sigma_t, validate_args=False).log_prob(mu).sum(-1).sum(-1)
+                     + cat(probs=enc_rws_local.probs(x, mu, K), validate_args=False).log_prob(z).sum(-1)
+                     + Beta(c1_t, c0_t, validate_args=False).log_prob(beta).sum(-1).sum(-1))
+        if needs_grad(dec):
+            ll = dec.log_likelihood_torch(x, mu, z, beta).sum(-1)
+    _book(trace, result_flags, w.log_w, log_q, ll, w.density)
     if result_flags['mode_required']:
         trace['E_mu'].append(q_mu.mean(0).unsqueeze(0))
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
@@ -108,7 +125,14 @@ def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags, h
     if h2 is None:
         h2 = dec.hidden2(beta)             # the decoder sees beta only: one evaluation serves f and b
     w = kernels.logw_mu(x, z, h2, q_mu, q_sigma, mu, mu_old, dec)
-    _book(trace, result_flags, w.log_w, w.log_q_f, w.ll_f, w.density)
+    log_q, ll = w.log_q_f, w.ll_f
+    if result_flags['loss_required']:
+        if needs_grad(enc_apg_mu):                           # objectives.py:123 with a graph
+            q_mu_t, q_sigma_t = enc_apg_mu.params_torch(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+            log_q = Normal(q_mu_t, q_sigma_t, validate_args=False).log_prob(mu).sum(-1).sum(-1)
+        if needs_grad(dec):
+            ll = dec.log_likelihood_torch(x, mu, z, beta).sum(-1)
+    _book(trace, result_flags, w.log_w, log_q, ll, w.density)
     if result_flags['mode_required']:
         trace['E_mu'].append(q_mu.mean(0).unsqueeze(0))
     return w.log_w, mu, trace
@@ -131,8 +155,15 @@ def _update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_f
                            local=need_local)
     if result_flags['loss_required']:
         w_local, _ = ops.local_weight_stats(w.log_w_local, want_w=True, want_sum=False)
-        trace['loss_phi'][-1] = trace['loss_phi'][-1] + (w_local * (-w.log_q_local)).sum(0).sum(-1).mean().unsqueeze(0)
-        trace['loss_theta'][-1] = trace['loss_theta'][-1] + (w_local * (-w.ll_local)).sum(0).sum(-1).mean().unsqueeze(0)
+        log_q_local, ll_local = w.log_q_local, w.ll_local
+        if needs_grad(enc_apg_local):                        # objectives.py:162 with a graph
+            c1_t, c0_t = enc_apg_local.cons(x, mu, z)
+            log_q_local = (cat(probs=enc_apg_local.probs(x, mu, K), validate_args=False).log_prob(z)
+                           + Beta(c1_t, c0_t, validate_args=False).log_prob(beta).sum(-1))
+        if needs_grad(dec):
+            ll_local = dec.log_likelihood_torch(x, mu, z, beta)
+        trace['loss_phi'][-1] = trace['loss_phi'][-1] + (w_local * (-log_q_local)).sum(0).sum(-1).mean().unsqueeze(0)
+        trace['loss_theta'][-1] = trace['loss_theta'][-1] + (w_local * (-ll_local)).sum(0).sum(-1).mean().unsqueeze(0)
     if result_flags['mode_required']:
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
         trace['E_recon'].append(_E_recon(dec, mu, z, h2))

@@ -15,7 +15,10 @@ for l in open(dis):
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/', l)
     if m: line_of[int(m.group(1), 16)] = cur
 rr = list(csv.reader(open(src)))
-h = rr[1]; body = rr[2:]
+h = rr[1]; body = []
+for r in rr[2:]:
+    if r and r[0] == 'Kernel Name': break
+    body.append(r)
 ia, ie, iss = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples")
 base = int(body[0][ia], 16)
 agg = collections.defaultdict(lambda: [0, 0, 0])

@@ -305,3 +305,100 @@ def test_beta_sample_matches_torch_distribution():
         m, v = 2.5 / 3.2, 2.5 * 0.7 / (3.2 ** 2 * 4.2)
         assert abs(float(b.mean()) - m) < 5 * (v / b.numel()) ** 0.5
         assert abs(float(b.var()) - v) < 0.02 * v
+
+
+# ------------------------------------------------------------------------------ N2: training mode
+def _train_mods(K=4, D=2, H=32):
+    from apgs_b200.dmm import models as M
+    torch.manual_seed(0)
+    P = od.make_params(K, D, H, 8, H, H)
+    ms, opt = M.init_apg_models(K, D, H, 8, H, H, 0.5, True, DEV, lr=1e-3)
+    for m, key in zip(ms, ("enc_rws_mu", "enc_apg_local", "enc_apg_mu", "dec")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})
+    return P, ms, opt
+
+
+def _grad_close(module, Pg, rtol=3e-3):
+    scale = max(float(v.grad.abs().max()) for v in Pg.values() if v.grad is not None)
+    for name, p in module.named_parameters():
+        ref = Pg[name].grad
+        assert p.grad is not None, name
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref.numpy(), rtol=rtol, atol=1e-4 * scale, err_msg=name)
+
+
+def test_N2_dmm_step_gradients_match_oracle_autograd():
+    """loss_phi / loss_theta .backward() through the drop-in mu and local steps == autograd through the oracle
+    (= the reference's computation) on the same draws."""
+    from apgs_b200.dmm import objectives as O
+    K, D, N, S, B = 4, 2, 50, 7, 5
+    P, (enc_rws_mu, enc_apg_local, enc_apg_mu, dec), _ = _train_mods(K, D)
+    prior = od.make_prior(K, D)
+    torch.manual_seed(1)
+    x = od.simulate(B, N, K, D)
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    beta, mu_old = torch.rand(S, B, N, 1), torch.randn(S, B, K, D) * 2
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    new = lambda: {"loss_phi": [], "loss_theta": [], "ess": [], "E_mu": [], "E_z": [], "E_recon": [], "density": []}
+    leaf = lambda d: {k: v.clone().requires_grad_(True) for k, v in d.items()}
+    # ---- mu step
+    trace = new()
+    log_w, mu, trace = O.apg_update_mu(enc_apg_mu, dec, x.to(DEV), z.to(DEV), beta.to(DEV), mu_old.to(DEV), K, trace, flags)
+    (trace["loss_phi"][0] + trace["loss_theta"][0]).sum().backward()
+    Pm, Pd = leaf(P["enc_apg_mu"]), leaf(P["dec"])
+    q_mu, q_sigma = od.enc_mu_params(Pm, torch.cat((xs, z), -1), prior)
+    lw, lq, _, ll = od.mu_step_weights(prior, Pd, xs, z, od.dec_hidden2(Pd, beta), q_mu, q_sigma, mu.cpu(), mu_old)
+    w = torch.softmax(lw.detach(), 0)
+    ((w * (-lq)).sum(0).mean() + (w * (-ll)).sum(0).mean()).backward()
+    np.testing.assert_allclose(float(trace["loss_phi"][0].detach()), float(((w * (-lq)).sum(0).mean()).detach()), rtol=3e-4)
+    np.testing.assert_allclose(float(trace["loss_theta"][0].detach()), float(((w * (-ll)).sum(0).mean()).detach()), rtol=3e-4)
+    _grad_close(enc_apg_mu, Pm)
+    _grad_close(dec, Pd)
+    # ---- local step
+    for m in (enc_apg_mu, dec):
+        m.zero_grad()
+    trace = new()
+    trace["loss_phi"].append(torch.zeros(1, device=DEV)); trace["loss_theta"].append(torch.zeros(1, device=DEV))
+    trace["density"].append(torch.zeros(1, S, B, device=DEV))
+    log_w, z_new, beta_new, trace = O.apg_update_local(enc_apg_local, dec, x.to(DEV), mu, z.to(DEV), beta.to(DEV), K, trace, flags)
+    (trace["loss_phi"][0] + trace["loss_theta"][0]).sum().backward()
+    Pl, Pd = leaf(P["enc_apg_local"]), leaf(P["dec"])
+    muc, zc, bc = mu.cpu(), z_new.cpu(), beta_new.cpu()
+    q_probs = od.enc_local_probs(Pl, xs, muc, K)
+    c1, c0 = od.enc_local_cons(Pl, xs, muc, zc)
+    c1b, c0b = od.enc_local_cons(Pl, xs, muc, z)
+    lwl, _, lqf, llf, _ = od.local_step_weights(prior, Pd, xs, muc, q_probs, zc, bc, c1, c0, od.dec_hidden2(Pd, bc),
+                                                z, beta, c1b, c0b, od.dec_hidden2(Pd, beta))
+    wl = torch.softmax(lwl.detach(), 0)
+    ref_phi, ref_theta = (wl * (-lqf)).sum(0).sum(-1).mean(), (wl * (-llf)).sum(0).sum(-1).mean()
+    (ref_phi + ref_theta).backward()
+    np.testing.assert_allclose(float(trace["loss_phi"][0].detach()), float((ref_phi).detach()), rtol=3e-4)
+    np.testing.assert_allclose(float(trace["loss_theta"][0].detach()), float((ref_theta).detach()), rtol=3e-4)
+    _grad_close(enc_apg_local, Pl)
+    _grad_close(dec, Pd)
+
+
+def test_N2_dmm_training_loop_runs_like_reference_train():
+    """the reference's train() inner loop (apgs/dmm/apg_training.py) on the drop-in: finite losses, every parameter gets
+    a gradient, Adam steps change the weights."""
+    from apgs_b200.dmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    K, D, N, S, B, sweeps = 4, 2, 200, 10, 20, 4
+    P, models, opt = _train_mods(K, D)
+    torch.manual_seed(1)
+    data = od.simulate(B, N, K, D).to(DEV)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    rs = Resampler("systematic", S, True, DEV)
+    before = [p.detach().clone() for m in models for p in m.parameters()]
+    for it in range(3):
+        opt.zero_grad()
+        trace = O.apg_objective(models, data.repeat(S, 1, 1, 1), K, flags, sweeps, rs)
+        loss = trace["loss_phi"].sum() + trace["loss_theta"].sum()
+        loss.backward()
+        assert bool(torch.isfinite(loss))
+        for m in models:
+            for n_, p in m.named_parameters():
+                assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n_
+        opt.step()
+    after = [p.detach() for m in models for p in m.parameters()]
+    assert all(not torch.equal(a, b) for a, b in zip(before, after))
