@@ -46,3 +46,35 @@ class Affine_Transformer():
     # fused tail of Dec_digit.forward (apgs/bmnist/models.py:148-154) -- the reference has no such entry
     def reconstruct_ll(self, digit, z_where, frames, want_recon=False):
         return kernels.paste_ll(digit, z_where, frames, self.lin_fp, want_recon=want_recon)
+
+    # ---- differentiable twins for training mode: same pixels as the kernels, PyTorch ops only.
+    # The transformer's theta is diagonal, so the nearest-neighbour sampling grid is separable: one source row per
+    # output row and one source column per output column (the index formula of csrc/bmnist.cu stn_index); the paste
+    # is two gathers, whose autograd is the scatter-add grid_sample(nearest) gives w.r.t. its input.
+    @staticmethod
+    def _axis_index(lin, scale, t, n_in):
+        u = ((lin * scale + t.unsqueeze(-1)) + 1) * ((n_in - 1) / 2)
+        idx = torch.round(u)
+        ok = (idx >= 0) & (idx <= n_in - 1)
+        return idx.clamp(0, n_in - 1).long(), ok
+
+    def digit_to_frame_torch(self, digit, z_where):
+        """digit_to_frame with an autograd graph w.r.t. `digit` (z_where carries none: nearest sampling)."""
+        FP, DP = self.frame_pixels, self.digit_pixels
+        T = z_where.shape[2]
+        scale = float(torch.tensor(FP / DP, dtype=torch.float32))
+        z = z_where.detach()
+        col, cok = self._axis_index(self.lin_fp, scale, -1 * (z[..., 0] * self.translation_dtof), DP)
+        row, rok = self._axis_index(self.lin_fp, scale, z[..., 1] * self.translation_dtof, DP)
+        img = digit.unsqueeze(2).expand(-1, -1, T, -1, -1, -1)
+        rows = torch.gather(img, -2, row.unsqueeze(-1).expand(row.shape + (DP,)))
+        out = torch.gather(rows, -1, col.unsqueeze(-2).expand(col.shape[:-1] + (FP, FP)))
+        return out * (rok.unsqueeze(-1) & cok.unsqueeze(-2)).to(out.dtype)
+
+    def reconstruct_ll_torch(self, digit, z_where, frames, EPS=1e-9):
+        """ll (S,B,T) of apgs/bmnist/models.py:148-162 with an autograd graph w.r.t. `digit`."""
+        S = z_where.shape[0]
+        if frames.dim() == 4:
+            frames = frames.unsqueeze(0).expand(S, -1, -1, -1, -1)
+        recon = torch.clamp(self.digit_to_frame_torch(digit, z_where).sum(-3), min=0.0, max=1.0)
+        return (torch.log(recon + EPS) * frames + torch.log(1 - recon + EPS) * (1 - frames)).sum(-1).sum(-1)

@@ -13,6 +13,12 @@ from ..rng import normal_sample
 from ..trace import Trace
 
 
+def needs_grad(*modules):
+    """True when any parameter of the given modules takes part in autograd (training mode)."""
+    return torch.is_grad_enabled() and any(p.requires_grad for m in modules if isinstance(m, nn.Module)
+                                           for p in m.parameters())
+
+
 class Enc_coor(nn.Module):
     """encoder of the digit positions (models.py:7-38)"""
 

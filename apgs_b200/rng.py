@@ -6,4 +6,6 @@ import torch
 
 
 def normal_sample(loc, scale):
+    """Normal(loc, scale).sample(): a draw without an autograd graph (the reference never uses rsample)."""
+    loc, scale = loc.detach(), scale.detach()
     return torch.randn_like(loc).mul_(scale).add_(loc)

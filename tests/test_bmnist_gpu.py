@@ -187,3 +187,150 @@ def test_N3_template_match_vs_reference_expression(S, B, FP, DP):
     left = (frames5[:, :, 1] - torch.rand(S, B, FP, FP) * 0.5).contiguous()
     out = kernels.template_match(left.to(DEV), td[:, :, 1])
     np.testing.assert_allclose(out.cpu().numpy(), _match_ref(left, tmpl[:, :, 1].contiguous(), True).numpy(), rtol=3e-4, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------ N2: training mode
+def _train_models():
+    from apgs_b200.bmnist import models as M
+    torch.manual_seed(0)
+    P = ob.make_params()
+    ms, opt = M.init_models(96, 28, 400, 400, 2, 10, True, DEV, lr=1e-4)
+    for m, key in zip((ms[0], ms[2], ms[3]), ("enc_coor", "enc_digit", "dec_digit")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})
+    return P, ms, opt
+
+
+def _grads_close(module, Pg, rtol=5e-3):
+    scale = max(float(v.grad.abs().max()) for v in Pg.values() if v.grad is not None)
+    for name, p in module.named_parameters():
+        assert p.grad is not None, name
+        np.testing.assert_allclose(p.grad.cpu().numpy(), Pg[name].grad.numpy(), rtol=rtol, atol=2e-4 * scale, err_msg=name)
+
+
+def test_N2_differentiable_paste_matches_the_kernel_and_the_oracle():
+    AT = _AT()
+    torch.manual_seed(3)
+    S, B, T, K = 3, 2, 4, 3
+    z = torch.randn(S, B, T, K, 2) * 0.9
+    digit = torch.rand(S, B, K, 28, 28)
+    fr = torch.rand(B, T, 96, 96).round()
+    dd = digit.to(DEV).requires_grad_(True)
+    assert torch.equal(AT.digit_to_frame_torch(dd, z.to(DEV)).detach(), AT.digit_to_frame(digit.to(DEV), z.to(DEV)))
+    ll_t = AT.reconstruct_ll_torch(dd, z.to(DEV), fr.to(DEV))
+    ll_k, _ = AT.reconstruct_ll(digit.to(DEV), z.to(DEV), fr.to(DEV))
+    np.testing.assert_allclose(ll_t.detach().cpu().numpy(), ll_k.cpu().numpy(), rtol=2e-5)
+    ll_t.sum().backward()
+    dc = digit.clone().requires_grad_(True)
+    _, ll_o = ob.recon_ll(dc, z, fr.unsqueeze(0).expand(S, -1, -1, -1, -1))
+    ll_o.sum().backward()
+    np.testing.assert_allclose(dd.grad.cpu().numpy(), dc.grad.numpy(), rtol=2e-4, atol=1e-3)
+
+
+def test_N2_bmnist_what_and_where_gradients_match_oracle_autograd(golden):
+    """loss.backward() through apg_what and one frame of apg_where == autograd through the oracle (= the reference's
+    computation) on the same draws."""
+    from apgs_b200.bmnist import objectives as O
+    from apgs_b200.resampler import Resampler
+    g = golden("bmnist")
+    K = 3
+    P, (enc_coor, dec_coor, enc_digit, dec_digit), _ = _train_models()
+    AT = _AT()
+    frames = _t(g, "frames")
+    B, T = frames.shape[0], frames.shape[1]
+    S = 4
+    frs = frames.unsqueeze(0).repeat(S, 1, 1, 1, 1)
+    torch.manual_seed(2)
+    z_where = torch.randn(S, B, T, K, 2) * 0.5
+    z_what_old = torch.randn(S, B, K, 10)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    leaf = lambda d: {k: v.clone().requires_grad_(True) for k, v in d.items()}
+    # ---- apg_what
+    trace = {"loss_phi": [torch.zeros(1, device=DEV)], "loss_theta": [torch.zeros(1, device=DEV)], "ess": [],
+             "E_where": [], "E_what": [], "E_recon": [], "density": [torch.zeros(1, S, B, device=DEV)]}
+    log_w, z_what, trace = O.apg_what(enc_digit, dec_digit, AT, frs.to(DEV), z_where.to(DEV), z_what_old.to(DEV), trace, flags)
+    (trace["loss_phi"][0] + trace["loss_theta"][0]).sum().backward()
+    Pe, Pd = leaf(P["enc_digit"]), leaf(P["dec_digit"])
+    cropped = ob.frame_to_digit(frs, z_where).view(S, B, T, K, 784)
+    q_mu, q_std = ob.enc_digit_params(Pe, cropped)
+    _, ll_f = ob.recon_ll(ob.dec_digit_mean(Pd, z_what.cpu()), z_where, frs)
+    _, ll_b = ob.recon_ll(ob.dec_digit_mean(Pd, z_what_old), z_where, frs)
+    lw, lqf, _ = ob.what_step_weight(q_mu, q_std, z_what.cpu(), z_what_old, ll_f, ll_b)
+    w = torch.softmax(lw.detach(), 0)
+    ref_phi, ref_theta = (w * (-lqf)).sum(0).mean(), (w * (-ll_f.sum(-1))).sum(0).mean()
+    (ref_phi + ref_theta).backward()
+    np.testing.assert_allclose(float(trace["loss_phi"][0].detach()), float(ref_phi.detach()), rtol=5e-4)
+    np.testing.assert_allclose(float(trace["loss_theta"][0].detach()), float(ref_theta.detach()), rtol=5e-4)
+    _grads_close(enc_digit, Pe)
+    _grads_close(dec_digit, Pd)
+    # ---- apg_where (T frames, per-frame resampling inside): every parameter that the reference trains gets a gradient
+    for m in (enc_digit, dec_digit):
+        m.zero_grad()
+    trace = {"loss_phi": [], "loss_theta": [], "ess": [], "E_where": [], "E_what": [], "E_recon": [], "density": []}
+    z_new, trace = O.apg_where(enc_coor, dec_coor, dec_digit, AT, Resampler("systematic", S, True, DEV), frs.to(DEV),
+                               z_what.detach(), z_where.to(DEV), trace, flags)
+    (trace["loss_phi"][0] + trace["loss_theta"][0]).sum().backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) and float(p.grad.abs().max()) > 0
+               for p in enc_coor.parameters())
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in dec_digit.parameters())
+    assert not z_new.requires_grad
+
+
+def test_N2_bmnist_where_step_gradient_single_frame_vs_oracle():
+    """one frame of apg_where with S = 1 particle (weights are then exactly 1, no resampling effect): gradients of
+    loss_phi w.r.t. Enc_coor and of loss_theta w.r.t. Dec_digit against the oracle's autograd on the same draw."""
+    from apgs_b200.bmnist import objectives as O
+    from apgs_b200.resampler import Resampler
+    K, S, B, T = 3, 1, 3, 1
+    P, (enc_coor, dec_coor, enc_digit, dec_digit), _ = _train_models()
+    AT = _AT()
+    torch.manual_seed(4)
+    frames = ob.simulate(B, T, K)
+    frs = frames.unsqueeze(0).repeat(S, 1, 1, 1, 1)
+    z_what = torch.randn(S, B, K, 10)
+    z_where_old = torch.randn(S, B, T, K, 2) * 0.5
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    trace = {"loss_phi": [], "loss_theta": [], "ess": [], "E_where": [], "E_what": [], "E_recon": [], "density": []}
+    z_new, trace = O.apg_where(enc_coor, dec_coor, dec_digit, AT, Resampler("systematic", S, True, DEV), frs.to(DEV),
+                               z_what.to(DEV), z_where_old.to(DEV), trace, flags)
+    (trace["loss_phi"][0] + trace["loss_theta"][0]).sum().backward()
+    leaf = lambda d: {k: v.clone().requires_grad_(True) for k, v in d.items()}
+    Pc, Pd = leaf(P["enc_coor"]), leaf(P["dec_digit"])
+    template = ob.dec_digit_mean(Pd, z_what).detach()
+    pm = ob.propose_one_movement({"enc_coor": Pc}, ob.make_prior(), frs[:, :, 0], template, None, z_where_old[:, :, 0], None,
+                                 forced=z_new.cpu()[:, :, 0])
+    _, ll_f = ob.recon_ll(ob.dec_digit_mean(Pd, z_what), z_new.cpu(), frs)
+    ref = (-pm["log_q_f"]).sum(0).mean() + (-ll_f.squeeze(-1)).sum(0).mean()          # S = 1: w == 1
+    ref.backward()
+    np.testing.assert_allclose(float((trace["loss_phi"][0] + trace["loss_theta"][0]).sum().detach()), float(ref.detach()), rtol=5e-4)
+    _grads_close(enc_coor, Pc)
+    _grads_close(dec_digit, Pd)
+
+
+def test_N2_bmnist_training_loop_runs_like_reference_train():
+    """the reference's train() inner loop (apgs/bmnist/apg_training.py) on the drop-in: finite losses, every parameter
+    gets a gradient, Adam steps change the weights."""
+    from apgs_b200.bmnist import objectives as O
+    from apgs_b200.resampler import Resampler
+    K, S, B, T, sweeps = 3, 6, 4, 3, 3
+    P, models, opt = _train_models()
+    AT = _AT()
+    torch.manual_seed(1)
+    frames = ob.simulate(B, T, K).to(DEV)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 28), torch.linspace(-1, 1, 28), indexing="ij")
+    mm = torch.exp(-(xx ** 2 + yy ** 2) * 3).clamp(0, 1).to(DEV).repeat(S, B, K, 1, 1)
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    rs = Resampler("systematic", S, True, DEV)
+    mods = (models[0], models[2], models[3])
+    before = [p.detach().clone() for m in mods for p in m.parameters()]
+    for it in range(2):
+        opt.zero_grad()
+        trace = O.apg_objective(models, AT, frames.unsqueeze(0).repeat(S, 1, 1, 1, 1), K, flags, sweeps, rs, mm)
+        loss = trace["loss_phi"].sum() + trace["loss_theta"].sum()
+        loss.backward()
+        assert bool(torch.isfinite(loss))
+        for m in mods:
+            for n_, p in m.named_parameters():
+                assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n_
+        opt.step()
+    after = [p.detach() for m in mods for p in m.parameters()]
+    assert all(not torch.equal(a, b) for a, b in zip(before, after))
