@@ -7,7 +7,7 @@
 //     row is one 128 B transaction;
 //   * a latent is (S,B,inner): the output of the gather is a dense stream, the input is B chunks of
 //     `inner` bytes per output row.
-#include "common.cuh"
+#include "resample.cuh"
 
 namespace apgs {
 
@@ -22,25 +22,6 @@ namespace apgs {
 // The tile lives in shared memory (S*TB*4 B) or, for very long particle axes, in a global
 // workspace with the same (row, column) addressing.
 // =============================================================================================
-struct AncArgs {
-    const float* log_w;
-    const float* w_norm;
-    const float* u_sys;        // [B]
-    const double* u_mult;      // strided
-    long long us, ub;
-    long long S, B;
-    int strategy;              // APGS_SYSTEMATIC / APGS_MULTINOMIAL / -1 (stats only)
-    int blocked;               // CDF mode
-    int tile_in_smem;
-    int dbl;                   // exact systematic CDF kept in a shared fp64 tile (no conversions on the chain)
-    float* ws;                 // global tile (S,B) when !tile_in_smem
-    long long* anc64;
-    int* anc32;
-    float* w_out;
-    float* ess;
-    float* lse;
-};
-
 template <int TB, typename T, typename Op>
 __device__ __forceinline__ T col_reduce(T v, Op op, T* scratch, int col) {
     // reduce over all threads of the CTA that share `col` (= tid % TB)
@@ -331,6 +312,9 @@ static int launch_ancestors(AncArgs a, void* workspace, size_t workspace_bytes, 
     AncPlan p = plan_ancestors(a.S, a.B, a.strategy == APGS_SYSTEMATIC && !a.blocked);
     a.tile_in_smem = p.tile_in_smem;
     a.dbl = p.dbl;
+    // particle axes beyond a shared-memory tile: the split-S pipeline (resample_large.cu) unless the caller insists on
+    // the exact sequential chain
+    if (!p.tile_in_smem && (a.blocked || a.strategy < 0)) return launch_ancestors_large(a, workspace, workspace_bytes, st);
     if (!p.tile_in_smem) {
         size_t need = (size_t)a.S * a.B * sizeof(float);
         if (workspace == nullptr || workspace_bytes < need)
@@ -533,7 +517,7 @@ static int check_sb(long long S, long long B, const char* who) {
 extern "C" size_t apgs_ancestors_workspace_bytes(int64_t S, int64_t B) {
     if (S <= 0 || B <= 0) return 0;
     if (((size_t)S + 2) * 12 <= kSmemTileBudget) return 0;      // CDF tile fits in shared memory
-    return (size_t)S * (size_t)B * sizeof(float);
+    return ancestors_large_workspace_bytes(S, B);               // >= S*B*4, which the exact global-tile variant needs
 }
 
 extern "C" size_t apgs_resample_workspace_bytes(int64_t S, int64_t B) {

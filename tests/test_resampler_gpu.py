@@ -276,3 +276,49 @@ def test_gather_large_rows(S, B, shape):
         idx = anc.view(Sx, B, *([1] * len(shape))).expand_as(v)
         assert torch.equal(o, torch.gather(v, 0, idx))
         assert torch.equal(o2, torch.gather(small, 0, anc.view(Sx, B, 1, 1).expand_as(small)))
+
+
+# ------------------------------------------------------------------ split-S pipeline (S beyond a shared-memory tile)
+@pytest.mark.parametrize("S,B", [(60000, 3), (100000, 1), (131072, 33), (70001, 40)])
+def test_split_S_pipeline_from_log_weights(S, B):
+    """S > ~51k runs resample_large.cu: weights / ESS / lse against torch, systematic ancestors against the oracle run
+    on the kernel's own weights (level 1), and the fused resample against a plain gather."""
+    ops = _ops()
+    torch.manual_seed(S + B)
+    lw = torch.randn(S, B) * 2.0
+    lw[:, 0] = torch.randn(S) * 12.0                                      # one nearly degenerate instance
+    u = torch.rand(B)
+    w, ess, lse = ops.weight_stats(lw.to(DEV))
+    w_ref = torch.softmax(lw.double(), 0)
+    np.testing.assert_allclose(w.cpu().numpy(), w_ref.float().numpy(), rtol=2e-5, atol=1e-37)
+    np.testing.assert_allclose(ess.cpu().numpy(), (1.0 / (w_ref ** 2).sum(0)).numpy(), rtol=2e-5)
+    np.testing.assert_allclose(lse.cpu().numpy(), torch.logsumexp(lw.double(), 0).numpy(), rtol=1e-6, atol=1e-5)
+    a = ops.sample_ancestors(log_w=lw.to(DEV), strategy="systematic", uniforms=u.to(DEV))
+    assert a.dtype == torch.int64 and int(a.min()) >= 0 and int(a.max()) < S
+    assert bool((a[1:] >= a[:-1]).all())
+    ref = orc.systematic_ancestors(w.cpu().numpy(), u.numpy())
+    bad = (a.cpu().numpy() != ref).sum()
+    assert bad <= 2, "fp64 re-association should flip (almost) nothing: %d" % bad
+    a32 = ops.sample_ancestors(log_w=lw.to(DEV), strategy="systematic", uniforms=u.to(DEV), index_dtype=torch.int32)
+    assert torch.equal(a32.long(), a)
+    # fused entry
+    lat = torch.randn(S, B, 3, device=DEV)
+    (out,), _, _ = ops.resample([lat], log_w=lw.to(DEV), strategy="systematic", uniforms=u.to(DEV))
+    assert torch.equal(out, torch.gather(lat, 0, a.unsqueeze(-1).expand_as(lat)))
+
+
+def test_split_S_pipeline_multinomial_and_given_weights():
+    ops = _ops()
+    S, B = 80000, 5
+    torch.manual_seed(1)
+    w = torch.softmax(torch.randn(S, B) * 2.0, 0)
+    um = torch.rand(S, B, dtype=torch.float64)
+    a = ops.sample_ancestors(w_norm=w.to(DEV), strategy="multinomial", uniforms=um.to(DEV)).cpu().numpy()
+    ref = orc.multinomial_ancestors(w.numpy(), um.t().numpy(), cdf_mode="f64")
+    assert (a != ref).sum() <= 2
+    u = torch.rand(B)
+    a = ops.sample_ancestors(w_norm=w.to(DEV), strategy="systematic", uniforms=u.to(DEV)).cpu().numpy()
+    assert (a != orc.systematic_ancestors(w.numpy(), u.numpy())).sum() <= 2
+    # the exact sequential chain is still available on request (single-CTA global-tile variant)
+    a = ops.sample_ancestors(w_norm=w.to(DEV), strategy="systematic", uniforms=u.to(DEV), cdf_mode=1).cpu().numpy()     # APGS_CDF_EXACT
+    assert np.array_equal(a, orc.systematic_ancestors(w.numpy(), u.numpy()))
