@@ -178,3 +178,72 @@ def resample_variables(resampler, tau, mu, z, log_weights):
     """objectives.py:229-234: one ancestor draw, one gather launch for the three latents."""
     tau, mu, z = resampler.resample([tau, mu, z], log_weights)
     return tau, mu, z
+
+
+# ------------------------------------------------------------------ baselines around the path (SURVEY.md row N4)
+def _prior_as_post(generative, S, B):
+    return tuple(p.unsqueeze(0).unsqueeze(0).expand(S, B, -1, -1).contiguous() for p in generative.prior_ng)
+
+
+def posterior_z(x, tau, mu, prior_pi):
+    """log posterior responsibilities (S,B,N,K) given eta (apgs/gmm/kls_gmm.py:121-133)."""
+    sigma = 1. / tau.sqrt()
+    xe = x.unsqueeze(2)                                                  # S,B,1,N,D (broadcast over K)
+    log_gammas = Normal(mu.unsqueeze(-2), sigma.unsqueeze(-2), validate_args=False).log_prob(xe).sum(-1).transpose(-1, -2)
+    return torch.log_softmax(log_gammas + prior_pi.log(), dim=-1)
+
+
+def gibbs_objective(models, x, result_flags, num_sweeps):
+    """The Gibbs sampler baseline (objectives.py:236-247)."""
+    trace = {'density': []}
+    (enc_rws_eta, enc_rws_z, _, generative) = models
+    if x.dim() == 3:
+        raise ValueError("gibbs_objective takes the S-replicated (S,B,N,D) data, as the reference")
+    _, tau, mu, z, trace = oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags)
+    for m in range(num_sweeps - 1):
+        tau, mu, z, trace = gibbs_sweep(generative, x, z, trace)
+    if result_flags['density_required']:
+        trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def gibbs_sweep(generative, x, z, trace):
+    """Exact conjugate updates (objectives.py:249-274): eta | z through the G1 kernel on the plain statistics,
+    z | eta in PyTorch, the log joint through the G4 density kernel."""
+    post = kernels.nss_posterior(x.contiguous(), z, generative)          # posterior_eta(x, z): gamma = z, x' = x
+    tau, mu = _sample_eta(post)
+    logits = posterior_z(x, tau, mu, generative.prior_pi)
+    q_probs = logits.exp()
+    z = cat(logits=logits, validate_args=False).sample()
+    w = kernels.logw_oneshot(x, post, generative, tau, mu, q_probs, z)   # density = ll + log p(eta) + log p(z)
+    trace['density'].append(w.density.unsqueeze(0))
+    return tau, mu, z, trace
+
+
+def bpg_objective(models, x, result_flags, num_sweeps, resampler):
+    """APG whose eta block proposes from the prior (objectives.py:291-306); the reference runs it with S * bpg_factor
+    particles (evaluation.py:27,41-42), which is what the split-S ancestor pipeline is for."""
+    trace = {'density': []}
+    (enc_rws_eta, enc_apg_z, enc_apg_eta, generative) = models
+    if x.dim() == 3:
+        x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)
+    log_w, tau, mu, z, trace = oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags)
+    tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
+    for m in range(num_sweeps - 1):
+        log_w_eta, tau, mu, trace = bpg_update_eta(generative, x, z, tau, mu, trace)
+        tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_eta)
+        log_w_z, z, trace = apg_update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags)
+        tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_z)
+    trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def bpg_update_eta(generative, x, z, tau_old, mu_old, trace):
+    """eta proposed from the prior: weight = likelihood ratio (objectives.py:308-320).  One G2 launch with the prior as
+    the proposal: log p(eta) - log q(eta) cancels bit for bit, leaving ll_f - ll_b; density = log p(eta_new)."""
+    S, B = z.shape[0], z.shape[1]
+    post = _prior_as_post(generative, S, B)
+    tau, mu = _sample_eta(post)
+    w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
+    trace['density'].append(w.density.unsqueeze(0))
+    return w.log_w, tau, mu, trace

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define APGS_ABI_VERSION 1
+#define APGS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define APGS_API __attribute__((visibility("default")))
@@ -84,7 +84,9 @@ APGS_API int apgs_local_weight_stats_f32(const float* log_w_local, int64_t S, in
  *   strategy APGS_MULTINOMIAL: uniforms = float64, element (s,b) at uniforms[s*u_stride_s +
  *                              b*u_stride_b] (the reference's generator order is (B,S):
  *                              u_stride_s = 1, u_stride_b = S).
- *   anc64 (S,B) int64 and/or anc32 (S,B) int32 receive the ancestors (either may be NULL).   */
+ *   anc64 (S,B) int64 and/or anc32 (S,B) int32 receive the ancestors (either may be NULL).
+ *   workspace: 0 bytes while one instance's CDF fits a shared-memory tile (S <= ~17k); beyond that the transposed
+ *   CDF (S*B floats) plus the per-chunk partials of the split-S pipeline, 256-byte aligned.          */
 APGS_API size_t apgs_ancestors_workspace_bytes(int64_t S, int64_t B);
 APGS_API int apgs_sample_ancestors_f32(const float* log_w, const float* w_norm, int64_t S, int64_t B,
                               int strategy, const void* uniforms,

@@ -8,6 +8,8 @@ Follows, in the reference's operation order (torch-CPU fp32):
   apgs/gmm/models.py:139-185     Generative.eta_prior / z_prior / log_prob (quirk Q3)
   apgs/gmm/objectives.py:9-234   apg_objective / oneshot / apg_update_{eta,z,joint} /
                                  resample_variables
+  apgs/gmm/objectives.py:236-330 gibbs_objective / gibbs_sweep / bpg_objective / bpg_update_eta (baselines, N4)
+  apgs/gmm/kls_gmm.py:121-133    posterior_z
 
 Parameters are plain dicts keyed like the reference's nn.Module state_dicts
 ('gamma.0.weight', 'ob.0.weight', 'pi_log_prob.0.weight', ...).  Random draws use the
@@ -321,6 +323,70 @@ def apg_objective(P, prior, x, result_flags, num_sweeps, block='decomposed',
         if result_flags[k + '_required']:
             out[k] = torch.cat(trace[k], 0)
     return out
+
+
+# ------------------------------------------------- baselines around the path
+def posterior_z_logits(x, tau, mu, prior):
+    """kls_gmm.py:121-133: log posterior responsibilities (S,B,N,K) given eta."""
+    N, K = x.shape[-2], mu.shape[-2]
+    sigma = 1. / tau.sqrt()
+    mu_e = mu.unsqueeze(-2).repeat(1, 1, 1, N, 1)
+    sigma_e = sigma.unsqueeze(-2).repeat(1, 1, 1, N, 1)
+    ob_e = x.unsqueeze(2).repeat(1, 1, K, 1, 1)
+    log_gammas = Normal(mu_e, sigma_e).log_prob(ob_e).sum(-1).transpose(-1, -2) + prior['pi'].log()
+    return F.softmax(log_gammas, dim=-1).log()
+
+
+def _oneshot(P, prior, x):
+    post = enc_rws_eta_posterior(P['enc_rws_eta'], x, prior)
+    tau, mu = _sample_eta(post)
+    q_probs = enc_apg_z_probs(P['enc_apg_z'], x, tau, mu)
+    z = OneHotCategorical(q_probs).sample()
+    log_w, log_q, log_p = oneshot_weights(x, post, prior, tau, mu, q_probs, z)
+    return log_w, log_p, tau, mu, z
+
+
+def gibbs_objective(P, prior, x, num_sweeps):
+    """objectives.py:236-274: one-shot initialisation, then exact conjugate Gibbs sweeps; trace of the log joint
+    (num_sweeps, S, B)."""
+    _, log_p, tau, mu, z = _oneshot(P, prior, x)
+    dens = [log_p.unsqueeze(0)]
+    for _ in range(num_sweeps - 1):
+        post = nss_posterior(x, z, prior)                        # posterior_eta(x, z=z, ...): the same formulas (Q1, Q2)
+        tau, mu = _sample_eta(post)
+        logits = posterior_z_logits(x, tau, mu, prior)
+        z = OneHotCategorical(logits=logits).sample()
+        lp_tau = dists.gamma_log_prob(tau, prior['alpha'], prior['beta']).sum(-1).sum(-1)
+        lp_mu = dists.normal_log_prob(mu, prior['mu'], 1. / (prior['nu'] * tau).sqrt()).sum(-1).sum(-1)
+        log_joint = (log_likelihood(x, z, tau, mu, True) + lp_tau + lp_mu                        # the order of :270
+                     + dists.onehot_categorical_log_prob(z, prior['pi']).sum(-1))
+        dens.append(log_joint.unsqueeze(0))
+    return {'density': torch.cat(dens, 0)}
+
+
+def bpg_objective(P, prior, x, num_sweeps, strategy='systematic'):
+    """objectives.py:291-330: APG whose eta block proposes from the PRIOR (weight = likelihood ratio); density trace
+    (num_sweeps, S, B): one-shot log joint, then the prior log-density of each proposed eta plus the z-step density."""
+    S, B = x.shape[0], x.shape[1]
+    rs = _Resampler(strategy, S)
+    log_w, log_p, tau, mu, z = _oneshot(P, prior, x)
+    dens = [log_p.unsqueeze(0)]
+    tau, mu, z = _resample(rs, log_w, tau, mu, z)
+    K, D = prior['alpha'].shape
+    for _ in range(num_sweeps - 1):
+        rep = lambda t: t.unsqueeze(0).unsqueeze(0).repeat(S, B, 1, 1)
+        tau_new = Gamma(rep(prior['alpha']), rep(prior['beta'])).sample()
+        mu_new = Normal(rep(prior['mu']), 1. / (prior['nu'] * tau_new).sqrt()).sample()
+        log_p_f = eta_log_prior(tau_new, mu_new, prior)
+        log_w = log_likelihood(x, z, tau_new, mu_new, True) - log_likelihood(x, z, tau, mu, True)
+        dens.append(log_p_f.unsqueeze(0))
+        tau, mu, z = _resample(rs, log_w, tau_new, mu_new, z)
+        q_probs = enc_apg_z_probs(P['enc_apg_z'], x, tau, mu)
+        z_new = OneHotCategorical(q_probs).sample()
+        log_w_local, log_w, log_q_f, d = z_step_weights(x, tau, mu, q_probs, prior, z_new, z)
+        dens[-1] = dens[-1] + d.sum(-1).unsqueeze(0)
+        tau, mu, z = _resample(rs, log_w, tau, mu, z_new)
+    return {'density': torch.cat(dens, 0)}
 
 
 # ---------------------------------------------------------------------- synthetic data

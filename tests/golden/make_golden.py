@@ -166,6 +166,25 @@ def section_gmm():
             tr = O.apg_objective(models, xx.repeat(S, 1, 1, 1), flags, sweeps, block, Resampler(strategy, S, False, None))
             for k in ("loss", "ess", "density"):
                 out["full_%s_%s_%s" % (block, strategy, k)] = tr[k]
+
+    # baselines around the path: Gibbs sweeps and BPG (prior proposals, S * bpg_factor particles)
+    dflags = {"loss_required": False, "ess_required": False, "mode_required": False, "density_required": True}
+    P = {n_: {k: v for k, v in m_.state_dict().items()} for n_, m_ in
+         (("enc_rws_eta", enc_rws_eta), ("enc_apg_z", enc_apg_z), ("enc_apg_eta", enc_apg_eta))}
+    with torch.no_grad():
+        torch.manual_seed(8)
+        tr = O.gibbs_objective(models, xx.repeat(S, 1, 1, 1), dflags, sweeps)
+        torch.manual_seed(8)
+        mine = og.gibbs_objective(P, gen, xx.repeat(S, 1, 1, 1), sweeps)
+        assert torch.equal(tr["density"], mine["density"]), "oracle gibbs_objective != reference"
+        out["gibbs_density"] = tr["density"]
+        S_bpg = S * 4
+        torch.manual_seed(9)
+        tr = O.bpg_objective(models, xx.repeat(S_bpg, 1, 1, 1), dflags, sweeps, Resampler("systematic", S_bpg, False, None))
+        torch.manual_seed(9)
+        mine = og.bpg_objective(P, gen, xx.repeat(S_bpg, 1, 1, 1), sweeps, "systematic")
+        assert torch.equal(tr["density"], mine["density"]), "oracle bpg_objective != reference"
+        out["bpg_density"] = tr["density"]
     save("gmm", **out)
 
 

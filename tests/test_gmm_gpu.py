@@ -573,3 +573,60 @@ def test_N2_training_loop_runs_like_reference_train():
         opt.step()
     after = [p.detach() for m in models[:3] for p in m.parameters()]
     assert all(not torch.equal(a, b) for a, b in zip(before, after))
+
+
+# ------------------------------------------------------------ N4: Gibbs / BPG baselines on the kernels
+def test_N4_bpg_eta_step_and_gibbs_sweep_arithmetic_vs_oracle():
+    from apgs_b200.gmm import objectives as O
+    S, B, N, K, D = 9, 4, 60, 3, 2
+    torch.manual_seed(0)
+    prior = og.make_prior()
+    x = og.simulate(B)
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    tau_old, mu_old = torch.rand(S, B, K, D) + 0.5, torch.randn(S, B, K, D)
+    gen = _models_from_params(og.make_params())[3]
+    # BPG: weight = likelihood ratio, density = log prior of the proposed eta (objectives.py:308-320)
+    trace = {"density": []}
+    log_w, tau, mu, trace = O.bpg_update_eta(gen, xs.to(DEV), z.to(DEV), tau_old.to(DEV), mu_old.to(DEV), trace)
+    ll_f = og.log_likelihood(xs, z, tau.cpu(), mu.cpu(), True)
+    ll_b = og.log_likelihood(xs, z, tau_old, mu_old, True)
+    _close(log_w, ll_f - ll_b, rtol=0, atol=RT * (ll_f.abs() + ll_b.abs()), what="bpg log_w")
+    _close(trace["density"][0][0], og.eta_log_prior(tau.cpu(), mu.cpu(), prior), rtol=RT, atol=1e-4, what="bpg density")
+    # Gibbs: the log joint of the sweep's own draws (objectives.py:249-274)
+    trace = {"density": []}
+    tau, mu, z_new, trace = O.gibbs_sweep(gen, xs.to(DEV), z.to(DEV), trace)
+    assert bool((z_new.sum(-1) == 1).all())
+    lj = (og.log_likelihood(xs, z_new.cpu(), tau.cpu(), mu.cpu(), True) + og.eta_log_prior(tau.cpu(), mu.cpu(), prior)
+          + og.z_log_prior(z_new.cpu(), prior).sum(-1))
+    _close(trace["density"][0][0], lj, rtol=RT, atol=1e-5 * lj.abs().max(), what="gibbs log joint")
+    # the responsibilities are the reference's (kls_gmm.py:121-133)
+    logits = O.posterior_z(xs.to(DEV), tau, mu, gen.prior_pi)
+    _close(logits.exp(), og.posterior_z_logits(xs, tau.cpu(), mu.cpu(), prior).exp(), rtol=1e-4, atol=1e-7, what="posterior_z")
+
+
+def test_N4_gibbs_and_bpg_objectives_match_reference_traces_statistically(golden):
+    """whole baselines against the reference's golden density traces (different generators: Monte-Carlo comparison of
+    the per-sweep mean log joint over the same 20 instances)."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    g = golden("gmm")
+    S, sweeps = 10, 5
+    x = _t(g, "full_x")
+    B = x.shape[0]
+    models = _models_from_params(_params(g))
+    flags = {"loss_required": False, "ess_required": False, "mode_required": False, "density_required": True}
+    reps = 12
+    with torch.no_grad():
+        torch.manual_seed(3)
+        gib = torch.stack([O.gibbs_objective(models, x.to(DEV).repeat(S, 1, 1, 1), flags, sweeps)["density"] for _ in range(reps)])
+        bpg = torch.stack([O.bpg_objective(models, x.to(DEV).repeat(4 * S, 1, 1, 1), flags, sweeps,
+                                           Resampler("systematic", 4 * S, True, DEV))["density"] for _ in range(reps)])
+    for name, mine, ref in (("gibbs", gib, _t(g, "gibbs_density")), ("bpg", bpg, _t(g, "bpg_density"))):
+        assert tuple(mine.shape[1:]) == tuple(ref.shape), name
+        assert bool(torch.isfinite(mine).all()), name
+        a = mine.cpu().mean(2).permute(1, 0, 2).reshape(sweeps, -1)          # (sweeps, reps * B): particle means
+        b = ref.mean(1)                                                      # (sweeps, B)
+        for m in range(sweeps):
+            se = (a[m].var() / a.shape[1] + b[m].var() / B).sqrt()
+            assert abs(float(a[m].mean() - b[m].mean())) < 6 * float(se) + 1e-3 * abs(float(b[m].mean())), (name, m)

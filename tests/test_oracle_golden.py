@@ -142,6 +142,22 @@ def test_gmm_full_objective_reproduces_reference_trace(golden, block, strategy):
         torch.testing.assert_close(tr[k], ref, rtol=1e-6, atol=1e-6)
 
 
+def test_gmm_gibbs_and_bpg_baselines_reproduce_reference_traces(golden):
+    """gibbs_objective / bpg_objective (apgs/gmm/objectives.py:236-330) under the generating seeds."""
+    g = golden("gmm")
+    S, sweeps = 10, 5
+    torch.manual_seed(0)
+    P, prior = og.make_params(), og.make_prior()
+    x = _t(g, "full_x")
+    with torch.no_grad():
+        torch.manual_seed(8)
+        tr = og.gibbs_objective(P, prior, x.repeat(S, 1, 1, 1), sweeps)
+        torch.testing.assert_close(tr["density"], _t(g, "gibbs_density"), rtol=1e-6, atol=1e-5)
+        torch.manual_seed(9)
+        tr = og.bpg_objective(P, prior, x.repeat(4 * S, 1, 1, 1), sweeps, "systematic")
+        torch.testing.assert_close(tr["density"], _t(g, "bpg_density"), rtol=1e-6, atol=1e-5)
+
+
 # ------------------------------------------------------------------------ STN / bmnist
 def test_stn_closed_form_bit_exact(golden):
     from oracle import stn
