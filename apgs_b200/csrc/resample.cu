@@ -244,21 +244,45 @@ __global__ void __launch_bounds__(1024, 1) k_ancestors(AncArgs a) {
     // ---- phase 6: ancestors
     if (!colok) return;
     const float fS = (float)S;
-    const float u = (a.strategy == APGS_SYSTEMATIC) ? __ldg(a.u_sys + b) : 0.f;
-    for (int i = rg; i < S; i += R) {
-        int lo = 0, hi = S;
-        if (a.strategy == APGS_SYSTEMATIC) {
+    if (a.strategy == APGS_SYSTEMATIC) {
+        // Positions (u + s)/S increase with s and so do their ancestors: a thread owns a STRIP of consecutive
+        // particles, locates the first one by binary search and then gallops forward from the previous answer
+        // (typically 1-2 probes per particle instead of log2 S; identical result: the lower bound of pos in the CDF).
+        const float u = __ldg(a.u_sys + b);
+        const int per = (S + R - 1) / R;
+        const int i0 = min(rg * per, S), i1 = min(i0 + per, S);
+        int anc = 0;
+        for (int i = i0; i < i1; ++i) {
             const float pos = __fdiv_rn(__fadd_rn(u, (float)i), fS);          // resampler.py:28
+            int lo, hi;
+            if (i == i0) {
+                lo = 0; hi = S;
+            } else if (anc < S && tile.ld(anc) < pos) {                       // advance: cdf[anc] < pos
+                int step = 1;
+                lo = anc;
+                while (lo + step < S && tile.ld(lo + step) < pos) { lo += step; step <<= 1; }
+                hi = min(lo + step, S);
+                lo = lo + 1;
+            } else {
+                lo = hi = anc;
+            }
             while (lo < hi) {
-                int mid = (lo + hi) >> 1;
+                const int mid = (lo + hi) >> 1;
                 if (tile.ld(mid) < pos) lo = mid + 1; else hi = mid;
             }
-        } else {
-            const double ud = __ldg(a.u_mult + (long long)i * a.us + b * a.ub);
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if ((double)tile.ld(mid) < ud) lo = mid + 1; else hi = mid;
-            }
+            anc = lo;
+            const int out = min(anc, S - 1);                                  // memory safety on NaN / degenerate weights
+            if (a.anc32 != nullptr) a.anc32[(long long)i * B + b] = out;
+            if (a.anc64 != nullptr) a.anc64[(long long)i * B + b] = out;
+        }
+        return;
+    }
+    for (int i = rg; i < S; i += R) {
+        int lo = 0, hi = S;
+        const double ud = __ldg(a.u_mult + (long long)i * a.us + b * a.ub);
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if ((double)tile.ld(mid) < ud) lo = mid + 1; else hi = mid;
         }
         if (lo > S - 1) lo = S - 1;                        // memory safety on NaN / degenerate weights
         if (a.anc32 != nullptr) a.anc32[(long long)i * B + b] = lo;
