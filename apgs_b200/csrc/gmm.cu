@@ -239,6 +239,223 @@ __global__ void __launch_bounds__(P* LANES, STATS ? 4 : 1) k_gmm_nss_posterior(N
 }
 
 // ============================================================================================
+// G1 for the fused heads with one-hot z (Enc_apg_eta), instance-major.
+// A CTA owns ONE instance b and P particles of it (rows r = s*B + b, one bulk copy per 720-byte z row), as the fused
+// z step does.  With z one-hot, the two Linear heads on cat(x_n, z_n) -- and therefore gamma_n, x'_n and every product
+// gamma_nk x'_nd, gamma_nk x'_nd^2 that enters the neural statistics -- take only K distinct values per data point:
+// they are tabulated ONCE PER CTA in shared memory, T[n][label] = { gamma (K), gamma x' (K D), gamma x'^2 (K D) }, and
+// the per-particle work shrinks to: label of the point, four LDS.128, K (1 + 2D) additions (+ the centred one-hot
+// statistics for the eta-step weights, packed fp32x2).  ~45 instructions per point instead of ~100.
+// ============================================================================================
+constexpr int kP = 32, kLanes = 8;
+
+// row stride (floats) of the staged z rows: a multiple of 4 (16-byte bulk-copy destinations) that is 8 or 24 mod 32, so
+// that the four particles of a warp reading z[n][k] (n = lane-in-particle + 8 it) hit 32 different banks
+__host__ __device__ inline int nss_im_zstride(int NK) {
+    int st = (NK + 3) / 4 * 4;
+    while ((st & 31) != 8 && (st & 31) != 24) st += 4;
+    return st;
+}
+
+template <int K, int D, int P, int LANES, bool STATS>
+__global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long bar;
+    constexpr int KD = K * D, IN = D + K;
+    constexpr int TE = K + 2 * KD;                                      // table planes: gamma, gamma x', gamma x'^2
+    constexpr int ST = 1 + 2 * D, NS = K * ST;                          // plain statistics per particle
+    constexpr int RW = (TE > NS ? TE : NS) | 1;                         // reduction row (odd stride: no bank conflicts)
+    const int N = a.N, NK = N * K;
+    const int ZS = nss_im_zstride(NK);
+    const size_t zreg = max((size_t)P * ZS, (size_t)P * LANES * RW);    // z rows, later the cross-lane reduction buffer
+    float* s_z = reinterpret_cast<float*>(smem);
+    // structure-of-arrays table: plane e holds T_e[n*K + label].  The 8 lanes of a particle read rows 3n + label with
+    // n = j + 8 it, i.e. 8..24 distinct consecutive-ish addresses, and the 4 particles of a warp read the same window:
+    // every LDS.32 of the warp is conflict-free (an array-of-structs row of 16 floats costs ~2.3x the wavefronts).
+    float* s_tab = s_z + (zreg + 3) / 4 * 4;                            // [TE][NK]
+    float* s_x = s_tab + (size_t)TE * NK;                               // [N][D]
+    const int b = (int)(blockIdx.x % (unsigned int)a.B);
+    const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
+    const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
+    const bool valid = s0 + p < S;
+    const long long r = (long long)(s0 + p) * a.B + b;
+    const int rows = min(P, S - s0);
+    const unsigned int rb = (unsigned int)NK * 4u;
+    const bool bulk_in = (rb & 15u) == 0 && aligned(a.z, 16);
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows : 0u);
+    if (valid) {
+        if (bulk_in) {
+            if (j == 0) bulk_g2s(s_z + (size_t)p * ZS, a.z + r * NK, rb, &bar);
+        } else {
+            for (int i = j; i < NK; i += LANES) s_z[(size_t)p * ZS + i] = __ldg(a.z + r * NK + i);
+        }
+    }
+    // ---- per-CTA table over (point, label), while the rows are in flight
+    const float* xb = a.x + (size_t)b * N * D;
+    for (int idx = threadIdx.x; idx < NK; idx += blockDim.x) {
+        const int n = idx / K, lab = idx % K;
+        float xin[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xin[d] = __ldg(xb + n * D + d);
+        if (lab == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) s_x[n * D + d] = xin[d];
+        }
+        // the two Linear heads on cat(x_n, e_label) (models.py:56-65), in the accumulation order of the un-tabulated form
+        float lg[K], mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float acc = __ldg(a.bg + k);
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc = fmaf(__ldg(a.Wg + k * IN + d), xin[d], acc);
+            acc += __ldg(a.Wg + k * IN + D + lab);
+            lg[k] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        float se = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { lg[k] = ex2_ftz((lg[k] - mx) * 1.4426950408889634f); se += lg[k]; }
+        const float rse = rcp_ftz(se);
+        float xp[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float acc = __ldg(a.bo + d);
+#pragma unroll
+            for (int i = 0; i < D; ++i) acc = fmaf(__ldg(a.Wo + d * IN + i), xin[i], acc);
+            xp[d] = acc + __ldg(a.Wo + d * IN + D + lab);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float gk = lg[k] * rse;
+            s_tab[(size_t)k * NK + idx] = gk;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                s_tab[(size_t)(K + k * D + d) * NK + idx] = __fmul_rn(gk, xp[d]);                         // z_expand * ob_expand
+                s_tab[(size_t)(K + KD + k * D + d) * NK + idx] = __fmul_rn(gk, __fmul_rn(xp[d], xp[d]));  // z_expand * ob_expand**2
+            }
+        }
+    }
+    float cen[STATS ? K : 1][D];
+    f32x2 c2p[STATS ? K : 1], c3p[STATS ? K : 1], ncen2[STATS ? K : 1];
+    float c1[STATS ? K : 1], c2[STATS ? K : 1][D], c3[STATS ? K : 1][D];
+    if (STATS) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            c1[k] = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                c2[k][d] = 0.f; c3[k][d] = 0.f;
+                cen[k][d] = valid ? __ldg(a.center + r * KD + k * D + d) : 0.f;
+            }
+            c2p[k] = pack2(0.f, 0.f); c3p[k] = c2p[k];
+            ncen2[k] = pack2(-cen[k][0], -cen[k][D - 1]);
+        }
+    }
+    stage_wait(&bar, 0);                                        // rows landed; table and s_x visible
+
+    float acc[TE];
+#pragma unroll
+    for (int e = 0; e < TE; ++e) acc[e] = 0.f;
+    if (valid) {
+        const float* zr = s_z + (size_t)p * ZS;
+        for (int n = j; n < N; n += LANES) {
+            int lab = 0;
+            float best = zr[n * K];
+#pragma unroll
+            for (int k = 1; k < K; ++k) { const float v = zr[n * K + k]; if (v > best) { best = v; lab = k; } }
+            const float* t = s_tab + n * K + lab;
+#pragma unroll
+            for (int e = 0; e < TE; ++e) acc[e] = __fadd_rn(acc[e], t[e * NK]);
+            if (STATS) {
+                float ind[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) { ind[k] = (lab == k) ? 1.f : 0.f; c1[k] += ind[k]; }
+                if (D == 2) {
+                    f32x2 t = pack2(s_x[n * D], s_x[n * D + D - 1]);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) t = fma2(pack2(ind[k], ind[k]), ncen2[k], t);      // x - c_lab
+                    const f32x2 t2 = mul2(t, t);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const f32x2 ik = pack2(ind[k], ind[k]);
+                        c2p[k] = fma2(ik, t, c2p[k]);
+                        c3p[k] = fma2(ik, t2, c3p[k]);
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        float c = 0.f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) c = fmaf(ind[k], cen[k][d], c);
+                        const float t = s_x[n * D + d] - c, t2 = t * t;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { c2[k][d] = fmaf(ind[k], t, c2[k][d]); c3[k][d] = fmaf(ind[k], t2, c3[k][d]); }
+                    }
+                }
+            }
+        }
+    }
+    // ---- the LANES partials of a particle meet in shared memory (the z rows are no longer needed)
+    __syncthreads();
+    float* s_red = s_z;
+    float* mine = s_red + (size_t)threadIdx.x * RW;
+#pragma unroll
+    for (int e = 0; e < TE; ++e) mine[e] = acc[e];
+    __syncwarp();
+    double n1 = 0.0, n2 = 0.0, n3 = 0.0;
+    const bool fin = valid && j < KD;                            // lane e = (k, d) finishes one posterior element
+    if (fin) {
+        const int k = j / D;
+#pragma unroll
+        for (int i = 0; i < LANES; ++i) {
+            const float* o = s_red + (size_t)(p * LANES + i) * RW;
+            n1 += (double)o[k]; n2 += (double)o[K + j]; n3 += (double)o[K + KD + j];
+        }
+    }
+    if (STATS) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (D == 2) { unpack2(c2p[k], c2[k][0], c2[k][D - 1]); unpack2(c3p[k], c3[k][0], c3[k][D - 1]); }
+            mine[k * ST] = c1[k];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { mine[k * ST + 1 + d] = c2[k][d]; mine[k * ST + 1 + D + d] = c3[k][d]; }
+        }
+        __syncwarp();
+        if (valid) {
+            float* so = a.stats + r * NS;
+            for (int e = j; e < NS; e += LANES) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < LANES; ++i) v += s_red[(size_t)(p * LANES + i) * RW + e];
+                so[e] = v;
+            }
+        }
+    }
+    static_assert(KD <= LANES, "one posterior element per lane");
+    if (!fin) return;
+    {   // kls_gmm.py:110-118, fp32, reference order
+        const int e = j;
+        const float f1 = (float)n1, f2 = (float)n2, f3 = (float)n3;
+        const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
+        const float cnt = (f1 == 0.f) ? 1.f : f1;                                   // Q1
+        const float x_bar = __fdiv_rn(f2, cnt);
+        const float alpha = __fadd_rn(a0, __fdiv_rn(cnt, 2.f));
+        const float nu = __fadd_rn(n0, cnt);
+        const float cn = __fadd_rn(cnt, n0);
+        const float mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), f2), cn);
+        const float u1 = __fdiv_rn(__fsub_rn(f3, __fdiv_rn(__fmul_rn(f2, f2), cnt)), 2.f);
+        const float dx = __fsub_rn(x_bar, n0);                                       // Q2: prior_nu
+        const float u2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
+        const float beta = __fadd_rn(__fadd_rn(b0, u1), u2);
+        const long long o = r * KD + e;
+        a.oa[o] = alpha; a.ob[o] = beta; a.om[o] = mu; a.on[o] = nu;
+    }
+}
+
+// ============================================================================================
 // G2 / G3 / G4
 // ============================================================================================
 enum { STEP_ONESHOT = 0, STEP_ETA = 1, STEP_Z = 2, STEP_JOINT = 3 };
@@ -548,10 +765,29 @@ static int launch_eta_stats(const EtaStatsArgs& a, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------- launchers
-constexpr int kP = 32, kLanes = 8;
+
+template <int K, int D>
+static int launch_nss_im(const NssArgs& a, cudaStream_t st) {
+    constexpr int NS = K * (1 + 2 * D), TE = K + 2 * K * D;
+    constexpr int RW = (TE > NS ? TE : NS) | 1;
+    const long long S = a.R / a.B;
+    const size_t zreg = (max((size_t)kP * nss_im_zstride(a.N * K), (size_t)kP * kLanes * RW) + 3) / 4 * 4;
+    const size_t smem = (zreg + (size_t)a.N * K * TE + (size_t)a.N * D) * 4;
+    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_eta_posterior: N=%d too large for one tile", a.N);
+    void (*kern)(NssArgs, int) = a.stats != nullptr ? k_gmm_nss_im<K, D, kP, kLanes, true> : k_gmm_nss_im<K, D, kP, kLanes, false>;
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
+    const long long grid = (long long)a.B * ((S + kP - 1) / kP);
+    if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_eta_posterior: S*B too large for one launch");
+    kern<<<(unsigned int)grid, kP * kLanes, smem, st>>>(a, (int)S);
+    APGS_LAUNCH_OK("k_gmm_nss_im launch");
+    return 0;
+}
 
 template <int K, int D>
 static int launch_nss(const NssArgs& a, cudaStream_t st) {
+    if constexpr (K * D <= kLanes) {
+        if (a.gamma == nullptr && a.z != nullptr) return launch_nss_im<K, D>(a, st);
+    }
     size_t smem = (size_t)kP * a.N * (a.gamma == nullptr ? K : K + D) * 4;   // the fused variants only stage z
     if (a.stats != nullptr) smem = max(smem, (size_t)kP * kLanes * ((K * (1 + 2 * D)) | 1) * 4);
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_nss_posterior: N=%d too large for one tile", a.N);
