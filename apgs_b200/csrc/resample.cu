@@ -431,7 +431,7 @@ __device__ __forceinline__ void gather_block(const GLat& L, const GatherArgs& g,
     }
 #pragma unroll
     for (int k = 0; k < kGUnroll; ++k)
-        if (so[k] >= 0) val[k] = __ldcs(src + so[k]);
+        if (so[k] >= 0) val[k] = __ldg(src + so[k]);
 #pragma unroll
     for (int k = 0; k < kGUnroll; ++k) {
         unsigned int t = t0 + k * kGThreads + threadIdx.x;
