@@ -283,12 +283,15 @@ def resample_probe(S, B, dev, iters=10):
     u = r.draw_uniforms(S, B, dev)
     anc = ops.sample_ancestors(log_w=lw, strategy='systematic', uniforms=u, index_dtype=torch.int32)
 
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
     def med(fn):
         for _ in range(3):
             fn()
         ts = []
         for _ in range(iters):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()        # evicts L2 and keeps the GPU busy while the host enqueues (no launch gap inside the events)
             e0.record()
             fn()
             e1.record()

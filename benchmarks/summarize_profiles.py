@@ -58,7 +58,9 @@ with open(os.path.join(PR, "%s_ncu_kernels.md" % tag), "w") as f:
     seen = set()
     for r in body:
         name = r[hdr.index("Kernel Name")]
-        key = (name, r[hdr.index("gpu__time_duration.sum")][:3])
+        if name in seen:                      # one capture per kernel (the first after the skipped warm-up launches)
+            continue
+        seen.add(name)
         f.write("## `%s`\n\n| metric | value |\n|---|---|\n" % name)
         for m, label in want:
             if m in hdr:
