@@ -256,7 +256,13 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": "particle-sweeps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": res_host.numel() * 8, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "roofline": roof,
-                "kernels": {k: {"calls": v["calls"], "ms_avg": round(v["ms_avg"], 4), "alg_GBs": round(v["gbs"], 1)}
+                # every C-ABI call of one profiled step: share of the step's kernel time, algorithmic GB/s and its fraction
+                # of the HBM peak.  gmm_z_step_fused (the largest share) is NOT an HBM-bound kernel: its inner loop sits at
+                # the FP32 FMA-pipe bound, so its hbm fraction is low by construction; the roofline
+                # object above is the gather, the HBM-bound kernel of the resample step the metric is about.
+                "kernels": {k: {"calls": v["calls"], "ms_avg": round(v["ms_avg"], 4), "alg_GBs": round(v["gbs"], 1),
+                                "frac_hbm": round(v["gbs"] / peak, 3),
+                                "share": round(v["calls"] * v["ms_avg"] / max(1e-9, sum(q["calls"] * q["ms_avg"] for q in prof.values())), 3)}
                             for k, v in sorted(prof.items())},
                 "final_metrics": {"ess_last": float(final['ess'][-1]), "density_last": float(final['density'][-1])}}
         if world == 1 and not args.no_cpu_baseline:
