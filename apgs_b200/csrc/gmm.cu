@@ -35,6 +35,8 @@ struct NssArgs {
     // from which the eta-step log-likelihoods follow in O(K D) per particle (k_gmm_eta_weights_stats)
     const float* center;
     float* stats;         // (R, K, 1 + 2 D)
+    const unsigned char* zl;   // (R, N) labels instead of the one-hot z (compact latents inside a sweep), or null
+    long long LN;              // bytes between the label rows of consecutive particles (>= N)
 };
 
 template <int K, int D, int P, int LANES, bool FUSED, bool HAS_Z, bool STATS = false>
@@ -281,12 +283,16 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     const long long r = (long long)(s0 + p) * a.B + b;
     const int rows = min(P, S - s0);
     const unsigned int rb = (unsigned int)NK * 4u;
-    const bool bulk_in = (rb & 15u) == 0 && aligned(a.z, 16);
+    const bool labels = a.zl != nullptr;
+    const bool bulk_in = !labels && (rb & 15u) == 0 && aligned(a.z, 16);
+    unsigned char* s_lab = reinterpret_cast<unsigned char*>(s_z);       // [P][N] in label mode (the z region is free then)
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows : 0u);
     if (valid) {
-        if (bulk_in) {
+        if (labels) {
+            for (int i = j; i < N; i += LANES) s_lab[(size_t)p * N + i] = __ldg(a.zl + r * a.LN + i);
+        } else if (bulk_in) {
             if (j == 0) bulk_g2s(s_z + (size_t)p * ZS, a.z + r * NK, rb, &bar);
         } else {
             for (int i = j; i < NK; i += LANES) s_z[(size_t)p * ZS + i] = __ldg(a.z + r * NK + i);
@@ -362,9 +368,13 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
         const float* zr = s_z + (size_t)p * ZS;
         for (int n = j; n < N; n += LANES) {
             int lab = 0;
-            float best = zr[n * K];
+            if (labels) {
+                lab = min((int)s_lab[(size_t)p * N + n], K - 1);
+            } else {
+                float best = zr[n * K];
 #pragma unroll
-            for (int k = 1; k < K; ++k) { const float v = zr[n * K + k]; if (v > best) { best = v; lab = k; } }
+                for (int k = 1; k < K; ++k) { const float v = zr[n * K + k]; if (v > best) { best = v; lab = k; } }
+            }
             const float* t = s_tab + n * K + lab;
 #pragma unroll
             for (int e = 0; e < TE; ++e) acc[e] = __fadd_rn(acc[e], t[e * NK]);
@@ -786,7 +796,7 @@ static int launch_nss_im(const NssArgs& a, cudaStream_t st) {
 template <int K, int D>
 static int launch_nss(const NssArgs& a, cudaStream_t st) {
     if constexpr (K * D <= kLanes) {
-        if (a.gamma == nullptr && a.z != nullptr) return launch_nss_im<K, D>(a, st);
+        if (a.gamma == nullptr && (a.z != nullptr || a.zl != nullptr)) return launch_nss_im<K, D>(a, st);
     }
     size_t smem = (size_t)kP * a.N * (a.gamma == nullptr ? K : K + D) * 4;   // the fused variants only stage z
     if (a.stats != nullptr) smem = max(smem, (size_t)kP * kLanes * ((K * (1 + 2 * D)) | 1) * 4);
@@ -991,4 +1001,32 @@ extern "C" int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* cent
     cudaStream_t st = (cudaStream_t)stream;
     APGS_KD_DISPATCH(K, D, launch_eta_stats);
     return fail(APGS_E_UNSUPPORTED, "gmm_logw_eta_stats: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
+}
+
+extern "C" int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels, const float* Wg,
+                                                       const float* bg, const float* Wo, const float* bo, int64_t S,
+                                                       int64_t B, int64_t N, int64_t K, int64_t D,
+                                                       const float* prior_alpha, const float* prior_beta,
+                                                       const float* prior_mu, const float* prior_nu, float* post_alpha,
+                                                       float* post_beta, float* post_mu, float* post_nu,
+                                                       const float* center, float* stats, int64_t label_stride,
+                                                       void* stream) {
+    if (int e = check_gmm_dims(S, B, N, K, D, "gmm_eta_posterior_stats_labels")) return e;
+    if (label_stride < N) return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels: label_stride %lld < N", (long long)label_stride);
+    if (!x || !z_labels || !Wg || !bg || !Wo || !bo || !prior_alpha || !prior_beta || !prior_mu || !prior_nu ||
+        !post_alpha || !post_beta || !post_mu || !post_nu)
+        return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels: NULL pointer");
+    if ((center == nullptr) != (stats == nullptr))
+        return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels: center and stats go together");
+    if (K * D > kLanes) return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats_labels: K*D <= %d supported", kLanes);
+    NssArgs a = {};
+    a.x = x; a.zl = z_labels; a.LN = label_stride; a.Wg = Wg; a.bg = bg; a.Wo = Wo; a.bo = bo;
+    a.ra = prior_alpha; a.rb = prior_beta; a.rm = prior_mu; a.rn = prior_nu;
+    a.oa = post_alpha; a.ob = post_beta; a.om = post_mu; a.on = post_nu;
+    a.center = center; a.stats = stats;
+    a.R = (long long)S * B; a.N = (int)N; a.B = (int)B;
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_nss);
+    return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats_labels: (K=%lld, D=%lld) not instantiated", (long long)K,
+                (long long)D);
 }

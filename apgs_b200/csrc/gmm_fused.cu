@@ -23,6 +23,10 @@ struct ZFusedArgs {
     const float* z_old;             // (R, N, K) one-hot, or null (sample-only mode)
     const float* z_forced;          // (R, N, K) one-hot to use instead of sampling, or null
     const float* u;                 // (R, N) uniforms in [0,1), required unless z_forced
+    // label mode (compact latents inside a sweep): assignments as one byte per point instead of K one-hot floats
+    const unsigned char* zl_old;    // (R, N) labels of the backward term, or null
+    unsigned char* zl_new;          // (R, N) labels out, or null (then z_new one-hot is written)
+    long long LN;                   // bytes between the label rows of consecutive particles (>= N)
     const float* rpi;               // (K)
     int S, B, N, H;
     float* z_new;                   // (R, N, K) out
@@ -108,9 +112,11 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const int nIt = (N + LANES * PB - 1) / (LANES * PB);       // passes of 32 points
     const int EXS = nIt * LANES * PB;                          // floats of Ex per hidden unit
     const int EPs = H * KP + 4;                                // per-particle stride of the Ee table (floats)
-    const bool has_bwd = a.z_old != nullptr;
+    const bool lab_old = a.zl_old != nullptr, lab_new = a.zl_new != nullptr;
+    const bool has_bwd = a.z_old != nullptr || lab_old;
     const bool forced = a.z_forced != nullptr;
-    const size_t tile_f = ((size_t)P * NK + 3) / 4 * 4;
+    const bool tiles = a.z_old != nullptr || forced || !lab_new;          // any one-hot row staged in / out?
+    const size_t tile_f = tiles ? ((size_t)P * NK + 3) / 4 * 4 : 0;
     float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
     float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
     float* s_ex = s_zn + tile_f;                               // H * EXS, slot order inside a quad: q0 q2 q1 q3
@@ -126,19 +132,20 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const int rows = min(P, a.S - s0);
     const unsigned int rb = (unsigned int)NK * 4u;
     // a row goes through the bulk-copy engine when its size keeps every row 16-byte aligned
-    const bool bulk_in = (rb & 15u) == 0 && (!has_bwd || aligned(a.z_old, 16)) && (!forced || aligned(a.z_forced, 16));
+    const bool old_tile = a.z_old != nullptr;
+    const bool bulk_in = (rb & 15u) == 0 && (!old_tile || aligned(a.z_old, 16)) && (!forced || aligned(a.z_forced, 16));
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows * ((has_bwd ? 1u : 0u) + (forced ? 1u : 0u)) : 0u);
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows * ((old_tile ? 1u : 0u) + (forced ? 1u : 0u)) : 0u);
     if (valid) {
         if (bulk_in) {
             if (j == 0) {
-                if (has_bwd) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + r * NK, rb, &bar);
+                if (old_tile) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + r * NK, rb, &bar);
                 if (forced) bulk_g2s(s_zn + (size_t)p * NK, a.z_forced + r * NK, rb, &bar);
             }
         } else {
             for (int i = j; i < NK; i += LANES) {
-                if (has_bwd) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + r * NK + i);
+                if (old_tile) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + r * NK + i);
                 if (forced) s_zn[(size_t)p * NK + i] = __ldg(a.z_forced + r * NK + i);
             }
         }
@@ -275,16 +282,20 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     if (valid) {
         const float* zo = s_zo + (size_t)p * NK;
         float* zn = s_zn + (size_t)p * NK;
+        const unsigned char* zlo = a.zl_old + r * a.LN;          // label rows of this particle (label mode)
+        unsigned char* zln = a.zl_new + r * a.LN;
         const float* tab = s_tab + (size_t)p * (KD * 3);
         for (int it = 0; it < nIt; ++it) {
             const int n0 = it * (LANES * PB) + j;
             float xv[PB][D], logit[PB][K], uq[PB];
+            int lbq[PB];
 #pragma unroll
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
 #pragma unroll
                 for (int d = 0; d < D; ++d) xv[q][d] = (n < N) ? __ldg(xb + n * D + d) : 0.f;
                 uq[q] = (n < N && !forced) ? __ldg(a.u + r * N + n) : 0.f;      // in flight during the MLP
+                lbq[q] = (n < N && lab_old) ? (int)__ldg(zlo + n) : 0;
             }
             // ---- the MLP: hidden unit h for 4 points x K clusters at a time; points are paired as (0,2) and (1,3)
             if (fast) {
@@ -335,9 +346,12 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                     float c = 0.f;
 #pragma unroll
                     for (int k = 0; k < K - 1; ++k) { c = __fadd_rn(c, pr[k]); lf += (t >= c) ? 1 : 0; }
+                    if (!lab_new) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) zn[n * K + k] = (k == lf) ? 1.f : 0.f;
+                        for (int k = 0; k < K; ++k) zn[n * K + k] = (k == lf) ? 1.f : 0.f;
+                    }
                 }
+                if (lab_new) zln[n] = (unsigned char)lf;
                 float plf = pr[0], lpf = logpi[0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) if (lf == k) { plf = pr[k]; lpf = logpi[k]; }
@@ -351,10 +365,12 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 }
                 A_llf.add(llf); A_lqzf.add(lqf); A_lpzf.add(lpf);
                 if (has_bwd) {
-                    int lb = 0;
-                    float best = zo[n * K];
+                    int lb = lbq[q];
+                    if (!lab_old) {
+                        float best = zo[n * K];
 #pragma unroll
-                    for (int k = 1; k < K; ++k) { const float v = zo[n * K + k]; if (v > best) { best = v; lb = k; } }
+                        for (int k = 1; k < K; ++k) { const float v = zo[n * K + k]; if (v > best) { best = v; lb = k; } }
+                    }
                     float plb = pr[0], lpb = logpi[0];
 #pragma unroll
                     for (int k = 1; k < K; ++k) if (lb == k) { plb = pr[k]; lpb = logpi[k]; }
@@ -390,7 +406,8 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         if (a.log_q_f != nullptr) a.log_q_f[r] = lqz_f;
         if (a.dens != nullptr) a.dens[r] = __fadd_rn(ll_f, lpz_f);
     }
-    // ---- z_new rows out (one bulk store per particle row)
+    // ---- z_new rows out (one bulk store per particle row); nothing to do in label mode
+    if (a.z_new == nullptr) return;
     const bool bulk_out = (rb & 15u) == 0 && aligned(a.z_new, 16);
     if (bulk_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
@@ -415,7 +432,8 @@ template <int K, int D>
 static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     constexpr int KP = ((K + 1) + 3) / 4 * 4;
     const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
-    const size_t tile_f = ((size_t)kFP * a.N * K + 3) / 4 * 4;
+    const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.zl_new == nullptr;
+    const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
     const size_t smem = (2 * tile_f + (size_t)a.H * nIt * kFLanes * kFPB + (size_t)kFP * (a.H * KP + 4) +
                          (size_t)(a.H + 3) / 4 * 4 + (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
@@ -432,22 +450,24 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
 
 using namespace apgs;
 
-extern "C" int apgs_gmm_z_step_fused_f32(const float* x, const float* tau, const float* mu, const float* W1,
-                                         const float* b1, const float* W2, const float* b2, int64_t H,
-                                         const apgs_gmm_prior_t* prior, const float* z_old, const float* z_forced,
-                                         const float* uniforms, int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
-                                         float* z_new, float* q_probs, const apgs_gmm_out_t* out, void* stream) {
+static int z_step_fused(const float* x, const float* tau, const float* mu, const float* W1, const float* b1,
+                        const float* W2, const float* b2, int64_t H, const apgs_gmm_prior_t* prior, const float* z_old,
+                        const unsigned char* z_old_lab, const float* z_forced, const float* uniforms, int64_t S,
+                        int64_t B, int64_t N, int64_t K, int64_t D, float* z_new, unsigned char* z_new_lab,
+                        int64_t label_stride, float* q_probs, const apgs_gmm_out_t* out, void* stream) {
     if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024)
         return fail(APGS_E_SHAPE, "gmm_z_step_fused: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S, (long long)B,
                     (long long)N, (long long)H);
-    if (!x || !tau || !mu || !W1 || !b1 || !W2 || !b2 || !prior || !prior->pi || !z_new)
+    if (!x || !tau || !mu || !W1 || !b1 || !W2 || !b2 || !prior || !prior->pi || (!z_new && !z_new_lab))
         return fail(APGS_E_BADARG, "gmm_z_step_fused: NULL input");
     if (!z_forced && !uniforms) return fail(APGS_E_BADARG, "gmm_z_step_fused: uniforms (or z_forced) required");
+    if (z_old && z_old_lab) return fail(APGS_E_BADARG, "gmm_z_step_fused: give z_old either one-hot or as labels, not both");
+    if (K > 255) return fail(APGS_E_SHAPE, "gmm_z_step_fused: K=%lld does not fit a label byte", (long long)K);
     ZFusedArgs a = {};
     a.x = x; a.tau = tau; a.mu = mu; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
-    a.z_old = z_old; a.z_forced = z_forced; a.u = uniforms; a.rpi = prior->pi;
+    a.z_old = z_old; a.zl_old = z_old_lab; a.z_forced = z_forced; a.u = uniforms; a.rpi = prior->pi;
     a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
-    a.z_new = z_new; a.q_probs = q_probs;
+    a.z_new = z_new; a.zl_new = z_new_lab; a.LN = label_stride; a.q_probs = q_probs;
     if (out) {
         a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;
         a.log_w_b = out->log_w_b; a.lw_local = out->log_w_local; a.lq_local = out->log_q_local;
@@ -459,4 +479,25 @@ extern "C" int apgs_gmm_z_step_fused_f32(const float* x, const float* tau, const
     if (K == 5 && D == 2) return launch_zfused<5, 2>(a, st);
     if (K == 3 && D == 3) return launch_zfused<3, 3>(a, st);
     return fail(APGS_E_UNSUPPORTED, "gmm_z_step_fused: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
+}
+
+extern "C" int apgs_gmm_z_step_fused_f32(const float* x, const float* tau, const float* mu, const float* W1,
+                                         const float* b1, const float* W2, const float* b2, int64_t H,
+                                         const apgs_gmm_prior_t* prior, const float* z_old, const float* z_forced,
+                                         const float* uniforms, int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                         float* z_new, float* q_probs, const apgs_gmm_out_t* out, void* stream) {
+    return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, z_old, nullptr, z_forced, uniforms, S, B, N, K, D, z_new,
+                        nullptr, N, q_probs, out, stream);
+}
+
+extern "C" int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau, const float* mu, const float* W1,
+                                                const float* b1, const float* W2, const float* b2, int64_t H,
+                                                const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels,
+                                                const float* uniforms, int64_t S, int64_t B, int64_t N, int64_t K,
+                                                int64_t D, uint8_t* z_new_labels, int64_t label_stride,
+                                                float* q_probs, const apgs_gmm_out_t* out, void* stream) {
+    if (!z_new_labels) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels: z_new_labels is NULL");
+    if (label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels: label_stride %lld < N", (long long)label_stride);
+    return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, nullptr, z_old_labels, nullptr, uniforms, S, B, N, K, D,
+                        nullptr, z_new_labels, label_stride, q_probs, out, stream);
 }

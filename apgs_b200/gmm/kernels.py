@@ -168,6 +168,27 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     if tuple(W1.shape) != (H, 3 * D) or W2.numel() != H or b1.numel() != H or b2.numel() != 1:
         raise ValueError("unexpected Enc_apg_z weight shapes")
     dev = tau.device
+    labels = z_old is not None and z_old.dtype == torch.uint8
+    if labels:
+        # label mode: assignments as one byte per point, in and out (compact latents inside a sweep)
+        if z_forced is not None:
+            raise ValueError("label mode samples from uniforms; z_forced needs the one-hot entry")
+        z_old = _req(z_old, "z_old labels", dtype=torch.uint8, ndim=3)
+        LN = z_old.shape[-1]                              # label rows may be padded (16-byte gather vectors)
+        if tuple(z_old.shape[:2]) != (S, B) or LN < N:
+            raise ValueError("z_old labels have shape %s, expected (%d,%d,>=%d)" % (tuple(z_old.shape), S, B, N))
+        uniforms = torch.rand(S, B, N, device=dev) if uniforms is None else _req(uniforms, "uniforms", ndim=3)
+        z_new = torch.empty(S, B, LN, dtype=torch.uint8, device=dev)
+        q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
+        rs, rk = _prior_struct(prior)
+        w, o = _outs(S, B, N, dev, parts, local)
+        nbytes = S * B * (2 * N + 4 * (N + 2 * K * D + 3 + (N * K if want_q else 0)))
+        with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes):
+            check(lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
+                                                       C.byref(rs), ptr(z_old), ptr(uniforms), S, B, N, K, D,
+                                                       ptr(z_new), LN, ptr(q), C.byref(o), _stream()),
+                  "apgs_gmm_z_step_fused_labels_f32")
+        return z_new, q, w
     if z_old is not None:
         z_old = _req(z_old, "z_old", ndim=4)
     if z_forced is not None:
@@ -198,6 +219,27 @@ def eta_posterior_fused(x, z, heads, prior, center=None):
     B, N, D = x.shape
     Wg, bg, Wo, bo = [_req(v, "head weight") for v in heads]
     K = Wg.shape[0]
+    if z is not None and z.dtype == torch.uint8:
+        # label mode: z (S,B,N) uint8
+        z = _req(z, "z labels", dtype=torch.uint8, ndim=3)
+        S, LN = z.shape[0], z.shape[-1]
+        if z.shape[1] != B or LN < N:
+            raise ValueError("z labels have shape %s, expected (S,%d,>=%d)" % (tuple(z.shape), B, N))
+        if tuple(Wg.shape) != (K, D + K) or tuple(Wo.shape) != (D, D + K):
+            raise ValueError("unexpected head weight shapes %s %s" % (tuple(Wg.shape), tuple(Wo.shape)))
+        pr = [_req(getattr(prior, "prior_" + n), "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
+        outs = [torch.empty(S, B, K, D, dtype=torch.float32, device=x.device) for _ in range(4)]
+        stats = None
+        if center is not None:
+            center = _req(center, "center", ndim=4)
+            if tuple(center.shape) != (S, B, K, D):
+                raise ValueError("center has shape %s, expected %s" % (tuple(center.shape), (S, B, K, D)))
+            stats = torch.empty(S, B, K, 1 + 2 * D, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device), _call("gmm_eta_posterior_stats", 1, S * B * (N + 4 * (6 * K * D + K * (1 + 2 * D)))):
+            check(lib.apgs_gmm_eta_posterior_stats_labels_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
+                                                              *[ptr(v) for v in pr], *[ptr(v) for v in outs], ptr(center),
+                                                              ptr(stats), LN, _stream()), "apgs_gmm_eta_posterior_stats_labels_f32")
+        return tuple(outs) + ((stats,) if stats is not None else ())
     if z is not None:
         z = _req(z, "z", ndim=4)
         S = z.shape[0]

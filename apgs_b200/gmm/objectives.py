@@ -57,6 +57,14 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     if x.dim() == 3:
         x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)       # stride-0 S axis; never materialised
     log_w, tau, mu, z, trace = oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags)
+    if _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, z):
+        # Inside the sweeps the assignments never need their one-hot (S,B,N,K) fp32 form (the objective returns only
+        # the trace): carry them as one byte per point.  The two per-sweep kernels take / return labels, and the z row
+        # every resampling gather moves shrinks from 4*K*N to N bytes (720 -> 60 B for the GMM shapes).
+        z = z.argmax(-1).to(torch.uint8)
+        pad = (-z.shape[-1]) % 16                       # 16-byte rows: the gather moves them as 16-byte vectors
+        if pad:
+            z = torch.nn.functional.pad(z, (0, pad))
     tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
     for m in range(num_sweeps - 1):
         if block == 'decomposed':
@@ -80,6 +88,20 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     if result_flags['density_required']:
         trace['density'] = torch.cat(trace['density'], 0)
     return trace
+
+
+compact_labels = True          # module switch (tests compare both representations)
+
+
+def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, z):
+    K, D = z.shape[-1], generative_dims(enc_apg_eta)
+    return (compact_labels and block == 'decomposed' and not result_flags['loss_required']
+            and enc_apg_z.can_fuse(False) and getattr(enc_apg_eta, 'fused', False) and K <= 255 and K * D <= 8)
+
+
+def generative_dims(enc_apg_eta):
+    """data dimension D from the Enc_apg_eta heads (ob: Linear(K + D, D))."""
+    return enc_apg_eta.ob[0].weight.shape[0]
 
 
 def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):

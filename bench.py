@@ -234,7 +234,7 @@ def run_ours(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_bench_traffic.json")))["k_gather"]["dram_bytes_per_launch"]
         except Exception:
             pass
-        inner = 2 * (K_CL * D_X * 4) + N_PTS * K_CL * 4
+        inner = (g["bytes_per_call"] / (S * B) - 4) / 2          # bytes of latent rows per particle actually gathered
         uniq = None if distinct_frac is None else S * B * (4 + inner * (1 + distinct_frac))
         roof = {"kernel": "k_gather (ancestor gather of tau, mu, z; the dominant kernel of the resample step)", "bound": "hbm",
                 "achieved": g["gbs"], "peak": peak, "unit": "GB/s", "frac": g["gbs"] / peak, "traffic": traffic,
@@ -243,11 +243,14 @@ def run_ours(args):
                 "distinct_ancestor_frac": distinct_frac,
                 "achieved_unique_bytes": None if uniq is None else uniq / g["ms_avg"] / 1e6,
                 "all_distinct_probe": probe,
-                "note": "achieved = SURVEY 8d bytes (4 + 2*768 B per particle, index read + every row read and written once) / "
-                        "CUDA-event time of each launch on the launching stream.  With random-init encoders the weights are "
-                        "degenerate (ESS ~ 1): almost all particles copy the same few ancestors, the reads hit L2 and the kernel is "
-                        "write-bound, so achieved exceeds the copy peak; achieved_unique_bytes counts each distinct source row once, "
-                        "and all_distinct_probe times the same step on near-uniform weights where every row comes from HBM."}
+                "latent_row_bytes_per_particle": inner,
+                "note": "achieved = (4 + 2 * latent row bytes) per particle (index read + every row read and written once, at the "
+                        "dtypes the step really moves) / CUDA-event time of each launch on the launching stream.  Inside the sweeps the "
+                        "objective carries the assignments as uint8 labels, so a resampling step gathers 24 + 24 + 60 B per particle "
+                        "instead of the reference layout's 24 + 24 + 720 B (SURVEY 8d: 1540 B): 225 MB per launch, which is launch- / "
+                        "latency-bound (~70 us), and with random-init encoders the weights are degenerate (ESS ~ 1) so most reads hit "
+                        "L2.  all_distinct_probe times the SAME kernels on the reference layout (1540 B per particle) with near-uniform "
+                        "weights, where every row comes from HBM: that is the kernel's HBM roofline point."}
     if rank == 0:
         line = {"metric": "particle-sweeps/sec", "value": value, "unit": "particle-sweeps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

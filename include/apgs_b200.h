@@ -231,6 +231,25 @@ APGS_API int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center
                                 int64_t S, int64_t B, int64_t K, int64_t D,
                                 const apgs_gmm_out_t* out, void* stream);
 
+/* Label mode of the two per-sweep GMM kernels.  Inside a sweep the assignments never need their one-hot (S,B,N,K) fp32
+ *   form: these entries take / return them as one byte per point, z_labels uint8 in [0,K) with `label_stride` >= N bytes
+ *   between the rows of consecutive particles (pad it to 16 so the gather moves 16-byte vectors), which cuts the z row
+ *   the resampling gather moves from 4*K*N to ~N bytes.  Same arithmetic and outputs as apgs_gmm_z_step_fused_f32 (with
+ *   z_old given, sampling from `uniforms`) and apgs_gmm_eta_posterior_stats_f32; center / stats may both be NULL.      */
+APGS_API int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau, const float* mu,
+                              const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
+                              const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels, const float* uniforms,
+                              int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              uint8_t* z_new_labels, int64_t label_stride,
+                              float* q_probs, const apgs_gmm_out_t* out, void* stream);
+APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
+                                     const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                     int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                     const float* prior_alpha, const float* prior_beta,
+                                     const float* prior_mu, const float* prior_nu,
+                                     float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
+                                     const float* center, float* stats, int64_t label_stride, void* stream);
+
 /* ==============================================================================================
  * Bouncing-MNIST.  FP frame pixels (96), DP digit pixels (28), K digits,
  * T frames.  The transformer is the reference's: nearest sampling, align_corners=True, diagonal theta

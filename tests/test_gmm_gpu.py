@@ -630,3 +630,65 @@ def test_N4_gibbs_and_bpg_objectives_match_reference_traces_statistically(golden
         for m in range(sweeps):
             se = (a[m].var() / a.shape[1] + b[m].var() / B).sqrt()
             assert abs(float(a[m].mean() - b[m].mean())) < 6 * float(se) + 1e-3 * abs(float(b[m].mean())), (name, m)
+
+
+# ------------------------------------------------------------------ compact labels inside a sweep
+@pytest.mark.parametrize("S,B,N,K,D,H", [(37, 5, 60, 3, 2, 32), (9, 3, 41, 4, 2, 16), (33, 2, 9, 3, 2, 8)])
+def test_label_mode_equals_one_hot_mode_bit_for_bit(S, B, N, K, D, H):
+    """the label entries (z as one byte per point) give exactly the outputs of the one-hot entries on the same inputs
+    and uniforms: z step (draw, weights, density, q_probs) and eta posterior + statistics."""
+    from apgs_b200.gmm import kernels
+    torch.manual_seed(S + N)
+    P = og.make_params(K, D, H)
+    gen = _Gen(K, D)
+    x = (torch.randn(B, N, D) * 2).to(DEV)
+    tau, mu = (torch.rand(S, B, K, D) * 3 + 0.1).to(DEV), (torch.randn(S, B, K, D) * 2).to(DEV)
+    lab_old = torch.randint(0, K, (S, B, N), dtype=torch.uint8, device=DEV)
+    z_old = torch.nn.functional.one_hot(lab_old.long(), K).float()
+    u = torch.rand(S, B, N, device=DEV)
+    mlp = [P["enc_apg_z"][k].to(DEV) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+    z1, q1, w1 = kernels.z_step_fused(x, tau, mu, mlp, gen, z_old=z_old, uniforms=u, want_q=True, parts=True, local=True)
+    z2, q2, w2 = kernels.z_step_fused(x, tau, mu, mlp, gen, z_old=lab_old, uniforms=u, want_q=True, parts=True, local=True)
+    assert z2.dtype == torch.uint8 and tuple(z2.shape) == (S, B, N)
+    assert torch.equal(z1.argmax(-1), z2.long()) and torch.equal(q1, q2)
+    for name in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b", "log_w_local", "log_q_local"):
+        assert torch.equal(getattr(w1, name), getattr(w2, name)), name
+    heads = [P["enc_apg_eta"][k].to(DEV) for k in ("gamma.0.weight", "gamma.0.bias", "ob.0.weight", "ob.0.bias")]
+    a = kernels.eta_posterior_fused(x, z_old, heads, gen, center=mu)
+    b = kernels.eta_posterior_fused(x, lab_old, heads, gen, center=mu)
+    assert len(a) == len(b) == 5
+    for t1, t2 in zip(a, b):
+        assert torch.equal(t1, t2)
+    c = kernels.eta_posterior_fused(x, lab_old, heads, gen)
+    assert len(c) == 4 and all(torch.equal(t1, t2) for t1, t2 in zip(a[:4], c))
+    # label rows padded to 16 bytes (what the objective carries, so that the gather moves 16-byte vectors)
+    LN = (N + 15) // 16 * 16
+    lab_pad = torch.full((S, B, LN), 255, dtype=torch.uint8, device=DEV)
+    lab_pad[..., :N] = lab_old
+    z3, q3, w3 = kernels.z_step_fused(x, tau, mu, mlp, gen, z_old=lab_pad, uniforms=u, want_q=True)
+    assert tuple(z3.shape) == (S, B, LN) and torch.equal(z3[..., :N], z2) and torch.equal(q3, q2) and torch.equal(w3.log_w, w2.log_w)
+    d = kernels.eta_posterior_fused(x, lab_pad, heads, gen, center=mu)
+    assert all(torch.equal(t1, t2) for t1, t2 in zip(b, d))
+
+
+def test_objective_with_compact_labels_matches_one_hot_objective():
+    """same seed, same draws: the whole decomposed objective gives identical traces with z carried as labels or one-hot."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B, sweeps = 64, 24, 4
+    torch.manual_seed(0)
+    models = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    flags = {"loss_required": False, "ess_required": True, "mode_required": True, "density_required": True}
+    out = {}
+    for compact in (True, False):
+        O.compact_labels = compact
+        try:
+            torch.manual_seed(5)
+            with torch.no_grad():
+                out[compact] = O.apg_objective(models, x, flags, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
+        finally:
+            O.compact_labels = True
+    for k in ("ess", "density", "E_z", "E_tau", "E_mu"):
+        assert torch.equal(out[True][k], out[False][k]), k
