@@ -93,7 +93,7 @@ SIGNATURES = {
     "apgs_gmm_eta_posterior_stats_labels_f32": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64,
                                                        _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "apgs_gmm_z_step_fused_labels_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p,
-                                                _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _OUT, _p]),
+                                                _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _OUT, _p]),
     "apgs_gmm_logw_eta_stats_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_z_step_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p, _p,
                                          _i64, _i64, _i64, _i64, _i64, _p, _p, _OUT, _p]),

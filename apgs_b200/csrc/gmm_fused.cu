@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const bool lab_old = a.zl_old != nullptr, lab_new = a.zl_new != nullptr;
     const bool has_bwd = a.z_old != nullptr || lab_old;
     const bool forced = a.z_forced != nullptr;
-    const bool tiles = a.z_old != nullptr || forced || !lab_new;          // any one-hot row staged in / out?
+    const bool hot_new = a.z_new != nullptr;                               // one-hot z_new wanted (labels may come along)
+    const bool tiles = a.z_old != nullptr || forced || hot_new;           // any one-hot row staged in / out?
     const size_t tile_f = tiles ? ((size_t)P * NK + 3) / 4 * 4 : 0;
     float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
     float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                     float c = 0.f;
 #pragma unroll
                     for (int k = 0; k < K - 1; ++k) { c = __fadd_rn(c, pr[k]); lf += (t >= c) ? 1 : 0; }
-                    if (!lab_new) {
+                    if (hot_new) {
 #pragma unroll
                         for (int k = 0; k < K; ++k) zn[n * K + k] = (k == lf) ? 1.f : 0.f;
                     }
@@ -432,7 +433,7 @@ template <int K, int D>
 static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     constexpr int KP = ((K + 1) + 3) / 4 * 4;
     const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
-    const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.zl_new == nullptr;
+    const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
     const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
     const size_t smem = (2 * tile_f + (size_t)a.H * nIt * kFLanes * kFPB + (size_t)kFP * (a.H * KP + 4) +
                          (size_t)(a.H + 3) / 4 * 4 + (size_t)kFP * K * D * 3) * 4;
@@ -495,9 +496,10 @@ extern "C" int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau
                                                 const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels,
                                                 const float* uniforms, int64_t S, int64_t B, int64_t N, int64_t K,
                                                 int64_t D, uint8_t* z_new_labels, int64_t label_stride,
-                                                float* q_probs, const apgs_gmm_out_t* out, void* stream) {
+                                                float* z_new_onehot, float* q_probs, const apgs_gmm_out_t* out,
+                                                void* stream) {
     if (!z_new_labels) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels: z_new_labels is NULL");
     if (label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels: label_stride %lld < N", (long long)label_stride);
     return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, nullptr, z_old_labels, nullptr, uniforms, S, B, N, K, D,
-                        nullptr, z_new_labels, label_stride, q_probs, out, stream);
+                        z_new_onehot, z_new_labels, label_stride, q_probs, out, stream);
 }

@@ -155,9 +155,11 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
 
 
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
-                 parts=False, local=False):
+                 parts=False, local=False, also_labels=0):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
-    mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights)."""
+    mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
+    z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
+    also_labels = row stride (>= N): sample-only call that returns ((z_new one-hot, labels), q_probs, Weights)."""
     lib = _lib.load()
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -168,6 +170,22 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     if tuple(W1.shape) != (H, 3 * D) or W2.numel() != H or b1.numel() != H or b2.numel() != 1:
         raise ValueError("unexpected Enc_apg_z weight shapes")
     dev = tau.device
+    if also_labels:
+        if z_old is not None or z_forced is not None:
+            raise ValueError("also_labels is a sample-only mode")
+        LN = int(also_labels)
+        uniforms = torch.rand(S, B, N, device=dev) if uniforms is None else _req(uniforms, "uniforms", ndim=3)
+        z_hot = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
+        z_lab = torch.empty(S, B, LN, dtype=torch.uint8, device=dev)
+        q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
+        rs, rk = _prior_struct(prior)
+        w, o = _outs(S, B, N, dev, False, False)
+        with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, S * B * (LN + 4 * (N * K + N + 2 * K * D + (N * K if want_q else 0)))):
+            check(lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
+                                                       C.byref(rs), None, ptr(uniforms), S, B, N, K, D,
+                                                       ptr(z_lab), LN, ptr(z_hot), ptr(q), C.byref(o), _stream()),
+                  "apgs_gmm_z_step_fused_labels_f32")
+        return (z_hot, z_lab), q, w
     labels = z_old is not None and z_old.dtype == torch.uint8
     if labels:
         # label mode: assignments as one byte per point, in and out (compact latents inside a sweep)
@@ -186,7 +204,7 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
         with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes):
             check(lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
                                                        C.byref(rs), ptr(z_old), ptr(uniforms), S, B, N, K, D,
-                                                       ptr(z_new), LN, ptr(q), C.byref(o), _stream()),
+                                                       ptr(z_new), LN, None, ptr(q), C.byref(o), _stream()),
                   "apgs_gmm_z_step_fused_labels_f32")
         return z_new, q, w
     if z_old is not None:

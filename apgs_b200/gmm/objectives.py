@@ -56,15 +56,16 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     (enc_rws_eta, enc_apg_z, enc_apg_eta, generative) = models
     if x.dim() == 3:
         x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)       # stride-0 S axis; never materialised
-    log_w, tau, mu, z, trace = oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags)
-    if _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, z):
+    if _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
         # Inside the sweeps the assignments never need their one-hot (S,B,N,K) fp32 form (the objective returns only
         # the trace): carry them as one byte per point.  The two per-sweep kernels take / return labels, and the z row
-        # every resampling gather moves shrinks from 4*K*N to N bytes (720 -> 60 B for the GMM shapes).
-        z = z.argmax(-1).to(torch.uint8)
-        pad = (-z.shape[-1]) % 16                       # 16-byte rows: the gather moves them as 16-byte vectors
-        if pad:
-            z = torch.nn.functional.pad(z, (0, pad))
+        # every resampling gather moves shrinks from 4*K*N to ~N bytes (720 -> 64 B for the GMM shapes; rows padded to
+        # 16 bytes so that the gather moves 16-byte vectors).  The one-shot's sampler emits the labels with its draw.
+        N = x.shape[-2]
+        log_w, tau, mu, _, trace, z = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags,
+                                               label_stride=(N + 15) // 16 * 16)
+    else:
+        log_w, tau, mu, z, trace = oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags)
     tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
     for m in range(num_sweeps - 1):
         if block == 'decomposed':
@@ -93,8 +94,8 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
 compact_labels = True          # module switch (tests compare both representations)
 
 
-def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, z):
-    K, D = z.shape[-1], generative_dims(enc_apg_eta)
+def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
+    K, D = generative.prior_pi.numel(), generative_dims(enc_apg_eta)
     return (compact_labels and block == 'decomposed' and not result_flags['loss_required']
             and enc_apg_z.can_fuse(False) and getattr(enc_apg_eta, 'fused', False) and K <= 255 and K * D <= 8)
 
@@ -106,9 +107,17 @@ def generative_dims(enc_apg_eta):
 
 def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
     """One-shot for eta and z, like a normal RWS (objectives.py:74-110)."""
+    return _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags)[:5]
+
+
+def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_stride=0):
+    """oneshot; with label_stride (fused sampler only) the draw of z also comes back as uint8 labels (6th value)."""
     post = enc_rws_eta.params(x, generative.prior_ng)
     tau, mu = _sample_eta(post)
-    if enc_rws_z.can_fuse(result_flags['loss_required']):
+    z_lab = None
+    if label_stride:
+        z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride)
+    elif enc_rws_z.can_fuse(result_flags['loss_required']):
         z, q_probs = enc_rws_z.sample_fused(x, tau, mu, generative)
     else:
         q_probs = enc_rws_z.probs(x, tau, mu)
@@ -123,7 +132,7 @@ def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
         trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0).detach())
-    return w.log_w, tau, mu, z, trace
+    return w.log_w, tau, mu, z, trace, z_lab
 
 
 def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old, trace, result_flags):

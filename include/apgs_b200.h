@@ -235,12 +235,14 @@ APGS_API int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center
  *   form: these entries take / return them as one byte per point, z_labels uint8 in [0,K) with `label_stride` >= N bytes
  *   between the rows of consecutive particles (pad it to 16 so the gather moves 16-byte vectors), which cuts the z row
  *   the resampling gather moves from 4*K*N to ~N bytes.  Same arithmetic and outputs as apgs_gmm_z_step_fused_f32 (with
- *   z_old given, sampling from `uniforms`) and apgs_gmm_eta_posterior_stats_f32; center / stats may both be NULL.      */
+ *   z_old given, sampling from `uniforms`) and apgs_gmm_eta_posterior_stats_f32; center / stats may both be NULL;
+ *   z_old_labels may be NULL (sample-only: no weights) and z_new_onehot (S,B,N,K), when given, receives the one-hot
+ *   form of the same draw (the one-shot needs both).                                                                 */
 APGS_API int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau, const float* mu,
                               const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
                               const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels, const float* uniforms,
                               int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
-                              uint8_t* z_new_labels, int64_t label_stride,
+                              uint8_t* z_new_labels, int64_t label_stride, float* z_new_onehot,
                               float* q_probs, const apgs_gmm_out_t* out, void* stream);
 APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
                                      const float* Wg, const float* bg, const float* Wo, const float* bo,
