@@ -703,6 +703,9 @@ struct EtaStatsArgs {
     const float *tau_f, *mu_f, *tau_b, *mu_b;
     long long R;
     float *log_w, *log_q_f, *dens, *log_w_f, *log_w_b;
+    // optional fused draw: standard Gamma(alpha) and standard Normal variates -> tau, mu written out and scored
+    const float *g_std, *e_std;       // (R, K, D) or null
+    float *tau_out, *mu_out;          // (R, K, D), required with the draws
 };
 
 template <int K, int D, int LANES>
@@ -725,11 +728,24 @@ __global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
     if (valid) {
         for (int e = j; e < KD; e += LANES) {
             const int k = e / D, d = e % D;
-            const float tf = __ldg(a.tau_f + r * KD + e), mf = __ldg(a.mu_f + r * KD + e);
             const float tbk = __ldg(a.tau_b + r * KD + e), mbk = __ldg(a.mu_b + r * KD + e);
             const float a0 = s_pr[e][0], b0 = s_pr[e][1], m0 = s_pr[e][2], n0 = s_pr[e][3], gp = s_pr[e][4], Ln0 = s_pr[e][5];
             const float qa = __ldg(a.pa + r * KD + e), qb = __ldg(a.pb + r * KD + e);
             const float qm = __ldg(a.pm + r * KD + e), qn = __ldg(a.pn + r * KD + e);
+            float tf, mf;
+            if (a.g_std != nullptr) {
+                // tau = Gamma(alpha, beta).sample() = max(standard_gamma(alpha) / beta, tiny)   (torch gamma.py:73-77)
+                // mu  = Normal(q_mu, 1/sqrt(q_nu tau)).sample() = e * scale + q_mu               (models.py:69-78)
+                // the same IEEE operations the PyTorch elementwise kernels perform, so the draws are bit-identical
+                tf = fmaxf(__fdiv_rn(__ldg(a.g_std + r * KD + e), qb), 1.17549435e-38f);
+                const float sc = __fdiv_rn(1.f, __fsqrt_rn(__fmul_rn(qn, tf)));
+                mf = __fadd_rn(__fmul_rn(__ldg(a.e_std + r * KD + e), sc), qm);
+                a.tau_out[r * KD + e] = tf;
+                a.mu_out[r * KD + e] = mf;
+            } else {
+                tf = __ldg(a.tau_f + r * KD + e);
+                mf = __ldg(a.mu_f + r * KD + e);
+            }
             const float* sp = a.stats + r * (K * ST) + k * ST;
             const float cnt = __ldg(sp), S1 = __ldg(sp + 1 + d), S2 = __ldg(sp + 1 + D + d);
             const float cen = __ldg(a.center + r * KD + e);
@@ -980,13 +996,37 @@ extern "C" int apgs_gmm_eta_posterior_stats_f32(const float* x, const float* z, 
                 (long long)D);
 }
 
+static int logw_eta_stats(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                          const apgs_gmm_prior_t* prior, const float* tau, const float* mu, const float* g_std,
+                          const float* e_std, float* tau_out, float* mu_out, const float* tau_old, const float* mu_old,
+                          int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream);
+
 extern "C" int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
                                            const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
                                            const float* tau_old, const float* mu_old, int64_t S, int64_t B, int64_t K,
                                            int64_t D, const apgs_gmm_out_t* out, void* stream) {
+    if (!tau || !mu) return fail(APGS_E_BADARG, "gmm_logw_eta_stats: NULL input");
+    return logw_eta_stats(stats, center, post, prior, tau, mu, nullptr, nullptr, nullptr, nullptr, tau_old, mu_old, S, B,
+                          K, D, out, stream);
+}
+
+extern "C" int apgs_gmm_draw_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                                const apgs_gmm_prior_t* prior, const float* gamma_std,
+                                                const float* normal_std, float* tau, float* mu, const float* tau_old,
+                                                const float* mu_old, int64_t S, int64_t B, int64_t K, int64_t D,
+                                                const apgs_gmm_out_t* out, void* stream) {
+    if (!gamma_std || !normal_std || !tau || !mu) return fail(APGS_E_BADARG, "gmm_draw_logw_eta_stats: NULL input");
+    return logw_eta_stats(stats, center, post, prior, nullptr, nullptr, gamma_std, normal_std, tau, mu, tau_old, mu_old, S,
+                          B, K, D, out, stream);
+}
+
+static int logw_eta_stats(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                          const apgs_gmm_prior_t* prior, const float* tau, const float* mu, const float* g_std,
+                          const float* e_std, float* tau_out, float* mu_out, const float* tau_old, const float* mu_old,
+                          int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream) {
     if (S <= 0 || B <= 0 || S * B >= (1ll << 36))
         return fail(APGS_E_SHAPE, "gmm_logw_eta_stats: bad sizes S=%lld B=%lld", (long long)S, (long long)B);
-    if (!stats || !center || !post || !prior || !out || !tau || !mu || !tau_old || !mu_old)
+    if (!stats || !center || !post || !prior || !out || !tau_old || !mu_old)
         return fail(APGS_E_BADARG, "gmm_logw_eta_stats: NULL input");
     if (!post->alpha || !post->beta || !post->mu || !post->nu || !prior->alpha || !prior->beta || !prior->mu || !prior->nu)
         return fail(APGS_E_BADARG, "gmm_logw_eta_stats: NULL prior / posterior parameter");
@@ -995,6 +1035,7 @@ extern "C" int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* cent
     a.pa = post->alpha; a.pb = post->beta; a.pm = post->mu; a.pn = post->nu;
     a.ra = prior->alpha; a.rb = prior->beta; a.rm = prior->mu; a.rn = prior->nu;
     a.tau_f = tau; a.mu_f = mu; a.tau_b = tau_old; a.mu_b = mu_old;
+    a.g_std = g_std; a.e_std = e_std; a.tau_out = tau_out; a.mu_out = mu_out;
     a.R = (long long)S * B;
     a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;
     a.log_w_b = out->log_w_b;

@@ -120,6 +120,30 @@ def logw_eta_stats(stats, center, post, prior, tau, mu, tau_old, mu_old, parts=F
     return w
 
 
+def draw_logw_eta_stats(stats, center, post, prior, gamma_std, normal_std, tau_old, mu_old, parts=False):
+    """logw_eta_stats with the draw fused in: gamma_std = torch._standard_gamma(alpha), normal_std = torch.randn(...)
+    (S,B,K,D).  Returns (Weights, tau, mu) with tau, mu bit-identical to Gamma(alpha, beta).sample() and
+    Normal(q_mu, 1/sqrt(q_nu tau)).sample() formed from the same variates."""
+    lib = _lib.load()
+    stats, center = _req(stats, "stats", ndim=4), _req(center, "center", ndim=4)
+    g, e, tau_old, mu_old = [_req(v, "draws / old eta", ndim=4) for v in (gamma_std, normal_std, tau_old, mu_old)]
+    S, B, K, D = g.shape
+    if tuple(stats.shape) != (S, B, K, 1 + 2 * D) or tuple(center.shape) != (S, B, K, D):
+        raise ValueError("stats/center have shapes %s %s" % (tuple(stats.shape), tuple(center.shape)))
+    for v in (e, tau_old, mu_old):
+        if tuple(v.shape) != (S, B, K, D):
+            raise ValueError("draw / old eta shapes differ")
+    ps, pk = _post_struct(post)
+    rs, rk = _prior_struct(prior)
+    tau, mu = torch.empty_like(g), torch.empty_like(g)
+    w, o = _outs(S, B, 1, g.device, parts, False)
+    with torch.cuda.device(g.device), _call("gmm_logw_eta_stats", 1, 4 * S * B * (K * (1 + 2 * D) + 11 * K * D + 3)):
+        check(lib.apgs_gmm_draw_logw_eta_stats_f32(ptr(stats), ptr(center), C.byref(ps), C.byref(rs), ptr(g), ptr(e),
+                                                   ptr(tau), ptr(mu), ptr(tau_old), ptr(mu_old), S, B, K, D,
+                                                   C.byref(o), _stream()), "apgs_gmm_draw_logw_eta_stats_f32")
+    return w, tau, mu
+
+
 def logw_z(x, tau, mu, q_probs, prior, z, z_old, parts=False, local=False):
     """G3 (+W2): z-step weights (apgs/gmm/objectives.py:197-227)."""
     lib = _lib.load()

@@ -164,8 +164,11 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
         # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of
         *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old)
         post = tuple(post)
-        tau, mu = _sample_eta(post)
-        w = kernels.logw_eta_stats(stats, mu_old, post, generative, tau, mu, tau_old, mu_old)
+        # the draw of _sample_eta with its elementwise tail fused into the weight kernel: same variates, same IEEE
+        # operations (tau = max(g / beta, tiny), mu = e / sqrt(nu tau) + q_mu), seven launches less per step
+        g_std = torch._standard_gamma(post[0])
+        e_std = torch.randn_like(post[2])
+        w, tau, mu = kernels.draw_logw_eta_stats(stats, mu_old, post, generative, g_std, e_std, tau_old, mu_old)
     else:
         post = enc_apg_eta.params(x, z, generative.prior_ng)
         tau, mu = _sample_eta(post)

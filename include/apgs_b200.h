@@ -231,6 +231,16 @@ APGS_API int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center
                                 int64_t S, int64_t B, int64_t K, int64_t D,
                                 const apgs_gmm_out_t* out, void* stream);
 
+/* apgs_gmm_logw_eta_stats_f32 with the draw fused in: given standard variates (torch._standard_gamma(alpha),
+ *   torch.randn) it forms tau = max(g / beta, tiny) and mu = e / sqrt(nu tau) + q_mu with the IEEE operations of
+ *   Gamma(alpha, beta).sample() / Normal(q_mu, 1/sqrt(q_nu tau)).sample() (apgs/gmm/models.py:69-78), writes them to
+ *   tau / mu (S,B,K,D) and scores them -- seven elementwise launches per eta step less, bit-identical draws.          */
+APGS_API int apgs_gmm_draw_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                const apgs_gmm_prior_t* prior, const float* gamma_std, const float* normal_std,
+                                float* tau, float* mu, const float* tau_old, const float* mu_old,
+                                int64_t S, int64_t B, int64_t K, int64_t D,
+                                const apgs_gmm_out_t* out, void* stream);
+
 /* Label mode of the two per-sweep GMM kernels.  Inside a sweep the assignments never need their one-hot (S,B,N,K) fp32
  *   form: these entries take / return them as one byte per point, z_labels uint8 in [0,K) with `label_stride` >= N bytes
  *   between the rows of consecutive particles (pad it to 16 so the gather moves 16-byte vectors), which cuts the z row

@@ -692,3 +692,29 @@ def test_objective_with_compact_labels_matches_one_hot_objective():
             O.compact_labels = True
     for k in ("ess", "density", "E_z", "E_tau", "E_mu"):
         assert torch.equal(out[True][k], out[False][k]), k
+
+
+def test_fused_eta_draw_is_bit_identical_to_torch_sampling():
+    """draw_logw_eta_stats forms (tau, mu) from the standard variates with the IEEE operations of
+    Gamma(alpha, beta).sample() / Normal(q_mu, 1/sqrt(q_nu tau)).sample(): same seed -> the same draws, bit for bit,
+    and the same weights as scoring those draws through logw_eta_stats."""
+    from apgs_b200.gmm import kernels, objectives as O
+    S, B, N, K, D = 21, 7, 60, 3, 2
+    torch.manual_seed(0)
+    gen = _Gen(K, D)
+    x = (torch.randn(B, N, D) * 2).to(DEV)
+    lab = torch.randint(0, K, (S, B, N), dtype=torch.uint8, device=DEV)
+    tau_old, mu_old = (torch.rand(S, B, K, D) + 0.5).to(DEV), torch.randn(S, B, K, D).to(DEV)
+    P = og.make_params(K, D)
+    heads = [P["enc_apg_eta"][k].to(DEV) for k in ("gamma.0.weight", "gamma.0.bias", "ob.0.weight", "ob.0.bias")]
+    *post, stats = kernels.eta_posterior_fused(x, lab, heads, gen, center=mu_old)
+    post = tuple(post)
+    torch.manual_seed(11)
+    tau_ref, mu_ref = O._sample_eta(post)
+    torch.manual_seed(11)
+    g, e = torch._standard_gamma(post[0]), torch.randn_like(post[2])
+    w, tau, mu = kernels.draw_logw_eta_stats(stats, mu_old, post, gen, g, e, tau_old, mu_old, parts=True)
+    assert torch.equal(tau, tau_ref) and torch.equal(mu, mu_ref)
+    w2 = kernels.logw_eta_stats(stats, mu_old, post, gen, tau_ref, mu_ref, tau_old, mu_old, parts=True)
+    for name in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b"):
+        assert torch.equal(getattr(w, name), getattr(w2, name)), name
