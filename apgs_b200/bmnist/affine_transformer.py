@@ -43,6 +43,11 @@ class Affine_Transformer():
         [frame: S * B * T * FP * FP, z_where: S * B * T * K * 2 ===> digit: S * B * T * K * DP * DP]"""
         return kernels.crop(frames, z_where, self.lin_dp, self.digit_pixels)
 
+    def subtract_digit(self, frame, digit, z_where):
+        """frame (S,B,FP,FP) - digit_to_frame(digit (S,B,DP,DP), z_where (S,B,2)): the residual-frame update of the
+        sequential template matches (apgs/bmnist/objectives.py:87-89) -- the reference has no such entry."""
+        return kernels.paste_subtract(frame, digit, z_where, self.lin_fp)
+
     # fused tail of Dec_digit.forward (apgs/bmnist/models.py:148-154) -- the reference has no such entry
     def reconstruct_ll(self, digit, z_where, frames, want_recon=False):
         return kernels.paste_ll(digit, z_where, frames, self.lin_fp, want_recon=want_recon)

@@ -138,3 +138,23 @@ def template_match(frame, template, softmax=True):
                                                  S, B, FP, DP, 1 if softmax else 0, ptr(out), _stream()),
               "apgs_bmnist_template_match_f32")
     return out
+
+
+def paste_subtract(frame, digit, z_where, lin_fp):
+    """frame (S,B,FP,FP) - digit_to_frame(digit (S,B,DP,DP), z_where (S,B,2)) -> (S,B,FP,FP): the frame_left update of
+    the sequential template matches (apgs/bmnist/objectives.py:87-89) in one pass.  Strided views are read in place."""
+    lib = _lib.load()
+    f, d = _dense_images(frame, "frame"), _dense_images(digit, "digit")
+    S, B, FP, _ = f.shape
+    DP = d.shape[-1]
+    z = _req(z_where, "z_where", ndim=3)
+    if tuple(d.shape) != (S, B, DP, DP) or tuple(z.shape) != (S, B, 2):
+        raise ValueError("frame %s / digit %s / z_where %s shapes do not match" % (tuple(f.shape), tuple(d.shape), tuple(z.shape)))
+    if d.stride(1) == 0:
+        d = d.contiguous()
+    out = torch.empty(S, B, FP, FP, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device), _call("bmnist_paste_subtract", 1, 4 * S * B * (2 * FP * FP + DP * DP + 2)):
+        check(lib.apgs_bmnist_paste_subtract_f32(ptr(f), f.stride(0), f.stride(1), ptr(d), d.stride(0), d.stride(1), ptr(z),
+                                                 ptr(lin_fp), S, B, FP, DP, ptr(out), _stream()),
+              "apgs_bmnist_paste_subtract_f32")
+    return out

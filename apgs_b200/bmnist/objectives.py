@@ -79,8 +79,8 @@ def _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t
         q_mean, q_std = enc_coor.params(conved_k)
         z_where_k = normal_sample(q_mean.detach(), q_std.detach())
         zs.append(z_where_k.unsqueeze(2)); means.append(q_mean.unsqueeze(2)); stds.append(q_std.unsqueeze(2))
-        recon_k = AT.digit_to_frame(template_k.unsqueeze(2), z_where_k.unsqueeze(2).unsqueeze(2)).squeeze(2).squeeze(2)
-        frame_left = frame_left - recon_k
+        if k + 1 < K:                                        # frame_left - digit_to_frame(template_k, z_where_k) (:87-89)
+            frame_left = AT.subtract_digit(frame_left, template_k, z_where_k)
     z_where = torch.cat(zs, 2)
     q_mean, q_std = torch.cat(means, 2), torch.cat(stds, 2)
     log_q_graph = Normal(q_mean, q_std, validate_args=False).log_prob(z_where).sum(-1).sum(-1) if train else None

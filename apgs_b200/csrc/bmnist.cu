@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(256) k_stn_paste(StnArgs a) {
     int* s_idx = reinterpret_cast<int*>(s_dig + K * DP * DP);         // [K][2][FP]
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
-    StageReq req[1] = {{s_dig, a.src + ((long long)s * a.B + b) * K * DP * DP, (unsigned int)(K * DP * DP * 4)}};
+    // digits of (s,b): dense (S,B,K,DP,DP), or -- residual mode, K = 1 -- one DP x DP image at explicit (s,b) strides
+    const float* dig = (a.ss | a.sb) ? a.src + s * a.ss + b * a.sb : a.src + ((long long)s * a.B + b) * K * DP * DP;
+    StageReq req[1] = {{s_dig, dig, (unsigned int)(K * DP * DP * 4)}};
     stage_issue(req, 1, &bar);
     const float scale = (float)((double)FP / (double)DP);             // FloatTensor([[FP/DP, 0], [0, FP/DP]]) (:36)
     const float tr = (float)((double)(FP - DP) / (double)DP);         // (:48)
@@ -91,10 +93,13 @@ __global__ void __launch_bounds__(256) k_stn_paste(StnArgs a) {
 
     if (!WITH_LL) {
         float* out = a.dst + (long long)sbt * K * FP * FP;
+        // residual mode (frames given, K = 1): out = frame - paste, the frame_left update of objectives.py:87-89
+        const float* res = a.frames != nullptr ? a.frames + s * a.fs + b * a.fb + t * a.ft : nullptr;
         for (int o = threadIdx.x; o < K * FP * FP; o += blockDim.x) {
             const int k = o / (FP * FP), i = (o / FP) % FP, j = o % FP;
             const int r = s_idx[(k * 2 + 0) * FP + i], c = s_idx[(k * 2 + 1) * FP + j];
-            __stcs(out + o, (r >= 0 && c >= 0) ? s_dig[(k * DP + r) * DP + c] : 0.f);
+            const float v = (r >= 0 && c >= 0) ? s_dig[(k * DP + r) * DP + c] : 0.f;
+            __stcs(out + o, res != nullptr ? __fsub_rn(__ldg(res + o), v) : v);
         }
         return;
     }
@@ -287,6 +292,25 @@ extern "C" int apgs_bmnist_paste_f32(const float* digits, const float* z_where, 
     if (int e = check_stn(S, B, T, K, FP, DP, "bmnist_paste")) return e;
     if (!digits || !z_where || !lin_fp || !frames_out) return fail(APGS_E_BADARG, "bmnist_paste: NULL pointer");
     return launch_paste(false, digits, z_where, lin_fp, nullptr, 0, 0, 0, S, B, T, K, FP, DP, frames_out, nullptr, stream);
+}
+
+extern "C" int apgs_bmnist_paste_subtract_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                              const float* digit, int64_t digit_stride_s, int64_t digit_stride_b,
+                                              const float* z_where, const float* lin_fp, int64_t S, int64_t B,
+                                              int64_t FP, int64_t DP, float* out, void* stream) {
+    if (int e = check_stn(S, B, 1, 1, FP, DP, "bmnist_paste_subtract")) return e;
+    if (!frame || !digit || !z_where || !lin_fp || !out) return fail(APGS_E_BADARG, "bmnist_paste_subtract: NULL pointer");
+    if (frame_stride_s < 0 || frame_stride_b < 0 || digit_stride_s < 0 || digit_stride_b <= 0)
+        return fail(APGS_E_BADARG, "bmnist_paste_subtract: bad stride");
+    StnArgs a = {};
+    a.src = digit; a.ss = digit_stride_s; a.sb = digit_stride_b; a.z_where = z_where; a.lin = lin_fp; a.dst = out;
+    a.frames = frame; a.fs = frame_stride_s; a.fb = frame_stride_b; a.ft = 0;
+    a.S = (int)S; a.B = (int)B; a.T = 1; a.K = 1; a.FP = (int)FP; a.DP = (int)DP;
+    const size_t smem = (size_t)DP * DP * 4 + (size_t)2 * FP * sizeof(int);
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_stn_paste<false>), smem), "smem attr");
+    k_stn_paste<false><<<(unsigned int)(S * B), 256, smem, (cudaStream_t)stream>>>(a);
+    APGS_LAUNCH_OK("k_stn_paste launch");
+    return 0;
 }
 
 extern "C" int apgs_bmnist_paste_ll_f32(const float* digits, const float* z_where, const float* lin_fp,

@@ -393,6 +393,15 @@ APGS_API int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
 APGS_API int apgs_dmm_decoder_hidden2_f32(const float* beta, const apgs_dmm_mlp_t* net, int64_t H, int64_t D,
                                  int64_t M, float* hidden2, void* stream);
 
+/* frame_left update of the K sequential matches (apgs/bmnist/objectives.py:87-89):
+ *     out[s,b] = frame[s,b] - digit_to_frame(digit[s,b], z_where[s,b])           (FP x FP, nearest paste, zero outside)
+ *   frame (s,b) at frame + s*frame_stride_s + b*frame_stride_b (dense FP*FP; stride 0 allowed), digit (s,b) likewise
+ *   (dense DP*DP, e.g. template[:, :, k] of (S,B,K,DP,DP)), z_where (S,B,2), out (S,B,FP,FP) dense.                  */
+APGS_API int apgs_bmnist_paste_subtract_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                   const float* digit, int64_t digit_stride_s, int64_t digit_stride_b,
+                                   const float* z_where, const float* lin_fp,
+                                   int64_t S, int64_t B, int64_t FP, int64_t DP, float* out, void* stream);
+
 /* N3  bmnist template matching (apgs/bmnist/objectives.py:72-74):
  *     conv2d(frame_left (1, S*B, FP, FP), template_k (S*B, 1, DP, DP), groups = S*B) -> (S, B, CP*CP), CP = FP-DP+1,
  *     i.e. image (s,b) cross-correlated with ITS OWN template, optionally followed by the softmax over the CP*CP scores.

@@ -334,3 +334,21 @@ def test_N2_bmnist_training_loop_runs_like_reference_train():
         opt.step()
     after = [p.detach() for m in mods for p in m.parameters()]
     assert all(not torch.equal(a, b) for a, b in zip(before, after))
+
+
+def test_paste_subtract_equals_paste_then_subtract():
+    """the fused residual-frame update == digit_to_frame followed by the subtraction, bit for bit, on strided views."""
+    AT = _AT()
+    torch.manual_seed(9)
+    S, B, T, K = 3, 4, 3, 3
+    frames = torch.rand(B, T, 96, 96, device=DEV).unsqueeze(0).expand(S, -1, -1, -1, -1)      # stride-0 particle axis
+    tmpl = torch.rand(S, B, K, 28, 28, device=DEV)
+    z = (torch.randn(S, B, K, 2, device=DEV) * 0.9)
+    z[0, 0, 0] = torch.tensor([1.6, -1.7], device=DEV)                                       # partly outside the frame
+    for t, k in ((0, 0), (2, 1), (1, 2)):
+        ref = frames[:, :, t] - AT.digit_to_frame(tmpl[:, :, k].unsqueeze(2), z[:, :, k].unsqueeze(2).unsqueeze(2)).squeeze(2).squeeze(2)
+        out = AT.subtract_digit(frames[:, :, t], tmpl[:, :, k], z[:, :, k])
+        assert torch.equal(out, ref), (t, k)
+    left = torch.randn(S, B, 96, 96, device=DEV)
+    ref = left - AT.digit_to_frame(tmpl[:, :, 1].unsqueeze(2), z[:, :, 1].unsqueeze(2).unsqueeze(2)).squeeze(2).squeeze(2)
+    assert torch.equal(AT.subtract_digit(left, tmpl[:, :, 1], z[:, :, 1]), ref)
