@@ -100,12 +100,14 @@ class Enc_apg_mu(_EncMu):
         inp = torch.cat((x.unsqueeze(2).expand(B, N, K, D), eye.expand(B, N, K, K)), -1)
         return self.nss1(inp).contiguous(), self.nss2(inp).contiguous()
 
-    def params(self, ob, z, beta, K, priors):
+    def params(self, ob, z, beta, K, priors, tables=None):
+        """tables: label_tables(x) computed by the caller (they depend on the data and the weights only, so one
+        evaluation serves every sweep of an objective)."""
         x = _x_inst(ob)
         if self.fused:
             # forward values only (the draws carry no gradient); training rebuilds log q through params_torch()
             with torch.no_grad():
-                tab1, tab2 = self.label_tables(x)
+                tab1, tab2 = self.label_tables(x) if tables is None else tables
                 nss_prior = kernels.nss_pool_onehot(tab1, tab2, z, priors[0], priors[1])
                 return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
         h1 = torch.tanh(_split_linear(self.nss1[0], x, z))

@@ -44,10 +44,14 @@ def apg_objective(models, x, K, result_flags, num_sweeps, resampler):
     # the decoder output h2 is a function of beta alone, so it travels with beta through the resampling steps
     # (one more 8-byte-per-point latent in the same gather launch) instead of being re-evaluated from the gathered
     # beta: one decoder evaluation per sweep instead of three
+    tables = None
+    if getattr(enc_apg_mu, 'fused', False) and num_sweeps > 1:
+        with torch.no_grad():
+            tables = enc_apg_mu.label_tables(x[0] if x.dim() == 4 else x)      # data + weights only: once per objective
     log_w, mu, z, beta, h2, trace = _oneshot(enc_rws_mu, enc_apg_local, dec, x, K, trace, result_flags)
     mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w)
     for m in range(num_sweeps - 1):
-        log_w_mu, mu, trace = apg_update_mu(enc_apg_mu, dec, x, z, beta, mu, K, trace, result_flags, h2=h2)
+        log_w_mu, mu, trace = apg_update_mu(enc_apg_mu, dec, x, z, beta, mu, K, trace, result_flags, h2=h2, tables=tables)
         mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w_mu)
         log_w_z, z, beta, h2, trace = _update_local(enc_apg_local, dec, x, mu, z, beta, K, trace, result_flags, h2_old=h2)
         mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w_z)
@@ -117,10 +121,13 @@ def _oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
     return w.log_w, mu, z, beta, h2, trace
 
 
-def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags, h2=None):
+def apg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, result_flags, h2=None, tables=None):
     """Given local variables {z, beta}, update the centres mu (objectives.py:116-151).  h2: the decoder output of
-    beta when the caller already holds it."""
-    q_mu, q_sigma = enc_apg_mu.params(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
+    beta when the caller already holds it; tables: Enc_apg_mu.label_tables(x) when the caller already holds them."""
+    if tables is not None:
+        q_mu, q_sigma = enc_apg_mu.params(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma), tables=tables)
+    else:
+        q_mu, q_sigma = enc_apg_mu.params(x, z, beta, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
     mu = normal_sample(q_mu, q_sigma)
     if h2 is None:
         h2 = dec.hidden2(beta)             # the decoder sees beta only: one evaluation serves f and b
