@@ -718,3 +718,59 @@ def test_fused_eta_draw_is_bit_identical_to_torch_sampling():
     w2 = kernels.logw_eta_stats(stats, mu_old, post, gen, tau_ref, mu_ref, tau_old, mu_old, parts=True)
     for name in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b"):
         assert torch.equal(getattr(w, name), getattr(w2, name)), name
+
+
+def test_gmm_label_kernels_stay_inside_their_buffers():
+    """raw C-ABI calls of the two label-mode kernels with outputs embedded in sentinel guard bands (the pool has no
+    compute-sanitizer): padded label rows, ragged tiles (S not a multiple of 32), every optional output."""
+    import ctypes as C
+    from apgs_b200 import _lib
+    from apgs_b200._lib import ptr
+    lib = _lib.load()
+    S, B, N, K, D, H, LN = 37, 5, 60, 3, 2, 32, 64
+    torch.manual_seed(3)
+    P = og.make_params(K, D, H)
+    G = 2048
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=DEV)
+        return buf, buf[G:G + n]
+    x = (torch.randn(B, N, D) * 2).to(DEV)
+    tau, mu = (torch.rand(S, B, K, D) * 3 + 0.1).to(DEV), (torch.randn(S, B, K, D) * 2).to(DEV)
+    lab = torch.randint(0, K, (S, B, LN), dtype=torch.uint8, device=DEV)
+    u = torch.rand(S, B, N, device=DEV)
+    mlp = [P["enc_apg_z"][k].to(DEV).contiguous() for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+    gen = _Gen(K, D)
+    from apgs_b200.gmm.kernels import _prior_struct
+    rs, keep = _prior_struct(gen)
+    bufs = {}
+    bufs["zl"] = guarded(S * B * LN, torch.uint8, 0xEE)
+    bufs["q"] = guarded(S * B * N * K, torch.float32, -7.0)
+    for name in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b"):
+        bufs[name] = guarded(S * B, torch.float32, -7.0)
+    for name in ("log_w_local", "log_q_local"):
+        bufs[name] = guarded(S * B * N, torch.float32, -7.0)
+    o = _lib.GmmOut()
+    for name in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b", "log_w_local", "log_q_local"):
+        setattr(o, name, bufs[name][1].data_ptr())
+    rc = lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(mlp[0]), ptr(mlp[1]), ptr(mlp[2]), ptr(mlp[3]), H,
+                                              C.byref(rs), ptr(lab), ptr(u), S, B, N, K, D, ptr(bufs["zl"][1]), LN, None,
+                                              ptr(bufs["q"][1]), C.byref(o), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.apgs_last_error()
+    heads = [P["enc_apg_eta"][k].to(DEV).contiguous() for k in ("gamma.0.weight", "gamma.0.bias", "ob.0.weight", "ob.0.bias")]
+    pr = [getattr(gen, "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
+    for name in ("pa", "pb", "pm", "pn"):
+        bufs[name] = guarded(S * B * K * D, torch.float32, -7.0)
+    bufs["stats"] = guarded(S * B * K * (1 + 2 * D), torch.float32, -7.0)
+    rc = lib.apgs_gmm_eta_posterior_stats_labels_f32(ptr(x), ptr(lab), *[ptr(h) for h in heads], S, B, N, K, D,
+                                                     *[ptr(v) for v in pr], *[ptr(bufs[n][1]) for n in ("pa", "pb", "pm", "pn")],
+                                                     ptr(mu), ptr(bufs["stats"][1]), LN, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.apgs_last_error()
+    torch.cuda.synchronize()
+    for name, (buf, view) in bufs.items():
+        fill = 0xEE if buf.dtype == torch.uint8 else -7.0
+        assert bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all()), name
+    zl = bufs["zl"][1].view(S, B, LN)
+    assert bool((zl[..., :N] < K).all()) and bool((zl[..., N:] == 0xEE).all())            # pad bytes are never written
+    for name in ("q", "log_w", "density", "pa", "pb", "pm", "pn", "stats", "log_w_local"):
+        assert bool(torch.isfinite(bufs[name][1]).all()) and not bool((bufs[name][1] == -7.0).all()), name

@@ -322,3 +322,45 @@ def test_split_S_pipeline_multinomial_and_given_weights():
     # the exact sequential chain is still available on request (single-CTA global-tile variant)
     a = ops.sample_ancestors(w_norm=w.to(DEV), strategy="systematic", uniforms=u.to(DEV), cdf_mode=1).cpu().numpy()     # APGS_CDF_EXACT
     assert np.array_equal(a, orc.systematic_ancestors(w.numpy(), u.numpy()))
+
+
+# ------------------------------------------------------------------ guard bands (the pool has no compute-sanitizer)
+@pytest.mark.parametrize("S,B,strategy", [(70001, 5, "systematic"), (60000, 33, "multinomial"), (1000, 37, "systematic"),
+                                          (9000, 3, "multinomial")])
+def test_ancestor_kernels_stay_inside_their_buffers(S, B, strategy):
+    """raw C-ABI call with every output and the workspace embedded in sentinel-filled guard bands: nothing outside the
+    documented extents may be written (covers the shared-memory tile, blocked and split-S variants)."""
+    from apgs_b200 import _lib
+    from apgs_b200._lib import ptr
+    lib = _lib.load()
+    torch.manual_seed(S)
+    G = 4096                                                     # guard elements on both sides
+    lw = (torch.randn(S, B) * 2).to(DEV)
+    if strategy == "systematic":
+        u, us, ub = torch.rand(B, device=DEV), 0, 0
+    else:
+        u, us, ub = torch.rand(B, S, dtype=torch.float64, device=DEV), 1, S
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=DEV)
+        return buf, buf[G:G + n]
+    b64, a64 = guarded(S * B, torch.int64, -7)
+    b32, a32 = guarded(S * B, torch.int32, -7)
+    bw, w = guarded(S * B, torch.float32, -7.0)
+    be, ess = guarded(B, torch.float32, -7.0)
+    bl, lse = guarded(B, torch.float32, -7.0)
+    nws = lib.apgs_ancestors_workspace_bytes(S, B)
+    bws = torch.full((nws + 2 * 256 * 16,), 0x5A, dtype=torch.uint8, device=DEV)
+    off = (-bws.data_ptr()) % 256 + 256 * 8                      # keep the interior 256-byte aligned
+    ws = bws[off:off + nws]
+    rc = lib.apgs_sample_ancestors_f32(ptr(lw), None, S, B, _lib.SYSTEMATIC if strategy == "systematic" else _lib.MULTINOMIAL,
+                                       ptr(u), us, ub, 0, ptr(a64), ptr(a32), ptr(w), ptr(ess), ptr(lse),
+                                       ptr(ws) if nws else None, nws, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.apgs_last_error()
+    torch.cuda.synchronize()
+    for buf, fill in ((b64, -7), (b32, -7), (bw, -7.0), (be, -7.0), (bl, -7.0)):
+        assert bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all())
+    assert bool((bws[:off] == 0x5A).all()) and bool((bws[off + nws:] == 0x5A).all())
+    assert int(a64.min()) >= 0 and int(a64.max()) < S and torch.equal(a64, a32.long())
+    assert bool(torch.isfinite(ess).all()) and bool(torch.isfinite(lse).all())
+    np.testing.assert_allclose(w.view(S, B).sum(0).cpu().numpy(), 1.0, rtol=1e-4)
