@@ -352,3 +352,38 @@ def test_paste_subtract_equals_paste_then_subtract():
     left = torch.randn(S, B, 96, 96, device=DEV)
     ref = left - AT.digit_to_frame(tmpl[:, :, 1].unsqueeze(2), z[:, :, 1].unsqueeze(2).unsqueeze(2)).squeeze(2).squeeze(2)
     assert torch.equal(AT.subtract_digit(left, tmpl[:, :, 1], z[:, :, 1]), ref)
+
+
+def test_bmnist_match_and_residual_kernels_stay_inside_their_buffers():
+    """raw C-ABI calls with the outputs embedded in sentinel guard bands and strided inputs (no compute-sanitizer on
+    this pool)."""
+    from apgs_b200 import _lib
+    from apgs_b200._lib import ptr
+    lib = _lib.load()
+    S, B, T, K, FP, DP = 3, 5, 2, 3, 96, 28
+    CP = FP - DP + 1
+    G = 4096
+    torch.manual_seed(2)
+    frames = torch.rand(B, T, FP, FP, device=DEV)
+    tmpl = torch.rand(S, B, K, DP, DP, device=DEV)
+    z = torch.randn(S, B, 2, device=DEV) * 0.8
+    lin = torch.linspace(-1, 1, FP).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(n):
+        buf = torch.full((n + 2 * G,), -7.0, device=DEV)
+        return buf, buf[G:G + n]
+    bo, out = guarded(S * B * CP * CP)
+    f_t, t_k = frames[:, 1], tmpl[:, :, 2]
+    rc = lib.apgs_bmnist_template_match_f32(ptr(f_t), 0, f_t.stride(0), ptr(t_k), t_k.stride(0), t_k.stride(1), S, B, FP, DP, 1,
+                                            ptr(out), st)
+    assert rc == 0, lib.apgs_last_error()
+    br, res = guarded(S * B * FP * FP)
+    rc = lib.apgs_bmnist_paste_subtract_f32(ptr(f_t), 0, f_t.stride(0), ptr(t_k), t_k.stride(0), t_k.stride(1), ptr(z), ptr(lin),
+                                            S, B, FP, DP, ptr(res), st)
+    assert rc == 0, lib.apgs_last_error()
+    torch.cuda.synchronize()
+    for buf in (bo, br):
+        assert bool((buf[:G] == -7.0).all()) and bool((buf[-G:] == -7.0).all())
+    np.testing.assert_allclose(out.view(S, B, -1).sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
+    assert bool(torch.isfinite(res).all())
