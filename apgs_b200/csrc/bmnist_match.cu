@@ -36,7 +36,7 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
 }
 
 template <int FP, int DP, int SEG>
-__global__ void __launch_bounds__(224, 2) k_template_match(MatchArgs a) {
+__global__ void __launch_bounds__(224, 5) k_template_match(MatchArgs a) {
     constexpr int CP = FP - DP + 1, NSEG = CP / SEG, FS = FP + 1, WIN = SEG + DP - 1;
     static_assert(CP % SEG == 0 && DP % 4 == 0, "tile shape");
     static_assert(CP * NSEG <= 224, "one thread per (output row, column segment)");
