@@ -64,3 +64,44 @@ def test_no_cpu_fallback():
         ops.weight_stats(torch.zeros(4, 4))
     with pytest.raises(_lib.ApgsError):
         Resampler("systematic", 4, False, None)
+
+
+def test_bad_arguments_of_the_fused_entry_points_are_rejected_before_launch():
+    """every check below happens on the host, before any CUDA call: negative APGS_E_* code + a message."""
+    lib = _lib.load()
+    P = C.c_void_p(64)                       # a non-NULL dummy; never dereferenced on these paths
+    pr = _lib.GmmPrior(64, 64, 64, 64, 64)
+    out = _lib.GmmOut()
+    mlp = _lib.DmmMlp(64, 64, 64, 64)
+    # fused z step: uniforms or z_forced required; label variant needs its output and a stride >= N
+    assert lib.apgs_gmm_z_step_fused_f32(P, P, P, P, P, P, P, 32, C.byref(pr), None, None, None, 4, 4, 60, 3, 2, P, None,
+                                         C.byref(out), None) < 0
+    assert b"uniforms" in lib.apgs_last_error()
+    assert lib.apgs_gmm_z_step_fused_f32(P, P, P, P, P, P, P, 0, C.byref(pr), None, None, P, 4, 4, 60, 3, 2, P, None,
+                                         C.byref(out), None) < 0
+    assert lib.apgs_gmm_z_step_fused_f32(P, P, P, P, P, P, P, 32, C.byref(pr), None, None, P, 4, 4, 60, 7, 5, P, None,
+                                         C.byref(out), None) == -5            # APGS_E_UNSUPPORTED (K, D) not instantiated
+    assert lib.apgs_gmm_z_step_fused_labels_f32(P, P, P, P, P, P, P, 32, C.byref(pr), P, P, 4, 4, 60, 3, 2, None, 64, None, None,
+                                                C.byref(out), None) < 0
+    assert lib.apgs_gmm_z_step_fused_labels_f32(P, P, P, P, P, P, P, 32, C.byref(pr), P, P, 4, 4, 60, 3, 2, P, 48, None, None,
+                                                C.byref(out), None) < 0
+    assert b"label_stride" in lib.apgs_last_error()
+    # statistics route of the eta step
+    assert lib.apgs_gmm_eta_posterior_stats_f32(P, P, P, P, P, P, 4, 4, 60, 3, 2, P, P, P, P, P, P, P, P, None, P, None) < 0
+    assert lib.apgs_gmm_eta_posterior_stats_labels_f32(P, P, P, P, P, P, 4, 4, 60, 3, 2, P, P, P, P, P, P, P, P, P, None, 64, None) < 0
+    assert lib.apgs_gmm_eta_posterior_stats_labels_f32(P, P, P, P, P, P, 4, 4, 60, 3, 2, P, P, P, P, P, P, P, P, P, P, 10, None) < 0
+    post = _lib.GmmPost(64, 64, 64, 64)
+    assert lib.apgs_gmm_logw_eta_stats_f32(None, P, C.byref(post), C.byref(pr), P, P, P, P, 4, 4, 3, 2, C.byref(out), None) < 0
+    assert lib.apgs_gmm_draw_logw_eta_stats_f32(P, P, C.byref(post), C.byref(pr), None, P, P, P, P, P, 4, 4, 3, 2, C.byref(out), None) < 0
+    # DMM fused encoders
+    assert lib.apgs_dmm_nss_pool_onehot_f32(P, P, None, P, P, 4, 4, 200, 4, 8, 2, P, None) < 0
+    assert lib.apgs_dmm_local_encoder_fused_f32(P, P, C.byref(mlp), C.byref(mlp), C.byref(mlp), 32, None, None, None,
+                                                4, 4, 200, 4, 2, P, P, P, P, None, None, None) < 0
+    assert b"uniforms" in lib.apgs_last_error()
+    assert lib.apgs_dmm_local_encoder_fused_f32(P, P, C.byref(mlp), C.byref(mlp), C.byref(mlp), 32, P, None, P,
+                                                4, 4, 200, 4, 2, P, P, P, P, None, None, None) < 0     # z_old needs its outputs
+    assert lib.apgs_dmm_decoder_hidden2_f32(P, C.byref(mlp), 32, 2, 0, P, None) < 0
+    # bmnist
+    assert lib.apgs_bmnist_template_match_f32(P, 0, 9216, P, 784, 784, 4, 4, 28, 96, 1, P, None) < 0      # DP > FP
+    assert lib.apgs_bmnist_template_match_f32(P, -1, 9216, P, 784, 784, 4, 4, 96, 28, 1, P, None) < 0
+    assert lib.apgs_bmnist_paste_subtract_f32(P, 0, 9216, P, 784, 0, P, P, 4, 4, 96, 28, P, None) < 0
