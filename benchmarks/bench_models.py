@@ -2,6 +2,9 @@
 (bit-identical to the reference on CPU) on a bounded sample.  particle-sweeps/s = S * B * sweeps / time(apg_objective).
 
     python benchmarks/bench_models.py [--out gpurun_out/models.json] [--no-cpu]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 benchmarks/bench_models.py --no-cpu
+        weak scaling along the instance axis: every rank runs the SAME per-GPU shape on its own instances (the path
+        shards along B with no data-path collective); a row then reports the slowest rank's time and N times the work.
 """
 import argparse
 import json
@@ -13,7 +16,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 FLAGS = {'loss_required': False, 'ess_required': True, 'mode_required': False, 'density_required': True}
-DEV = torch.device("cuda", 0)
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+DEV = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
 
 
 def gpu_time(fn, iters=5, warm=2):
@@ -123,15 +128,31 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    torch.cuda.set_device(DEV)
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=DEV)
     rows = []
     for fn, args in ((gmm, (10, 20, 5, 20)), (gmm, (1000, 1024, 10, 16)), (dmm, (100, 256, 7, 8)), (bmnist, (10, 64, 5, 2))):
-        rows.append(fn(*args, a.no_cpu))
-        r = rows[-1]
+        torch.manual_seed(1000 + RANK)                       # every rank owns different instances
+        r = fn(*args, a.no_cpu or WORLD > 1 or RANK != 0)
+        if WORLD > 1:                                        # slowest rank, N times the work (weak scaling along B)
+            for key in ("gpu_s", "graph_s"):
+                if key in r:
+                    t = torch.tensor([r[key]], dtype=torch.float64, device=DEV)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    r[key] = float(t)
+                    r[key.replace("_s", "_psw_s")] = WORLD * r["S"] * r["B"] * r["sweeps"] / r[key]
+            r["n_gpus"], r["B_per_gpu"] = WORLD, r["B"]
+        rows.append(r)
         if "cpu_psw_s" in r:
             r["gpu_over_cpu"] = r["gpu_psw_s"] / r["cpu_psw_s"]
-        print(json.dumps(r), flush=True)
-    if a.out:
+        if RANK == 0:
+            print(json.dumps(r), flush=True)
+    if a.out and RANK == 0:
         json.dump(rows, open(a.out, "w"), indent=1)
+    if WORLD > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
