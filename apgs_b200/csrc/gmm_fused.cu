@@ -3,15 +3,15 @@
 //       logit_nk = W2 . tanh(W1 [x_n ; mu_k ; tau_k] + b1) + b2,   q_n = softmax_k(logit_n)
 //   + categorical draw of z_n by inverse CDF from a supplied uniform (RNG stays in PyTorch)
 //   + the z-step importance weight (apgs/gmm/objectives.py:197-227) against z_old
-// in ONE pass over the particles: reads x (per instance), tau/mu (48 B), z_old (720 B) and the uniforms
-// (240 B) per particle and writes z_new (720 B) + a few scalars, instead of PyTorch's ~100 KB of
+// in ONE pass over the particles: reads x (per instance), tau/mu (48 B), z_old (720 B one-hot, or 64 B as labels) and
+// the uniforms (240 B) per particle and writes z_new (720 B / 64 B) + a few scalars, instead of PyTorch's ~100 KB of
 // (S,B,N,K,H) activations per particle.  The first Linear is split into its x / mu / tau column blocks:
 //   W1 [x;mu_k;tau_k] + b1 = (W1x x_n) + (W1m mu_k + W1t tau_k + b1) =: xh_n + e_k
 // and, because 2^(a+b) = 2^a 2^b, the exponential inside tanh(u) = 1 - 2/(2^(2u log2 e) + 1) factorises too:
-//   2^(xh'_n + e'_k) = Ex_n * Ee_k,   Ex_n = 2^xh'_n (one ex2 per point and hidden unit, shared by the K clusters),
+//   2^(xh'_n + e'_k) = Ex_n * Ee_k,   Ex_n = 2^xh'_n (a function of the data only: one table per CTA, see "tile mapping"),
 //   Ee_k = 2^e'_k (K*H values per particle, computed once in the prologue and kept in shared memory).
-// The inner loop is then  y = fma(Ex, Ee, 1) -> clamp -> batch inversion of four y -> fma  per tanh:
-// ~7 instructions and 0.6 SFU operations instead of 13 / 2.  Compute-bound (issue + SFU), not HBM-bound.
+// The inner loop is then  y = fma(Ex, Ee, c) -> batch inversion of four y with one MUFU.RCP -> fma  per tanh, in packed
+// fp32x2: 2.9 instructions and 0.25 SFU operations per tanh instead of 13 / 2.  Compute-bound (FMA pipe), not HBM-bound.
 #include "gmm_common.cuh"
 
 namespace apgs {

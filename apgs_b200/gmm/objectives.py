@@ -11,7 +11,11 @@ Differences in how the work is done:
   * softmax / ESS over S is one kernel (W1); resampling is ancestors + one gather launch for
     (tau, mu, z) with no int64 index expansion;
   * `x` may be passed as (B,N,D); the reference's S-replicated (S,B,N,D) is accepted and only
-    its first slice is read.
+    its first slice is read;
+  * inside `apg_objective` (decomposed block, evaluation flags) the assignments travel as uint8 labels (S,B,N) instead
+    of one-hot (S,B,N,K) floats -- the objective returns only the trace, so the one-hot form is never needed between
+    the one-shot and the last sweep; traces are identical bit for bit (`compact_labels` switches it off).  Called on
+    their own, the step functions take and return the reference's one-hot tensors.
 Gradients: the kernels are forward-only.  The APG loss is  sum_s w_s.detach() * (-log q_s), so the
 only graph autograd needs is that of the FORWARD proposal log-density; when `loss_required` is set and the encoder
 parameters require grad, that term is rebuilt with PyTorch ops (models.posterior_eta_torch / eta_log_q_torch / the
