@@ -10,8 +10,10 @@
 // and, because 2^(a+b) = 2^a 2^b, the exponential inside tanh(u) = 1 - 2/(2^(2u log2 e) + 1) factorises too:
 //   2^(xh'_n + e'_k) = Ex_n * Ee_k,   Ex_n = 2^xh'_n (a function of the data only: one table per CTA, see "tile mapping"),
 //   Ee_k = 2^e'_k (K*H values per particle, computed once in the prologue and kept in shared memory).
-// The inner loop is then  y = fma(Ex, Ee, c) -> batch inversion of four y with one MUFU.RCP -> fma  per tanh, in packed
-// fp32x2: 2.9 instructions and 0.25 SFU operations per tanh instead of 13 / 2.  Compute-bound (FMA pipe), not HBM-bound.
+// The inner loop is then  y = fma(Ex, Ee, c)  per tanh, and the output layer's  sum_h w_h / y_h  is accumulated four
+// hidden units at a time as ONE fraction (numerator and denominator built pairwise, one MUFU.RCP per four terms), in
+// packed fp32x2: 1.75 instructions (3.5 FMA-pipe cycles) and 0.25 SFU operations per tanh instead of 13 / 2.
+// Compute-bound (FMA pipe), not HBM-bound.
 #include "gmm_common.cuh"
 
 namespace apgs {
@@ -39,54 +41,76 @@ struct ZFusedArgs {
 // A CTA owns ONE instance b and P particles s0..s0+P-1 of it (rows r = s*B + b: P separate N*K*4-byte rows, each
 // moved by its own bulk copy).  Everything that depends only on the data is then shared by the whole CTA:
 // Ex_n[h] = 2^(W1x x_n)' is tabulated ONCE per CTA in shared memory (N*H ex2 instead of P*N*H), which takes the
-// exponentials out of the inner loop altogether -- per hidden unit a thread issues two LDS.128 (Ex of its four
-// points; Ee of the K clusters + the output weight) and, per cluster, 11 packed-fp32 instructions and one MUFU.RCP.
+// exponentials out of the inner loop altogether -- per quad of hidden units a thread issues 6 + 2K LDS.128 (Ex of its
+// four points, the output weights, Ee of the K clusters) and, per cluster and pair of points, 14 packed-fp32
+// instructions and two MUFU.RCP.
 //
-// Range contract of the factorised loop.  The batch inversion multiplies four y = Ex*Ee + 1 >= 1; everything is
-// carried scaled by 2^-31 (y' = Ex * (2^-31 Ee) + 2^-31, the 2^-31 folded into the Ee table and the output weight),
-// so y in [1, 2^62] keeps the product of four y' inside [2^-124, 2^124] and no clamp is needed.  A particle may
+// Range contract of the factorised loop.  The fraction's denominator is the product of four y = Ex*Ee + 1 >= 1 (four
+// hidden units of one point); the y are carried scaled by 2^-31 (y' = Ex * (2^-31 Ee) + 2^-31, the 2^-31 folded
+// into the Ee table; the accumulated sum comes out scaled by 2^31 and is rescaled once after the loop), so y in
+// [1, 2^62] keeps the product of four y' inside [2^-124, 2^124], the numerators (weight x three y') inside
+// |w| [2^-93, 2^95], and no clamp is needed.  A particle may
 // run this loop iff  (a) every e'_k[h] is in [-80, 80],  (b) XM[h] = max_n xh'_n[h] <= 126 (Ex finite), and
 // (c) max_h (XM[h] + max_k e'_k[h]) <= 61.  XM is per CTA, the e' test per particle; both are evaluated in the
 // prologue.  Any other particle (saturating pre-activations far beyond anything a trained encoder produces, or
 // NaN/inf inputs) runs the plain loop  y = 2^(xh' + e') + 1, 1/y by MUFU.RCP per element  -- exact for every
 // input, ~3x slower, and in practice never taken.
 
-template <int K, int KP>
+// sum over four hidden units of A_h / y_h as ONE fraction (pairwise: n/d = (A0 y1 + A1 y0)/(y0 y1), then the two pairs
+// combined the same way), for two points at a time in packed fp32: 14 packed instructions and one reciprocal per lane
+// for four tanh terms -- 3.5 FMA-pipe cycles per term against 4.25 for inverting each y (batch inversion) first.
+__device__ __forceinline__ f32x2 frac4(const f32x2 (&ex)[4], const f32x2 (&ee)[4], const f32x2 (&aw)[4], f32x2 c2,
+                                       f32x2 acc) {
+    const f32x2 y0 = fma2(ex[0], ee[0], c2), y1 = fma2(ex[1], ee[1], c2);
+    const f32x2 y2 = fma2(ex[2], ee[2], c2), y3 = fma2(ex[3], ee[3], c2);
+    const f32x2 n01 = fma2(aw[0], y1, mul2(aw[1], y0)), d01 = mul2(y0, y1);
+    const f32x2 n23 = fma2(aw[2], y3, mul2(aw[3], y2)), d23 = mul2(y2, y3);
+    const f32x2 n = fma2(n01, d23, mul2(n23, d01));
+    float dl, dh;
+    unpack2(mul2(d01, d23), dl, dh);
+    return fma2(n, pack2(rcp_ftz(dl), rcp_ftz(dh)), acc);
+}
+
+// ev_ptr: this particle's table, per quad of hidden units h0..h3 and cluster k the four values Ee'_k[h0..h3] (one
+// LDS.128) -- index ee_slot(h, k); aw_ptr: the CTA-wide output weights -2 W2[h].  H4 = H rounded up to 4 (padding rows: Ee' = 0, weight 0).  The accumulators
+// come out scaled by 2^31 (y' = 2^-31 y and the weights are unscaled), the caller multiplies by 2^-31.
+template <int K>
+__device__ __forceinline__ int ee_slot(int h, int k) { return (h >> 2) * (4 * K) + k * 4 + (h & 3); }
+
+template <int K>
 __device__ __forceinline__ void mlp_quad_fast(const unsigned char* ex_ptr, int ex_stride_b, const unsigned char* ev_ptr,
-                                              int H, f32x2 (&L02)[K], f32x2 (&L13)[K]) {
+                                              const unsigned char* aw_ptr, int H4, f32x2 (&L02)[K], f32x2 (&L13)[K]) {
     const f32x2 c2 = pack2(4.656612873077393e-10f, 4.656612873077393e-10f);   // 2^-31
-#pragma unroll 2
-    for (int h = 0; h < H; ++h) {
-        const ulonglong2 exq = *reinterpret_cast<const ulonglong2*>(ex_ptr + (size_t)h * ex_stride_b);
-        const f32x2 ex02 = exq.x, ex13 = exq.y;                       // (Ex[q0], Ex[q2]), (Ex[q1], Ex[q3])
-        float ev[KP];
+#pragma unroll 1
+    for (int h = 0; h < H4; h += 4) {
+        f32x2 ex02[4], ex13[4], aw[4];
 #pragma unroll
-        for (int i = 0; i < KP / 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(ev_ptr + ((size_t)h * KP + i * 4) * 4);
-            ev[i * 4 + 0] = v.x; ev[i * 4 + 1] = v.y; ev[i * 4 + 2] = v.z; ev[i * 4 + 3] = v.w;
+        for (int i = 0; i < 4; ++i) {
+            const ulonglong2 exq = *reinterpret_cast<const ulonglong2*>(ex_ptr + (size_t)(h + i) * ex_stride_b);
+            ex02[i] = exq.x; ex13[i] = exq.y;                         // (Ex[q0], Ex[q2]), (Ex[q1], Ex[q3])
         }
-        const f32x2 wm2p = pack2(ev[K], ev[K]);                       // -2 * W2[h] * 2^-31
+        {
+            const float4 v = *reinterpret_cast<const float4*>(aw_ptr + (size_t)h * 4);
+            aw[0] = pack2(v.x, v.x); aw[1] = pack2(v.y, v.y); aw[2] = pack2(v.z, v.z); aw[3] = pack2(v.w, v.w);
+        }
+        const float4* evq = reinterpret_cast<const float4*>(ev_ptr + (size_t)h * K * 4);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const f32x2 eep = pack2(ev[k], ev[k]);                    // 2^-31 Ee_k[h]
-            // 1/y' for four points with ONE reciprocal (batch inversion)
-            const f32x2 yA = fma2(ex02, eep, c2), yB = fma2(ex13, eep, c2);
-            float p01, p23;
-            unpack2(mul2(yA, yB), p01, p23);
-            const float r = rcp_ftz(p01 * p23);
-            const f32x2 rr = pack2(r * p23, r * p01);                 // (1/(y0 y1), 1/(y2 y3))
-            L02[k] = fma2(wm2p, mul2(rr, yB), L02[k]);                // 1/y0 = y1/(y0 y1), 1/y2 = y3/(y2 y3)
-            L13[k] = fma2(wm2p, mul2(rr, yA), L13[k]);
+        for (int k = 0; k < K; ++k) {                                 // cluster k of the four units: one LDS.128
+            const float4 v = evq[k];
+            const f32x2 ee[4] = {pack2(v.x, v.x), pack2(v.y, v.y), pack2(v.z, v.z), pack2(v.w, v.w)};
+            L02[k] = frac4(ex02, ee, aw, c2, L02[k]);
+            L13[k] = frac4(ex13, ee, aw, c2, L13[k]);
         }
     }
 }
 
-// the plain loop: ev holds the raw e'_k[h] and -2 W2[h]; xh' is recomputed exactly as the Ex table does
-template <int K, int KP, int D, int PB>
-__device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv)[PB][D], const float* ev, int H,
-                                               float (&logit)[PB][K]) {
+// the plain loop: ev holds the raw e'_k[h] at ee_slot(h, k), aw the weights -2 W2[h];
+// xh' is recomputed exactly as the Ex table does
+template <int K, int D, int PB>
+__device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv)[PB][D], const float* ev, const float* aw,
+                                               int H, float (&logit)[PB][K]) {
     for (int h = 0; h < H; ++h) {
-        const float wm2 = ev[h * KP + K];
+        const float wm2 = aw[h];
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
             float acc = 0.f;
@@ -94,7 +118,7 @@ __device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv
             for (int d = 0; d < D; ++d) acc = fmaf(TANH_PRESCALE * __ldg(W1 + h * (3 * D) + d), xv[q][d], acc);
 #pragma unroll
             for (int k = 0; k < K; ++k)      // 2^a = +inf gives 1/y = 0 (tanh = 1), 2^a = 0 gives 1/y = 1 (tanh = -1)
-                logit[q][k] = fmaf(wm2, rcp_ftz(ex2_ftz(acc + ev[h * KP + k]) + 1.f), logit[q][k]);
+                logit[q][k] = fmaf(wm2, rcp_ftz(ex2_ftz(acc + ev[ee_slot<K>(h, k)]) + 1.f), logit[q][k]);
         }
     }
 }
@@ -106,12 +130,12 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     __shared__ unsigned long long bar;
     __shared__ float s_misc[1 + K];
     constexpr int KD = K * D;
-    constexpr int KP = ((K + 1) + 3) / 4 * 4;                  // Ee_0..Ee_{K-1}, -2 W2[h], padding
-    const int N = a.N, H = a.H;
+    constexpr int RK = K;                                      // table floats per hidden unit
+    const int N = a.N, H = a.H, H4 = (a.H + 3) / 4 * 4;
     const int NK = N * K;
     const int nIt = (N + LANES * PB - 1) / (LANES * PB);       // passes of 32 points
     const int EXS = nIt * LANES * PB;                          // floats of Ex per hidden unit
-    const int EPs = H * KP + 4;                                // per-particle stride of the Ee table (floats)
+    const int EPs = H4 * RK + 4;                               // per-particle stride of the Ee table (floats)
     const bool lab_old = a.zl_old != nullptr, lab_new = a.zl_new != nullptr;
     const bool has_bwd = a.z_old != nullptr || lab_old;
     const bool forced = a.z_forced != nullptr;
@@ -120,10 +144,11 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const size_t tile_f = tiles ? ((size_t)P * NK + 3) / 4 * 4 : 0;
     float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
     float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
-    float* s_ex = s_zn + tile_f;                               // H * EXS, slot order inside a quad: q0 q2 q1 q3
-    float* s_e = s_ex + (size_t)H * EXS;                       // P * EPs
-    float* s_xm = s_e + (size_t)P * EPs;                       // H
-    float* s_tab = s_xm + (H + 3) / 4 * 4;                     // P * KD * 3: mu, 1/(2 var), log sigma + c
+    float* s_ex = s_zn + tile_f;                               // H4 * EXS, slot order inside a quad: q0 q2 q1 q3
+    float* s_e = s_ex + (size_t)H4 * EXS;                      // P * EPs
+    float* s_xm = s_e + (size_t)P * EPs;                       // H4
+    float* s_aw = s_xm + H4;                                   // H4: -2 W2[h], 0 in the padding rows
+    float* s_tab = s_aw + H4;                                  // P * KD * 3: mu, 1/(2 var), log sigma + c
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
     const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
@@ -163,6 +188,11 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
 #pragma unroll
             for (int d = 0; d < D; ++d) xr[si][d] = (slot < EXS && n < N) ? __ldg(xb + n * D + d) : NAN;
+        }
+        for (int h = H + warp; h < H4; h += (P * LANES) / 32)       // padding rows of the last quad of hidden units
+            for (int slot = lane; slot < EXS; slot += 32) s_ex[(size_t)h * EXS + slot] = 0.f;
+        for (int i = threadIdx.x; i < H4; i += P * LANES) {
+            s_aw[i] = (i < H) ? -2.f * __ldg(a.W2 + i) : 0.f;
         }
         for (int h = warp; h < H; h += (P * LANES) / 32) {
             float w[D];
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             s_misc[1 + lane] = logf(fminf(fmaxf(__fdiv_rn(__ldg(a.rpi + lane), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
         }
     }
-    __syncthreads();                                               // s_xm, s_misc
+    __syncthreads();                                               // s_xm, s_aw, s_misc
     const float b2 = s_misc[0];
     float logpi[K];
 #pragma unroll
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 const float ee = TANH_PRESCALE * acc;
                 emax = fmaxf(emax, ee);
                 elo = fminf(elo, ee);
-                ep[h * KP + k] = ee;
+                ep[ee_slot<K>(h, k)] = ee;
                 if (!(ee == ee)) ehi = INFINITY;                               // NaN: fmaxf/fminf would drop it
             }
             ehi = fmaxf(ehi, emax);
@@ -265,15 +295,12 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         elo = fminf(elo, __shfl_xor_sync(0xffffffffu, elo, o));
     }
     const bool fast = (bound <= 61.f) && (ehi <= 80.f) && (elo >= -80.f);
-    if (valid) {                                  // each lane converts the entries it wrote itself
-        for (int h = j; h < H; h += LANES) {
-            const float w2 = -2.f * __ldg(a.W2 + h);
-            if (fast) {
+    if (valid && fast) {                          // each lane converts the entries it wrote itself
+        for (int h = j; h < H4; h += LANES) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) ep[h * KP + k] = ex2_ftz(ep[h * KP + k] - 31.f);    // 2^-31 Ee_k[h]
-                ep[h * KP + K] = w2 * 4.656612873077393e-10f;
-            } else {
-                ep[h * KP + K] = w2;
+            for (int k = 0; k < K; ++k) {
+                const int o = ee_slot<K>(h, k);
+                ep[o] = (h < H) ? ex2_ftz(ep[o] - 31.f) : 0.f;                                   // 2^-31 Ee_k[h]
             }
         }
     }
@@ -302,17 +329,25 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             if (fast) {
                 f32x2 L02[K], L13[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) { L02[k] = pack2(b2, b2); L13[k] = L02[k]; }
+                for (int k = 0; k < K; ++k) { L02[k] = 0ull; L13[k] = 0ull; }
                 const unsigned char* exb = reinterpret_cast<const unsigned char*>(s_ex + (size_t)(it * LANES + j) * PB);
-                mlp_quad_fast<K, KP>(exb, EXS * 4, reinterpret_cast<const unsigned char*>(ep), H, L02, L13);
+                mlp_quad_fast<K>(exb, EXS * 4, reinterpret_cast<const unsigned char*>(ep),
+                                 reinterpret_cast<const unsigned char*>(s_aw), H4, L02, L13);
 #pragma unroll
-                for (int k = 0; k < K; ++k) { unpack2(L02[k], logit[0][k], logit[2][k]); unpack2(L13[k], logit[1][k], logit[3][k]); }
+                for (int k = 0; k < K; ++k) {
+                    unpack2(L02[k], logit[0][k], logit[2][k]);
+                    unpack2(L13[k], logit[1][k], logit[3][k]);
+                }
+#pragma unroll
+                for (int q = 0; q < PB; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) logit[q][k] = fmaf(logit[q][k], 4.656612873077393e-10f, b2);
             } else {
 #pragma unroll
                 for (int q = 0; q < PB; ++q)
 #pragma unroll
                     for (int k = 0; k < K; ++k) logit[q][k] = b2;
-                mlp_quad_plain<K, KP, D, PB>(a.W1, xv, ep, H, logit);
+                mlp_quad_plain<K, D, PB>(a.W1, xv, ep, s_aw, H, logit);
             }
             // ---- per point: softmax, draw, log-densities
 #pragma unroll
@@ -431,12 +466,12 @@ constexpr int kFP = 32, kFLanes = 8, kFPB = 4;
 
 template <int K, int D>
 static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
-    constexpr int KP = ((K + 1) + 3) / 4 * 4;
+    const int H4 = (a.H + 3) / 4 * 4;
     const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
     const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
     const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
-    const size_t smem = (2 * tile_f + (size_t)a.H * nIt * kFLanes * kFPB + (size_t)kFP * (a.H * KP + 4) +
-                         (size_t)(a.H + 3) / 4 * 4 + (size_t)kFP * K * D * 3) * 4;
+    const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * (H4 * K + 4) +
+                         (size_t)2 * H4 + (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     auto kern = k_gmm_z_fused<K, D, kFP, kFLanes, kFPB>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
