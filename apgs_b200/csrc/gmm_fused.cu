@@ -81,7 +81,7 @@ template <int K>
 __device__ __forceinline__ void mlp_quad_fast(const unsigned char* ex_ptr, int ex_stride_b, const unsigned char* ev_ptr,
                                               const unsigned char* aw_ptr, int H4, f32x2 (&L02)[K], f32x2 (&L13)[K]) {
     const f32x2 c2 = pack2(4.656612873077393e-10f, 4.656612873077393e-10f);   // 2^-31
-#pragma unroll 1
+#pragma unroll 1      // unroll 2 measured slower (1.60 vs 1.53 ms): the second quad's table loads raise the register pressure
     for (int h = 0; h < H4; h += 4) {
         f32x2 ex02[4], ex13[4], aw[4];
 #pragma unroll
@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     float* s_e = s_ex + (size_t)H4 * EXS;                      // P * EPs
     float* s_xm = s_e + (size_t)P * EPs;                       // H4
     float* s_aw = s_xm + H4;                                   // H4: -2 W2[h], 0 in the padding rows
-    float* s_tab = s_aw + H4;                                  // P * KD * 3: mu, 1/(2 var), log sigma + c
+    float* s_em = s_aw + H4;                                   // P * H4: max_k e'_k[h] per particle (range test)
+    float* s_tab = s_em + (size_t)P * H4;                            // P * KD * 3: mu, 1/(2 var), log sigma + c
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
     const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         for (int i = threadIdx.x; i < H4; i += P * LANES) {
             s_aw[i] = (i < H) ? -2.f * __ldg(a.W2 + i) : 0.f;
         }
+#pragma unroll 4
         for (int h = warp; h < H; h += (P * LANES) / 32) {
             float w[D];
 #pragma unroll
@@ -244,38 +246,45 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             s_misc[1 + lane] = logf(fminf(fmaxf(__fdiv_rn(__ldg(a.rpi + lane), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
         }
     }
-    __syncthreads();                                               // s_xm, s_aw, s_misc
-    const float b2 = s_misc[0];
-    float logpi[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) logpi[k] = s_misc[1 + k];
-
-    // ---- per-particle pieces: e'_k[h] = 2 log2(e) (b1 + W1m mu_k + W1t tau_k), the range test, Normal tables
-    float bound = -INFINITY, elo = INFINITY, ehi = -INFINITY;
+    // ---- per-particle pieces: e'_k[h] = 2 log2(e) (b1 + W1m mu_k + W1t tau_k), Normal tables.  The Ee table is written
+    // for the factorised loop right away (2^-31 Ee_k[h]); the rare particle that fails the range test below rewrites
+    // its entries with the raw e' for the plain loop.
+    float elo = INFINITY, ehi = -INFINITY;
     float* ep = s_e + (size_t)p * EPs;
+    float* em = s_em + (size_t)p * H4;
+    float tk[KD], mk[KD];
     if (valid) {
-        float tk[KD], mk[KD];
 #pragma unroll
         for (int e = 0; e < KD; ++e) { tk[e] = __ldg(a.tau + r * KD + e); mk[e] = __ldg(a.mu + r * KD + e); }
-        for (int h = j; h < H; h += LANES) {
-            const float bh = __ldg(a.b1 + h);
+#pragma unroll 2
+        for (int h = j; h < H4; h += LANES) {
+            const bool live = h < H;
+            const float bh = live ? __ldg(a.b1 + h) : 0.f;
+            float wm[D], wt[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                wm[d] = live ? __ldg(a.W1 + h * 3 * D + D + d) : 0.f;
+                wt[d] = live ? __ldg(a.W1 + h * 3 * D + 2 * D + d) : 0.f;
+            }
             float emax = -INFINITY;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float acc = bh;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mk[k * D + d], acc);
-                    acc = fmaf(__ldg(a.W1 + h * 3 * D + 2 * D + d), tk[k * D + d], acc);
+                    acc = fmaf(wm[d], mk[k * D + d], acc);
+                    acc = fmaf(wt[d], tk[k * D + d], acc);
                 }
                 const float ee = TANH_PRESCALE * acc;
-                emax = fmaxf(emax, ee);
-                elo = fminf(elo, ee);
-                ep[ee_slot<K>(h, k)] = ee;
-                if (!(ee == ee)) ehi = INFINITY;                               // NaN: fmaxf/fminf would drop it
+                if (live) {
+                    emax = fmaxf(emax, ee);
+                    elo = fminf(elo, ee);
+                    if (!(ee == ee)) ehi = INFINITY;                           // NaN: fmaxf/fminf would drop it
+                }
+                ep[ee_slot<K>(h, k)] = live ? ex2_ftz(ee - 31.f) : 0.f;        // 2^-31 Ee_k[h]; padding rows 0
             }
+            em[h] = emax;
             ehi = fmaxf(ehi, emax);
-            bound = fmaxf(bound, s_xm[h] + emax);
         }
         float* tab = s_tab + (size_t)p * (KD * 3);
         for (int e = j; e < KD; e += LANES) {
@@ -288,6 +297,14 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             tab[e * 3 + 2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
         }
     }
+    __syncthreads();                                               // s_xm, s_aw, s_misc
+    const float b2 = s_misc[0];
+    float logpi[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) logpi[k] = s_misc[1 + k];
+    float bound = -INFINITY;
+    if (valid)
+        for (int h = j; h < H; h += LANES) bound = fmaxf(bound, s_xm[h] + em[h]);    // each lane reads what it wrote
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) {
         bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
@@ -295,12 +312,18 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         elo = fminf(elo, __shfl_xor_sync(0xffffffffu, elo, o));
     }
     const bool fast = (bound <= 61.f) && (ehi <= 80.f) && (elo >= -80.f);
-    if (valid && fast) {                          // each lane converts the entries it wrote itself
-        for (int h = j; h < H4; h += LANES) {
+    if (valid && !fast) {                         // plain loop: raw e' (each lane rewrites the entries it owns)
+        for (int h = j; h < H; h += LANES) {
+            const float bh = __ldg(a.b1 + h);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const int o = ee_slot<K>(h, k);
-                ep[o] = (h < H) ? ex2_ftz(ep[o] - 31.f) : 0.f;                                   // 2^-31 Ee_k[h]
+                float acc = bh;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mk[k * D + d], acc);
+                    acc = fmaf(__ldg(a.W1 + h * 3 * D + 2 * D + d), tk[k * D + d], acc);
+                }
+                ep[ee_slot<K>(h, k)] = TANH_PRESCALE * acc;
             }
         }
     }
@@ -471,7 +494,7 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
     const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
     const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * (H4 * K + 4) +
-                         (size_t)2 * H4 + (size_t)kFP * K * D * 3) * 4;
+                         (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     auto kern = k_gmm_z_fused<K, D, kFP, kFLanes, kFPB>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");

@@ -4,7 +4,7 @@ from apgs_b200.gmm import apg_objective, init_apg_models
 from apgs_b200.gmm.sim import simulate
 from apgs_b200.resampler import Resampler
 dev = torch.device("cuda", 0)
-S, B, sweeps = 1000, 1024, 2
+S, B, sweeps = 1000, 1024, 4
 torch.manual_seed(0)
 models = init_apg_models(3, 2, 32, True, dev)
 x = simulate(B).to(dev)
