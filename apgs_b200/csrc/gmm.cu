@@ -285,13 +285,20 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     const unsigned int rb = (unsigned int)NK * 4u;
     const bool labels = a.zl != nullptr;
     const bool bulk_in = !labels && (rb & 15u) == 0 && aligned(a.z, 16);
-    unsigned char* s_lab = reinterpret_cast<unsigned char*>(s_z);       // [P][N] in label mode (the z region is free then)
+    unsigned char* s_lab = reinterpret_cast<unsigned char*>(s_z);       // [P][LS] in label mode (the z region is free then)
+    const int LS = (N + 15) & ~15;                                      // 16-byte rows: one LDG.128 per 16 labels when the
+    const bool lab_vec = labels && (a.LN & 15) == 0 && a.LN >= LS && aligned(a.zl, 16);   // caller pads its rows likewise
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows : 0u);
     if (valid) {
         if (labels) {
-            for (int i = j; i < N; i += LANES) s_lab[(size_t)p * N + i] = __ldg(a.zl + r * a.LN + i);
+            if (lab_vec) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.zl + r * a.LN);
+                for (int i = j; i < LS / 16; i += LANES) reinterpret_cast<uint4*>(s_lab + (size_t)p * LS)[i] = __ldg(src + i);
+            } else {
+                for (int i = j; i < N; i += LANES) s_lab[(size_t)p * LS + i] = __ldg(a.zl + r * a.LN + i);
+            }
         } else if (bulk_in) {
             if (j == 0) bulk_g2s(s_z + (size_t)p * ZS, a.z + r * NK, rb, &bar);
         } else {
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
         for (int n = j; n < N; n += LANES) {
             int lab = 0;
             if (labels) {
-                lab = min((int)s_lab[(size_t)p * N + n], K - 1);
+                lab = min((int)s_lab[(size_t)p * LS + n], K - 1);
             } else {
                 float best = zr[n * K];
 #pragma unroll
