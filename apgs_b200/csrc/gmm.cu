@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     // structure-of-arrays table: plane e holds T_e[n*K + label].  The 8 lanes of a particle read rows 3n + label with
     // n = j + 8 it, i.e. 8..24 distinct consecutive-ish addresses, and the 4 particles of a warp read the same window:
     // every LDS.32 of the warp is conflict-free (an array-of-structs row of 16 floats costs ~2.3x the wavefronts).
+    // Pairs of planes read as LDS.64 + add.f32x2 (half the instructions) were measured slower: 0.437 vs 0.418 ms.
     float* s_tab = s_z + (zreg + 3) / 4 * 4;                            // [TE][NK]
     float* s_x = s_tab + (size_t)TE * NK;                               // [N][D]
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
