@@ -50,8 +50,8 @@ struct ZFusedArgs {
 // into the Ee table; the accumulated sum comes out scaled by 2^31 and is rescaled once after the loop), so y in
 // [1, 2^62] keeps the product of four y' inside [2^-124, 2^124], the numerators (weight x three y') inside
 // |w| [2^-93, 2^95], and no clamp is needed.  A particle may
-// run this loop iff  (a) every e'_k[h] is in [-80, 80],  (b) XM[h] = max_n xh'_n[h] <= 126 (Ex finite), and
-// (c) max_h (XM[h] + max_k e'_k[h]) <= 61.  XM is per CTA, the e' test per particle; both are evaluated in the
+// run this loop iff  (a) every e'_k[h] is in [-80, 80],  (b) XM[h] = max_n xh'_n[h] <= 126 (Ex finite),
+// (c) max_h (XM[h] + max_k e'_k[h]) <= 61, and (d) max_h |W2[h]| <= 2^24.  XM is per CTA, the e' test per particle; both are evaluated in the
 // prologue.  Any other particle (saturating pre-activations far beyond anything a trained encoder produces, or
 // NaN/inf inputs) runs the plain loop  y = 2^(xh' + e') + 1, 1/y by MUFU.RCP per element  -- exact for every
 // input, ~3x slower, and in practice never taken.
@@ -235,10 +235,20 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     // per-CTA scalars, once: b2' = b2 + sum_h W2[h]  (tanh = 1 - 2/y  =>  sum_h w2_h tanh_h = sum_h w2_h - sum_h 2 w2_h / y_h,
     // the loops accumulate the second sum) and the clamped log prior of the assignments
     if (warp == 0) {
-        float part = 0.f;
-        for (int i = lane; i < H; i += 32) part += __ldg(a.W2 + i);
+        float part = 0.f, wmax = 0.f;
+        for (int i = lane; i < H; i += 32) {
+            const float w = __ldg(a.W2 + i);
+            part += w;
+            wmax = fmaxf(wmax, (w == w) ? fabsf(w) : INFINITY);
+        }
         part = warp_sum(part);
-        if (lane == 0) s_misc[0] = __ldg(a.b2) + part;
+        wmax = warp_max(wmax);
+        if (lane == 0) {
+            s_misc[0] = __ldg(a.b2) + part;
+            // (d) output weights: the numerators are |w| [2^-93, 2^95]; beyond 2^24 (or NaN) the CTA takes the plain
+            // loop -- signalled through XM[0], which this warp's lane 0 wrote itself
+            if (!(wmax <= 16777216.f)) s_xm[0] = INFINITY;
+        }
         if (lane < K) {
             float sp = 0.f;
 #pragma unroll

@@ -423,7 +423,9 @@ def test_N1_fused_z_step_teacher_forced_vs_reference_golden(golden):
     _close(w.log_w, _t(g, "z_log_w"), rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="log_w")
 
 
-@pytest.mark.parametrize("S,B,N,K,D,H", [(6, 5, 60, 3, 2, 32), (37, 3, 41, 4, 2, 16), (33, 2, 9, 3, 3, 48)])
+# H = 10, 7: hidden widths that are not a multiple of four (the fused loop pads its tables to quads of hidden units)
+@pytest.mark.parametrize("S,B,N,K,D,H", [(6, 5, 60, 3, 2, 32), (37, 3, 41, 4, 2, 16), (33, 2, 9, 3, 3, 48),
+                                         (5, 4, 23, 3, 2, 10), (40, 2, 60, 2, 2, 7)])
 def test_N1_fused_sampling_is_inverse_cdf_of_oracle_probs(S, B, N, K, D, H):
     from apgs_b200.gmm import kernels
     torch.manual_seed(S + H)
@@ -469,6 +471,28 @@ def test_N1_fused_saturating_preactivations_take_the_plain_loop(xs_scale, w_scal
     _close(q, q_ref, rtol=3e-5, atol=2e-7, what="q_probs (saturating)")
     z_new = z_new.cpu()
     assert bool((z_new.sum(-1) == 1).all())
+
+
+def test_N1_fused_huge_output_weights_take_the_plain_loop():
+    """output-layer weights beyond 2^24 would overflow the numerators of the fraction-form loop: range test (d)."""
+    from apgs_b200.gmm import kernels
+    S, B, N, K, D, H = 9, 3, 60, 3, 2, 32
+    torch.manual_seed(4)
+    P = og.make_params(K, D, H)
+    enc = {k: v.clone() for k, v in P["enc_apg_z"].items()}
+    enc["pi_log_prob.2.weight"] = enc["pi_log_prob.2.weight"] * 1e8
+    enc["pi_log_prob.2.weight"][0, 3:] = 0.0                       # three live units: logits stay comparable
+    x = torch.randn(B, N, D)
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    tau, mu = torch.rand(S, B, K, D) * 3 + 0.1, torch.randn(S, B, K, D)
+    u = torch.rand(S, B, N)
+    q_ref = og.enc_apg_z_probs(enc, xs, tau, mu)
+    mlp = [enc[k].to(DEV) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+    z_new, q, _ = kernels.z_step_fused(x.to(DEV), tau.to(DEV), mu.to(DEV), mlp, _Gen(K, D), uniforms=u.to(DEV), want_q=True)
+    assert bool(torch.isfinite(q).all())
+    assert bool((z_new.cpu().sum(-1) == 1).all())
+    # logits of magnitude 1e8 carry fp32 rounding of ~1e1, so q is one-hot: compare the argmax (a near-tie may flip)
+    assert float((q.cpu().argmax(-1) != q_ref.argmax(-1)).float().mean()) <= 2e-3
 
 
 def test_sweep_statistics_torch_encoder_path():
@@ -633,7 +657,7 @@ def test_N4_gibbs_and_bpg_objectives_match_reference_traces_statistically(golden
 
 
 # ------------------------------------------------------------------ compact labels inside a sweep
-@pytest.mark.parametrize("S,B,N,K,D,H", [(37, 5, 60, 3, 2, 32), (9, 3, 41, 4, 2, 16), (33, 2, 9, 3, 2, 8)])
+@pytest.mark.parametrize("S,B,N,K,D,H", [(37, 5, 60, 3, 2, 32), (9, 3, 41, 4, 2, 16), (33, 2, 9, 3, 2, 8), (11, 3, 30, 3, 2, 10)])
 def test_label_mode_equals_one_hot_mode_bit_for_bit(S, B, N, K, D, H):
     """the label entries (z as one byte per point) give exactly the outputs of the one-hot entries on the same inputs
     and uniforms: z step (draw, weights, density, q_probs) and eta posterior + statistics."""
