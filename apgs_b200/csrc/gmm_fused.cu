@@ -123,7 +123,9 @@ __device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv
     }
 }
 
-template <int K, int D, int P, int LANES, int PB>
+// LEAN: the launch a sweep repeats -- labels in, labels out, uniforms given, no one-hot rows, no per-point outputs.
+// The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
+template <int K, int D, int P, int LANES, int PB, bool LEAN>
 __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -136,11 +138,13 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const int nIt = (N + LANES * PB - 1) / (LANES * PB);       // passes of 32 points
     const int EXS = nIt * LANES * PB;                          // floats of Ex per hidden unit
     const int EPs = H4 * RK + 4;                               // per-particle stride of the Ee table (floats)
-    const bool lab_old = a.zl_old != nullptr, lab_new = a.zl_new != nullptr;
-    const bool has_bwd = a.z_old != nullptr || lab_old;
-    const bool forced = a.z_forced != nullptr;
-    const bool hot_new = a.z_new != nullptr;                               // one-hot z_new wanted (labels may come along)
-    const bool tiles = a.z_old != nullptr || forced || hot_new;           // any one-hot row staged in / out?
+    const bool lab_old = LEAN || a.zl_old != nullptr, lab_new = LEAN || a.zl_new != nullptr;
+    const bool has_bwd = LEAN || a.z_old != nullptr || lab_old;
+    const bool forced = !LEAN && a.z_forced != nullptr;
+    const bool hot_new = !LEAN && a.z_new != nullptr;                      // one-hot z_new wanted (labels may come along)
+    const bool tiles = !LEAN && (a.z_old != nullptr || forced || hot_new); // any one-hot row staged in / out?
+    const bool want_q = !LEAN && a.q_probs != nullptr, want_lw = !LEAN && a.lw_local != nullptr;
+    const bool want_lq = !LEAN && a.lq_local != nullptr;
     const size_t tile_f = tiles ? ((size_t)P * NK + 3) / 4 * 4 : 0;
     float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
     float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
@@ -159,12 +163,14 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const int rows = min(P, a.S - s0);
     const unsigned int rb = (unsigned int)NK * 4u;
     // a row goes through the bulk-copy engine when its size keeps every row 16-byte aligned
-    const bool old_tile = a.z_old != nullptr;
+    const bool old_tile = !LEAN && a.z_old != nullptr;
     const bool bulk_in = (rb & 15u) == 0 && (!old_tile || aligned(a.z_old, 16)) && (!forced || aligned(a.z_forced, 16));
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows * ((old_tile ? 1u : 0u) + (forced ? 1u : 0u)) : 0u);
-    if (valid) {
+    if (!LEAN) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows * ((old_tile ? 1u : 0u) + (forced ? 1u : 0u)) : 0u);
+    }
+    if (!LEAN && valid) {
         if (bulk_in) {
             if (j == 0) {
                 if (old_tile) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + r * NK, rb, &bar);
@@ -337,7 +343,8 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             }
         }
     }
-    stage_wait(&bar, 0);                                           // rows landed; also publishes s_e / s_tab
+    if (LEAN) __syncthreads();                                     // publishes s_e / s_tab
+    else stage_wait(&bar, 0);                                      // rows landed; also publishes s_e / s_tab
 
     PlainF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;     // <= ceil(N/LANES) terms per lane
     if (valid) {
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, pr[k]);            // Categorical renormalisation
                 const float rsq = rcp_ftz(sq);
-                if (a.q_probs != nullptr) {
+                if (want_q) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) a.q_probs[(r * N + n) * K + k] = pr[k];
                 }
@@ -456,9 +463,9 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                     const float wb = __fsub_rn(__fadd_rn(llb, lpb), lqb);
                     const float loc = __fsub_rn(wf, wb);
                     A_loc.add(loc);
-                    if (a.lw_local != nullptr) a.lw_local[r * N + n] = loc;
+                    if (want_lw) a.lw_local[r * N + n] = loc;
                 }
-                if (a.lq_local != nullptr) a.lq_local[r * N + n] = lqf;
+                if (want_lq) a.lq_local[r * N + n] = lqf;
             }
         }
     }
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         if (a.dens != nullptr) a.dens[r] = __fadd_rn(ll_f, lpz_f);
     }
     // ---- z_new rows out (one bulk store per particle row); nothing to do in label mode
-    if (a.z_new == nullptr) return;
+    if (LEAN || a.z_new == nullptr) return;
     const bool bulk_out = (rb & 15u) == 0 && aligned(a.z_new, 16);
     if (bulk_out) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
@@ -506,7 +513,8 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * (H4 * K + 4) +
                          (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
-    auto kern = k_gmm_z_fused<K, D, kFP, kFLanes, kFPB>;
+    const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local;
+    auto kern = lean ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true> : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (long long)a.B * ((a.S + kFP - 1) / kFP);
     if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_z_fused: S*B too large for one launch");
