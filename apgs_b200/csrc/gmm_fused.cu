@@ -125,7 +125,8 @@ __device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv
 
 // LEAN: the launch a sweep repeats -- labels in, labels out, uniforms given, no one-hot rows, no per-point outputs.
 // The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
-template <int K, int D, int P, int LANES, int PB, bool LEAN>
+// HC / NC: hidden width and points per instance when known at compile time (the reference's 32 and 60), else 0.
+template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0>
 __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     __shared__ float s_misc[1 + K];
     constexpr int KD = K * D;
     constexpr int RK = K;                                      // table floats per hidden unit
-    const int N = a.N, H = a.H, H4 = (a.H + 3) / 4 * 4;
+    const int N = NC ? NC : a.N, H = HC ? HC : a.H, H4 = (H + 3) / 4 * 4;
     const int NK = N * K;
     const int nIt = (N + LANES * PB - 1) / (LANES * PB);       // passes of 32 points
     const int EXS = nIt * LANES * PB;                          // floats of Ex per hidden unit
@@ -514,7 +515,10 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
                          (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local;
-    auto kern = lean ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true> : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>;
+    auto kern = lean ? (a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60>
+                                               : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32>)
+                                  : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true>)
+                     : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (long long)a.B * ((a.S + kFP - 1) / kFP);
     if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_z_fused: S*B too large for one launch");
