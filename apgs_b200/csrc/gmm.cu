@@ -259,7 +259,7 @@ __host__ __device__ inline int nss_im_zstride(int NK) {
     return st;
 }
 
-template <int K, int D, int P, int LANES, bool STATS>
+template <int K, int D, int P, int LANES, bool STATS, int NC = 0>   // NC: points per instance when known at compile time
 __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     constexpr int TE = K + 2 * KD;                                      // table planes: gamma, gamma x', gamma x'^2
     constexpr int ST = 1 + 2 * D, NS = K * ST;                          // plain statistics per particle
     constexpr int RW = (TE > NS ? TE : NS) | 1;                         // reduction row (odd stride: no bank conflicts)
-    const int N = a.N, NK = N * K;
+    const int N = NC ? NC : a.N, NK = N * K;
     const int ZS = nss_im_zstride(NK);
     const size_t zreg = max((size_t)P * ZS, (size_t)P * LANES * RW);    // z rows, later the cross-lane reduction buffer
     float* s_z = reinterpret_cast<float*>(smem);
@@ -809,6 +809,7 @@ static int launch_nss_im(const NssArgs& a, cudaStream_t st) {
     const size_t smem = (zreg + (size_t)a.N * K * TE + (size_t)a.N * D) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_eta_posterior: N=%d too large for one tile", a.N);
     void (*kern)(NssArgs, int) = a.stats != nullptr ? k_gmm_nss_im<K, D, kP, kLanes, true> : k_gmm_nss_im<K, D, kP, kLanes, false>;
+    if (a.stats != nullptr && a.N == 60) kern = k_gmm_nss_im<K, D, kP, kLanes, true, 60>;      // the reference's data set
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (long long)a.B * ((S + kP - 1) / kP);
     if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_eta_posterior: S*B too large for one launch");
