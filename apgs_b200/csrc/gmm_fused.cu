@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     float* s_aw = s_xm + H4;                                   // H4: -2 W2[h], 0 in the padding rows
     float* s_em = s_aw + H4;                                   // P * H4: max_k e'_k[h] per particle (range test)
     float* s_tab = s_em + (size_t)P * H4;                            // P * KD * 3: mu, 1/(2 var), log sigma + c
+    float* s_x = s_tab + (size_t)P * KD * 3;                         // N * D: the instance's points (read after the MLP)
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
     const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         for (int i = threadIdx.x; i < H4; i += P * LANES) {
             s_aw[i] = (i < H) ? -2.f * __ldg(a.W2 + i) : 0.f;
         }
+        for (int i = threadIdx.x; i < N * D; i += P * LANES) s_x[i] = __ldg(xb + i);
 #pragma unroll 4
         for (int h = warp; h < H; h += (P * LANES) / 32) {
             float w[D];
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     if (valid) {
 #pragma unroll
         for (int e = 0; e < KD; ++e) { tk[e] = __ldg(a.tau + r * KD + e); mk[e] = __ldg(a.mu + r * KD + e); }
-#pragma unroll 2
+#pragma unroll 4
         for (int h = j; h < H4; h += LANES) {
             const bool live = h < H;
             const float bh = live ? __ldg(a.b1 + h) : 0.f;
@@ -356,13 +358,11 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         const float* tab = s_tab + (size_t)p * (KD * 3);
         for (int it = 0; it < nIt; ++it) {
             const int n0 = it * (LANES * PB) + j;
-            float xv[PB][D], logit[PB][K], uq[PB];
+            float logit[PB][K], uq[PB];
             int lbq[PB];
 #pragma unroll
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
-#pragma unroll
-                for (int d = 0; d < D; ++d) xv[q][d] = (n < N) ? __ldg(xb + n * D + d) : 0.f;
                 uq[q] = (n < N && !forced) ? __ldg(a.u + r * N + n) : 0.f;      // in flight during the MLP
                 lbq[q] = (n < N && lab_old) ? (int)__ldg(zlo + n) : 0;
             }
@@ -388,13 +388,21 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 for (int q = 0; q < PB; ++q)
 #pragma unroll
                     for (int k = 0; k < K; ++k) logit[q][k] = b2;
-                mlp_quad_plain<K, D, PB>(a.W1, xv, ep, s_aw, H, logit);
+                float xq[PB][D];
+#pragma unroll
+                for (int q = 0; q < PB; ++q)
+#pragma unroll
+                    for (int d = 0; d < D; ++d) xq[q][d] = (n0 + q * LANES < N) ? s_x[(n0 + q * LANES) * D + d] : 0.f;
+                mlp_quad_plain<K, D, PB>(a.W1, xq, ep, s_aw, H, logit);
             }
             // ---- per point: softmax, draw, log-densities
 #pragma unroll
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
                 if (n >= N) continue;
+                float xn[D];                                          // the point itself: only the log-densities need it
+#pragma unroll
+                for (int d = 0; d < D; ++d) xn[d] = s_x[n * D + d];
                 float mx = logit[q][0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) mx = fmaxf(mx, logit[q][k]);
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     const float* tf = tab + (lf * D + d) * 3;
-                    const float df = __fsub_rn(xv[q][d], tf[0]);
+                    const float df = __fsub_rn(xn[d], tf[0]);
                     llf = __fadd_rn(llf, __fsub_rn(-__fmul_rn(__fmul_rn(df, df), tf[1]), tf[2]));
                 }
                 A_llf.add(llf); A_lqzf.add(lqf); A_lpzf.add(lpf);
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) {
                         const float* tbp = tab + (lb * D + d) * 3;
-                        const float db = __fsub_rn(xv[q][d], tbp[0]);
+                        const float db = __fsub_rn(xn[d], tbp[0]);
                         llb = __fadd_rn(llb, __fsub_rn(-__fmul_rn(__fmul_rn(db, db), tbp[1]), tbp[2]));
                     }
                     A_llb.add(llb); A_lqzb.add(lqb); A_lpzb.add(lpb);
@@ -512,13 +520,15 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
     const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
     const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * (H4 * K + 4) +
-                         (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3) * 4;
+                         (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3 +
+                         (size_t)a.N * D) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local;
     auto kern = lean ? (a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60>
                                                : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32>)
                                   : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true>)
-                     : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>;
+                     : (a.H == 32 && a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false, 32, 60>
+                                               : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>);
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (long long)a.B * ((a.S + kFP - 1) / kFP);
     if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_z_fused: S*B too large for one launch");
