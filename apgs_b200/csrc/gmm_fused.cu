@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     float* s_em = s_aw + H4;                                   // P * H4: max_k e'_k[h] per particle (range test)
     float* s_tab = s_em + (size_t)P * H4;                            // P * KD * 3: mu, 1/(2 var), log sigma + c
     float* s_x = s_tab + (size_t)P * KD * 3;                         // N * D: the instance's points (read after the MLP)
+    // lean variant: the particles' uniforms and old labels are prefetched into shared memory with cp.async, so nothing
+    // of them lives in registers across the MLP
+    const int NU = (N + 3) / 4 * 4, LS = (N + 15) & ~15;
+    float* s_u = s_x + (size_t)(N * D + 3) / 4 * 4;                  // P * NU (lean)
+    unsigned char* s_lb = reinterpret_cast<unsigned char*>(s_u + (size_t)P * NU);   // P * LS (lean)
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
     const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
@@ -184,6 +189,24 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                 if (forced) s_zn[(size_t)p * NK + i] = __ldg(a.z_forced + r * NK + i);
             }
         }
+    }
+
+    if (LEAN && valid) {
+        const float* ur = a.u + r * N;
+        if ((N & 3) == 0 && aligned(a.u, 16)) {                      // rows of N floats: every row start is 16-byte aligned
+            for (int c = j; c < N / 4; c += LANES)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_u + (size_t)p * NU + c * 4)), "l"(ur + c * 4) : "memory");
+        } else {
+            for (int i = j; i < N; i += LANES) s_u[(size_t)p * NU + i] = __ldg(ur + i);
+        }
+        const unsigned char* lr = a.zl_old + r * a.LN;
+        if ((a.LN & 15) == 0 && a.LN >= LS && aligned(a.zl_old, 16)) {
+            for (int c = j; c < LS / 16; c += LANES)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_lb + (size_t)p * LS + c * 16)), "l"(lr + c * 16) : "memory");
+        } else {
+            for (int i = j; i < N; i += LANES) s_lb[(size_t)p * LS + i] = __ldg(lr + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     // ---- per-CTA table Ex_n[h] = 2^(2 log2(e) W1x x_n) and its per-unit maximum exponent, while the rows are in flight
@@ -346,7 +369,10 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             }
         }
     }
-    if (LEAN) __syncthreads();                                     // publishes s_e / s_tab
+    if (LEAN) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's uniforms / labels landed
+        __syncthreads();                                           // publishes them and s_e / s_tab
+    }
     else stage_wait(&bar, 0);                                      // rows landed; also publishes s_e / s_tab
 
     PlainF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;     // <= ceil(N/LANES) terms per lane
@@ -363,8 +389,10 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
 #pragma unroll
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
-                uq[q] = (n < N && !forced) ? __ldg(a.u + r * N + n) : 0.f;      // in flight during the MLP
-                lbq[q] = (n < N && lab_old) ? (int)__ldg(zlo + n) : 0;
+                if (!LEAN) {
+                    uq[q] = (n < N && !forced) ? __ldg(a.u + r * N + n) : 0.f;  // in flight during the MLP
+                    lbq[q] = (n < N && lab_old) ? (int)__ldg(zlo + n) : 0;
+                }
             }
             // ---- the MLP: hidden unit h for 4 points x K clusters at a time; points are paired as (0,2) and (1,3)
             if (fast) {
@@ -400,6 +428,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
                 if (n >= N) continue;
+                if (LEAN) { uq[q] = s_u[(size_t)p * NU + n]; lbq[q] = (int)s_lb[(size_t)p * LS + n]; }
                 float xn[D];                                          // the point itself: only the log-densities need it
 #pragma unroll
                 for (int d = 0; d < D; ++d) xn[d] = s_x[n * D + d];
@@ -521,7 +550,8 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
     const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * (H4 * K + 4) +
                          (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3 +
-                         (size_t)a.N * D) * 4;
+                         (size_t)(a.N * D + 3) / 4 * 4) * 4;
+    const size_t smem_lean = smem + (size_t)kFP * ((a.N + 3) / 4 * 4) * 4 + (size_t)kFP * ((a.N + 15) / 16 * 16);
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
     const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local;
     auto kern = lean ? (a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60>
@@ -529,10 +559,11 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
                                   : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true>)
                      : (a.H == 32 && a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false, 32, 60>
                                                : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>);
-    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
+    const size_t smem_used = lean ? smem_lean : smem;
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_used), "smem attr");
     const long long grid = (long long)a.B * ((a.S + kFP - 1) / kFP);
     if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_z_fused: S*B too large for one launch");
-    kern<<<(unsigned int)grid, kFP * kFLanes, smem, st>>>(a);
+    kern<<<(unsigned int)grid, kFP * kFLanes, smem_used, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_z_fused launch");
     return 0;
 }
