@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     }
     if (LEAN) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's uniforms / labels landed
-        __syncthreads();                                           // publishes them and s_e / s_tab
+        __syncwarp();                                              // a particle's lanes share a warp: publishes them, s_e, s_tab
     }
     else stage_wait(&bar, 0);                                      // rows landed; also publishes s_e / s_tab
 
