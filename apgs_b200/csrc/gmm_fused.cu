@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     const int NU = (N + 3) / 4 * 4, LS = (N + 15) & ~15;
     float* s_u = s_x + (size_t)(N * D + 3) / 4 * 4;                  // P * NU (lean)
     unsigned char* s_lb = reinterpret_cast<unsigned char*>(s_u + (size_t)P * NU);   // P * LS (lean)
-    const int b = (int)(blockIdx.x % (unsigned int)a.B);
-    const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
+    const int b = (int)blockIdx.x;                             // grid = (B, ceil(S / P)): no division
+    const int s0 = (int)blockIdx.y * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool valid = s0 + p < a.S;
@@ -561,9 +561,9 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
                                                : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>);
     const size_t smem_used = lean ? smem_lean : smem;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_used), "smem attr");
-    const long long grid = (long long)a.B * ((a.S + kFP - 1) / kFP);
-    if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_z_fused: S*B too large for one launch");
-    kern<<<(unsigned int)grid, kFP * kFLanes, smem_used, st>>>(a);
+    const int chunks = (a.S + kFP - 1) / kFP;
+    if (chunks > 65535) return fail(APGS_E_SHAPE, "gmm_z_fused: S=%d too large for one launch", a.S);
+    kern<<<dim3((unsigned int)a.B, (unsigned int)chunks), kFP * kFLanes, smem_used, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_z_fused launch");
     return 0;
 }
