@@ -147,6 +147,7 @@ template <int D>
 __device__ __forceinline__ float tanh_net(const float* __restrict__ wt, int H, const float (&d)[D], float w2sum) {
     float acc0 = w2sum, acc1 = 0.f;
     int h = 0;
+#pragma unroll 2
     for (; h + 1 < H; h += 2) {
         const float* w0 = wt + h * (D + 2);
         const float* w1 = w0 + (D + 2);
@@ -169,10 +170,10 @@ __device__ __forceinline__ float tanh_net(const float* __restrict__ wt, int H, c
     return acc0 + acc1;
 }
 
-template <int K, int D>
+template <int K, int D, int HC = 0>     // HC: hidden width when known at compile time (the reference's 32), else 0
 __global__ void __launch_bounds__(kFW * 32) k_dmm_local_fused(LocalEncArgs a) {
     extern __shared__ __align__(16) float s_f[];
-    const int H = a.H, N = a.N;
+    const int H = HC ? HC : a.H, N = a.N;
     constexpr int WS = D + 2;
     float* s_pi = s_f;                          // [H][D+2]: W0[h][:], b0[h], W2[h]
     float* s_c1 = s_pi + H * WS;                // [H][D+2]: 2log2e W0[h][:], 2log2e b0[h], -2 W2[h]
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(kFW * 32) k_dmm_local_fused(LocalEncArgs a) {
         float lg[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) lg[k] = pb2;
+#pragma unroll 4
         for (int h = 0; h < H; ++h) {
             const float* w = s_pi + h * WS;
             float xh = w[D];
@@ -336,7 +338,7 @@ template <int K, int D>
 static int launch_local(const LocalEncArgs& a, cudaStream_t st) {
     const size_t smem = ((size_t)3 * a.H * (D + 2) + (size_t)kFW * a.H * K + (size_t)kFW * K * D) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "dmm_local_encoder_fused: H=%d too large", a.H);
-    auto kern = k_dmm_local_fused<K, D>;
+    auto kern = a.H == 32 ? k_dmm_local_fused<K, D, 32> : k_dmm_local_fused<K, D>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const long long grid = (a.R + kFW - 1) / kFW;
     kern<<<(unsigned int)grid, kFW * 32, smem, st>>>(a);
