@@ -295,8 +295,12 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     if (valid) {
         if (labels) {
             if (lab_vec) {
-                const uint4* src = reinterpret_cast<const uint4*>(a.zl + r * a.LN);
-                for (int i = j; i < LS / 16; i += LANES) reinterpret_cast<uint4*>(s_lab + (size_t)p * LS)[i] = __ldg(src + i);
+                // cp.async: no register in between, so the table build below overlaps the HBM latency of the rows
+                const unsigned char* src = a.zl + r * a.LN;
+                for (int i = j; i < LS / 16; i += LANES)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_lab + (size_t)p * LS + i * 16)),
+                                 "l"(src + i * 16) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
             } else {
                 for (int i = j; i < N; i += LANES) s_lab[(size_t)p * LS + i] = __ldg(a.zl + r * a.LN + i);
             }
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
             ncen2[k] = pack2(-cen[k][0], -cen[k][D - 1]);
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's label rows (no-op otherwise)
     stage_wait(&bar, 0);                                        // rows landed; table and s_x visible
 
     float acc[TE];
