@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(P* LANES, STATS ? 4 : 1) k_gmm_nss_posterior(N
 // A CTA owns ONE instance b and P particles of it (rows r = s*B + b, one bulk copy per 720-byte z row), as the fused
 // z step does.  With z one-hot, the two Linear heads on cat(x_n, z_n) -- and therefore gamma_n, x'_n and every product
 // gamma_nk x'_nd, gamma_nk x'_nd^2 that enters the neural statistics -- take only K distinct values per data point:
-// they are tabulated ONCE PER CTA in shared memory, T[n][label] = { gamma (K), gamma x' (K D), gamma x'^2 (K D) }, and
-// the per-particle work shrinks to: label of the point, four LDS.128, K (1 + 2D) additions (+ the centred one-hot
-// statistics for the eta-step weights, packed fp32x2).  ~45 instructions per point instead of ~100.
+// the factors are tabulated ONCE PER CTA in shared memory, T[n][label] = { x' (D), gamma (K) }, and the per-particle
+// work shrinks to: label of the point, two loads, K (1 + 2D) accumulating FMAs in packed fp32x2 (+ the centred
+// one-hot statistics for the eta-step weights).  ~30 instructions per point instead of ~100.
 // ============================================================================================
 constexpr int kP = 32, kLanes = 8;
 
@@ -271,11 +271,15 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     const int ZS = nss_im_zstride(NK);
     const size_t zreg = max((size_t)P * ZS, (size_t)P * LANES * RW);    // z rows, later the cross-lane reduction buffer
     float* s_z = reinterpret_cast<float*>(smem);
-    // structure-of-arrays table: plane e holds T_e[n*K + label].  The 8 lanes of a particle read rows 3n + label with
-    // n = j + 8 it, i.e. 8..24 distinct consecutive-ish addresses, and the 4 particles of a warp read the same window:
-    // every LDS.32 of the warp is conflict-free (an array-of-structs row of 16 floats costs ~2.3x the wavefronts).
-    // Pairs of planes read as LDS.64 + add.f32x2 (half the instructions) were measured slower: 0.437 vs 0.418 ms.
-    float* s_tab = s_z + (zreg + 3) / 4 * 4;                            // [TE][NK]
+    // The table holds the FACTORS, one short row per (point, label): { x'_0..x'_{D-1}, gamma_0..gamma_{K-1} }, and the
+    // products gamma_k x'_d, gamma_k x'_d^2 are formed by the FMAs that accumulate them (FMA pipe has headroom, the
+    // LSU does not): K + D loaded values per point (one LDS.128 + one LDS.32 at K = 3, D = 2) and K(1 + 2D)
+    // accumulating FMAs, instead of the K(1 + 2D) = 15 LDS.32 + 15 FADD of a table of products (0.37 ms, LSU-bound;
+    // an array-of-structs row of 16 products cost ~2.3x the wavefronts, pairs of product planes were slower too).
+    // Row stride: a multiple of four floats with an odd number of quads, so consecutive rows fall on distinct banks.
+    constexpr int RS = (((K + D + 3) / 4) | 1) * 4;
+    static_assert(RS <= TE, "the launcher sizes the table region as TE floats per row");
+    float* s_tab = s_z + (zreg + 3) / 4 * 4;                            // [NK][RS] (region sized [NK][TE])
     float* s_x = s_tab + (size_t)TE * NK;                               // [N][D]
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
     const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
@@ -345,15 +349,9 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
             xp[d] = acc + __ldg(a.Wo + d * IN + D + lab);
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float gk = lg[k] * rse;
-            s_tab[(size_t)k * NK + idx] = gk;
+        for (int d = 0; d < D; ++d) s_tab[(size_t)idx * RS + d] = xp[d];
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                s_tab[(size_t)(K + k * D + d) * NK + idx] = __fmul_rn(gk, xp[d]);                         // z_expand * ob_expand
-                s_tab[(size_t)(K + KD + k * D + d) * NK + idx] = __fmul_rn(gk, __fmul_rn(xp[d], xp[d]));  // z_expand * ob_expand**2
-            }
-        }
+        for (int k = 0; k < K; ++k) s_tab[(size_t)idx * RS + D + k] = lg[k] * rse;
     }
     float cen[STATS ? K : 1][D];
     f32x2 c2p[STATS ? K : 1], c3p[STATS ? K : 1], ncen2[STATS ? K : 1];
@@ -374,9 +372,14 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's label rows (no-op otherwise)
     stage_wait(&bar, 0);                                        // rows landed; table and s_x visible
 
-    float acc[TE];
+    float ag[K], a2[K][D], a3[K][D];                            // sum gamma_k, sum gamma_k x'_d, sum gamma_k x'_d^2
+    f32x2 a2p[K], a3p[K];                                       // the same, packed, when D == 2
 #pragma unroll
-    for (int e = 0; e < TE; ++e) acc[e] = 0.f;
+    for (int k = 0; k < K; ++k) {
+        ag[k] = 0.f; a2p[k] = 0ull; a3p[k] = 0ull;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { a2[k][d] = 0.f; a3[k][d] = 0.f; }
+    }
     if (valid) {
         const float* zr = s_z + (size_t)p * ZS;
         for (int n = j; n < N; n += LANES) {
@@ -388,9 +391,33 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
 #pragma unroll
                 for (int k = 1; k < K; ++k) { const float v = zr[n * K + k]; if (v > best) { best = v; lab = k; } }
             }
-            const float* t = s_tab + n * K + lab;
+            const float* t = s_tab + (size_t)(n * K + lab) * RS;
+            if (D == 2 && K >= 2) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(t);          // (x'_0, x'_1), (gamma_0, gamma_1)
+                float g[K];
+                unpack2(v.y, g[0], g[1]);
 #pragma unroll
-            for (int e = 0; e < TE; ++e) acc[e] = __fadd_rn(acc[e], t[e * NK]);
+                for (int k = 2; k < K; ++k) g[k] = t[D + k];
+                const f32x2 xp2 = v.x, sq2 = mul2(xp2, xp2);                           // ob_expand, ob_expand**2
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const f32x2 gk = pack2(g[k], g[k]);
+                    ag[k] = __fadd_rn(ag[k], g[k]);
+                    a2p[k] = fma2(gk, xp2, a2p[k]);                                    // z_expand * ob_expand
+                    a3p[k] = fma2(gk, sq2, a3p[k]);                                    // z_expand * ob_expand**2
+                }
+            } else {
+                float xp[D], sq[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) { xp[d] = t[d]; sq[d] = __fmul_rn(xp[d], xp[d]); }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float gk = t[D + k];
+                    ag[k] = __fadd_rn(ag[k], gk);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { a2[k][d] = fmaf(gk, xp[d], a2[k][d]); a3[k][d] = fmaf(gk, sq[d], a3[k][d]); }
+                }
+            }
             if (STATS) {
                 float ind[K];
 #pragma unroll
@@ -425,7 +452,12 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     float* s_red = s_z;
     float* mine = s_red + (size_t)threadIdx.x * RW;
 #pragma unroll
-    for (int e = 0; e < TE; ++e) mine[e] = acc[e];
+    for (int k = 0; k < K; ++k) {
+        if (D == 2 && K >= 2) { unpack2(a2p[k], a2[k][0], a2[k][D - 1]); unpack2(a3p[k], a3[k][0], a3[k][D - 1]); }
+        mine[k] = ag[k];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { mine[K + k * D + d] = a2[k][d]; mine[K + KD + k * D + d] = a3[k][d]; }
+    }
     __syncwarp();
     double n1 = 0.0, n2 = 0.0, n3 = 0.0;
     const bool fin = valid && j < KD;                            // lane e = (k, d) finishes one posterior element
