@@ -540,6 +540,8 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
     }
 }
 
+// 32 particles per CTA (3 CTAs/SM).  Measured alternatives on the lean launch: 16 particles (6 CTAs/SM, phases less
+// correlated, twice the Ex-table work) 1.23 ms vs 1.20; tau / mu loads hoisted above the Ex table 1.22 ms.
 constexpr int kFP = 32, kFLanes = 8, kFPB = 4;
 
 template <int K, int D>
