@@ -251,6 +251,22 @@ def run_ours(args):
                         "latency-bound (~70 us), and with random-init encoders the weights are degenerate (ESS ~ 1) so most reads hit "
                         "L2.  all_distinct_probe times the SAME kernels on the reference layout (1540 B per particle) with near-uniform "
                         "weights, where every row comes from HBM: that is the kernel's HBM roofline point."}
+    zf = prof.get("gmm_z_step_fused", None)
+    if roof is not None and zf:
+        # the kernel with the largest share of the step is compute-bound: report it against ITS bound as well.  Floor =
+        # tanh terms (S*B * 64 padded points * K * H) * 3.5 FMA-pipe cycles (14 packed instructions
+        # of 2 cycles per 4 terms of 2 points) / (32 lanes * 4 schedulers * SMs) / SM clock sampled during the run.
+        N_, K_, H_ = 60, 3, 32
+        clk = (sampler.summary() or {}).get("sm_mhz") or 1965
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        terms = S * B * ((N_ + 31) // 32 * 32) * K_ * H_
+        floor_ms = terms * 3.5 / 32 / (4 * sms) / (clk * 1e6) * 1e3
+        tot = max(1e-9, sum(q["calls"] * q["ms_avg"] for q in prof.values()))
+        roof["step_dominant_kernel"] = {
+            "kernel": "k_gmm_z_fused (fused Enc_apg_z + draw + z-step weight)", "bound": "fp32 FMA pipe (not hbm, not tensor)",
+            "share_of_step": round(zf["calls"] * zf["ms_avg"] / tot, 3), "avg_launch_ms": round(zf["ms_avg"], 4),
+            "fma_pipe_floor_ms": round(floor_ms, 4), "frac_of_fma_pipe_floor": round(floor_ms / zf["ms_avg"], 3),
+            "alg_GBs": round(zf["gbs"], 1), "frac_hbm": round(zf["gbs"] / peak, 3)}
     if rank == 0:
         line = {"metric": "particle-sweeps/sec", "value": value, "unit": "particle-sweeps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
