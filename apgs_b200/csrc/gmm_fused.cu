@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
         const unsigned char* zlo = a.zl_old + r * a.LN;          // label rows of this particle (label mode)
         unsigned char* zln = a.zl_new + r * a.LN;
         const float* tab = s_tab + (size_t)p * (KD * 3);
+#pragma unroll(NC ? 2 : 1)
         for (int it = 0; it < nIt; ++it) {
             const int n0 = it * (LANES * PB) + j;
             float logit[PB][K], uq[PB];
