@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
     }
     if (valid) {
         const float* zr = s_z + (size_t)p * ZS;
+        // left to the compiler's own unrolling: `#pragma unroll 8` (N = 60) measured 0.44 ms, `unroll 2` 0.351, default 0.344
         for (int n = j; n < N; n += LANES) {
             int lab = 0;
             if (labels) {
