@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
                         const float db = __fsub_rn(xn[d], tbp[0]);
                         llb = __fadd_rn(llb, __fsub_rn(-__fmul_rn(__fmul_rn(db, db), tbp[1]), tbp[2]));
                     }
-                    A_llb.add(llb); A_lqzb.add(lqb); A_lpzb.add(lpb);
+                    if (!LEAN) { A_llb.add(llb); A_lqzb.add(lqb); A_lpzb.add(lpb); }   // only log_w_b needs these sums
                     const float wf = __fsub_rn(__fadd_rn(llf, lpf), lqf);
                     const float wb = __fsub_rn(__fadd_rn(llb, lpb), lqb);
                     const float loc = __fsub_rn(wf, wb);
@@ -508,16 +508,21 @@ __global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
             }
         }
     }
-    const double S_llf = group_sum<LANES>(A_llf.value()), S_llb = group_sum<LANES>(A_llb.value());
-    const double S_lpzf = group_sum<LANES>(A_lpzf.value()), S_lpzb = group_sum<LANES>(A_lpzb.value());
-    const double S_lqzf = group_sum<LANES>(A_lqzf.value()), S_lqzb = group_sum<LANES>(A_lqzb.value());
+    const double S_llf = group_sum<LANES>(A_llf.value()), S_lpzf = group_sum<LANES>(A_lpzf.value());
+    const double S_lqzf = group_sum<LANES>(A_lqzf.value());
+    double S_llb = 0.0, S_lpzb = 0.0, S_lqzb = 0.0;                // the lean variant never writes log_w_f / log_w_b
+    if (!LEAN) {
+        S_llb = group_sum<LANES>(A_llb.value());
+        S_lpzb = group_sum<LANES>(A_lpzb.value());
+        S_lqzb = group_sum<LANES>(A_lqzb.value());
+    }
     const double S_loc = group_sum<LANES>(A_loc.value());
     if (valid && j == 0) {
         const float ll_f = (float)S_llf, ll_b = (float)S_llb;
         const float lpz_f = (float)S_lpzf, lpz_b = (float)S_lpzb, lqz_f = (float)S_lqzf, lqz_b = (float)S_lqzb;
         if (a.log_w != nullptr) a.log_w[r] = (float)S_loc;
-        if (a.log_w_f != nullptr) a.log_w_f[r] = __fsub_rn(__fadd_rn(ll_f, lpz_f), lqz_f);
-        if (a.log_w_b != nullptr) a.log_w_b[r] = __fsub_rn(__fadd_rn(ll_b, lpz_b), lqz_b);
+        if (!LEAN && a.log_w_f != nullptr) a.log_w_f[r] = __fsub_rn(__fadd_rn(ll_f, lpz_f), lqz_f);
+        if (!LEAN && a.log_w_b != nullptr) a.log_w_b[r] = __fsub_rn(__fadd_rn(ll_b, lpz_b), lqz_b);
         if (a.log_q_f != nullptr) a.log_q_f[r] = lqz_f;
         if (a.dens != nullptr) a.dens[r] = __fadd_rn(ll_f, lpz_f);
     }
@@ -557,7 +562,8 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
                          (size_t)(a.N * D + 3) / 4 * 4) * 4;
     const size_t smem_lean = smem + (size_t)kFP * ((a.N + 3) / 4 * 4) * 4 + (size_t)kFP * ((a.N + 15) / 16 * 16);
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
-    const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local;
+    const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local &&
+                      !a.log_w_f && !a.log_w_b;
     auto kern = lean ? (a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60>
                                                : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32>)
                                   : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true>)
