@@ -260,7 +260,7 @@ __host__ __device__ inline int nss_im_zstride(int NK) {
 }
 
 template <int K, int D, int P, int LANES, bool STATS, int NC = 0>   // NC: points per instance when known at compile time
-__global__ void __launch_bounds__(P* LANES, 3) k_gmm_nss_im(NssArgs a, int S) {
+__global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
     constexpr int KD = K * D, IN = D + K;

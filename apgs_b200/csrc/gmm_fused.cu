@@ -127,7 +127,7 @@ __device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv
 // The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
 // HC / NC: hidden width and points per instance when known at compile time (the reference's 32 and 60), else 0.
 template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0>
-__global__ void __launch_bounds__(P* LANES, 3) k_gmm_z_fused(ZFusedArgs a) {
+__global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedArgs a) {
     static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
