@@ -102,7 +102,7 @@ struct DmmArgs {
     float *lw_local, *lq_local, *ll_local;                          // (R, N), optional
 };
 
-__global__ void __launch_bounds__(kWarps * 32) k_dmm_step(DmmArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, 4) k_dmm_step(DmmArgs a) {
     __shared__ float s_mu[kWarps][2][kDK * kDD];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * kWarps + wid;
