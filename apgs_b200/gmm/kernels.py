@@ -179,11 +179,13 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
 
 
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
-                 parts=False, local=False, also_labels=0):
+                 parts=False, local=False, also_labels=0, want_onehot=True):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
     mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
     z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
-    also_labels = row stride (>= N): sample-only call that returns ((z_new one-hot, labels), q_probs, Weights)."""
+    also_labels = row stride (>= N): sample-only call that returns ((z_new one-hot, labels), q_probs, Weights);
+    want_onehot=False leaves the one-hot form out (None): the draw then costs ~N bytes per particle instead of 4 K N,
+    and Weights.density / .log_q_f carry log p(x, z | eta) and log q(z) of the draw."""
     lib = _lib.load()
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -199,12 +201,12 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
             raise ValueError("also_labels is a sample-only mode")
         LN = int(also_labels)
         uniforms = torch.rand(S, B, N, device=dev) if uniforms is None else _req(uniforms, "uniforms", ndim=3)
-        z_hot = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
+        z_hot = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_onehot else None
         z_lab = torch.empty(S, B, LN, dtype=torch.uint8, device=dev)
         q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
         rs, rk = _prior_struct(prior)
         w, o = _outs(S, B, N, dev, False, False)
-        with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, S * B * (LN + 4 * (N * K + N + 2 * K * D + (N * K if want_q else 0)))):
+        with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, S * B * (LN + 4 * ((N * K if want_onehot else 0) + N + 2 * K * D + (N * K if want_q else 0)))):
             check(lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
                                                        C.byref(rs), None, ptr(uniforms), S, B, N, K, D,
                                                        ptr(z_lab), LN, ptr(z_hot), ptr(q), C.byref(o), _stream()),

@@ -119,6 +119,21 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
     post = enc_rws_eta.params(x, generative.prior_ng)
     tau, mu = _sample_eta(post)
     z_lab = None
+    if label_stride and not result_flags['mode_required'] and not result_flags['loss_required']:
+        # nothing downstream needs q_probs or the one-hot draw: the sampler returns labels plus log p(x, z | eta) and
+        # log q(z) of its draw, and the eta terms come from the statistics weight kernel on EMPTY statistics (no point
+        # assigned: its log-likelihoods vanish, its density / log_q_f are log p(eta) and log q(eta)).  Same terms as
+        # kernels.logw_oneshot, summed as (ll + log p(z)) + log p(eta) instead of (ll + log p(eta)) + log p(z).
+        (_, z_lab), _, wz = kernels.z_step_fused(x, tau, mu, enc_rws_z.mlp(), generative, want_q=False,
+                                                 also_labels=label_stride, want_onehot=False)
+        S, B, K, D = tau.shape
+        we = kernels.logw_eta_stats(torch.zeros(S, B, K, 1 + 2 * D, device=tau.device), mu, post, generative,
+                                    tau, mu, tau, mu)
+        log_p = wz.density + we.density
+        log_q = we.log_q_f + wz.log_q_f
+        log_w = log_p - log_q
+        _book(trace, result_flags, log_w, log_q, log_p)
+        return log_w, tau, mu, None, trace, z_lab
     if label_stride:
         z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride)
     elif enc_rws_z.can_fuse(result_flags['loss_required']):

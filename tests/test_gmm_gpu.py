@@ -718,6 +718,40 @@ def test_objective_with_compact_labels_matches_one_hot_objective():
         assert torch.equal(out[True][k], out[False][k]), k
 
 
+def test_lean_oneshot_matches_the_oneshot_weight_kernel():
+    """the one-shot of the compact-label objective (labels-only sampler + eta terms from the statistics weight kernel on
+    empty statistics) against kernels.logw_oneshot on the SAME draw: same terms, another summation order."""
+    from apgs_b200.gmm import kernels
+    from apgs_b200.gmm import objectives as O
+    S, B, N, K, D = 37, 6, 60, 3, 2
+    torch.manual_seed(0)
+    enc_rws_eta, enc_apg_z, enc_apg_eta, gen = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    with torch.no_grad():
+        post = enc_rws_eta.params(x.unsqueeze(0).expand(S, -1, -1, -1), gen.prior_ng)
+        tau, mu = O._sample_eta(post)
+        u = torch.rand(S, B, N, device=DEV)
+        LN = 64
+        (z, lab), q, _ = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), gen, uniforms=u, want_q=True, also_labels=LN)
+        ref = kernels.logw_oneshot(x, post, gen, tau, mu, q, z)
+        (none, lab2), q2, wz = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), gen, uniforms=u, want_q=False,
+                                                   also_labels=LN, want_onehot=False)
+        assert none is None and q2 is None and torch.equal(lab[..., :N], lab2[..., :N])
+        we = kernels.logw_eta_stats(torch.zeros(S, B, K, 1 + 2 * D, device=DEV), mu, post, gen, tau, mu, tau, mu)
+        log_p = wz.density + we.density
+        log_q = we.log_q_f + wz.log_q_f
+    _close(log_p, ref.density, rtol=3e-6, atol=1e-4, what="log p")
+    _close(log_q, ref.log_q_f, rtol=3e-6, atol=1e-4, what="log q")
+    _close(log_p - log_q, ref.log_w, rtol=0, atol=3e-6 * (ref.density.abs() + ref.log_q_f.abs()).cpu() + 1e-4, what="log w")
+    # and the objective takes this path with the budget_analysis flags: finite traces of the right shape
+    flags = {"loss_required": False, "ess_required": True, "mode_required": False, "density_required": True}
+    from apgs_b200.resampler import Resampler
+    with torch.no_grad():
+        tr = O.apg_objective((enc_rws_eta, enc_apg_z, enc_apg_eta, gen), x, flags, 3, "decomposed", Resampler("systematic", S, True, DEV))
+    assert tuple(tr["ess"].shape) == (3, B) and bool(torch.isfinite(tr["ess"]).all()) and bool(torch.isfinite(tr["density"]).all())
+
+
 def test_fused_eta_draw_is_bit_identical_to_torch_sampling():
     """draw_logw_eta_stats forms (tau, mu) from the standard variates with the IEEE operations of
     Gamma(alpha, beta).sample() / Normal(q_mu, 1/sqrt(q_nu tau)).sample(): same seed -> the same draws, bit for bit,
