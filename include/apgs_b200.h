@@ -246,8 +246,10 @@ APGS_API int apgs_gmm_draw_logw_eta_stats_f32(const float* stats, const float* c
  *   between the rows of consecutive particles (pad it to 16 so the gather moves 16-byte vectors), which cuts the z row
  *   the resampling gather moves from 4*K*N to ~N bytes.  Same arithmetic and outputs as apgs_gmm_z_step_fused_f32 (with
  *   z_old given, sampling from `uniforms`) and apgs_gmm_eta_posterior_stats_f32; center / stats may both be NULL;
- *   z_old_labels may be NULL (sample-only: no weights) and z_new_onehot (S,B,N,K), when given, receives the one-hot
- *   form of the same draw (the one-shot needs both).                                                                 */
+ *   z_old_labels may be NULL (sample-only: out->density = log p(x, z | eta) and out->log_q_f = log q(z) of the draw,
+ *   out->log_w = 0) and z_new_onehot (S,B,N,K), when given, receives the one-hot form of the same draw.  The launch a
+ *   sweep repeats (labels in, labels out, no one-hot / q_probs / per-point / log_w_f / log_w_b outputs) runs a lean
+ *   compile-time variant, specialised further for the reference's hidden width 32 and N = 60 points.                 */
 APGS_API int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau, const float* mu,
                               const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
                               const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels, const float* uniforms,
