@@ -22,6 +22,8 @@ parameters require grad, that term is rebuilt with PyTorch ops (models.posterior
 un-fused Enc_apg_z MLP) and multiplied by the detached kernel weights -- the reference's train() works unchanged and
 gets the reference's gradients, while every forward quantity still comes from the kernels.
 """
+import math
+
 import torch
 from torch.distributions.gamma import Gamma
 from torch.distributions.normal import Normal
@@ -42,50 +44,77 @@ def _sample_eta(post):
     return tau, mu
 
 
-def _book(trace, result_flags, log_w, log_q_f, density, append=True):
-    """loss / ess / density bookkeeping shared by the steps (objectives.py:93-109,181-194)."""
-    if result_flags['loss_required'] or result_flags['ess_required']:
-        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
-        if result_flags['loss_required']:
-            trace['loss'].append((w * (-log_q_f)).sum(0).mean().unsqueeze(0))
-        if result_flags['ess_required']:
-            trace['ess'].append(ess.unsqueeze(0))
+def _book_weights(trace, result_flags, log_q_f, stats):
+    """loss / ess / log-marginal from the normalised weights (objectives.py:93-98,181-186).  stats = (w, ess, lse) of the
+    step's log-weights.  log Z-hat_b = logsumexp_s log_w - log S (the reference never materialises it; it
+    is the `lse` the softmax kernel computes anyway) is appended to trace['log_z'] next to the ESS."""
+    w, ess, lse = stats
+    if result_flags['loss_required']:
+        trace['loss'].append((w * (-log_q_f)).sum(0).mean().unsqueeze(0))
+    if result_flags['ess_required']:
+        trace['ess'].append(ess.unsqueeze(0))
+        S = log_q_f.shape[0]
+        trace.setdefault('log_z', []).append((lse - math.log(S)).unsqueeze(0))
+
+
+def _book(trace, result_flags, log_w, log_q_f, density, defer=False):
+    """loss / ess / density bookkeeping shared by the steps (objectives.py:93-109,181-194).  defer: the caller takes the
+    weight statistics from the resampling launch that follows (Resampler.resample(want_stats=True): the ancestor kernel
+    normalises the same log-weights anyway) and calls _book_weights itself."""
+    if not defer and (result_flags['loss_required'] or result_flags['ess_required']):
+        _book_weights(trace, result_flags, log_q_f, ops.weight_stats(log_w, want_w=result_flags['loss_required']))
     if result_flags['density_required']:
         trace['density'].append(density.unsqueeze(0))
 
 
 def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
-    """Amortized Population Gibbs objective in the GMM problem (objectives.py:9-53)."""
-    trace = {'loss': [], 'ess': [], 'E_tau': [], 'E_mu': [], 'E_z': [], 'density': []}
+    """Amortized Population Gibbs objective in the GMM problem (objectives.py:9-53).
+    Besides the reference's trace keys, `log_z` (num_sweeps, B) carries the log-marginal estimate
+    logsumexp_s log_w - log S of every step that appends an ESS (north_star: "log-marginal/ESS metric")."""
+    trace = {'loss': [], 'ess': [], 'E_tau': [], 'E_mu': [], 'E_z': [], 'density': [], 'log_z': []}
     (enc_rws_eta, enc_apg_z, enc_apg_eta, generative) = models
     if x.dim() == 3:
         x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)       # stride-0 S axis; never materialised
+    need_stats = bool(result_flags['loss_required'] or result_flags['ess_required'])
+
+    def resample_and_book(tau, mu, z, log_w, log_q_f):
+        """resample_variables + the W1 bookkeeping of the step from the SAME launch: the ancestor kernel's softmax over S
+        is the normalisation the loss / ESS need (the reference computes it twice, objectives.py:93 and resampler.py:30)."""
+        if not need_stats:
+            return resample_variables(resampler, tau, mu, z, log_weights=log_w)
+        (tau, mu, z), _, stats = resampler.resample([tau, mu, z], log_w, want_stats=True,
+                                                    want_w=bool(result_flags['loss_required']))
+        _book_weights(trace, result_flags, log_q_f, stats)
+        return tau, mu, z
+
     if _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
         # Inside the sweeps the assignments never need their one-hot (S,B,N,K) fp32 form (the objective returns only
         # the trace): carry them as one byte per point.  The two per-sweep kernels take / return labels, and the z row
         # every resampling gather moves shrinks from 4*K*N to ~N bytes (720 -> 64 B for the GMM shapes; rows padded to
         # 16 bytes so that the gather moves 16-byte vectors).  The one-shot's sampler emits the labels with its draw.
         N = x.shape[-2]
-        log_w, tau, mu, _, trace, z = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags,
-                                               label_stride=(N + 15) // 16 * 16)
+        log_w, tau, mu, _, trace, z, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags,
+                                                      label_stride=(N + 15) // 16 * 16, defer=True)
     else:
-        log_w, tau, mu, z, trace = oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags)
-    tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
+        log_w, tau, mu, z, trace, _, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags, defer=True)
+    tau, mu, z = resample_and_book(tau, mu, z, log_w, log_q)
     for m in range(num_sweeps - 1):
         if block == 'decomposed':
-            log_w_eta, tau, mu, trace = apg_update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags)
-            tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_eta)
+            log_w_eta, tau, mu, trace, log_q_f = _update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags, defer=True)
+            tau, mu, z = resample_and_book(tau, mu, z, log_w_eta, log_q_f)
             log_w_z, z, trace = apg_update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags)
             tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_z)
         elif block == 'joint':
-            log_w, tau, mu, z, trace = apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z, tau, mu, trace, result_flags)
-            tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w)
+            log_w, tau, mu, z, trace, log_q_f = _update_joint(enc_apg_z, enc_apg_eta, generative, x, z, tau, mu, trace,
+                                                              result_flags, defer=True)
+            tau, mu, z = resample_and_book(tau, mu, z, log_w, log_q_f)
         else:
             raise ValueError
     if result_flags['loss_required']:
         trace['loss'] = torch.cat(trace['loss'], 0)
     if result_flags['ess_required']:
         trace['ess'] = torch.cat(trace['ess'], 0)
+        trace['log_z'] = torch.cat(trace['log_z'], 0)
     if result_flags['mode_required']:
         trace['E_tau'] = torch.cat(trace['E_tau'], 0)
         trace['E_mu'] = torch.cat(trace['E_mu'], 0)
@@ -95,7 +124,8 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     return trace
 
 
-compact_labels = True          # module switch (tests compare both representations)
+compact_labels = True          # module switches (tests compare the representations / the two one-shot paths)
+lean_oneshot = True
 
 
 def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
@@ -114,12 +144,13 @@ def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
     return _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags)[:5]
 
 
-def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_stride=0):
-    """oneshot; with label_stride (fused sampler only) the draw of z also comes back as uint8 labels (6th value)."""
+def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_stride=0, defer=False):
+    """oneshot; with label_stride (fused sampler only) the draw of z also comes back as uint8 labels (6th value);
+    the 7th value is log q of the draw (what a deferred _book_weights needs)."""
     post = enc_rws_eta.params(x, generative.prior_ng)
     tau, mu = _sample_eta(post)
     z_lab = None
-    if label_stride and not result_flags['mode_required'] and not result_flags['loss_required']:
+    if label_stride and lean_oneshot and not result_flags['mode_required'] and not result_flags['loss_required']:
         # nothing downstream needs q_probs or the one-hot draw: the sampler returns labels plus log p(x, z | eta) and
         # log q(z) of its draw, and the eta terms come from the statistics weight kernel on EMPTY statistics (no point
         # assigned: its log-likelihoods vanish, its density / log_q_f are log p(eta) and log q(eta)).  Same terms as
@@ -132,8 +163,8 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
         log_p = wz.density + we.density
         log_q = we.log_q_f + wz.log_q_f
         log_w = log_p - log_q
-        _book(trace, result_flags, log_w, log_q, log_p)
-        return log_w, tau, mu, None, trace, z_lab
+        _book(trace, result_flags, log_w, log_q, log_p, defer)
+        return log_w, tau, mu, None, trace, z_lab, log_q
     if label_stride:
         z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride)
     elif enc_rws_z.can_fuse(result_flags['loss_required']):
@@ -146,16 +177,20 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
     if result_flags['loss_required'] and needs_grad(enc_rws_eta, enc_rws_z):
         log_q = (eta_log_q_torch(enc_rws_eta.params_torch(x, generative.prior_ng), tau, mu)
                  + cat(q_probs, validate_args=False).log_prob(z).sum(-1))
-    _book(trace, result_flags, w.log_w, log_q, w.density)
+    _book(trace, result_flags, w.log_w, log_q, w.density, defer)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
         trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0).detach())
-    return w.log_w, tau, mu, z, trace, z_lab
+    return w.log_w, tau, mu, z, trace, z_lab, log_q
 
 
 def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old, trace, result_flags):
     """Jointly update all the variables (objectives.py:112-158)."""
+    return _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old, trace, result_flags)[:5]
+
+
+def _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old, trace, result_flags, defer=False):
     post = enc_apg_eta.params(x, z_old, generative.prior_ng)
     tau, mu = _sample_eta(post)
     if enc_apg_z.can_fuse(result_flags['loss_required']):
@@ -168,17 +203,21 @@ def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_o
     if result_flags['loss_required'] and needs_grad(enc_apg_eta, enc_apg_z):
         log_q_f = (eta_log_q_torch(enc_apg_eta.params_torch(x, z_old, generative.prior_ng), tau, mu)
                    + cat(q_probs, validate_args=False).log_prob(z).sum(-1))
-    _book(trace, result_flags, w.log_w, log_q_f, w.density)
+    _book(trace, result_flags, w.log_w, log_q_f, w.density, defer)
     if result_flags['mode_required']:
         # the reference's branch (objectives.py:149-155) reads an undefined name; emit what it intends
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
         trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
         trace['E_z'].append(z.unsqueeze(0))
-    return w.log_w, tau, mu, z, trace
+    return w.log_w, tau, mu, z, trace, log_q_f
 
 
 def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags):
     """Given local variable z, update global variables eta := {mu, tau} (objectives.py:161-195)."""
+    return _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags)[:4]
+
+
+def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False):
     if getattr(enc_apg_eta, 'fused', False):
         # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of
         *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old)
@@ -195,11 +234,11 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
     log_q_f = w.log_q_f
     if result_flags['loss_required'] and needs_grad(enc_apg_eta):
         log_q_f = eta_log_q_torch(enc_apg_eta.params_torch(x, z, generative.prior_ng), tau, mu)
-    _book(trace, result_flags, w.log_w, log_q_f, w.density)
+    _book(trace, result_flags, w.log_w, log_q_f, w.density, defer)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
         trace['E_mu'].append(post[2].mean(0).unsqueeze(0))
-    return w.log_w, tau, mu, trace
+    return w.log_w, tau, mu, trace, log_q_f
 
 
 def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):

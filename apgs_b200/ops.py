@@ -140,9 +140,11 @@ def _uniform_args(strategy, uniforms, S, B):
 
 
 def sample_ancestors(log_w=None, w_norm=None, strategy="systematic", uniforms=None,
-                     cdf_mode=_lib.CDF_AUTO, index_dtype=torch.int64, want_stats=False):
+                     cdf_mode=_lib.CDF_AUTO, index_dtype=torch.int64, want_stats=False, want_w=True):
     """Ancestor indices (S,B) from log-weights (or already-normalised weights) and explicit
-    uniforms.  Returns anc or (anc, w, ess, lse) when want_stats (log_w input only)."""
+    uniforms.  Returns anc or (anc, w, ess, lse) when want_stats (log_w input only; w is None unless want_w):
+    the softmax the ancestor kernel computes anyway IS the W1 normalisation, so a caller that needs ESS / lse of the
+    weights it resamples with gets them from the same launch ("duplicated")."""
     lib = _lib.load()
     src = log_w if log_w is not None else w_norm
     if (log_w is None) == (w_norm is None):
@@ -160,7 +162,7 @@ def sample_ancestors(log_w=None, w_norm=None, strategy="systematic", uniforms=No
     if want_stats:
         if log_w is None:
             raise ValueError("want_stats needs log_w")
-        w = torch.empty_like(src)
+        w = torch.empty_like(src) if want_w else None
         ess = torch.empty(B, dtype=torch.float32, device=dev)
         lse = torch.empty(B, dtype=torch.float32, device=dev)
     nws = lib.apgs_ancestors_workspace_bytes(S, B)
@@ -211,9 +213,9 @@ def gather_ancestors(latents, anc):
 
 # ------------------------------------------------------------------------------------------ R5
 def resample(latents, log_w=None, w_norm=None, strategy="systematic", uniforms=None,
-             cdf_mode=_lib.CDF_AUTO, want_index=False, want_stats=False):
+             cdf_mode=_lib.CDF_AUTO, want_index=False, want_stats=False, want_w=True):
     """Fused resample: ancestors (int32, in workspace) + gather of every latent.
-    Returns (outs, anc64 or None, (w, ess, lse) or None)."""
+    Returns (outs, anc64 or None, (w, ess, lse) or None); w is None unless want_w."""
     lib = _lib.load()
     src = log_w if log_w is not None else w_norm
     if (log_w is None) == (w_norm is None):
@@ -229,7 +231,7 @@ def resample(latents, log_w=None, w_norm=None, strategy="systematic", uniforms=N
     if want_stats:
         if log_w is None:
             raise ValueError("want_stats needs log_w")
-        w = torch.empty_like(src)
+        w = torch.empty_like(src) if want_w else None
         ess = torch.empty(B, dtype=torch.float32, device=dev)
         lse = torch.empty(B, dtype=torch.float32, device=dev)
     nws = lib.apgs_resample_workspace_bytes(S, B)

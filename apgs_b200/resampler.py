@@ -67,25 +67,29 @@ class Resampler():
         return ops.gather_ancestors([var], ancestral_index)[0]
 
     # ------------------------------------------------------------------ fused entry
-    def resample(self, latents, log_weights, uniforms=None, want_stats=False, want_index=False):
+    def resample(self, latents, log_weights, uniforms=None, want_stats=False, want_index=False, want_w=True):
         """One ancestor draw + gather of every latent (2 launches, no int64 index tensor).
-        Returns the list of resampled latents (and (w, ess, lse) / ancestors when asked)."""
+        Returns the list of resampled latents; with want_stats / want_index: (latents, ancestors or None,
+        (w, ess, lse) or None) -- the normalised weights, ESS and logsumexp of `log_weights` come out of the ancestor
+        kernel's own softmax, so the W1 bookkeeping of a sweep costs no extra launch (w is None unless want_w)."""
         self._check(log_weights)
         S, B = log_weights.shape
         if uniforms is None:
             uniforms = self.draw_uniforms(S, B, log_weights.device)
-        if ops.PROFILE.events and not (want_stats or want_index):
+        if ops.PROFILE.events and not want_index:
             # bench.py roofline accounting: same two kernels, timed separately
-            anc32 = ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms,
-                                         cdf_mode=self.cdf_mode, index_dtype=torch.int32)
+            r = ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms,
+                                     cdf_mode=self.cdf_mode, index_dtype=torch.int32, want_stats=want_stats, want_w=want_w)
+            anc32, stats = (r[0], tuple(r[1:])) if want_stats else (r, None)
             # fraction of source rows that are actually read (distinct ancestors): the rest is served by L2
             srt = anc32 if self.strategy == "systematic" else anc32.sort(0).values
             distinct = ((srt[1:] != srt[:-1]).sum() + B).float() / float(S * B)
             ops.PROFILE.notes.setdefault("distinct_ancestor_frac", []).append(distinct)
-            return ops.gather_ancestors(latents, anc32)
+            outs = ops.gather_ancestors(latents, anc32)
+            return (outs, None, stats) if want_stats else outs
         outs, anc, stats = ops.resample(latents, log_w=log_weights, strategy=self.strategy,
                                         uniforms=uniforms, cdf_mode=self.cdf_mode,
-                                        want_index=want_index, want_stats=want_stats)
+                                        want_index=want_index, want_stats=want_stats, want_w=want_w)
         if want_stats or want_index:
             return outs, anc, stats
         return outs

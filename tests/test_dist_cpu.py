@@ -48,10 +48,11 @@ def _worker(rank, world, port, S, B, out_dir):
         w_r = torch.softmax(lw_r, 0)
         anc_r = orc.systematic_ancestors(w_r.numpy(), u_r.numpy())
         ess_r = (1. / (w_r ** 2).sum(0)).unsqueeze(0).repeat(3, 1)
-        trace = {"ess": ess_r, "density": adist.shard_instances(dens, rank, world, dim=2)}
+        logz_r = (torch.logsumexp(lw_r, 0) - np.log(S)).unsqueeze(0).repeat(3, 1)
+        trace = {"ess": ess_r, "density": adist.shard_instances(dens, rank, world, dim=2), "log_z": logz_r}
         m = adist.allreduce_metrics(trace)
         np.savez(os.path.join(out_dir, "r%d.npz" % rank), anc=anc_r, ess=m["ess"].numpy(), density=m["density"].numpy(),
-                 count=m["count"].numpy())
+                 count=m["count"].numpy(), log_z=m["log_z"].numpy())
     finally:
         dist.destroy_process_group()
 
@@ -68,7 +69,9 @@ def test_two_rank_sharded_run_equals_single_rank(tmp_path):
     parts = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(world)]
     assert np.array_equal(np.concatenate([p["anc"] for p in parts], 1), anc)
     ess = (1. / (w ** 2).sum(0)).mean().item()
+    log_z = (torch.logsumexp(log_w, 0) - np.log(S)).double().mean().item()
     for p in parts:
+        np.testing.assert_allclose(p["log_z"], log_z, rtol=1e-6)
         np.testing.assert_allclose(p["ess"], ess, rtol=1e-6)
         np.testing.assert_allclose(p["density"], dens.double().mean(1).mean(-1).numpy(), rtol=1e-6, atol=1e-9)
         assert (p["count"] == B).all()

@@ -1,0 +1,341 @@
+"""GPU parity of the instantiations the BENCHMARK runs ("What's weak" #1).
+
+bench.py's 10-sweep GMM step repeats, per sweep, the LEAN label-mode z step (`k_gmm_z_fused<..., LEAN, 32, 60>`: labels in,
+labels out, only log_w / density requested, H = 32, N = 60), the N = 60 label-mode statistics of the eta step and the fused
+draw + eta weights.  The tests of tests/test_gmm_gpu.py reach those kernels mostly through their non-lean variants
+(want_q / parts / local), so this file pins the lean launches themselves, at S = 1000:
+
+  * against the oracle (oracle/gmm.py == the reference bit for bit on CPU): labels = inverse CDF of the oracle's q_probs on
+    the same uniforms (a label may differ only where u sits on a CDF boundary), log_w / density against
+    oracle.gmm.z_step_weights on the kernel's own draw (teacher-forced), 1e-5 relative to the summed magnitudes;
+  * bit for bit against the non-lean variant on the same inputs;
+  * at the full BASELINE.json shapes (C2: S = 1000, B = 1024) on slices of instances incl. b = 0 and b = B - 1;
+  * through apg_objective with the bench flags, compact labels vs the one-hot objective.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gmm as og
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RT = 1e-5
+BENCH_FLAGS = {"loss_required": False, "ess_required": True, "mode_required": False, "density_required": True}
+
+
+class _Gen:
+    def __init__(self, K=3, D=2):
+        pr = og.make_prior(K, D)
+        self.prior_alpha, self.prior_beta = pr["alpha"].to(DEV), pr["beta"].to(DEV)
+        self.prior_mu, self.prior_nu, self.prior_pi = pr["mu"].to(DEV), pr["nu"].to(DEV), pr["pi"].to(DEV)
+        self.prior_ng = (self.prior_alpha, self.prior_beta, self.prior_mu, self.prior_nu)
+
+
+def _mlp(P):
+    p = P["enc_apg_z"]
+    return [p[k].to(DEV) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+
+
+def _heads(P):
+    p = P["enc_apg_eta"]
+    return [p[k].to(DEV) for k in ("gamma.0.weight", "gamma.0.bias", "ob.0.weight", "ob.0.bias")]
+
+
+def _close(a, b, rtol=RT, atol=0.0, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    atol_t = atol.cpu().double() if torch.is_tensor(atol) else torch.full_like(b, atol)
+    err = (a - b).abs() - (atol_t + rtol * b.abs())
+    assert float(err.max()) <= 0, "%s: worst excess %g (max abs diff %g)" % (what, float(err.max()), float((a - b).abs().max()))
+    return float(((a - b).abs() / (atol_t + rtol * b.abs()).clamp_min(1e-300)).max())
+
+
+def _pad_labels(lab, LN=64):
+    out = torch.full(tuple(lab.shape[:2]) + (LN,), 255, dtype=torch.uint8, device=lab.device)
+    out[..., :lab.shape[-1]] = lab
+    return out
+
+
+def _latents(S, B, K=3, D=2, N=60, seed=0):
+    """a particle population like the one a sweep carries: data from the simulator, eta around the data."""
+    torch.manual_seed(seed)
+    x = og.simulate(B, N, K, D)
+    tau = torch.rand(S, B, K, D) * 3 + 0.2
+    mu = torch.randn(S, B, K, D) * 2
+    lab_old = torch.randint(0, K, (S, B, N), dtype=torch.uint8)
+    u = torch.rand(S, B, N)
+    return x, tau, mu, lab_old, u
+
+
+def _check_z_lean_vs_oracle(P, x, tau, mu, lab_old, u, lab_new, w, K=3):
+    """x (b,N,D) ... CPU tensors of a slice of instances; lab_new / w the lean kernel's outputs for the same slice."""
+    S = tau.shape[0]
+    prior = og.make_prior(K, x.shape[-1])
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    q_ref = og.enc_apg_z_probs(P["enc_apg_z"], xs, tau, mu)
+    cdf = torch.cumsum(q_ref, -1)
+    lab_ref = (u.unsqueeze(-1) * cdf[..., -1:] >= cdf[..., :-1]).sum(-1)
+    bad = lab_new.long() != lab_ref
+    assert float(bad.float().mean()) <= 1e-3, "label mismatch fraction %g" % float(bad.float().mean())
+    gap = (u.unsqueeze(-1) * cdf[..., -1:] - cdf[..., :-1]).abs().min(-1).values
+    assert bool((gap[bad] < 1e-5).all()), "a label differs away from a CDF boundary"
+    z_new = torch.nn.functional.one_hot(lab_new.long(), K).float()
+    z_old = torch.nn.functional.one_hot(lab_old.long(), K).float()
+    ref = og.z_step_weights(xs, tau, mu, q_ref, prior, z_new, z_old, parts=True)
+    r1 = _close(w["log_w"], ref[1], rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="lean log_w")
+    r2 = _close(w["density"], ref[3].sum(-1), what="lean density")
+    return int(bad.sum()), r1, r2
+
+
+def test_lean_z_step_vs_oracle_and_vs_nonlean_S1000():
+    """the launch a sweep repeats: labels in / out, log_w + density only, H = 32, N = 60, S = 1000."""
+    from apgs_b200.gmm import kernels
+    S, B, N, K, D = 1000, 64, 60, 3, 2
+    torch.manual_seed(0)
+    P = og.make_params(K, D, 32)
+    x, tau, mu, lab_old, u = _latents(S, B, K, D, N, seed=1)
+    gen = _Gen(K, D)
+    xd, td, md, ud = x.to(DEV), tau.to(DEV), mu.to(DEV), u.to(DEV)
+    lab_pad = _pad_labels(lab_old.to(DEV))
+    # lean: only log_w / log_q_f / density
+    z_lean, q_none, w_lean = kernels.z_step_fused(xd, td, md, _mlp(P), gen, z_old=lab_pad, uniforms=ud)
+    assert q_none is None and w_lean.log_w_f is None and w_lean.log_w_local is None
+    assert z_lean.dtype == torch.uint8 and tuple(z_lean.shape) == (S, B, 64)
+    # non-lean variants of the same step: every optional output requested / one-hot z
+    z_full, q_full, w_full = kernels.z_step_fused(xd, td, md, _mlp(P), gen, z_old=lab_pad, uniforms=ud,
+                                                  want_q=True, parts=True, local=True)
+    assert torch.equal(z_lean[..., :N], z_full[..., :N]), "lean labels != non-lean labels"
+    for name in ("log_w", "density", "log_q_f"):
+        assert torch.equal(getattr(w_lean, name), getattr(w_full, name)), "lean %s is not bit-identical to the non-lean variant" % name
+    z_hot, _, w_hot = kernels.z_step_fused(xd, td, md, _mlp(P), gen, z_old=torch.nn.functional.one_hot(lab_old.long(), K).float().to(DEV),
+                                           uniforms=ud)
+    assert torch.equal(z_hot.argmax(-1), z_lean[..., :N].long()) and torch.equal(w_hot.log_w, w_lean.log_w)
+    # the oracle on 16 of the instances (the (S,b,N,K,H) activations of the reference MLP are 23 MB per instance)
+    sel = [0, 1, 2, 3, 4, 5, 6, 7, 31, 32, 33, 59, 60, 61, 62, 63]
+    w_sel = {"log_w": w_lean.log_w[:, sel].cpu(), "density": w_lean.density[:, sel].cpu()}
+    nbad, r1, r2 = _check_z_lean_vs_oracle(P, x[sel], tau[:, sel], mu[:, sel], lab_old[:, sel], u[:, sel],
+                                           z_lean[:, sel, :N].cpu(), w_sel, K)
+    print("lean z step S=1000: %d boundary labels of %d; worst log_w err / bound %.3f, density %.3f" % (nbad, S * len(sel) * N, r1, r2))
+
+
+def test_lean_eta_statistics_and_draw_weights_vs_oracle_S1000():
+    """k_gmm_nss_im<..., STATS, 60> in label mode + k_gmm_eta_weights_stats with the fused draw, S = 1000."""
+    from apgs_b200.gmm import kernels
+    S, B, N, K, D = 1000, 24, 60, 3, 2
+    torch.manual_seed(0)
+    P = og.make_params(K, D, 32)
+    prior = og.make_prior(K, D)
+    x, tau_old, mu_old, lab, _ = _latents(S, B, K, D, N, seed=2)
+    # centres near the data, as in a sweep (the statistics are centred at the old mu)
+    gen = _Gen(K, D)
+    lab_pad = _pad_labels(lab.to(DEV))
+    *post, stats = kernels.eta_posterior_fused(x.to(DEV), lab_pad, _heads(P), gen, center=mu_old.to(DEV))
+    z = torch.nn.functional.one_hot(lab.long(), K).float()
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    ref_post = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, z, prior)
+    xp, gamma = og.enc_eta_heads(P["enc_apg_eta"], torch.cat((xs, z), -1))
+    g5, x5 = gamma.double().unsqueeze(-1), xp.double().unsqueeze(-2)
+    s2a, s3 = (g5 * x5.abs()).sum(2), (g5 * x5 ** 2).sum(2)
+    cnt = gamma.double().sum(2).unsqueeze(-1).expand_as(s3).clone()
+    cnt[cnt == 0] = 1
+    _close(post[0], ref_post[0], what="alpha")
+    _close(post[3], ref_post[3], what="nu")
+    _close(post[2], ref_post[2], atol=2e-6 * s2a / cnt, what="mu")
+    _close(post[1], ref_post[1], atol=4e-6 * (s3.abs() + s2a ** 2 / cnt), what="beta")
+    # centred one-hot statistics
+    dx = xs.unsqueeze(3) - mu_old.unsqueeze(2)                                    # S,B,N,K,D
+    zz = z.unsqueeze(-1)
+    ref_stats = torch.cat((z.sum(2).unsqueeze(-1), (zz * dx).sum(2), (zz * dx * dx).sum(2)), -1)
+    mag = torch.cat((z.sum(2).unsqueeze(-1), (zz * dx.abs()).sum(2), (zz * dx * dx).sum(2)), -1)
+    _close(stats, ref_stats, rtol=0, atol=4e-6 * mag + 1e-6, what="centred statistics")
+    # the fused draw + eta weights on the kernel's own posterior parameters
+    torch.manual_seed(5)
+    g_std = torch._standard_gamma(post[0])
+    e_std = torch.randn_like(post[2])
+    w, tau, mu = kernels.draw_logw_eta_stats(stats, mu_old.to(DEV), tuple(post), gen, g_std, e_std, tau_old.to(DEV), mu_old.to(DEV), parts=True)
+    post_c = [p.cpu() for p in post]
+    ref = og.eta_step_weights(xs, z, post_c, prior, tau.cpu(), mu.cpu(), tau_old, mu_old, parts=True)
+    _close(w.log_w_f, ref[4], what="eta log_w_f")
+    _close(w.log_w_b, ref[5], what="eta log_w_b")
+    _close(w.density, ref[2], what="eta density")
+    _close(w.log_w, ref[0], rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="eta log_w")
+    # without `parts` (the launch the sweep makes) the same numbers come out
+    w2, tau2, mu2 = kernels.draw_logw_eta_stats(stats, mu_old.to(DEV), tuple(post), gen, g_std, e_std, tau_old.to(DEV), mu_old.to(DEV))
+    assert torch.equal(tau2, tau) and torch.equal(mu2, mu)
+    for name in ("log_w", "density", "log_q_f"):
+        assert torch.equal(getattr(w2, name), getattr(w, name)), name
+
+
+def test_full_shape_C2_slices_vs_oracle():
+    """BASELINE.json configs[1]: S = 1000, B = 1024 through the lean launches; instances 0, 511, 1022, 1023 against the oracle."""
+    from apgs_b200.gmm import kernels
+    S, B, N, K, D = 1000, 1024, 60, 3, 2
+    torch.manual_seed(0)
+    P = og.make_params(K, D, 32)
+    prior = og.make_prior(K, D)
+    gen = _Gen(K, D)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    torch.manual_seed(4)
+    x = og.simulate(B, N, K, D)
+    xd = x.to(DEV)
+    tau = torch.rand(S, B, K, D, device=DEV, generator=g) * 3 + 0.2
+    mu = torch.randn(S, B, K, D, device=DEV, generator=g) * 2
+    lab_old = torch.randint(0, K, (S, B, 64), dtype=torch.uint8, device=DEV, generator=g)
+    u = torch.rand(S, B, N, device=DEV, generator=g)
+    z_new, _, w = kernels.z_step_fused(xd, tau, mu, _mlp(P), gen, z_old=lab_old, uniforms=u)
+    sel = [0, 511, 1022, 1023]
+    w_sel = {"log_w": w.log_w[:, sel].cpu(), "density": w.density[:, sel].cpu()}
+    _check_z_lean_vs_oracle(P, x[sel], tau[:, sel].cpu(), mu[:, sel].cpu(), lab_old[:, sel, :N].cpu(), u[:, sel].cpu(),
+                            z_new[:, sel, :N].cpu(), w_sel, K)
+    # eta step at the full shape on the labels just drawn
+    *post, stats = kernels.eta_posterior_fused(xd, z_new, _heads(P), gen, center=mu)
+    g_std = torch._standard_gamma(post[0])
+    e_std = torch.randn_like(post[2])
+    tau_old = tau
+    we, tau2, mu2 = kernels.draw_logw_eta_stats(stats, mu, tuple(post), gen, g_std, e_std, tau_old, mu)
+    zs = torch.nn.functional.one_hot(z_new[:, sel, :N].long().cpu(), K).float()
+    xs = x[sel].unsqueeze(0).repeat(S, 1, 1, 1)
+    ref_post = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, zs, prior)
+    _close(post[0][:, sel], ref_post[0], what="alpha (C2)")
+    _close(post[3][:, sel], ref_post[3], what="nu (C2)")
+    post_c = [p[:, sel].cpu() for p in post]
+    ref = og.eta_step_weights(xs, zs, post_c, prior, tau2[:, sel].cpu(), mu2[:, sel].cpu(), tau_old[:, sel].cpu(), mu[:, sel].cpu(), parts=True)
+    _close(we.log_w[:, sel], ref[0], rtol=0, atol=RT * (ref[4].abs() + ref[5].abs()), what="eta log_w (C2)")
+    _close(we.density[:, sel], ref[2], what="eta density (C2)")
+    # resample at the full shape: ancestors of the kernel == oracle ancestors given the kernel's normalised weights
+    from apgs_b200 import ops
+    from oracle import resampler as orc
+    ub = torch.rand(B, device=DEV, generator=g)
+    anc, wn, ess, lse = ops.sample_ancestors(log_w=we.log_w, strategy="systematic", uniforms=ub, want_stats=True)
+    a_ref = orc.systematic_ancestors(wn[:, sel].cpu().numpy(), ub[sel].cpu().numpy())
+    assert np.array_equal(anc[:, sel].cpu().numpy(), a_ref), "ancestors (C2 slices)"
+    outs = ops.gather_ancestors([tau2, mu2, z_new], anc)
+    for o, v in zip(outs, (tau2, mu2, z_new)):
+        ref_g = orc.gather_ancestors(v[:, sel].cpu().numpy(), a_ref)
+        assert np.array_equal(o[:, sel].cpu().numpy(), ref_g), "gather (C2 slices)"
+    lse_ref = torch.logsumexp(we.log_w[:, sel].cpu().double(), 0)
+    _close(lse[sel], lse_ref, rtol=RT, what="lse (C2)")
+
+
+def _models_from_params(P, K=3, D=2, H=32):
+    from apgs_b200.gmm import models as M
+    ms = M.init_apg_models(K, D, H, True, DEV)
+    for m, key in zip(ms[:3], ("enc_rws_eta", "enc_apg_z", "enc_apg_eta")):
+        m.load_state_dict({k: v.to(DEV) for k, v in P[key].items()})
+    return ms
+
+
+def test_objective_bench_flags_compact_labels_vs_one_hot():
+    """apg_objective with the flags bench.py uses (ess + density, no mode, no loss).  With the lean one-shot switched off
+    in both runs, carrying z as labels (lean z-step / N=60 statistics launches) or one-hot (their non-lean variants)
+    gives identical traces bit for bit; the lean one-shot itself only re-associates one sum (checked to tolerance on
+    sweep 0, which is independent of the resampling that follows)."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B, sweeps = 1000, 12, 4
+    torch.manual_seed(0)
+    models = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    out = {}
+    for tag, compact, lean1 in (("hot", False, False), ("lab", True, False), ("lean", True, True)):
+        O.compact_labels, O.lean_oneshot = compact, lean1
+        try:
+            torch.manual_seed(5)
+            with torch.no_grad():
+                out[tag] = O.apg_objective(models, x, BENCH_FLAGS, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
+        finally:
+            O.compact_labels, O.lean_oneshot = True, True
+    for k in ("ess", "density"):
+        assert torch.equal(out["lab"][k], out["hot"][k]), k
+    d0, d1 = out["lean"]["density"][0], out["hot"]["density"][0]
+    _close(d0, d1, rtol=3e-6, atol=1e-4, what="one-shot density, lean vs regular")
+    for k in ("ess", "density"):
+        assert tuple(out["lean"][k].shape) == tuple(out["hot"][k].shape) and bool(torch.isfinite(out["lean"][k]).all())
+
+
+# ------------------------------------------------------------------ W1 from the resampling launch, log-marginal
+@pytest.mark.parametrize("strategy", ["systematic", "multinomial"])
+def test_resample_stats_equal_weight_stats_and_log_marginal(strategy):
+    """Resampler.resample(want_stats=True): w / ESS / lse come out of the ancestor kernel's own softmax -- bit-identical
+    to apgs_weight_stats_f32 on the same log-weights, lse = torch.logsumexp within 1e-5 (north_star: log-marginal)."""
+    from apgs_b200 import ops
+    from apgs_b200.resampler import Resampler
+    S, B = 1000, 96
+    torch.manual_seed(7)
+    lw = (torch.randn(S, B) * 4).to(DEV)
+    lat = [torch.randn(S, B, 3, 2, device=DEV), torch.randint(0, 3, (S, B, 64), dtype=torch.uint8, device=DEV)]
+    rs = Resampler(strategy, S, True, DEV)
+    u = rs.draw_uniforms(S, B, DEV)
+    w0, ess0, lse0 = ops.weight_stats(lw, want_w=True)
+    outs, anc, (w1, ess1, lse1) = rs.resample(lat, lw, uniforms=u, want_stats=True, want_index=True)
+    assert torch.equal(w0, w1) and torch.equal(ess0, ess1) and torch.equal(lse0, lse1)
+    outs2, _, (w2, ess2, lse2) = rs.resample(lat, lw, uniforms=u, want_stats=True, want_w=False)
+    assert w2 is None and torch.equal(ess2, ess0) and torch.equal(lse2, lse0)
+    plain = rs.resample(lat, lw, uniforms=u)
+    for a, b, c in zip(outs, outs2, plain):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    _close(lse1, torch.logsumexp(lw.cpu().double(), 0), rtol=RT, what="lse")
+    _close(ess1, 1. / (torch.softmax(lw.cpu().double(), 0) ** 2).sum(0), rtol=RT, what="ess")
+
+
+def test_objective_reports_log_marginal_estimate():
+    """trace['log_z'][m, b] = logsumexp_s log_w - log S of the step whose ESS is trace['ess'][m, b]."""
+    from apgs_b200.gmm import objectives as O, kernels
+    from apgs_b200.resampler import Resampler
+    from apgs_b200 import dist as adist
+    S, B, sweeps = 50, 20, 3
+    torch.manual_seed(0)
+    models = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    with torch.no_grad():
+        tr = O.apg_objective(models, x, BENCH_FLAGS, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
+    assert tuple(tr["log_z"].shape) == (sweeps, B) and bool(torch.isfinite(tr["log_z"]).all())
+    # ESS and log Z-hat are consistent: ess <= S, and for the one-shot both come from the same log-weights: recompute them
+    # through the public step function on the same seed
+    torch.manual_seed(9)
+    with torch.no_grad():
+        trace = {'loss': [], 'ess': [], 'E_tau': [], 'E_mu': [], 'E_z': [], 'density': []}
+        log_w, tau, mu, z, trace = O.oneshot(models[0], models[1], models[3], x.unsqueeze(0).expand(S, -1, -1, -1), trace, BENCH_FLAGS)
+    ref = torch.logsumexp(log_w.cpu().double(), 0) - np.log(S)
+    _close(trace["log_z"][0][0], ref, rtol=RT, what="log_z of the one-shot")
+    m = adist.allreduce_metrics(tr)
+    _close(m["log_z"], tr["log_z"].double().mean(-1), rtol=1e-12, what="metric means")
+
+
+# ------------------------------------------------------------------ B-sharded == single
+@pytest.mark.parametrize("world", [2, 3])
+def test_instance_sharded_kernels_equal_the_full_batch_bit_for_bit(world):
+    """every kernel of the sweep run on B-slices (its uniforms / variates sliced from ONE global draw via
+    dist.shard_uniforms / shard_instances) reproduces the full-B run bit for bit: z step, eta statistics, draw + eta
+    weights, ancestors, gather.  (No op mixes instances, SURVEY.md 8e -- this is the GPU-side check of it.)"""
+    from apgs_b200 import ops, dist as adist
+    from apgs_b200.gmm import kernels
+    S, B, N, K, D = 200, 37, 60, 3, 2
+    torch.manual_seed(0)
+    P = og.make_params(K, D, 32)
+    gen = _Gen(K, D)
+    x, tau, mu, lab, u = [t.to(DEV) for t in _latents(S, B, K, D, N, seed=3)]
+    lab = _pad_labels(lab)
+    g_std = torch._standard_gamma(torch.full((S, B, K, D), 3.0, device=DEV))
+    e_std = torch.randn(S, B, K, D, device=DEV)
+    ub = torch.rand(B, device=DEV)
+
+    def sweep(x, tau, mu, lab, u, g_std, e_std, ub):
+        z_new, _, wz = kernels.z_step_fused(x, tau, mu, _mlp(P), gen, z_old=lab, uniforms=u)
+        outs, anc, st = ops.resample([tau, mu, z_new], log_w=wz.log_w, uniforms=ub, want_index=True, want_stats=True)
+        tau1, mu1, z1 = outs
+        *post, stats = kernels.eta_posterior_fused(x, z1, _heads(P), gen, center=mu1)
+        we, tau2, mu2 = kernels.draw_logw_eta_stats(stats, mu1, tuple(post), gen, g_std, e_std, tau1, mu1)
+        return dict(z_new=z_new[..., :N], log_w_z=wz.log_w, dens_z=wz.density, anc=anc, ess=st[1], lse=st[2], tau1=tau1, mu1=mu1,
+                    z1=z1[..., :N], alpha=post[0], beta=post[1], stats=stats, log_w_eta=we.log_w, tau2=tau2, mu2=mu2)
+    full = sweep(x, tau, mu, lab, u, g_std, e_std, ub)
+    parts = []
+    for r in range(world):
+        sl = lambda t, dim: adist.shard_instances(t, r, world, dim=dim).contiguous()      # noqa: E731
+        parts.append(sweep(sl(x, 0), sl(tau, 1), sl(mu, 1), sl(lab, 1), sl(u, 1), sl(g_std, 1), sl(e_std, 1),
+                           adist.shard_uniforms(ub, r, world).contiguous()))
+    for k, v in full.items():
+        dim = 0 if v.dim() == 1 else 1
+        assert torch.equal(torch.cat([p[k] for p in parts], dim), v), k
