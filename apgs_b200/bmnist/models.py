@@ -144,3 +144,9 @@ def init_models(frame_pixels, digit_pixels, num_hidden_digit, num_hidden_coor, z
         for p in m.parameters():
             p.requires_grad = False
     return (enc_coor, dec_coor, enc_digit, dec_digit)
+
+
+def save_models(models, save_version):
+    """apgs/bmnist/apg_training.py:95-104: weights/cp-<version> with keys enc-coor / enc-digit / dec-digit."""
+    from .. import checkpoint
+    return checkpoint.save("bmnist", models, save_version)

@@ -16,6 +16,8 @@ gathers, affine_transformer.reconstruct_ll_torch) are rebuilt with PyTorch ops o
 the detached kernel weights.  Everything else (weights, ESS, densities, resampling) stays in the
 kernels.
 """
+import math
+
 import torch
 from torch.distributions.normal import Normal
 
@@ -50,6 +52,7 @@ def apg_objective(models, AT, frames, K, result_flags, num_sweeps, resampler, mn
         trace['loss_theta'] = torch.cat(trace['loss_theta'], 0)
     if result_flags['ess_required']:
         trace['ess'] = torch.cat(trace['ess'], 0)
+        trace['log_z'] = torch.cat(trace['log_z'], 0)
     if result_flags['mode_required']:
         trace['E_where'] = torch.cat(trace['E_where'], 0)
         trace['E_what'] = torch.cat(trace['E_what'], 0)
@@ -124,12 +127,13 @@ def oneshot(enc_coor, dec_coor, enc_digit, dec_digit, AT, frames, digit, trace, 
         log_q = log_q_where + Normal(q_mu, q_std, validate_args=False).log_prob(z_what).sum(-1).sum(-1)
         ll_sum = AT.reconstruct_ll_torch(dec_digit.templates(z_what), z_where, frames).sum(-1)
     if result_flags['loss_required'] or result_flags['ess_required']:
-        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        w, ess, lse = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
         if result_flags['loss_required']:
             trace['loss_phi'].append((w * (-log_q)).sum(0).mean().unsqueeze(0))
             trace['loss_theta'].append((w * (-ll_sum)).sum(0).mean().unsqueeze(0))
         if result_flags['ess_required']:
             trace['ess'].append(ess.unsqueeze(0))
+            trace.setdefault('log_z', []).append((lse - math.log(log_w.shape[0])).unsqueeze(0))     # log-marginal estimate (W1)
     if result_flags['mode_required']:
         trace['E_where'].append(E_where.mean(0).unsqueeze(0))
         trace['E_what'].append(q_mu.detach().mean(0).unsqueeze(0))
@@ -200,15 +204,47 @@ def apg_what(enc_digit, dec_digit, AT, frames, z_where, z_what_old, trace, resul
         if needs_grad(dec_digit):
             ll_sum = AT.reconstruct_ll_torch(dec_digit.templates(z_what), z_where, frames).sum(-1)
     if result_flags['loss_required'] or result_flags['ess_required']:
-        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        w, ess, lse = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
         if result_flags['loss_required']:
             trace['loss_phi'][-1] = trace['loss_phi'][-1] + (w * (-log_q_f)).sum(0).mean().unsqueeze(0)
             trace['loss_theta'][-1] = trace['loss_theta'][-1] + (w * (-ll_sum)).sum(0).mean().unsqueeze(0)
         if result_flags['ess_required']:
             trace['ess'].append(ess.unsqueeze(0))
+            trace.setdefault('log_z', []).append((lse - math.log(log_w.shape[0])).unsqueeze(0))     # log-marginal estimate (W1)
     if result_flags['mode_required']:
         trace['E_what'].append(q_mu.detach().mean(0).unsqueeze(0))
         trace['E_recon'].append(recon.mean(0).unsqueeze(0))
     if result_flags['density_required']:
         trace['density'][-1] = trace['density'][-1] + dens.unsqueeze(0)
+    return log_w, z_what, trace
+
+
+# ------------------------------------------------------------------ baseline around the path
+def bpg_objective(models, AT, frames, result_flags, num_sweeps, resampler, mnist_mean):
+    """APG whose z_what block proposes from the prior (apgs/bmnist/objectives.py:272-288)."""
+    trace = {'density': []}
+    frames = _frames5(frames, resampler.S)
+    (enc_coor, dec_coor, enc_digit, dec_digit) = models
+    log_w, z_where, z_what, trace = oneshot(enc_coor, dec_coor, enc_digit, dec_digit, AT, frames, mnist_mean, trace, result_flags)
+    z_where, z_what = resample_variables(resampler, z_where, z_what, log_weights=log_w)
+    for m in range(num_sweeps - 1):
+        z_where, trace = apg_where(enc_coor, dec_coor, dec_digit, AT, resampler, frames, z_what, z_where, trace, result_flags)
+        log_w, z_what, trace = bpg_what(dec_digit, AT, frames, z_where, z_what, trace)
+        z_where, z_what = resample_variables(resampler, z_where, z_what, log_weights=log_w)
+    trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def bpg_what(dec_digit, AT, frames, z_where, z_what_old, trace):
+    """z_what proposed from its prior: weight = likelihood ratio (apgs/bmnist/objectives.py:290-302).  The B4 `what`
+    kernel with the prior as the proposal (log p - log q cancels term by term); density += ll_f + log p(z_what_new)."""
+    S, B, T, K, _ = z_where.shape
+    shape = (S, B, K, z_what_old.shape[-1])
+    q_mu = dec_digit.prior_mu.expand(shape).contiguous()
+    q_std = dec_digit.prior_std.expand(shape).contiguous()
+    z_what = normal_sample(q_mu, q_std)
+    ll_f, _ = AT.reconstruct_ll(dec_digit.templates(z_what), z_where, frames)
+    ll_b, _ = AT.reconstruct_ll(dec_digit.templates(z_what_old), z_where, frames)
+    log_w, _, dens, _ = kernels.logw_what(q_mu, q_std, z_what, z_what_old, ll_f, ll_b)
+    trace['density'][-1] = trace['density'][-1] + dens.unsqueeze(0)
     return log_w, z_what, trace

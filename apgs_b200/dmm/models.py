@@ -248,3 +248,9 @@ def init_apg_models(K, D, num_hidden_mu, num_nss, num_hidden_local, num_hidden_d
         for p in m.parameters():
             p.requires_grad = False
     return (enc_rws_mu, enc_apg_local, enc_apg_mu, dec)
+
+
+def save_apg_models(models, save_version):
+    """apgs/dmm/apg_training.py:103-116: weights/cp-<version> with keys enc-rws-mu / enc-apg-local / enc-apg-mu / dec."""
+    from .. import checkpoint
+    return checkpoint.save("dmm", models, save_version)

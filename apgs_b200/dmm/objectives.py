@@ -12,6 +12,8 @@ terms are rebuilt with PyTorch ops on the kernels' draws and multiplied by the d
 train() works unchanged and gets the reference's gradients, while weights, ESS, densities and resampling still come
 from the kernels.
 """
+import math
+
 import torch
 from torch.distributions.beta import Beta
 from torch.distributions.normal import Normal
@@ -25,12 +27,14 @@ from .models import needs_grad
 
 def _book(trace, result_flags, log_w, log_q, ll, density):
     if result_flags['loss_required'] or result_flags['ess_required']:
-        w, ess, _ = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
+        w, ess, lse = ops.weight_stats(log_w, want_w=result_flags['loss_required'])
         if result_flags['loss_required']:
             trace['loss_phi'].append((w * (-log_q)).sum(0).mean().unsqueeze(0))
             trace['loss_theta'].append((w * (-ll)).sum(0).mean().unsqueeze(0))
         if result_flags['ess_required']:
             trace['ess'].append(ess.unsqueeze(0))
+            # log-marginal estimate of the step, logsumexp_s log_w - log S: the kernel's lse output
+            trace.setdefault('log_z', []).append((lse - math.log(log_w.shape[0])).unsqueeze(0))
     if result_flags['density_required']:
         trace['density'].append(density.unsqueeze(0))
 
@@ -60,6 +64,7 @@ def apg_objective(models, x, K, result_flags, num_sweeps, resampler):
         trace['loss_theta'] = torch.cat(trace['loss_theta'], 0)
     if result_flags['ess_required']:
         trace['ess'] = torch.cat(trace['ess'], 0)
+        trace['log_z'] = torch.cat(trace['log_z'], 0)
     if result_flags['mode_required']:
         trace['E_mu'] = torch.cat(trace['E_mu'], 0)
         trace['E_z'] = torch.cat(trace['E_z'], 0)
@@ -182,3 +187,36 @@ def _update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_f
 def resample_variables(resampler, mu, z, beta, log_weights):
     mu, z, beta = resampler.resample([mu, z, beta], log_weights)
     return mu, z, beta
+
+
+# ------------------------------------------------------------------ baseline around the path
+def bpg_objective(models, x, K, result_flags, num_sweeps, resampler):
+    """APG whose mu block proposes from the prior (apgs/dmm/objectives.py:209-224); the reference runs it with
+    S * bpg_factor particles, which is what the split-S ancestor pipeline is for."""
+    trace = {'density': []}
+    (enc_rws_mu, enc_apg_local, enc_apg_mu, dec) = models
+    if x.dim() == 3:
+        x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)
+    log_w, mu, z, beta, h2, trace = _oneshot(enc_rws_mu, enc_apg_local, dec, x, K, trace, result_flags)
+    mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w)
+    for m in range(num_sweeps - 1):
+        log_w_mu, mu, trace = bpg_update_mu(enc_apg_mu, dec, x, z, beta, mu, K, trace, h2=h2)
+        mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w_mu)
+        log_w_z, z, beta, h2, trace = _update_local(enc_apg_local, dec, x, mu, z, beta, K, trace, result_flags, h2_old=h2)
+        mu, z, beta, h2 = resampler.resample([mu, z, beta, h2], log_w_z)
+    trace['density'] = torch.cat(trace['density'], 0)
+    return trace
+
+
+def bpg_update_mu(enc_apg_mu, dec, x, z, beta, mu_old, K, trace, h2=None):
+    """mu proposed from its prior: weight = likelihood ratio (apgs/dmm/objectives.py:226-236).  One D2 launch with the
+    prior as the proposal -- log p(mu) - log q(mu) cancels inside the kernel -- leaving ll_f - ll_b; density = log p(mu_new)."""
+    S, B, K_, D = mu_old.shape
+    q_mu = dec.prior_mu_mu.expand(S, B, K_, D).contiguous()
+    q_sigma = dec.prior_mu_sigma.expand(S, B, K_, D).contiguous()
+    mu = normal_sample(q_mu, q_sigma)
+    if h2 is None:
+        h2 = dec.hidden2(beta)
+    w = kernels.logw_mu(x, z, h2, q_mu, q_sigma, mu, mu_old, dec)
+    trace['density'].append(w.density.unsqueeze(0))
+    return w.log_w, mu, trace

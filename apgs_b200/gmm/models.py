@@ -268,3 +268,9 @@ def init_apg_models(K, D, num_hidden_z, CUDA, device, load_version=None, lr=None
         for p in m.parameters():
             p.requires_grad = False
     return (enc_rws_eta, enc_apg_z, enc_apg_eta, generative)
+
+
+def save_apg_models(models, save_version):
+    """apgs/gmm/apg_training.py:101-115: weights/cp-<version> with keys enc-rws-eta / enc-apg-z / enc-apg-eta."""
+    from .. import checkpoint
+    return checkpoint.save("gmm", models, save_version)

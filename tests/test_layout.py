@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _py_files(d):
-    for base, _, files in os.walk(os.path.join(ROOT, d)):
+    for base, dirs, files in os.walk(os.path.join(ROOT, d)):
+        dirs[:] = [x for x in dirs if x != "_ref"]          # oracle/_ref: the installed, unmodified reference (git-ignored)
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 yield os.path.join(base, f)
