@@ -192,7 +192,7 @@ def bmnist_step_fn(S, B, sweeps, device="cpu", K=3, T=10, seed=0):
     return step
 
 
-def resample_step_fn(S, B, d, strategy="systematic", device="cpu", sigma=2.0, seed=0):
+def resample_step_fn(S, B, d, strategy="systematic", device="cpu", sigma=0.1, seed=0):
     """the reference's resample of ONE latent (S,B,1,d): sample_ancestral_index + resample_4dims (apgs/resampler.py:22-49)."""
     load()
     from apgs.resampler import Resampler
