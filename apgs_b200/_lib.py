@@ -95,6 +95,8 @@ SIGNATURES = {
                                                        _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "apgs_gmm_z_step_fused_labels_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p,
                                                 _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _OUT, _p]),
+    "apgs_gmm_z_step_fused_labels_eta_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p,
+                                                    _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _p, _PO, _p, _OUT, _p]),
     "apgs_gmm_draw_logw_eta_stats_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_logw_eta_stats_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_z_step_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p, _p,

@@ -263,10 +263,9 @@ template <int K, int D, int P, int LANES, bool STATS, int NC = 0>   // NC: point
 __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
-    constexpr int KD = K * D, IN = D + K;
-    constexpr int TE = K + 2 * KD;                                      // table planes: gamma, gamma x', gamma x'^2
-    constexpr int ST = 1 + 2 * D, NS = K * ST;                          // plain statistics per particle
-    constexpr int RW = (TE > NS ? TE : NS) | 1;                         // reduction row (odd stride: no bank conflicts)
+    constexpr int KD = K * D;
+    constexpr int TE = EtaTab<K, D>::TE;                                // table planes: gamma, gamma x', gamma x'^2
+    constexpr int RW = EtaTab<K, D>::RW;                                // reduction row (odd stride: no bank conflicts)
     const int N = NC ? NC : a.N, NK = N * K;
     const int ZS = nss_im_zstride(NK);
     const size_t zreg = max((size_t)P * ZS, (size_t)P * LANES * RW);    // z rows, later the cross-lane reduction buffer
@@ -276,8 +275,7 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     // LSU does not): K + D loaded values per point (one LDS.128 + one LDS.32 at K = 3, D = 2) and K(1 + 2D)
     // accumulating FMAs, instead of the K(1 + 2D) = 15 LDS.32 + 15 FADD of a table of products (0.37 ms, LSU-bound;
     // an array-of-structs row of 16 products cost ~2.3x the wavefronts, pairs of product planes were slower too).
-    // Row stride: a multiple of four floats with an odd number of quads, so consecutive rows fall on distinct banks.
-    constexpr int RS = (((K + D + 3) / 4) | 1) * 4;
+    constexpr int RS = EtaTab<K, D>::RS;
     static_assert(RS <= TE, "the launcher sizes the table region as TE floats per row");
     float* s_tab = s_z + (zreg + 3) / 4 * 4;                            // [NK][RS] (region sized [NK][TE])
     float* s_x = s_tab + (size_t)TE * NK;                               // [N][D]
@@ -325,61 +323,20 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
 #pragma unroll
             for (int d = 0; d < D; ++d) s_x[n * D + d] = xin[d];
         }
-        // the two Linear heads on cat(x_n, e_label) (models.py:56-65), in the accumulation order of the un-tabulated form
-        float lg[K], mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            float acc = __ldg(a.bg + k);
-#pragma unroll
-            for (int d = 0; d < D; ++d) acc = fmaf(__ldg(a.Wg + k * IN + d), xin[d], acc);
-            acc += __ldg(a.Wg + k * IN + D + lab);
-            lg[k] = acc;
-            mx = fmaxf(mx, acc);
-        }
-        float se = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) { lg[k] = ex2_ftz((lg[k] - mx) * 1.4426950408889634f); se += lg[k]; }
-        const float rse = rcp_ftz(se);
-        float xp[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            float acc = __ldg(a.bo + d);
-#pragma unroll
-            for (int i = 0; i < D; ++i) acc = fmaf(__ldg(a.Wo + d * IN + i), xin[i], acc);
-            xp[d] = acc + __ldg(a.Wo + d * IN + D + lab);
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) s_tab[(size_t)idx * RS + d] = xp[d];
-#pragma unroll
-        for (int k = 0; k < K; ++k) s_tab[(size_t)idx * RS + D + k] = lg[k] * rse;
+        eta_head_factors<K, D>(a.Wg, a.bg, a.Wo, a.bo, xin, lab, s_tab + (size_t)idx * RS);   // models.py:56-65
     }
-    float cen[STATS ? K : 1][D];
-    f32x2 c2p[STATS ? K : 1], c3p[STATS ? K : 1], ncen2[STATS ? K : 1];
-    float c1[STATS ? K : 1], c2[STATS ? K : 1][D], c3[STATS ? K : 1][D];
-    if (STATS) {
+    EtaNssAcc<K, D, STATS> acc;
+    {
+        float cen[K][D];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            c1[k] = 0.f;
+        for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                c2[k][d] = 0.f; c3[k][d] = 0.f;
-                cen[k][d] = valid ? __ldg(a.center + r * KD + k * D + d) : 0.f;
-            }
-            c2p[k] = pack2(0.f, 0.f); c3p[k] = c2p[k];
-            ncen2[k] = pack2(-cen[k][0], -cen[k][D - 1]);
-        }
+            for (int d = 0; d < D; ++d) cen[k][d] = (STATS && valid) ? __ldg(a.center + r * KD + k * D + d) : 0.f;
+        acc.init(cen);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's label rows (no-op otherwise)
     stage_wait(&bar, 0);                                        // rows landed; table and s_x visible
 
-    float ag[K], a2[K][D], a3[K][D];                            // sum gamma_k, sum gamma_k x'_d, sum gamma_k x'_d^2
-    f32x2 a2p[K], a3p[K];                                       // the same, packed, when D == 2
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        ag[k] = 0.f; a2p[k] = 0ull; a3p[k] = 0ull;
-#pragma unroll
-        for (int d = 0; d < D; ++d) { a2[k][d] = 0.f; a3[k][d] = 0.f; }
-    }
     if (valid) {
         const float* zr = s_z + (size_t)p * ZS;
         // left to the compiler's own unrolling: `#pragma unroll 8` (N = 60) measured 0.44 ms, `unroll 2` 0.351, default 0.344
@@ -392,123 +349,13 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
 #pragma unroll
                 for (int k = 1; k < K; ++k) { const float v = zr[n * K + k]; if (v > best) { best = v; lab = k; } }
             }
-            const float* t = s_tab + (size_t)(n * K + lab) * RS;
-            if (D == 2 && K >= 2) {
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(t);          // (x'_0, x'_1), (gamma_0, gamma_1)
-                float g[K];
-                unpack2(v.y, g[0], g[1]);
-#pragma unroll
-                for (int k = 2; k < K; ++k) g[k] = t[D + k];
-                const f32x2 xp2 = v.x, sq2 = mul2(xp2, xp2);                           // ob_expand, ob_expand**2
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const f32x2 gk = pack2(g[k], g[k]);
-                    ag[k] = __fadd_rn(ag[k], g[k]);
-                    a2p[k] = fma2(gk, xp2, a2p[k]);                                    // z_expand * ob_expand
-                    a3p[k] = fma2(gk, sq2, a3p[k]);                                    // z_expand * ob_expand**2
-                }
-            } else {
-                float xp[D], sq[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) { xp[d] = t[d]; sq[d] = __fmul_rn(xp[d], xp[d]); }
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float gk = t[D + k];
-                    ag[k] = __fadd_rn(ag[k], gk);
-#pragma unroll
-                    for (int d = 0; d < D; ++d) { a2[k][d] = fmaf(gk, xp[d], a2[k][d]); a3[k][d] = fmaf(gk, sq[d], a3[k][d]); }
-                }
-            }
-            if (STATS) {
-                float ind[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) { ind[k] = (lab == k) ? 1.f : 0.f; c1[k] += ind[k]; }
-                if (D == 2) {
-                    f32x2 t = pack2(s_x[n * D], s_x[n * D + D - 1]);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) t = fma2(pack2(ind[k], ind[k]), ncen2[k], t);      // x - c_lab
-                    const f32x2 t2 = mul2(t, t);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const f32x2 ik = pack2(ind[k], ind[k]);
-                        c2p[k] = fma2(ik, t, c2p[k]);
-                        c3p[k] = fma2(ik, t2, c3p[k]);
-                    }
-                } else {
-#pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        float c = 0.f;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) c = fmaf(ind[k], cen[k][d], c);
-                        const float t = s_x[n * D + d] - c, t2 = t * t;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { c2[k][d] = fmaf(ind[k], t, c2[k][d]); c3[k][d] = fmaf(ind[k], t2, c3[k][d]); }
-                    }
-                }
-            }
+            acc.add(s_tab + (size_t)(n * K + lab) * RS, lab, s_x + n * D);
         }
     }
     // ---- the LANES partials of a particle meet in shared memory (the z rows are no longer needed)
     __syncthreads();
-    float* s_red = s_z;
-    float* mine = s_red + (size_t)threadIdx.x * RW;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if (D == 2 && K >= 2) { unpack2(a2p[k], a2[k][0], a2[k][D - 1]); unpack2(a3p[k], a3[k][0], a3[k][D - 1]); }
-        mine[k] = ag[k];
-#pragma unroll
-        for (int d = 0; d < D; ++d) { mine[K + k * D + d] = a2[k][d]; mine[K + KD + k * D + d] = a3[k][d]; }
-    }
-    __syncwarp();
-    double n1 = 0.0, n2 = 0.0, n3 = 0.0;
-    const bool fin = valid && j < KD;                            // lane e = (k, d) finishes one posterior element
-    if (fin) {
-        const int k = j / D;
-#pragma unroll
-        for (int i = 0; i < LANES; ++i) {
-            const float* o = s_red + (size_t)(p * LANES + i) * RW;
-            n1 += (double)o[k]; n2 += (double)o[K + j]; n3 += (double)o[K + KD + j];
-        }
-    }
-    if (STATS) {
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (D == 2) { unpack2(c2p[k], c2[k][0], c2[k][D - 1]); unpack2(c3p[k], c3[k][0], c3[k][D - 1]); }
-            mine[k * ST] = c1[k];
-#pragma unroll
-            for (int d = 0; d < D; ++d) { mine[k * ST + 1 + d] = c2[k][d]; mine[k * ST + 1 + D + d] = c3[k][d]; }
-        }
-        __syncwarp();
-        if (valid) {
-            float* so = a.stats + r * NS;
-            for (int e = j; e < NS; e += LANES) {
-                float v = 0.f;
-#pragma unroll
-                for (int i = 0; i < LANES; ++i) v += s_red[(size_t)(p * LANES + i) * RW + e];
-                so[e] = v;
-            }
-        }
-    }
-    static_assert(KD <= LANES, "one posterior element per lane");
-    if (!fin) return;
-    {   // kls_gmm.py:110-118, fp32, reference order
-        const int e = j;
-        const float f1 = (float)n1, f2 = (float)n2, f3 = (float)n3;
-        const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
-        const float cnt = (f1 == 0.f) ? 1.f : f1;                                   // Q1
-        const float x_bar = __fdiv_rn(f2, cnt);
-        const float alpha = __fadd_rn(a0, __fdiv_rn(cnt, 2.f));
-        const float nu = __fadd_rn(n0, cnt);
-        const float cn = __fadd_rn(cnt, n0);
-        const float mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), f2), cn);
-        const float u1 = __fdiv_rn(__fsub_rn(f3, __fdiv_rn(__fmul_rn(f2, f2), cnt)), 2.f);
-        const float dx = __fsub_rn(x_bar, n0);                                       // Q2: prior_nu
-        const float u2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
-        const float beta = __fadd_rn(__fadd_rn(b0, u1), u2);
-        const long long o = r * KD + e;
-        a.oa[o] = alpha; a.ob[o] = beta; a.om[o] = mu; a.on[o] = nu;
-    }
+    eta_nss_finish<K, D, LANES, STATS>(acc, s_z + (size_t)p * LANES * RW, j, valid, r, a.ra, a.rb, a.rm, a.rn,
+                                       a.oa, a.ob, a.om, a.on, a.stats);
 }
 
 // ============================================================================================

@@ -35,6 +35,14 @@ struct ZFusedArgs {
     float* q_probs;                 // (R, N, K) out, optional
     float *log_w, *log_q_f, *dens, *log_w_f, *log_w_b;   // (R), optional
     float *lw_local, *lq_local;                           // (R, N), optional
+    // NSS (label mode only): also emit what the NEXT eta step needs from the labels just drawn -- Enc_apg_eta's
+    // Normal-Gamma posterior parameters (apgs/gmm/models.py:56-66, kls_gmm.py:92-119) and the one-hot statistics of
+    // z_new centred at this particle's mu -- so that no separate pass over the labels is needed after the resampling
+    // step (per-particle functions of (z, mu) travel with the particle through the ancestor gather).
+    const float *Wg, *bg, *Wo, *bo;                       // Enc_apg_eta heads (K, D+K), (K), (D, D+K), (D)
+    const float *ra, *rb, *rm, *rn;                       // prior alpha, beta, mu, nu (K, D)
+    float *oa, *ob, *om, *on;                             // posterior out (R, K, D)
+    float* stats;                                         // (R, K, 1 + 2 D) out
 };
 
 // ---- tile mapping -----------------------------------------------------------------------------------------------
@@ -123,12 +131,22 @@ __device__ __forceinline__ void mlp_quad_plain(const float* W1, const float (&xv
     }
 }
 
+// floats of a particle's private shared-memory block: Ee table (H4 K + 4) + per-unit maxima (H4); with NSS at least the
+// LANES x RW scratch rows of the eta-statistics reduction that reuses it
+template <int K, int D, int LANES, bool NSS>
+__host__ __device__ inline int zf_block_floats(int H4) {
+    int b = H4 * K + 4 + H4;
+    if (NSS && b < LANES * EtaTab<K, D>::RW) b = LANES * EtaTab<K, D>::RW;
+    return (b + 3) / 4 * 4;
+}
+
 // LEAN: the launch a sweep repeats -- labels in, labels out, uniforms given, no one-hot rows, no per-point outputs.
 // The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
 // HC / NC: hidden width and points per instance when known at compile time (the reference's 32 and 60), else 0.
-template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0>
+template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0, bool NSS = false>
 __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedArgs a) {
     static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
+    static_assert(!NSS || LEAN, "the eta statistics ride on the lean label-mode launch");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
     __shared__ float s_misc[1 + K];
@@ -138,7 +156,10 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
     const int NK = N * K;
     const int nIt = (N + LANES * PB - 1) / (LANES * PB);       // passes of 32 points
     const int EXS = nIt * LANES * PB;                          // floats of Ex per hidden unit
-    const int EPs = H4 * RK + 4;                               // per-particle stride of the Ee table (floats)
+    const int EPs = H4 * RK + 4;                               // floats of a particle's Ee table
+    // per-particle private block: [ Ee table (EPs) | max_k e'_k[h] (H4) ]; once the particle's lanes are through the
+    // MLP the block is scratch for the cross-lane reduction of the eta statistics (NSS: LANES rows of RW floats)
+    const int EPB = zf_block_floats<K, D, LANES, NSS>(H4);
     const bool lab_old = LEAN || a.zl_old != nullptr, lab_new = LEAN || a.zl_new != nullptr;
     const bool has_bwd = LEAN || a.z_old != nullptr || lab_old;
     const bool forced = !LEAN && a.z_forced != nullptr;
@@ -150,17 +171,17 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
     float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
     float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
     float* s_ex = s_zn + tile_f;                               // H4 * EXS, slot order inside a quad: q0 q2 q1 q3
-    float* s_e = s_ex + (size_t)H4 * EXS;                      // P * EPs
-    float* s_xm = s_e + (size_t)P * EPs;                       // H4
+    float* s_e = s_ex + (size_t)H4 * EXS;                      // P * EPB
+    float* s_xm = s_e + (size_t)P * EPB;                       // H4
     float* s_aw = s_xm + H4;                                   // H4: -2 W2[h], 0 in the padding rows
-    float* s_em = s_aw + H4;                                   // P * H4: max_k e'_k[h] per particle (range test)
-    float* s_tab = s_em + (size_t)P * H4;                            // P * KD * 3: mu, 1/(2 var), log sigma + c
+    float* s_tab = s_aw + H4;                                        // P * KD * 3: mu, 1/(2 var), log sigma + c
     float* s_x = s_tab + (size_t)P * KD * 3;                         // N * D: the instance's points (read after the MLP)
     // lean variant: the particles' uniforms and old labels are prefetched into shared memory with cp.async, so nothing
     // of them lives in registers across the MLP
     const int NU = (N + 3) / 4 * 4, LS = (N + 15) & ~15;
     float* s_u = s_x + (size_t)(N * D + 3) / 4 * 4;                  // P * NU (lean)
-    unsigned char* s_lb = reinterpret_cast<unsigned char*>(s_u + (size_t)P * NU);   // P * LS (lean)
+    unsigned char* s_lb = reinterpret_cast<unsigned char*>(s_u + (size_t)P * NU);   // P * LS (lean): old labels in, new out
+    float* s_nt = reinterpret_cast<float*>(s_lb + (size_t)P * LS);                 // N * K rows of EtaTab::RS floats (NSS)
     const int b = (int)blockIdx.x;                             // grid = (B, ceil(S / P)): no division
     const int s0 = (int)blockIdx.y * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
@@ -227,6 +248,16 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
             s_aw[i] = (i < H) ? -2.f * __ldg(a.W2 + i) : 0.f;
         }
         for (int i = threadIdx.x; i < N * D; i += P * LANES) s_x[i] = __ldg(xb + i);
+        if constexpr (NSS) {
+            // per-CTA table of Enc_apg_eta's head factors over (point, label) (see gmm_common.cuh)
+            for (int idx = threadIdx.x; idx < NK; idx += P * LANES) {
+                const int n = idx / K, lab = idx - n * K;
+                float xin[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xin[d] = __ldg(xb + n * D + d);
+                eta_head_factors<K, D>(a.Wg, a.bg, a.Wo, a.bo, xin, lab, s_nt + (size_t)idx * EtaTab<K, D>::RS);
+            }
+        }
 #pragma unroll 4
         for (int h = warp; h < H; h += (P * LANES) / 32) {
             float w[D];
@@ -292,8 +323,8 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
     // for the factorised loop right away (2^-31 Ee_k[h]); the rare particle that fails the range test below rewrites
     // its entries with the raw e' for the plain loop.
     float elo = INFINITY, ehi = -INFINITY;
-    float* ep = s_e + (size_t)p * EPs;
-    float* em = s_em + (size_t)p * H4;
+    float* ep = s_e + (size_t)p * EPB;
+    float* em = ep + EPs;
     float tk[KD], mk[KD];
     if (valid) {
 #pragma unroll
@@ -466,7 +497,8 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
                         for (int k = 0; k < K; ++k) zn[n * K + k] = (k == lf) ? 1.f : 0.f;
                     }
                 }
-                if (lab_new) zln[n] = (unsigned char)lf;
+                if (LEAN) s_lb[(size_t)p * LS + n] = (unsigned char)lf;      // the old label of this point is already in lbq
+                else if (lab_new) zln[n] = (unsigned char)lf;
                 float plf = pr[0], lpf = logpi[0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) if (lf == k) { plf = pr[k]; lpf = logpi[k]; }
@@ -507,6 +539,53 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
                 if (want_lq) a.lq_local[r * N + n] = lqf;
             }
         }
+    }
+    if (LEAN) {
+        // ---- label rows out: the N label bytes of a particle sit in shared memory; its lanes store them as 16-byte
+        // vectors (pad bytes of the caller's row are never written)
+        __syncwarp();
+        if (valid) {
+            unsigned char* zln = a.zl_new + r * a.LN;
+            const unsigned char* src = s_lb + (size_t)p * LS;
+            if ((a.LN & 15) == 0 && aligned(a.zl_new, 16)) {
+                for (int off = j * 16; off < N; off += LANES * 16) {
+                    int len = N - off;
+                    if (len >= 16) {
+                        *reinterpret_cast<uint4*>(zln + off) = *reinterpret_cast<const uint4*>(src + off);
+                    } else {
+                        int o = off;
+                        if (len & 8) { *reinterpret_cast<uint2*>(zln + o) = *reinterpret_cast<const uint2*>(src + o); o += 8; }
+                        if (len & 4) { *reinterpret_cast<unsigned int*>(zln + o) = *reinterpret_cast<const unsigned int*>(src + o); o += 4; }
+                        if (len & 2) { *reinterpret_cast<unsigned short*>(zln + o) = *reinterpret_cast<const unsigned short*>(src + o); o += 2; }
+                        if (len & 1) zln[o] = src[o];
+                    }
+                }
+            } else {
+                for (int n = j; n < N; n += LANES) zln[n] = src[n];
+            }
+        }
+    }
+    if constexpr (NSS) {
+        // ---- the next eta step's inputs from the labels just drawn (k_gmm_nss_im's arithmetic, same order: this lane
+        // owns the points n = j, j + LANES, ... -- exactly the labels it wrote itself)
+        EtaNssAcc<K, D, true> acc;
+        {
+            float cen[K][D];
+            const float* tab = s_tab + (size_t)p * (KD * 3);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int d = 0; d < D; ++d) cen[k][d] = valid ? tab[(k * D + d) * 3] : 0.f;      // this particle's mu
+            acc.init(cen);
+        }
+        if (valid) {
+            for (int n = j; n < N; n += LANES) {
+                const int lab = min((int)s_lb[(size_t)p * LS + n], K - 1);
+                acc.add(s_nt + (size_t)(n * K + lab) * EtaTab<K, D>::RS, lab, s_x + n * D);
+            }
+        }
+        __syncwarp();                                  // every lane of the particle is through with its Ee / em block
+        eta_nss_finish<K, D, LANES, true>(acc, ep, j, valid, r, a.ra, a.rb, a.rm, a.rn, a.oa, a.ob, a.om, a.on, a.stats);
     }
     const double S_llf = group_sum<LANES>(A_llf.value()), S_lpzf = group_sum<LANES>(A_lpzf.value());
     const double S_lqzf = group_sum<LANES>(A_lqzf.value());
@@ -551,28 +630,60 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
 // walks four chunks of its instance (one Ex table, no CTA barrier after the first chunk) 1.21 ms.
 constexpr int kFP = 32, kFLanes = 8, kFPB = 4;
 
+template <int K, int D, bool NSS>
+static int launch_zfused_lean(const ZFusedArgs& a, cudaStream_t st, size_t smem_used) {
+    auto kern = a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60, NSS>
+                                       : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 0, NSS>)
+                          : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 0, 0, NSS>;
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_used), "smem attr");
+    const int chunks = (a.S + kFP - 1) / kFP;
+    kern<<<dim3((unsigned int)a.B, (unsigned int)chunks), kFP * kFLanes, smem_used, st>>>(a);
+    APGS_LAUNCH_OK("k_gmm_z_fused launch");
+    return 0;
+}
+
 template <int K, int D>
 static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const int H4 = (a.H + 3) / 4 * 4;
     const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
     const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
-    const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
-    const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * (H4 * K + 4) +
-                         (size_t)(2 + kFP) * H4 + (size_t)kFP * K * D * 3 +
-                         (size_t)(a.N * D + 3) / 4 * 4) * 4;
-    const size_t smem_lean = smem + (size_t)kFP * ((a.N + 3) / 4 * 4) * 4 + (size_t)kFP * ((a.N + 15) / 16 * 16);
-    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
+    const bool nss = a.oa != nullptr;
     const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local &&
                       !a.log_w_f && !a.log_w_b;
-    auto kern = lean ? (a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60>
-                                               : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32>)
-                                  : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true>)
-                     : (a.H == 32 && a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false, 32, 60>
-                                               : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>);
+    if (nss && !lean) return fail(APGS_E_BADARG, "gmm_z_fused: the eta statistics ride on the lean label-mode launch only");
+    constexpr bool kNssOk = K * D <= kFLanes;
+    if (nss && !kNssOk) return fail(APGS_E_UNSUPPORTED, "gmm_z_fused: eta statistics need K*D <= %d", kFLanes);
+    const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
+    const int EPB = (nss && kNssOk) ? zf_block_floats<K, D, kFLanes, kNssOk>(H4) : zf_block_floats<K, D, kFLanes, false>(H4);
+    const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * EPB + (size_t)2 * H4 +
+                         (size_t)kFP * K * D * 3 + (size_t)(a.N * D + 3) / 4 * 4) * 4;
+    const size_t smem_lean = smem + (size_t)kFP * ((a.N + 3) / 4 * 4) * 4 + (size_t)kFP * ((a.N + 15) / 16 * 16) +
+                             (nss ? (size_t)a.N * K * EtaTab<K, D>::RS * 4 : 0);
     const size_t smem_used = lean ? smem_lean : smem;
-    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_used), "smem attr");
+    // dynamic + static (mbarrier, s_misc) shared memory against the opt-in limit of one CTA (227 KB on sm_100)
+    if (smem_used + 256 > 200 * 1024) {
+        if (lean && !nss && smem + 256 <= 200 * 1024) {
+            // the lean variant's staging of uniforms / labels does not fit: the generic variant (same numbers) does
+            APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>), smem), "smem attr");
+            const int chunks = (a.S + kFP - 1) / kFP;
+            if (chunks > 65535) return fail(APGS_E_SHAPE, "gmm_z_fused: S=%d too large for one launch", a.S);
+            k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false><<<dim3((unsigned int)a.B, (unsigned int)chunks), kFP * kFLanes, smem, st>>>(a);
+            APGS_LAUNCH_OK("k_gmm_z_fused launch");
+            return 0;
+        }
+        return fail(APGS_E_SHAPE, "gmm_z_fused: N=%d H=%d too large for one tile", a.N, a.H);
+    }
     const int chunks = (a.S + kFP - 1) / kFP;
     if (chunks > 65535) return fail(APGS_E_SHAPE, "gmm_z_fused: S=%d too large for one launch", a.S);
+    if (lean) {
+        if constexpr (kNssOk) {
+            if (nss) return launch_zfused_lean<K, D, true>(a, st, smem_used);
+        }
+        return launch_zfused_lean<K, D, false>(a, st, smem_used);
+    }
+    auto kern = (a.H == 32 && a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false, 32, 60>
+                                        : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, false>);
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_used), "smem attr");
     kern<<<dim3((unsigned int)a.B, (unsigned int)chunks), kFP * kFLanes, smem_used, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_z_fused launch");
     return 0;
@@ -586,7 +697,9 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
                         const float* W2, const float* b2, int64_t H, const apgs_gmm_prior_t* prior, const float* z_old,
                         const unsigned char* z_old_lab, const float* z_forced, const float* uniforms, int64_t S,
                         int64_t B, int64_t N, int64_t K, int64_t D, float* z_new, unsigned char* z_new_lab,
-                        int64_t label_stride, float* q_probs, const apgs_gmm_out_t* out, void* stream) {
+                        int64_t label_stride, float* q_probs, const apgs_gmm_out_t* out, void* stream,
+                        const float* const* heads = nullptr, const apgs_gmm_post_out_t* post_out = nullptr,
+                        float* stats_out = nullptr) {
     if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024)
         return fail(APGS_E_SHAPE, "gmm_z_step_fused: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S, (long long)B,
                     (long long)N, (long long)H);
@@ -603,6 +716,15 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
     if (out) {
         a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;
         a.log_w_b = out->log_w_b; a.lw_local = out->log_w_local; a.lq_local = out->log_q_local;
+    }
+    if (post_out) {
+        if (!heads || !heads[0] || !heads[1] || !heads[2] || !heads[3] || !stats_out || !post_out->alpha || !post_out->beta ||
+            !post_out->mu || !post_out->nu || !prior->alpha || !prior->beta || !prior->mu || !prior->nu)
+            return fail(APGS_E_BADARG, "gmm_z_step_fused: eta statistics need the heads, the Normal-Gamma prior and all outputs");
+        a.Wg = heads[0]; a.bg = heads[1]; a.Wo = heads[2]; a.bo = heads[3];
+        a.ra = prior->alpha; a.rb = prior->beta; a.rm = prior->mu; a.rn = prior->nu;
+        a.oa = post_out->alpha; a.ob = post_out->beta; a.om = post_out->mu; a.on = post_out->nu;
+        a.stats = stats_out;
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 3 && D == 2) return launch_zfused<3, 2>(a, st);
@@ -633,4 +755,22 @@ extern "C" int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau
     if (label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels: label_stride %lld < N", (long long)label_stride);
     return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, nullptr, z_old_labels, nullptr, uniforms, S, B, N, K, D,
                         z_new_onehot, z_new_labels, label_stride, q_probs, out, stream);
+}
+
+extern "C" int apgs_gmm_z_step_fused_labels_eta_f32(const float* x, const float* tau, const float* mu, const float* W1,
+                                                    const float* b1, const float* W2, const float* b2, int64_t H,
+                                                    const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels,
+                                                    const float* uniforms, int64_t S, int64_t B, int64_t N, int64_t K,
+                                                    int64_t D, uint8_t* z_new_labels, int64_t label_stride,
+                                                    const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                                    const apgs_gmm_post_out_t* post_out, float* stats_out,
+                                                    const apgs_gmm_out_t* out, void* stream) {
+    if (!z_new_labels || !z_old_labels || !uniforms) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels_eta: labels in / out and uniforms are required");
+    if (label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels_eta: label_stride %lld < N", (long long)label_stride);
+    if (!post_out || !stats_out) return fail(APGS_E_BADARG, "gmm_z_step_fused_labels_eta: post_out / stats_out is NULL");
+    if (out && (out->log_w_f || out->log_w_b || out->log_w_local || out->log_q_local))
+        return fail(APGS_E_BADARG, "gmm_z_step_fused_labels_eta: only log_w / log_q_f / density are available on this launch");
+    const float* heads[4] = {Wg, bg, Wo, bo};
+    return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, nullptr, z_old_labels, nullptr, uniforms, S, B, N, K, D,
+                        nullptr, z_new_labels, label_stride, nullptr, out, stream, heads, post_out, stats_out);
 }

@@ -179,13 +179,16 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
 
 
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
-                 parts=False, local=False, also_labels=0, want_onehot=True):
+                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
     mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
     z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
     also_labels = row stride (>= N): sample-only call that returns ((z_new one-hot, labels), q_probs, Weights);
     want_onehot=False leaves the one-hot form out (None): the draw then costs ~N bytes per particle instead of 4 K N,
-    and Weights.density / .log_q_f carry log p(x, z | eta) and log q(z) of the draw."""
+    and Weights.density / .log_q_f carry log p(x, z | eta) and log q(z) of the draw.
+    eta_heads = (Wg, bg, Wo, bo) of Enc_apg_eta (label mode only): the same launch also emits the NEXT eta step's inputs
+    for the labels just drawn -- returns (z_new, None, Weights, (alpha, beta, mu_q, nu), stats) with stats the one-hot
+    statistics of z_new centred at `mu` -- bit-identical to eta_posterior_fused(x, z_new, heads, prior, center=mu)."""
     lib = _lib.load()
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -227,6 +230,22 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
         rs, rk = _prior_struct(prior)
         w, o = _outs(S, B, N, dev, parts, local)
         nbytes = S * B * (2 * N + 4 * (N + 2 * K * D + 3 + (N * K if want_q else 0)))
+        if eta_heads is not None:
+            if want_q or parts or local:
+                raise ValueError("the eta statistics ride on the lean launch: no q_probs / parts / per-point outputs")
+            Wg, bg, Wo, bo = [_req(v, "head weight") for v in eta_heads]
+            if tuple(Wg.shape) != (K, D + K) or tuple(Wo.shape) != (D, D + K):
+                raise ValueError("unexpected head weight shapes %s %s" % (tuple(Wg.shape), tuple(Wo.shape)))
+            post = [torch.empty(S, B, K, D, dtype=torch.float32, device=dev) for _ in range(4)]
+            stats = torch.empty(S, B, K, 1 + 2 * D, dtype=torch.float32, device=dev)
+            po = GmmPost(*[v.data_ptr() for v in post])
+            with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes + 4 * S * B * (4 * K * D + K * (1 + 2 * D))):
+                check(lib.apgs_gmm_z_step_fused_labels_eta_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
+                                                               C.byref(rs), ptr(z_old), ptr(uniforms), S, B, N, K, D,
+                                                               ptr(z_new), LN, ptr(Wg), ptr(bg), ptr(Wo), ptr(bo),
+                                                               C.byref(po), ptr(stats), C.byref(o), _stream()),
+                      "apgs_gmm_z_step_fused_labels_eta_f32")
+            return z_new, None, w, tuple(post), stats
         with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes):
             check(lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
                                                        C.byref(rs), ptr(z_old), ptr(uniforms), S, B, N, K, D,

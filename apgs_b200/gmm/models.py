@@ -129,6 +129,10 @@ class Enc_apg_eta(nn.Module):
 
     fused = True
 
+    def head_weights(self):
+        """(Wg, bg, Wo, bo) as the fused kernels take them."""
+        return (self.gamma[0].weight, self.gamma[0].bias, self.ob[0].weight, self.ob[0].bias)
+
     def params(self, ob, z, prior_ng, center=None):
         """posterior parameters (alpha, beta, mu, nu); with `center` (the old mu) the fused kernel's pass over z also
         returns the centred one-hot statistics of z as a fifth tensor (see kernels.logw_eta_stats)."""

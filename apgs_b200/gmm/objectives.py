@@ -98,12 +98,24 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     else:
         log_w, tau, mu, z, trace, _, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags, defer=True)
     tau, mu, z = resample_and_book(tau, mu, z, log_w, log_q)
+    compact = z.dtype == torch.uint8
+    pre = None         # (posterior parameters, centred statistics) of the current z, emitted by the previous z step
     for m in range(num_sweeps - 1):
         if block == 'decomposed':
-            log_w_eta, tau, mu, trace, log_q_f = _update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags, defer=True)
+            log_w_eta, tau, mu, trace, log_q_f = _update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags,
+                                                             defer=True, pre=pre)
             tau, mu, z = resample_and_book(tau, mu, z, log_w_eta, log_q_f)
-            log_w_z, z, trace = apg_update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags)
-            tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_z)
+            # the z step of every sweep but the last also emits the NEXT eta step's posterior parameters and statistics
+            # (functions of the new labels and this particle's mu); they ride through the resampling gather with the
+            # particle, so apg_update_eta needs no pass of its own over the labels
+            emit = compact and fuse_eta_stats and m < num_sweeps - 2 and _can_emit_eta(enc_apg_eta, generative)
+            log_w_z, z, trace, pre = _update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags,
+                                               eta_heads=enc_apg_eta.head_weights() if emit else None)
+            if pre is not None:
+                outs = resampler.resample([tau, mu, z] + list(pre[0]) + [pre[1]], log_w_z)
+                tau, mu, z, pre = outs[0], outs[1], outs[2], (tuple(outs[3:7]), outs[7])
+            else:
+                tau, mu, z = resample_variables(resampler, tau, mu, z, log_weights=log_w_z)
         elif block == 'joint':
             log_w, tau, mu, z, trace, log_q_f = _update_joint(enc_apg_z, enc_apg_eta, generative, x, z, tau, mu, trace,
                                                               result_flags, defer=True)
@@ -126,6 +138,12 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
 
 compact_labels = True          # module switches (tests compare the representations / the two one-shot paths)
 lean_oneshot = True
+fuse_eta_stats = True          # z step emits the next eta step's posterior parameters + statistics (one launch less per sweep)
+
+
+def _can_emit_eta(enc_apg_eta, generative):
+    K, D = generative.prior_pi.numel(), generative_dims(enc_apg_eta)
+    return K * D <= 8
 
 
 def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
@@ -217,11 +235,14 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
     return _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags)[:4]
 
 
-def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False):
+def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False, pre=None):
     if getattr(enc_apg_eta, 'fused', False):
-        # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of
-        *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old)
-        post = tuple(post)
+        if pre is not None:
+            post, stats = pre            # emitted by the z step that drew these labels, centred at its mu == mu_old
+        else:
+            # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of
+            *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old)
+            post = tuple(post)
         # the draw of _sample_eta with its elementwise tail fused into the weight kernel: same variates, same IEEE
         # operations (tau = max(g / beta, tiny), mu = e / sqrt(nu tau) + q_mu), seven launches less per step
         g_std = torch._standard_gamma(post[0])
@@ -243,8 +264,19 @@ def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_fl
 
 def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
     """Given the current samples of eta, update the assignments z (objectives.py:197-227)."""
+    return _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags)[:3]
+
+
+def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None):
+    """apg_update_z; with eta_heads (label mode, evaluation flags) the fused kernel also emits the next eta step's
+    (posterior parameters, statistics) as the 4th value (else None)."""
     need_local = bool(result_flags['loss_required'])
-    if enc_apg_z.can_fuse(result_flags['loss_required']):
+    pre = None
+    if eta_heads is not None and not (result_flags['mode_required'] or need_local):
+        z, q_probs, w, post, stats = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
+                                                          eta_heads=eta_heads)
+        pre = (post, stats)
+    elif enc_apg_z.can_fuse(result_flags['loss_required']):
         # N1: MLP + softmax + draw + weights in one kernel; q_probs only materialised when asked for
         z, q_probs, w = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
                                              want_q=bool(result_flags['mode_required']), local=need_local)
@@ -263,7 +295,7 @@ def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
         trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
     if result_flags['density_required']:
         trace['density'][-1] = trace['density'][-1] + w.density.unsqueeze(0)
-    return w.log_w, z, trace
+    return w.log_w, z, trace, pre
 
 
 def resample_variables(resampler, tau, mu, z, log_weights):

@@ -145,6 +145,9 @@ typedef struct apgs_gmm_prior {       /* HOST struct of DEVICE pointers; apgs/gm
 typedef struct apgs_gmm_post {        /* proposal parameters from G1, (S,B,K,D) each */
     const float *alpha, *beta, *mu, *nu;
 } apgs_gmm_post_t;
+typedef struct apgs_gmm_post_out {    /* the same four tensors as OUTPUTS of a kernel */
+    float *alpha, *beta, *mu, *nu;
+} apgs_gmm_post_out_t;
 typedef struct apgs_gmm_out {         /* every field optional (NULL = not wanted) */
     float *log_w;        /* (S,B)   log importance weight of the step                               */
     float *log_q_f;      /* (S,B)   forward proposal log-density (the loss term)                    */
@@ -256,6 +259,22 @@ APGS_API int apgs_gmm_z_step_fused_labels_f32(const float* x, const float* tau, 
                               int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
                               uint8_t* z_new_labels, int64_t label_stride, float* z_new_onehot,
                               float* q_probs, const apgs_gmm_out_t* out, void* stream);
+/* The label-mode z step that ALSO emits the next eta step's inputs (G3 + W2 + N1 + G1 in one launch): besides z_new_labels
+ *   and out->{log_w, log_q_f, density} it writes, for the labels just drawn, Enc_apg_eta's Normal-Gamma posterior
+ *   parameters (apgs/gmm/models.py:56-66 -> kls_gmm.py:92-119; heads Wg (K,D+K), bg (K), Wo (D,D+K), bo (D); prior->
+ *   alpha/beta/mu/nu) to post_out (S,B,K,D each) and the one-hot statistics of z_new centred at this particle's mu to
+ *   stats_out (S,B,K,1+2D) -- bit-identical to apgs_gmm_eta_posterior_stats_labels_f32(z_new_labels, center = mu).
+ *   They are per-particle functions of (z, mu), so the resampling gather that follows the z step moves them with the
+ *   particle (apgs_gather_ancestors copies rows) and the eta step of the next sweep needs no pass over the labels:
+ *   apgs/gmm/objectives.py:161-166 costs no launch of its own.  K*D <= 8; lean label-mode launch only.               */
+APGS_API int apgs_gmm_z_step_fused_labels_eta_f32(const float* x, const float* tau, const float* mu,
+                              const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
+                              const apgs_gmm_prior_t* prior, const uint8_t* z_old_labels, const float* uniforms,
+                              int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              uint8_t* z_new_labels, int64_t label_stride,
+                              const float* Wg, const float* bg, const float* Wo, const float* bo,
+                              const apgs_gmm_post_out_t* post_out, float* stats_out,
+                              const apgs_gmm_out_t* out, void* stream);
 APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
                                      const float* Wg, const float* bg, const float* Wo, const float* bo,
                                      int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,

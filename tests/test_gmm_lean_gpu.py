@@ -51,6 +51,7 @@ def _close(a, b, rtol=RT, atol=0.0, what=""):
 
 
 def _pad_labels(lab, LN=64):
+    LN = max(LN, (lab.shape[-1] + 15) // 16 * 16)
     out = torch.full(tuple(lab.shape[:2]) + (LN,), 255, dtype=torch.uint8, device=lab.device)
     out[..., :lab.shape[-1]] = lab
     return out
@@ -350,3 +351,106 @@ def test_instance_sharded_kernels_equal_the_full_batch_bit_for_bit(world):
     for k, v in full.items():
         dim = 0 if v.dim() == 1 else 1
         assert torch.equal(torch.cat([p[k] for p in parts], dim), v), k
+
+
+# ------------------------------------------------------------------ z step that emits the next eta step's inputs
+@pytest.mark.parametrize("S,B,N,K,D,H", [(1000, 16, 60, 3, 2, 32), (37, 5, 41, 3, 2, 16), (9, 3, 30, 2, 2, 10), (33, 4, 60, 4, 2, 32),
+                                         (70, 2, 61, 3, 2, 32)])
+def test_z_step_with_eta_statistics_equals_the_separate_kernels(S, B, N, K, D, H):
+    """apgs_gmm_z_step_fused_labels_eta_f32: labels / weights bit-identical to the plain lean launch, and the emitted
+    posterior parameters + centred statistics bit-identical to apgs_gmm_eta_posterior_stats_labels_f32 on those labels
+    (and therefore within the oracle tolerances checked above)."""
+    from apgs_b200.gmm import kernels
+    torch.manual_seed(S + N + K)
+    P = og.make_params(K, D, H)
+    gen = _Gen(K, D)
+    x, tau, mu, lab_old, u = [t.to(DEV) for t in _latents(S, B, K, D, N, seed=S)]
+    LN = (N + 15) // 16 * 16
+    lab_pad = _pad_labels(lab_old, LN)
+    z0, _, w0 = kernels.z_step_fused(x, tau, mu, _mlp(P), gen, z_old=lab_pad, uniforms=u)
+    z1, _, w1, post, stats = kernels.z_step_fused(x, tau, mu, _mlp(P), gen, z_old=lab_pad, uniforms=u, eta_heads=_heads(P))
+    assert torch.equal(z0[..., :N], z1[..., :N])
+    for name in ("log_w", "density", "log_q_f"):
+        assert torch.equal(getattr(w0, name), getattr(w1, name)), name
+    ref = kernels.eta_posterior_fused(x, z1, _heads(P), gen, center=mu)
+    for a, b, name in zip(list(post) + [stats], ref, ("alpha", "beta", "mu", "nu", "stats")):
+        assert tuple(a.shape) == tuple(b.shape) and torch.equal(a, b), name
+    # and against the oracle directly (posterior parameters of Enc_apg_eta on the one-hot form of the new labels)
+    if S <= 100:
+        z = torch.nn.functional.one_hot(z1[..., :N].long().cpu(), K).float()
+        xs = x.cpu().unsqueeze(0).repeat(S, 1, 1, 1)
+        rp = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, z, og.make_prior(K, D))
+        _close(post[0], rp[0], what="alpha vs oracle")
+        _close(post[3], rp[3], what="nu vs oracle")
+
+
+def test_objective_with_fused_eta_statistics_is_bit_identical():
+    """apg_objective (bench flags): the z step emitting the next eta step's inputs (8 launches of k_gmm_nss_im less per
+    10-sweep objective) vs the separate statistics kernel -- same seed, identical traces."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    S, B, sweeps = 1000, 10, 5
+    torch.manual_seed(0)
+    models = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    out = {}
+    for fuse in (True, False):
+        O.fuse_eta_stats = fuse
+        try:
+            torch.manual_seed(5)
+            with torch.no_grad():
+                out[fuse] = O.apg_objective(models, x, BENCH_FLAGS, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
+        finally:
+            O.fuse_eta_stats = True
+    for k in ("ess", "density", "log_z"):
+        assert torch.equal(out[True][k], out[False][k]), k
+
+
+def test_z_step_eta_entry_stays_inside_its_buffers():
+    """raw C-ABI call with every output embedded in guard bands; ragged tile (S not a multiple of 32), padded label rows."""
+    import ctypes as C
+    from apgs_b200 import _lib
+    from apgs_b200._lib import ptr
+    from apgs_b200.gmm.kernels import _prior_struct
+    lib = _lib.load()
+    S, B, N, K, D, H, LN = 37, 5, 60, 3, 2, 32, 64
+    torch.manual_seed(3)
+    P = og.make_params(K, D, H)
+    G = 2048
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=DEV)
+        return buf, buf[G:G + n]
+    x, tau, mu, lab_old, u = [t.to(DEV) for t in _latents(S, B, K, D, N, seed=9)]
+    lab = _pad_labels(lab_old, LN)
+    mlp = [t.contiguous() for t in _mlp(P)]
+    heads = [t.contiguous() for t in _heads(P)]
+    gen = _Gen(K, D)
+    rs, keep = _prior_struct(gen)
+    bufs = {"zl": guarded(S * B * LN, torch.uint8, 0xEE), "stats": guarded(S * B * K * (1 + 2 * D), torch.float32, -7.0)}
+    for name in ("pa", "pb", "pm", "pn"):
+        bufs[name] = guarded(S * B * K * D, torch.float32, -7.0)
+    for name in ("log_w", "log_q_f", "density"):
+        bufs[name] = guarded(S * B, torch.float32, -7.0)
+    o = _lib.GmmOut()
+    for name in ("log_w", "log_q_f", "density"):
+        setattr(o, name, bufs[name][1].data_ptr())
+    po = _lib.GmmPost(*[bufs[n][1].data_ptr() for n in ("pa", "pb", "pm", "pn")])
+    rc = lib.apgs_gmm_z_step_fused_labels_eta_f32(ptr(x), ptr(tau), ptr(mu), *[ptr(m) for m in mlp], H, C.byref(rs), ptr(lab), ptr(u),
+                                                  S, B, N, K, D, ptr(bufs["zl"][1]), LN, *[ptr(h) for h in heads],
+                                                  C.byref(po), ptr(bufs["stats"][1]), C.byref(o), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.apgs_last_error()
+    torch.cuda.synchronize()
+    for name, (buf, view) in bufs.items():
+        fill = 0xEE if buf.dtype == torch.uint8 else -7.0
+        assert bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all()), name
+    zl = bufs["zl"][1].view(S, B, LN)
+    assert bool((zl[..., :N] < K).all()) and bool((zl[..., N:] == 0xEE).all())            # pad bytes are never written
+    for name in ("pa", "pb", "pm", "pn", "stats", "log_w", "density"):
+        assert bool(torch.isfinite(bufs[name][1]).all()) and not bool((bufs[name][1] == -7.0).any()), name
+    # error paths: missing outputs / unsupported extras
+    rc = lib.apgs_gmm_z_step_fused_labels_eta_f32(ptr(x), ptr(tau), ptr(mu), *[ptr(m) for m in mlp], H, C.byref(rs), ptr(lab), ptr(u),
+                                                  S, B, N, K, D, ptr(bufs["zl"][1]), LN, *[ptr(h) for h in heads],
+                                                  None, ptr(bufs["stats"][1]), C.byref(o), torch.cuda.current_stream().cuda_stream)
+    assert rc != 0
