@@ -138,7 +138,11 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
 
 compact_labels = True          # module switches (tests compare the representations / the two one-shot paths)
 lean_oneshot = True
-fuse_eta_stats = True          # z step emits the next eta step's posterior parameters + statistics (one launch less per sweep)
+# z step emits the next eta step's posterior parameters + statistics (apgs_gmm_z_step_fused_labels_eta_f32; one launch
+# less per sweep, bit-identical traces).  Measured on B200 at S=1000, B=1024 (profiles/r2_fused_eta_stats.md): the
+# statistics are ~1000 instructions per thread wherever they run, so the z step grows by 0.25 ms against 0.32 ms for the
+# standalone kernel, and the 156 extra bytes per particle cost the gather 0.07 ms -- no net gain, hence off by default.
+fuse_eta_stats = False
 
 
 def _can_emit_eta(enc_apg_eta, generative):

@@ -394,7 +394,7 @@ def test_objective_with_fused_eta_statistics_is_bit_identical():
     models = _models_from_params(og.make_params())
     torch.manual_seed(1)
     x = og.simulate(B).to(DEV)
-    out = {}
+    out, default = {}, O.fuse_eta_stats
     for fuse in (True, False):
         O.fuse_eta_stats = fuse
         try:
@@ -402,7 +402,7 @@ def test_objective_with_fused_eta_statistics_is_bit_identical():
             with torch.no_grad():
                 out[fuse] = O.apg_objective(models, x, BENCH_FLAGS, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
         finally:
-            O.fuse_eta_stats = True
+            O.fuse_eta_stats = default
     for k in ("ess", "density", "log_z"):
         assert torch.equal(out[True][k], out[False][k]), k
 
