@@ -58,6 +58,8 @@ _DPR, _DOUT, _DMLP = C.POINTER(DmmPrior), C.POINTER(DmmOut), C.POINTER(DmmMlp)
 SIGNATURES = {
     "apgs_version": (_int, []),
     "apgs_last_error": (C.c_char_p, []),
+    "apgs_gmm_supported": (_int, [_i64, _i64]),
+    "apgs_dmm_supported": (_int, [_i64, _i64]),
     "apgs_weight_stats_f32": (_int, [_p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "apgs_local_weight_stats_f32": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "apgs_ancestors_workspace_bytes": (_sz, [_i64, _i64]),

@@ -413,6 +413,13 @@ extern "C" int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
                 (long long)D);
 }
 
+// bit 0: the fused local encoder is compiled for (K, D); bit 1: the decoder kernel for D.  The weight / pooling kernels
+// of dmm.cu take K and D at run time.
+extern "C" int apgs_dmm_supported(int64_t K, int64_t D) {
+    const bool loc = (D == 2 && K >= 2 && K <= 6) || (D == 3 && (K == 3 || K == 4));
+    return (loc ? 1 : 0) | ((D == 2 || D == 3) ? 2 : 0);
+}
+
 extern "C" int apgs_dmm_decoder_hidden2_f32(const float* beta, const apgs_dmm_mlp_t* net, int64_t H, int64_t D,
                                             int64_t M, float* hidden2, void* stream) {
     if (M <= 0 || H <= 0 || H > 4096 || D <= 0) return fail(APGS_E_SHAPE, "dmm_decoder_hidden2: bad sizes");

@@ -754,6 +754,15 @@ static int launch_weights(const GmmWArgs& a, cudaStream_t st) {
 
 using namespace apgs;
 
+// which kernel families are compiled for (K, D): bit 0 the reweighting / posterior kernels of this file (G1-G4),
+// bit 1 the fused z step (gmm_fused.cu), bit 2 the fused eta heads (+ statistics), bit 3 their label mode (K D <= 8 lanes)
+extern "C" int apgs_gmm_supported(int64_t K, int64_t D) {
+    const bool base = (K == 3 && D == 2) || (K == 2 && D == 2) || (K == 4 && D == 2) || (K == 5 && D == 2) ||
+                      (K == 3 && D == 3) || (K == 4 && D == 3) || (K == 3 && D == 1);
+    const bool zf = (K == 3 && D == 2) || (K == 2 && D == 2) || (K == 4 && D == 2) || (K == 5 && D == 2) || (K == 3 && D == 3);
+    return (base ? 1 : 0) | (zf ? 2 : 0) | (base ? 4 : 0) | ((base && K * D <= apgs::kLanes) ? 8 : 0);
+}
+
 static int check_gmm_dims(int64_t S, int64_t B, int64_t N, int64_t K, int64_t D, const char* who) {
     if (S <= 0 || B <= 0 || N <= 0) return fail(APGS_E_SHAPE, "%s: S=%lld B=%lld N=%lld must be positive", who,
                                                 (long long)S, (long long)B, (long long)N);

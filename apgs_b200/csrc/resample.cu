@@ -525,6 +525,52 @@ __global__ void __launch_bounds__(256) k_local_softmax(const float* __restrict__
     for (long long s = 0; s < S; ++s) w[s * C + c] = __fdiv_rn(expf(__ldg(lwl + s * C + c) - m), sum);
 }
 
+// Single-pass tile variant: a CTA owns TC adjacent columns and ALL S rows of them in shared memory -- one read and one
+// write of the (S,B,N) tensor instead of three reads and one write.  256 threads = 16 row groups x 16 columns: a warp
+// reads two 64-byte row segments per step (full sectors), the column maxima / sums of the 16 row groups meet in shared
+// memory, exp is evaluated once per element (kept in the tile) and normalised with the same IEEE division.
+constexpr int kLsTC = 16, kLsRG = 16;
+
+__global__ void __launch_bounds__(kLsTC* kLsRG) k_local_softmax_tile(const float* __restrict__ lwl, int S, long long C,
+                                                                     float* __restrict__ w) {
+    extern __shared__ __align__(16) float s_tile[];                 // [S][TC]
+    __shared__ float s_red[kLsRG][kLsTC + 1];
+    const int c = threadIdx.x % kLsTC, rg = threadIdx.x / kLsTC;
+    const long long col = (long long)blockIdx.x * kLsTC + c;
+    const bool live = col < C;
+    float m = -INFINITY;
+    if (live) {
+#pragma unroll 8
+        for (int s = rg; s < S; s += kLsRG) {
+            const float v = __ldg(lwl + (long long)s * C + col);
+            s_tile[s * kLsTC + c] = v;
+            m = fmaxf(m, v);
+        }
+    }
+    s_red[rg][c] = m;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kLsRG; ++i) m = fmaxf(m, s_red[i][c]);
+    __syncthreads();
+    float sum = 0.f;
+    if (live) {
+        for (int s = rg; s < S; s += kLsRG) {
+            const float e = expf(s_tile[s * kLsTC + c] - m);
+            s_tile[s * kLsTC + c] = e;
+            sum += e;
+        }
+    }
+    s_red[rg][c] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLsRG; ++i) sum += s_red[i][c];
+    if (live) {
+#pragma unroll 8
+        for (int s = rg; s < S; s += kLsRG) __stcs(w + (long long)s * C + col, __fdiv_rn(s_tile[s * kLsTC + c], sum));
+    }
+}
+
 }  // namespace apgs
 
 using namespace apgs;
@@ -627,10 +673,20 @@ extern "C" int apgs_local_weight_stats_f32(const float* log_w_local, int64_t S, 
     }
     if (w_local_out != nullptr) {
         long long C = (long long)B * N;
-        long long blocks = (C + 255) / 256;
-        if (blocks >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: too many columns");
-        k_local_softmax<<<(unsigned int)blocks, 256, 0, st>>>(log_w_local, S, C, w_local_out);
-        APGS_LAUNCH_OK("k_local_softmax launch");
+        const size_t tile = (size_t)S * kLsTC * sizeof(float);
+        if (tile <= kSmemTileBudget) {
+            long long blocks = (C + kLsTC - 1) / kLsTC;
+            if (blocks >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: too many columns");
+            APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_local_softmax_tile), tile), "smem attr");
+            k_local_softmax_tile<<<(unsigned int)blocks, kLsTC * kLsRG, tile, st>>>(log_w_local, (int)S, C, w_local_out);
+            APGS_LAUNCH_OK("k_local_softmax_tile launch");
+        } else {
+            // S beyond a shared-memory tile: three passes over global memory
+            long long blocks = (C + 255) / 256;
+            if (blocks >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: too many columns");
+            k_local_softmax<<<(unsigned int)blocks, 256, 0, st>>>(log_w_local, S, C, w_local_out);
+            APGS_LAUNCH_OK("k_local_softmax launch");
+        }
     }
     return 0;
 }

@@ -8,6 +8,17 @@ from .._lib import DmmMlp, DmmOut, DmmPrior, check, ptr
 from ..ops import _call, _req, _stream
 
 
+_SUPPORTED = {}
+
+
+def supported(K, D):
+    """apgs_dmm_supported: bit 0 the fused local encoder is compiled for (K, D), bit 1 the decoder kernel for D."""
+    key = (int(K), int(D))
+    if key not in _SUPPORTED:
+        _SUPPORTED[key] = int(_lib.load().apgs_dmm_supported(key[0], key[1]))
+    return _SUPPORTED[key]
+
+
 def _x3(x):
     if x.dim() == 4:
         x = x[0]

@@ -81,7 +81,10 @@ class Enc_rws_mu(_EncMu):
         return q_mu.expand(S, -1, -1, -1), q_sigma.expand(S, -1, -1, -1)
 
     def forward(self, ob, K, priors, sampled=True, mu_old=None, EPS=1e-8):
-        return self._trace(*self.params(ob, K, priors), sampled, mu_old)
+        # the reference's forward() is differentiable: with parameters that take part in autograd the Trace is built
+        # from the PyTorch-ops parameters (q['means'].log_prob then carries the graph a custom loss needs)
+        par = self.params_torch(ob, K, priors) if needs_grad(self) else self.params(ob, K, priors)
+        return self._trace(*par, sampled, mu_old)
 
 
 class Enc_apg_mu(_EncMu):
@@ -122,12 +125,15 @@ class Enc_apg_mu(_EncMu):
         return self._heads_torch(self.nss1[2](h1), F.softmax(self.nss2[2](h2), -1), priors)
 
     def forward(self, ob, z, beta, K, priors, sampled=True, mu_old=None, EPS=1e-8):
-        return self._trace(*self.params(ob, z, beta, K, priors), sampled, mu_old)
+        # differentiable like the reference's forward() when the parameters take part in autograd (see Enc_rws_mu)
+        par = self.params_torch(ob, z, beta, K, priors) if needs_grad(self) else self.params(ob, z, beta, K, priors)
+        return self._trace(*par, sampled, mu_old)
 
 
 class Enc_apg_local(nn.Module):
     def __init__(self, K, D, num_hidden):
         super(self.__class__, self).__init__()
+        self.K = K
         self.pi_log_prob = nn.Sequential(nn.Linear(D, num_hidden), nn.ReLU(), nn.Linear(num_hidden, 1))
         self.angle_log_con1 = nn.Sequential(nn.Linear(D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, 1))
         self.angle_log_con0 = nn.Sequential(nn.Linear(D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, 1))
@@ -135,7 +141,11 @@ class Enc_apg_local(nn.Module):
     fused = True          # evaluation path: csrc/dmm_fused.cu
 
     def can_fuse(self):
-        return self.fused
+        """the fused kernel is compiled for a fixed list of (K, D) (apgs_dmm_supported); other shapes use probs() / cons()"""
+        if not self.fused:
+            return False
+        K, D = getattr(self, 'K', None), self.pi_log_prob[0].weight.shape[1]
+        return K is None or bool(kernels.supported(K, D) & 1)
 
     def sample_fused(self, ob, mu, z_old=None, uniforms=None, z_forced=None):
         """probs + categorical draw + Beta concentrations (for z and, when given, for z_old) in one kernel:
@@ -192,7 +202,7 @@ class Decoder(nn.Module):
 
     def hidden2(self, beta):
         """unit-normalised decoder output (models.py:202-203)."""
-        if self.fused and beta.is_cuda:
+        if self.fused and beta.is_cuda and kernels.supported(2, self.recon_mu[2].weight.shape[0]) & 2:
             return kernels.decoder_hidden2(beta, self.recon_mu)      # forward values; the graph: log_likelihood_torch()
         return self.hidden2_torch(beta)
 

@@ -6,6 +6,26 @@ import torch
 from .. import _lib
 from .._lib import GmmOut, GmmPost, GmmPrior, check, ptr
 from ..ops import _call, _req, _stream
+from . import torch_path
+
+BASE, ZFUSED, ETA_FUSED, LABELS = 1, 2, 4, 8
+_SUPPORTED = {}
+
+
+def supported(K, D):
+    """bit mask of the kernel families compiled for (K, D) (apgs_gmm_supported): BASE = G1-G4, ZFUSED = the fused z step,
+    ETA_FUSED = the fused eta heads, LABELS = the label-mode entries.  Shapes without BASE run through stock PyTorch
+    CUDA ops (torch_path.py) instead of failing -- the reference accepts any --num_clusters / data dimension."""
+    key = (int(K), int(D))
+    if key not in _SUPPORTED:
+        _SUPPORTED[key] = int(_lib.load().apgs_gmm_supported(key[0], key[1]))
+    return _SUPPORTED[key]
+
+
+def _cuda_only(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.ApgsError("apgs_b200 has no CPU fallback: tensors must be CUDA tensors")
 
 
 def _prior_struct(prior):
@@ -34,6 +54,8 @@ def nss_posterior(xp, gamma, prior):
     xp, gamma = _req(xp, "xp", ndim=4), _req(gamma, "gamma", ndim=4)
     S, B, N, D = xp.shape
     K = gamma.shape[-1]
+    if not supported(K, D) & BASE:
+        return torch_path.nss_posterior(xp, gamma, prior)
     if tuple(gamma.shape[:3]) != (S, B, N):
         raise ValueError("xp %s and gamma %s disagree" % (tuple(xp.shape), tuple(gamma.shape)))
     pr = [_req(getattr(prior, "prior_" + n), "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
@@ -67,6 +89,10 @@ def _outs(S, B, N, dev, parts, local):
 
 def logw_oneshot(x, post, prior, tau, mu, q_probs, z, parts=False):
     """G4a: oneshot weights (apgs/gmm/objectives.py:74-110)."""
+    if not supported(tau.shape[-2], tau.shape[-1]) & BASE:
+        _cuda_only(x, tau, mu, z)
+        with torch.no_grad():
+            return torch_path.logw_oneshot(x, post, prior, tau, mu, q_probs, z, parts)
     lib = _lib.load()
     x = _x3(x)
     z, q_probs, tau, mu = _req(z, "z", ndim=4), _req(q_probs, "q_probs", ndim=4), _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -83,6 +109,10 @@ def logw_oneshot(x, post, prior, tau, mu, q_probs, z, parts=False):
 
 def logw_eta(x, z, post, prior, tau, mu, tau_old, mu_old, parts=False):
     """G2: eta-step weights (apgs/gmm/objectives.py:161-195)."""
+    if not supported(tau.shape[-2], tau.shape[-1]) & BASE:
+        _cuda_only(x, tau, mu, z)
+        with torch.no_grad():
+            return torch_path.logw_eta(x, z, post, prior, tau, mu, tau_old, mu_old, parts)
     lib = _lib.load()
     x = _x3(x)
     z = _req(z, "z", ndim=4)
@@ -146,6 +176,10 @@ def draw_logw_eta_stats(stats, center, post, prior, gamma_std, normal_std, tau_o
 
 def logw_z(x, tau, mu, q_probs, prior, z, z_old, parts=False, local=False):
     """G3 (+W2): z-step weights (apgs/gmm/objectives.py:197-227)."""
+    if not supported(tau.shape[-2], tau.shape[-1]) & BASE:
+        _cuda_only(x, tau, mu, z)
+        with torch.no_grad():
+            return torch_path.logw_z(x, tau, mu, q_probs, prior, z, z_old, parts, local)
     lib = _lib.load()
     x = _x3(x)
     z, z_old, q_probs = _req(z, "z", ndim=4), _req(z_old, "z_old", ndim=4), _req(q_probs, "q_probs", ndim=4)
@@ -162,6 +196,10 @@ def logw_z(x, tau, mu, q_probs, prior, z, z_old, parts=False, local=False):
 
 def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, parts=False):
     """G4b: joint-step weights (apgs/gmm/objectives.py:112-158)."""
+    if not supported(tau.shape[-2], tau.shape[-1]) & BASE:
+        _cuda_only(x, tau, mu, z)
+        with torch.no_grad():
+            return torch_path.logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, parts)
     lib = _lib.load()
     x = _x3(x)
     z, z_old, q_probs = _req(z, "z", ndim=4), _req(z_old, "z_old", ndim=4), _req(q_probs, "q_probs", ndim=4)

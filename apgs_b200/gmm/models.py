@@ -89,7 +89,7 @@ class Enc_rws_eta(nn.Module):
         x = _x_inst(ob)
         S = ob.shape[0] if ob.dim() == 4 else S
         # the heads depend on the data only: evaluate once per instance, not once per particle
-        if self.fused:
+        if self.fused and kernels.supported(self.gamma[0].weight.shape[0], x.shape[-1]) & kernels.ETA_FUSED:
             post = kernels.eta_posterior_fused(x, None, (self.gamma[0].weight, self.gamma[0].bias,
                                                          self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng))
         else:
@@ -105,7 +105,11 @@ class Enc_rws_eta(nn.Module):
         return tuple(v.expand(S, -1, -1, -1) for v in post)
 
     def forward(self, ob, prior_ng, sampled=True, tau_old=None, mu_old=None):
-        return _eta_trace(self.params(ob, prior_ng), sampled, tau_old, mu_old)
+        # the reference's forward() is differentiable: when the parameters take part in autograd the Trace is built from
+        # the PyTorch-ops parameters, so q['means'].log_prob / q['precisions'].log_prob carry the graph a custom loss or
+        # the reference's own objectives.py need; otherwise (evaluation) from the kernel
+        post = self.params_torch(ob, prior_ng) if needs_grad(self) else self.params(ob, prior_ng)
+        return _eta_trace(post, sampled, tau_old, mu_old)
 
 
 class Enc_apg_eta(nn.Module):
@@ -129,6 +133,11 @@ class Enc_apg_eta(nn.Module):
 
     fused = True
 
+    def can_fuse(self):
+        """the fused heads + statistics kernels are compiled for a fixed list of (K, D) (kernels.supported)."""
+        K, D = self.gamma[0].weight.shape[0], self.ob[0].weight.shape[0]
+        return bool(self.fused and kernels.supported(K, D) & kernels.ETA_FUSED)
+
     def head_weights(self):
         """(Wg, bg, Wo, bo) as the fused kernels take them."""
         return (self.gamma[0].weight, self.gamma[0].bias, self.ob[0].weight, self.ob[0].bias)
@@ -136,7 +145,7 @@ class Enc_apg_eta(nn.Module):
     def params(self, ob, z, prior_ng, center=None):
         """posterior parameters (alpha, beta, mu, nu); with `center` (the old mu) the fused kernel's pass over z also
         returns the centred one-hot statistics of z as a fifth tensor (see kernels.logw_eta_stats)."""
-        if self.fused:
+        if self.can_fuse():
             return kernels.eta_posterior_fused(ob, z, (self.gamma[0].weight, self.gamma[0].bias,
                                                        self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng),
                                                center=center)
@@ -149,7 +158,9 @@ class Enc_apg_eta(nn.Module):
         return posterior_eta_torch(xp, gam, prior_ng)
 
     def forward(self, ob, z, prior_ng, sampled=True, tau_old=None, mu_old=None):
-        return _eta_trace(self.params(ob, z, prior_ng), sampled, tau_old, mu_old)
+        # differentiable like the reference's forward() when the parameters take part in autograd (see Enc_rws_eta)
+        post = self.params_torch(ob, z, prior_ng) if needs_grad(self) else self.params(ob, z, prior_ng)
+        return _eta_trace(post, sampled, tau_old, mu_old)
 
 
 class Enc_apg_z(nn.Module):
@@ -159,6 +170,7 @@ class Enc_apg_z(nn.Module):
 
     def __init__(self, K, D, num_hidden):
         super(self.__class__, self).__init__()
+        self.K = K
         self.pi_log_prob = nn.Sequential(nn.Linear(3 * D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, 1))
 
     def probs(self, ob, tau, mu):
@@ -187,6 +199,9 @@ class Enc_apg_z(nn.Module):
         """the fused kernel is forward-only: use it unless gradients w.r.t. the MLP are needed."""
         if not self.fused:
             return False
+        D = self.pi_log_prob[0].weight.shape[1] // 3
+        if self.K is not None and not kernels.supported(self.K, D) & kernels.ZFUSED:
+            return False                # (K, D) outside the compiled list: PyTorch MLP + the un-fused weight path
         return not (need_grad and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
 
     def sample_fused(self, ob, tau, mu, generative, want_q=True, label_stride=0):

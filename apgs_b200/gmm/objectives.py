@@ -153,7 +153,12 @@ def _can_emit_eta(enc_apg_eta, generative):
 def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
     K, D = generative.prior_pi.numel(), generative_dims(enc_apg_eta)
     return (compact_labels and block == 'decomposed' and not result_flags['loss_required']
-            and enc_apg_z.can_fuse(False) and getattr(enc_apg_eta, 'fused', False) and K <= 255 and K * D <= 8)
+            and enc_apg_z.can_fuse(False) and _eta_fused(enc_apg_eta) and K <= 255
+            and kernels.supported(K, D) & kernels.LABELS)
+
+
+def _eta_fused(enc_apg_eta):
+    return enc_apg_eta.can_fuse() if hasattr(enc_apg_eta, 'can_fuse') else bool(getattr(enc_apg_eta, 'fused', False))
 
 
 def generative_dims(enc_apg_eta):
@@ -240,7 +245,7 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
 
 
 def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False, pre=None):
-    if getattr(enc_apg_eta, 'fused', False):
+    if _eta_fused(enc_apg_eta):
         if pre is not None:
             post, stats = pre            # emitted by the z step that drew these labels, centred at its mu == mu_old
         else:

@@ -119,7 +119,7 @@ def local_weight_stats(log_w_local, want_w=True, want_sum=True):
 
 
 # ------------------------------------------------------------------------------------- R2 / R3
-def _uniform_args(strategy, uniforms, S, B):
+def _uniform_args(strategy, uniforms, S, B, layout=None):
     if strategy == "systematic":
         u = _req(uniforms, "uniforms", torch.float32)
         if u.numel() != B:
@@ -131,16 +131,23 @@ def _uniform_args(strategy, uniforms, S, B):
         if uniforms.dtype != torch.float64:
             raise TypeError("multinomial resampling takes float64 uniforms")
         u = uniforms.detach()
-        if tuple(u.shape) == (S, B):
+        if layout not in (None, "sb", "bs"):
+            raise ValueError("uniform_layout must be 'sb', 'bs' or None")
+        if layout is None:
+            if S == B and tuple(u.shape) == (S, B):
+                raise ValueError("multinomial uniforms of shape (%d,%d) are ambiguous when S == B: pass uniform_layout='sb' "
+                                 "((S,B)) or 'bs' ((B,S), the reference's generator order)" % (S, B))
+            layout = "sb" if tuple(u.shape) == (S, B) else "bs"
+        if layout == "sb" and tuple(u.shape) == (S, B):
             return u, u.stride(0), u.stride(1)
-        if tuple(u.shape) == (B, S):       # the reference's generator order
+        if layout == "bs" and tuple(u.shape) == (B, S):       # torch.rand(B, S): the reference's generator order
             return u, u.stride(1), u.stride(0)
-        raise ValueError("multinomial uniforms must be (S,B) or (B,S), got %s" % (tuple(u.shape),))
+        raise ValueError("multinomial uniforms must be (S,B) ['sb'] or (B,S) ['bs'], got %s with layout %r" % (tuple(u.shape), layout))
     raise ValueError("unknown resampling strategy %r" % (strategy,))
 
 
 def sample_ancestors(log_w=None, w_norm=None, strategy="systematic", uniforms=None,
-                     cdf_mode=_lib.CDF_AUTO, index_dtype=torch.int64, want_stats=False, want_w=True):
+                     cdf_mode=_lib.CDF_AUTO, index_dtype=torch.int64, want_stats=False, want_w=True, uniform_layout=None):
     """Ancestor indices (S,B) from log-weights (or already-normalised weights) and explicit
     uniforms.  Returns anc or (anc, w, ess, lse) when want_stats (log_w input only; w is None unless want_w):
     the softmax the ancestor kernel computes anyway IS the W1 normalisation, so a caller that needs ESS / lse of the
@@ -151,7 +158,7 @@ def sample_ancestors(log_w=None, w_norm=None, strategy="systematic", uniforms=No
         raise ValueError("give exactly one of log_w / w_norm")
     src = _req(src, "weights", ndim=2)
     S, B = src.shape
-    u, us, ub = _uniform_args(strategy, uniforms, S, B)
+    u, us, ub = _uniform_args(strategy, uniforms, S, B, uniform_layout)
     dev = src.device
     anc = torch.empty(S, B, dtype=index_dtype, device=dev)
     a64 = anc if index_dtype == torch.int64 else None
@@ -213,7 +220,7 @@ def gather_ancestors(latents, anc):
 
 # ------------------------------------------------------------------------------------------ R5
 def resample(latents, log_w=None, w_norm=None, strategy="systematic", uniforms=None,
-             cdf_mode=_lib.CDF_AUTO, want_index=False, want_stats=False, want_w=True):
+             cdf_mode=_lib.CDF_AUTO, want_index=False, want_stats=False, want_w=True, uniform_layout=None):
     """Fused resample: ancestors (int32, in workspace) + gather of every latent.
     Returns (outs, anc64 or None, (w, ess, lse) or None); w is None unless want_w."""
     lib = _lib.load()
@@ -223,7 +230,7 @@ def resample(latents, log_w=None, w_norm=None, strategy="systematic", uniforms=N
     src = _req(src, "weights", ndim=2)
     S, B = src.shape
     dev = src.device
-    u, us, ub = _uniform_args(strategy, uniforms, S, B)
+    u, us, ub = _uniform_args(strategy, uniforms, S, B, uniform_layout)
     latents = list(latents)
     arr, srcs, outs = _latent_array(latents, S, B)
     anc64 = torch.empty(S, B, dtype=torch.int64, device=dev) if want_index else None

@@ -551,7 +551,8 @@ def microbench(cx, peak):
             for strat in ("systematic", "multinomial"):
                 r = Resampler(strat, S, True, dev)
                 u = r.draw_uniforms(S, B, dev)
-                fn = lambda: ops.resample(lat, log_w=lw, strategy=strat, uniforms=u)      # noqa: E731
+                lay = "bs" if strat == "multinomial" else None          # draw_uniforms: (B,S), the reference's generator order
+                fn = lambda: ops.resample(lat, log_w=lw, strategy=strat, uniforms=u, uniform_layout=lay)      # noqa: E731
                 cx.barrier()
                 t = torch.tensor([_median_ms(fn, flush, iters=7, warm=2)], dtype=torch.float64, device=dev)
                 if world > 1:

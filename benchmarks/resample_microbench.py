@@ -46,10 +46,12 @@ def run_case(S, B, inners, strategy, sigma, flush, iters=20):
     lat = [torch.randn(S, B, max(1, n // 4), device=dev) for n in inners]
     r = Resampler(strategy, S, True, dev)
     u = r.draw_uniforms(S, B, dev)
-    anc = ops.sample_ancestors(log_w=lw, strategy=strategy, uniforms=u, index_dtype=torch.int32)
-    t_idx = timed(lambda: ops.sample_ancestors(log_w=lw, strategy=strategy, uniforms=u, index_dtype=torch.int32), iters, flush=flush)
+    lay = "bs" if strategy == "multinomial" else None           # draw_uniforms: (B,S), the reference's generator order
+    anc = ops.sample_ancestors(log_w=lw, strategy=strategy, uniforms=u, index_dtype=torch.int32, uniform_layout=lay)
+    t_idx = timed(lambda: ops.sample_ancestors(log_w=lw, strategy=strategy, uniforms=u, index_dtype=torch.int32,
+                                               uniform_layout=lay), iters, flush=flush)
     t_gat = timed(lambda: ops.gather_ancestors(lat, anc), iters, flush=flush)
-    t_all = timed(lambda: ops.resample(lat, log_w=lw, strategy=strategy, uniforms=u), iters, flush=flush)
+    t_all = timed(lambda: ops.resample(lat, log_w=lw, strategy=strategy, uniforms=u, uniform_layout=lay), iters, flush=flush)
     P = S * B
     bytes_g = P * (4 + 2 * sum(inners))
     bytes_all = P * (4 + 2 * sum(inners))

@@ -138,6 +138,15 @@ APGS_API int apgs_gmm_nss_posterior_f32(const float* xp, const float* gamma,
                                float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
                                void* stream);
 
+/* Which (K clusters, D data dims) the templated GMM kernels are compiled for.  Bit 0: G1-G4 (nss_posterior, logw_*);
+ * bit 1: the fused z step (apgs_gmm_z_step_fused*); bit 2: the fused eta heads (apgs_gmm_eta_posterior_*); bit 3: the
+ * label-mode entries (*_labels_*, K*D <= 8).
+ * Entry points called with other shapes return APGS_E_UNSUPPORTED; the Python host side consults this and routes such
+ * shapes through stock PyTorch CUDA ops (apgs_b200/gmm/torch_path.py).  apgs_dmm_supported: bit 0 the fused local
+ * encoder, bit 1 the decoder kernel (the other DMM kernels take K, D at run time).                                   */
+APGS_API int apgs_gmm_supported(int64_t K, int64_t D);
+APGS_API int apgs_dmm_supported(int64_t K, int64_t D);
+
 typedef struct apgs_gmm_prior {       /* HOST struct of DEVICE pointers; apgs/gmm/models.py:124-128 */
     const float *alpha, *beta, *mu, *nu;   /* (K,D) each */
     const float *pi;                       /* (K)        */

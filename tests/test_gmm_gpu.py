@@ -832,3 +832,69 @@ def test_gmm_label_kernels_stay_inside_their_buffers():
     assert bool((zl[..., :N] < K).all()) and bool((zl[..., N:] == 0xEE).all())            # pad bytes are never written
     for name in ("q", "log_w", "density", "pa", "pb", "pm", "pn", "stats", "log_w_local"):
         assert bool(torch.isfinite(bufs[name][1]).all()) and not bool((bufs[name][1] == -7.0).all()), name
+
+
+# ------------------------------------------------------------------ shapes outside the compiled (K, D) list
+@pytest.mark.parametrize("K,D", [(6, 2), (3, 4), (7, 3)])
+def test_unsupported_cluster_shapes_run_through_the_generic_path(K, D):
+    """the reference accepts any --num_clusters / data dimension; kernels are compiled for a fixed list (apgs_gmm_supported).
+    Other shapes must run (stock PyTorch CUDA ops, gmm/torch_path.py) and agree with the oracle -- not raise UNSUPPORTED."""
+    from apgs_b200.gmm import kernels, objectives as O
+    from apgs_b200.resampler import Resampler
+    assert kernels.supported(3, 2) & kernels.BASE and kernels.supported(3, 2) & kernels.ZFUSED
+    assert not kernels.supported(K, D) & kernels.BASE
+    S, B, N, H = 8, 5, 30, 16
+    torch.manual_seed(K + D)
+    P, prior = og.make_params(K, D, H), og.make_prior(K, D)
+    x = og.simulate(B, N, K, D)
+    xs = x.repeat(S, 1, 1, 1)
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    z_old = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N)), K).float()
+    post = og.enc_apg_eta_posterior(P["enc_apg_eta"], xs, z, prior)
+    tau, mu = torch.rand(S, B, K, D) + 0.5, torch.randn(S, B, K, D)
+    tau_old, mu_old = torch.rand(S, B, K, D) + 0.5, torch.randn(S, B, K, D)
+    gen = _Gen(K, D)
+    ref = og.eta_step_weights(xs, z, post, prior, tau, mu, tau_old, mu_old, parts=True)
+    w = kernels.logw_eta(x.to(DEV), z.to(DEV), _dev(*post), gen, *_dev(tau, mu, tau_old, mu_old), parts=True)
+    _close(w.log_w_f, ref[4], rtol=2e-5, atol=1e-3, what="generic eta log_w_f")
+    _close(w.log_w, ref[0], rtol=0, atol=2e-5 * (ref[4].abs() + ref[5].abs()) + 1e-3, what="generic eta log_w")
+    q = og.enc_apg_z_probs(P["enc_apg_z"], xs, tau, mu)
+    refz = og.z_step_weights(xs, tau, mu, q, prior, z, z_old, parts=True)
+    wz = kernels.logw_z(x.to(DEV), *_dev(tau, mu, q), gen, *_dev(z, z_old), parts=True, local=True)
+    _close(wz.log_w_local, refz[0], rtol=2e-5, atol=1e-4, what="generic z log_w_local")
+    _close(wz.log_w, refz[1], rtol=0, atol=2e-5 * (refz[4].abs() + refz[5].abs()) + 1e-3, what="generic z log_w")
+    pk = kernels.nss_posterior(*_dev(*og.enc_eta_heads(P["enc_apg_eta"], torch.cat((xs, z), -1))), gen)
+    for a, b, name in zip(pk, post, ("alpha", "beta", "mu", "nu")):
+        _close(a, b, rtol=1e-4, atol=1e-4, what="generic posterior " + name)
+    # and the whole objective, both blocks
+    models = _models_from_params(P, K, D, H)
+    assert not models[1].can_fuse() and not models[2].can_fuse()
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    for block in ("decomposed", "joint"):
+        with torch.no_grad():
+            tr = O.apg_objective(models, x.to(DEV), flags, 3, block, Resampler("systematic", S, True, DEV))
+        assert tuple(tr["ess"].shape) == (3, B) and bool(torch.isfinite(tr["density"]).all()) and bool(torch.isfinite(tr["loss"]).all())
+    with pytest.raises(Exception):
+        kernels.logw_eta(x, z, post, gen, tau, mu, tau_old, mu_old)          # CPU tensors are still rejected
+
+
+def test_encoder_forward_is_differentiable_like_the_reference():
+    """Enc_*_eta.forward() builds its Trace from PyTorch ops when parameters take part in autograd, so a custom
+    loss on q[...].log_prob reaches the encoder weights (the kernel path is used only without autograd)."""
+    from apgs_b200.gmm import models as M
+    K, D, S, B, N = 3, 2, 6, 4, 60
+    torch.manual_seed(0)
+    (enc_rws_eta, enc_apg_z, enc_apg_eta, gen), opt = M.init_apg_models(K, D, 32, True, DEV, lr=1e-3)
+    x = og.simulate(B, N, K, D).to(DEV).repeat(S, 1, 1, 1)
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N), device=DEV), K).float()
+    q = enc_apg_eta(x, z, gen.prior_ng)
+    loss = -(q["means"].log_prob.sum() + q["precisions"].log_prob.sum())
+    loss.backward()
+    g = [p.grad for p in enc_apg_eta.parameters()]
+    assert all(t is not None and bool(torch.isfinite(t).all()) and float(t.abs().sum()) > 0 for t in g)
+    q0 = enc_rws_eta(x, gen.prior_ng)
+    (-(q0["means"].log_prob.sum())).backward()
+    assert all(p.grad is not None for p in enc_rws_eta.parameters())
+    with torch.no_grad():                                         # evaluation: the kernel path, same numbers
+        qe = enc_apg_eta(x, z, gen.prior_ng, sampled=False, tau_old=q["precisions"].value, mu_old=q["means"].value)
+    _close(qe["means"].log_prob, q["means"].log_prob, rtol=1e-4, atol=1e-4, what="kernel vs torch log q(mu)")

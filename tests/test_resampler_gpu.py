@@ -364,3 +364,65 @@ def test_ancestor_kernels_stay_inside_their_buffers(S, B, strategy):
     assert int(a64.min()) >= 0 and int(a64.max()) < S and torch.equal(a64, a32.long())
     assert bool(torch.isfinite(ess).all()) and bool(torch.isfinite(lse).all())
     np.testing.assert_allclose(w.view(S, B).sum(0).cpu().numpy(), 1.0, rtol=1e-4)
+
+
+def test_multinomial_uniform_layout_is_explicit_when_ambiguous():
+    """with S == B a (B,S) tensor in the reference's generator order must not be read as (S,B) silently."""
+    from apgs_b200.resampler import Resampler
+    ops = _ops()
+    S = B = 16
+    torch.manual_seed(0)
+    w = torch.softmax(torch.randn(S, B) * 2, 0)
+    p = orc.categorical_probs(w)
+    u_bs = torch.rand(B, S, dtype=torch.float64)
+    ref = orc.multinomial_ancestors(p.numpy(), u_bs.numpy())
+    with pytest.raises(ValueError):
+        ops.sample_ancestors(w_norm=p.to(DEV), strategy="multinomial", uniforms=u_bs.to(DEV))
+    a = ops.sample_ancestors(w_norm=p.to(DEV), strategy="multinomial", uniforms=u_bs.to(DEV), uniform_layout="bs")
+    assert np.array_equal(a.cpu().numpy(), ref)
+    a2 = ops.sample_ancestors(w_norm=p.to(DEV), strategy="multinomial", uniforms=u_bs.t().contiguous().to(DEV), uniform_layout="sb")
+    assert np.array_equal(a2.cpu().numpy(), ref)
+    # the Resampler draws torch.rand(B, S, float64) -- the reference's generator stream -- and reads it as such
+    r = Resampler("multinomial", S, True, DEV)
+    u = r.draw_uniforms(S, B, DEV)
+    assert tuple(u.shape) == (B, S) and u.dtype == torch.float64
+    lw = torch.log(w).to(DEV)
+    a3 = r.sample_ancestral_index(lw, uniforms=u)
+    assert int(a3.min()) >= 0 and int(a3.max()) < S
+
+
+def test_resample_dims_propagate_gradients_like_torch_gather():
+    """resample_4dims / 5dims are differentiable w.r.t. the latent, as the reference's torch.gather is."""
+    from apgs_b200.resampler import Resampler
+    S, B = 12, 5
+    torch.manual_seed(1)
+    r = Resampler("systematic", S, True, DEV)
+    a = r.sample_ancestral_index((torch.randn(S, B) * 2).to(DEV))
+    for shape in ((S, B, 3, 2), (S, B, 4, 3, 2)):
+        v = torch.randn(*shape, device=DEV, requires_grad=True)
+        g = torch.randn(*shape, device=DEV)
+        out = r.resample_4dims(v, a) if len(shape) == 4 else r.resample_5dims(v, a)
+        assert out.requires_grad
+        (out * g).sum().backward()
+        v2 = v.detach().clone().requires_grad_(True)
+        idx = a.view((S, B) + (1,) * (len(shape) - 2)).expand(*shape)
+        (torch.gather(v2, 0, idx) * g).sum().backward()
+        assert torch.equal(out.detach(), torch.gather(v2, 0, idx).detach())
+        torch.testing.assert_close(v.grad, v2.grad, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("S,B,N", [(1000, 64, 60), (100, 37, 200), (5, 3, 7), (3300, 4, 9), (1, 2, 5)])
+def test_W2_local_softmax_tile_kernel(S, B, N):
+    """per-point softmax over S (apgs/gmm/objectives.py:216-218): the single-pass shared-memory tile kernel (and, beyond
+    a tile, the three-pass one: S = 3300) against torch, incl. -inf entries and ragged column tiles; columns sum to 1."""
+    ops = _ops()
+    torch.manual_seed(S + N)
+    x = (torch.randn(S, B, N) * 4).to(DEV)
+    if S > 4:
+        x[::3, 0, 0] = -float("inf")
+    w, lw = ops.local_weight_stats(x)
+    ref = torch.softmax(x.double(), 0)
+    torch.testing.assert_close(w.double(), ref, rtol=1e-5, atol=1e-30)
+    torch.testing.assert_close(w.sum(0), torch.ones(B, N, device=DEV), rtol=1e-5, atol=1e-5)
+    fin = torch.isfinite(x).all(0)
+    torch.testing.assert_close(lw[:, fin.all(-1)].double(), x.double().sum(-1)[:, fin.all(-1)], rtol=1e-5, atol=1e-4)
