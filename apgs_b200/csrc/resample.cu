@@ -8,6 +8,7 @@
 //   * a latent is (S,B,inner): the output of the gather is a dense stream, the input is B chunks of
 //     `inner` bytes per output row.
 #include "resample.cuh"
+#include "tile.cuh"
 
 namespace apgs {
 
@@ -520,54 +521,94 @@ __global__ void __launch_bounds__(256) k_local_softmax(const float* __restrict__
     if (c >= C) return;
     float m = -INFINITY;
     for (long long s = 0; s < S; ++s) m = fmaxf(m, __ldg(lwl + s * C + c));
-    float sum = 0.f;
-    for (long long s = 0; s < S; ++s) sum += expf(__ldg(lwl + s * C + c) - m);
+    double acc = 0.0;                                               // S is large here (beyond a shared-memory tile)
+    for (long long s = 0; s < S; ++s) acc += (double)expf(__ldg(lwl + s * C + c) - m);
+    const float sum = (float)acc;
     for (long long s = 0; s < S; ++s) w[s * C + c] = __fdiv_rn(expf(__ldg(lwl + s * C + c) - m), sum);
 }
 
-// Single-pass tile variant: a CTA owns TC adjacent columns and ALL S rows of them in shared memory -- one read and one
-// write of the (S,B,N) tensor instead of three reads and one write.  256 threads = 16 row groups x 16 columns: a warp
-// reads two 64-byte row segments per step (full sectors), the column maxima / sums of the 16 row groups meet in shared
-// memory, exp is evaluated once per element (kept in the tile) and normalised with the same IEEE division.
-constexpr int kLsTC = 16, kLsRG = 16;
+// Single-pass tile variant: a CTA owns TC = 16 adjacent columns and ALL S rows of them in shared memory -- one read and
+// one write of the (S,B,N) tensor instead of three reads and one write.  256 threads = 64 row groups x 4 column quads:
+// a thread moves 16 bytes per row (cp.async straight into the tile, S/64 requests in flight per thread, no registers),
+// the column maxima / sums meet through warp shuffles (8 row groups per warp) and an 8 x 16 shared array, exp is evaluated
+// once per element (kept in the tile) and normalised with the same IEEE division; 16-byte streaming stores.
+constexpr int kLsTC = 16, kLsThreads = 256;
 
-__global__ void __launch_bounds__(kLsTC* kLsRG) k_local_softmax_tile(const float* __restrict__ lwl, int S, long long C,
-                                                                     float* __restrict__ w) {
+__device__ __forceinline__ float4 ls_reduce4(float4 v, float (*s_red)[kLsTC + 4], bool is_max) {
+    // across the 8 row groups of a warp (lanes differ in bits 2..4), then across the 8 warps
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        const float a = __shfl_xor_sync(0xffffffffu, v.x, o), b = __shfl_xor_sync(0xffffffffu, v.y, o);
+        const float c = __shfl_xor_sync(0xffffffffu, v.z, o), d = __shfl_xor_sync(0xffffffffu, v.w, o);
+        if (is_max) { v.x = fmaxf(v.x, a); v.y = fmaxf(v.y, b); v.z = fmaxf(v.z, c); v.w = fmaxf(v.w, d); }
+        else { v.x += a; v.y += b; v.z += c; v.w += d; }
+    }
+    const int q = threadIdx.x & 3, warp = threadIdx.x >> 5;
+    __syncthreads();                                           // previous use of s_red is over
+    if ((threadIdx.x & 31) < 4) *reinterpret_cast<float4*>(&s_red[warp][q * 4]) = v;
+    __syncthreads();
+    float4 r = *reinterpret_cast<const float4*>(&s_red[0][q * 4]);
+#pragma unroll
+    for (int i = 1; i < kLsThreads / 32; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(&s_red[i][q * 4]);
+        if (is_max) { r.x = fmaxf(r.x, t.x); r.y = fmaxf(r.y, t.y); r.z = fmaxf(r.z, t.z); r.w = fmaxf(r.w, t.w); }
+        else { r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+    }
+    return r;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kLsThreads) k_local_softmax_tile(const float* __restrict__ lwl, int S, long long C,
+                                                                   float* __restrict__ w) {
     extern __shared__ __align__(16) float s_tile[];                 // [S][TC]
-    __shared__ float s_red[kLsRG][kLsTC + 1];
-    const int c = threadIdx.x % kLsTC, rg = threadIdx.x / kLsTC;
-    const long long col = (long long)blockIdx.x * kLsTC + c;
-    const bool live = col < C;
-    float m = -INFINITY;
-    if (live) {
-#pragma unroll 8
-        for (int s = rg; s < S; s += kLsRG) {
-            const float v = __ldg(lwl + (long long)s * C + col);
-            s_tile[s * kLsTC + c] = v;
-            m = fmaxf(m, v);
-        }
-    }
-    s_red[rg][c] = m;
-    __syncthreads();
+    __shared__ __align__(16) float s_red[kLsThreads / 32][kLsTC + 4];
+    const int q = threadIdx.x & 3, rg = threadIdx.x >> 2;           // column quad, row group (0..63)
+    constexpr int RG = kLsThreads / 4;
+    const long long col = (long long)blockIdx.x * kLsTC + q * 4;
+    const bool live = col < C;                                      // VEC: C % 4 == 0, so a quad is all in or all out
+    if (VEC) {
+        if (live)
+            for (int s = rg; s < S; s += RG)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_tile + s * kLsTC + q * 4)),
+                             "l"(lwl + (long long)s * C + col) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int s = rg; s < S; s += RG)
 #pragma unroll
-    for (int i = 0; i < kLsRG; ++i) m = fmaxf(m, s_red[i][c]);
-    __syncthreads();
-    float sum = 0.f;
-    if (live) {
-        for (int s = rg; s < S; s += kLsRG) {
-            const float e = expf(s_tile[s * kLsTC + c] - m);
-            s_tile[s * kLsTC + c] = e;
-            sum += e;
-        }
+            for (int i = 0; i < 4; ++i) s_tile[s * kLsTC + q * 4 + i] = (col + i < C) ? __ldg(lwl + (long long)s * C + col + i) : -INFINITY;
     }
-    s_red[rg][c] = sum;
-    __syncthreads();
-    sum = 0.f;
+    // each thread only touches the tile elements it loaded itself: no barrier needed before the passes below
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (live || !VEC)
+        for (int s = rg; s < S; s += RG) {
+            const float4 v = *reinterpret_cast<const float4*>(s_tile + s * kLsTC + q * 4);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    m = ls_reduce4(m, s_red, true);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live || !VEC)
+        for (int s = rg; s < S; s += RG) {
+            float4* t = reinterpret_cast<float4*>(s_tile + s * kLsTC + q * 4);
+            float4 v = *t;
+            v.x = expf(v.x - m.x); v.y = expf(v.y - m.y); v.z = expf(v.z - m.z); v.w = expf(v.w - m.w);
+            *t = v;
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+    sum = ls_reduce4(sum, s_red, false);
+    if (VEC) {
+        if (live)
+            for (int s = rg; s < S; s += RG) {
+                float4 v = *reinterpret_cast<const float4*>(s_tile + s * kLsTC + q * 4);
+                v.x = __fdiv_rn(v.x, sum.x); v.y = __fdiv_rn(v.y, sum.y); v.z = __fdiv_rn(v.z, sum.z); v.w = __fdiv_rn(v.w, sum.w);
+                __stcs(reinterpret_cast<float4*>(w + (long long)s * C + col), v);
+            }
+    } else {
+        const float sm[4] = {sum.x, sum.y, sum.z, sum.w};
+        for (int s = rg; s < S; s += RG)
 #pragma unroll
-    for (int i = 0; i < kLsRG; ++i) sum += s_red[i][c];
-    if (live) {
-#pragma unroll 8
-        for (int s = rg; s < S; s += kLsRG) __stcs(w + (long long)s * C + col, __fdiv_rn(s_tile[s * kLsTC + c], sum));
+            for (int i = 0; i < 4; ++i)
+                if (col + i < C) w[(long long)s * C + col + i] = __fdiv_rn(s_tile[s * kLsTC + q * 4 + i], sm[i]);
     }
 }
 
@@ -677,8 +718,10 @@ extern "C" int apgs_local_weight_stats_f32(const float* log_w_local, int64_t S, 
         if (tile <= kSmemTileBudget) {
             long long blocks = (C + kLsTC - 1) / kLsTC;
             if (blocks >= (1ll << 31)) return fail(APGS_E_SHAPE, "local_weight_stats: too many columns");
-            APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_local_softmax_tile), tile), "smem attr");
-            k_local_softmax_tile<<<(unsigned int)blocks, kLsTC * kLsRG, tile, st>>>(log_w_local, (int)S, C, w_local_out);
+            const bool vec = (C & 3) == 0 && aligned(log_w_local, 16) && aligned(w_local_out, 16);
+            auto kern = vec ? k_local_softmax_tile<true> : k_local_softmax_tile<false>;
+            APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), tile), "smem attr");
+            kern<<<(unsigned int)blocks, kLsThreads, tile, st>>>(log_w_local, (int)S, C, w_local_out);
             APGS_LAUNCH_OK("k_local_softmax_tile launch");
         } else {
             // S beyond a shared-memory tile: three passes over global memory
