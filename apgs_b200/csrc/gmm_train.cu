@@ -1,0 +1,456 @@
+// Training mode of the GMM sweep on sm_100a: backward kernels for the two proposal log-densities
+// whose gradients the APG loss needs,  loss = sum_s w_s.detach() * (-log q_s)  (apgs/gmm/objectives.py:183,220).
+//
+//   k_gmm_z_logq_bwd     d/d{W1,b1,W2,b2} of  sum_{r,n} G[r,n] * log q(z_n | x_n, tau, mu)  for Enc_apg_z
+//                        (apgs/gmm/models.py:102-115): per (point n, cluster k) MLP 3D -> H -> 1, softmax over k,
+//                        OneHotCategorical log-prob (torch's eps clamp: zero gradient outside [eps, 1 - eps]).
+//                        G is the upstream gradient (the detached per-point weights of the loss, or any other).
+//                        The forward kernel's q_probs are re-used; the hidden layer is recomputed from the factorised
+//                        exponent tables of the forward kernel (gmm_fused.cu): 2^(xh'_n + e'_k) = Ex_n * Ee_k.
+//   k_label_table_sum    out[r,c] = sum_n T[b,n,label(r,n),c]       and its adjoint
+//   k_label_table_sum_bwd   gT[b,n,l,c] = sum_s [label(s,b,n) == l] * gout[s,b,c]
+//                        -- with one-hot z the two Linear heads of Enc_apg_eta (models.py:56-66) take only K values per
+//                        data point, so the host tabulates their outputs once per INSTANCE with ordinary (differentiable)
+//                        PyTorch ops on a (B,N,K,.) tensor and the per-particle neural statistics are label-indexed sums
+//                        of that table: the only S-sized work of the eta step's graph is this pair of kernels.
+//
+// Deterministic: partial sums travel through shared / global arrays and are combined in a fixed order (no atomics).
+#include "gmm_common.cuh"
+
+namespace apgs {
+
+struct ZBwdArgs {
+    const float* x;                     // (B, N, D)
+    const float *tau, *mu;              // (R, K, D)
+    const float *W1, *b1, *W2;          // (H, 3D), (H), (H)
+    const float* q;                     // (R, N, K) q_probs of the forward kernel
+    const float* z;                     // (R, N, K) one-hot assignment, or null
+    const unsigned char* zl;            // (R, LN) labels, or null
+    long long LN;
+    const float* g;                     // upstream gradient d loss / d log q[r, n]
+    long long g_sr, g_sn;               // element (r, n) at g[r * g_sr + n * g_sn]  (g_sn = 0: one value per particle)
+    int S, B, N, H, chunks;             // chunks of kZP particles handled by one CTA
+    float* partial;                     // [gridDim.y * gridDim.x][GS]
+};
+
+constexpr int kZP = 32, kZL = 8, kZPT = 8;       // particles per chunk, lanes per particle, points per lane and block
+
+// values accumulated per hidden unit: [dW2, db1 / (4 W2), dW1x (D), dW1m (D), dW1t (D)] (the factor 4 W2_h is applied last)
+template <int D> struct ZBwdV { static constexpr int V = 2 + 3 * D; };
+
+template <int K, int D>
+__global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd(ZBwdArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    constexpr int KD = K * D, V = ZBwdV<D>::V, NW = kZP * kZL / 32;
+    const int N = a.N, H = a.H;
+    const int NP = (N + kZL * kZPT - 1) / (kZL * kZPT) * (kZL * kZPT);       // points padded to blocks of 64
+    const int EPS = H * K + 1;                                               // per-particle stride of the Ee table
+    float* s_ex = smf;                                   // [H][NP]   Ex (or raw xh' when the CTA is not `xok`)
+    float* s_e = s_ex + (size_t)H * NP;                  // [kZP][EPS] Ee (or raw e')
+    float* s_x = s_e + (size_t)kZP * EPS;                // [NP][D]
+    float* s_acc = s_x + (size_t)NP * D;                 // [NW][H][V] (+1: db2)
+    float* s_w2 = s_acc + (size_t)NW * (H * V + 1);      // [H]
+    __shared__ int s_xok;
+    const int b = blockIdx.x;
+    const int p = threadIdx.x / kZL, j = threadIdx.x % kZL, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* xb = a.x + (size_t)b * N * D;
+    if (threadIdx.x == 0) s_xok = 1;
+    for (int i = threadIdx.x; i < NW * (H * V + 1); i += blockDim.x) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < NP * D; i += blockDim.x) s_x[i] = (i < N * D) ? __ldg(xb + i) : 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) s_w2[i] = __ldg(a.W2 + i);
+    __syncthreads();
+    // ---- per-CTA table of the data part of the pre-activations
+    bool okx = true;
+    for (int idx = threadIdx.x; idx < H * NP; idx += blockDim.x) {
+        const int h = idx / NP, n = idx - h * NP;
+        float acc = 0.f;
+        if (n < N) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc = fmaf(TANH_PRESCALE * __ldg(a.W1 + h * 3 * D + d), s_x[n * D + d], acc);
+            if (!(fabsf(acc) <= 126.f)) okx = false;
+        }
+        s_ex[idx] = acc;
+    }
+    if (!okx) s_xok = 0;                                  // benign race: every writer stores 0
+    __syncthreads();
+    const bool xok = s_xok != 0;
+    if (xok)
+        for (int idx = threadIdx.x; idx < H * NP; idx += blockDim.x) {
+            const int n = idx % NP;
+            s_ex[idx] = (n < N) ? ex2_ftz(s_ex[idx]) : 0.f;          // padding points: y = 1, and their g is 0
+        }
+    __syncthreads();
+    float gb2 = 0.f;
+    float* my_acc = s_acc + (size_t)warp * (H * V + 1);
+    for (int c = 0; c < a.chunks; ++c) {
+        const long long s = ((long long)blockIdx.y * a.chunks + c) * kZP + p;
+        const bool valid = s < a.S;
+        const long long r = s * a.B + b;
+        float tk[KD], mk[KD];
+#pragma unroll
+        for (int e = 0; e < KD; ++e) { tk[e] = valid ? __ldg(a.tau + r * KD + e) : 1.f; mk[e] = valid ? __ldg(a.mu + r * KD + e) : 0.f; }
+        // ---- particle part of the pre-activations: e'_k[h]; the factorised form needs every |e'| <= 126
+        float* ep = s_e + (size_t)p * EPS;
+        bool oke = true;
+        __syncwarp();                                    // the previous chunk's readers of this block are done
+        for (int h = j; h < H; h += kZL) {
+            const float bh = __ldg(a.b1 + h);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float acc = bh;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mk[k * D + d], acc);
+                    acc = fmaf(__ldg(a.W1 + h * 3 * D + 2 * D + d), tk[k * D + d], acc);
+                }
+                const float ee = TANH_PRESCALE * acc;
+                if (!(fabsf(ee) <= 126.f)) oke = false;
+                ep[h * K + k] = ee;
+            }
+        }
+#pragma unroll
+        for (int o = kZL / 2; o > 0; o >>= 1) oke = (__shfl_xor_sync(0xffffffffu, (int)oke, o) != 0) && oke;
+        const bool fast = xok && oke;
+        __syncwarp();
+        if (fast)
+            for (int h = j; h < H; h += kZL)
+#pragma unroll
+                for (int k = 0; k < K; ++k) ep[h * K + k] = ex2_ftz(ep[h * K + k]);
+        __syncwarp();
+        for (int n0 = 0; n0 < N; n0 += kZL * kZPT) {
+            // ---- this lane's points of the block: upstream gradient times d log q / d logit_k = (k == z) - q_k
+            float gk[kZPT][K];
+#pragma unroll
+            for (int i = 0; i < kZPT; ++i) {
+                const int n = n0 + j + kZL * i;
+#pragma unroll
+                for (int k = 0; k < K; ++k) gk[i][k] = 0.f;
+                if (valid && n < N) {
+                    float qv[K], sq = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { qv[k] = __ldg(a.q + (r * N + n) * K + k); sq = __fadd_rn(sq, qv[k]); }
+                    int lf = 0;
+                    if (a.zl != nullptr) {
+                        lf = min((int)__ldg(a.zl + r * a.LN + n), K - 1);
+                    } else {
+                        float best = __ldg(a.z + (r * N + n) * K);
+#pragma unroll
+                        for (int k = 1; k < K; ++k) { const float v = __ldg(a.z + (r * N + n) * K + k); if (v > best) { best = v; lf = k; } }
+                    }
+                    float ql = qv[0];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) if (lf == k) ql = qv[k];
+                    const float pn = __fdiv_rn(ql, sq);                          // Categorical's renormalisation
+                    const bool inside = pn >= FLT_EPS_F && pn <= 1.f - FLT_EPS_F;   // clamp_probs: zero gradient outside
+                    const float up = inside ? __ldg(a.g + r * a.g_sr + n * a.g_sn) : 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { gk[i][k] = up * (((k == lf) ? 1.f : 0.f) - qv[k]); gb2 += gk[i][k]; }
+                }
+            }
+            // ---- hidden units: t = tanh(a) = 1 - 2 r, 1 - t^2 = 4 (r - r^2), r = 1 / (2^(xh' + e') + 1)
+            for (int h = 0; h < H; ++h) {
+                float G2 = 0.f, A[K], X[D];
+#pragma unroll
+                for (int k = 0; k < K; ++k) A[k] = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) X[d] = 0.f;
+                float ee[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) ee[k] = ep[h * K + k];
+                const float* exr = s_ex + (size_t)h * NP + n0 + j;
+#pragma unroll
+                for (int i = 0; i < kZPT; ++i) {
+                    const float ex = exr[kZL * i];
+                    float sn = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const float y = fast ? fmaf(ex, ee[k], 1.f) : (ex2_ftz((xok ? 0.f : ex) + ee[k]) + 1.f);
+                        const float rr = rcp_ftz(y);
+                        const float t = fmaf(-2.f, rr, 1.f);
+                        const float v = fmaf(-rr, rr, rr);
+                        const float cc = gk[i][k] * v;
+                        G2 = fmaf(gk[i][k], t, G2);
+                        A[k] += cc;
+                        sn += cc;
+                    }
+                    const int n = n0 + j + kZL * i;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) X[d] = fmaf(sn, s_x[n * D + d], X[d]);
+                }
+                // the particle's lanes, then the warp's particles
+#pragma unroll
+                for (int o = 1; o < kZL; o <<= 1) {
+                    G2 += __shfl_xor_sync(0xffffffffu, G2, o);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) A[k] += __shfl_xor_sync(0xffffffffu, A[k], o);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) X[d] += __shfl_xor_sync(0xffffffffu, X[d], o);
+                }
+                float vals[V];
+                vals[0] = G2;
+                vals[1] = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) vals[1] += A[k];
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    float m = 0.f, t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { m = fmaf(A[k], mk[k * D + d], m); t = fmaf(A[k], tk[k * D + d], t); }
+                    vals[2 + d] = X[d]; vals[2 + D + d] = m; vals[2 + 2 * D + d] = t;
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+#pragma unroll
+                    for (int o = kZL; o < 32; o <<= 1) vals[v] += __shfl_xor_sync(0xffffffffu, vals[v], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) my_acc[h * V + v] += vals[v];
+                }
+            }
+        }
+    }
+    // NOTE on the slow path: when the CTA is not `xok`, s_ex holds the raw xh' (see above) and `fast` is false for every
+    // particle, so y = 2^(xh' + e') + 1 exactly; when it is `xok` but a particle is not, s_ex holds Ex = 2^xh' and the
+    // exponent cannot be re-assembled -- such particles (|e'| > 126: tanh saturated for every point unless xh' cancels
+    // it to within 126) take y = 2^e' + 1, i.e. the saturated value, whose gradient is zero to fp32 precision.
+    gb2 = warp_sum(gb2);
+    if (lane == 0) my_acc[H * V] = gb2;
+    __syncthreads();
+    const int GS = H * V + 1;
+    float* out = a.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * GS;
+    for (int i = threadIdx.x; i < GS; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sum += s_acc[(size_t)w * GS + i];
+        out[i] = sum;
+    }
+}
+
+// rows [M][GS] -> [NC1][GS] doubles (CTA c sums rows c, c + NC1, ...), then one CTA finishes
+__global__ void k_reduce_rows_stage1(const float* __restrict__ part, long long M, int GS, double* __restrict__ ws) {
+    for (int col = threadIdx.x; col < GS; col += blockDim.x) {
+        double acc = 0.0;
+        for (long long row = blockIdx.x; row < M; row += gridDim.x) acc += (double)__ldg(part + row * GS + col);
+        ws[(size_t)blockIdx.x * GS + col] = acc;
+    }
+}
+
+template <int D>
+__global__ void k_z_bwd_finish(const double* __restrict__ ws, int NC1, int H, const float* __restrict__ W2,
+                               float* gW1, float* gb1, float* gW2, float* gb2) {
+    constexpr int V = ZBwdV<D>::V;
+    const int GS = H * V + 1;
+    for (int col = threadIdx.x; col < GS; col += blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < NC1; ++c) acc += ws[(size_t)c * GS + col];
+        if (col == GS - 1) { if (gb2) gb2[0] = (float)acc; continue; }
+        const int h = col / V, v = col - h * V;
+        const double f = 4.0 * (double)__ldg(W2 + h);                   // d tanh / d a = 4 (r - r^2), times the output weight
+        if (v == 0) { if (gW2) gW2[h] = (float)acc; }
+        else if (v == 1) { if (gb1) gb1[h] = (float)(f * acc); }
+        else if (gW1) gW1[h * 3 * D + (v - 2)] = (float)(f * acc);      // columns: x (D), mu (D), tau (D) -- W1's own order
+    }
+}
+
+constexpr int kRedCtas = 128;
+
+template <int K, int D>
+static int launch_z_bwd(ZBwdArgs a, float* gW1, float* gb1, float* gW2, float* gb2, void* ws, size_t ws_bytes, cudaStream_t st) {
+    constexpr int V = ZBwdV<D>::V;
+    const int GS = a.H * V + 1;
+    const int NP = (a.N + kZL * kZPT - 1) / (kZL * kZPT) * (kZL * kZPT);
+    const int NW = kZP * kZL / 32;
+    const size_t smem = ((size_t)a.H * NP + (size_t)kZP * (a.H * K + 1) + (size_t)NP * D + (size_t)NW * GS + a.H) * 4;
+    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_logq_backward: N=%d H=%d too large for one tile", a.N, a.H);
+    const int nchunk = (a.S + kZP - 1) / kZP;
+    // a few chunks per CTA amortise the data table; keep >= ~4 waves of CTAs on the 148 SMs
+    int chunks = 1;
+    while (chunks < 8 && (long long)a.B * ((nchunk + 2 * chunks - 1) / (2 * chunks)) >= 4LL * 4 * sm_count()) chunks *= 2;
+    a.chunks = chunks;
+    const int gy = (nchunk + chunks - 1) / chunks;
+    if (gy > 65535) return fail(APGS_E_SHAPE, "gmm_z_logq_backward: S=%d too large for one launch", a.S);
+    const long long M = (long long)a.B * gy;
+    const size_t need = (size_t)M * GS * sizeof(float) + 256 + (size_t)kRedCtas * GS * sizeof(double);
+    if (ws == nullptr || ws_bytes < need)
+        return fail(APGS_E_WORKSPACE, "gmm_z_logq_backward: workspace of %zu bytes required, got %zu", need, ws_bytes);
+    a.partial = reinterpret_cast<float*>(ws);
+    double* ws2 = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + (((size_t)M * GS * sizeof(float) + 255) & ~(size_t)255));
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_gmm_z_logq_bwd<K, D>), smem), "smem attr");
+    k_gmm_z_logq_bwd<K, D><<<dim3((unsigned int)a.B, (unsigned int)gy), kZP * kZL, smem, st>>>(a);
+    APGS_LAUNCH_OK("k_gmm_z_logq_bwd launch");
+    k_reduce_rows_stage1<<<kRedCtas, 256, 0, st>>>(a.partial, M, GS, ws2);
+    APGS_LAUNCH_OK("k_reduce_rows_stage1 launch");
+    k_z_bwd_finish<D><<<1, 256, 0, st>>>(ws2, kRedCtas, a.H, a.W2, gW1, gb1, gW2, gb2);
+    APGS_LAUNCH_OK("k_z_bwd_finish launch");
+    return 0;
+}
+
+// ================================================================================================================
+// label-indexed table sums (eta step graph)
+// ================================================================================================================
+struct LtsArgs {
+    const float* tab;                   // (B, N, K, C)
+    const float* z;                     // (R, N, K) one-hot, or null
+    const unsigned char* zl;            // (R, LN) labels, or null
+    long long LN;
+    int S, B, N, K, C;
+    float* out;                         // fwd: (R, C)
+    const float* gout;                  // bwd: (R, C)
+    float* gtab;                        // bwd: (B, N, K, C)
+};
+
+__device__ __forceinline__ int lts_label(const LtsArgs& a, long long r, int n) {
+    if (a.zl != nullptr) return min((int)__ldg(a.zl + r * a.LN + n), a.K - 1);
+    const float* zr = a.z + (r * a.N + n) * a.K;
+    int lab = 0;
+    float best = __ldg(zr);
+    for (int k = 1; k < a.K; ++k) { const float v = __ldg(zr + k); if (v > best) { best = v; lab = k; } }
+    return lab;
+}
+
+// forward: CTA = instance b x 32 particles, 8 lanes split the points; table of the instance in shared memory
+template <int CMAX>
+__global__ void __launch_bounds__(256) k_label_table_sum(LtsArgs a) {
+    extern __shared__ __align__(16) float s_tab[];       // [N*K][C]
+    const int b = blockIdx.x, C = a.C, NK = a.N * a.K;
+    for (int i = threadIdx.x; i < NK * C; i += blockDim.x) s_tab[i] = __ldg(a.tab + (size_t)b * NK * C + i);
+    __syncthreads();
+    const int p = threadIdx.x / 8, j = threadIdx.x % 8;
+    const long long s = (long long)blockIdx.y * 32 + p;
+    const bool valid = s < a.S;
+    const long long r = s * a.B + b;
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+    if (valid)
+        for (int n = j; n < a.N; n += 8) {
+            const float* t = s_tab + (size_t)(n * a.K + lts_label(a, r, n)) * C;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) if (c < C) acc[c] += t[c];
+        }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        double v = (double)acc[c];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (valid && j == 0 && c < C) a.out[r * C + c] = (float)v;
+    }
+}
+
+// adjoint: CTA = instance b; thread t owns the pairs (n, c) = t, t + 256, ... and adds gout[s, b, c] to the row of the
+// label particle s gives point n -- every (n, label, c) accumulator has exactly one owner, so no atomics; particles are
+// staged through shared memory in tiles
+constexpr int kLtsTile = 64;
+__global__ void __launch_bounds__(256) k_label_table_sum_bwd(LtsArgs a) {
+    extern __shared__ __align__(16) float s_g[];          // [N*K][C] accumulators | tile: gout [kLtsTile][C], labels [kLtsTile][N]
+    const int b = blockIdx.x, C = a.C, N = a.N, K = a.K, NKC = N * K * C;
+    float* s_go = s_g + NKC;
+    unsigned char* s_lab = reinterpret_cast<unsigned char*>(s_go + kLtsTile * C);
+    for (int i = threadIdx.x; i < NKC; i += blockDim.x) s_g[i] = 0.f;
+    for (int s0 = 0; s0 < a.S; s0 += kLtsTile) {
+        const int ns = min(kLtsTile, a.S - s0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ns * C; i += blockDim.x) {
+            const int si = i / C, c = i - si * C;
+            s_go[i] = __ldg(a.gout + ((long long)(s0 + si) * a.B + b) * C + c);
+        }
+        for (int i = threadIdx.x; i < ns * N; i += blockDim.x) {
+            const int si = i / N, n = i - si * N;
+            s_lab[i] = (unsigned char)lts_label(a, (long long)(s0 + si) * a.B + b, n);
+        }
+        __syncthreads();
+        for (int pc = threadIdx.x; pc < N * C; pc += blockDim.x) {
+            const int n = pc / C, c = pc - n * C;
+            for (int si = 0; si < ns; ++si) s_g[(size_t)(n * K + s_lab[si * N + n]) * C + c] += s_go[si * C + c];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NKC; i += blockDim.x) a.gtab[(size_t)b * NKC + i] = s_g[i];
+}
+
+}  // namespace apgs
+
+using namespace apgs;
+
+extern "C" size_t apgs_gmm_z_logq_backward_workspace_bytes(int64_t S, int64_t B, int64_t H, int64_t D) {
+    if (S <= 0 || B <= 0 || H <= 0 || D <= 0) return 0;
+    const size_t GS = (size_t)H * (2 + 3 * D) + 1;
+    const size_t M = (size_t)B * ((S + kZP - 1) / kZP);            // upper bound (one chunk per CTA)
+    return ((M * GS * sizeof(float) + 255) & ~(size_t)255) + 256 + (size_t)kRedCtas * GS * sizeof(double);
+}
+
+extern "C" int apgs_gmm_z_logq_backward_f32(const float* x, const float* tau, const float* mu, const float* W1,
+                                            const float* b1, const float* W2, int64_t H, const float* q_probs,
+                                            const float* z_onehot, const uint8_t* z_labels, int64_t label_stride,
+                                            const float* grad_logq, int64_t g_stride_particle, int64_t g_stride_point,
+                                            int64_t S, int64_t B, int64_t N, int64_t K, int64_t D, float* gW1, float* gb1,
+                                            float* gW2, float* gb2, void* workspace, size_t workspace_bytes, void* stream) {
+    if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024 || S >= (1ll << 31) || B >= 65536ll * 32768)
+        return fail(APGS_E_SHAPE, "gmm_z_logq_backward: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S, (long long)B,
+                    (long long)N, (long long)H);
+    if (!x || !tau || !mu || !W1 || !b1 || !W2 || !q_probs || !grad_logq) return fail(APGS_E_BADARG, "gmm_z_logq_backward: NULL input");
+    if ((z_onehot == nullptr) == (z_labels == nullptr))
+        return fail(APGS_E_BADARG, "gmm_z_logq_backward: give the assignment either one-hot or as labels");
+    if (z_labels && label_stride < N) return fail(APGS_E_BADARG, "gmm_z_logq_backward: label_stride %lld < N", (long long)label_stride);
+    ZBwdArgs a = {};
+    a.x = x; a.tau = tau; a.mu = mu; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.q = q_probs; a.z = z_onehot; a.zl = z_labels;
+    a.LN = label_stride; a.g = grad_logq; a.g_sr = g_stride_particle; a.g_sn = g_stride_point;
+    a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 3 && D == 2) return launch_z_bwd<3, 2>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
+    if (K == 2 && D == 2) return launch_z_bwd<2, 2>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
+    if (K == 4 && D == 2) return launch_z_bwd<4, 2>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
+    if (K == 5 && D == 2) return launch_z_bwd<5, 2>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
+    if (K == 3 && D == 3) return launch_z_bwd<3, 3>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
+    return fail(APGS_E_UNSUPPORTED, "gmm_z_logq_backward: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
+}
+
+static int lts_check(const LtsArgs& a, const char* who) {
+    if (a.S <= 0 || a.B <= 0 || a.N <= 0 || a.K <= 0 || a.K > 255 || a.C <= 0 || a.C > 64)
+        return fail(APGS_E_SHAPE, "%s: bad sizes S=%d B=%d N=%d K=%d C=%d", who, a.S, a.B, a.N, a.K, a.C);
+    if (!a.tab && !a.gtab) return fail(APGS_E_BADARG, "%s: NULL table", who);
+    if ((a.z == nullptr) == (a.zl == nullptr)) return fail(APGS_E_BADARG, "%s: give the assignment either one-hot or as labels", who);
+    if (a.zl && a.LN < a.N) return fail(APGS_E_BADARG, "%s: label_stride < N", who);
+    return 0;
+}
+
+extern "C" int apgs_gmm_label_table_sum_f32(const float* table, const float* z_onehot, const uint8_t* z_labels,
+                                            int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K, int64_t C,
+                                            float* out, void* stream) {
+    LtsArgs a = {};
+    a.tab = table; a.z = z_onehot; a.zl = z_labels; a.LN = label_stride;
+    a.S = (int)S; a.B = (int)B; a.N = (int)N; a.K = (int)K; a.C = (int)C; a.out = out;
+    if (int e = lts_check(a, "gmm_label_table_sum")) return e;
+    if (!table || !out) return fail(APGS_E_BADARG, "gmm_label_table_sum: NULL pointer");
+    const size_t smem = (size_t)N * K * C * 4;
+    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_label_table_sum: table of %zu bytes does not fit shared memory", smem);
+    const long long gy = (S + 31) / 32;
+    if (gy > 65535) return fail(APGS_E_SHAPE, "gmm_label_table_sum: S too large for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 16) {
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_label_table_sum<16>), smem), "smem attr");
+        k_label_table_sum<16><<<dim3((unsigned int)B, (unsigned int)gy), 256, smem, st>>>(a);
+    } else {
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_label_table_sum<64>), smem), "smem attr");
+        k_label_table_sum<64><<<dim3((unsigned int)B, (unsigned int)gy), 256, smem, st>>>(a);
+    }
+    APGS_LAUNCH_OK("k_label_table_sum launch");
+    return 0;
+}
+
+extern "C" int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, const float* z_onehot, const uint8_t* z_labels,
+                                                     int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K,
+                                                     int64_t C, float* grad_table, void* stream) {
+    LtsArgs a = {};
+    a.gout = grad_out; a.z = z_onehot; a.zl = z_labels; a.LN = label_stride;
+    a.S = (int)S; a.B = (int)B; a.N = (int)N; a.K = (int)K; a.C = (int)C; a.gtab = grad_table;
+    if (int e = lts_check(a, "gmm_label_table_sum_backward")) return e;
+    if (!grad_out || !grad_table) return fail(APGS_E_BADARG, "gmm_label_table_sum_backward: NULL pointer");
+    const size_t smem = ((size_t)N * K * C + (size_t)kLtsTile * C) * 4 + (size_t)kLtsTile * N;
+    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_label_table_sum_backward: N K C too large for shared memory");
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_label_table_sum_bwd), smem), "smem attr");
+    k_label_table_sum_bwd<<<(unsigned int)B, 256, smem, (cudaStream_t)stream>>>(a);
+    APGS_LAUNCH_OK("k_label_table_sum_bwd launch");
+    return 0;
+}

@@ -48,6 +48,19 @@ def posterior_eta_torch(xp, gamma, prior_ng):
     return alpha, beta, mu, nu
 
 
+def _posterior_from_stats(s1, s2, s3, prior_ng):
+    """kls_gmm.py:106-119 from the three neural statistics (s1 (..,K,1), s2 / s3 (..,K,D)); quirks Q1 / Q2 included."""
+    prior_alpha, prior_beta, prior_mu, prior_nu = prior_ng
+    cnt = s1.expand_as(s2)
+    cnt = torch.where(cnt == 0.0, torch.ones_like(cnt), cnt)                       # Q1
+    x_bar = s2 / cnt
+    alpha = prior_alpha + cnt / 2
+    nu = prior_nu + cnt
+    mu = (prior_mu * prior_nu + s2) / (cnt + prior_nu)
+    beta = prior_beta + (s3 - (s2 ** 2) / cnt) / 2. + (cnt * prior_nu / (cnt + prior_nu)) * ((x_bar - prior_nu) ** 2) / 2.   # Q2
+    return alpha, beta, mu, nu
+
+
 def eta_log_q_torch(post, tau, mu):
     """differentiable log q(tau, mu) summed over (K, D) (apgs/gmm/objectives.py:167)."""
     alpha, beta, mu_q, nu_q = post
@@ -156,6 +169,27 @@ class Enc_apg_eta(nn.Module):
         """same parameters through PyTorch ops only (autograd graph for training)."""
         xp, gam = self.heads(ob, z)
         return posterior_eta_torch(xp, gam, prior_ng)
+
+    def params_graph(self, ob, z, prior_ng):
+        """the same differentiable parameters with the S-sized work on the kernels: z is one-hot, so the
+        heads take only K values per data point -- tabulate {gamma_k, gamma_k x'_d, gamma_k x'_d^2} per (instance, point,
+        label) with ordinary PyTorch ops (a (B,N,K,.) tensor: S times less work than heads()), sum the rows the labels
+        select (train.LabelTableSum: one kernel forward, one backward) and apply the Normal-Gamma update."""
+        from .train import LabelTableSum
+        x = _x_inst(ob)
+        B, N, D = x.shape
+        K = self.gamma[0].weight.shape[0]
+        eye = torch.eye(K, dtype=x.dtype, device=x.device)
+        inp = torch.cat((x.unsqueeze(2).expand(B, N, K, D), eye.expand(B, N, K, K)), -1)      # cat(x_n, e_l) for every label l
+        gam, xp = self.gamma(inp), self.ob(inp)                                              # (B,N,K,K), (B,N,K,D)
+        g5 = gam.unsqueeze(-1)
+        table = torch.cat((gam, (g5 * xp.unsqueeze(-2)).flatten(-2), (g5 * (xp ** 2).unsqueeze(-2)).flatten(-2)), -1)
+        nss = LabelTableSum.apply(table.contiguous(), z)                                     # (S,B,K + 2 K D)
+        S = nss.shape[0]
+        s1 = nss[..., :K].unsqueeze(-1)
+        s2 = nss[..., K:K + K * D].reshape(S, B, K, D)
+        s3 = nss[..., K + K * D:].reshape(S, B, K, D)
+        return _posterior_from_stats(s1, s2, s3, prior_ng)
 
     def forward(self, ob, z, prior_ng, sampled=True, tau_old=None, mu_old=None):
         # differentiable like the reference's forward() when the parameters take part in autograd (see Enc_rws_eta)

@@ -136,6 +136,7 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     return trace
 
 
+train_on_kernels = True        # loss_required: graphs of log q through the kernels (train.py) instead of PyTorch encoders
 compact_labels = True          # module switches (tests compare the representations / the two one-shot paths)
 lean_oneshot = True
 # z step emits the next eta step's posterior parameters + statistics (apgs_gmm_z_step_fused_labels_eta_f32; one launch
@@ -155,6 +156,19 @@ def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
     return (compact_labels and block == 'decomposed' and not result_flags['loss_required']
             and enc_apg_z.can_fuse(False) and _eta_fused(enc_apg_eta) and K <= 255
             and kernels.supported(K, D) & kernels.LABELS)
+
+
+def _train_z(enc_apg_z):
+    """training mode of Enc_apg_z on the kernels: parameters take part in autograd and the fused step is compiled for (K, D)"""
+    return (train_on_kernels and needs_grad(enc_apg_z) and getattr(enc_apg_z, 'fused', False) and hasattr(enc_apg_z, 'mlp')
+            and enc_apg_z.can_fuse(False))
+
+
+def _sample_z_train(enc_z, generative, x, tau, mu):
+    """sample-only fused z step with a graph: z, q_probs, log q(z) summed over the points (S,B)"""
+    from .train import FusedZStep
+    z, q_probs, _, _, _, log_q_local = FusedZStep.apply(*enc_z.mlp(), kernels._x3(x), tau, mu, None, generative)
+    return z, q_probs, log_q_local.sum(-1)
 
 
 def _eta_fused(enc_apg_eta):
@@ -192,7 +206,10 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
         log_w = log_p - log_q
         _book(trace, result_flags, log_w, log_q, log_p, defer)
         return log_w, tau, mu, None, trace, z_lab, log_q
-    if label_stride:
+    log_q_z = None
+    if result_flags['loss_required'] and _train_z(enc_rws_z):
+        z, q_probs, log_q_z = _sample_z_train(enc_rws_z, generative, x, tau, mu)
+    elif label_stride:
         z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride)
     elif enc_rws_z.can_fuse(result_flags['loss_required']):
         z, q_probs = enc_rws_z.sample_fused(x, tau, mu, generative)
@@ -202,8 +219,9 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
     w = kernels.logw_oneshot(x, post, generative, tau, mu, q_probs, z)
     log_q = w.log_q_f
     if result_flags['loss_required'] and needs_grad(enc_rws_eta, enc_rws_z):
-        log_q = (eta_log_q_torch(enc_rws_eta.params_torch(x, generative.prior_ng), tau, mu)
-                 + cat(q_probs, validate_args=False).log_prob(z).sum(-1))
+        if log_q_z is None:
+            log_q_z = cat(q_probs, validate_args=False).log_prob(z).sum(-1)
+        log_q = eta_log_q_torch(enc_rws_eta.params_torch(x, generative.prior_ng), tau, mu) + log_q_z
     _book(trace, result_flags, w.log_w, log_q, w.density, defer)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
@@ -220,7 +238,10 @@ def apg_update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_o
 def _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old, trace, result_flags, defer=False):
     post = enc_apg_eta.params(x, z_old, generative.prior_ng)
     tau, mu = _sample_eta(post)
-    if enc_apg_z.can_fuse(result_flags['loss_required']):
+    log_q_z = None
+    if result_flags['loss_required'] and _train_z(enc_apg_z):
+        z, q_probs, log_q_z = _sample_z_train(enc_apg_z, generative, x, tau, mu)
+    elif enc_apg_z.can_fuse(result_flags['loss_required']):
         z, q_probs = enc_apg_z.sample_fused(x, tau, mu, generative)
     else:
         q_probs = enc_apg_z.probs(x, tau, mu)
@@ -228,8 +249,10 @@ def _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old,
     w = kernels.logw_joint(x, post, generative, tau, mu, tau_old, mu_old, q_probs, z, z_old)
     log_q_f = w.log_q_f
     if result_flags['loss_required'] and needs_grad(enc_apg_eta, enc_apg_z):
-        log_q_f = (eta_log_q_torch(enc_apg_eta.params_torch(x, z_old, generative.prior_ng), tau, mu)
-                   + cat(q_probs, validate_args=False).log_prob(z).sum(-1))
+        if log_q_z is None:
+            log_q_z = cat(q_probs, validate_args=False).log_prob(z).sum(-1)
+        graph = enc_apg_eta.params_graph if (train_on_kernels and hasattr(enc_apg_eta, 'params_graph')) else enc_apg_eta.params_torch
+        log_q_f = eta_log_q_torch(graph(x, z_old, generative.prior_ng), tau, mu) + log_q_z
     _book(trace, result_flags, w.log_w, log_q_f, w.density, defer)
     if result_flags['mode_required']:
         # the reference's branch (objectives.py:149-155) reads an undefined name; emit what it intends
@@ -263,7 +286,8 @@ def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_fl
         w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
     log_q_f = w.log_q_f
     if result_flags['loss_required'] and needs_grad(enc_apg_eta):
-        log_q_f = eta_log_q_torch(enc_apg_eta.params_torch(x, z, generative.prior_ng), tau, mu)
+        graph = enc_apg_eta.params_graph if (train_on_kernels and hasattr(enc_apg_eta, 'params_graph')) else enc_apg_eta.params_torch
+        log_q_f = eta_log_q_torch(graph(x, z, generative.prior_ng), tau, mu)
     _book(trace, result_flags, w.log_w, log_q_f, w.density, defer)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
@@ -281,6 +305,19 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
     (posterior parameters, statistics) as the 4th value (else None)."""
     need_local = bool(result_flags['loss_required'])
     pre = None
+    if need_local and _train_z(enc_apg_z):
+        # N2: the fused forward launch + a backward kernel for the MLP gradients (train.FusedZStep)
+        from .train import FusedZStep
+        z, q_probs, log_w, density, log_w_local, log_q_local = FusedZStep.apply(*enc_apg_z.mlp(), kernels._x3(x), tau, mu,
+                                                                               z_old, generative)
+        w_local, _ = ops.local_weight_stats(log_w_local, want_w=True, want_sum=False)
+        loss = (w_local * (-log_q_local)).sum(0).sum(-1).mean()
+        trace['loss'][-1] = trace['loss'][-1] + loss.unsqueeze(0)
+        if result_flags['mode_required']:
+            trace['E_z'].append((q_probs / q_probs.sum(-1, keepdim=True)).mean(0).unsqueeze(0))
+        if result_flags['density_required']:
+            trace['density'][-1] = trace['density'][-1] + density.unsqueeze(0)
+        return log_w, z, trace, None
     if eta_heads is not None and not (result_flags['mode_required'] or need_local):
         z, q_probs, w, post, stats = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
                                                           eta_heads=eta_heads)

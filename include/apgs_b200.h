@@ -292,6 +292,39 @@ APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8
                                      float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
                                      const float* center, float* stats, int64_t label_stride, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Training mode.  The APG loss is  sum_s w_s.detach() * (-log q_s)
+ * (apgs/gmm/objectives.py:183,220), so autograd needs only the gradients of the FORWARD proposal log-densities.
+ *
+ * apgs_gmm_z_logq_backward_f32: gradients of  sum_{s,b,n} grad_logq[s,b,n] * log q(z_n | x_n, tau, mu)  w.r.t. the
+ *   Enc_apg_z MLP (apgs/gmm/models.py:97-115: W1 (H,3D), b1 (H), W2 (H), b2 (1)), where log q is
+ *   OneHotCategorical(probs=q_probs).log_prob(z) (torch's eps clamp: zero gradient outside [eps, 1-eps]).  q_probs
+ *   (S,B,N,K) are the forward kernel's (apgs_gmm_z_step_fused*_f32); the assignment comes one-hot (S,B,N,K) or as labels;
+ *   grad_logq element (r = s*B+b, n) sits at grad_logq[r*g_stride_particle + n*g_stride_point] (g_stride_point = 0: one
+ *   value per particle, the one-shot's sum over points, objectives.py:92-95).  Any of gW1/gb1/gW2/gb2 may be NULL.
+ *   Deterministic (no atomics).  workspace: apgs_gmm_z_logq_backward_workspace_bytes(S, B, H, D), 256-byte aligned.
+ *
+ * apgs_gmm_label_table_sum_f32 / _backward_f32: with one-hot z the two Linear heads of Enc_apg_eta on cat(x_n, z_n)
+ *   (models.py:56-66) take only K values per data point; the host tabulates any per-(instance, point, label) row
+ *   table (B,N,K,C) with differentiable PyTorch ops and these kernels do the only S-sized work of the eta step's graph:
+ *       out[s,b,c] = sum_n table[b, n, label(s,b,n), c]            (the neural sufficient statistics, kls_gmm.py:92-104)
+ *       grad_table[b,n,l,c] = sum_s [label(s,b,n) == l] grad_out[s,b,c]
+ *   C <= 64, K <= 255.                                                                                                  */
+APGS_API size_t apgs_gmm_z_logq_backward_workspace_bytes(int64_t S, int64_t B, int64_t H, int64_t D);
+APGS_API int apgs_gmm_z_logq_backward_f32(const float* x, const float* tau, const float* mu,
+                              const float* W1, const float* b1, const float* W2, int64_t H,
+                              const float* q_probs, const float* z_onehot, const uint8_t* z_labels, int64_t label_stride,
+                              const float* grad_logq, int64_t g_stride_particle, int64_t g_stride_point,
+                              int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              float* gW1, float* gb1, float* gW2, float* gb2,
+                              void* workspace, size_t workspace_bytes, void* stream);
+APGS_API int apgs_gmm_label_table_sum_f32(const float* table, const float* z_onehot, const uint8_t* z_labels,
+                              int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K, int64_t C,
+                              float* out, void* stream);
+APGS_API int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, const float* z_onehot, const uint8_t* z_labels,
+                              int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K, int64_t C,
+                              float* grad_table, void* stream);
+
 /* ==============================================================================================
  * Bouncing-MNIST.  FP frame pixels (96), DP digit pixels (28), K digits,
  * T frames.  The transformer is the reference's: nearest sampling, align_corners=True, diagonal theta

@@ -1,0 +1,172 @@
+"""GPU parity of the training-mode kernels: the backward kernel of the fused z step
+and the label-indexed table sums of the eta step, against PyTorch autograd through the oracle (== the reference's
+computation, apgs/gmm/models.py:56-66,102-115 + apgs/gmm/objectives.py:183,220), and the objective's training path."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gmm as og
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class _Gen:
+    def __init__(self, K=3, D=2):
+        pr = og.make_prior(K, D)
+        self.prior_alpha, self.prior_beta = pr["alpha"].to(DEV), pr["beta"].to(DEV)
+        self.prior_mu, self.prior_nu, self.prior_pi = pr["mu"].to(DEV), pr["nu"].to(DEV), pr["pi"].to(DEV)
+        self.prior_ng = (self.prior_alpha, self.prior_beta, self.prior_mu, self.prior_nu)
+
+
+def _mlp(P, grad=False):
+    p = P["enc_apg_z"]
+    return [p[k].to(DEV).requires_grad_(grad) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+
+
+def _grad_close(a, b, rtol, scale, what):
+    a, b = a.detach().cpu().double().reshape(-1), b.detach().cpu().double().reshape(-1)
+    err = (a - b).abs() - (rtol * b.abs() + 1e-5 * scale)
+    assert float(err.max()) <= 0, "%s: worst excess %g (max |diff| %g, scale %g)" % (what, float(err.max()), float((a - b).abs().max()), scale)
+
+
+@pytest.mark.parametrize("S,B,N,K,D,H,per_point", [(8, 6, 60, 3, 2, 32, True), (37, 3, 41, 4, 2, 16, True), (5, 2, 9, 3, 3, 8, False),
+                                                   (70, 2, 60, 2, 2, 10, False), (33, 1, 130, 3, 2, 32, True)])
+def test_z_logq_backward_vs_autograd(S, B, N, K, D, H, per_point):
+    """d sum(G * log q(z)) / d{W1,b1,W2,b2}: kernel vs autograd through the oracle's Enc_apg_z + OneHotCategorical.log_prob."""
+    from apgs_b200.gmm import kernels, train
+    torch.manual_seed(S + N + H)
+    P = og.make_params(K, D, H)
+    x = torch.randn(B, N, D) * 2
+    tau, mu = torch.rand(S, B, K, D) * 3 + 0.1, torch.randn(S, B, K, D) * 2
+    G = torch.randn(S, B, N) if per_point else torch.randn(S, B, 1).expand(S, B, N)
+    gen = _Gen(K, D)
+    z, q, w = kernels.z_step_fused(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), gen, want_q=True, local=True)
+    grads = train.z_logq_backward(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), q, z, G.to(DEV))
+    # labels instead of the one-hot assignment: same numbers
+    lab = z.argmax(-1).to(torch.uint8)
+    grads_l = train.z_logq_backward(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), q, lab, G.to(DEV).contiguous())
+    for a, b in zip(grads, grads_l):
+        assert torch.equal(a, b)
+    Pz = {k: v.clone().requires_grad_(True) for k, v in P["enc_apg_z"].items()}
+    xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
+    q_ref = og.enc_apg_z_probs(Pz, xs, tau, mu)
+    lq = og.z_log_q(z.cpu(), q_ref)
+    np.testing.assert_allclose(w.log_q_local.cpu().numpy(), lq.detach().numpy(), rtol=2e-5, atol=3e-6)
+    (G * lq).sum().backward()
+    names = ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")
+    scale = max(float(Pz[n].grad.abs().max()) for n in names)
+    for g, n in zip(grads, names):
+        assert tuple(g.shape) == tuple(Pz[n].grad.shape), n
+        _grad_close(g, Pz[n].grad, 2e-4, scale, n)
+
+
+def test_z_logq_backward_saturating_preactivations():
+    """pre-activations beyond the range of the factorised exponent tables take the exact path: finite, matches autograd."""
+    from apgs_b200.gmm import kernels, train
+    S, B, N, K, D, H = 9, 3, 60, 3, 2, 32
+    torch.manual_seed(3)
+    P = og.make_params(K, D, H)
+    enc = {k: v.clone() for k, v in P["enc_apg_z"].items()}
+    enc["pi_log_prob.0.weight"] = enc["pi_log_prob.0.weight"] * 10
+    x = torch.randn(B, N, D) * 40
+    x[1] = torch.randn(N, D) * 0.5
+    tau, mu = torch.rand(S, B, K, D) * 3 + 0.1, torch.randn(S, B, K, D) * 40
+    mu[:, 1] = torch.randn(S, K, D) * 0.5
+    G = torch.randn(S, B, N)
+    mlp = [enc[k].to(DEV) for k in ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")]
+    z, q, w = kernels.z_step_fused(x.to(DEV), tau.to(DEV), mu.to(DEV), mlp, _Gen(K, D), want_q=True, local=True)
+    grads = train.z_logq_backward(x.to(DEV), tau.to(DEV), mu.to(DEV), mlp, q, z, G.to(DEV))
+    assert all(bool(torch.isfinite(g).all()) for g in grads)
+    Pz = {k: v.clone().requires_grad_(True) for k, v in enc.items()}
+    q_ref = og.enc_apg_z_probs(Pz, x.unsqueeze(0).repeat(S, 1, 1, 1), tau, mu)
+    (G * og.z_log_q(z.cpu(), q_ref)).sum().backward()
+    names = ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")
+    scale = max(float(Pz[n].grad.abs().max()) for n in names)
+    for g, n in zip(grads, names):
+        _grad_close(g, Pz[n].grad, 2e-3, 10 * scale, n + " (saturating)")
+
+
+@pytest.mark.parametrize("S,B,N,K,C,labels", [(8, 6, 60, 3, 15, False), (70, 3, 41, 4, 20, True), (1, 1, 7, 2, 3, False), (200, 2, 60, 3, 15, True)])
+def test_label_table_sum_and_adjoint(S, B, N, K, C, labels):
+    from apgs_b200.gmm.train import LabelTableSum
+    torch.manual_seed(S + C)
+    tab = torch.randn(B, N, K, C, device=DEV, requires_grad=True)
+    lab = torch.randint(0, K, (S, B, N), device=DEV)
+    z = lab.to(torch.uint8) if labels else torch.nn.functional.one_hot(lab, K).float()
+    out = LabelTableSum.apply(tab, z)
+    idx = lab.permute(1, 2, 0)                                            # (B,N,S)
+    ref = torch.gather(tab.detach().double().unsqueeze(0).expand(S, B, N, K, C), 3,
+                       lab.view(S, B, N, 1, 1).expand(S, B, N, 1, C)).squeeze(3).sum(2)
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+    g = torch.randn(S, B, C, device=DEV)
+    (out * g).sum().backward()
+    t2 = tab.detach().clone().requires_grad_(True)
+    out2 = torch.gather(t2.unsqueeze(0).expand(S, B, N, K, C), 3, lab.view(S, B, N, 1, 1).expand(S, B, N, 1, C)).squeeze(3).sum(2)
+    (out2 * g).sum().backward()
+    torch.testing.assert_close(tab.grad, t2.grad, rtol=1e-4, atol=1e-4)
+    assert idx.shape == (B, N, S)
+
+
+def test_eta_params_graph_matches_params_torch_and_gradients():
+    """Enc_apg_eta.params_graph (per-instance head table + LabelTableSum) == params_torch (per-particle heads), values
+    and parameter gradients of a log q loss."""
+    from apgs_b200.gmm import models as M
+    K, D, S, B, N = 3, 2, 12, 5, 60
+    torch.manual_seed(0)
+    (enc_rws_eta, enc_apg_z, enc_apg_eta, gen), _ = M.init_apg_models(K, D, 32, True, DEV, lr=1e-3)
+    x = og.simulate(B, N, K, D).to(DEV)
+    z = torch.nn.functional.one_hot(torch.randint(0, K, (S, B, N), device=DEV), K).float()
+    z[1, 0] = torch.nn.functional.one_hot(torch.zeros(N, dtype=torch.long, device=DEV), K).float()        # empty clusters (Q1)
+    tau, mu = torch.rand(S, B, K, D, device=DEV) + 0.5, torch.randn(S, B, K, D, device=DEV)
+    wgt = torch.rand(S, B, device=DEV)
+    out = {}
+    for name, fn in (("graph", enc_apg_eta.params_graph), ("torch", enc_apg_eta.params_torch)):
+        for p in enc_apg_eta.parameters():
+            p.grad = None
+        post = fn(x, z, gen.prior_ng)
+        loss = (wgt * (-M.eta_log_q_torch(post, tau, mu))).sum()
+        loss.backward()
+        out[name] = ([v.detach() for v in post], float(loss), [p.grad.clone() for p in enc_apg_eta.parameters()])
+    for a, b in zip(out["graph"][0], out["torch"][0]):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(out["graph"][1], out["torch"][1], rtol=1e-4)
+    scale = max(float(g.abs().max()) for g in out["torch"][2])
+    for a, b in zip(out["graph"][2], out["torch"][2]):
+        _grad_close(a, b, 2e-3, scale, "eta head gradient")
+
+
+def test_objective_training_path_runs_on_the_kernels_and_matches_the_torch_graph():
+    """apg_objective with loss_required: the kernel-backed graph (train_on_kernels) gives the loss and the gradients of the
+    PyTorch-encoder graph on the same draws (same seed -> same random numbers: both paths draw uniforms / gamma / normal
+    variates with the same calls in the same order)."""
+    from apgs_b200.gmm import models as M, objectives as O
+    from apgs_b200.resampler import Resampler
+    from apgs_b200 import ops
+    S, B, sweeps = 20, 8, 3
+    flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
+    torch.manual_seed(0)
+    models, opt = M.init_apg_models(3, 2, 32, True, DEV, lr=1e-3)
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    res = {}
+    for on in (True, False):
+        O.train_on_kernels = on
+        try:
+            for m in models[:3]:
+                for p in m.parameters():
+                    p.grad = None
+            ops.PROFILE.reset(events=False)
+            torch.manual_seed(7)
+            tr = O.apg_objective(models, x, flags, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
+            tr["loss"].sum().backward()
+            res[on] = (tr["loss"].detach().clone(), tr["ess"].clone(), [p.grad.clone() for m in models[:3] for p in m.parameters()],
+                       ops.PROFILE.launches)
+        finally:
+            O.train_on_kernels = True
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=2e-4, atol=1e-4)
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=1e-4)
+    scale = max(float(g.abs().max()) for g in res[False][2])
+    for a, b in zip(res[True][2], res[False][2]):
+        _grad_close(a, b, 5e-3, scale, "objective gradient")
+    assert res[True][3] > res[False][3]            # more of the step runs in this repo's kernels
