@@ -15,6 +15,7 @@
 //                        of that table: the only S-sized work of the eta step's graph is this pair of kernels.
 //
 // Deterministic: partial sums travel through shared / global arrays and are combined in a fixed order (no atomics).
+#include <stdlib.h>
 #include "gmm_common.cuh"
 
 namespace apgs {
@@ -30,6 +31,7 @@ struct ZBwdArgs {
     const float* g;                     // upstream gradient d loss / d log q[r, n]
     long long g_sr, g_sn;               // element (r, n) at g[r * g_sr + n * g_sn]  (g_sn = 0: one value per particle)
     int S, B, N, H, chunks;             // chunks of kZP particles handled by one CTA
+    int force_point_major;              // tests: run the generic point-major kernel even when H <= 32
     float* partial;                     // [gridDim.y * gridDim.x][GS]
 };
 
@@ -227,6 +229,207 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd(ZBwdArgs a) {
     }
 }
 
+// ---- hidden-unit-major variant (H <= 8 HQ): lane j of a particle OWNS the hidden units h = j HQ .. j HQ + HQ - 1 and walks
+// all N points of the particle, so every accumulator is private to its thread for the whole chunk: no shuffles in the
+// main loop (the point-major kernel above spends ~30 % of its instructions reducing 6 sums per hidden unit across the
+// warp).  The upstream-gradient factors g[n][k] of a particle are staged once in shared memory by its 8 lanes; Ex is laid
+// out [n][h] so that a lane reads its HQ units with one vector load.  Per-thread totals live in shared memory slots owned
+// by the thread (no atomics); the CTA's particles are combined in a fixed order at the end.
+template <int K, int D, int HQ>
+__global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    constexpr int KD = K * D, V = ZBwdV<D>::V, H8 = HQ * kZL, NT = kZP * kZL;
+    const int N = a.N, H = a.H;
+    float* s_ex = smf;                                   // [N][H8]   Ex (or raw xh' when the CTA is not `xok`)
+    float* s_x = s_ex + (size_t)N * H8;                  // [N][D] (+pad)
+    float* s_g = s_x + (size_t)((N * D + 3) / 4 * 4);    // [kZP][N*K]
+    float* s_tot = s_g + (size_t)kZP * ((N * K + 3) / 4 * 4);     // [NT][HQ*V]
+    __shared__ int s_xok;
+    __shared__ float s_gb2[NT / 32];
+    const int GP = (N * K + 3) / 4 * 4;
+    const int b = blockIdx.x;
+    const int p = threadIdx.x / kZL, j = threadIdx.x % kZL, lane = threadIdx.x & 31;
+    const float* xb = a.x + (size_t)b * N * D;
+    if (threadIdx.x == 0) s_xok = 1;
+    for (int i = threadIdx.x; i < N * D; i += NT) s_x[i] = __ldg(xb + i);
+    float* tot = s_tot + (size_t)threadIdx.x * (HQ * V);
+#pragma unroll
+    for (int i = 0; i < HQ * V; ++i) tot[i] = 0.f;
+    __syncthreads();
+    bool okx = true;
+    for (int idx = threadIdx.x; idx < N * H8; idx += NT) {
+        const int n = idx / H8, h = idx - n * H8;
+        float acc = 0.f;
+        if (h < H) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc = fmaf(TANH_PRESCALE * __ldg(a.W1 + h * 3 * D + d), s_x[n * D + d], acc);
+            if (!(fabsf(acc) <= 126.f)) okx = false;
+        }
+        s_ex[idx] = acc;
+    }
+    if (!okx) s_xok = 0;
+    __syncthreads();
+    const bool xok = s_xok != 0;
+    if (xok)
+        for (int idx = threadIdx.x; idx < N * H8; idx += NT) s_ex[idx] = ex2_ftz(s_ex[idx]);
+    __syncthreads();
+    // this lane's hidden units: first-layer weights of the particle part, output weight is applied by the finishing kernel
+    float wm[HQ][D], wt[HQ][D], bh[HQ];
+#pragma unroll
+    for (int i = 0; i < HQ; ++i) {
+        const int h = j * HQ + i;
+        bh[i] = (h < H) ? __ldg(a.b1 + h) : 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            wm[i][d] = (h < H) ? __ldg(a.W1 + h * 3 * D + D + d) : 0.f;
+            wt[i][d] = (h < H) ? __ldg(a.W1 + h * 3 * D + 2 * D + d) : 0.f;
+        }
+    }
+    float gb2 = 0.f;
+    float* gp = s_g + (size_t)p * GP;
+    for (int c = 0; c < a.chunks; ++c) {
+        const long long s = ((long long)blockIdx.y * a.chunks + c) * kZP + p;
+        const bool valid = s < a.S;
+        const long long r = s * a.B + b;
+        float tk[KD], mk[KD];
+#pragma unroll
+        for (int e = 0; e < KD; ++e) { tk[e] = valid ? __ldg(a.tau + r * KD + e) : 1.f; mk[e] = valid ? __ldg(a.mu + r * KD + e) : 0.f; }
+        float ee[HQ][K];
+        bool oke = true;
+#pragma unroll
+        for (int i = 0; i < HQ; ++i)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float acc = bh[i];
+#pragma unroll
+                for (int d = 0; d < D; ++d) { acc = fmaf(wm[i][d], mk[k * D + d], acc); acc = fmaf(wt[i][d], tk[k * D + d], acc); }
+                ee[i][k] = TANH_PRESCALE * acc;
+                if (!(fabsf(ee[i][k]) <= 126.f)) oke = false;
+            }
+#pragma unroll
+        for (int o = kZL / 2; o > 0; o >>= 1) oke = (__shfl_xor_sync(0xffffffffu, (int)oke, o) != 0) && oke;
+        const bool fast = xok && oke;
+        if (fast) {
+#pragma unroll
+            for (int i = 0; i < HQ; ++i)
+#pragma unroll
+                for (int k = 0; k < K; ++k) ee[i][k] = ex2_ftz(ee[i][k]);
+        }
+        // ---- the particle's lanes stage g[n][k] = upstream * ((k == z_n) - q_nk) (zero outside the clamp / for dead particles)
+        __syncwarp();
+        for (int n = j; n < N; n += kZL) {
+            float gk[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) gk[k] = 0.f;
+            if (valid) {
+                float qv[K], sq = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { qv[k] = __ldg(a.q + (r * N + n) * K + k); sq = __fadd_rn(sq, qv[k]); }
+                int lf = 0;
+                if (a.zl != nullptr) {
+                    lf = min((int)__ldg(a.zl + r * a.LN + n), K - 1);
+                } else {
+                    float best = __ldg(a.z + (r * N + n) * K);
+#pragma unroll
+                    for (int k = 1; k < K; ++k) { const float v = __ldg(a.z + (r * N + n) * K + k); if (v > best) { best = v; lf = k; } }
+                }
+                float ql = qv[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) if (lf == k) ql = qv[k];
+                const float pn = __fdiv_rn(ql, sq);
+                const bool inside = pn >= FLT_EPS_F && pn <= 1.f - FLT_EPS_F;
+                const float up = inside ? __ldg(a.g + r * a.g_sr + n * a.g_sn) : 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { gk[k] = up * (((k == lf) ? 1.f : 0.f) - qv[k]); gb2 += gk[k]; }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) gp[n * K + k] = gk[k];
+        }
+        __syncwarp();
+        // ---- all points x this lane's hidden units
+        float G2[HQ], A[HQ][K], X[HQ][D];
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) {
+            G2[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) A[i][k] = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) X[i][d] = 0.f;
+        }
+        if (valid) {
+#pragma unroll 2
+            for (int n = 0; n < N; ++n) {
+                float g[K], xn[D], ex[HQ];
+#pragma unroll
+                for (int k = 0; k < K; ++k) g[k] = gp[n * K + k];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xn[d] = s_x[n * D + d];
+                if (HQ == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(s_ex + (size_t)n * H8 + j * HQ);
+                    ex[0] = v.x; ex[1] = v.y; ex[2 % HQ] = v.z; ex[3 % HQ] = v.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < HQ; ++i) ex[i] = s_ex[(size_t)n * H8 + j * HQ + i];
+                }
+#pragma unroll
+                for (int i = 0; i < HQ; ++i) {
+                    float sn = 0.f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const float y = fast ? fmaf(ex[i], ee[i][k], 1.f) : (ex2_ftz((xok ? 0.f : ex[i]) + ee[i][k]) + 1.f);
+                        const float rr = rcp_ftz(y);
+                        const float t = fmaf(-2.f, rr, 1.f);
+                        const float v = fmaf(-rr, rr, rr);
+                        const float cc = g[k] * v;
+                        G2[i] = fmaf(g[k], t, G2[i]);
+                        A[i][k] += cc;
+                        sn += cc;
+                    }
+#pragma unroll
+                    for (int d = 0; d < D; ++d) X[i][d] = fmaf(sn, xn[d], X[i][d]);
+                }
+            }
+        }
+        // ---- fold the particle's tau / mu in and add to this thread's totals
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) {
+            float* t = tot + i * V;
+            float sb = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) sb += A[i][k];
+            t[0] += G2[i];
+            t[1] += sb;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                float m = 0.f, tt = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) { m = fmaf(A[i][k], mk[k * D + d], m); tt = fmaf(A[i][k], tk[k * D + d], tt); }
+                t[2 + d] += X[i][d]; t[2 + D + d] += m; t[2 + 2 * D + d] += tt;
+            }
+        }
+    }
+    gb2 = warp_sum(gb2);
+    if (lane == 0) s_gb2[threadIdx.x >> 5] = gb2;
+    __syncthreads();
+    // ---- the CTA's particles in a fixed order; partial row layout [h][V] + db2, as the point-major kernel
+    const int GS = H * V + 1;
+    float* out = a.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * GS;
+    for (int idx = threadIdx.x; idx < H8 * V; idx += NT) {
+        const int h = idx / V, v = idx - h * V;
+        if (h >= H) continue;
+        const int jj = h / HQ, i = h - jj * HQ;
+        float sum = 0.f;
+        for (int pp = 0; pp < kZP; ++pp) sum += s_tot[(size_t)(pp * kZL + jj) * (HQ * V) + i * V + v];
+        out[h * V + v] = sum;
+    }
+    if (threadIdx.x == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) sum += s_gb2[w];
+        out[H * V] = sum;
+    }
+}
+
 // rows [M][GS] -> [NC1][GS] doubles (CTA c sums rows c, c + NC1, ...), then one CTA finishes
 __global__ void k_reduce_rows_stage1(const float* __restrict__ part, long long M, int GS, double* __restrict__ ws) {
     for (int col = threadIdx.x; col < GS; col += blockDim.x) {
@@ -276,9 +479,20 @@ static int launch_z_bwd(ZBwdArgs a, float* gW1, float* gb1, float* gW2, float* g
         return fail(APGS_E_WORKSPACE, "gmm_z_logq_backward: workspace of %zu bytes required, got %zu", need, ws_bytes);
     a.partial = reinterpret_cast<float*>(ws);
     double* ws2 = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + (((size_t)M * GS * sizeof(float) + 255) & ~(size_t)255));
-    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_gmm_z_logq_bwd<K, D>), smem), "smem attr");
-    k_gmm_z_logq_bwd<K, D><<<dim3((unsigned int)a.B, (unsigned int)gy), kZP * kZL, smem, st>>>(a);
-    APGS_LAUNCH_OK("k_gmm_z_logq_bwd launch");
+    // hidden-unit-major variant for H <= 32 (the reference's 32): no cross-lane reductions in the main loop
+    const int HQ = a.H <= 8 ? 1 : (a.H <= 16 ? 2 : 4);
+    const size_t smem_t = ((size_t)a.N * HQ * kZL + (size_t)((a.N * D + 3) / 4 * 4) + (size_t)kZP * ((a.N * K + 3) / 4 * 4) +
+                           (size_t)kZP * kZL * HQ * V) * 4;
+    if (a.H <= 32 && smem_t <= 200 * 1024 && !a.force_point_major) {
+        void (*kern)(ZBwdArgs) = HQ == 1 ? k_gmm_z_logq_bwd_t<K, D, 1> : (HQ == 2 ? k_gmm_z_logq_bwd_t<K, D, 2> : k_gmm_z_logq_bwd_t<K, D, 4>);
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_t), "smem attr");
+        kern<<<dim3((unsigned int)a.B, (unsigned int)gy), kZP * kZL, smem_t, st>>>(a);
+        APGS_LAUNCH_OK("k_gmm_z_logq_bwd_t launch");
+    } else {
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_gmm_z_logq_bwd<K, D>), smem), "smem attr");
+        k_gmm_z_logq_bwd<K, D><<<dim3((unsigned int)a.B, (unsigned int)gy), kZP * kZL, smem, st>>>(a);
+        APGS_LAUNCH_OK("k_gmm_z_logq_bwd launch");
+    }
     k_reduce_rows_stage1<<<kRedCtas, 256, 0, st>>>(a.partial, M, GS, ws2);
     APGS_LAUNCH_OK("k_reduce_rows_stage1 launch");
     k_z_bwd_finish<D><<<1, 256, 0, st>>>(ws2, kRedCtas, a.H, a.W2, gW1, gb1, gW2, gb2);
@@ -348,8 +562,11 @@ __global__ void __launch_bounds__(256) k_label_table_sum_bwd(LtsArgs a) {
     float* s_go = s_g + NKC;
     unsigned char* s_lab = reinterpret_cast<unsigned char*>(s_go + kLtsTile * C);
     for (int i = threadIdx.x; i < NKC; i += blockDim.x) s_g[i] = 0.f;
-    for (int s0 = 0; s0 < a.S; s0 += kLtsTile) {
-        const int ns = min(kLtsTile, a.S - s0);
+    // gridDim.y CTAs share the particles of the instance; each writes its own partial table (summed by the caller)
+    const int per = (a.S + gridDim.y - 1) / gridDim.y;
+    const int s_begin = blockIdx.y * per, s_end = min(a.S, s_begin + per);
+    for (int s0 = s_begin; s0 < s_end; s0 += kLtsTile) {
+        const int ns = min(kLtsTile, s_end - s0);
         __syncthreads();
         for (int i = threadIdx.x; i < ns * C; i += blockDim.x) {
             const int si = i / C, c = i - si * C;
@@ -366,7 +583,7 @@ __global__ void __launch_bounds__(256) k_label_table_sum_bwd(LtsArgs a) {
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NKC; i += blockDim.x) a.gtab[(size_t)b * NKC + i] = s_g[i];
+    for (int i = threadIdx.x; i < NKC; i += blockDim.x) a.gtab[((size_t)blockIdx.y * a.B + b) * NKC + i] = s_g[i];
 }
 
 }  // namespace apgs
@@ -397,6 +614,10 @@ extern "C" int apgs_gmm_z_logq_backward_f32(const float* x, const float* tau, co
     a.x = x; a.tau = tau; a.mu = mu; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.q = q_probs; a.z = z_onehot; a.zl = z_labels;
     a.LN = label_stride; a.g = grad_logq; a.g_sr = g_stride_particle; a.g_sn = g_stride_point;
     a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
+    {   // test hook: APGS_ZBWD_POINT_MAJOR=1 runs the generic point-major kernel even when H <= 32
+        const char* e = getenv("APGS_ZBWD_POINT_MAJOR");
+        a.force_point_major = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 3 && D == 2) return launch_z_bwd<3, 2>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
     if (K == 2 && D == 2) return launch_z_bwd<2, 2>(a, gW1, gb1, gW2, gb2, workspace, workspace_bytes, st);
@@ -439,6 +660,13 @@ extern "C" int apgs_gmm_label_table_sum_f32(const float* table, const float* z_o
     return 0;
 }
 
+extern "C" int apgs_gmm_label_table_sum_backward_splits(int64_t S, int64_t B) {
+    // enough CTAs for ~4 waves on the SMs, at least one tile of particles each
+    long long sp = 1;
+    while (sp < 16 && B * sp < 4LL * sm_count() && S / (sp * 2) >= kLtsTile) sp *= 2;
+    return (int)sp;
+}
+
 extern "C" int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, const float* z_onehot, const uint8_t* z_labels,
                                                      int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K,
                                                      int64_t C, float* grad_table, void* stream) {
@@ -450,7 +678,8 @@ extern "C" int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, cons
     const size_t smem = ((size_t)N * K * C + (size_t)kLtsTile * C) * 4 + (size_t)kLtsTile * N;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_label_table_sum_backward: N K C too large for shared memory");
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_label_table_sum_bwd), smem), "smem attr");
-    k_label_table_sum_bwd<<<(unsigned int)B, 256, smem, (cudaStream_t)stream>>>(a);
+    const int splits = apgs_gmm_label_table_sum_backward_splits(S, B);     // grad_table holds `splits` partial tables
+    k_label_table_sum_bwd<<<dim3((unsigned int)B, (unsigned int)splits), 256, smem, (cudaStream_t)stream>>>(a);
     APGS_LAUNCH_OK("k_label_table_sum_bwd launch");
     return 0;
 }

@@ -97,12 +97,13 @@ def label_table_sum_backward(grad_out, z, N, K):
     g = _req(grad_out, "grad_out", ndim=3)
     S, B, Cc = g.shape
     labels = z.dtype == torch.uint8
-    gt = torch.empty(B, N, K, Cc, dtype=torch.float32, device=g.device)
+    P = int(lib.apgs_gmm_label_table_sum_backward_splits(S, B))     # partial tables, one per slice of the particles
+    gt = torch.empty(P, B, N, K, Cc, dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device), _call("gmm_label_table_sum_backward", 1, S * B * ((N if labels else 4 * N * K) + 4 * Cc)):
         check(lib.apgs_gmm_label_table_sum_backward_f32(ptr(g), None if labels else ptr(z), ptr(z) if labels else None,
                                                         z.shape[-1] if labels else 0, S, B, N, K, Cc, ptr(gt), _stream()),
               "apgs_gmm_label_table_sum_backward_f32")
-    return gt
+    return gt[0] if P == 1 else gt.sum(0)
 
 
 class LabelTableSum(torch.autograd.Function):

@@ -309,7 +309,8 @@ APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8
  *   table (B,N,K,C) with differentiable PyTorch ops and these kernels do the only S-sized work of the eta step's graph:
  *       out[s,b,c] = sum_n table[b, n, label(s,b,n), c]            (the neural sufficient statistics, kls_gmm.py:92-104)
  *       grad_table[b,n,l,c] = sum_s [label(s,b,n) == l] grad_out[s,b,c]
- *   C <= 64, K <= 255.                                                                                                  */
+ *   C <= 64, K <= 255.  The adjoint splits the particles of an instance over P = apgs_gmm_label_table_sum_backward_splits
+ *   (S, B) CTAs: grad_table is (P,B,N,K,C), P partial tables the caller adds up (deterministic, no atomics).           */
 APGS_API size_t apgs_gmm_z_logq_backward_workspace_bytes(int64_t S, int64_t B, int64_t H, int64_t D);
 APGS_API int apgs_gmm_z_logq_backward_f32(const float* x, const float* tau, const float* mu,
                               const float* W1, const float* b1, const float* W2, int64_t H,
@@ -321,6 +322,7 @@ APGS_API int apgs_gmm_z_logq_backward_f32(const float* x, const float* tau, cons
 APGS_API int apgs_gmm_label_table_sum_f32(const float* table, const float* z_onehot, const uint8_t* z_labels,
                               int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K, int64_t C,
                               float* out, void* stream);
+APGS_API int apgs_gmm_label_table_sum_backward_splits(int64_t S, int64_t B);
 APGS_API int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, const float* z_onehot, const uint8_t* z_labels,
                               int64_t label_stride, int64_t S, int64_t B, int64_t N, int64_t K, int64_t C,
                               float* grad_table, void* stream);

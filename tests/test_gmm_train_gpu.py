@@ -31,7 +31,8 @@ def _grad_close(a, b, rtol, scale, what):
 
 
 @pytest.mark.parametrize("S,B,N,K,D,H,per_point", [(8, 6, 60, 3, 2, 32, True), (37, 3, 41, 4, 2, 16, True), (5, 2, 9, 3, 3, 8, False),
-                                                   (70, 2, 60, 2, 2, 10, False), (33, 1, 130, 3, 2, 32, True)])
+                                                   (70, 2, 60, 2, 2, 10, False), (33, 1, 130, 3, 2, 32, True), (9, 2, 60, 3, 2, 48, True),
+                                                   (1000, 4, 60, 3, 2, 32, True)])
 def test_z_logq_backward_vs_autograd(S, B, N, K, D, H, per_point):
     """d sum(G * log q(z)) / d{W1,b1,W2,b2}: kernel vs autograd through the oracle's Enc_apg_z + OneHotCategorical.log_prob."""
     from apgs_b200.gmm import kernels, train
@@ -43,6 +44,16 @@ def test_z_logq_backward_vs_autograd(S, B, N, K, D, H, per_point):
     gen = _Gen(K, D)
     z, q, w = kernels.z_step_fused(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), gen, want_q=True, local=True)
     grads = train.z_logq_backward(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), q, z, G.to(DEV))
+    # the generic point-major kernel (H > 32 takes it anyway) agrees with the hidden-unit-major one
+    import os
+    os.environ["APGS_ZBWD_POINT_MAJOR"] = "1"
+    try:
+        grads_pm = train.z_logq_backward(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), q, z, G.to(DEV))
+    finally:
+        del os.environ["APGS_ZBWD_POINT_MAJOR"]
+    sc = max(float(g.abs().max()) for g in grads)
+    for a, b in zip(grads, grads_pm):
+        _grad_close(a, b, 1e-4, sc, "point-major vs hidden-unit-major")
     # labels instead of the one-hot assignment: same numbers
     lab = z.argmax(-1).to(torch.uint8)
     grads_l = train.z_logq_backward(x.to(DEV), tau.to(DEV), mu.to(DEV), _mlp(P), q, lab, G.to(DEV).contiguous())
