@@ -63,7 +63,8 @@ def test_z_logq_backward_vs_autograd(S, B, N, K, D, H, per_point):
     xs = x.unsqueeze(0).repeat(S, 1, 1, 1)
     q_ref = og.enc_apg_z_probs(Pz, xs, tau, mu)
     lq = og.z_log_q(z.cpu(), q_ref)
-    np.testing.assert_allclose(w.log_q_local.cpu().numpy(), lq.detach().numpy(), rtol=2e-5, atol=3e-6)
+    # q_probs agree to 2e-5 relative (SFU exp / rcp in the fused MLP), i.e. log q to 2e-5 ABSOLUTE whatever its magnitude
+    np.testing.assert_allclose(w.log_q_local.cpu().numpy(), lq.detach().numpy(), rtol=2e-5, atol=2.5e-5)
     (G * lq).sum().backward()
     names = ("pi_log_prob.0.weight", "pi_log_prob.0.bias", "pi_log_prob.2.weight", "pi_log_prob.2.bias")
     scale = max(float(Pz[n].grad.abs().max()) for n in names)
