@@ -229,6 +229,46 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd(ZBwdArgs a) {
     }
 }
 
+// all points of one particle x the HQ hidden units of one lane.  FAST: y = Ex * Ee + 1 from the factorised tables; else the
+// exact form y = 2^(xh' + e') + 1 (s_ex holds the raw xh' when the CTA is not `xok`; see the note in the point-major kernel)
+template <int K, int D, int HQ, bool FAST>
+__device__ __forceinline__ void zbwd_points(int N, const float* __restrict__ gp, const float* __restrict__ s_x,
+                                            const float* __restrict__ exl, int H8, const float (&ee)[HQ][K], bool xok,
+                                            float (&G2)[HQ], float (&A)[HQ][K], float (&X)[HQ][D]) {
+#pragma unroll 2
+    for (int n = 0; n < N; ++n) {
+        float g[K], xn[D], ex[HQ];
+#pragma unroll
+        for (int k = 0; k < K; ++k) g[k] = gp[n * K + k];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d] = s_x[n * D + d];
+        if (HQ == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(exl + (size_t)n * H8);
+            ex[0] = v.x; ex[1 % HQ] = v.y; ex[2 % HQ] = v.z; ex[3 % HQ] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < HQ; ++i) ex[i] = exl[(size_t)n * H8 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < HQ; ++i) {
+            float sn = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float y = FAST ? fmaf(ex[i], ee[i][k], 1.f) : (ex2_ftz((xok ? 0.f : ex[i]) + ee[i][k]) + 1.f);
+                const float rr = rcp_ftz(y);
+                const float t = fmaf(-2.f, rr, 1.f);
+                const float v = fmaf(-rr, rr, rr);
+                const float cc = g[k] * v;
+                G2[i] = fmaf(g[k], t, G2[i]);
+                A[i][k] += cc;
+                sn += cc;
+            }
+#pragma unroll
+            for (int d = 0; d < D; ++d) X[i][d] = fmaf(sn, xn[d], X[i][d]);
+        }
+    }
+}
+
 // ---- hidden-unit-major variant (H <= 8 HQ): lane j of a particle OWNS the hidden units h = j HQ .. j HQ + HQ - 1 and walks
 // all N points of the particle, so every accumulator is private to its thread for the whole chunk: no shuffles in the
 // main loop (the point-major kernel above spends ~30 % of its instructions reducing 6 sums per hidden unit across the
@@ -357,38 +397,9 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
             for (int d = 0; d < D; ++d) X[i][d] = 0.f;
         }
         if (valid) {
-#pragma unroll 2
-            for (int n = 0; n < N; ++n) {
-                float g[K], xn[D], ex[HQ];
-#pragma unroll
-                for (int k = 0; k < K; ++k) g[k] = gp[n * K + k];
-#pragma unroll
-                for (int d = 0; d < D; ++d) xn[d] = s_x[n * D + d];
-                if (HQ == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(s_ex + (size_t)n * H8 + j * HQ);
-                    ex[0] = v.x; ex[1] = v.y; ex[2 % HQ] = v.z; ex[3 % HQ] = v.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < HQ; ++i) ex[i] = s_ex[(size_t)n * H8 + j * HQ + i];
-                }
-#pragma unroll
-                for (int i = 0; i < HQ; ++i) {
-                    float sn = 0.f;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float y = fast ? fmaf(ex[i], ee[i][k], 1.f) : (ex2_ftz((xok ? 0.f : ex[i]) + ee[i][k]) + 1.f);
-                        const float rr = rcp_ftz(y);
-                        const float t = fmaf(-2.f, rr, 1.f);
-                        const float v = fmaf(-rr, rr, rr);
-                        const float cc = g[k] * v;
-                        G2[i] = fmaf(g[k], t, G2[i]);
-                        A[i][k] += cc;
-                        sn += cc;
-                    }
-#pragma unroll
-                    for (int d = 0; d < D; ++d) X[i][d] = fmaf(sn, xn[d], X[i][d]);
-                }
-            }
+            // two copies of the loop: the per-particle `fast` flag must not put a second MUFU (ex2) into every term
+            if (fast) zbwd_points<K, D, HQ, true>(N, gp, s_x, s_ex + j * HQ, H8, ee, true, G2, A, X);
+            else zbwd_points<K, D, HQ, false>(N, gp, s_x, s_ex + j * HQ, H8, ee, xok, G2, A, X);
         }
         // ---- fold the particle's tau / mu in and add to this thread's totals
 #pragma unroll
