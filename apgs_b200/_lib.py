@@ -102,6 +102,7 @@ SIGNATURES = {
     "apgs_gmm_z_logq_backward_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "apgs_gmm_z_logq_backward_f32": (_int, [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64,
                                             _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "apgs_gmm_eta_logq_jac_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "apgs_gmm_label_table_sum_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_gmm_label_table_sum_backward_splits": (_int, [_i64, _i64]),
     "apgs_gmm_label_table_sum_backward_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),

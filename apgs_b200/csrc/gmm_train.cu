@@ -597,6 +597,65 @@ __global__ void __launch_bounds__(256) k_label_table_sum_bwd(LtsArgs a) {
     for (int i = threadIdx.x; i < NKC; i += blockDim.x) a.gtab[((size_t)blockIdx.y * a.B + b) * NKC + i] = s_g[i];
 }
 
+
+// ================================================================================================================
+// log q(tau, mu | neural statistics) of Enc_apg_eta and its Jacobian w.r.t. the statistics (eta step graph)
+//   nss[r] = { s1_k (K), s2_kd (K D), s3_kd (K D) }  ->  Normal-Gamma update (kls_gmm.py:106-119, quirks Q1 / Q2)
+//   log q = sum_kd [ Gamma(alpha, beta).log_prob(tau) + Normal(m, 1/sqrt(nu tau)).log_prob(mu) ]  (objectives.py:167)
+//   jac[r][c] = d log q[r] / d nss[r][c]   (zero for a count that quirk Q1 replaced)
+// One thread per particle; replaces ~150 elementwise PyTorch launches (forward + autograd) per eta step.
+// ================================================================================================================
+__device__ __forceinline__ float digamma_pos(float x) {
+    // psi(x) = psi(x + n) - sum_{i<n} 1/(x + i), then the asymptotic series at y >= 6 (next term 1/(240 y^8) < 3e-9)
+    float acc = 0.f;
+    while (x < 6.f) { acc += __fdiv_rn(1.f, x); x += 1.f; }
+    const float r = __fdiv_rn(1.f, x), r2 = r * r;
+    const float series = r2 * (0.0833333333333f - r2 * (0.00833333333333f - r2 * 0.00396825396825f));
+    return logf(x) - 0.5f * r - series - acc;
+}
+
+template <int K, int D>
+__global__ void __launch_bounds__(256) k_gmm_eta_logq_jac(const float* __restrict__ nss, const float* __restrict__ tau,
+                                                          const float* __restrict__ mu, const float* __restrict__ ra,
+                                                          const float* __restrict__ rb, const float* __restrict__ rm,
+                                                          const float* __restrict__ rn, long long R,
+                                                          float* __restrict__ lq_out, float* __restrict__ jac) {
+    constexpr int KD = K * D, C = K + 2 * KD;
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* s = nss + r * C;
+    float lq = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float s1 = __ldg(s + k);
+        const bool replaced = s1 == 0.f;                                     // Q1
+        const float c = replaced ? 1.f : s1;
+        float gc = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int e = k * D + d;
+            const float s2 = __ldg(s + K + e), s3 = __ldg(s + K + KD + e);
+            const float a0 = __ldg(ra + e), b0 = __ldg(rb + e), m0 = __ldg(rm + e), n0 = __ldg(rn + e);
+            const float t = __ldg(tau + r * KD + e), u = __ldg(mu + r * KD + e);
+            const float cn = c + n0, xb = s2 / c, A = c * n0 / cn, dx = xb - n0;      // Q2: (x_bar - prior_nu)
+            const float alpha = a0 + 0.5f * c, nu = n0 + c, m = (m0 * n0 + s2) / cn;
+            const float beta = b0 + 0.5f * (s3 - s2 * s2 / c) + 0.5f * A * dx * dx;
+            const float lbeta = logf(beta), lt = logf(t), dm_ = u - m;
+            lq += (alpha * lbeta + (alpha - 1.f) * lt - beta * t - lgammaf(alpha))
+                  + (-0.5f * dm_ * dm_ * nu * t + 0.5f * logf(nu * t) - LOG_SQRT_2PI_F);
+            const float g_alpha = lbeta + lt - digamma_pos(alpha);
+            const float g_beta = alpha / beta - t;
+            const float g_m = dm_ * nu * t;
+            const float g_nu = -0.5f * dm_ * dm_ * t + 0.5f / nu;
+            jac[r * C + K + KD + e] = 0.5f * g_beta;                                               // d / d s3
+            jac[r * C + K + e] = g_beta * (-xb + A * dx / c) + g_m / cn;                           // d / d s2
+            gc += 0.5f * g_alpha + g_nu - g_m * m / cn
+                  + g_beta * (0.5f * s2 * s2 / (c * c) + 0.5f * (n0 * n0 / (cn * cn)) * dx * dx - A * dx * xb / c);
+        }
+        jac[r * C + k] = replaced ? 0.f : gc;                                                      // d / d s1
+    }
+    lq_out[r] = lq;
+}
 }  // namespace apgs
 
 using namespace apgs;
@@ -693,4 +752,24 @@ extern "C" int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, cons
     k_label_table_sum_bwd<<<dim3((unsigned int)B, (unsigned int)splits), 256, smem, (cudaStream_t)stream>>>(a);
     APGS_LAUNCH_OK("k_label_table_sum_bwd launch");
     return 0;
+}
+
+extern "C" int apgs_gmm_eta_logq_jac_f32(const float* nss, const float* tau, const float* mu, const float* prior_alpha,
+                                         const float* prior_beta, const float* prior_mu, const float* prior_nu, int64_t S,
+                                         int64_t B, int64_t K, int64_t D, float* log_q, float* jac, void* stream) {
+    if (S <= 0 || B <= 0 || S * B >= (1ll << 40)) return fail(APGS_E_SHAPE, "gmm_eta_logq_jac: bad sizes S=%lld B=%lld", (long long)S, (long long)B);
+    if (!nss || !tau || !mu || !prior_alpha || !prior_beta || !prior_mu || !prior_nu || !log_q || !jac)
+        return fail(APGS_E_BADARG, "gmm_eta_logq_jac: NULL pointer");
+    const long long R = S * B;
+    const unsigned int grid = (unsigned int)((R + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define APGS_ELQ(K_, D_)                                                                                                 \
+    if (K == K_ && D == D_) {                                                                                            \
+        k_gmm_eta_logq_jac<K_, D_><<<grid, 256, 0, st>>>(nss, tau, mu, prior_alpha, prior_beta, prior_mu, prior_nu, R, log_q, jac); \
+        APGS_LAUNCH_OK("k_gmm_eta_logq_jac launch");                                                                     \
+        return 0;                                                                                                        \
+    }
+    APGS_ELQ(3, 2) APGS_ELQ(2, 2) APGS_ELQ(4, 2) APGS_ELQ(5, 2) APGS_ELQ(3, 3) APGS_ELQ(4, 3) APGS_ELQ(3, 1)
+#undef APGS_ELQ
+    return fail(APGS_E_UNSUPPORTED, "gmm_eta_logq_jac: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
 }

@@ -246,7 +246,7 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
         z_lab = torch.empty(S, B, LN, dtype=torch.uint8, device=dev)
         q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
         rs, rk = _prior_struct(prior)
-        w, o = _outs(S, B, N, dev, False, False)
+        w, o = _outs(S, B, N, dev, False, local)         # local: log_q_local of the draw (log_w_local has no meaning here)
         with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, S * B * (LN + 4 * ((N * K if want_onehot else 0) + N + 2 * K * D + (N * K if want_q else 0)))):
             check(lib.apgs_gmm_z_step_fused_labels_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
                                                        C.byref(rs), None, ptr(uniforms), S, B, N, K, D,

@@ -170,7 +170,7 @@ class Enc_apg_eta(nn.Module):
         xp, gam = self.heads(ob, z)
         return posterior_eta_torch(xp, gam, prior_ng)
 
-    def params_graph(self, ob, z, prior_ng):
+    def params_graph(self, ob, z, prior_ng, nss_only=False):
         """the same differentiable parameters with the S-sized work on the kernels: z is one-hot, so the
         heads take only K values per data point -- tabulate {gamma_k, gamma_k x'_d, gamma_k x'_d^2} per (instance, point,
         label) with ordinary PyTorch ops (a (B,N,K,.) tensor: S times less work than heads()), sum the rows the labels
@@ -185,11 +185,22 @@ class Enc_apg_eta(nn.Module):
         g5 = gam.unsqueeze(-1)
         table = torch.cat((gam, (g5 * xp.unsqueeze(-2)).flatten(-2), (g5 * (xp ** 2).unsqueeze(-2)).flatten(-2)), -1)
         nss = LabelTableSum.apply(table.contiguous(), z)                                     # (S,B,K + 2 K D)
+        if nss_only:
+            return nss
         S = nss.shape[0]
         s1 = nss[..., :K].unsqueeze(-1)
         s2 = nss[..., K:K + K * D].reshape(S, B, K, D)
         s3 = nss[..., K + K * D:].reshape(S, B, K, D)
         return _posterior_from_stats(s1, s2, s3, prior_ng)
+
+    def log_q_graph(self, ob, z, prior_ng, tau, mu):
+        """log q(tau, mu | x, z) (S,B) with a graph to the head weights: head table (PyTorch) -> LabelTableSum -> EtaLogQ
+        (one kernel for the Normal-Gamma update + log-densities + Jacobian) when (K, D) is compiled, else PyTorch ops."""
+        K, D = tau.shape[-2], tau.shape[-1]
+        if kernels.supported(K, D) & kernels.BASE:
+            from .train import EtaLogQ
+            return EtaLogQ.apply(self.params_graph(ob, z, prior_ng, nss_only=True), tau, mu, *prior_ng)
+        return eta_log_q_torch(self.params_graph(ob, z, prior_ng), tau, mu)
 
     def forward(self, ob, z, prior_ng, sampled=True, tau_old=None, mu_old=None):
         # differentiable like the reference's forward() when the parameters take part in autograd (see Enc_rws_eta)

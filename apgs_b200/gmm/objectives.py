@@ -153,9 +153,13 @@ def _can_emit_eta(enc_apg_eta, generative):
 
 def _compact_labels(block, result_flags, enc_apg_z, enc_apg_eta, generative):
     K, D = generative.prior_pi.numel(), generative_dims(enc_apg_eta)
-    return (compact_labels and block == 'decomposed' and not result_flags['loss_required']
-            and enc_apg_z.can_fuse(False) and _eta_fused(enc_apg_eta) and K <= 255
-            and kernels.supported(K, D) & kernels.LABELS)
+    if result_flags['loss_required']:
+        # training: the graphs of log q must take labels too -- FusedZStep (z) and LabelTableSum (eta) do
+        if not (_train_z(enc_apg_z) and train_on_kernels and hasattr(enc_apg_eta, 'params_graph')):
+            return False
+    return bool(compact_labels and block == 'decomposed'
+                and enc_apg_z.can_fuse(False) and _eta_fused(enc_apg_eta) and K <= 255
+                and kernels.supported(K, D) & kernels.LABELS)
 
 
 def _train_z(enc_apg_z):
@@ -164,11 +168,14 @@ def _train_z(enc_apg_z):
             and enc_apg_z.can_fuse(False))
 
 
-def _sample_z_train(enc_z, generative, x, tau, mu):
-    """sample-only fused z step with a graph: z, q_probs, log q(z) summed over the points (S,B)"""
+def _sample_z_train(enc_z, generative, x, tau, mu, label_stride=0):
+    """sample-only fused z step with a graph: z (one-hot), q_probs, log q(z) summed over the points (S,B), labels or None"""
     from .train import FusedZStep
-    z, q_probs, _, _, _, log_q_local = FusedZStep.apply(*enc_z.mlp(), kernels._x3(x), tau, mu, None, generative)
-    return z, q_probs, log_q_local.sum(-1)
+    z, q_probs, _, _, _, log_q_local, z_hot = FusedZStep.apply(*enc_z.mlp(), kernels._x3(x), tau, mu, None, generative,
+                                                               int(label_stride))
+    if label_stride:
+        return z_hot, q_probs, log_q_local.sum(-1), z
+    return z, q_probs, log_q_local.sum(-1), None
 
 
 def _eta_fused(enc_apg_eta):
@@ -208,7 +215,7 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
         return log_w, tau, mu, None, trace, z_lab, log_q
     log_q_z = None
     if result_flags['loss_required'] and _train_z(enc_rws_z):
-        z, q_probs, log_q_z = _sample_z_train(enc_rws_z, generative, x, tau, mu)
+        z, q_probs, log_q_z, z_lab = _sample_z_train(enc_rws_z, generative, x, tau, mu, label_stride)
     elif label_stride:
         z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride)
     elif enc_rws_z.can_fuse(result_flags['loss_required']):
@@ -240,7 +247,7 @@ def _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old,
     tau, mu = _sample_eta(post)
     log_q_z = None
     if result_flags['loss_required'] and _train_z(enc_apg_z):
-        z, q_probs, log_q_z = _sample_z_train(enc_apg_z, generative, x, tau, mu)
+        z, q_probs, log_q_z, _ = _sample_z_train(enc_apg_z, generative, x, tau, mu)
     elif enc_apg_z.can_fuse(result_flags['loss_required']):
         z, q_probs = enc_apg_z.sample_fused(x, tau, mu, generative)
     else:
@@ -251,8 +258,10 @@ def _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old,
     if result_flags['loss_required'] and needs_grad(enc_apg_eta, enc_apg_z):
         if log_q_z is None:
             log_q_z = cat(q_probs, validate_args=False).log_prob(z).sum(-1)
-        graph = enc_apg_eta.params_graph if (train_on_kernels and hasattr(enc_apg_eta, 'params_graph')) else enc_apg_eta.params_torch
-        log_q_f = eta_log_q_torch(graph(x, z_old, generative.prior_ng), tau, mu) + log_q_z
+        if train_on_kernels and hasattr(enc_apg_eta, 'log_q_graph'):
+            log_q_f = enc_apg_eta.log_q_graph(x, z_old, generative.prior_ng, tau, mu) + log_q_z
+        else:
+            log_q_f = eta_log_q_torch(enc_apg_eta.params_torch(x, z_old, generative.prior_ng), tau, mu) + log_q_z
     _book(trace, result_flags, w.log_w, log_q_f, w.density, defer)
     if result_flags['mode_required']:
         # the reference's branch (objectives.py:149-155) reads an undefined name; emit what it intends
@@ -286,8 +295,10 @@ def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_fl
         w = kernels.logw_eta(x, z, post, generative, tau, mu, tau_old, mu_old)
     log_q_f = w.log_q_f
     if result_flags['loss_required'] and needs_grad(enc_apg_eta):
-        graph = enc_apg_eta.params_graph if (train_on_kernels and hasattr(enc_apg_eta, 'params_graph')) else enc_apg_eta.params_torch
-        log_q_f = eta_log_q_torch(graph(x, z, generative.prior_ng), tau, mu)
+        if train_on_kernels and hasattr(enc_apg_eta, 'log_q_graph'):
+            log_q_f = enc_apg_eta.log_q_graph(x, z, generative.prior_ng, tau, mu)
+        else:
+            log_q_f = eta_log_q_torch(enc_apg_eta.params_torch(x, z, generative.prior_ng), tau, mu)
     _book(trace, result_flags, w.log_w, log_q_f, w.density, defer)
     if result_flags['mode_required']:
         trace['E_tau'].append((post[0] / post[1]).mean(0).unsqueeze(0))
@@ -308,8 +319,8 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
     if need_local and _train_z(enc_apg_z):
         # N2: the fused forward launch + a backward kernel for the MLP gradients (train.FusedZStep)
         from .train import FusedZStep
-        z, q_probs, log_w, density, log_w_local, log_q_local = FusedZStep.apply(*enc_apg_z.mlp(), kernels._x3(x), tau, mu,
-                                                                               z_old, generative)
+        z, q_probs, log_w, density, log_w_local, log_q_local, _ = FusedZStep.apply(*enc_apg_z.mlp(), kernels._x3(x), tau, mu,
+                                                                                  z_old, generative, 0)
         w_local, _ = ops.local_weight_stats(log_w_local, want_w=True, want_sum=False)
         loss = (w_local * (-log_q_local)).sum(0).sum(-1).mean()
         trace['loss'][-1] = trace['loss'][-1] + loss.unsqueeze(0)

@@ -57,24 +57,33 @@ class FusedZStep(torch.autograd.Function):
     """z ~ q(z | x, tau, mu) and everything the z step needs from ONE forward launch; differentiable w.r.t. the MLP through
     log_q_local only (the weights are detached in the reference too, objectives.py:216-220).
 
-    apply(W1, b1, W2, b2, x, tau, mu, z_old, prior) -> z_new, q_probs, log_w, density, log_w_local, log_q_local
-    (z_old None: sample-only mode of the one-shot / joint step; log_w / log_w_local are then meaningless)."""
+    apply(W1, b1, W2, b2, x, tau, mu, z_old, prior, label_stride)
+        -> z_new, q_probs, log_w, density, log_w_local, log_q_local, z_onehot
+    z_old one-hot (S,B,N,K) or uint8 labels (S,B,LN) -> z_new in the same form.  z_old None: sample-only mode of the
+    one-shot / joint step (log_w / log_w_local are then meaningless); with label_stride > 0 the draw comes back as labels
+    (z_new) AND one-hot (z_onehot, what the one-shot's weight kernel reads), else z_onehot is z_new."""
 
     @staticmethod
-    def forward(ctx, W1, b1, W2, b2, x, tau, mu, z_old, prior):
-        z_new, q, w = kernels.z_step_fused(x, tau, mu, (W1, b1, W2, b2), prior, z_old=z_old, want_q=True, local=True)
+    def forward(ctx, W1, b1, W2, b2, x, tau, mu, z_old, prior, label_stride=0):
+        if z_old is None and label_stride:
+            (z_hot, z_new), q, w = kernels.z_step_fused(x, tau, mu, (W1, b1, W2, b2), prior, want_q=True, local=True,
+                                                        also_labels=label_stride)
+        else:
+            z_new, q, w = kernels.z_step_fused(x, tau, mu, (W1, b1, W2, b2), prior, z_old=z_old, want_q=True, local=True)
+            z_hot = z_new
         ctx.save_for_backward(W1, b1, W2, b2, x, tau, mu, q, z_new)
-        outs = (z_new, q, w.log_w, w.density, w.log_w_local, w.log_q_local)
-        ctx.mark_non_differentiable(*outs[:5])
+        log_w_local = w.log_w_local if w.log_w_local is not None else w.log_q_local.new_zeros(())
+        outs = (z_new, q, w.log_w, w.density, log_w_local, w.log_q_local, z_hot if z_hot is not z_new else z_new.new_zeros(()))
+        ctx.mark_non_differentiable(outs[0], outs[1], outs[2], outs[3], outs[4], outs[6])
         return outs
 
     @staticmethod
-    def backward(ctx, gz, gq, glw, gd, glwl, glq):
+    def backward(ctx, gz, gq, glw, gd, glwl, glq, gzh):
         W1, b1, W2, b2, x, tau, mu, q, z_new = ctx.saved_tensors
         if glq is None:
-            return (None,) * 9
+            return (None,) * 10
         gW1, gb1, gW2, gb2 = z_logq_backward(x, tau, mu, (W1, b1, W2, b2), q, z_new, glq)
-        return gW1, gb1, gW2, gb2, None, None, None, None, None
+        return gW1, gb1, gW2, gb2, None, None, None, None, None, None
 
 
 def label_table_sum(table, z):
@@ -119,3 +128,30 @@ class LabelTableSum(torch.autograd.Function):
     def backward(ctx, grad_out):
         (z,) = ctx.saved_tensors
         return label_table_sum_backward(grad_out.contiguous(), z, *ctx.dims), None
+
+
+class EtaLogQ(torch.autograd.Function):
+    """log q(tau, mu) (S,B) of Enc_apg_eta as a differentiable function of its neural statistics nss (S,B,K+2KD): the
+    Normal-Gamma update and the Gamma / Normal log-densities in one kernel that also returns the Jacobian."""
+
+    @staticmethod
+    def forward(ctx, nss, tau, mu, prior_alpha, prior_beta, prior_mu, prior_nu):
+        lib = _lib.load()
+        nss = _req(nss, "nss", ndim=3)
+        tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
+        S, B, K, D = tau.shape
+        if nss.shape[-1] != K + 2 * K * D:
+            raise ValueError("nss has %d columns, expected K + 2 K D = %d" % (nss.shape[-1], K + 2 * K * D))
+        pr = [_req(v, "prior") for v in (prior_alpha, prior_beta, prior_mu, prior_nu)]
+        lq = torch.empty(S, B, dtype=torch.float32, device=tau.device)
+        jac = torch.empty_like(nss)
+        with torch.cuda.device(tau.device), _call("gmm_eta_logq_jac", 1, 4 * S * B * (2 * nss.shape[-1] + 2 * K * D + 1)):
+            check(lib.apgs_gmm_eta_logq_jac_f32(ptr(nss), ptr(tau), ptr(mu), *[ptr(v) for v in pr], S, B, K, D, ptr(lq), ptr(jac),
+                                                _stream()), "apgs_gmm_eta_logq_jac_f32")
+        ctx.save_for_backward(jac)
+        return lq
+
+    @staticmethod
+    def backward(ctx, g):
+        (jac,) = ctx.saved_tensors
+        return g.unsqueeze(-1) * jac, None, None, None, None, None, None

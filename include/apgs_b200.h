@@ -311,6 +311,13 @@ APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8
  *       grad_table[b,n,l,c] = sum_s [label(s,b,n) == l] grad_out[s,b,c]
  *   C <= 64, K <= 255.  The adjoint splits the particles of an instance over P = apgs_gmm_label_table_sum_backward_splits
  *   (S, B) CTAs: grad_table is (P,B,N,K,C), P partial tables the caller adds up (deterministic, no atomics).           */
+/* log q(tau, mu) of Enc_apg_eta from its neural statistics nss (S,B,K+2KD) = {s1_k, s2_kd, s3_kd} -- the Normal-Gamma update
+ * (apgs/gmm/kls_gmm.py:106-119, quirks Q1 / Q2) followed by Gamma / Normal log-densities summed over (K,D)
+ * (apgs/gmm/objectives.py:167) -- and its Jacobian jac (S,B,K+2KD) = d log_q / d nss, in one launch: the eta step's graph
+ * is then  head table (PyTorch, per instance) -> apgs_gmm_label_table_sum_f32 -> this.                                   */
+APGS_API int apgs_gmm_eta_logq_jac_f32(const float* nss, const float* tau, const float* mu,
+                              const float* prior_alpha, const float* prior_beta, const float* prior_mu, const float* prior_nu,
+                              int64_t S, int64_t B, int64_t K, int64_t D, float* log_q, float* jac, void* stream);
 APGS_API size_t apgs_gmm_z_logq_backward_workspace_bytes(int64_t S, int64_t B, int64_t H, int64_t D);
 APGS_API int apgs_gmm_z_logq_backward_f32(const float* x, const float* tau, const float* mu,
                               const float* W1, const float* b1, const float* W2, int64_t H,

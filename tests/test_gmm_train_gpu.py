@@ -195,3 +195,33 @@ def test_objective_training_path_runs_on_the_kernels():
         gb = torch.cat([g.reshape(-1) for g in res[(block, False)][1]])
         cos = float((ga * gb).sum() / (ga.norm() * gb.norm()))
         assert cos > 0.8, (block, cos)
+
+
+@pytest.mark.parametrize("K,D", [(3, 2), (4, 2), (3, 3)])
+def test_eta_logq_kernel_value_and_jacobian_vs_autograd(K, D):
+    """EtaLogQ: log q(tau, mu | nss) and d log q / d nss against autograd through the PyTorch formulas, incl. an empty
+    cluster (quirk Q1: the replaced count carries no gradient)."""
+    from apgs_b200.gmm import models as M
+    from apgs_b200.gmm.train import EtaLogQ
+    S, B = 9, 7
+    torch.manual_seed(K * 10 + D)
+    gen = _Gen(K, D)
+    s1 = torch.rand(S, B, K, device=DEV) * 30
+    s1[0, 0, 0] = 0.0
+    xbar = torch.randn(S, B, K, D, device=DEV) * 2
+    s2 = s1.unsqueeze(-1) * xbar
+    s3 = s1.unsqueeze(-1) * (xbar ** 2 + torch.rand(S, B, K, D, device=DEV) + 0.1)
+    s2[0, 0, 0], s3[0, 0, 0] = 0.0, 0.0
+    tau, mu = torch.rand(S, B, K, D, device=DEV) + 0.5, torch.randn(S, B, K, D, device=DEV) * 2
+    nss = torch.cat((s1, s2.flatten(-2), s3.flatten(-2)), -1).requires_grad_(True)
+    g = torch.randn(S, B, device=DEV)
+    lq = EtaLogQ.apply(nss, tau, mu, *gen.prior_ng)
+    (lq * g).sum().backward()
+    n2 = nss.detach().clone().requires_grad_(True)
+    post = M._posterior_from_stats(n2[..., :K].unsqueeze(-1), n2[..., K:K + K * D].reshape(S, B, K, D), n2[..., K + K * D:].reshape(S, B, K, D),
+                                   gen.prior_ng)
+    ref = M.eta_log_q_torch(post, tau, mu)
+    (ref * g).sum().backward()
+    torch.testing.assert_close(lq, ref, rtol=2e-5, atol=2e-4)
+    torch.testing.assert_close(nss.grad, n2.grad, rtol=2e-4, atol=2e-4 * float(n2.grad.abs().max()))
+    assert float(nss.grad[0, 0, 0]) == 0.0
