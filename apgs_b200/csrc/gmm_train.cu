@@ -231,11 +231,18 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd(ZBwdArgs a) {
 
 // all points of one particle x the HQ hidden units of one lane.  FAST: y = Ex * Ee + 1 from the factorised tables; else the
 // exact form y = 2^(xh' + e') + 1 (s_ex holds the raw xh' when the CTA is not `xok`; see the note in the point-major kernel)
+#ifndef APGS_ZBWD_UNROLL
+#define APGS_ZBWD_UNROLL 2
+#endif
+#ifndef APGS_ZBWD_MINB
+#define APGS_ZBWD_MINB 2
+#endif
 template <int K, int D, int HQ, bool FAST>
 __device__ __forceinline__ void zbwd_points(int N, const float* __restrict__ gp, const float* __restrict__ s_x,
                                             const float* __restrict__ exl, int H8, const float (&ee)[HQ][K], bool xok,
                                             float (&G2)[HQ], float (&A)[HQ][K], float (&X)[HQ][D]) {
-#pragma unroll 2
+    constexpr int kUnroll = APGS_ZBWD_UNROLL;
+#pragma unroll kUnroll
     for (int n = 0; n < N; ++n) {
         float g[K], xn[D], ex[HQ];
 #pragma unroll
@@ -254,12 +261,13 @@ __device__ __forceinline__ void zbwd_points(int N, const float* __restrict__ gp,
             float sn = 0.f;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
+                // t = 1 - 2 r and 1 - t^2 = 4 r (1 - r):  g t = g - 2 (g r)  (the caller adds sum g once per particle) and
+                // g r (1 - r) = gr - gr r: six FMA-pipe operations and one MUFU per term
                 const float y = FAST ? fmaf(ex[i], ee[i][k], 1.f) : (ex2_ftz((xok ? 0.f : ex[i]) + ee[i][k]) + 1.f);
                 const float rr = rcp_ftz(y);
-                const float t = fmaf(-2.f, rr, 1.f);
-                const float v = fmaf(-rr, rr, rr);
-                const float cc = g[k] * v;
-                G2[i] = fmaf(g[k], t, G2[i]);
+                const float gr = g[k] * rr;
+                const float cc = fmaf(-gr, rr, gr);
+                G2[i] += gr;                                 // sum g r
                 A[i][k] += cc;
                 sn += cc;
             }
@@ -276,7 +284,7 @@ __device__ __forceinline__ void zbwd_points(int N, const float* __restrict__ gp,
 // out [n][h] so that a lane reads its HQ units with one vector load.  Per-thread totals live in shared memory slots owned
 // by the thread (no atomics); the CTA's particles are combined in a fixed order at the end.
 template <int K, int D, int HQ>
-__global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
+__global__ void __launch_bounds__(kZP* kZL, APGS_ZBWD_MINB) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
     extern __shared__ __align__(16) float smf[];
     constexpr int KD = K * D, V = ZBwdV<D>::V, H8 = HQ * kZL, NT = kZP * kZL;
     const int N = a.N, H = a.H;
@@ -357,6 +365,7 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
         }
         // ---- the particle's lanes stage g[n][k] = upstream * ((k == z_n) - q_nk) (zero outside the clamp / for dead particles)
         __syncwarp();
+        float sgp = 0.f;
         for (int n = j; n < N; n += kZL) {
             float gk[K];
 #pragma unroll
@@ -383,8 +392,10 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
                 for (int k = 0; k < K; ++k) { gk[k] = up * (((k == lf) ? 1.f : 0.f) - qv[k]); gb2 += gk[k]; }
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) gp[n * K + k] = gk[k];
+            for (int k = 0; k < K; ++k) { gp[n * K + k] = gk[k]; sgp += gk[k]; }
         }
+#pragma unroll
+        for (int o = kZL / 2; o > 0; o >>= 1) sgp += __shfl_xor_sync(0xffffffffu, sgp, o);     // sum of g over the particle
         __syncwarp();
         // ---- all points x this lane's hidden units
         float G2[HQ], A[HQ][K], X[HQ][D];
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(kZP* kZL) k_gmm_z_logq_bwd_t(ZBwdArgs a) {
             float sb = 0.f;
 #pragma unroll
             for (int k = 0; k < K; ++k) sb += A[i][k];
-            t[0] += G2[i];
+            t[0] += fmaf(-2.f, G2[i], sgp);              // sum g tanh = sum g - 2 sum g r
             t[1] += sb;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
@@ -567,6 +578,7 @@ __global__ void __launch_bounds__(256) k_label_table_sum(LtsArgs a) {
 // label particle s gives point n -- every (n, label, c) accumulator has exactly one owner, so no atomics; particles are
 // staged through shared memory in tiles
 constexpr int kLtsTile = 64;
+template <int KT>                       // KT = K when K <= 5 (accumulators in registers), 0: generic
 __global__ void __launch_bounds__(256) k_label_table_sum_bwd(LtsArgs a) {
     extern __shared__ __align__(16) float s_g[];          // [N*K][C] accumulators | tile: gout [kLtsTile][C], labels [kLtsTile][N]
     const int b = blockIdx.x, C = a.C, N = a.N, K = a.K, NKC = N * K * C;
@@ -590,7 +602,25 @@ __global__ void __launch_bounds__(256) k_label_table_sum_bwd(LtsArgs a) {
         __syncthreads();
         for (int pc = threadIdx.x; pc < N * C; pc += blockDim.x) {
             const int n = pc / C, c = pc - n * C;
-            for (int si = 0; si < ns; ++si) s_g[(size_t)(n * K + s_lab[si * N + n]) * C + c] += s_go[si * C + c];
+            if (KT > 0) {
+                // the K accumulators of this (n, c) in registers, a predicated add per label value: no read-modify-write
+                // chain through shared memory (consecutive particles often carry the same label)
+                float acc[KT > 0 ? KT : 1];
+#pragma unroll
+                for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+#pragma unroll 8
+                for (int si = 0; si < ns; ++si) {
+                    const int lab = s_lab[si * N + n];
+                    const float g = s_go[si * C + c];
+#pragma unroll
+                    for (int k = 0; k < KT; ++k)
+                        if (lab == k) acc[k] += g;
+                }
+#pragma unroll
+                for (int k = 0; k < KT; ++k) s_g[(size_t)(n * K + k) * C + c] += acc[k];
+            } else {
+                for (int si = 0; si < ns; ++si) s_g[(size_t)(n * K + s_lab[si * N + n]) * C + c] += s_go[si * C + c];
+            }
         }
     }
     __syncthreads();
@@ -747,9 +777,11 @@ extern "C" int apgs_gmm_label_table_sum_backward_f32(const float* grad_out, cons
     if (!grad_out || !grad_table) return fail(APGS_E_BADARG, "gmm_label_table_sum_backward: NULL pointer");
     const size_t smem = ((size_t)N * K * C + (size_t)kLtsTile * C) * 4 + (size_t)kLtsTile * N;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_label_table_sum_backward: N K C too large for shared memory");
-    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_label_table_sum_bwd), smem), "smem attr");
+    void (*kern)(LtsArgs) = K == 2 ? k_label_table_sum_bwd<2> : K == 3 ? k_label_table_sum_bwd<3> : K == 4 ? k_label_table_sum_bwd<4>
+                            : K == 5 ? k_label_table_sum_bwd<5> : k_label_table_sum_bwd<0>;
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
     const int splits = apgs_gmm_label_table_sum_backward_splits(S, B);     // grad_table holds `splits` partial tables
-    k_label_table_sum_bwd<<<dim3((unsigned int)B, (unsigned int)splits), 256, smem, (cudaStream_t)stream>>>(a);
+    kern<<<dim3((unsigned int)B, (unsigned int)splits), 256, smem, (cudaStream_t)stream>>>(a);
     APGS_LAUNCH_OK("k_label_table_sum_bwd launch");
     return 0;
 }
