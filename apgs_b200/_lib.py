@@ -107,6 +107,7 @@ SIGNATURES = {
     "apgs_gmm_label_table_sum_backward_splits": (_int, [_i64, _i64]),
     "apgs_gmm_label_table_sum_backward_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_gmm_draw_logw_eta_stats_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_gmm_draw_logw_eta_stats_rng_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_logw_eta_stats_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_z_step_fused_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p, _p,
                                          _i64, _i64, _i64, _i64, _i64, _p, _p, _OUT, _p]),

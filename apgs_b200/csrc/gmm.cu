@@ -12,6 +12,7 @@
 // evaluate the small (K,D) terms; LANES lanes then split the N points of each particle.
 // fp32 arithmetic in the reference's operation order; N-sums are accumulated in fp64.
 #include "gmm_common.cuh"
+#include "rng.cuh"
 
 namespace apgs {
 
@@ -599,6 +600,8 @@ struct EtaStatsArgs {
     // optional fused draw: standard Gamma(alpha) and standard Normal variates -> tau, mu written out and scored
     const float *g_std, *e_std;       // (R, K, D) or null
     float *tau_out, *mu_out;          // (R, K, D), required with the draws
+    // ... or drawn in the kernel: device pointer to two 64-bit words {seed, stream} the host took from torch's generator
+    const unsigned long long* seed;
 };
 
 template <int K, int D, int LANES>
@@ -633,6 +636,23 @@ __global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
                 tf = fmaxf(__fdiv_rn(__ldg(a.g_std + r * KD + e), qb), 1.17549435e-38f);
                 const float sc = __fdiv_rn(1.f, __fsqrt_rn(__fmul_rn(qn, tf)));
                 mf = __fadd_rn(__fmul_rn(__ldg(a.e_std + r * KD + e), sc), qm);
+                a.tau_out[r * KD + e] = tf;
+                a.mu_out[r * KD + e] = mf;
+            } else if (a.seed != nullptr) {
+                // the same draw with the variates made here (rng.cuh): standard Gamma(alpha) by Marsaglia-Tsang and a
+                // standard normal by Box-Muller from Philox words counted by (particle, element) -- no _standard_gamma /
+                // randn launches and no variate tensors; distribution-equal, not stream-equal, to torch's draws
+                const unsigned long long sd = __ldg(a.seed), st = __ldg(a.seed + 1);
+                const uint2 key = make_uint2((unsigned int)sd, (unsigned int)(sd >> 32));
+                const uint4 ctr = make_uint4((unsigned int)r, (unsigned int)((unsigned long long)r >> 32) ^ (unsigned int)st,
+                                             (unsigned int)e ^ (unsigned int)(st >> 32), 0u);
+                const uint4 w = philox4x32_10(ctr, key);
+                float x0, en;
+                box_muller(w.x, w.y, x0, en);
+                const float g = gamma_mt(qa, x0, w.z, w.w, ctr, key);
+                tf = fmaxf(__fdiv_rn(g, qb), 1.17549435e-38f);
+                const float sc = __fdiv_rn(1.f, __fsqrt_rn(__fmul_rn(qn, tf)));
+                mf = __fadd_rn(__fmul_rn(en, sc), qm);
                 a.tau_out[r * KD + e] = tf;
                 a.mu_out[r * KD + e] = mf;
             } else {
@@ -902,7 +922,8 @@ extern "C" int apgs_gmm_eta_posterior_stats_f32(const float* x, const float* z, 
 static int logw_eta_stats(const float* stats, const float* center, const apgs_gmm_post_t* post,
                           const apgs_gmm_prior_t* prior, const float* tau, const float* mu, const float* g_std,
                           const float* e_std, float* tau_out, float* mu_out, const float* tau_old, const float* mu_old,
-                          int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream);
+                          int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream,
+                          const uint64_t* seed = nullptr);
 
 extern "C" int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
                                            const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
@@ -923,10 +944,20 @@ extern "C" int apgs_gmm_draw_logw_eta_stats_f32(const float* stats, const float*
                           B, K, D, out, stream);
 }
 
+extern "C" int apgs_gmm_draw_logw_eta_stats_rng_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                                    const apgs_gmm_prior_t* prior, const uint64_t* philox_seed, float* tau,
+                                                    float* mu, const float* tau_old, const float* mu_old, int64_t S,
+                                                    int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream) {
+    if (!philox_seed || !tau || !mu) return fail(APGS_E_BADARG, "gmm_draw_logw_eta_stats_rng: NULL input");
+    return logw_eta_stats(stats, center, post, prior, nullptr, nullptr, nullptr, nullptr, tau, mu, tau_old, mu_old, S, B, K, D,
+                          out, stream, philox_seed);
+}
+
 static int logw_eta_stats(const float* stats, const float* center, const apgs_gmm_post_t* post,
                           const apgs_gmm_prior_t* prior, const float* tau, const float* mu, const float* g_std,
                           const float* e_std, float* tau_out, float* mu_out, const float* tau_old, const float* mu_old,
-                          int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream) {
+                          int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream,
+                          const uint64_t* seed) {
     if (S <= 0 || B <= 0 || S * B >= (1ll << 36))
         return fail(APGS_E_SHAPE, "gmm_logw_eta_stats: bad sizes S=%lld B=%lld", (long long)S, (long long)B);
     if (!stats || !center || !post || !prior || !out || !tau_old || !mu_old)
@@ -939,6 +970,7 @@ static int logw_eta_stats(const float* stats, const float* center, const apgs_gm
     a.ra = prior->alpha; a.rb = prior->beta; a.rm = prior->mu; a.rn = prior->nu;
     a.tau_f = tau; a.mu_f = mu; a.tau_b = tau_old; a.mu_b = mu_old;
     a.g_std = g_std; a.e_std = e_std; a.tau_out = tau_out; a.mu_out = mu_out;
+    a.seed = reinterpret_cast<const unsigned long long*>(seed);
     a.R = (long long)S * B;
     a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;
     a.log_w_b = out->log_w_b;

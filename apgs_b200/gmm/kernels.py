@@ -174,6 +174,32 @@ def draw_logw_eta_stats(stats, center, post, prior, gamma_std, normal_std, tau_o
     return w, tau, mu
 
 
+def draw_logw_eta_stats_rng(stats, center, post, prior, seed, tau_old, mu_old, parts=False):
+    """draw_logw_eta_stats with the Gamma / Normal variates made inside the kernel (Philox + Marsaglia-Tsang + Box-Muller):
+    `seed` is an int64 CUDA tensor of two words drawn from torch's generator (philox_seed()).  Returns (Weights, tau, mu)."""
+    lib = _lib.load()
+    stats, center = _req(stats, "stats", ndim=4), _req(center, "center", ndim=4)
+    tau_old, mu_old = _req(tau_old, "tau_old", ndim=4), _req(mu_old, "mu_old", ndim=4)
+    seed = _req(seed, "seed", dtype=torch.int64, ndim=1)
+    S, B, K, D = tau_old.shape
+    if tuple(stats.shape) != (S, B, K, 1 + 2 * D) or tuple(center.shape) != (S, B, K, D) or seed.numel() < 2:
+        raise ValueError("stats / center / seed have unexpected shapes")
+    ps, pk = _post_struct(post)
+    rs, rk = _prior_struct(prior)
+    tau, mu = torch.empty_like(tau_old), torch.empty_like(tau_old)
+    w, o = _outs(S, B, 1, tau_old.device, parts, False)
+    with torch.cuda.device(tau_old.device), _call("gmm_logw_eta_stats", 1, 4 * S * B * (K * (1 + 2 * D) + 9 * K * D + 3)):
+        check(lib.apgs_gmm_draw_logw_eta_stats_rng_f32(ptr(stats), ptr(center), C.byref(ps), C.byref(rs), ptr(seed), ptr(tau),
+                                                       ptr(mu), ptr(tau_old), ptr(mu_old), S, B, K, D, C.byref(o), _stream()),
+              "apgs_gmm_draw_logw_eta_stats_rng_f32")
+    return w, tau, mu
+
+
+def philox_seed(device, generator=None):
+    """two 64-bit words from torch's generator, on the device (graph-safe: fresh values on every replay)"""
+    return torch.randint(-2 ** 62, 2 ** 62, (2,), dtype=torch.int64, device=device, generator=generator)
+
+
 def logw_z(x, tau, mu, q_probs, prior, z, z_old, parts=False, local=False):
     """G3 (+W2): z-step weights (apgs/gmm/objectives.py:197-227)."""
     if not supported(tau.shape[-2], tau.shape[-1]) & BASE:

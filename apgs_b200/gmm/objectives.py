@@ -136,6 +136,7 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     return trace
 
 
+rng_in_kernels = True          # eta step: Gamma / Normal variates drawn inside the weight kernel (else torch._standard_gamma / randn)
 train_on_kernels = True        # loss_required: graphs of log q through the kernels (train.py) instead of PyTorch encoders
 compact_labels = True          # module switches (tests compare the representations / the two one-shot paths)
 lean_oneshot = True
@@ -286,9 +287,15 @@ def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_fl
             post = tuple(post)
         # the draw of _sample_eta with its elementwise tail fused into the weight kernel: same variates, same IEEE
         # operations (tau = max(g / beta, tiny), mu = e / sqrt(nu tau) + q_mu), seven launches less per step
-        g_std = torch._standard_gamma(post[0])
-        e_std = torch.randn_like(post[2])
-        w, tau, mu = kernels.draw_logw_eta_stats(stats, mu_old, post, generative, g_std, e_std, tau_old, mu_old)
+        if rng_in_kernels:
+            # the variates themselves made in the kernel (Philox keyed by two words from torch's generator): no
+            # _standard_gamma / randn launches, no variate tensors -- distribution-equal to the torch draws below
+            w, tau, mu = kernels.draw_logw_eta_stats_rng(stats, mu_old, post, generative, kernels.philox_seed(mu_old.device),
+                                                         tau_old, mu_old)
+        else:
+            g_std = torch._standard_gamma(post[0])
+            e_std = torch.randn_like(post[2])
+            w, tau, mu = kernels.draw_logw_eta_stats(stats, mu_old, post, generative, g_std, e_std, tau_old, mu_old)
     else:
         post = enc_apg_eta.params(x, z, generative.prior_ng)
         tau, mu = _sample_eta(post)

@@ -253,6 +253,17 @@ APGS_API int apgs_gmm_draw_logw_eta_stats_f32(const float* stats, const float* c
                                 int64_t S, int64_t B, int64_t K, int64_t D,
                                 const apgs_gmm_out_t* out, void* stream);
 
+/* ... and with the variates made in the kernel: standard Gamma(alpha) by Marsaglia-Tsang (the method of ATen's sample_gamma)
+ *   and standard normals by Box-Muller from Philox4x32-10 words keyed by philox_seed[0] (+ stream word philox_seed[1]) and
+ *   counted by (particle, element) -- philox_seed is a DEVICE pointer to two 64-bit words the host draws from its own
+ *   generator per launch (torch.randint: fresh on every CUDA-graph replay).  Saves the _standard_gamma / randn launches and
+ *   both variate tensors; the draws are distribution-equal (not stream-equal) to torch's.                              */
+APGS_API int apgs_gmm_draw_logw_eta_stats_rng_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                const apgs_gmm_prior_t* prior, const uint64_t* philox_seed,
+                                float* tau, float* mu, const float* tau_old, const float* mu_old,
+                                int64_t S, int64_t B, int64_t K, int64_t D,
+                                const apgs_gmm_out_t* out, void* stream);
+
 /* Label mode of the two per-sweep GMM kernels.  Inside a sweep the assignments never need their one-hot (S,B,N,K) fp32
  *   form: these entries take / return them as one byte per point, z_labels uint8 in [0,K) with `label_stride` >= N bytes
  *   between the rows of consecutive particles (pad it to 16 so the gather moves 16-byte vectors), which cuts the z row

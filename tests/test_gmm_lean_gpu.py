@@ -454,3 +454,86 @@ def test_z_step_eta_entry_stays_inside_its_buffers():
                                                   S, B, N, K, D, ptr(bufs["zl"][1]), LN, *[ptr(h) for h in heads],
                                                   None, ptr(bufs["stats"][1]), C.byref(o), torch.cuda.current_stream().cuda_stream)
     assert rc != 0
+
+
+# ------------------------------------------------------------------ eta draw with the variates made in the kernel
+def test_in_kernel_eta_draw_distribution_and_weights():
+    """apgs_gmm_draw_logw_eta_stats_rng_f32: tau ~ Gamma(alpha, beta) (Marsaglia-Tsang on Philox words, incl. alpha < 1) and
+    mu ~ N(q_mu, 1/sqrt(q_nu tau)) (Box-Muller) -- Kolmogorov-Smirnov against the exact laws, moments, reproducibility
+    from the seed words, and weights bit-identical to scoring the same draws through apgs_gmm_logw_eta_stats_f32."""
+    import scipy.stats as st
+    from apgs_b200.gmm import kernels
+    S, B, K, D = 4000, 24, 3, 2
+    torch.manual_seed(0)
+    gen = _Gen(K, D)
+    alphas = torch.tensor([0.4, 1.0, 2.5, 7.0, 31.0, 150.0])
+    alpha = alphas[torch.arange(K * D) % len(alphas)].view(1, 1, K, D).expand(S, B, K, D).contiguous().to(DEV)
+    beta = (torch.rand(1, B, K, D) * 3 + 0.3).expand(S, B, K, D).contiguous().to(DEV)
+    q_mu = (torch.randn(1, B, K, D) * 2).expand(S, B, K, D).contiguous().to(DEV)
+    q_nu = (torch.rand(1, B, K, D) * 20 + 0.5).expand(S, B, K, D).contiguous().to(DEV)
+    post = (alpha, beta, q_mu, q_nu)
+    stats = torch.rand(S, B, K, 1 + 2 * D, device=DEV)
+    tau_old, mu_old = torch.rand(S, B, K, D, device=DEV) + 0.5, torch.randn(S, B, K, D, device=DEV)
+    seed = kernels.philox_seed(DEV)
+    w, tau, mu = kernels.draw_logw_eta_stats_rng(stats, mu_old, post, gen, seed, tau_old, mu_old, parts=True)
+    w2, tau2, mu2 = kernels.draw_logw_eta_stats_rng(stats, mu_old, post, gen, seed, tau_old, mu_old)
+    assert torch.equal(tau, tau2) and torch.equal(mu, mu2) and torch.equal(w.log_w, w2.log_w)       # a function of the seed
+    w3, tau3, mu3 = kernels.draw_logw_eta_stats_rng(stats, mu_old, post, gen, kernels.philox_seed(DEV), tau_old, mu_old)
+    assert not torch.equal(tau, tau3) and not torch.equal(mu, mu3)
+    ref = kernels.logw_eta_stats(stats, mu_old, post, gen, tau, mu, tau_old, mu_old, parts=True)
+    for name in ("log_w", "log_q_f", "density", "log_w_f", "log_w_b"):
+        assert torch.equal(getattr(w, name), getattr(ref, name)), name
+    assert bool(torch.isfinite(tau).all()) and bool((tau > 0).all()) and bool(torch.isfinite(mu).all())
+    # laws, per (k, d) element and one instance column (S = 4000 draws each) -- and pooled over instances after scaling
+    g = (tau * beta).cpu().double()                                      # standard Gamma(alpha)
+    e = ((mu - q_mu) * (q_nu * tau).sqrt()).cpu().double()               # standard normal
+    for k in range(K):
+        for d in range(D):
+            a = float(alpha[0, 0, k, d])
+            pooled = g[:, :, k, d].reshape(-1).numpy()
+            assert st.kstest(pooled[::3], "gamma", args=(a,)).pvalue > 1e-4, ("gamma KS", a)
+            assert abs(pooled.mean() - a) < 6 * (a / pooled.size) ** 0.5 + 1e-9, ("gamma mean", a, pooled.mean())
+            assert abs(pooled.var() - a) < 0.05 * a + 12 * a / pooled.size ** 0.5, ("gamma var", a, pooled.var())
+            n = e[:, :, k, d].reshape(-1).numpy()
+            assert st.kstest(n[::3], "norm").pvalue > 1e-4, "normal KS"
+            assert abs(np.corrcoef(n, pooled)[0, 1]) < 0.02, "gamma and normal variates are independent"
+    # neighbouring particles / elements are uncorrelated
+    flat = e.reshape(S, -1).numpy()
+    assert abs(np.corrcoef(flat[:-1].reshape(-1), flat[1:].reshape(-1))[0, 1]) < 0.01
+    assert abs(np.corrcoef(flat[:, :-1].reshape(-1), flat[:, 1:].reshape(-1))[0, 1]) < 0.01
+
+
+def test_objective_with_in_kernel_eta_draw_matches_torch_draws_statistically():
+    """rng_in_kernels on / off: same objective, different variate streams -> mean ESS / density / log_z of the last sweep
+    agree within Monte-Carlo error; and the CUDA-graph replay of the objective gives fresh draws on every replay."""
+    from apgs_b200.gmm import objectives as O
+    from apgs_b200.resampler import Resampler
+    from apgs_b200.graph import GraphedObjective
+    S, B, sweeps = 100, 400, 4
+    torch.manual_seed(0)
+    models = _models_from_params(og.make_params())
+    torch.manual_seed(1)
+    x = og.simulate(B).to(DEV)
+    rs = Resampler("systematic", S, True, DEV)
+    out, default = {}, O.rng_in_kernels
+    for on in (True, False):
+        O.rng_in_kernels = on
+        try:
+            torch.manual_seed(5)
+            with torch.no_grad():
+                out[on] = O.apg_objective(models, x, BENCH_FLAGS, sweeps, "decomposed", rs)
+        finally:
+            O.rng_in_kernels = default
+    for k in ("ess", "log_z"):
+        a, b = out[True][k][-1].cpu().double(), out[False][k][-1].cpu().double()
+        se = (a.var() / B + b.var() / B).sqrt()
+        assert abs(float(a.mean() - b.mean())) < 5 * float(se) + 1e-6, (k, float(a.mean()), float(b.mean()), float(se))
+    a, b = out[True]["density"][-1].mean(0).cpu().double(), out[False]["density"][-1].mean(0).cpu().double()
+    se = (a.var() / B + b.var() / B).sqrt()
+    assert abs(float(a.mean() - b.mean())) < 5 * float(se), ("density", float(a.mean()), float(b.mean()), float(se))
+    with torch.no_grad():
+        gobj = GraphedObjective(lambda xx: O.apg_objective(models, xx, BENCH_FLAGS, sweeps, "decomposed", rs), x, warmup=1)
+        t1 = {k: v.clone() for k, v in gobj(x).items() if torch.is_tensor(v)}
+        t2 = {k: v.clone() for k, v in gobj(x).items() if torch.is_tensor(v)}
+    assert not torch.equal(t1["density"], t2["density"]), "graph replays must draw fresh variates"
+    assert bool(torch.isfinite(t2["density"]).all())
