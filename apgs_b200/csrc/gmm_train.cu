@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(kZP* kZL, APGS_ZBWD_MINB) k_gmm_z_logq_bwd_t(Z
     float* s_ex = smf;                                   // [N][H8]   Ex (or raw xh' when the CTA is not `xok`)
     float* s_x = s_ex + (size_t)N * H8;                  // [N][D] (+pad)
     float* s_g = s_x + (size_t)((N * D + 3) / 4 * 4);    // [kZP][N*K]
-    float* s_tot = s_g + (size_t)kZP * ((N * K + 3) / 4 * 4);     // [NT][HQ*V]
+    float* s_tot = s_g + (size_t)kZP * ((N * K + 3) / 4 * 4);     // [NT][HQ*V + 1] (odd stride: a warp's slots on 32 banks)
+    constexpr int TS = HQ * V + 1;
     __shared__ int s_xok;
     __shared__ float s_gb2[NT / 32];
     const int GP = (N * K + 3) / 4 * 4;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(kZP* kZL, APGS_ZBWD_MINB) k_gmm_z_logq_bwd_t(Z
     const float* xb = a.x + (size_t)b * N * D;
     if (threadIdx.x == 0) s_xok = 1;
     for (int i = threadIdx.x; i < N * D; i += NT) s_x[i] = __ldg(xb + i);
-    float* tot = s_tot + (size_t)threadIdx.x * (HQ * V);
+    float* tot = s_tot + (size_t)threadIdx.x * TS;
 #pragma unroll
     for (int i = 0; i < HQ * V; ++i) tot[i] = 0.f;
     __syncthreads();
@@ -366,33 +367,49 @@ __global__ void __launch_bounds__(kZP* kZL, APGS_ZBWD_MINB) k_gmm_z_logq_bwd_t(Z
         // ---- the particle's lanes stage g[n][k] = upstream * ((k == z_n) - q_nk) (zero outside the clamp / for dead particles)
         __syncwarp();
         float sgp = 0.f;
-        for (int n = j; n < N; n += kZL) {
-            float gk[K];
+        for (int n0 = 0; n0 < N; n0 += kZL * kZPT) {
+            // all global loads of this lane's (up to) 8 points first -- 40 independent requests in flight -- then the
+            // arithmetic (the IEEE division below keeps the compiler from overlapping the iterations by itself)
+            float qv[kZPT][K], up[kZPT];
+            int lf[kZPT];
 #pragma unroll
-            for (int k = 0; k < K; ++k) gk[k] = 0.f;
-            if (valid) {
-                float qv[K], sq = 0.f;
+            for (int i = 0; i < kZPT; ++i) {
+                const int n = n0 + j + kZL * i;
+                const bool live = valid && n < N;
 #pragma unroll
-                for (int k = 0; k < K; ++k) { qv[k] = __ldg(a.q + (r * N + n) * K + k); sq = __fadd_rn(sq, qv[k]); }
-                int lf = 0;
-                if (a.zl != nullptr) {
-                    lf = min((int)__ldg(a.zl + r * a.LN + n), K - 1);
-                } else {
-                    float best = __ldg(a.z + (r * N + n) * K);
+                for (int k = 0; k < K; ++k) qv[i][k] = live ? __ldg(a.q + (r * N + n) * K + k) : 1.f;
+                up[i] = live ? __ldg(a.g + r * a.g_sr + n * a.g_sn) : 0.f;
+                lf[i] = 0;
+                if (live) {
+                    if (a.zl != nullptr) {
+                        lf[i] = min((int)__ldg(a.zl + r * a.LN + n), K - 1);
+                    } else {
+                        float best = __ldg(a.z + (r * N + n) * K);
 #pragma unroll
-                    for (int k = 1; k < K; ++k) { const float v = __ldg(a.z + (r * N + n) * K + k); if (v > best) { best = v; lf = k; } }
+                        for (int k = 1; k < K; ++k) { const float v = __ldg(a.z + (r * N + n) * K + k); if (v > best) { best = v; lf[i] = k; } }
+                    }
                 }
-                float ql = qv[0];
-#pragma unroll
-                for (int k = 1; k < K; ++k) if (lf == k) ql = qv[k];
-                const float pn = __fdiv_rn(ql, sq);
-                const bool inside = pn >= FLT_EPS_F && pn <= 1.f - FLT_EPS_F;
-                const float up = inside ? __ldg(a.g + r * a.g_sr + n * a.g_sn) : 0.f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) { gk[k] = up * (((k == lf) ? 1.f : 0.f) - qv[k]); gb2 += gk[k]; }
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) { gp[n * K + k] = gk[k]; sgp += gk[k]; }
+            for (int i = 0; i < kZPT; ++i) {
+                const int n = n0 + j + kZL * i;
+                float sq = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, qv[i][k]);
+                float ql = qv[i][0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) if (lf[i] == k) ql = qv[i][k];
+                const float pn = __fdiv_rn(ql, sq);
+                const bool inside = pn >= FLT_EPS_F && pn <= 1.f - FLT_EPS_F;
+                const float u = (valid && inside) ? up[i] : 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float gk = u * (((k == lf[i]) ? 1.f : 0.f) - qv[i][k]);
+                    if (n < N) gp[n * K + k] = gk;
+                    gb2 += gk;                       // u = 0 for the padding points
+                    sgp += gk;
+                }
+            }
         }
 #pragma unroll
         for (int o = kZL / 2; o > 0; o >>= 1) sgp += __shfl_xor_sync(0xffffffffu, sgp, o);     // sum of g over the particle
@@ -441,7 +458,7 @@ __global__ void __launch_bounds__(kZP* kZL, APGS_ZBWD_MINB) k_gmm_z_logq_bwd_t(Z
         if (h >= H) continue;
         const int jj = h / HQ, i = h - jj * HQ;
         float sum = 0.f;
-        for (int pp = 0; pp < kZP; ++pp) sum += s_tot[(size_t)(pp * kZL + jj) * (HQ * V) + i * V + v];
+        for (int pp = 0; pp < kZP; ++pp) sum += s_tot[(size_t)(pp * kZL + jj) * TS + i * V + v];
         out[h * V + v] = sum;
     }
     if (threadIdx.x == 0) {
@@ -504,7 +521,7 @@ static int launch_z_bwd(ZBwdArgs a, float* gW1, float* gb1, float* gW2, float* g
     // hidden-unit-major variant for H <= 32 (the reference's 32): no cross-lane reductions in the main loop
     const int HQ = a.H <= 8 ? 1 : (a.H <= 16 ? 2 : 4);
     const size_t smem_t = ((size_t)a.N * HQ * kZL + (size_t)((a.N * D + 3) / 4 * 4) + (size_t)kZP * ((a.N * K + 3) / 4 * 4) +
-                           (size_t)kZP * kZL * HQ * V) * 4;
+                           (size_t)kZP * kZL * (HQ * V + 1)) * 4;
     if (a.H <= 32 && smem_t <= 200 * 1024 && !a.force_point_major) {
         void (*kern)(ZBwdArgs) = HQ == 1 ? k_gmm_z_logq_bwd_t<K, D, 1> : (HQ == 2 ? k_gmm_z_logq_bwd_t<K, D, 2> : k_gmm_z_logq_bwd_t<K, D, 4>);
         APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_t), "smem attr");
