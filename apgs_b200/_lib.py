@@ -83,6 +83,8 @@ SIGNATURES = {
     "apgs_dmm_logw_local_f32": (_int, [_p] * 13 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
     "apgs_dmm_logw_oneshot_f32": (_int, [_p] * 10 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
     "apgs_bmnist_crop_f32": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_bmnist_crop_bilinear_f32": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_bmnist_paste_bilinear_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_bmnist_paste_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_bmnist_paste_ll_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "apgs_bmnist_paste_subtract_f32": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _p, _p]),

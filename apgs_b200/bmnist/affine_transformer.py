@@ -14,8 +14,14 @@ from . import kernels
 
 
 class Affine_Transformer():
-    def __init__(self, frame_pixels, digit_pixels, CUDA=True, DEVICE=None):
+    def __init__(self, frame_pixels, digit_pixels, CUDA=True, DEVICE=None, mode="nearest"):
+        """mode: 'nearest' -- what the reference samples with (affine_transformer.py:50-51,63-64; the parity mode) -- or
+        'bilinear' (north_star's mode switch) for digit_to_frame / frame_to_digit; the fused likelihood and residual
+        entries follow the reference (nearest)."""
         super().__init__()
+        if mode not in ("nearest", "bilinear"):
+            raise ValueError("mode must be 'nearest' or 'bilinear'")
+        self.mode = mode
         if not CUDA:
             raise _lib.ApgsError("apgs_b200 Affine_Transformer runs on CUDA only (no CPU fallback)")
         _lib.load()
@@ -36,12 +42,12 @@ class Affine_Transformer():
     def digit_to_frame(self, digit, z_where):
         """transfer the digits to the frame
         [digit: S * B * K * DP * DP, z_where: S * B * T * K * 2 ===> frame: S * B * T * K * FP * FP]"""
-        return kernels.paste(digit, z_where, self.lin_fp, self.frame_pixels)
+        return kernels.paste(digit, z_where, self.lin_fp, self.frame_pixels, mode=self.mode)
 
     def frame_to_digit(self, frames, z_where):
         """transfer the frames to the digits
         [frame: S * B * T * FP * FP, z_where: S * B * T * K * 2 ===> digit: S * B * T * K * DP * DP]"""
-        return kernels.crop(frames, z_where, self.lin_dp, self.digit_pixels)
+        return kernels.crop(frames, z_where, self.lin_dp, self.digit_pixels, mode=self.mode)
 
     def subtract_digit(self, frame, digit, z_where):
         """frame (S,B,FP,FP) - digit_to_frame(digit (S,B,DP,DP), z_where (S,B,2)): the residual-frame update of the

@@ -17,31 +17,34 @@ def _frames_view(frames, S):
     return frames.detach()
 
 
-def crop(frames, z_where, lin_dp, DP):
-    """B1: (S,B,T,FP,FP) x (S,B,T,K,2) -> (S,B,T,K,DP,DP)."""
+def crop(frames, z_where, lin_dp, DP, mode="nearest"):
+    """B1: (S,B,T,FP,FP) x (S,B,T,K,2) -> (S,B,T,K,DP,DP).  mode: 'nearest' (the reference's) or 'bilinear'."""
     lib = _lib.load()
+    fn, fname = ((lib.apgs_bmnist_crop_f32, "apgs_bmnist_crop_f32") if mode == "nearest" else
+                 (lib.apgs_bmnist_crop_bilinear_f32, "apgs_bmnist_crop_bilinear_f32"))
     z = _req(z_where, "z_where", ndim=5)
     S, B, T, K, _ = z.shape
     fr = _frames_view(frames, S)
     FP = fr.shape[-1]
     out = torch.empty(S, B, T, K, DP, DP, dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device), _call("bmnist_crop", 1, 8 * S * B * T * K * DP * DP):
-        check(lib.apgs_bmnist_crop_f32(ptr(fr), fr.stride(0), fr.stride(1), fr.stride(2), ptr(z), ptr(lin_dp),
-                                       S, B, T, K, FP, DP, ptr(out), _stream()), "apgs_bmnist_crop_f32")
+        check(fn(ptr(fr), fr.stride(0), fr.stride(1), fr.stride(2), ptr(z), ptr(lin_dp),
+                 S, B, T, K, FP, DP, ptr(out), _stream()), fname)
     return out
 
 
-def paste(digits, z_where, lin_fp, FP):
-    """B2: (S,B,K,DP,DP) x (S,B,T,K,2) -> (S,B,T,K,FP,FP)."""
+def paste(digits, z_where, lin_fp, FP, mode="nearest"):
+    """B2: (S,B,K,DP,DP) x (S,B,T,K,2) -> (S,B,T,K,FP,FP).  mode: 'nearest' (the reference's) or 'bilinear'."""
     lib = _lib.load()
+    fn, fname = ((lib.apgs_bmnist_paste_f32, "apgs_bmnist_paste_f32") if mode == "nearest" else
+                 (lib.apgs_bmnist_paste_bilinear_f32, "apgs_bmnist_paste_bilinear_f32"))
     z = _req(z_where, "z_where", ndim=5)
     d = _req(digits, "digit", ndim=5)
     S, B, T, K, _ = z.shape
     DP = d.shape[-1]
     out = torch.empty(S, B, T, K, FP, FP, dtype=torch.float32, device=z.device)
     with torch.cuda.device(z.device), _call("bmnist_paste", 1, 4 * S * B * (K * DP * DP + T * K * FP * FP)):
-        check(lib.apgs_bmnist_paste_f32(ptr(d), ptr(z), ptr(lin_fp), S, B, T, K, FP, DP, ptr(out), _stream()),
-              "apgs_bmnist_paste_f32")
+        check(fn(ptr(d), ptr(z), ptr(lin_fp), S, B, T, K, FP, DP, ptr(out), _stream()), fname)
     return out
 
 

@@ -135,6 +135,60 @@ __global__ void __launch_bounds__(256) k_stn_paste(StnArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------- bilinear mode (north_star item 4)
+// The reference's transformer samples with mode='nearest' (that is the parity mode, above); the bilinear
+// variant is the same separable transform with grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True)
+// semantics: per output row / column a lower source index and a fraction, out = sum of the four in-bounds neighbours
+// weighted (1-fr)(1-fc), (1-fr) fc, fr (1-fc), fr fc.  CTA per (s,b,t); index / fraction vectors in shared memory.
+__device__ __forceinline__ void stn_axis_bilinear(float lin, float scale, float t, int n_in, int& i0, float& f) {
+    const float v = __fadd_rn(__fmul_rn(lin, scale), t);
+    const float u = __fmul_rn(__fadd_rn(v, 1.f), (float)(n_in - 1) * 0.5f);
+    const float fl = floorf(u);
+    // far out of range: park the index where both neighbours are out of bounds
+    i0 = (fl >= -2.f && fl <= (float)n_in) ? (int)fl : -2;
+    f = u - fl;
+}
+
+template <bool PASTE>
+__global__ void __launch_bounds__(256) k_stn_bilinear(StnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_b[];
+    const int sbt = blockIdx.x;
+    const int t = sbt % a.T, b = (sbt / a.T) % a.B, s = sbt / (a.T * a.B);
+    const int K = a.K, DP = a.DP, FP = a.FP;
+    const int NO = PASTE ? FP : DP, NI = PASTE ? DP : FP;            // output / input resolution
+    int* s_i0 = reinterpret_cast<int*>(smem_b);                      // [K][2][NO]
+    float* s_f = reinterpret_cast<float*>(s_i0 + K * 2 * NO);        // [K][2][NO]
+    const float scale = (float)((double)NO / (double)NI);
+    const float tr = PASTE ? (float)((double)(FP - DP) / (double)DP) : (float)((double)(FP - DP) / (double)FP);
+    for (int i = threadIdx.x; i < K * 2 * NO; i += blockDim.x) {
+        const int k = i / (2 * NO), ax = (i / NO) & 1, j = i % NO;
+        const float* zw = a.z_where + ((long long)sbt * K + k) * 2;
+        float tt;
+        if (PASTE) tt = ax == 0 ? __fmul_rn(__ldg(zw + 1), tr) : -__fmul_rn(__ldg(zw), tr);      // affine_transformer.py:47-49
+        else tt = ax == 0 ? -__fmul_rn(__ldg(zw + 1), tr) : __fmul_rn(__ldg(zw), tr);            // :60-62
+        stn_axis_bilinear(__ldg(a.lin + j), scale, tt, NI, s_i0[i], s_f[i]);
+    }
+    __syncthreads();
+    float* out = a.dst + (long long)sbt * K * NO * NO;
+    for (int o = threadIdx.x; o < K * NO * NO; o += blockDim.x) {
+        const int k = o / (NO * NO), i = (o / NO) % NO, j = o % NO;
+        const float* img = PASTE ? a.src + (((long long)s * a.B + b) * K + k) * DP * DP
+                                 : a.src + s * a.ss + b * a.sb + t * a.st;
+        const int r0 = s_i0[(k * 2 + 0) * NO + i], c0 = s_i0[(k * 2 + 1) * NO + j];
+        const float fr = s_f[(k * 2 + 0) * NO + i], fc = s_f[(k * 2 + 1) * NO + j];
+        float v = 0.f;
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+            for (int dc = 0; dc < 2; ++dc) {
+                const int r = r0 + dr, c = c0 + dc;
+                if (r >= 0 && r < NI && c >= 0 && c < NI)
+                    v = fmaf(__ldg(img + r * NI + c), (dr ? fr : 1.f - fr) * (dc ? fc : 1.f - fc), v);
+            }
+        out[o] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- B4
 #define LOG_SQRT_2PI_F 0.918938533204672741780329736406f
 __device__ __forceinline__ float normal_lp(float v, float loc, float scale) {      // torch normal.py:87-101
@@ -263,6 +317,35 @@ extern "C" int apgs_bmnist_crop_f32(const float* frames, int64_t stride_s, int64
     const size_t smem = (size_t)K * 2 * DP * sizeof(int);
     k_stn_crop<<<(unsigned int)(S * B * T), 256, smem, (cudaStream_t)stream>>>(a);
     APGS_LAUNCH_OK("k_stn_crop launch");
+    return 0;
+}
+
+extern "C" int apgs_bmnist_crop_bilinear_f32(const float* frames, int64_t stride_s, int64_t stride_b, int64_t stride_t,
+                                             const float* z_where, const float* lin_dp, int64_t S, int64_t B, int64_t T,
+                                             int64_t K, int64_t FP, int64_t DP, float* digits_out, void* stream) {
+    if (int e = check_stn(S, B, T, K, FP, DP, "bmnist_crop_bilinear")) return e;
+    if (!frames || !z_where || !lin_dp || !digits_out) return fail(APGS_E_BADARG, "bmnist_crop_bilinear: NULL pointer");
+    StnArgs a = {};
+    a.src = frames; a.ss = stride_s; a.sb = stride_b; a.st = stride_t; a.z_where = z_where; a.lin = lin_dp;
+    a.dst = digits_out; a.S = (int)S; a.B = (int)B; a.T = (int)T; a.K = (int)K; a.FP = (int)FP; a.DP = (int)DP;
+    const size_t smem = (size_t)K * 2 * DP * 8;
+    k_stn_bilinear<false><<<(unsigned int)(S * B * T), 256, smem, (cudaStream_t)stream>>>(a);
+    APGS_LAUNCH_OK("k_stn_bilinear<crop> launch");
+    return 0;
+}
+
+extern "C" int apgs_bmnist_paste_bilinear_f32(const float* digits, const float* z_where, const float* lin_fp, int64_t S,
+                                              int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP, float* frames_out,
+                                              void* stream) {
+    if (int e = check_stn(S, B, T, K, FP, DP, "bmnist_paste_bilinear")) return e;
+    if (!digits || !z_where || !lin_fp || !frames_out) return fail(APGS_E_BADARG, "bmnist_paste_bilinear: NULL pointer");
+    StnArgs a = {};
+    a.src = digits; a.z_where = z_where; a.lin = lin_fp; a.dst = frames_out;
+    a.S = (int)S; a.B = (int)B; a.T = (int)T; a.K = (int)K; a.FP = (int)FP; a.DP = (int)DP;
+    const size_t smem = (size_t)K * 2 * FP * 8;
+    if (smem > 48 * 1024) return fail(APGS_E_SHAPE, "bmnist_paste_bilinear: K*FP too large");
+    k_stn_bilinear<true><<<(unsigned int)(S * B * T), 256, smem, (cudaStream_t)stream>>>(a);
+    APGS_LAUNCH_OK("k_stn_bilinear<paste> launch");
     return 0;
 }
 

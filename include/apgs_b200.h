@@ -364,6 +364,16 @@ APGS_API int apgs_bmnist_crop_f32(const float* frames, int64_t stride_s, int64_t
 APGS_API int apgs_bmnist_paste_f32(const float* digits, const float* z_where, const float* lin_fp,
                           int64_t S, int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP,
                           float* frames_out, void* stream);
+/* Bilinear mode of B1 / B2 (north_star item 4; the reference itself samples with mode='nearest', SURVEY.md F5, which is
+ * the parity-checked mode above): grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) semantics on
+ * the same diagonal affine grid.  Same arguments and layouts as apgs_bmnist_crop_f32 / apgs_bmnist_paste_f32.         */
+APGS_API int apgs_bmnist_crop_bilinear_f32(const float* frames, int64_t stride_s, int64_t stride_b, int64_t stride_t,
+                         const float* z_where, const float* lin_dp,
+                         int64_t S, int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP,
+                         float* digits_out, void* stream);
+APGS_API int apgs_bmnist_paste_bilinear_f32(const float* digits, const float* z_where, const float* lin_fp,
+                          int64_t S, int64_t B, int64_t T, int64_t K, int64_t FP, int64_t DP,
+                          float* frames_out, void* stream);
 /* B2+B3  paste + sum over digits + clamp + Bernoulli-like pixel log-likelihood, fused.
  * replaces the tail of Dec_digit.forward, apgs/bmnist/models.py:148-154, and MBern_log_prob :156-162.
  *   ll_out (S,B,T); recon_out (S,B,T,FP,FP) or NULL.  The (S,B,T,K,FP,FP) pasted tensor never exists.  */

@@ -387,3 +387,40 @@ def test_bmnist_match_and_residual_kernels_stay_inside_their_buffers():
         assert bool((buf[:G] == -7.0).all()) and bool((buf[-G:] == -7.0).all())
     np.testing.assert_allclose(out.view(S, B, -1).sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
     assert bool(torch.isfinite(res).all())
+
+
+@pytest.mark.parametrize("S,B,T,K", [(2, 3, 4, 3), (1, 1, 1, 1)])
+def test_stn_bilinear_mode_vs_torch_grid_sample(S, B, T, K):
+    """the bilinear mode switch (north_star item 4): digit_to_frame / frame_to_digit with mode='bilinear' against
+    affine_grid + grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) on the reference's own theta
+    (apgs/bmnist/affine_transformer.py:41-65), incl. digits partly outside the frame."""
+    import torch.nn.functional as F
+    from apgs_b200.bmnist import Affine_Transformer
+    FP, DP = 96, 28
+    torch.manual_seed(S + T)
+    AT = Affine_Transformer(FP, DP, True, DEV, mode="bilinear")
+    digit = torch.rand(S, B, K, DP, DP, device=DEV)
+    frames = torch.rand(S, B, T, FP, FP, device=DEV)
+    z = (torch.rand(S, B, T, K, 2, device=DEV) * 2 - 1) * 1.2
+    # reference expressions (diagonal theta), on the GPU through stock torch ops
+    M = S * B * T * K
+    s_dtof = torch.tensor([[FP / DP, 0], [0, FP / DP]], device=DEV).repeat(S, B, T, K, 1, 1)
+    zz = z.clone()
+    zz[..., 0] = zz[..., 0] * -1
+    theta = torch.cat((s_dtof, (zz * ((FP - DP) / DP)).unsqueeze(-1)), -1).view(M, 2, 3)
+    grid = F.affine_grid(theta, torch.Size((M, 1, FP, FP)), align_corners=True)
+    ref_paste = F.grid_sample(digit.unsqueeze(2).repeat(1, 1, T, 1, 1, 1).view(M, DP, DP).unsqueeze(1), grid, mode="bilinear",
+                              padding_mode="zeros", align_corners=True).squeeze(1).view(S, B, T, K, FP, FP)
+    out = AT.digit_to_frame(digit, z)
+    torch.testing.assert_close(out, ref_paste, rtol=1e-5, atol=2e-6)
+    s_ftod = torch.tensor([[DP / FP, 0], [0, DP / FP]], device=DEV).repeat(S, B, T, K, 1, 1)
+    zz = z.clone()
+    zz[..., 1] = zz[..., 1] * -1
+    theta = torch.cat((s_ftod, (zz * ((FP - DP) / FP)).unsqueeze(-1)), -1).view(M, 2, 3)
+    grid = F.affine_grid(theta, torch.Size((M, 1, DP, DP)), align_corners=True)
+    ref_crop = F.grid_sample(frames.unsqueeze(3).repeat(1, 1, 1, K, 1, 1).view(M, FP, FP).unsqueeze(1), grid, mode="bilinear",
+                             padding_mode="zeros", align_corners=True).squeeze(1).view(S, B, T, K, DP, DP)
+    out = AT.frame_to_digit(frames, z)
+    torch.testing.assert_close(out, ref_crop, rtol=1e-5, atol=2e-6)
+    # the default stays the reference's nearest mode
+    assert Affine_Transformer(FP, DP, True, DEV).mode == "nearest"
