@@ -494,10 +494,21 @@ def extras(cx, args, peak):
     ms = cx.timed(fn, 5) / 5
     prof, _ = profile_step(fn, 1)
     top = _dominant(prof, peak)
+    roof = {"kernel": top[0]["kernel"], "bound": "hbm", "achieved": top[0]["alg_GBs"], "peak": peak, "unit": "GB/s", "frac": top[0]["frac_hbm"]}
+    le = prof.get("dmm_local_encoder_fused")
+    if le and top[0]["kernel"] == "dmm_local_encoder_fused":
+        # k_dmm_local_fused is a fused MLP, not a stream: per point K*H ReLU units of the pi MLP (3 FMA-pipe lane-cycles: first
+        # layer, max, output FMA) and 2 nets x 2 assignments x H tanh units of the Beta-concentration MLPs (4.25: pair inversion)
+        H = 32
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        cyc = S * B * N * (K * H * 3.0 + 4 * H * 4.25)
+        ach = cyc / (le["ms_avg"] * 1e-3) / 1e12
+        pk = sms * 128 * 1965e6 / 1e12
+        roof = {"kernel": "k_dmm_local_fused", "bound": "fp32 FMA pipe (fused per-point MLPs)", "achieved": ach, "peak": pk,
+                "unit": "T lane-cycles/s", "frac": ach / pk, "alg_GBs": le["gbs"], "frac_hbm": le["gbs"] / peak}
     out["C3_dmm"] = {"workload": "DMM K=4 N=200 D=2, S=100 x B=256 per GPU, 7 sweeps, systematic", "value": world * S * B * sweeps / (ms / 1e3),
                      "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "scaling": "weak", "dominant_kernels": top,
-                     "roofline": {"kernel": top[0]["kernel"], "bound": "hbm", "achieved": top[0]["alg_GBs"], "peak": peak,
-                                  "unit": "GB/s", "frac": top[0]["frac_hbm"]}}
+                     "roofline": roof}
     del models, x
     # ---- C4: bouncing MNIST K=3 digits, T=10 frames of 96x96, S=10, B=64 per GPU, 5 sweeps
     from apgs_b200.bmnist import apg_objective as bm_objective, init_models as bm_models, Affine_Transformer
