@@ -705,20 +705,37 @@ static int launch_eta_stats(const EtaStatsArgs& a, cudaStream_t st) {
 
 // ----------------------------------------------------------------------------------- launchers
 
+// lanes per particle / particles per CTA of the instance-major statistics kernel.  4 lanes x 64 particles: the per-lane
+// costs that do not depend on the number of points (cross-lane reduction, posterior update, row pointers) and the
+// per-CTA head table are spread over twice the points per thread compared with 8 x 32.
+constexpr int kImLanes = kEtaNssLanes, kImP = 256 / kImLanes;
+
 template <int K, int D>
 static int launch_nss_im(const NssArgs& a, cudaStream_t st) {
     constexpr int NS = K * (1 + 2 * D), TE = K + 2 * K * D;
     constexpr int RW = (TE > NS ? TE : NS) | 1;
     const long long S = a.R / a.B;
-    const size_t zreg = (max((size_t)kP * nss_im_zstride(a.N * K), (size_t)kP * kLanes * RW) + 3) / 4 * 4;
+    const size_t zreg = (max((size_t)kImP * nss_im_zstride(a.N * K), (size_t)kImP * kImLanes * RW) + 3) / 4 * 4;
     const size_t smem = (zreg + (size_t)a.N * K * TE + (size_t)a.N * D) * 4;
-    if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_eta_posterior: N=%d too large for one tile", a.N);
-    void (*kern)(NssArgs, int) = a.stats != nullptr ? k_gmm_nss_im<K, D, kP, kLanes, true> : k_gmm_nss_im<K, D, kP, kLanes, false>;
-    if (a.stats != nullptr && a.N == 60) kern = k_gmm_nss_im<K, D, kP, kLanes, true, 60>;      // the reference's data set
+    if (smem > 200 * 1024) {
+        // the one-hot rows of 64 particles do not fit: 32 particles x 8 lanes
+        const size_t zreg8 = (max((size_t)kP * nss_im_zstride(a.N * K), (size_t)kP * kLanes * RW) + 3) / 4 * 4;
+        const size_t smem8 = (zreg8 + (size_t)a.N * K * TE + (size_t)a.N * D) * 4;
+        if (smem8 > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_eta_posterior: N=%d too large for one tile", a.N);
+        void (*kern8)(NssArgs, int) = a.stats != nullptr ? k_gmm_nss_im<K, D, kP, kLanes, true> : k_gmm_nss_im<K, D, kP, kLanes, false>;
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern8), smem8), "smem attr");
+        const long long grid8 = (long long)a.B * ((S + kP - 1) / kP);
+        if (grid8 > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_eta_posterior: S*B too large for one launch");
+        kern8<<<(unsigned int)grid8, kP * kLanes, smem8, st>>>(a, (int)S);
+        APGS_LAUNCH_OK("k_gmm_nss_im launch");
+        return 0;
+    }
+    void (*kern)(NssArgs, int) = a.stats != nullptr ? k_gmm_nss_im<K, D, kImP, kImLanes, true> : k_gmm_nss_im<K, D, kImP, kImLanes, false>;
+    if (a.stats != nullptr && a.N == 60) kern = k_gmm_nss_im<K, D, kImP, kImLanes, true, 60>;      // the reference's data set
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
-    const long long grid = (long long)a.B * ((S + kP - 1) / kP);
+    const long long grid = (long long)a.B * ((S + kImP - 1) / kImP);
     if (grid > 0x7fffffffLL) return fail(APGS_E_SHAPE, "gmm_eta_posterior: S*B too large for one launch");
-    kern<<<(unsigned int)grid, kP * kLanes, smem, st>>>(a, (int)S);
+    kern<<<(unsigned int)grid, kImP * kImLanes, smem, st>>>(a, (int)S);
     APGS_LAUNCH_OK("k_gmm_nss_im launch");
     return 0;
 }

@@ -126,6 +126,13 @@ __device__ __forceinline__ float tanh_prescaled(float a) {
 // statistics { cnt_k, sum z (x - c), sum z (x - c)^2 } that the eta-step log-likelihoods are functions of.
 // Both kernels run EXACTLY this code, so they agree bit for bit.
 // ---------------------------------------------------------------------------------------------------------------
+// lanes that split a particle's points in the statistics accumulation (k_gmm_nss_im: 4 lanes x 64 particles per CTA).
+// The fused z step keeps the same partition -- lanes >= kEtaNssLanes of its 8 idle in that pass -- so both agree bit for bit.
+#ifndef APGS_NSS_IM_LANES
+#define APGS_NSS_IM_LANES 4
+#endif
+constexpr int kEtaNssLanes = APGS_NSS_IM_LANES;
+
 template <int K, int D>
 struct EtaTab {
     // row stride (floats): a multiple of four with an odd number of quads, so consecutive rows fall on distinct banks
@@ -291,26 +298,30 @@ __device__ __forceinline__ void ng_posterior_elem(float f1, float f2, float f3, 
     beta = __fadd_rn(__fadd_rn(b0, u1), u2);
 }
 
-// A particle's LANES partials meet in a scratch block (LANES rows of RW floats): lane j = (k, d) < K D finishes one
-// posterior element (fp64 across lanes), then every lane sums its share of the plain statistics (fp32, lane order).
+// A particle's LANES partials meet in a scratch block (LANES rows of RW floats): lane j finishes the posterior elements
+// e = j, j + LANES, ... (fp64 across lanes), then every lane sums its share of the plain statistics (fp32, lane order).
 // Called by all lanes of the warp (the __syncwarp()s are unconditional); only `valid` particles write.
 template <int K, int D, int LANES, bool STATS>
 __device__ __forceinline__ void eta_nss_finish(EtaNssAcc<K, D, STATS>& acc, float* blk, int j, bool valid, long long r,
                                                const float* ra, const float* rb, const float* rm, const float* rn,
                                                float* oa, float* ob, float* om, float* on, float* stats) {
     constexpr int KD = K * D, RW = EtaTab<K, D>::RW, NS = EtaTab<K, D>::NS;
-    static_assert(KD <= LANES, "one posterior element per lane");
+    constexpr int EPL = (KD + LANES - 1) / LANES;                  // posterior elements per lane
     float* mine = blk + j * RW;
     acc.spill_nss(mine);
     __syncwarp();
-    double n1 = 0.0, n2 = 0.0, n3 = 0.0;
-    const bool fin = valid && j < KD;
-    if (fin) {
-        const int k = j / D;
+    double n1[EPL], n2[EPL], n3[EPL];
 #pragma unroll
-        for (int i = 0; i < LANES; ++i) {
-            const float* o = blk + i * RW;
-            n1 += (double)o[k]; n2 += (double)o[K + j]; n3 += (double)o[K + KD + j];
+    for (int q = 0; q < EPL; ++q) {
+        n1[q] = 0.0; n2[q] = 0.0; n3[q] = 0.0;
+        const int e = j + q * LANES;
+        if (valid && e < KD) {
+            const int k = e / D;
+#pragma unroll
+            for (int i = 0; i < LANES; ++i) {
+                const float* o = blk + i * RW;
+                n1[q] += (double)o[k]; n2[q] += (double)o[K + e]; n3[q] += (double)o[K + KD + e];
+            }
         }
     }
     if (STATS) {
@@ -327,11 +338,16 @@ __device__ __forceinline__ void eta_nss_finish(EtaNssAcc<K, D, STATS>& acc, floa
             }
         }
     }
-    if (!fin) return;
-    float alpha, beta, mu, nu;
-    ng_posterior_elem((float)n1, (float)n2, (float)n3, __ldg(ra + j), __ldg(rb + j), __ldg(rm + j), __ldg(rn + j), alpha, beta, mu, nu);
-    const long long o = r * KD + j;
-    oa[o] = alpha; ob[o] = beta; om[o] = mu; on[o] = nu;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+        const int e = j + q * LANES;
+        if (!(valid && e < KD)) continue;
+        float alpha, beta, mu, nu;
+        ng_posterior_elem((float)n1[q], (float)n2[q], (float)n3[q], __ldg(ra + e), __ldg(rb + e), __ldg(rm + e), __ldg(rn + e), alpha, beta,
+                          mu, nu);
+        const long long o = r * KD + e;
+        oa[o] = alpha; ob[o] = beta; om[o] = mu; on[o] = nu;
+    }
 }
 
 }  // namespace apgs

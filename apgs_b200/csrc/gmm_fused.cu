@@ -566,8 +566,8 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
         }
     }
     if constexpr (NSS) {
-        // ---- the next eta step's inputs from the labels just drawn (k_gmm_nss_im's arithmetic, same order: this lane
-        // owns the points n = j, j + LANES, ... -- exactly the labels it wrote itself)
+        // ---- the next eta step's inputs from the labels just drawn (k_gmm_nss_im's arithmetic in its order: lanes
+        // j < kEtaNssLanes own the points n = j, j + kEtaNssLanes, ...; the other lanes contribute zeros)
         EtaNssAcc<K, D, true> acc;
         {
             float cen[K][D];
@@ -578,8 +578,9 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
                 for (int d = 0; d < D; ++d) cen[k][d] = valid ? tab[(k * D + d) * 3] : 0.f;      // this particle's mu
             acc.init(cen);
         }
-        if (valid) {
-            for (int n = j; n < N; n += LANES) {
+        __syncwarp();                                  // the labels of the particle's other lanes
+        if (valid && j < kEtaNssLanes) {
+            for (int n = j; n < N; n += kEtaNssLanes) {
                 const int lab = min((int)s_lb[(size_t)p * LS + n], K - 1);
                 acc.add(s_nt + (size_t)(n * K + lab) * EtaTab<K, D>::RS, lab, s_x + n * D);
             }
