@@ -19,59 +19,6 @@ def needs_grad(*modules):
                                            for p in m.parameters())
 
 
-# ---------------------------------------------------------------------------------------------------------------
-# The task's one dense contraction: Enc_coor's Linear(4761 -> 400) (and Enc_digit's Linear(784 -> 400)).  As plain
-# fp32 `nn.Linear` cuBLAS runs them on the SIMT pipe (~40 % of the C4 step); a single TF32 pass is 1e-3 off.  3xTF32
-# keeps them on the tensor cores at fp32 accuracy: x = x_hi + x_lo, W = W_hi + W_lo with the `hi` parts exactly
-# representable in TF32 (low 13 mantissa bits cleared), and  x W^T ~= x_hi W_hi^T + (x_hi W_lo^T + x_lo W_hi^T)  with fp32
-# accumulation -- the dropped x_lo W_lo^T term and the TF32 rounding of the `lo` parts are ~2^-22 relative to
-# sum |x| |w|, below the summation-order noise of the SIMT GEMM itself.  Library GEMMs (cuBLAS via torch.matmul), not a
-# kernel of this repo (north_star: the encoders stay in PyTorch / cuBLAS); evaluation path only (no autograd graph).
-# ---------------------------------------------------------------------------------------------------------------
-_TF32_MASK = -8192            # 0xFFFFE000 as int32: keep sign, exponent and the top 10 mantissa bits
-_split_cache = {}
-linear_3xtf32_enabled = True
-
-
-def _split_tf32(t):
-    hi = (t.contiguous().view(torch.int32) & _TF32_MASK).view(torch.float32)
-    return hi, t - hi
-
-
-def linear_3xtf32(x, weight, bias=None):
-    """F.linear(x, weight, bias) through three TF32 tensor-core GEMMs at fp32 accuracy (see above)."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
-    ent = _split_cache.get(key[0])
-    if ent is None or ent[0] != key:                     # the split of the weight is reused until the weight changes
-        if len(_split_cache) >= 16:
-            _split_cache.clear()
-        wh, wl = _split_tf32(weight.detach())
-        ent = (key, wh.t().contiguous(), wl.t().contiguous())
-        _split_cache[key[0]] = ent
-    _, wh_t, wl_t = ent
-    x2 = x.detach().reshape(-1, x.shape[-1])
-    xh, xl = _split_tf32(x2)
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        y = torch.mm(xh, wl_t)
-        y.addmm_(xl, wh_t)
-        y.addmm_(xh, wh_t)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-    if bias is not None:
-        y += bias.detach()
-    return y.view(x.shape[:-1] + (weight.shape[0],))
-
-
-def _big_linear(lin, x):
-    """the first Linear of an encoder: 3xTF32 on the evaluation path of a CUDA run, the plain module otherwise"""
-    if (linear_3xtf32_enabled and x.is_cuda and x.dtype == torch.float32 and lin.in_features >= 512
-            and not (torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad))):
-        return linear_3xtf32(x, lin.weight, lin.bias)
-    return lin(x)
-
-
 class Enc_coor(nn.Module):
     """encoder of the digit positions (models.py:7-38)"""
 
@@ -84,7 +31,7 @@ class Enc_coor(nn.Module):
                                            nn.Linear(int(0.5 * num_hidden), z_where_dim))
 
     def params(self, conved):
-        hidden = self.enc_hidden[1](_big_linear(self.enc_hidden[0], conved))
+        hidden = self.enc_hidden(conved)
         return self.where_mean(hidden), self.where_log_std(hidden).exp()
 
     def forward(self, conved, sampled=True, z_where_old=None):
@@ -109,8 +56,7 @@ class Enc_digit(nn.Module):
         self.q_log_std = nn.Sequential(nn.Linear(int(0.5 * num_hidden), z_what_dim))
 
     def params(self, cropped):
-        h = self.enc_hidden[1](_big_linear(self.enc_hidden[0], cropped))
-        hidden = self.enc_hidden[3](self.enc_hidden[2](h)).mean(2)          # T is the 3rd dim of cropped
+        hidden = self.enc_hidden(cropped).mean(2)          # T is the 3rd dim of cropped
         return self.q_mean(hidden), self.q_log_std(hidden).exp()
 
     def forward(self, cropped, sampled=True, z_what_old=None):

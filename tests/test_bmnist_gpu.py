@@ -424,35 +424,3 @@ def test_stn_bilinear_mode_vs_torch_grid_sample(S, B, T, K):
     torch.testing.assert_close(out, ref_crop, rtol=1e-5, atol=2e-6)
     # the default stays the reference's nearest mode
     assert Affine_Transformer(FP, DP, True, DEV).mode == "nearest"
-
-
-@pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (1920, 784, 400), (7, 513, 3)])
-def test_linear_3xtf32_keeps_fp32_accuracy(M, K, N):
-    """the 3xTF32 form of the encoders' big Linear layers (tensor cores) against an fp64 evaluation: at least as close as
-    the fp32 F.linear it replaces, and within 1e-6 of sum |x| |w| (a single TF32 pass is ~1e-3 off)."""
-    from apgs_b200.bmnist import models as M_
-    torch.manual_seed(M + N)
-    x = torch.softmax(torch.randn(M, K, device=DEV) * 3, -1) if K == 4761 else torch.rand(M, K, device=DEV)
-    lin = torch.nn.Linear(K, N).to(DEV)
-    with torch.no_grad():
-        y = M_.linear_3xtf32(x, lin.weight, lin.bias)
-        y32 = torch.nn.functional.linear(x, lin.weight, lin.bias)
-        ref = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
-        mag = torch.nn.functional.linear(x.abs().double(), lin.weight.abs().double()) + lin.bias.abs().double()
-    err = ((y.double() - ref).abs() / mag).max()
-    err32 = ((y32.double() - ref).abs() / mag).max()
-    assert float(err) < 1e-6, float(err)
-    assert float(err) < 4 * float(err32) + 2e-7, (float(err), float(err32))
-    # the module path takes it on the evaluation path only
-    enc = M_.Enc_coor(K, 8, 2).to(DEV) if K >= 512 else None
-    if enc is not None:
-        with torch.no_grad():
-            a = enc.params(x)[0]
-            M_.linear_3xtf32_enabled = False
-            try:
-                b = enc.params(x)[0]
-            finally:
-                M_.linear_3xtf32_enabled = True
-        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
-        out = enc.params(x)[0]                       # parameters require grad and autograd is on: the plain module (graph kept)
-        assert out.requires_grad
