@@ -144,7 +144,7 @@ __host__ __device__ inline int zf_block_floats(int H4) {
 // The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
 // HC / NC: hidden width and points per instance when known at compile time (the reference's 32 and 60), else 0.
 template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0, bool NSS = false>
-__global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedArgs a) {
+__global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fused(ZFusedArgs a) {
     static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
     static_assert(!NSS || LEAN, "the eta statistics ride on the lean label-mode launch");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -629,7 +629,10 @@ __global__ void __launch_bounds__(P* LANES, LEAN ? 4 : 3) k_gmm_z_fused(ZFusedAr
 // 32 particles per CTA (3 CTAs/SM).  Measured alternatives on the lean launch: 16 particles (6 CTAs/SM, phases less
 // correlated, twice the Ex-table work) 1.23 ms vs 1.20; tau / mu loads hoisted above the Ex table 1.22 ms; a CTA that
 // walks four chunks of its instance (one Ex table, no CTA barrier after the first chunk) 1.21 ms.
-constexpr int kFP = 32, kFLanes = 8, kFPB = 4;
+#ifndef APGS_ZF_P
+#define APGS_ZF_P 32
+#endif
+constexpr int kFP = APGS_ZF_P, kFLanes = 8, kFPB = 4;
 
 template <int K, int D, bool NSS>
 static int launch_zfused_lean(const ZFusedArgs& a, cudaStream_t st, size_t smem_used) {
