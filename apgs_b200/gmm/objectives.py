@@ -137,6 +137,50 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
 
 
 rng_in_kernels = True          # eta step: Gamma / Normal variates drawn inside the weight kernel (else torch._standard_gamma / randn)
+_SIDE_STREAMS = {}
+
+
+def apg_objective_streams(models, x, result_flags, num_sweeps, block, resampler, parts=2):
+    """apg_objective with the instance batch cut into `parts` contiguous slices that run on separate CUDA streams.
+    Instances never interact (every op normalises / scans / gathers over S within one instance), so the slices
+    are independent sweeps; on separate streams the latency-bound launches of one slice (ancestors, gather, eta weights,
+    the small PyTorch glue) overlap the compute-bound z step of the other.  Capturable: inside a CUDA graph the slices
+    become parallel branches.  Same trace as apg_objective (slices concatenated along the instance axis)."""
+    B = x.shape[-3]
+    parts = max(1, min(int(parts), B))
+    if parts == 1:
+        return apg_objective(models, x, result_flags, num_sweeps, block, resampler)
+    main = torch.cuda.current_stream(x.device)
+    key = (x.device, parts)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=x.device) for _ in range(parts)]
+    bounds = [(i * B // parts, (i + 1) * B // parts) for i in range(parts)]
+    outs = []
+    for (lo, hi), st in zip(bounds, _SIDE_STREAMS[key]):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            xs = x.narrow(x.dim() - 3, lo, hi - lo)
+            outs.append(apg_objective(models, xs, result_flags, num_sweeps, block, resampler))
+    for st in _SIDE_STREAMS[key]:
+        main.wait_stream(st)
+    trace = {}
+    for k, v0 in outs[0].items():
+        if not torch.is_tensor(v0):
+            trace[k] = v0
+            continue
+        vs = [o[k] for o in outs]
+        for v in vs:
+            v.record_stream(main)
+        if k.startswith('loss'):                                   # means over the instances of a slice -> of the batch
+            w = torch.tensor([hi - lo for lo, hi in bounds], dtype=v0.dtype, device=v0.device) / float(B)
+            trace[k] = sum(wi * v for wi, v in zip(w, vs))
+        elif k == 'density':
+            trace[k] = torch.cat(vs, 2)                            # (sweeps, S, B)
+        else:
+            trace[k] = torch.cat(vs, 1)                            # ess / log_z (sweeps, B); E_* (sweeps, B, ...)
+    return trace
+
+
 train_on_kernels = True        # loss_required: graphs of log q through the kernels (train.py) instead of PyTorch encoders
 compact_labels = True          # module switches (tests compare the representations / the two one-shot paths)
 lean_oneshot = True

@@ -238,7 +238,7 @@ def profile_step(fn, passes=2):
 
 def run_ours(args):
     from apgs_b200 import ops, dist as adist
-    from apgs_b200.gmm import apg_objective, init_apg_models
+    from apgs_b200.gmm import apg_objective, apg_objective_streams, init_apg_models
     from apgs_b200.resampler import Resampler
     from apgs_b200.gmm.sim import simulate
 
@@ -257,6 +257,8 @@ def run_ours(args):
     x_dev = x_host.to(dev)
 
     def objective(x):
+        if args.streams > 1:
+            return apg_objective_streams(models, x, FLAGS, sweeps, 'decomposed', resampler, parts=args.streams)
         return apg_objective(models, x, FLAGS, sweeps, 'decomposed', resampler)
 
     def step_eager(x):
@@ -618,6 +620,7 @@ def main():
     ap.add_argument("--encoder", default="auto", choices=["auto", "torch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C4 / C5 / strong-scaling entries of `configs`")
+    ap.add_argument("--streams", type=int, default=1, help="slices of the instance batch run on separate CUDA streams")
     ap.add_argument("--graph", default="auto", choices=["auto", "off"], help="replay the objective as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
