@@ -695,10 +695,17 @@ __global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
     if (a.log_w_b != nullptr) a.log_w_b[r] = lwb;
 }
 
+#ifndef APGS_ETA_W_LANES
+#define APGS_ETA_W_LANES 1
+#endif
 template <int K, int D>
 static int launch_eta_stats(const EtaStatsArgs& a, cudaStream_t st) {
-    const long long grid = (a.R + 31) / 32;
-    k_gmm_eta_weights_stats<K, D, 8><<<(unsigned int)grid, 256, 0, st>>>(a);
+    // lanes per particle, measured at K D = 6 on B200 (ms per launch): 8 lanes 0.172 (a quarter of them idle, three shuffle
+    // rounds for six sums), 4: 0.168, 2: 0.120, 1: 0.111 -- one thread walks the particle's K D elements (a warp still reads
+    // 32 adjacent 24-byte rows)
+    constexpr int EL = APGS_ETA_W_LANES;
+    const long long grid = (a.R + 256 / EL - 1) / (256 / EL);
+    k_gmm_eta_weights_stats<K, D, EL><<<(unsigned int)grid, 256, 0, st>>>(a);
     APGS_LAUNCH_OK("k_gmm_eta_weights_stats launch");
     return 0;
 }

@@ -22,10 +22,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ float u01_open(unsigned int x) { return ((x >> 8) + 0.5f) * 5.9604644775390625e-08f; }
 
 // two independent standard normals from two 32-bit words (Box-Muller)
+// (SFU forms: __logf / __sincosf are accurate to ~1e-6 absolute on these ranges -- a perturbation of the variate far below
+// the resolution of the 24-bit uniforms it is made from)
 __device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, float& n0, float& n1) {
-    const float r = sqrtf(-2.f * logf(u01_open(a)));
+    const float r = sqrtf(-2.f * __logf(u01_open(a)));
     float s, c;
-    sincospif(2.f * u01_open(b), &s, &c);
+    __sincosf(6.283185307179586f * u01_open(b) - 3.141592653589793f, &s, &c);      // angle in (-pi, pi)
     n0 = r * c; n1 = r * s;
 }
 
@@ -43,7 +45,7 @@ __device__ __forceinline__ float gamma_mt(float alpha, float x0, unsigned int u0
         if (t > 0.f) {
             const float v = t * t * t;
             const float u = u01_open(uw);
-            if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return scale * d * v;
+            if (__logf(u) < 0.5f * x * x + d - d * v + d * __logf(v)) return scale * d * v;
         }
         ctr.w = (unsigned int)attempt;
         const uint4 w = philox4x32_10(ctr, key);
