@@ -295,6 +295,9 @@ static const size_t kSmemTileBudget = 200 * 1024;
 
 struct AncPlan { int TB; int nthr; int tile_in_smem; int dbl; size_t smem; int grid; };
 
+#ifndef APGS_ANC_MIN_TB
+#define APGS_ANC_MIN_TB 4
+#endif
 static AncPlan plan_ancestors(long long S, long long B, bool want_dbl) {
     AncPlan p;
     int TB = 32;
@@ -304,7 +307,7 @@ static AncPlan plan_ancestors(long long S, long long B, bool want_dbl) {
     p.dbl = (want_dbl && p.tile_in_smem) ? 1 : 0;
     if (p.tile_in_smem) {
         // spread over the 148 SMs: shrink the column tile while the grid is under ~2 CTAs/SM
-        while (TB > 4 && (B + TB - 1) / TB < 2 * sm_count()) TB >>= 1;
+        while (TB > APGS_ANC_MIN_TB && (B + TB - 1) / TB < 2 * sm_count()) TB >>= 1;
     } else {
         TB = 8;
     }
