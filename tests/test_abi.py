@@ -105,3 +105,16 @@ def test_bad_arguments_of_the_fused_entry_points_are_rejected_before_launch():
     assert lib.apgs_bmnist_template_match_f32(P, 0, 9216, P, 784, 784, 4, 4, 28, 96, 1, P, None) < 0      # DP > FP
     assert lib.apgs_bmnist_template_match_f32(P, -1, 9216, P, 784, 784, 4, 4, 96, 28, 1, P, None) < 0
     assert lib.apgs_bmnist_paste_subtract_f32(P, 0, 9216, P, 784, 0, P, P, 4, 4, 96, 28, P, None) < 0
+
+
+def test_supported_shape_queries_need_no_gpu():
+    """apgs_gmm_supported / apgs_dmm_supported are pure host functions: the compiled (K, D) list the host layer consults
+    before it routes a shape to the kernels or to the generic PyTorch path."""
+    from apgs_b200 import _lib
+    lib = _lib.load()
+    assert lib.apgs_gmm_supported(3, 2) == 1 | 2 | 4 | 8          # reweighting, fused z step, fused eta heads, label mode
+    assert lib.apgs_gmm_supported(5, 2) == 1 | 2 | 4               # K D = 10 > 8: no label mode
+    assert lib.apgs_gmm_supported(4, 3) == 1 | 4                   # no fused z step
+    assert lib.apgs_gmm_supported(6, 2) == 0 and lib.apgs_gmm_supported(3, 4) == 0
+    assert lib.apgs_dmm_supported(4, 2) == 3 and lib.apgs_dmm_supported(7, 2) == 2 and lib.apgs_dmm_supported(4, 5) == 0
+    assert lib.apgs_gmm_label_table_sum_backward_splits(1000, 1024) >= 1
