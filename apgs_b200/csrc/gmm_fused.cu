@@ -15,6 +15,7 @@
 // packed fp32x2: 1.75 instructions (3.5 FMA-pipe cycles) and 0.25 SFU operations per tanh instead of 13 / 2.
 // Compute-bound (FMA pipe), not HBM-bound.
 #include "gmm_common.cuh"
+#include "rng.cuh"
 
 namespace apgs {
 
@@ -24,7 +25,8 @@ struct ZFusedArgs {
     const float *W1, *b1, *W2, *b2; // (H, 3D), (H), (H), (1)
     const float* z_old;             // (R, N, K) one-hot, or null (sample-only mode)
     const float* z_forced;          // (R, N, K) one-hot to use instead of sampling, or null
-    const float* u;                 // (R, N) uniforms in [0,1), required unless z_forced
+    const float* u;                 // (R, N) uniforms in [0,1), required unless z_forced or seed
+    const unsigned long long* seed; // device word keying the in-kernel Philox stream that replaces `u`, or null
     // label mode (compact latents inside a sweep): assignments as one byte per point instead of K one-hot floats
     const unsigned char* zl_old;    // (R, N) labels of the backward term, or null
     unsigned char* zl_new;          // (R, N) labels out, or null (then z_new one-hot is written)
@@ -44,6 +46,13 @@ struct ZFusedArgs {
     float *oa, *ob, *om, *on;                             // posterior out (R, K, D)
     float* stats;                                         // (R, K, 1 + 2 D) out
 };
+
+// in-kernel uniforms of the categorical draw: one Philox block per (particle row, lane, pass) -- its four words are the
+// uniforms of that lane's PB points of the pass; [0, 1) with 24 bits like torch.rand
+__device__ __forceinline__ uint4 philox_block(long long r, int slot, uint2 key) {
+    return philox4x32_10(make_uint4((unsigned int)r, (unsigned int)((unsigned long long)r >> 32), (unsigned int)slot, 0x7a737465u), key);
+}
+__device__ __forceinline__ float u01_co(unsigned int w) { return (float)(w >> 8) * 5.9604644775390625e-08f; }
 
 // ---- tile mapping -----------------------------------------------------------------------------------------------
 // A CTA owns ONE instance b and P particles s0..s0+P-1 of it (rows r = s*B + b: P separate N*K*4-byte rows, each
@@ -163,6 +172,9 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     const bool lab_old = LEAN || a.zl_old != nullptr, lab_new = LEAN || a.zl_new != nullptr;
     const bool has_bwd = LEAN || a.z_old != nullptr || lab_old;
     const bool forced = !LEAN && a.z_forced != nullptr;
+    const bool rng = a.seed != nullptr && !forced;
+    uint2 key = make_uint2(0u, 0u);
+    if (rng) { const unsigned long long sd = __ldg(a.seed); key = make_uint2((unsigned int)sd, (unsigned int)(sd >> 32)); }
     const bool hot_new = !LEAN && a.z_new != nullptr;                      // one-hot z_new wanted (labels may come along)
     const bool tiles = !LEAN && (a.z_old != nullptr || forced || hot_new); // any one-hot row staged in / out?
     const bool want_q = !LEAN && a.q_probs != nullptr, want_lw = !LEAN && a.lw_local != nullptr;
@@ -214,7 +226,20 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 
     if (LEAN && valid) {
         const float* ur = a.u + r * N;
-        if ((N & 3) == 0 && aligned(a.u, 16)) {                      // rows of N floats: every row start is 16-byte aligned
+        if (rng) {
+            // the uniforms of this lane's own points (read back by the same thread in the epilogue), made here -- while the
+            // label rows and the CTA's tables are in flight -- so that the main loop carries no generator state
+            static_assert(PB <= 4, "one Philox block carries four uniforms");
+            for (int it = 0; it < nIt; ++it) {
+                const uint4 w = philox_block(r, it * LANES + j, key);
+                const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < PB; ++q) {
+                    const int n = it * (LANES * PB) + j + q * LANES;
+                    if (n < N) s_u[(size_t)p * NU + n] = u01_co(ww[q]);
+                }
+            }
+        } else if ((N & 3) == 0 && aligned(a.u, 16)) {               // rows of N floats: every row start is 16-byte aligned
             for (int c = j; c < N / 4; c += LANES)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_u + (size_t)p * NU + c * 4)), "l"(ur + c * 4) : "memory");
         } else {
@@ -422,7 +447,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
                 if (!LEAN) {
-                    uq[q] = (n < N && !forced) ? __ldg(a.u + r * N + n) : 0.f;  // in flight during the MLP
+                    uq[q] = (n < N && !forced && !rng) ? __ldg(a.u + r * N + n) : 0.f;  // in flight during the MLP
                     lbq[q] = (n < N && lab_old) ? (int)__ldg(zlo + n) : 0;
                 }
             }
@@ -454,6 +479,12 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 #pragma unroll
                     for (int d = 0; d < D; ++d) xq[q][d] = (n0 + q * LANES < N) ? s_x[(n0 + q * LANES) * D + d] : 0.f;
                 mlp_quad_plain<K, D, PB>(a.W1, xq, ep, s_aw, H, logit);
+            }
+            if (!LEAN && rng) {
+                const uint4 w = philox_block(r, it * LANES + j, key);
+                const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < PB; ++q) uq[q] = u01_co(ww[q]);
             }
             // ---- per point: softmax, draw, log-densities
 #pragma unroll
@@ -652,7 +683,7 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
     const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
     const bool nss = a.oa != nullptr;
-    const bool lean = a.zl_old && a.zl_new && a.u && !tiles && !a.q_probs && !a.lw_local && !a.lq_local &&
+    const bool lean = a.zl_old && a.zl_new && (a.u || a.seed) && !tiles && !a.q_probs && !a.lw_local && !a.lq_local &&
                       !a.log_w_f && !a.log_w_b;
     if (nss && !lean) return fail(APGS_E_BADARG, "gmm_z_fused: the eta statistics ride on the lean label-mode launch only");
     constexpr bool kNssOk = K * D <= kFLanes;
@@ -703,18 +734,19 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
                         int64_t B, int64_t N, int64_t K, int64_t D, float* z_new, unsigned char* z_new_lab,
                         int64_t label_stride, float* q_probs, const apgs_gmm_out_t* out, void* stream,
                         const float* const* heads = nullptr, const apgs_gmm_post_out_t* post_out = nullptr,
-                        float* stats_out = nullptr) {
+                        float* stats_out = nullptr, const uint64_t* philox_seed = nullptr) {
     if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024)
         return fail(APGS_E_SHAPE, "gmm_z_step_fused: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S, (long long)B,
                     (long long)N, (long long)H);
     if (!x || !tau || !mu || !W1 || !b1 || !W2 || !b2 || !prior || !prior->pi || (!z_new && !z_new_lab))
         return fail(APGS_E_BADARG, "gmm_z_step_fused: NULL input");
-    if (!z_forced && !uniforms) return fail(APGS_E_BADARG, "gmm_z_step_fused: uniforms (or z_forced) required");
+    if (!z_forced && !uniforms && !philox_seed) return fail(APGS_E_BADARG, "gmm_z_step_fused: uniforms (or z_forced) required");
     if (z_old && z_old_lab) return fail(APGS_E_BADARG, "gmm_z_step_fused: give z_old either one-hot or as labels, not both");
     if (K > 255) return fail(APGS_E_SHAPE, "gmm_z_step_fused: K=%lld does not fit a label byte", (long long)K);
     ZFusedArgs a = {};
     a.x = x; a.tau = tau; a.mu = mu; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
     a.z_old = z_old; a.zl_old = z_old_lab; a.z_forced = z_forced; a.u = uniforms; a.rpi = prior->pi;
+    a.seed = reinterpret_cast<const unsigned long long*>(philox_seed);
     a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
     a.z_new = z_new; a.zl_new = z_new_lab; a.LN = label_stride; a.q_probs = q_probs;
     if (out) {
@@ -777,4 +809,26 @@ extern "C" int apgs_gmm_z_step_fused_labels_eta_f32(const float* x, const float*
     const float* heads[4] = {Wg, bg, Wo, bo};
     return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, nullptr, z_old_labels, nullptr, uniforms, S, B, N, K, D,
                         nullptr, z_new_labels, label_stride, nullptr, out, stream, heads, post_out, stats_out);
+}
+
+extern "C" int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, const float* mu, const float* W1,
+                                             const float* b1, const float* W2, const float* b2, int64_t H,
+                                             const apgs_gmm_prior_t* prior, const float* z_old_onehot,
+                                             const uint8_t* z_old_labels, const uint64_t* philox_seed, int64_t S, int64_t B,
+                                             int64_t N, int64_t K, int64_t D, float* z_new_onehot, uint8_t* z_new_labels,
+                                             int64_t label_stride, float* q_probs, const float* Wg, const float* bg,
+                                             const float* Wo, const float* bo, const apgs_gmm_post_out_t* post_out,
+                                             float* stats_out, const apgs_gmm_out_t* out, void* stream) {
+    if (!philox_seed) return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: philox_seed is NULL");
+    if (z_new_labels && label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: label_stride %lld < N", (long long)label_stride);
+    if (post_out || stats_out) {
+        if (!post_out || !stats_out || !z_old_labels || !z_new_labels || z_new_onehot || q_probs)
+            return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: the eta statistics ride on the labels-in / labels-out launch only");
+        if (out && (out->log_w_f || out->log_w_b || out->log_w_local || out->log_q_local))
+            return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: only log_w / log_q_f / density are available with the eta statistics");
+    }
+    const float* heads[4] = {Wg, bg, Wo, bo};
+    return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, z_old_onehot, z_old_labels, nullptr, nullptr, S, B, N, K, D,
+                        z_new_onehot, z_new_labels, z_new_labels ? label_stride : N, q_probs, out, stream,
+                        post_out ? heads : nullptr, post_out, stats_out, philox_seed);
 }

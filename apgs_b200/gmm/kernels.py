@@ -243,7 +243,7 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
 
 
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
-                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None):
+                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None, seed=None):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
     mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
     z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
@@ -252,8 +252,15 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     and Weights.density / .log_q_f carry log p(x, z | eta) and log q(z) of the draw.
     eta_heads = (Wg, bg, Wo, bo) of Enc_apg_eta (label mode only): the same launch also emits the NEXT eta step's inputs
     for the labels just drawn -- returns (z_new, None, Weights, (alpha, beta, mu_q, nu), stats) with stats the one-hot
-    statistics of z_new centred at `mu` -- bit-identical to eta_posterior_fused(x, z_new, heads, prior, center=mu)."""
+    statistics of z_new centred at `mu` -- bit-identical to eta_posterior_fused(x, z_new, heads, prior, center=mu).
+    seed = philox_seed(device) (a one-element int64 device tensor): the uniforms of the draw are made inside the kernel
+    (same distribution, Philox stream keyed by the seed) instead of being read from `uniforms`."""
     lib = _lib.load()
+    if seed is not None:
+        if uniforms is not None or z_forced is not None:
+            raise ValueError("seed replaces uniforms; it has no meaning with z_forced")
+        return _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot,
+                                 eta_heads, seed)
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
     S, B, K, D = tau.shape
@@ -333,6 +340,70 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
         check(lib.apgs_gmm_z_step_fused_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
                                             C.byref(rs), ptr(z_old), ptr(z_forced), ptr(uniforms), S, B, N, K, D,
                                             ptr(z_new), ptr(q), C.byref(o), _stream()), "apgs_gmm_z_step_fused_f32")
+    return z_new, q, w
+
+
+def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot, eta_heads, seed):
+    """z_step_fused with in-kernel uniforms: the same modes and return values, one entry point."""
+    x = _x3(x)
+    tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
+    S, B, K, D = tau.shape
+    N = x.shape[-2]
+    W1, b1, W2, b2 = [_req(v, "mlp weight") for v in mlp]
+    H = W1.shape[0]
+    if tuple(W1.shape) != (H, 3 * D) or W2.numel() != H or b1.numel() != H or b2.numel() != 1:
+        raise ValueError("unexpected Enc_apg_z weight shapes")
+    dev = tau.device
+    seed = _req(seed, "seed", dtype=torch.int64)
+    rs, rk = _prior_struct(prior)
+    z_hot_old = z_lab_old = z_hot = z_lab = post = stats = po = None
+    heads = [None] * 4
+    LN = N
+    if also_labels:
+        if z_old is not None:
+            raise ValueError("also_labels is a sample-only mode")
+        LN = int(also_labels)
+        z_hot = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_onehot else None
+        z_lab = torch.empty(S, B, LN, dtype=torch.uint8, device=dev)
+        w, o = _outs(S, B, N, dev, False, local)
+        nbytes = S * B * (LN + 4 * ((N * K if want_onehot else 0) + 2 * K * D + (N * K if want_q else 0)))
+    elif z_old is not None and z_old.dtype == torch.uint8:
+        z_lab_old = _req(z_old, "z_old labels", dtype=torch.uint8, ndim=3)
+        LN = z_lab_old.shape[-1]
+        if tuple(z_lab_old.shape[:2]) != (S, B) or LN < N:
+            raise ValueError("z_old labels have shape %s, expected (%d,%d,>=%d)" % (tuple(z_lab_old.shape), S, B, N))
+        z_lab = torch.empty(S, B, LN, dtype=torch.uint8, device=dev)
+        w, o = _outs(S, B, N, dev, parts, local)
+        nbytes = S * B * (2 * N + 4 * (2 * K * D + 3 + (N * K if want_q else 0)))
+        if eta_heads is not None:
+            if want_q or parts or local:
+                raise ValueError("the eta statistics ride on the lean launch: no q_probs / parts / per-point outputs")
+            heads = [_req(v, "head weight") for v in eta_heads]
+            if tuple(heads[0].shape) != (K, D + K) or tuple(heads[2].shape) != (D, D + K):
+                raise ValueError("unexpected head weight shapes %s %s" % (tuple(heads[0].shape), tuple(heads[2].shape)))
+            post = [torch.empty(S, B, K, D, dtype=torch.float32, device=dev) for _ in range(4)]
+            stats = torch.empty(S, B, K, 1 + 2 * D, dtype=torch.float32, device=dev)
+            po = GmmPost(*[v.data_ptr() for v in post])
+            nbytes += 4 * S * B * (4 * K * D + K * (1 + 2 * D))
+    else:
+        if eta_heads is not None:
+            raise ValueError("the eta statistics need label mode")
+        z_hot_old = _req(z_old, "z_old", ndim=4) if z_old is not None else None
+        z_hot = torch.empty(S, B, N, K, dtype=torch.float32, device=dev)
+        w, o = _outs(S, B, N, dev, parts, local)
+        nbytes = 4 * S * B * (N * K * (2 if z_old is not None else 1) + 2 * K * D + 3 + (N * K if want_q else 0))
+    q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
+    with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes):
+        check(lib.apgs_gmm_z_step_fused_rng_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
+                                                C.byref(rs), ptr(z_hot_old), ptr(z_lab_old), ptr(seed), S, B, N, K, D,
+                                                ptr(z_hot), ptr(z_lab), LN, ptr(q), ptr(heads[0]), ptr(heads[1]),
+                                                ptr(heads[2]), ptr(heads[3]), C.byref(po) if po is not None else None,
+                                                ptr(stats), C.byref(o), _stream()), "apgs_gmm_z_step_fused_rng_f32")
+    if also_labels:
+        return (z_hot, z_lab), q, w
+    z_new = z_lab if z_lab is not None else z_hot
+    if post is not None:
+        return z_new, None, w, tuple(post), stats
     return z_new, q, w
 
 

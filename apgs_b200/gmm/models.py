@@ -249,14 +249,14 @@ class Enc_apg_z(nn.Module):
             return False                # (K, D) outside the compiled list: PyTorch MLP + the un-fused weight path
         return not (need_grad and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()))
 
-    def sample_fused(self, ob, tau, mu, generative, want_q=True, label_stride=0):
+    def sample_fused(self, ob, tau, mu, generative, want_q=True, label_stride=0, seed=None):
         """z ~ q(z | x, tau, mu) and q_probs from the fused kernel (sample-only mode).  With label_stride the same draw
         also comes back as uint8 labels (S,B,label_stride): returns (z, q_probs, labels)."""
         if label_stride:
             (z, lab), q_probs, _ = kernels.z_step_fused(ob, tau, mu, self.mlp(), generative, want_q=want_q,
-                                                        also_labels=label_stride)
+                                                        also_labels=label_stride, seed=seed)
             return z, q_probs, lab
-        z, q_probs, _ = kernels.z_step_fused(ob, tau, mu, self.mlp(), generative, want_q=want_q)
+        z, q_probs, _ = kernels.z_step_fused(ob, tau, mu, self.mlp(), generative, want_q=want_q, seed=seed)
         return z, q_probs
 
     def forward(self, ob, tau, mu, sampled=True, z_old=None):

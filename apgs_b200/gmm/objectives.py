@@ -136,7 +136,8 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     return trace
 
 
-rng_in_kernels = True          # eta step: Gamma / Normal variates drawn inside the weight kernel (else torch._standard_gamma / randn)
+rng_in_kernels = True          # eta step: Gamma / Normal variates drawn inside the weight kernel (else torch._standard_gamma / randn);
+                               # z step: the uniforms of the categorical draw made inside the fused kernel (else torch.rand)
 _SIDE_STREAMS = {}
 
 
@@ -217,7 +218,7 @@ def _sample_z_train(enc_z, generative, x, tau, mu, label_stride=0):
     """sample-only fused z step with a graph: z (one-hot), q_probs, log q(z) summed over the points (S,B), labels or None"""
     from .train import FusedZStep
     z, q_probs, _, _, _, log_q_local, z_hot = FusedZStep.apply(*enc_z.mlp(), kernels._x3(x), tau, mu, None, generative,
-                                                               int(label_stride))
+                                                               int(label_stride), _zseed(tau.device))
     if label_stride:
         return z_hot, q_probs, log_q_local.sum(-1), z
     return z, q_probs, log_q_local.sum(-1), None
@@ -237,6 +238,11 @@ def oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags):
     return _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags)[:5]
 
 
+def _zseed(dev):
+    """Philox key of an in-kernel z draw (None: the kernel reads torch.rand uniforms)"""
+    return kernels.philox_seed(dev) if rng_in_kernels else None
+
+
 def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_stride=0, defer=False):
     """oneshot; with label_stride (fused sampler only) the draw of z also comes back as uint8 labels (6th value);
     the 7th value is log q of the draw (what a deferred _book_weights needs)."""
@@ -249,7 +255,7 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
         # assigned: its log-likelihoods vanish, its density / log_q_f are log p(eta) and log q(eta)).  Same terms as
         # kernels.logw_oneshot, summed as (ll + log p(z)) + log p(eta) instead of (ll + log p(eta)) + log p(z).
         (_, z_lab), _, wz = kernels.z_step_fused(x, tau, mu, enc_rws_z.mlp(), generative, want_q=False,
-                                                 also_labels=label_stride, want_onehot=False)
+                                                 also_labels=label_stride, want_onehot=False, seed=_zseed(tau.device))
         S, B, K, D = tau.shape
         we = kernels.logw_eta_stats(torch.zeros(S, B, K, 1 + 2 * D, device=tau.device), mu, post, generative,
                                     tau, mu, tau, mu)
@@ -262,9 +268,9 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
     if result_flags['loss_required'] and _train_z(enc_rws_z):
         z, q_probs, log_q_z, z_lab = _sample_z_train(enc_rws_z, generative, x, tau, mu, label_stride)
     elif label_stride:
-        z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride)
+        z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride, seed=_zseed(tau.device))
     elif enc_rws_z.can_fuse(result_flags['loss_required']):
-        z, q_probs = enc_rws_z.sample_fused(x, tau, mu, generative)
+        z, q_probs = enc_rws_z.sample_fused(x, tau, mu, generative, seed=_zseed(tau.device))
     else:
         q_probs = enc_rws_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()
@@ -294,7 +300,7 @@ def _update_joint(enc_apg_z, enc_apg_eta, generative, x, z_old, tau_old, mu_old,
     if result_flags['loss_required'] and _train_z(enc_apg_z):
         z, q_probs, log_q_z, _ = _sample_z_train(enc_apg_z, generative, x, tau, mu)
     elif enc_apg_z.can_fuse(result_flags['loss_required']):
-        z, q_probs = enc_apg_z.sample_fused(x, tau, mu, generative)
+        z, q_probs = enc_apg_z.sample_fused(x, tau, mu, generative, seed=_zseed(tau.device))
     else:
         q_probs = enc_apg_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()
@@ -371,7 +377,7 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
         # N2: the fused forward launch + a backward kernel for the MLP gradients (train.FusedZStep)
         from .train import FusedZStep
         z, q_probs, log_w, density, log_w_local, log_q_local, _ = FusedZStep.apply(*enc_apg_z.mlp(), kernels._x3(x), tau, mu,
-                                                                                  z_old, generative, 0)
+                                                                                  z_old, generative, 0, _zseed(tau.device))
         w_local, _ = ops.local_weight_stats(log_w_local, want_w=True, want_sum=False)
         loss = (w_local * (-log_q_local)).sum(0).sum(-1).mean()
         trace['loss'][-1] = trace['loss'][-1] + loss.unsqueeze(0)
@@ -382,12 +388,13 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
         return log_w, z, trace, None
     if eta_heads is not None and not (result_flags['mode_required'] or need_local):
         z, q_probs, w, post, stats = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
-                                                          eta_heads=eta_heads)
+                                                          eta_heads=eta_heads, seed=_zseed(tau.device))
         pre = (post, stats)
     elif enc_apg_z.can_fuse(result_flags['loss_required']):
         # N1: MLP + softmax + draw + weights in one kernel; q_probs only materialised when asked for
         z, q_probs, w = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
-                                             want_q=bool(result_flags['mode_required']), local=need_local)
+                                             want_q=bool(result_flags['mode_required']), local=need_local,
+                                             seed=_zseed(tau.device))
     else:
         q_probs = enc_apg_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()

@@ -295,6 +295,21 @@ APGS_API int apgs_gmm_z_step_fused_labels_eta_f32(const float* x, const float* t
                               const float* Wg, const float* bg, const float* Wo, const float* bo,
                               const apgs_gmm_post_out_t* post_out, float* stats_out,
                               const apgs_gmm_out_t* out, void* stream);
+/* The z step with the draw's uniforms made INSIDE the kernel (replaces `Categorical(probs).sample()`,
+ *   apgs/gmm/models.py:115-117, whose random stream is torch's own; the draw is distributed identically, the stream is
+ *   Philox4x32-10 keyed by *philox_seed -- a device word the host fills from torch's generator per launch, so that manual
+ *   seeds reproduce and CUDA-graph replays get fresh draws -- and counted by (particle row, lane, pass)).  One entry for every
+ *   mode of the three above: z_old as one-hot OR labels OR neither (sample-only), z_new as one-hot and / or labels, and
+ *   the eta statistics when Wg..stats_out are given (then labels in / labels out only).  Saves the (S,B,N) uniforms:
+ *   one launch writing and one pass reading 4 N bytes per particle.                                                   */
+APGS_API int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, const float* mu,
+                              const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
+                              const apgs_gmm_prior_t* prior, const float* z_old_onehot, const uint8_t* z_old_labels,
+                              const uint64_t* philox_seed, int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              float* z_new_onehot, uint8_t* z_new_labels, int64_t label_stride, float* q_probs,
+                              const float* Wg, const float* bg, const float* Wo, const float* bo,
+                              const apgs_gmm_post_out_t* post_out, float* stats_out,
+                              const apgs_gmm_out_t* out, void* stream);
 APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
                                      const float* Wg, const float* bg, const float* Wo, const float* bo,
                                      int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,

@@ -568,3 +568,53 @@ def test_objective_on_stream_slices_gives_the_same_trace_shapes_and_statistics()
     # the one-shot of the first slice sees the same generator state as the un-sliced run's first instances only in law;
     # E_tau of the one-shot is a function of the data alone -> identical
     assert torch.equal(a["E_tau"][0], b["E_tau"][0])
+
+
+def test_z_step_in_kernel_uniforms_draw_from_q_and_are_independent():
+    """seed= mode of the fused z step (uniforms made inside the kernel by Philox, keyed per launch):
+      * deterministic in the seed, different for another seed, and the SAME draw in every variant of the kernel (lean
+        labels, non-lean labels, one-hot) -- a draw is a function of (seed, particle, point) only;
+      * the draw follows q: with (tau, mu) replicated over S particles the label frequencies over s match q_probs of each
+        (b, n) within 4.5 standard errors -- which also rules out uniforms shared between particles;
+      * no correlation between neighbouring points / particles."""
+    from apgs_b200.gmm import kernels
+    S, B, N, K = 512, 6, 60, 3
+    P, gen = og.make_params(), _Gen()
+    x, tau, mu, lab_old, _ = _latents(S, B, seed=11)
+    tau, mu = tau[:1].repeat(S, 1, 1, 1).contiguous(), (mu[:1] * 0.3).repeat(S, 1, 1, 1).contiguous()
+    xg, tg, mg, lo = x.to(DEV), tau.to(DEV), mu.to(DEV), _pad_labels(lab_old.to(DEV))
+    s1 = torch.tensor([1234567, 0], dtype=torch.int64, device=DEV)
+    s2 = torch.tensor([1234568, 0], dtype=torch.int64, device=DEV)
+    z_lean, _, w_lean = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=lo, seed=s1)
+    z_again, _, w_again = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=lo, seed=s1)
+    z_full, q, w_full = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=lo, seed=s1, want_q=True, parts=True, local=True)
+    hot_old = torch.nn.functional.one_hot(lab_old.long(), K).float().to(DEV)
+    z_hot, _, w_hot = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=hot_old, seed=s1)
+    (zs_hot, zs_lab), _, _ = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, also_labels=64, seed=s1)
+    z_other, _, _ = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=lo, seed=s2)
+    lab = z_lean[..., :N]
+    assert torch.equal(z_again[..., :N], lab) and torch.equal(w_again.log_w, w_lean.log_w)   # pad bytes are never written
+    assert torch.equal(z_full[..., :N], lab) and torch.equal(w_full.log_w, w_lean.log_w)
+    assert torch.equal(z_hot.argmax(-1).to(torch.uint8), lab) and torch.equal(w_hot.log_w, w_lean.log_w)
+    assert torch.equal(zs_lab[..., :N], lab) and torch.equal(zs_hot.argmax(-1).to(torch.uint8), lab)
+    assert float((z_other[..., :N] != lab).float().mean()) > 0.2
+    assert int(lab.max()) < K
+    # frequencies over the S particles against q of each point
+    hot = torch.nn.functional.one_hot(lab.long(), K).double()
+    freq = hot.mean(0)                                           # (B, N, K)
+    qn = (q / q.sum(-1, keepdim=True))[0].double()
+    se = (qn * (1 - qn) / S).sqrt()
+    zscore = ((freq - qn).abs() - 1e-6) / se.clamp_min(1e-4)
+    assert float(zscore.max()) < 4.5, float(zscore.max())
+    assert float((freq - qn).mean(0).mean(0).abs().max()) < 4.5 * float((qn * (1 - qn)).mean().sqrt()) / (S * B * N) ** 0.5
+    # residual correlation between neighbours (points of a particle share a Philox block in fours; particles share a CTA)
+    resid = hot - qn.unsqueeze(0)
+    for shift_dim in (0, 2):
+        a = resid.narrow(shift_dim, 0, resid.shape[shift_dim] - 1)[..., 0]
+        b = resid.narrow(shift_dim, 1, resid.shape[shift_dim] - 1)[..., 0]
+        corr = float((a * b).mean() / (a.pow(2).mean() * b.pow(2).mean()).sqrt())
+        assert abs(corr) < 4.5 / a.numel() ** 0.5, (shift_dim, corr)
+    for lag in (8, 32):                                          # lane / pass strides of the point-to-thread mapping
+        a, b = resid[:, :, :-lag, 0], resid[:, :, lag:, 0]
+        corr = float((a * b).mean() / (a.pow(2).mean() * b.pow(2).mean()).sqrt())
+        assert abs(corr) < 4.5 / a.numel() ** 0.5, (lag, corr)
