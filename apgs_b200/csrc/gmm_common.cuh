@@ -101,6 +101,14 @@ __device__ __forceinline__ float log_fast(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y * 0.693147180559945309417f;
 }
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+#define LN2_F 0.693147180559945309417f
+#define LOG_EPS_F (-15.9423851528787f)          // log(FLT_EPSILON)
+#define LOG_1M_EPS_F (-1.1920929665620834e-07f)   // log(1 - FLT_EPSILON)
 // lgamma(x), x > 0, for the Gamma normaliser of the eta step: shift up by four (lgamma(x) = lgamma(x+4) - log(x(x+1)(x+2)(x+3)))
 // and Stirling's series at y = x + 4 >= 4 (first omitted term 1/(1680 y^7) < 4e-8).  ~25 instructions and two SFU logs
 // instead of the ~100 of lgammaf(); absolute error ~3e-7 |lgamma| + 1e-6, the same order as lgammaf's own (a few ulp).

@@ -17,6 +17,10 @@
 #include "gmm_common.cuh"
 #include "rng.cuh"
 
+#ifndef APGS_ZF_EXPT
+#define APGS_ZF_EXPT 0      // measurement-only builds: 1 = no MLP loop, 2 = no per-point epilogue (lean launch)
+#endif
+
 namespace apgs {
 
 struct ZFusedArgs {
@@ -45,7 +49,34 @@ struct ZFusedArgs {
     const float *ra, *rb, *rm, *rn;                       // prior alpha, beta, mu, nu (K, D)
     float *oa, *ob, *om, *on;                             // posterior out (R, K, D)
     float* stats;                                         // (R, K, 1 + 2 D) out
+    // per-instance tables made once per objective by k_gmm_z_tables (everything of the step that depends only on the data
+    // and the encoder weights), or null: the CTA then builds its own copy in the prologue
+    const float* tables;
 };
+
+// ---- per-instance tables ------------------------------------------------------------------------------------------
+// Everything of the z step that is a function of (instance data, encoder weights) alone -- the Ex table, its per-unit
+// maxima, the output weights, b2' and the clamped log prior, the points themselves -- is the same for the ~S/32 CTAs of
+// an instance and for every sweep of an objective.  k_gmm_z_tables writes it once per instance as one contiguous block
+// in the kernel's own shared-memory layout, and a CTA of the step fetches its instance's block with ONE bulk copy
+// (cp.async.bulk, ~10 KB from L2) that lands while the per-particle prologue runs.  Behind the copied part sits the
+// first layer's particle-side weights, pre-scaled (rows of 8 floats per hidden unit: W1m'[D], W1t'[D], b1' - 31), read
+// with two L1-resident 16-byte loads per unit.
+struct ZTabLayout {
+    int xm, aw, misc, x, copy_floats, wt, total;      // offsets in floats (the Ex table sits at 0)
+};
+__host__ __device__ inline ZTabLayout zf_tab_layout(int N, int H4, int D) {
+    ZTabLayout L;
+    const int EXS = (N + 31) / 32 * 32;
+    L.xm = H4 * EXS;
+    L.aw = L.xm + H4;
+    L.misc = L.aw + H4;                                // b2', log pi_k (K <= 6), [7]: 1 = the factorised loop is safe
+    L.x = L.misc + 8;
+    L.copy_floats = L.x + (N * D + 3) / 4 * 4;
+    L.wt = L.copy_floats;
+    L.total = L.wt + H4 * 8;
+    return L;
+}
 
 // in-kernel uniforms of the categorical draw: one Philox block per (particle row, lane, pass) -- its four words are the
 // uniforms of that lane's PB points of the pass; [0, 1) with 24 bits like torch.rand
@@ -149,6 +180,136 @@ __host__ __device__ inline int zf_block_floats(int H4) {
     return (b + 3) / 4 * 4;
 }
 
+// magnitudes beyond which the particle-side pre-activations are not guaranteed finite (5 products of two such values)
+#define ZF_IN_MAX 1.0e17f
+
+// The per-instance tables, built by all threads of a CTA (the z step's own prologue when no tables are handed in, and
+// k_gmm_z_tables): Ex_n[h] = 2^(2 log2(e) W1x x_n) in the MLP's slot order with its per-unit maximum exponent XM[h]
+// (+inf: the CTA takes the plain loop), the output weights -2 W2[h], b2' = b2 + sum_h W2[h]  (tanh = 1 - 2/y  =>
+// sum_h w2_h tanh_h = sum_h w2_h - sum_h 2 w2_h / y_h; the loops accumulate the second sum), the clamped log prior of
+// the assignments, and the instance's points.  The caller synchronises the CTA afterwards.
+template <int K, int D, int LANES, int PB>
+__device__ __forceinline__ void zf_cta_tables(const float* xb, const float* W1, const float* b1, const float* W2,
+                                              const float* b2, const float* rpi, int N, int H, float* s_ex, float* s_xm,
+                                              float* s_aw, float* s_misc, float* s_x) {
+    const int H4 = (H + 3) / 4 * 4, EXS = (N + LANES * PB - 1) / (LANES * PB) * (LANES * PB);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
+    constexpr int XS = 2;                                       // slots per lane kept in registers (N <= 64)
+    float xr[XS][D];
+#pragma unroll
+    for (int si = 0; si < XS; ++si) {
+        const int slot = lane + 32 * si, qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);   // slot order q0 q2 q1 q3
+        const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xr[si][d] = (slot < EXS && n < N) ? __ldg(xb + n * D + d) : NAN;
+    }
+    for (int h = H + warp; h < H4; h += nwarp)                  // padding rows of the last quad of hidden units
+        for (int slot = lane; slot < EXS; slot += 32) s_ex[(size_t)h * EXS + slot] = 0.f;
+    for (int i = threadIdx.x; i < H4; i += nthr) s_aw[i] = (i < H) ? -2.f * __ldg(W2 + i) : 0.f;
+    for (int i = threadIdx.x; i < N * D; i += nthr) s_x[i] = __ldg(xb + i);
+#pragma unroll 4
+    for (int h = warp; h < H; h += nwarp) {
+        float w[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) w[d] = TANH_PRESCALE * __ldg(W1 + h * (3 * D) + d);
+        float mx = -INFINITY;
+        // the unit's particle-side weights: beyond ZF_IN_MAX (or NaN) the pre-activations e' may not be finite -> plain loop
+        bool bad = (lane >= D && lane < 3 * D) ? !(fabsf(__ldg(W1 + h * (3 * D) + lane)) <= ZF_IN_MAX)
+                                               : (lane == 3 * D ? !(fabsf(__ldg(b1 + h)) <= ZF_IN_MAX) : false);
+#pragma unroll
+        for (int si = 0; si < XS; ++si) {
+            const int slot = lane + 32 * si;
+            if (slot < EXS) {
+                const int qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);
+                const bool in = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2) < N;
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) acc = fmaf(w[d], xr[si][d], acc);
+                if (in) { mx = fmaxf(mx, acc); bad |= !(acc == acc); }
+                // an underflow to 0 is exact enough (the sum of exponents is then < -46); overflow is caught via XM
+                s_ex[(size_t)h * EXS + slot] = in ? ex2_ftz(acc) : 0.f;
+            }
+        }
+        for (int slot = lane + 32 * XS; slot < EXS; slot += 32) {
+            const int qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);
+            const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
+            float acc = 0.f;
+            if (n < N) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) acc = fmaf(w[d], __ldg(xb + n * D + d), acc);
+                mx = fmaxf(mx, acc);
+                bad |= !(acc == acc);
+            }
+            s_ex[(size_t)h * EXS + slot] = (n < N) ? ex2_ftz(acc) : 0.f;
+        }
+        mx = warp_max(bad ? INFINITY : mx);
+        if (lane == 0) s_xm[h] = (mx <= 126.f) ? mx : INFINITY;     // +inf: the instance takes the plain loop
+    }
+    if (warp == 0) {
+        float part = 0.f, wmax = 0.f;
+        for (int i = lane; i < H; i += 32) {
+            const float w = __ldg(W2 + i);
+            part += w;
+            wmax = fmaxf(wmax, (w == w) ? fabsf(w) : INFINITY);
+        }
+        part = warp_sum(part);
+        wmax = warp_max(wmax);
+        if (lane == 0) {
+            s_misc[0] = __ldg(b2) + part;
+            // (d) output weights: the numerators are |w| [2^-93, 2^95]; beyond 2^24 (or NaN) the instance takes the plain
+            // loop (flag in s_misc[7])
+            s_misc[7] = (wmax <= 16777216.f) ? 1.f : 0.f;
+        }
+        if (lane < 6) {
+            float v = 0.f;
+            if (lane < K) {
+                float sp = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) sp = __fadd_rn(sp, __ldg(rpi + k));
+                v = logf(fminf(fmaxf(__fdiv_rn(__ldg(rpi + lane), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
+            }
+            s_misc[1 + lane] = v;
+        }
+    }
+}
+
+// row h of the particle-side first-layer weights, pre-scaled for the factorised loop: W1m'[D], W1t'[D], b1' - 31
+// (2^-31 folded into the Ee table, see the range contract above); padding rows are zero
+template <int D>
+__device__ __forceinline__ void zf_wt_row(const float* W1, const float* b1, int h, bool live, float (&wm)[D], float (&wt)[D],
+                                          float& bh) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        wm[d] = live ? TANH_PRESCALE * __ldg(W1 + h * 3 * D + D + d) : 0.f;
+        wt[d] = live ? TANH_PRESCALE * __ldg(W1 + h * 3 * D + 2 * D + d) : 0.f;
+    }
+    bh = live ? __fadd_rn(TANH_PRESCALE * __ldg(b1 + h), -31.f) : 0.f;
+}
+
+template <int K, int D>
+__global__ void __launch_bounds__(256) k_gmm_z_tables(const float* x, const float* W1, const float* b1, const float* W2,
+                                                      const float* b2, const float* rpi, int N, int H, float* tables) {
+    static_assert(2 * D + 1 <= 8 && K <= 6, "table rows of 8 floats");
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* sm = reinterpret_cast<float*>(smem);
+    const int H4 = (H + 3) / 4 * 4;
+    const ZTabLayout L = zf_tab_layout(N, H4, D);
+    const int b = (int)blockIdx.x;
+    for (int i = threadIdx.x; i < L.total; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    zf_cta_tables<K, D, 8, 4>(x + (size_t)b * N * D, W1, b1, W2, b2, rpi, N, H, sm, sm + L.xm, sm + L.aw, sm + L.misc, sm + L.x);
+    for (int h = threadIdx.x; h < H4; h += blockDim.x) {
+        float wm[D], wt[D], bh;
+        zf_wt_row<D>(W1, b1, h, h < H, wm, wt, bh);
+#pragma unroll
+        for (int d = 0; d < D; ++d) { sm[L.wt + h * 8 + d] = wm[d]; sm[L.wt + h * 8 + D + d] = wt[d]; }
+        sm[L.wt + h * 8 + 2 * D] = bh;
+    }
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(tables + (size_t)b * L.total);      // L.total is a multiple of 4 floats
+    for (int i = threadIdx.x; i < L.total / 4; i += blockDim.x) dst[i] = reinterpret_cast<const float4*>(sm)[i];
+}
+
 // LEAN: the launch a sweep repeats -- labels in, labels out, uniforms given, no one-hot rows, no per-point outputs.
 // The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
 // HC / NC: hidden width and points per instance when known at compile time (the reference's 32 and 60), else 0.
@@ -158,7 +319,6 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     static_assert(!NSS || LEAN, "the eta statistics ride on the lean label-mode launch");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ unsigned long long bar;
-    __shared__ float s_misc[1 + K];
     constexpr int KD = K * D;
     constexpr int RK = K;                                      // table floats per hidden unit
     const int N = NC ? NC : a.N, H = HC ? HC : a.H, H4 = (H + 3) / 4 * 4;
@@ -173,6 +333,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     const bool has_bwd = LEAN || a.z_old != nullptr || lab_old;
     const bool forced = !LEAN && a.z_forced != nullptr;
     const bool rng = a.seed != nullptr && !forced;
+    const bool have_tab = a.tables != nullptr;
     uint2 key = make_uint2(0u, 0u);
     if (rng) { const unsigned long long sd = __ldg(a.seed); key = make_uint2((unsigned int)sd, (unsigned int)(sd >> 32)); }
     const bool hot_new = !LEAN && a.z_new != nullptr;                      // one-hot z_new wanted (labels may come along)
@@ -180,24 +341,28 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     const bool want_q = !LEAN && a.q_probs != nullptr, want_lw = !LEAN && a.lw_local != nullptr;
     const bool want_lq = !LEAN && a.lq_local != nullptr;
     const size_t tile_f = tiles ? ((size_t)P * NK + 3) / 4 * 4 : 0;
+    const ZTabLayout TL = zf_tab_layout(N, H4, D);
     float* s_zo = reinterpret_cast<float*>(smem);              // z_old rows
     float* s_zn = s_zo + tile_f;                               // z_new rows (staged in from z_forced, out to z_new)
+    // the per-instance tables, contiguous in the layout of zf_tab_layout (one bulk copy when they are handed in)
     float* s_ex = s_zn + tile_f;                               // H4 * EXS, slot order inside a quad: q0 q2 q1 q3
-    float* s_e = s_ex + (size_t)H4 * EXS;                      // P * EPB
-    float* s_xm = s_e + (size_t)P * EPB;                       // H4
-    float* s_aw = s_xm + H4;                                   // H4: -2 W2[h], 0 in the padding rows
-    float* s_tab = s_aw + H4;                                        // P * KD * 3: mu, 1/(2 var), log sigma + c
-    float* s_x = s_tab + (size_t)P * KD * 3;                         // N * D: the instance's points (read after the MLP)
+    float* s_xm = s_ex + TL.xm;                                // H4
+    float* s_aw = s_ex + TL.aw;                                // H4: -2 W2[h], 0 in the padding rows
+    float* s_misc = s_ex + TL.misc;                            // 8: b2', log pi_k
+    float* s_x = s_ex + TL.x;                                  // N * D: the instance's points (read after the MLP)
+    float* s_e = s_ex + TL.copy_floats;                        // P * EPB
+    // Normal tables: per particle K rows {mu_d, 1/(2 var_d), log sigma_d + c}_d of TRS floats (16-byte loads)
+    constexpr int TRS = (3 * D + 3) / 4 * 4;
+    float* s_tab = s_e + (size_t)P * EPB;                      // P * K * TRS
     // lean variant: the particles' uniforms and old labels are prefetched into shared memory with cp.async, so nothing
     // of them lives in registers across the MLP
     const int NU = (N + 3) / 4 * 4, LS = (N + 15) & ~15;
-    float* s_u = s_x + (size_t)(N * D + 3) / 4 * 4;                  // P * NU (lean)
+    float* s_u = s_tab + (size_t)P * K * TRS;                  // P * NU (lean)
     unsigned char* s_lb = reinterpret_cast<unsigned char*>(s_u + (size_t)P * NU);   // P * LS (lean): old labels in, new out
     float* s_nt = reinterpret_cast<float*>(s_lb + (size_t)P * LS);                 // N * K rows of EtaTab::RS floats (NSS)
     const int b = (int)blockIdx.x;                             // grid = (B, ceil(S / P)): no division
     const int s0 = (int)blockIdx.y * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool valid = s0 + p < a.S;
     const long long r = (long long)(s0 + p) * a.B + b;
     const int rows = min(P, a.S - s0);
@@ -205,21 +370,27 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     // a row goes through the bulk-copy engine when its size keeps every row 16-byte aligned
     const bool old_tile = !LEAN && a.z_old != nullptr;
     const bool bulk_in = (rb & 15u) == 0 && (!old_tile || aligned(a.z_old, 16)) && (!forced || aligned(a.z_forced, 16));
-    if (!LEAN) {
-        if (threadIdx.x == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows * ((old_tile ? 1u : 0u) + (forced ? 1u : 0u)) : 0u);
+    const unsigned int tab_bytes = have_tab ? (unsigned int)TL.copy_floats * 4u : 0u;
+    const bool use_bar = !LEAN || have_tab;
+    if (use_bar && threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        // the waits sit behind the CTA barrier that follows the per-particle prologue, which also publishes the init
+        mbar_expect_tx(&bar, tab_bytes + ((!LEAN && bulk_in) ? rb * (unsigned int)rows * ((old_tile ? 1u : 0u) + (forced ? 1u : 0u)) : 0u));
+        if (have_tab) bulk_g2s(s_ex, a.tables + (size_t)b * TL.total, tab_bytes, &bar);
     }
-    if (!LEAN && valid) {
-        if (bulk_in) {
-            if (j == 0) {
-                if (old_tile) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + r * NK, rb, &bar);
-                if (forced) bulk_g2s(s_zn + (size_t)p * NK, a.z_forced + r * NK, rb, &bar);
-            }
-        } else {
-            for (int i = j; i < NK; i += LANES) {
-                if (old_tile) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + r * NK + i);
-                if (forced) s_zn[(size_t)p * NK + i] = __ldg(a.z_forced + r * NK + i);
+    if (!LEAN) {
+        __syncthreads();                                           // the particles' own lanes issue their row copies
+        if (valid) {
+            if (bulk_in) {
+                if (j == 0) {
+                    if (old_tile) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + r * NK, rb, &bar);
+                    if (forced) bulk_g2s(s_zn + (size_t)p * NK, a.z_forced + r * NK, rb, &bar);
+                }
+            } else {
+                for (int i = j; i < NK; i += LANES) {
+                    if (old_tile) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + r * NK + i);
+                    if (forced) s_zn[(size_t)p * NK + i] = __ldg(a.z_forced + r * NK + i);
+                }
             }
         }
     }
@@ -255,114 +426,46 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    // ---- per-CTA table Ex_n[h] = 2^(2 log2(e) W1x x_n) and its per-unit maximum exponent, while the rows are in flight
+    // ---- per-CTA tables (no tables handed in): built here, while the rows are in flight
     const float* xb = a.x + (size_t)b * N * D;
-    {
-        constexpr int XS = 2;                                       // slots per lane kept in registers (N <= 64)
-        float xr[XS][D];
+    if (!have_tab) zf_cta_tables<K, D, LANES, PB>(xb, a.W1, a.b1, a.W2, a.b2, a.rpi, N, H, s_ex, s_xm, s_aw, s_misc, s_x);
+    if constexpr (NSS) {
+        // per-CTA table of Enc_apg_eta's head factors over (point, label) (see gmm_common.cuh)
+        for (int idx = threadIdx.x; idx < NK; idx += P * LANES) {
+            const int n = idx / K, lab = idx - n * K;
+            float xin[D];
 #pragma unroll
-        for (int si = 0; si < XS; ++si) {
-            const int slot = lane + 32 * si, qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);   // slot order q0 q2 q1 q3
-            const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
-#pragma unroll
-            for (int d = 0; d < D; ++d) xr[si][d] = (slot < EXS && n < N) ? __ldg(xb + n * D + d) : NAN;
-        }
-        for (int h = H + warp; h < H4; h += (P * LANES) / 32)       // padding rows of the last quad of hidden units
-            for (int slot = lane; slot < EXS; slot += 32) s_ex[(size_t)h * EXS + slot] = 0.f;
-        for (int i = threadIdx.x; i < H4; i += P * LANES) {
-            s_aw[i] = (i < H) ? -2.f * __ldg(a.W2 + i) : 0.f;
-        }
-        for (int i = threadIdx.x; i < N * D; i += P * LANES) s_x[i] = __ldg(xb + i);
-        if constexpr (NSS) {
-            // per-CTA table of Enc_apg_eta's head factors over (point, label) (see gmm_common.cuh)
-            for (int idx = threadIdx.x; idx < NK; idx += P * LANES) {
-                const int n = idx / K, lab = idx - n * K;
-                float xin[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) xin[d] = __ldg(xb + n * D + d);
-                eta_head_factors<K, D>(a.Wg, a.bg, a.Wo, a.bo, xin, lab, s_nt + (size_t)idx * EtaTab<K, D>::RS);
-            }
-        }
-#pragma unroll 4
-        for (int h = warp; h < H; h += (P * LANES) / 32) {
-            float w[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) w[d] = TANH_PRESCALE * __ldg(a.W1 + h * (3 * D) + d);
-            float mx = -INFINITY;
-            bool bad = false;
-#pragma unroll
-            for (int si = 0; si < XS; ++si) {
-                const int slot = lane + 32 * si;
-                if (slot < EXS) {
-                    const int qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);
-                    const bool in = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2) < N;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) acc = fmaf(w[d], xr[si][d], acc);
-                    if (in) { mx = fmaxf(mx, acc); bad |= !(acc == acc); }
-                    // an underflow to 0 is exact enough (the sum of exponents is then < -46); overflow is caught via XM
-                    s_ex[(size_t)h * EXS + slot] = in ? ex2_ftz(acc) : 0.f;
-                }
-            }
-            for (int slot = lane + 32 * XS; slot < EXS; slot += 32) {
-                const int qs = slot & 3, q = ((qs & 1) << 1) | (qs >> 1);
-                const int n = (slot >> 5) * (LANES * PB) + q * LANES + ((slot & 31) >> 2);
-                float acc = 0.f;
-                if (n < N) {
-#pragma unroll
-                    for (int d = 0; d < D; ++d) acc = fmaf(w[d], __ldg(xb + n * D + d), acc);
-                    mx = fmaxf(mx, acc);
-                    bad |= !(acc == acc);
-                }
-                s_ex[(size_t)h * EXS + slot] = (n < N) ? ex2_ftz(acc) : 0.f;
-            }
-            mx = warp_max(bad ? INFINITY : mx);
-            if (lane == 0) s_xm[h] = (mx <= 126.f) ? mx : INFINITY;     // +inf: the CTA takes the plain loop
+            for (int d = 0; d < D; ++d) xin[d] = __ldg(xb + n * D + d);
+            eta_head_factors<K, D>(a.Wg, a.bg, a.Wo, a.bo, xin, lab, s_nt + (size_t)idx * EtaTab<K, D>::RS);
         }
     }
-    // per-CTA scalars, once: b2' = b2 + sum_h W2[h]  (tanh = 1 - 2/y  =>  sum_h w2_h tanh_h = sum_h w2_h - sum_h 2 w2_h / y_h,
-    // the loops accumulate the second sum) and the clamped log prior of the assignments
-    if (warp == 0) {
-        float part = 0.f, wmax = 0.f;
-        for (int i = lane; i < H; i += 32) {
-            const float w = __ldg(a.W2 + i);
-            part += w;
-            wmax = fmaxf(wmax, (w == w) ? fabsf(w) : INFINITY);
-        }
-        part = warp_sum(part);
-        wmax = warp_max(wmax);
-        if (lane == 0) {
-            s_misc[0] = __ldg(a.b2) + part;
-            // (d) output weights: the numerators are |w| [2^-93, 2^95]; beyond 2^24 (or NaN) the CTA takes the plain
-            // loop -- signalled through XM[0], which this warp's lane 0 wrote itself
-            if (!(wmax <= 16777216.f)) s_xm[0] = INFINITY;
-        }
-        if (lane < K) {
-            float sp = 0.f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) sp = __fadd_rn(sp, __ldg(a.rpi + k));
-            s_misc[1 + lane] = logf(fminf(fmaxf(__fdiv_rn(__ldg(a.rpi + lane), sp), FLT_EPS_F), 1.f - FLT_EPS_F));
-        }
-    }
-    // ---- per-particle pieces: e'_k[h] = 2 log2(e) (b1 + W1m mu_k + W1t tau_k), Normal tables.  The Ee table is written
-    // for the factorised loop right away (2^-31 Ee_k[h]); the rare particle that fails the range test below rewrites
-    // its entries with the raw e' for the plain loop.
-    float elo = INFINITY, ehi = -INFINITY;
+    // ---- per-particle pieces: e''_k[h] = 2 log2(e) (b1 + W1m mu_k + W1t tau_k) - 31, Normal tables.  The Ee table is
+    // written for the factorised loop right away (2^e'' = 2^-31 Ee_k[h]); the rare particle that fails the range test
+    // below rewrites its entries with the raw e' for the plain loop.
+    float elo = INFINITY, ehi = -INFINITY;                     // range of e'' over this lane's entries
+    bool in_ok = true;                                         // inputs small enough for every e' to be finite
     float* ep = s_e + (size_t)p * EPB;
     float* em = ep + EPs;
     float tk[KD], mk[KD];
     if (valid) {
 #pragma unroll
         for (int e = 0; e < KD; ++e) { tk[e] = __ldg(a.tau + r * KD + e); mk[e] = __ldg(a.mu + r * KD + e); }
+#pragma unroll
+        for (int e = 0; e < KD; ++e) in_ok &= (fabsf(tk[e]) <= ZF_IN_MAX) & (fabsf(mk[e]) <= ZF_IN_MAX);   // false for NaN
+        const float* wtp = a.tables + TL.wt;                   // instance 0's copy: the rows are the same for all
 #pragma unroll 4
         for (int h = j; h < H4; h += LANES) {
             const bool live = h < H;
-            const float bh = live ? __ldg(a.b1 + h) : 0.f;
-            float wm[D], wt[D];
+            float wm[D], wt[D], bh;
+            if (have_tab) {
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(wtp + h * 8));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(wtp + h * 8 + 4));
+                const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                wm[d] = live ? __ldg(a.W1 + h * 3 * D + D + d) : 0.f;
-                wt[d] = live ? __ldg(a.W1 + h * 3 * D + 2 * D + d) : 0.f;
+                for (int d = 0; d < D; ++d) { wm[d] = v[d]; wt[d] = v[D + d]; }
+                bh = v[2 * D];
+            } else {
+                zf_wt_row<D>(a.W1, a.b1, h, live, wm, wt, bh);
             }
             float emax = -INFINITY;
 #pragma unroll
@@ -373,49 +476,51 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
                     acc = fmaf(wm[d], mk[k * D + d], acc);
                     acc = fmaf(wt[d], tk[k * D + d], acc);
                 }
-                const float ee = TANH_PRESCALE * acc;
-                if (live) {
-                    emax = fmaxf(emax, ee);
-                    elo = fminf(elo, ee);
-                    if (!(ee == ee)) ehi = INFINITY;                           // NaN: fmaxf/fminf would drop it
-                }
-                ep[ee_slot<K>(h, k)] = live ? ex2_ftz(ee - 31.f) : 0.f;        // 2^-31 Ee_k[h]; padding rows 0
+                if (live) { emax = fmaxf(emax, acc); elo = fminf(elo, acc); }
+                ep[ee_slot<K>(h, k)] = live ? ex2_ftz(acc) : 0.f;              // 2^-31 Ee_k[h]; padding rows 0
             }
             em[h] = emax;
             ehi = fmaxf(ehi, emax);
         }
-        float* tab = s_tab + (size_t)p * (KD * 3);
+        float* tab = s_tab + (size_t)p * (K * TRS);
         for (int e = j; e < KD; e += LANES) {
             float tf = 0.f, mf = 0.f;
 #pragma unroll
             for (int ee = 0; ee < KD; ++ee) if (ee == e) { tf = tk[ee]; mf = mk[ee]; }
             const float sg = inv_sqrt_ref(tf);
-            tab[e * 3 + 0] = mf;
-            tab[e * 3 + 1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sg, sg)));
-            tab[e * 3 + 2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
+            float* row = tab + (e / D) * TRS + (e % D) * 3;
+            row[0] = mf;
+            row[1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sg, sg)));
+            row[2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
         }
     }
-    __syncthreads();                                               // s_xm, s_aw, s_misc
+    if (LEAN) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's uniforms / labels landed
+    __syncthreads();                                               // tables built here / mbarrier init / cooperative rows
+    if (use_bar) mbar_wait(&bar, 0);                               // tables and rows staged by the copy engine landed
     const float b2 = s_misc[0];
     float logpi[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) logpi[k] = s_misc[1 + k];
     float bound = -INFINITY;
     if (valid)
-        for (int h = j; h < H; h += LANES) bound = fmaxf(bound, s_xm[h] + em[h]);    // each lane reads what it wrote
+        for (int h = j; h < H; h += LANES) {                                         // each lane reads the em it wrote
+            const float xm = s_xm[h];
+            bound = fmaxf(bound, (xm <= 126.f) ? xm + em[h] : INFINITY);             // +inf stays +inf whatever em is
+        }
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) {
         bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
         ehi = fmaxf(ehi, __shfl_xor_sync(0xffffffffu, ehi, o));
         elo = fminf(elo, __shfl_xor_sync(0xffffffffu, elo, o));
     }
-    const bool fast = (bound <= 61.f) && (ehi <= 80.f) && (elo >= -80.f);
+    // with e'' = e' - 31:  XM + e' <= 61,  -80 <= e' <= 80;  in_ok is the same for all lanes of a particle
+    const bool fast = in_ok && (s_misc[7] != 0.f) && (bound <= 30.f) && (ehi <= 49.f) && (elo >= -111.f);
     if (valid && !fast) {                         // plain loop: raw e' (each lane rewrites the entries it owns)
         for (int h = j; h < H; h += LANES) {
             const float bh = __ldg(a.b1 + h);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                float acc = bh;
+                float acc = bh;                   // unscaled weights, one scaling of the sum: no error growth under cancellation
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     acc = fmaf(__ldg(a.W1 + h * 3 * D + D + d), mk[k * D + d], acc);
@@ -425,11 +530,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
             }
         }
     }
-    if (LEAN) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's uniforms / labels landed
-        __syncwarp();                                              // a particle's lanes share a warp: publishes them, s_e, s_tab
-    }
-    else stage_wait(&bar, 0);                                      // rows landed; also publishes s_e / s_tab
+    __syncwarp();                                                  // a particle's lanes share a warp: publishes s_e
 
     PlainF A_llf, A_llb, A_lpzf, A_lpzb, A_lqzf, A_lqzb, A_loc;     // <= ceil(N/LANES) terms per lane
     if (valid) {
@@ -437,7 +538,8 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
         float* zn = s_zn + (size_t)p * NK;
         const unsigned char* zlo = a.zl_old + r * a.LN;          // label rows of this particle (label mode)
         unsigned char* zln = a.zl_new + r * a.LN;
-        const float* tab = s_tab + (size_t)p * (KD * 3);
+        const float* tab = s_tab + (size_t)p * (K * TRS);
+        const float b2l = b2 * 1.4426950408889634f;              // logits are carried in log2 units: l' = log2(e) logit
 #pragma unroll(NC ? 2 : 1)
         for (int it = 0; it < nIt; ++it) {
             const int n0 = it * (LANES * PB) + j;
@@ -457,8 +559,10 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 #pragma unroll
                 for (int k = 0; k < K; ++k) { L02[k] = 0ull; L13[k] = 0ull; }
                 const unsigned char* exb = reinterpret_cast<const unsigned char*>(s_ex + (size_t)(it * LANES + j) * PB);
+#if APGS_ZF_EXPT != 1
                 mlp_quad_fast<K>(exb, EXS * 4, reinterpret_cast<const unsigned char*>(ep),
                                  reinterpret_cast<const unsigned char*>(s_aw), H4, L02, L13);
+#endif
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     unpack2(L02[k], logit[0][k], logit[2][k]);
@@ -467,7 +571,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 #pragma unroll
                 for (int q = 0; q < PB; ++q)
 #pragma unroll
-                    for (int k = 0; k < K; ++k) logit[q][k] = fmaf(logit[q][k], 4.656612873077393e-10f, b2);
+                    for (int k = 0; k < K; ++k) logit[q][k] = fmaf(logit[q][k], 4.656612873077393e-10f * 1.4426950408889634f, b2l);
             } else {
 #pragma unroll
                 for (int q = 0; q < PB; ++q)
@@ -479,6 +583,10 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 #pragma unroll
                     for (int d = 0; d < D; ++d) xq[q][d] = (n0 + q * LANES < N) ? s_x[(n0 + q * LANES) * D + d] : 0.f;
                 mlp_quad_plain<K, D, PB>(a.W1, xq, ep, s_aw, H, logit);
+#pragma unroll
+                for (int q = 0; q < PB; ++q)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) logit[q][k] *= 1.4426950408889634f;
             }
             if (!LEAN && rng) {
                 const uint4 w = philox_block(r, it * LANES + j, key);
@@ -491,26 +599,27 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
             for (int q = 0; q < PB; ++q) {
                 const int n = n0 + q * LANES;
                 if (n >= N) continue;
+#if APGS_ZF_EXPT == 2
+                if (LEAN) { A_loc.add(logit[q][0] + logit[q][1] + logit[q][K - 1]); continue; }
+#endif
                 if (LEAN) { uq[q] = s_u[(size_t)p * NU + n]; lbq[q] = (int)s_lb[(size_t)p * LS + n]; }
                 float xn[D];                                          // the point itself: only the log-densities need it
 #pragma unroll
                 for (int d = 0; d < D; ++d) xn[d] = s_x[n * D + d];
+                // softmax in log2 units: e_k = 2^(l'_k - max), q_k = e_k / sum e.  The draw compares u * sum e against the
+                // running sums of e (no normalised probabilities needed), and log q_k = ln 2 (l'_k - (max + log2 sum e)):
+                // ONE lg2 serves the forward and the backward label.  (The reference normalises twice -- F.softmax, then
+                // Categorical's probs / probs.sum(-1), apgs/gmm/models.py:104,115 -- which is this quotient up to rounding.)
                 float mx = logit[q][0];
 #pragma unroll
                 for (int k = 1; k < K; ++k) mx = fmaxf(mx, logit[q][k]);
                 float pr[K], se = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) { pr[k] = ex2_ftz((logit[q][k] - mx) * 1.4426950408889634f); se += pr[k]; }
-                const float rse = rcp_ftz(se);
-#pragma unroll
-                for (int k = 0; k < K; ++k) pr[k] *= rse;                         // F.softmax(., -1)
-                float sq = 0.f;
-#pragma unroll
-                for (int k = 0; k < K; ++k) sq = __fadd_rn(sq, pr[k]);            // Categorical renormalisation
-                const float rsq = rcp_ftz(sq);
+                for (int k = 0; k < K; ++k) { pr[k] = ex2_ftz(logit[q][k] - mx); se = __fadd_rn(se, pr[k]); }
                 if (want_q) {
+                    const float rse = rcp_ftz(se);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) a.q_probs[(r * N + n) * K + k] = pr[k];
+                    for (int k = 0; k < K; ++k) a.q_probs[(r * N + n) * K + k] = pr[k] * rse;     // F.softmax(., -1)
                 }
                 int lf = 0;
                 if (forced) {
@@ -518,8 +627,8 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 #pragma unroll
                     for (int k = 1; k < K; ++k) { const float v = zn[n * K + k]; if (v > best) { best = v; lf = k; } }
                 } else {
-                    // inverse CDF on the (unnormalised) probabilities: label = #{k : cdf_k <= u * sum}
-                    const float t = __fmul_rn(uq[q], sq);
+                    // inverse CDF on the unnormalised probabilities: label = #{k : cdf_k <= u * sum}
+                    const float t = __fmul_rn(uq[q], se);
                     float c = 0.f;
 #pragma unroll
                     for (int k = 0; k < K - 1; ++k) { c = __fadd_rn(c, pr[k]); lf += (t >= c) ? 1 : 0; }
@@ -530,16 +639,23 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
                 }
                 if (LEAN) s_lb[(size_t)p * LS + n] = (unsigned char)lf;      // the old label of this point is already in lbq
                 else if (lab_new) zln[n] = (unsigned char)lf;
-                float plf = pr[0], lpf = logpi[0];
+                const float lnorm = __fadd_rn(mx, lg2_ftz(se));              // log2 of the softmax normaliser
+                float slf = logit[q][0], lpf = logpi[0];
 #pragma unroll
-                for (int k = 1; k < K; ++k) if (lf == k) { plf = pr[k]; lpf = logpi[k]; }
-                const float lqf = log_fast(fminf(fmaxf(plf * rsq, FLT_EPS_F), 1.f - FLT_EPS_F));
+                for (int k = 1; k < K; ++k) if (lf == k) { slf = logit[q][k]; lpf = logpi[k]; }
+                // Categorical.log_prob clamps the probability to [eps, 1 - eps] (torch/distributions/utils.py clamp_probs)
+                const float lqf = fminf(fmaxf(__fmul_rn(__fsub_rn(slf, lnorm), LN2_F), LOG_EPS_F), LOG_1M_EPS_F);
                 float llf = 0.f;
+                {
+                    float row[TRS];
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const float* tf = tab + (lf * D + d) * 3;
-                    const float df = __fsub_rn(xn[d], tf[0]);
-                    llf = __fadd_rn(llf, __fsub_rn(-__fmul_rn(__fmul_rn(df, df), tf[1]), tf[2]));
+                    for (int i = 0; i < TRS / 4; ++i)
+                        *reinterpret_cast<float4*>(row + 4 * i) = *reinterpret_cast<const float4*>(tab + lf * TRS + 4 * i);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float df = __fsub_rn(xn[d], row[3 * d]);
+                        llf = __fadd_rn(llf, __fsub_rn(-__fmul_rn(__fmul_rn(df, df), row[3 * d + 1]), row[3 * d + 2]));
+                    }
                 }
                 A_llf.add(llf); A_lqzf.add(lqf); A_lpzf.add(lpf);
                 if (has_bwd) {
@@ -549,16 +665,21 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 #pragma unroll
                         for (int k = 1; k < K; ++k) { const float v = zo[n * K + k]; if (v > best) { best = v; lb = k; } }
                     }
-                    float plb = pr[0], lpb = logpi[0];
+                    float slb = logit[q][0], lpb = logpi[0];
 #pragma unroll
-                    for (int k = 1; k < K; ++k) if (lb == k) { plb = pr[k]; lpb = logpi[k]; }
-                    const float lqb = log_fast(fminf(fmaxf(plb * rsq, FLT_EPS_F), 1.f - FLT_EPS_F));
+                    for (int k = 1; k < K; ++k) if (lb == k) { slb = logit[q][k]; lpb = logpi[k]; }
+                    const float lqb = fminf(fmaxf(__fmul_rn(__fsub_rn(slb, lnorm), LN2_F), LOG_EPS_F), LOG_1M_EPS_F);
                     float llb = 0.f;
+                    {
+                        float row[TRS];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) {
-                        const float* tbp = tab + (lb * D + d) * 3;
-                        const float db = __fsub_rn(xn[d], tbp[0]);
-                        llb = __fadd_rn(llb, __fsub_rn(-__fmul_rn(__fmul_rn(db, db), tbp[1]), tbp[2]));
+                        for (int i = 0; i < TRS / 4; ++i)
+                            *reinterpret_cast<float4*>(row + 4 * i) = *reinterpret_cast<const float4*>(tab + lb * TRS + 4 * i);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const float db = __fsub_rn(xn[d], row[3 * d]);
+                            llb = __fadd_rn(llb, __fsub_rn(-__fmul_rn(__fmul_rn(db, db), row[3 * d + 1]), row[3 * d + 2]));
+                        }
                     }
                     if (!LEAN) { A_llb.add(llb); A_lqzb.add(lqb); A_lpzb.add(lpb); }   // only log_w_b needs these sums
                     const float wf = __fsub_rn(__fadd_rn(llf, lpf), lqf);
@@ -602,11 +723,11 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
         EtaNssAcc<K, D, true> acc;
         {
             float cen[K][D];
-            const float* tab = s_tab + (size_t)p * (KD * 3);
+            const float* tab = s_tab + (size_t)p * (K * TRS);
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int d = 0; d < D; ++d) cen[k][d] = valid ? tab[(k * D + d) * 3] : 0.f;      // this particle's mu
+                for (int d = 0; d < D; ++d) cen[k][d] = valid ? tab[k * TRS + d * 3] : 0.f;      // this particle's mu
             acc.init(cen);
         }
         __syncwarp();                                  // the labels of the particle's other lanes
@@ -661,7 +782,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
 // correlated, twice the Ex-table work) 1.23 ms vs 1.20; tau / mu loads hoisted above the Ex table 1.22 ms; a CTA that
 // walks four chunks of its instance (one Ex table, no CTA barrier after the first chunk) 1.21 ms.
 #ifndef APGS_ZF_P
-#define APGS_ZF_P 32
+#define APGS_ZF_P 16
 #endif
 constexpr int kFP = APGS_ZF_P, kFLanes = 8, kFPB = 4;
 
@@ -680,7 +801,6 @@ static int launch_zfused_lean(const ZFusedArgs& a, cudaStream_t st, size_t smem_
 template <int K, int D>
 static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     const int H4 = (a.H + 3) / 4 * 4;
-    const int nIt = (a.N + kFLanes * kFPB - 1) / (kFLanes * kFPB);
     const bool tiles = a.z_old != nullptr || a.z_forced != nullptr || a.z_new != nullptr;
     const bool nss = a.oa != nullptr;
     const bool lean = a.zl_old && a.zl_new && (a.u || a.seed) && !tiles && !a.q_probs && !a.lw_local && !a.lq_local &&
@@ -690,12 +810,13 @@ static int launch_zfused(const ZFusedArgs& a, cudaStream_t st) {
     if (nss && !kNssOk) return fail(APGS_E_UNSUPPORTED, "gmm_z_fused: eta statistics need K*D <= %d", kFLanes);
     const size_t tile_f = tiles ? ((size_t)kFP * a.N * K + 3) / 4 * 4 : 0;
     const int EPB = (nss && kNssOk) ? zf_block_floats<K, D, kFLanes, kNssOk>(H4) : zf_block_floats<K, D, kFLanes, false>(H4);
-    const size_t smem = (2 * tile_f + (size_t)H4 * nIt * kFLanes * kFPB + (size_t)kFP * EPB + (size_t)2 * H4 +
-                         (size_t)kFP * K * D * 3 + (size_t)(a.N * D + 3) / 4 * 4) * 4;
+    const ZTabLayout TL = zf_tab_layout(a.N, H4, D);
+    if (a.tables && !aligned(a.tables, 16)) return fail(APGS_E_BADARG, "gmm_z_fused: tables must be 16-byte aligned");
+    const size_t smem = (2 * tile_f + (size_t)TL.copy_floats + (size_t)kFP * EPB + (size_t)kFP * K * ((3 * D + 3) / 4 * 4)) * 4;
     const size_t smem_lean = smem + (size_t)kFP * ((a.N + 3) / 4 * 4) * 4 + (size_t)kFP * ((a.N + 15) / 16 * 16) +
                              (nss ? (size_t)a.N * K * EtaTab<K, D>::RS * 4 : 0);
     const size_t smem_used = lean ? smem_lean : smem;
-    // dynamic + static (mbarrier, s_misc) shared memory against the opt-in limit of one CTA (227 KB on sm_100)
+    // dynamic + static (mbarrier) shared memory against the opt-in limit of one CTA (227 KB on sm_100)
     if (smem_used + 256 > 200 * 1024) {
         if (lean && !nss && smem + 256 <= 200 * 1024) {
             // the lean variant's staging of uniforms / labels does not fit: the generic variant (same numbers) does
@@ -734,7 +855,7 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
                         int64_t B, int64_t N, int64_t K, int64_t D, float* z_new, unsigned char* z_new_lab,
                         int64_t label_stride, float* q_probs, const apgs_gmm_out_t* out, void* stream,
                         const float* const* heads = nullptr, const apgs_gmm_post_out_t* post_out = nullptr,
-                        float* stats_out = nullptr, const uint64_t* philox_seed = nullptr) {
+                        float* stats_out = nullptr, const uint64_t* philox_seed = nullptr, const float* tables = nullptr) {
     if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024)
         return fail(APGS_E_SHAPE, "gmm_z_step_fused: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S, (long long)B,
                     (long long)N, (long long)H);
@@ -747,6 +868,7 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
     a.x = x; a.tau = tau; a.mu = mu; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
     a.z_old = z_old; a.zl_old = z_old_lab; a.z_forced = z_forced; a.u = uniforms; a.rpi = prior->pi;
     a.seed = reinterpret_cast<const unsigned long long*>(philox_seed);
+    a.tables = tables;
     a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
     a.z_new = z_new; a.zl_new = z_new_lab; a.LN = label_stride; a.q_probs = q_probs;
     if (out) {
@@ -769,6 +891,39 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
     if (K == 5 && D == 2) return launch_zfused<5, 2>(a, st);
     if (K == 3 && D == 3) return launch_zfused<3, 3>(a, st);
     return fail(APGS_E_UNSUPPORTED, "gmm_z_step_fused: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
+}
+
+template <int K, int D>
+static int launch_ztables(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const float* rpi, int B, int N, int H, float* tables, cudaStream_t st) {
+    const ZTabLayout L = zf_tab_layout(N, (H + 3) / 4 * 4, D);
+    const size_t smem = (size_t)L.total * 4;
+    if (smem + 256 > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_z_tables: N=%d H=%d too large for one tile", N, H);
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_gmm_z_tables<K, D>), smem), "smem attr");
+    k_gmm_z_tables<K, D><<<(unsigned int)B, 256, smem, st>>>(x, W1, b1, W2, b2, rpi, N, H, tables);
+    APGS_LAUNCH_OK("k_gmm_z_tables launch");
+    return 0;
+}
+
+extern "C" size_t apgs_gmm_z_tables_bytes(int64_t B, int64_t N, int64_t H, int64_t K, int64_t D) {
+    if (B <= 0 || N <= 0 || H <= 0 || H > 1024 || K <= 0 || D <= 0) return 0;
+    return (size_t)B * (size_t)zf_tab_layout((int)N, (int)((H + 3) / 4 * 4), (int)D).total * 4;
+}
+
+extern "C" int apgs_gmm_z_tables_f32(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                                     int64_t H, const apgs_gmm_prior_t* prior, int64_t B, int64_t N, int64_t K, int64_t D,
+                                     float* tables, void* stream) {
+    if (B <= 0 || N <= 0 || H <= 0 || H > 1024)
+        return fail(APGS_E_SHAPE, "gmm_z_tables: bad sizes B=%lld N=%lld H=%lld", (long long)B, (long long)N, (long long)H);
+    if (!x || !W1 || !b1 || !W2 || !b2 || !prior || !prior->pi || !tables) return fail(APGS_E_BADARG, "gmm_z_tables: NULL input");
+    if (!aligned(tables, 16)) return fail(APGS_E_BADARG, "gmm_z_tables: tables must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 3 && D == 2) return launch_ztables<3, 2>(x, W1, b1, W2, b2, prior->pi, (int)B, (int)N, (int)H, tables, st);
+    if (K == 2 && D == 2) return launch_ztables<2, 2>(x, W1, b1, W2, b2, prior->pi, (int)B, (int)N, (int)H, tables, st);
+    if (K == 4 && D == 2) return launch_ztables<4, 2>(x, W1, b1, W2, b2, prior->pi, (int)B, (int)N, (int)H, tables, st);
+    if (K == 5 && D == 2) return launch_ztables<5, 2>(x, W1, b1, W2, b2, prior->pi, (int)B, (int)N, (int)H, tables, st);
+    if (K == 3 && D == 3) return launch_ztables<3, 3>(x, W1, b1, W2, b2, prior->pi, (int)B, (int)N, (int)H, tables, st);
+    return fail(APGS_E_UNSUPPORTED, "gmm_z_tables: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
 }
 
 extern "C" int apgs_gmm_z_step_fused_f32(const float* x, const float* tau, const float* mu, const float* W1,
@@ -811,6 +966,29 @@ extern "C" int apgs_gmm_z_step_fused_labels_eta_f32(const float* x, const float*
                         nullptr, z_new_labels, label_stride, nullptr, out, stream, heads, post_out, stats_out);
 }
 
+extern "C" int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, const float* mu, const float* W1,
+                                             const float* b1, const float* W2, const float* b2, int64_t H,
+                                             const apgs_gmm_prior_t* prior, const float* z_old_onehot,
+                                             const uint8_t* z_old_labels, const uint64_t* philox_seed, int64_t S, int64_t B,
+                                             int64_t N, int64_t K, int64_t D, float* z_new_onehot, uint8_t* z_new_labels,
+                                             int64_t label_stride, float* q_probs, const float* Wg, const float* bg,
+                                             const float* Wo, const float* bo, const apgs_gmm_post_out_t* post_out,
+                                             float* stats_out, const apgs_gmm_out_t* out, const float* tables,
+                                             void* stream) {
+    if (!philox_seed) return fail(APGS_E_BADARG, "gmm_z_step_fused_tab: philox_seed is NULL");
+    if (z_new_labels && label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_tab: label_stride %lld < N", (long long)label_stride);
+    if (post_out || stats_out) {
+        if (!post_out || !stats_out || !z_old_labels || !z_new_labels || z_new_onehot || q_probs)
+            return fail(APGS_E_BADARG, "gmm_z_step_fused_tab: the eta statistics ride on the labels-in / labels-out launch only");
+        if (out && (out->log_w_f || out->log_w_b || out->log_w_local || out->log_q_local))
+            return fail(APGS_E_BADARG, "gmm_z_step_fused_tab: only log_w / log_q_f / density are available with the eta statistics");
+    }
+    const float* heads[4] = {Wg, bg, Wo, bo};
+    return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, z_old_onehot, z_old_labels, nullptr, nullptr, S, B, N, K, D,
+                        z_new_onehot, z_new_labels, z_new_labels ? label_stride : N, q_probs, out, stream,
+                        post_out ? heads : nullptr, post_out, stats_out, philox_seed, tables);
+}
+
 extern "C" int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, const float* mu, const float* W1,
                                              const float* b1, const float* W2, const float* b2, int64_t H,
                                              const apgs_gmm_prior_t* prior, const float* z_old_onehot,
@@ -820,15 +998,7 @@ extern "C" int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, c
                                              const float* Wo, const float* bo, const apgs_gmm_post_out_t* post_out,
                                              float* stats_out, const apgs_gmm_out_t* out, void* stream) {
     if (!philox_seed) return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: philox_seed is NULL");
-    if (z_new_labels && label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: label_stride %lld < N", (long long)label_stride);
-    if (post_out || stats_out) {
-        if (!post_out || !stats_out || !z_old_labels || !z_new_labels || z_new_onehot || q_probs)
-            return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: the eta statistics ride on the labels-in / labels-out launch only");
-        if (out && (out->log_w_f || out->log_w_b || out->log_w_local || out->log_q_local))
-            return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: only log_w / log_q_f / density are available with the eta statistics");
-    }
-    const float* heads[4] = {Wg, bg, Wo, bo};
-    return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, z_old_onehot, z_old_labels, nullptr, nullptr, S, B, N, K, D,
-                        z_new_onehot, z_new_labels, z_new_labels ? label_stride : N, q_probs, out, stream,
-                        post_out ? heads : nullptr, post_out, stats_out, philox_seed);
+    return apgs_gmm_z_step_fused_tab_f32(x, tau, mu, W1, b1, W2, b2, H, prior, z_old_onehot, z_old_labels, philox_seed, S, B, N, K,
+                                         D, z_new_onehot, z_new_labels, label_stride, q_probs, Wg, bg, Wo, bo, post_out,
+                                         stats_out, out, nullptr, stream);
 }

@@ -242,8 +242,31 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
     return w
 
 
+def z_tables(x, mlp, prior):
+    """Per-instance tables of the fused z step (apgs_gmm_z_tables_f32): the part of Enc_apg_z that depends only on the data
+    and the encoder weights, built once per objective and handed to z_step_fused(seed=..., tables=...).  x is (B,N,D) or
+    an (S,B,N,D) view of it; returns a float32 CUDA tensor (B, floats per instance)."""
+    lib = _lib.load()
+    x = _x3(x)
+    B, N, D = x.shape
+    W1, b1, W2, b2 = [_req(v, "mlp weight") for v in mlp]
+    H = W1.shape[0]
+    K = prior.prior_pi.numel()
+    if tuple(W1.shape) != (H, 3 * D) or W2.numel() != H or b1.numel() != H or b2.numel() != 1:
+        raise ValueError("unexpected Enc_apg_z weight shapes")
+    nbytes = lib.apgs_gmm_z_tables_bytes(B, N, H, K, D)
+    if nbytes == 0 or nbytes % (4 * B):
+        raise ValueError("apgs_gmm_z_tables_bytes rejected the shape")
+    tables = torch.empty(B, nbytes // (4 * B), dtype=torch.float32, device=x.device)
+    rs, rk = _prior_struct(prior)
+    with torch.cuda.device(x.device), _call("gmm_z_tables", 1, nbytes):
+        check(lib.apgs_gmm_z_tables_f32(ptr(x), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H, C.byref(rs), B, N, K, D,
+                                        ptr(tables), _stream()), "apgs_gmm_z_tables_f32")
+    return tables
+
+
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
-                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None, seed=None):
+                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None, seed=None, tables=None):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
     mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
     z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
@@ -254,13 +277,17 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     for the labels just drawn -- returns (z_new, None, Weights, (alpha, beta, mu_q, nu), stats) with stats the one-hot
     statistics of z_new centred at `mu` -- bit-identical to eta_posterior_fused(x, z_new, heads, prior, center=mu).
     seed = philox_seed(device) (a one-element int64 device tensor): the uniforms of the draw are made inside the kernel
-    (same distribution, Philox stream keyed by the seed) instead of being read from `uniforms`."""
+    (same distribution, Philox stream keyed by the seed) instead of being read from `uniforms`.
+    tables = z_tables(x, mlp, prior) (with seed): the per-instance part of the encoder is fetched instead of rebuilt by
+    every CTA; same results bit for bit."""
     lib = _lib.load()
     if seed is not None:
         if uniforms is not None or z_forced is not None:
             raise ValueError("seed replaces uniforms; it has no meaning with z_forced")
         return _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot,
-                                 eta_heads, seed)
+                                 eta_heads, seed, tables)
+    if tables is not None:
+        raise ValueError("tables ride on the seed entry (apgs_gmm_z_step_fused_tab_f32)")
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
     S, B, K, D = tau.shape
@@ -343,7 +370,8 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     return z_new, q, w
 
 
-def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot, eta_heads, seed):
+def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot, eta_heads, seed,
+                      tables=None):
     """z_step_fused with in-kernel uniforms: the same modes and return values, one entry point."""
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -355,6 +383,10 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
         raise ValueError("unexpected Enc_apg_z weight shapes")
     dev = tau.device
     seed = _req(seed, "seed", dtype=torch.int64)
+    if tables is not None:
+        tables = _req(tables, "tables", ndim=2)
+        if tables.shape[0] != B or tables.numel() * 4 != lib.apgs_gmm_z_tables_bytes(B, N, H, K, D):
+            raise ValueError("tables were built for another shape")
     rs, rk = _prior_struct(prior)
     z_hot_old = z_lab_old = z_hot = z_lab = post = stats = po = None
     heads = [None] * 4
@@ -394,11 +426,12 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
         nbytes = 4 * S * B * (N * K * (2 if z_old is not None else 1) + 2 * K * D + 3 + (N * K if want_q else 0))
     q = torch.empty(S, B, N, K, dtype=torch.float32, device=dev) if want_q else None
     with torch.cuda.device(dev), _call("gmm_z_step_fused", 1, nbytes):
-        check(lib.apgs_gmm_z_step_fused_rng_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
+        check(lib.apgs_gmm_z_step_fused_tab_f32(ptr(x), ptr(tau), ptr(mu), ptr(W1), ptr(b1), ptr(W2), ptr(b2), H,
                                                 C.byref(rs), ptr(z_hot_old), ptr(z_lab_old), ptr(seed), S, B, N, K, D,
                                                 ptr(z_hot), ptr(z_lab), LN, ptr(q), ptr(heads[0]), ptr(heads[1]),
                                                 ptr(heads[2]), ptr(heads[3]), C.byref(po) if po is not None else None,
-                                                ptr(stats), C.byref(o), _stream()), "apgs_gmm_z_step_fused_rng_f32")
+                                                ptr(stats), C.byref(o), ptr(tables), _stream()),
+              "apgs_gmm_z_step_fused_tab_f32")
     if also_labels:
         return (z_hot, z_lab), q, w
     z_new = z_lab if z_lab is not None else z_hot

@@ -76,6 +76,12 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     if x.dim() == 3:
         x = x.unsqueeze(0).expand(resampler.S, -1, -1, -1)       # stride-0 S axis; never materialised
     need_stats = bool(result_flags['loss_required'] or result_flags['ess_required'])
+    # the part of Enc_apg_z that depends only on (x, weights) is the same for every particle and every sweep of this call:
+    # tabulated once per instance, fetched by the z-step CTAs with one bulk copy (kernels.z_tables)
+    ztab = None
+    if (z_tables_per_objective and rng_in_kernels and not result_flags['loss_required'] and getattr(enc_apg_z, 'fused', False)
+            and hasattr(enc_apg_z, 'mlp') and enc_apg_z.can_fuse(False)):
+        ztab = kernels.z_tables(x, enc_apg_z.mlp(), generative)
 
     def resample_and_book(tau, mu, z, log_w, log_q_f):
         """resample_variables + the W1 bookkeeping of the step from the SAME launch: the ancestor kernel's softmax over S
@@ -94,7 +100,7 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
         # 16 bytes so that the gather moves 16-byte vectors).  The one-shot's sampler emits the labels with its draw.
         N = x.shape[-2]
         log_w, tau, mu, _, trace, z, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags,
-                                                      label_stride=(N + 15) // 16 * 16, defer=True)
+                                                      label_stride=(N + 15) // 16 * 16, defer=True, tables=ztab)
     else:
         log_w, tau, mu, z, trace, _, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags, defer=True)
     tau, mu, z = resample_and_book(tau, mu, z, log_w, log_q)
@@ -110,7 +116,7 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
             # particle, so apg_update_eta needs no pass of its own over the labels
             emit = compact and fuse_eta_stats and m < num_sweeps - 2 and _can_emit_eta(enc_apg_eta, generative)
             log_w_z, z, trace, pre = _update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags,
-                                               eta_heads=enc_apg_eta.head_weights() if emit else None)
+                                               eta_heads=enc_apg_eta.head_weights() if emit else None, tables=ztab)
             if pre is not None:
                 outs = resampler.resample([tau, mu, z] + list(pre[0]) + [pre[1]], log_w_z)
                 tau, mu, z, pre = outs[0], outs[1], outs[2], (tuple(outs[3:7]), outs[7])
@@ -190,6 +196,7 @@ lean_oneshot = True
 # statistics are ~1000 instructions per thread wherever they run, so the z step grows by 0.25 ms against 0.32 ms for the
 # standalone kernel, and the 156 extra bytes per particle cost the gather 0.07 ms -- no net gain, hence off by default.
 fuse_eta_stats = False
+z_tables_per_objective = True  # evaluation sweeps: per-instance tables of the z step built once per apg_objective call
 
 
 def _can_emit_eta(enc_apg_eta, generative):
@@ -243,7 +250,7 @@ def _zseed(dev):
     return kernels.philox_seed(dev) if rng_in_kernels else None
 
 
-def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_stride=0, defer=False):
+def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_stride=0, defer=False, tables=None):
     """oneshot; with label_stride (fused sampler only) the draw of z also comes back as uint8 labels (6th value);
     the 7th value is log q of the draw (what a deferred _book_weights needs)."""
     post = enc_rws_eta.params(x, generative.prior_ng)
@@ -255,7 +262,8 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
         # assigned: its log-likelihoods vanish, its density / log_q_f are log p(eta) and log q(eta)).  Same terms as
         # kernels.logw_oneshot, summed as (ll + log p(z)) + log p(eta) instead of (ll + log p(eta)) + log p(z).
         (_, z_lab), _, wz = kernels.z_step_fused(x, tau, mu, enc_rws_z.mlp(), generative, want_q=False,
-                                                 also_labels=label_stride, want_onehot=False, seed=_zseed(tau.device))
+                                                 also_labels=label_stride, want_onehot=False, seed=_zseed(tau.device),
+                                                 tables=tables if rng_in_kernels else None)
         S, B, K, D = tau.shape
         we = kernels.logw_eta_stats(torch.zeros(S, B, K, 1 + 2 * D, device=tau.device), mu, post, generative,
                                     tau, mu, tau, mu)
@@ -368,7 +376,7 @@ def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
     return _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags)[:3]
 
 
-def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None):
+def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None, tables=None):
     """apg_update_z; with eta_heads (label mode, evaluation flags) the fused kernel also emits the next eta step's
     (posterior parameters, statistics) as the 4th value (else None)."""
     need_local = bool(result_flags['loss_required'])
@@ -388,13 +396,14 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
         return log_w, z, trace, None
     if eta_heads is not None and not (result_flags['mode_required'] or need_local):
         z, q_probs, w, post, stats = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
-                                                          eta_heads=eta_heads, seed=_zseed(tau.device))
+                                                          eta_heads=eta_heads, seed=_zseed(tau.device),
+                                                          tables=tables if rng_in_kernels else None)
         pre = (post, stats)
     elif enc_apg_z.can_fuse(result_flags['loss_required']):
         # N1: MLP + softmax + draw + weights in one kernel; q_probs only materialised when asked for
         z, q_probs, w = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
                                              want_q=bool(result_flags['mode_required']), local=need_local,
-                                             seed=_zseed(tau.device))
+                                             seed=_zseed(tau.device), tables=tables if rng_in_kernels else None)
     else:
         q_probs = enc_apg_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()

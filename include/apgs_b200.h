@@ -310,6 +310,27 @@ APGS_API int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, con
                               const float* Wg, const float* bg, const float* Wo, const float* bo,
                               const apgs_gmm_post_out_t* post_out, float* stats_out,
                               const apgs_gmm_out_t* out, void* stream);
+/* Per-instance tables of the z step.  Everything Enc_apg_z.forward (apgs/gmm/models.py:102-115) computes from the DATA
+ *   and the encoder WEIGHTS alone -- the data half of the first Linear (W1[:, :D] x_n, tabulated as 2^(2 log2(e) .)), the
+ *   output weights, b2 + sum_h W2[h], the clamped log prior (apgs/gmm/models.py:168-170) and the points -- is the same for
+ *   every particle of an instance and for every sweep of an objective (the reference re-evaluates it S times per sweep
+ *   on the repeated data, apgs/gmm/apg_training.py:19).  apgs_gmm_z_tables_f32 writes it once per instance
+ *   (apgs_gmm_z_tables_bytes(B, N, H, K, D) bytes, 16-byte aligned) and apgs_gmm_z_step_fused_tab_f32 -- the in-kernel-
+ *   uniform entry with one more argument -- fetches an instance's block with a single bulk copy per CTA instead of
+ *   rebuilding it.  tables = NULL: identical to apgs_gmm_z_step_fused_rng_f32.  Results are bit-identical either way.
+ *   The tables depend on (x, W1, b1, W2, b2, prior->pi): rebuild them when any of these changes.                       */
+APGS_API size_t apgs_gmm_z_tables_bytes(int64_t B, int64_t N, int64_t H, int64_t K, int64_t D);
+APGS_API int apgs_gmm_z_tables_f32(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                              int64_t H, const apgs_gmm_prior_t* prior, int64_t B, int64_t N, int64_t K, int64_t D,
+                              float* tables, void* stream);
+APGS_API int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, const float* mu,
+                              const float* W1, const float* b1, const float* W2, const float* b2, int64_t H,
+                              const apgs_gmm_prior_t* prior, const float* z_old_onehot, const uint8_t* z_old_labels,
+                              const uint64_t* philox_seed, int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                              float* z_new_onehot, uint8_t* z_new_labels, int64_t label_stride, float* q_probs,
+                              const float* Wg, const float* bg, const float* Wo, const float* bo,
+                              const apgs_gmm_post_out_t* post_out, float* stats_out,
+                              const apgs_gmm_out_t* out, const float* tables, void* stream);
 APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
                                      const float* Wg, const float* bg, const float* Wo, const float* bo,
                                      int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,

@@ -618,3 +618,59 @@ def test_z_step_in_kernel_uniforms_draw_from_q_and_are_independent():
         a, b = resid[:, :, :-lag, 0], resid[:, :, lag:, 0]
         corr = float((a * b).mean() / (a.pow(2).mean() * b.pow(2).mean()).sqrt())
         assert abs(corr) < 4.5 / a.numel() ** 0.5, (lag, corr)
+
+
+@pytest.mark.parametrize("S,B,N,K,D,H", [(1000, 8, 60, 3, 2, 32), (37, 5, 41, 3, 2, 16), (9, 3, 30, 2, 2, 10), (33, 4, 60, 4, 2, 32),
+                                         (21, 3, 17, 3, 3, 7), (40, 2, 100, 5, 2, 32)])
+def test_z_step_with_per_instance_tables_is_bit_identical(S, B, N, K, D, H):
+    """kernels.z_tables: the data / weight dependent part of Enc_apg_z tabulated once per instance and fetched by the CTAs
+    with one bulk copy -- the same numbers as the CTA building them itself, bit for bit, in every variant (lean labels,
+    non-lean labels with every optional output, one-hot, sample-only), including instances that take the plain loop."""
+    from apgs_b200.gmm import kernels
+    torch.manual_seed(5)
+    P, gen = og.make_params(K, D, H), _Gen(K, D)
+    x, tau, mu, lab_old, _ = _latents(S, B, K, D, N, seed=21)
+    if B >= 3:
+        mu[:, 1] *= 40.0                                       # saturating pre-activations: these particles take the plain loop
+    xg, tg, mg = x.to(DEV), tau.to(DEV), mu.to(DEV)
+    lo = _pad_labels(lab_old.to(DEV), LN=(N + 15) // 16 * 16)
+    seed = torch.tensor([424242, 0], dtype=torch.int64, device=DEV)
+    mlp = _mlp(P)
+    tab = kernels.z_tables(xg, mlp, gen)
+    assert tab.shape[0] == B and tab.dtype == torch.float32
+    for kw in (dict(z_old=lo), dict(z_old=lo, want_q=True, parts=True, local=True),
+               dict(z_old=torch.nn.functional.one_hot(lab_old.long(), K).float().to(DEV), want_q=True),
+               dict(also_labels=lo.shape[-1])):
+        a = kernels.z_step_fused(xg, tg, mg, mlp, gen, seed=seed, **kw)
+        b = kernels.z_step_fused(xg, tg, mg, mlp, gen, seed=seed, tables=tab, **kw)
+        za, zb = (a[0], b[0]) if not isinstance(a[0], tuple) else (a[0][1], b[0][1])
+        assert torch.equal(za[..., :N], zb[..., :N]), kw.keys()
+        if a[1] is not None:
+            assert torch.equal(a[1], b[1])
+        for name in ("log_w", "density", "log_q_f", "log_w_f", "log_w_b", "log_w_local", "log_q_local"):
+            va, vb = getattr(a[2], name, None), getattr(b[2], name, None)
+            if va is not None:
+                assert torch.equal(va, vb), (name, kw.keys())
+    # tables built for another shape are refused
+    with pytest.raises(ValueError):
+        kernels.z_step_fused(xg, tg, mg, mlp, gen, z_old=lo, seed=seed, tables=tab[:, :-4].contiguous())
+
+
+def test_objective_with_per_instance_tables_is_bit_identical():
+    """apg_objective with the bench flags: z tables on / off give the same trace bit for bit (same torch seed)."""
+    from apgs_b200.gmm import objectives
+    from apgs_b200.resampler import Resampler
+    P = og.make_params()
+    models = _models_from_params(P)
+    x = og.simulate(24, 60, 3, 2).to(DEV)
+    out = {}
+    for on in (True, False):
+        objectives.z_tables_per_objective = on
+        try:
+            torch.manual_seed(3)
+            with torch.no_grad():
+                out[on] = objectives.apg_objective(models, x, BENCH_FLAGS, 4, "decomposed", Resampler("systematic", 200, True, DEV))
+        finally:
+            objectives.z_tables_per_objective = True
+    for k in ("ess", "density", "log_z"):
+        assert torch.equal(out[True][k], out[False][k]), k
