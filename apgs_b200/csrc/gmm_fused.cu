@@ -18,7 +18,8 @@
 #include "rng.cuh"
 
 #ifndef APGS_ZF_EXPT
-#define APGS_ZF_EXPT 0      // measurement-only builds: 1 = no MLP loop, 2 = no per-point epilogue (lean launch)
+#define APGS_ZF_EXPT 0      // measurement-only builds: 1 = no MLP loop, 2 = no per-point epilogue (lean launch),
+                            // 3 = constant uniforms (no Philox), 4 = constant Ee table (no per-particle first layer)
 #endif
 
 namespace apgs {
@@ -129,19 +130,23 @@ template <int K>
 __device__ __forceinline__ void mlp_quad_fast(const unsigned char* ex_ptr, int ex_stride_b, const unsigned char* ev_ptr,
                                               const unsigned char* aw_ptr, int H4, f32x2 (&L02)[K], f32x2 (&L13)[K]) {
     const f32x2 c2 = pack2(4.656612873077393e-10f, 4.656612873077393e-10f);   // 2^-31
-#pragma unroll 1      // unroll 2 measured slower (1.60 vs 1.53 ms): the second quad's table loads raise the register pressure
-    for (int h = 0; h < H4; h += 4) {
+    // unroll 1: unroll 2 measured slower (1.60 vs 1.53 ms: the second quad's table loads raise the register pressure), and
+    // unroll 2 / 4 / 8 with a compiler barrier between the quads (immediate offsets, no pointer updates) 1.17 / 1.16 / 1.19
+    // vs 1.155 ms
+#pragma unroll 1
+    for (const unsigned char* ev_end = ev_ptr + (size_t)H4 * K * 4; ev_ptr != ev_end;      // one compare, no separate counter
+         ev_ptr += 4 * K * 4, ex_ptr += 4 * (size_t)ex_stride_b, aw_ptr += 16) {
         f32x2 ex02[4], ex13[4], aw[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const ulonglong2 exq = *reinterpret_cast<const ulonglong2*>(ex_ptr + (size_t)(h + i) * ex_stride_b);
+            const ulonglong2 exq = *reinterpret_cast<const ulonglong2*>(ex_ptr + (size_t)i * ex_stride_b);
             ex02[i] = exq.x; ex13[i] = exq.y;                         // (Ex[q0], Ex[q2]), (Ex[q1], Ex[q3])
         }
         {
-            const float4 v = *reinterpret_cast<const float4*>(aw_ptr + (size_t)h * 4);
+            const float4 v = *reinterpret_cast<const float4*>(aw_ptr);
             aw[0] = pack2(v.x, v.x); aw[1] = pack2(v.y, v.y); aw[2] = pack2(v.z, v.z); aw[3] = pack2(v.w, v.w);
         }
-        const float4* evq = reinterpret_cast<const float4*>(ev_ptr + (size_t)h * K * 4);
+        const float4* evq = reinterpret_cast<const float4*>(ev_ptr);
 #pragma unroll
         for (int k = 0; k < K; ++k) {                                 // cluster k of the four units: one LDS.128
             const float4 v = evq[k];
@@ -313,7 +318,9 @@ __global__ void __launch_bounds__(256) k_gmm_z_tables(const float* x, const floa
 // LEAN: the launch a sweep repeats -- labels in, labels out, uniforms given, no one-hot rows, no per-point outputs.
 // The options are compile-time false there, so their tests, pointers and staging code drop out of the hot variant.
 // HC / NC: hidden width and points per instance when known at compile time (the reference's 32 and 60), else 0.
-template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0, bool NSS = false>
+// TABM: 1 / 0 = per-instance tables handed in / not, known at compile time (the hot lean instantiations: the other path's
+// code -- predicated off at run time otherwise, but still issued -- drops out); 2 = decided at run time.
+template <int K, int D, int P, int LANES, int PB, bool LEAN, int HC = 0, int NC = 0, bool NSS = false, int TABM = 2>
 __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fused(ZFusedArgs a) {
     static_assert(LANES == 8 && PB == 4, "the Ex table layout assumes 8 lanes x 4 points per particle and pass");
     static_assert(!NSS || LEAN, "the eta statistics ride on the lean label-mode launch");
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     const bool has_bwd = LEAN || a.z_old != nullptr || lab_old;
     const bool forced = !LEAN && a.z_forced != nullptr;
     const bool rng = a.seed != nullptr && !forced;
-    const bool have_tab = a.tables != nullptr;
+    const bool have_tab = TABM == 2 ? a.tables != nullptr : TABM == 1;
     uint2 key = make_uint2(0u, 0u);
     if (rng) { const unsigned long long sd = __ldg(a.seed); key = make_uint2((unsigned int)sd, (unsigned int)(sd >> 32)); }
     const bool hot_new = !LEAN && a.z_new != nullptr;                      // one-hot z_new wanted (labels may come along)
@@ -402,7 +409,11 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
             // label rows and the CTA's tables are in flight -- so that the main loop carries no generator state
             static_assert(PB <= 4, "one Philox block carries four uniforms");
             for (int it = 0; it < nIt; ++it) {
+#if APGS_ZF_EXPT == 3
+                const uint4 w = make_uint4(key.x, key.y, (unsigned int)r, (unsigned int)(it * LANES + j));
+#else
                 const uint4 w = philox_block(r, it * LANES + j, key);
+#endif
                 const unsigned int ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
                 for (int q = 0; q < PB; ++q) {
@@ -470,6 +481,10 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
             float emax = -INFINITY;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
+#if APGS_ZF_EXPT == 4
+                emax = -31.f; elo = -31.f;
+                ep[ee_slot<K>(h, k)] = bh * mk[k * D] + wm[0] * tk[k * D];
+#else
                 float acc = bh;
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
@@ -478,6 +493,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
                 }
                 if (live) { emax = fmaxf(emax, acc); elo = fminf(elo, acc); }
                 ep[ee_slot<K>(h, k)] = live ? ex2_ftz(acc) : 0.f;              // 2^-31 Ee_k[h]; padding rows 0
+#endif
             }
             em[h] = emax;
             ehi = fmaxf(ehi, emax);
@@ -487,11 +503,14 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
             float tf = 0.f, mf = 0.f;
 #pragma unroll
             for (int ee = 0; ee < KD; ++ee) if (ee == e) { tf = tk[ee]; mf = mk[ee]; }
-            const float sg = inv_sqrt_ref(tf);
+            // sigma = 1 / sqrt(tau) (apgs/gmm/models.py:177):  1 / (2 sigma^2) = tau / 2  and  log sigma = -log(tau) / 2, without
+            // the IEEE sqrt / two divides / logf of the literal form (~45 instructions per particle-warp): the quotient differs
+            // from the reference's rounding chain by <= 2.5 ulp, the SFU log by ~1e-7 absolute -- both far inside the 1e-5 of
+            // the summed magnitudes the weights are held to; tau <= 0 or NaN gives NaN / inf exactly where the reference does
             float* row = tab + (e / D) * TRS + (e % D) * 3;
             row[0] = mf;
-            row[1] = __fdiv_rn(1.f, __fmul_rn(2.f, __fmul_rn(sg, sg)));
-            row[2] = __fadd_rn(logf(sg), LOG_SQRT_2PI_F);
+            row[1] = 0.5f * tf;
+            row[2] = fmaf(lg2_ftz(tf), -0.5f * LN2_F, LOG_SQRT_2PI_F);
         }
     }
     if (LEAN) asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's uniforms / labels landed
@@ -563,6 +582,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
                 mlp_quad_fast<K>(exb, EXS * 4, reinterpret_cast<const unsigned char*>(ep),
                                  reinterpret_cast<const unsigned char*>(s_aw), H4, L02, L13);
 #endif
+
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     unpack2(L02[k], logit[0][k], logit[2][k]);
@@ -788,7 +808,8 @@ constexpr int kFP = APGS_ZF_P, kFLanes = 8, kFPB = 4;
 
 template <int K, int D, bool NSS>
 static int launch_zfused_lean(const ZFusedArgs& a, cudaStream_t st, size_t smem_used) {
-    auto kern = a.H == 32 ? (a.N == 60 ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60, NSS>
+    auto kern = a.H == 32 ? (a.N == 60 ? (a.tables ? k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60, NSS, 1>
+                                                   : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 60, NSS, 0>)
                                        : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 32, 0, NSS>)
                           : k_gmm_z_fused<K, D, kFP, kFLanes, kFPB, true, 0, 0, NSS>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_used), "smem attr");
