@@ -105,6 +105,7 @@ SIGNATURES = {
                                              _i64, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _PO, _p, _OUT, _p]),
     "apgs_gmm_z_step_fused_tab_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _PR, _p, _p, _p,
                                              _i64, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _PO, _p, _OUT, _p, _p]),
+    "apgs_gmm_z_loop_probe_f32": (_int, [_i64, _i64, _p, _p]),
     "apgs_gmm_z_tables_bytes": (_sz, [_i64, _i64, _i64, _i64, _i64]),
     "apgs_gmm_z_tables_f32": (_int, [_p, _p, _p, _p, _p, _i64, _PR, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_gmm_z_logq_backward_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),

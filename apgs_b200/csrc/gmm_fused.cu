@@ -914,6 +914,33 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
     return fail(APGS_E_UNSUPPORTED, "gmm_z_step_fused: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
 }
 
+// Measurement only (bench.py: roofline.mlp_loop_alone): the main loop of the fused z step -- mlp_quad_fast itself, K = 3,
+// H = 32, 32 particles x 8 lanes per CTA as in the step -- on synthetic shared-memory tables, with no prologue and no
+// epilogue.  A CTA runs `passes` passes of eight quads of hidden units; S*B/32 CTAs x 2 passes is the loop work of one
+// launch of the step at N <= 64.  What it shows: packed FFMA2 / FMUL2 take TWO issue slots each, so the loop (84 packed
+// + 27 other instructions per quad) needs ~212 cycles per quad and scheduler against 168 of FMA-pipe time.
+__global__ void __launch_bounds__(256, 4) k_gmm_z_loop_probe(float* out, int passes) {
+    constexpr int K = 3, H4 = 32, EXS = 64, EPB = 132;
+    __shared__ __align__(16) float s_ex[H4 * EXS];
+    __shared__ __align__(16) float s_aw[H4];
+    __shared__ __align__(16) float s_e[32 * EPB];
+    for (int i = threadIdx.x; i < H4 * EXS; i += 256) s_ex[i] = 1.f + 1e-3f * (float)(i & 15);
+    for (int i = threadIdx.x; i < H4; i += 256) s_aw[i] = 0.01f * (float)(i + 1);
+    for (int i = threadIdx.x; i < 32 * EPB; i += 256) s_e[i] = 4.6e-10f * (1.f + 1e-3f * (float)(i & 7));
+    __syncthreads();
+    const int p = threadIdx.x / 8, j = threadIdx.x % 8;
+    f32x2 L02[K], L13[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { L02[k] = 0ull; L13[k] = 0ull; }
+    for (int r = 0; r < passes; ++r)
+        mlp_quad_fast<K>(reinterpret_cast<const unsigned char*>(s_ex + (size_t)((r & 1) * 8 + j) * 4), EXS * 4,
+                         reinterpret_cast<const unsigned char*>(s_e + p * EPB), reinterpret_cast<const unsigned char*>(s_aw), H4, L02, L13);
+    float acc = 0.f, lo, hi;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { unpack2(L02[k], lo, hi); acc += lo + hi; unpack2(L13[k], lo, hi); acc += lo + hi; }
+    out[(size_t)blockIdx.x * 256 + threadIdx.x] = acc;
+}
+
 template <int K, int D>
 static int launch_ztables(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
                           const float* rpi, int B, int N, int H, float* tables, cudaStream_t st) {
@@ -923,6 +950,14 @@ static int launch_ztables(const float* x, const float* W1, const float* b1, cons
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_gmm_z_tables<K, D>), smem), "smem attr");
     k_gmm_z_tables<K, D><<<(unsigned int)B, 256, smem, st>>>(x, W1, b1, W2, b2, rpi, N, H, tables);
     APGS_LAUNCH_OK("k_gmm_z_tables launch");
+    return 0;
+}
+
+extern "C" int apgs_gmm_z_loop_probe_f32(int64_t ctas, int64_t passes, float* out, void* stream) {
+    if (ctas <= 0 || ctas > 0x7fffffff || passes <= 0 || passes > (1 << 20) || !out)
+        return fail(APGS_E_BADARG, "gmm_z_loop_probe: bad arguments");
+    k_gmm_z_loop_probe<<<(unsigned int)ctas, 256, 0, (cudaStream_t)stream>>>(out, (int)passes);
+    APGS_LAUNCH_OK("k_gmm_z_loop_probe launch");
     return 0;
 }
 

@@ -242,6 +242,20 @@ def logw_joint(x, post, prior, tau, mu, tau_old, mu_old, q_probs, z, z_old, part
     return w
 
 
+def z_loop_probe(ctas, passes, out=None, device=None):
+    """Measurement only (apgs_gmm_z_loop_probe_f32): launches the fused z step's main loop alone on synthetic tables --
+    `ctas` CTAs of 32 particles, `passes` passes of eight quads of hidden units -- and returns the checksum buffer."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(int(ctas) * 256, dtype=torch.float32, device=device if device is not None else "cuda")
+    out = _req(out, "out", ndim=1)
+    if out.numel() < int(ctas) * 256:
+        raise ValueError("out needs ctas * 256 floats")
+    with torch.cuda.device(out.device):
+        check(lib.apgs_gmm_z_loop_probe_f32(int(ctas), int(passes), ptr(out), _stream()), "apgs_gmm_z_loop_probe_f32")
+    return out
+
+
 def z_tables(x, mlp, prior):
     """Per-instance tables of the fused z step (apgs_gmm_z_tables_f32): the part of Enc_apg_z that depends only on the data
     and the encoder weights, built once per objective and handed to z_step_fused(seed=..., tables=...).  x is (B,N,D) or

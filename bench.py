@@ -376,6 +376,7 @@ def gmm_roofline(prof, S, B, peak, peak_src, clocks, distinct_frac, probe, dev):
             "share_of_step_kernel_time": round(zf["calls"] * zf["ms_avg"] / tot, 3), "avg_launch_ms": zf["ms_avg"],
             "launches_timed": zf["calls"], "sm_mhz": clk, "alg_GBs": zf["gbs"], "frac_hbm": zf["gbs"] / peak,
             "peak_source": "SMs x 128 lanes x sampled SM clock; hbm: " + peak_src}
+    roof["mlp_loop_alone"] = mlp_loop_probe(S, B, dev, zf["ms_avg"], fma_ops / (peak_fma * 1e12) * 1e3)
     cap = ncu_capture()
     if cap:
         roof["ncu_capture"] = cap
@@ -396,6 +397,31 @@ def gmm_roofline(prof, S, B, peak, peak_src, clocks, distinct_frac, probe, dev):
                               "alg_GBs": ew["gbs"], "frac": ew["gbs"] / peak}
     roof["hbm"] = hbm
     return roof
+
+
+def mlp_loop_probe(S, B, dev, step_ms, fma_floor_ms, iters=5):
+    """The z step's main loop ALONE (apgs_gmm_z_loop_probe_f32: the kernel's own mlp_quad_fast on synthetic shared-memory
+    tables, no prologue / epilogue), timed live for the loop work of one launch (S*B/32 CTAs x 2 passes): the ceiling of
+    the MLP part on this GPU.  Packed FFMA2 / FMUL2 take two issue slots, so the loop (84 packed + 27 other instructions per
+    quad of hidden units) is bound by instruction issue above its FMA-pipe time; the step's other ~1500 instructions per
+    warp share the same issue port."""
+    from apgs_b200.gmm import kernels
+    ctas = (S * B + 31) // 32
+    out = torch.empty(ctas * 256, dtype=torch.float32, device=dev)
+    kernels.z_loop_probe(ctas, 2, out)
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        kernels.z_loop_probe(ctas, 2, out)
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts) // 2]
+    return {"ms": ms, "fma_pipe_floor_ms": fma_floor_ms, "loop_ceiling_frac_of_fma_pipe": fma_floor_ms / ms,
+            "step_launch_ms": step_ms, "loop_share_of_step_launch": ms / step_ms,
+            "note": "the loop alone, same work as one launch of the step, measured in this run; FFMA2/FMUL2 occupy two issue "
+                    "slots each (benchmarks/micro/mlp_loop.cu, profiles/r2_z_step_issue_bound.md)"}
 
 
 def ncu_capture():

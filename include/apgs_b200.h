@@ -331,6 +331,10 @@ APGS_API int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, con
                               const float* Wg, const float* bg, const float* Wo, const float* bo,
                               const apgs_gmm_post_out_t* post_out, float* stats_out,
                               const apgs_gmm_out_t* out, const float* tables, void* stream);
+/* Measurement only: the main loop of the fused z step alone (K = 3, H = 32; `ctas` CTAs of 32 particles x 8 lanes, `passes`
+ *   passes of eight quads of hidden units each, synthetic tables) -- the ceiling of the step's MLP part on this GPU, timed
+ *   by bench.py next to the step itself (roofline.mlp_loop_alone).  out: ctas * 256 floats (a checksum per thread).      */
+APGS_API int apgs_gmm_z_loop_probe_f32(int64_t ctas, int64_t passes, float* out, void* stream);
 APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
                                      const float* Wg, const float* bg, const float* Wo, const float* bo,
                                      int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,

@@ -674,3 +674,15 @@ def test_objective_with_per_instance_tables_is_bit_identical():
             objectives.z_tables_per_objective = True
     for k in ("ess", "density", "log_z"):
         assert torch.equal(out[True][k], out[False][k]), k
+
+
+def test_z_loop_probe_runs_the_main_loop_alone():
+    """apgs_gmm_z_loop_probe_f32 (bench.py's live ceiling of the MLP part): launches, writes a finite checksum per thread,
+    identical on every call; bad arguments are refused before launch."""
+    from apgs_b200.gmm import kernels
+    a = kernels.z_loop_probe(64, 2, device=DEV)
+    b = kernels.z_loop_probe(64, 2, device=DEV)
+    assert a.numel() == 64 * 256 and bool(torch.isfinite(a).all()) and torch.equal(a, b)
+    assert float(a.abs().max()) > 0
+    with pytest.raises(Exception):
+        kernels.z_loop_probe(0, 2, device=DEV)
