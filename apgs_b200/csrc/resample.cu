@@ -382,6 +382,8 @@ struct GLat {
     unsigned int chunks;       // chunks per row when rows_per_blk == 1
     unsigned int blk_begin;    // first block of this latent
     FastDiv d_vpr, d_Bv, d_chunks;
+    const int* first;          // optional (S,B) int32: the latent still sits in the order BEFORE an earlier resampling step
+                               // whose ancestors these are -- the row read is src[first[anc[s,b], b], b]
 };
 struct GatherArgs {
     GLat lat[APGS_MAX_LATENTS];
@@ -430,6 +432,7 @@ __device__ __forceinline__ void gather_block(const GLat& L, const GatherArgs& g,
             long long s = s0 + ds;
             long long anc = g.anc32 ? (long long)__ldg(g.anc32 + s * g.B + bcol)
                                     : __ldg(g.anc64 + s * g.B + bcol);
+            if (L.first != nullptr) anc = (long long)__ldg(L.first + anc * g.B + bcol);
             so[k] = anc * Bv + v;
         }
     }
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(kGThreads) k_gather(const __grid_constant__ Ga
 }
 
 static int launch_gather(const int* anc32, const long long* anc64, long long S, long long B,
-                         const apgs_latent_t* lat, int n, cudaStream_t st) {
+                         const apgs_latent_t* lat, int n, cudaStream_t st, const int32_t* const* first = nullptr) {
     if (n < 0 || n > APGS_MAX_LATENTS) return fail(APGS_E_BADARG, "gather: n_latents=%d out of [0,%d]", n, APGS_MAX_LATENTS);
     if ((anc32 == nullptr) == (anc64 == nullptr)) return fail(APGS_E_BADARG, "gather: exactly one of anc32/anc64 must be given");
     if (n == 0 || S == 0 || B == 0) return 0;
@@ -480,6 +483,7 @@ static int launch_gather(const int* anc32, const long long* anc64, long long S, 
         GLat& L = g.lat[i];
         L.src = reinterpret_cast<const char*>(a.src);
         L.dst = reinterpret_cast<char*>(a.dst);
+        L.first = first ? first[i] : nullptr;
         L.vlog = vlog; L.vpr = (unsigned int)vpr; L.Bv = (unsigned int)Bv;
         L.d_vpr = make_fastdiv(L.vpr); L.d_Bv = make_fastdiv(L.Bv);
         unsigned long long nb;
@@ -681,6 +685,14 @@ extern "C" int apgs_gather_ancestors(const int32_t* anc32, const int64_t* anc64,
     if (latents == nullptr && n_latents > 0) return fail(APGS_E_BADARG, "gather_ancestors: latents is NULL");
     return launch_gather(anc32, reinterpret_cast<const long long*>(anc64), S, B, latents, n_latents,
                          (cudaStream_t)stream);
+}
+
+extern "C" int apgs_gather_ancestors_via(const int32_t* anc32, int64_t S, int64_t B, const apgs_latent_t* latents,
+                                         const int32_t* const* first, int n_latents, void* stream) {
+    if (int e = check_sb(S, B, "gather_ancestors_via")) return e;
+    if (anc32 == nullptr) return fail(APGS_E_BADARG, "gather_ancestors_via: anc32 is NULL");
+    if ((latents == nullptr || first == nullptr) && n_latents > 0) return fail(APGS_E_BADARG, "gather_ancestors_via: latents / first is NULL");
+    return launch_gather(anc32, nullptr, S, B, latents, n_latents, (cudaStream_t)stream, first);
 }
 
 extern "C" int apgs_resample_f32(const float* log_w, const float* w_norm, int64_t S, int64_t B, int strategy,

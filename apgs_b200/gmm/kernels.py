@@ -280,7 +280,8 @@ def z_tables(x, mlp, prior):
 
 
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
-                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None, seed=None, tables=None):
+                 parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None, seed=None, tables=None,
+                 src_ancestors=None):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
     mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
     z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
@@ -293,15 +294,18 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     seed = philox_seed(device) (a one-element int64 device tensor): the uniforms of the draw are made inside the kernel
     (same distribution, Philox stream keyed by the seed) instead of being read from `uniforms`.
     tables = z_tables(x, mlp, prior) (with seed): the per-instance part of the encoder is fetched instead of rebuilt by
-    every CTA; same results bit for bit."""
+    every CTA; same results bit for bit.
+    src_ancestors (S,B) int32 (with seed): tau, mu and z_old of particle (s,b) are read from row (src_ancestors[s,b], b) --
+    the ancestors of a resampling step whose gather is deferred (ops.gather_ancestors(..., first=...)); same results as
+    gathering first."""
     lib = _lib.load()
     if seed is not None:
         if uniforms is not None or z_forced is not None:
             raise ValueError("seed replaces uniforms; it has no meaning with z_forced")
         return _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot,
-                                 eta_heads, seed, tables)
-    if tables is not None:
-        raise ValueError("tables ride on the seed entry (apgs_gmm_z_step_fused_tab_f32)")
+                                 eta_heads, seed, tables, src_ancestors)
+    if tables is not None or src_ancestors is not None:
+        raise ValueError("tables / src_ancestors ride on the seed entry (apgs_gmm_z_step_fused_tab_f32)")
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
     S, B, K, D = tau.shape
@@ -385,7 +389,7 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
 
 
 def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot, eta_heads, seed,
-                      tables=None):
+                      tables=None, src_ancestors=None):
     """z_step_fused with in-kernel uniforms: the same modes and return values, one entry point."""
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -401,6 +405,10 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
         tables = _req(tables, "tables", ndim=2)
         if tables.shape[0] != B or tables.numel() * 4 != lib.apgs_gmm_z_tables_bytes(B, N, H, K, D):
             raise ValueError("tables were built for another shape")
+    if src_ancestors is not None:
+        src_ancestors = _req(src_ancestors, "src_ancestors", dtype=torch.int32, ndim=2)
+        if tuple(src_ancestors.shape) != (S, B):
+            raise ValueError("src_ancestors must be (S, B) int32")
     rs, rk = _prior_struct(prior)
     z_hot_old = z_lab_old = z_hot = z_lab = post = stats = po = None
     heads = [None] * 4
@@ -444,7 +452,7 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
                                                 C.byref(rs), ptr(z_hot_old), ptr(z_lab_old), ptr(seed), S, B, N, K, D,
                                                 ptr(z_hot), ptr(z_lab), LN, ptr(q), ptr(heads[0]), ptr(heads[1]),
                                                 ptr(heads[2]), ptr(heads[3]), C.byref(po) if po is not None else None,
-                                                ptr(stats), C.byref(o), ptr(tables), _stream()),
+                                                ptr(stats), C.byref(o), ptr(tables), ptr(src_ancestors), _stream()),
               "apgs_gmm_z_step_fused_tab_f32")
     if also_labels:
         return (z_hot, z_lab), q, w

@@ -110,6 +110,20 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
         if block == 'decomposed':
             log_w_eta, tau, mu, trace, log_q_f = _update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags,
                                                              defer=True, pre=pre)
+            if compact and defer_gather and ztab is not None and not fuse_eta_stats:
+                # Deferred gather: the z step only READS (tau, mu, z) of the resampled particles, so it takes them through
+                # this resampling step's ancestors, and the gather after the z step composes the two index maps for the
+                # latents that are still in the old order (tau, mu) -- one gather launch per sweep instead of two.
+                if need_stats:
+                    anc1, stats = resampler.ancestors32(log_w_eta, want_stats=True, want_w=bool(result_flags['loss_required']))
+                    _book_weights(trace, result_flags, log_q_f, stats)
+                else:
+                    anc1 = resampler.ancestors32(log_w_eta)
+                log_w_z, z_new, trace, _ = _update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags, tables=ztab,
+                                                     src_ancestors=anc1)
+                anc2 = resampler.ancestors32(log_w_z)
+                tau, mu, z = ops.gather_ancestors([tau, mu, z_new], anc2, first=[anc1, anc1, None])
+                continue
             tau, mu, z = resample_and_book(tau, mu, z, log_w_eta, log_q_f)
             # the z step of every sweep but the last also emits the NEXT eta step's posterior parameters and statistics
             # (functions of the new labels and this particle's mu); they ride through the resampling gather with the
@@ -196,6 +210,7 @@ lean_oneshot = True
 # statistics are ~1000 instructions per thread wherever they run, so the z step grows by 0.25 ms against 0.32 ms for the
 # standalone kernel, and the 156 extra bytes per particle cost the gather 0.07 ms -- no net gain, hence off by default.
 fuse_eta_stats = False
+defer_gather = True            # evaluation sweeps: the z step reads through the eta step's ancestors (one gather per sweep)
 z_tables_per_objective = True  # evaluation sweeps: per-instance tables of the z step built once per apg_objective call
 
 
@@ -376,7 +391,7 @@ def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
     return _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags)[:3]
 
 
-def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None, tables=None):
+def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None, tables=None, src_ancestors=None):
     """apg_update_z; with eta_heads (label mode, evaluation flags) the fused kernel also emits the next eta step's
     (posterior parameters, statistics) as the 4th value (else None)."""
     need_local = bool(result_flags['loss_required'])
@@ -403,7 +418,8 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
         # N1: MLP + softmax + draw + weights in one kernel; q_probs only materialised when asked for
         z, q_probs, w = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
                                              want_q=bool(result_flags['mode_required']), local=need_local,
-                                             seed=_zseed(tau.device), tables=tables if rng_in_kernels else None)
+                                             seed=_zseed(tau.device), tables=tables if rng_in_kernels else None,
+                                             src_ancestors=src_ancestors)
     else:
         q_probs = enc_apg_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()

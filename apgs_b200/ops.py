@@ -200,8 +200,11 @@ def _latent_array(latents, S, B):
     return arr, srcs, outs
 
 
-def gather_ancestors(latents, anc):
-    """out_l[s,b,...] = latent_l[anc[s,b], b, ...] for every latent, in ONE launch (R4)."""
+def gather_ancestors(latents, anc, first=None):
+    """out_l[s,b,...] = latent_l[anc[s,b], b, ...] for every latent, in ONE launch (R4).
+    first: optional list (one entry per latent) of (S,B) int32 ancestor maps or None -- a latent with a map still sits in the
+    order before an earlier resampling step whose gather was deferred, and is read through both maps:
+    out_l[s,b] = latent_l[first_l[anc[s,b], b], b] (apgs_gather_ancestors_via)."""
     lib = _lib.load()
     if anc.dtype not in (torch.int64, torch.int32):
         raise TypeError("ancestor index must be int64 or int32")
@@ -209,6 +212,17 @@ def gather_ancestors(latents, anc):
     S, B = anc.shape
     latents = list(latents)
     arr, srcs, outs = _latent_array(latents, S, B)
+    if first is not None and any(f is not None for f in first):
+        if anc.dtype != torch.int32 or len(first) != len(latents):
+            raise ValueError("composed gathers take int32 ancestors and one `first` entry per latent")
+        fl = [None if f is None else _req(f, "first-level ancestors", dtype=torch.int32, ndim=2) for f in first]
+        if any(f is not None and tuple(f.shape) != (S, B) for f in fl):
+            raise ValueError("first-level ancestor maps must be (S, B)")
+        fp = (C.c_void_p * len(latents))(*[None if f is None else f.data_ptr() for f in fl])
+        nbytes = S * B * (4 + 2 * sum(int(a.inner_bytes) for a in arr[:len(latents)]) + 4 * sum(f is not None for f in fl))
+        with torch.cuda.device(anc.device), _call("gather_ancestors", 1, nbytes):
+            check(lib.apgs_gather_ancestors_via(ptr(anc), S, B, arr, fp, len(latents), _stream()), "apgs_gather_ancestors_via")
+        return outs
     a32 = anc if anc.dtype == torch.int32 else None
     a64 = anc if anc.dtype == torch.int64 else None
     nbytes = S * B * (anc.element_size() + 2 * sum(int(a.inner_bytes) for a in arr[:len(latents)]))

@@ -85,6 +85,23 @@ class Resampler():
         return ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms,
                                     cdf_mode=self.cdf_mode, uniform_layout=self._layout(uniforms, S, B, uniform_layout))
 
+    def ancestors32(self, log_weights, want_stats=False, want_w=True, uniforms=None, uniform_layout=None):
+        """sample_ancestral_index as the kernels keep it (int32), optionally with (w, ess, lse) of the same softmax: the
+        building block of a deferred gather (ops.gather_ancestors(..., first=...)).  Returns anc or (anc, (w, ess, lse))."""
+        self._check(log_weights)
+        S, B = log_weights.shape
+        if uniforms is None:
+            uniforms = self.draw_uniforms(S, B, log_weights.device)
+        r = ops.sample_ancestors(log_w=log_weights, strategy=self.strategy, uniforms=uniforms, cdf_mode=self.cdf_mode,
+                                 index_dtype=torch.int32, want_stats=want_stats, want_w=want_w,
+                                 uniform_layout=self._layout(uniforms, S, B, uniform_layout))
+        if ops.PROFILE.events:                                 # bench.py: fraction of source rows actually read
+            a = r[0] if want_stats else r
+            srt = a if self.strategy == "systematic" else a.sort(0).values
+            ops.PROFILE.notes.setdefault("distinct_ancestor_frac", []).append(
+                ((srt[1:] != srt[:-1]).sum() + B).float() / float(S * B))
+        return (r[0], tuple(r[1:])) if want_stats else r
+
     def resample_4dims(self, var, ancestral_index):
         if var.dim() != 4:
             raise ValueError("resample_4dims expects a 4-D tensor")

@@ -111,6 +111,16 @@ typedef struct apgs_latent {
 APGS_API int apgs_gather_ancestors(const int32_t* anc32, const int64_t* anc64, int64_t S, int64_t B,
                           const apgs_latent_t* latents, int n_latents, void* stream);
 
+/* R4 through an earlier resampling step that was never materialised (deferred gather): a block update that only READS the
+ *   latents of the previous step can take them through that step's ancestors (apgs_gmm_z_step_fused_tab_f32:
+ *   src_ancestors) instead of having them gathered first; the gather after it then composes the two index maps:
+ *     first[l] == NULL:  dst_l[s, b, :] = src_l[anc32[s, b], b, :]                         (latent made by the update)
+ *     first[l] != NULL:  dst_l[s, b, :] = src_l[first[l][anc32[s, b], b], b, :]            (latent still in the old order)
+ *   first: HOST array of n_latents device pointers to (S,B) int32 ancestor maps.  One launch, same kernel as R4.
+ *   Saves one apgs_gather_ancestors per sweep in apgs/gmm/objectives.py:37-45 (eta step -> resample -> z step -> resample). */
+APGS_API int apgs_gather_ancestors_via(const int32_t* anc32, int64_t S, int64_t B, const apgs_latent_t* latents,
+                              const int32_t* const* first, int n_latents, void* stream);
+
 /* R5  fused resample = R2/R3 + R4.  replaces resample_variables,
  *     apgs/gmm/objectives.py:229-234, apgs/dmm/objectives.py:190-195, apgs/bmnist/objectives.py:5-9.
  *   workspace: apgs_resample_workspace_bytes(S,B) (holds the int32 ancestors + CDF scratch).  */
@@ -318,6 +328,9 @@ APGS_API int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, con
  *   (apgs_gmm_z_tables_bytes(B, N, H, K, D) bytes, 16-byte aligned) and apgs_gmm_z_step_fused_tab_f32 -- the in-kernel-
  *   uniform entry with one more argument -- fetches an instance's block with a single bulk copy per CTA instead of
  *   rebuilding it.  tables = NULL: identical to apgs_gmm_z_step_fused_rng_f32.  Results are bit-identical either way.
+ *   src_ancestors (S,B) int32 or NULL: the INPUT latents (tau, mu, z_old) of particle (s,b) are read from row
+ *   (src_ancestors[s,b], b) -- the ancestors of a resampling step whose gather is deferred (apgs_gather_ancestors_via);
+ *   outputs and the random stream are those of particle (s,b).  Bit-identical to gathering first.
  *   The tables depend on (x, W1, b1, W2, b2, prior->pi): rebuild them when any of these changes.                       */
 APGS_API size_t apgs_gmm_z_tables_bytes(int64_t B, int64_t N, int64_t H, int64_t K, int64_t D);
 APGS_API int apgs_gmm_z_tables_f32(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -330,7 +343,7 @@ APGS_API int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, con
                               float* z_new_onehot, uint8_t* z_new_labels, int64_t label_stride, float* q_probs,
                               const float* Wg, const float* bg, const float* Wo, const float* bo,
                               const apgs_gmm_post_out_t* post_out, float* stats_out,
-                              const apgs_gmm_out_t* out, const float* tables, void* stream);
+                              const apgs_gmm_out_t* out, const float* tables, const int32_t* src_ancestors, void* stream);
 /* Measurement only: the main loop of the fused z step alone (K = 3, H = 32; `ctas` CTAs of 32 particles x 8 lanes, `passes`
  *   passes of eight quads of hidden units each, synthetic tables) -- the ceiling of the step's MLP part on this GPU, timed
  *   by bench.py next to the step itself (roofline.mlp_loop_alone).  out: ctas * 256 floats (a checksum per thread).      */

@@ -686,3 +686,64 @@ def test_z_loop_probe_runs_the_main_loop_alone():
     assert float(a.abs().max()) > 0
     with pytest.raises(Exception):
         kernels.z_loop_probe(0, 2, device=DEV)
+
+
+@pytest.mark.parametrize("strategy", ["systematic", "multinomial"])
+def test_deferred_gather_z_step_through_ancestors_and_composed_gather(strategy):
+    """Deferred gather: the z step reading (tau, mu, z_old) through a resampling step's ancestors (src_ancestors) gives the
+    same numbers as gathering first, and ops.gather_ancestors(first=...) composes the two index maps -- bit for bit, in the
+    lean and the non-lean variants."""
+    from apgs_b200 import ops
+    from apgs_b200.gmm import kernels
+    from apgs_b200.resampler import Resampler
+    S, B, N, K = 200, 7, 60, 3
+    P, gen = og.make_params(), _Gen()
+    x, tau, mu, lab_old, _ = _latents(S, B, seed=31)
+    xg, tg, mg, lo = x.to(DEV), tau.to(DEV), mu.to(DEV), _pad_labels(lab_old.to(DEV))
+    torch.manual_seed(7)
+    rs = Resampler(strategy, S, True, DEV)
+    anc1 = rs.ancestors32(torch.randn(S, B, device=DEV) * 2)
+    anc2 = rs.ancestors32(torch.randn(S, B, device=DEV) * 2)
+    assert anc1.dtype == torch.int32 and int(anc1.min()) >= 0 and int(anc1.max()) < S
+    seed = torch.tensor([99, 0], dtype=torch.int64, device=DEV)
+    tab = kernels.z_tables(xg, _mlp(P), gen)
+    tg1, mg1, lo1 = ops.gather_ancestors([tg, mg, lo], anc1)
+    for kw in (dict(), dict(want_q=True, parts=True, local=True)):
+        za, qa, wa = kernels.z_step_fused(xg, tg1, mg1, _mlp(P), gen, z_old=lo1, seed=seed, tables=tab, **kw)
+        zb, qb, wb = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=lo, seed=seed, tables=tab, src_ancestors=anc1, **kw)
+        assert torch.equal(za[..., :N], zb[..., :N])
+        assert torch.equal(wa.log_w, wb.log_w) and torch.equal(wa.density, wb.density) and torch.equal(wa.log_q_f, wb.log_q_f)
+        if qa is not None:
+            assert torch.equal(qa, qb) and torch.equal(wa.log_w_local, wb.log_w_local) and torch.equal(wa.log_w_b, wb.log_w_b)
+    # one-hot z_old rows through the ancestors as well
+    hot = torch.nn.functional.one_hot(lab_old.long(), K).float().to(DEV)
+    (hot1,) = ops.gather_ancestors([hot], anc1)
+    zc, _, wc = kernels.z_step_fused(xg, tg1, mg1, _mlp(P), gen, z_old=hot1, seed=seed)
+    zd, _, wd = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=hot, seed=seed, src_ancestors=anc1)
+    assert torch.equal(zc, zd) and torch.equal(wc.log_w, wd.log_w)
+    # composed gather == two gathers
+    t2, m2, z2 = ops.gather_ancestors([tg1, mg1, za], anc2)
+    t3, m3, z3 = ops.gather_ancestors([tg, mg, za], anc2, first=[anc1, anc1, None])
+    assert torch.equal(t2, t3) and torch.equal(m2, m3) and torch.equal(z2, z3)
+    with pytest.raises(ValueError):
+        ops.gather_ancestors([tg], anc2.long(), first=[anc1])
+
+
+@pytest.mark.parametrize("strategy", ["systematic", "multinomial"])
+def test_objective_with_deferred_gather_is_bit_identical(strategy):
+    """apg_objective (bench flags): one gather per sweep (deferred) vs two -- the same trace bit for bit under one seed."""
+    from apgs_b200.gmm import objectives
+    from apgs_b200.resampler import Resampler
+    models = _models_from_params(og.make_params())
+    x = og.simulate(24, 60, 3, 2).to(DEV)
+    out = {}
+    for on in (True, False):
+        objectives.defer_gather = on
+        try:
+            torch.manual_seed(3)
+            with torch.no_grad():
+                out[on] = objectives.apg_objective(models, x, BENCH_FLAGS, 4, "decomposed", Resampler(strategy, 200, True, DEV))
+        finally:
+            objectives.defer_gather = True
+    for k in ("ess", "density", "log_z"):
+        assert torch.equal(out[True][k], out[False][k]), k
