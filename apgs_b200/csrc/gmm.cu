@@ -38,6 +38,9 @@ struct NssArgs {
     float* stats;         // (R, K, 1 + 2 D)
     const unsigned char* zl;   // (R, N) labels instead of the one-hot z (compact latents inside a sweep), or null
     long long LN;              // bytes between the label rows of consecutive particles (>= N)
+    // deferred gathers (k_gmm_nss_im, label mode): particle (s,b) reads its label row from row (z_anc[s,b], b) and its centre
+    // from row (c_anc[s,b], b) -- ancestor maps (S,B) int32 of resampling steps that were never materialised -- or null
+    const int *z_anc, *c_anc;
 };
 
 template <int K, int D, int P, int LANES, bool FUSED, bool HAS_Z, bool STATS = false>
@@ -285,6 +288,8 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
     const bool valid = s0 + p < S;
     const long long r = (long long)(s0 + p) * a.B + b;
+    const long long rz = (valid && a.z_anc != nullptr) ? (long long)__ldg(a.z_anc + r) * a.B + b : r;     // row of the labels
+    const long long rc = (valid && a.c_anc != nullptr) ? (long long)__ldg(a.c_anc + r) * a.B + b : r;     // row of the centre
     const int rows = min(P, S - s0);
     const unsigned int rb = (unsigned int)NK * 4u;
     const bool labels = a.zl != nullptr;
@@ -299,13 +304,13 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
         if (labels) {
             if (lab_vec) {
                 // cp.async: no register in between, so the table build below overlaps the HBM latency of the rows
-                const unsigned char* src = a.zl + r * a.LN;
+                const unsigned char* src = a.zl + rz * a.LN;
                 for (int i = j; i < LS / 16; i += LANES)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_lab + (size_t)p * LS + i * 16)),
                                  "l"(src + i * 16) : "memory");
                 asm volatile("cp.async.commit_group;" ::: "memory");
             } else {
-                for (int i = j; i < N; i += LANES) s_lab[(size_t)p * LS + i] = __ldg(a.zl + r * a.LN + i);
+                for (int i = j; i < N; i += LANES) s_lab[(size_t)p * LS + i] = __ldg(a.zl + rz * a.LN + i);
             }
         } else if (bulk_in) {
             if (j == 0) bulk_g2s(s_z + (size_t)p * ZS, a.z + r * NK, rb, &bar);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int d = 0; d < D; ++d) cen[k][d] = (STATS && valid) ? __ldg(a.center + r * KD + k * D + d) : 0.f;
+            for (int d = 0; d < D; ++d) cen[k][d] = (STATS && valid) ? __ldg(a.center + rc * KD + k * D + d) : 0.f;
         acc.init(cen);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's label rows (no-op otherwise)
@@ -602,6 +607,9 @@ struct EtaStatsArgs {
     float *tau_out, *mu_out;          // (R, K, D), required with the draws
     // ... or drawn in the kernel: device pointer to two 64-bit words {seed, stream} the host took from torch's generator
     const unsigned long long* seed;
+    // deferred gather: the OLD latents (center, tau_b, mu_b) of particle r = s B + b are read from row old_anc[r] B + b
+    const int* old_anc;
+    int B;
 };
 
 template <int K, int D, int LANES>
@@ -622,9 +630,10 @@ __global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
     const bool valid = r < a.R;
     float lq_f = 0.f, lp_f = 0.f, lq_b = 0.f, lp_b = 0.f, ll_f = 0.f, ll_b = 0.f;
     if (valid) {
+        const long long ro = a.old_anc != nullptr ? (long long)__ldg(a.old_anc + r) * a.B + (r % a.B) : r;
         for (int e = j; e < KD; e += LANES) {
             const int k = e / D, d = e % D;
-            const float tbk = __ldg(a.tau_b + r * KD + e), mbk = __ldg(a.mu_b + r * KD + e);
+            const float tbk = __ldg(a.tau_b + ro * KD + e), mbk = __ldg(a.mu_b + ro * KD + e);
             const float a0 = s_pr[e][0], b0 = s_pr[e][1], m0 = s_pr[e][2], n0 = s_pr[e][3], gp = s_pr[e][4], Ln0 = s_pr[e][5];
             const float qa = __ldg(a.pa + r * KD + e), qb = __ldg(a.pb + r * KD + e);
             const float qm = __ldg(a.pm + r * KD + e), qn = __ldg(a.pn + r * KD + e);
@@ -661,7 +670,7 @@ __global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
             }
             const float* sp = a.stats + r * (K * ST) + k * ST;
             const float cnt = __ldg(sp), S1 = __ldg(sp + 1 + d), S2 = __ldg(sp + 1 + D + d);
-            const float cen = __ldg(a.center + r * KD + e);
+            const float cen = __ldg(a.center + ro * KD + e);
             // SFU logs (abs error ~1e-7 |log|) and the Stirling lgamma: each enters the sums with a factor <= alpha, i.e.
             // ~1e-7 relative to the magnitudes summed.  Same shared-log forms as k_gmm_weights (see the note there).
             const float Ltf = log_fast(tf), Ltb = log_fast(tbk);
@@ -947,7 +956,7 @@ static int logw_eta_stats(const float* stats, const float* center, const apgs_gm
                           const apgs_gmm_prior_t* prior, const float* tau, const float* mu, const float* g_std,
                           const float* e_std, float* tau_out, float* mu_out, const float* tau_old, const float* mu_old,
                           int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream,
-                          const uint64_t* seed = nullptr);
+                          const uint64_t* seed = nullptr, const int32_t* old_anc = nullptr);
 
 extern "C" int apgs_gmm_logw_eta_stats_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
                                            const apgs_gmm_prior_t* prior, const float* tau, const float* mu,
@@ -977,11 +986,22 @@ extern "C" int apgs_gmm_draw_logw_eta_stats_rng_f32(const float* stats, const fl
                           out, stream, philox_seed);
 }
 
+extern "C" int apgs_gmm_draw_logw_eta_stats_rng_via_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                                        const apgs_gmm_prior_t* prior, const uint64_t* philox_seed, float* tau,
+                                                        float* mu, const float* tau_old, const float* mu_old,
+                                                        const int32_t* old_ancestors, int64_t S, int64_t B, int64_t K,
+                                                        int64_t D, const apgs_gmm_out_t* out, void* stream) {
+    if (!philox_seed || !tau || !mu) return fail(APGS_E_BADARG, "gmm_draw_logw_eta_stats_rng_via: NULL input");
+    if (B >= (1ll << 31)) return fail(APGS_E_SHAPE, "gmm_draw_logw_eta_stats_rng_via: B too large");
+    return logw_eta_stats(stats, center, post, prior, nullptr, nullptr, nullptr, nullptr, tau, mu, tau_old, mu_old, S, B, K, D,
+                          out, stream, philox_seed, old_ancestors);
+}
+
 static int logw_eta_stats(const float* stats, const float* center, const apgs_gmm_post_t* post,
                           const apgs_gmm_prior_t* prior, const float* tau, const float* mu, const float* g_std,
                           const float* e_std, float* tau_out, float* mu_out, const float* tau_old, const float* mu_old,
                           int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream,
-                          const uint64_t* seed) {
+                          const uint64_t* seed, const int32_t* old_anc) {
     if (S <= 0 || B <= 0 || S * B >= (1ll << 36))
         return fail(APGS_E_SHAPE, "gmm_logw_eta_stats: bad sizes S=%lld B=%lld", (long long)S, (long long)B);
     if (!stats || !center || !post || !prior || !out || !tau_old || !mu_old)
@@ -995,6 +1015,7 @@ static int logw_eta_stats(const float* stats, const float* center, const apgs_gm
     a.tau_f = tau; a.mu_f = mu; a.tau_b = tau_old; a.mu_b = mu_old;
     a.g_std = g_std; a.e_std = e_std; a.tau_out = tau_out; a.mu_out = mu_out;
     a.seed = reinterpret_cast<const unsigned long long*>(seed);
+    a.old_anc = old_anc; a.B = (int)B;
     a.R = (long long)S * B;
     a.log_w = out->log_w; a.log_q_f = out->log_q_f; a.dens = out->density; a.log_w_f = out->log_w_f;
     a.log_w_b = out->log_w_b;
@@ -1028,5 +1049,35 @@ extern "C" int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uin
     cudaStream_t st = (cudaStream_t)stream;
     APGS_KD_DISPATCH(K, D, launch_nss);
     return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats_labels: (K=%lld, D=%lld) not instantiated", (long long)K,
+                (long long)D);
+}
+
+extern "C" int apgs_gmm_eta_posterior_stats_labels_via_f32(const float* x, const uint8_t* z_labels, const float* Wg,
+                                                       const float* bg, const float* Wo, const float* bo, int64_t S,
+                                                       int64_t B, int64_t N, int64_t K, int64_t D,
+                                                       const float* prior_alpha, const float* prior_beta,
+                                                       const float* prior_mu, const float* prior_nu, float* post_alpha,
+                                                       float* post_beta, float* post_mu, float* post_nu,
+                                                       const float* center, float* stats, int64_t label_stride,
+                                                       const int32_t* z_ancestors, const int32_t* center_ancestors,
+                                                       void* stream) {
+    if (int e = check_gmm_dims(S, B, N, K, D, "gmm_eta_posterior_stats_labels_via")) return e;
+    if (label_stride < N) return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels_via: label_stride %lld < N", (long long)label_stride);
+    if (!x || !z_labels || !Wg || !bg || !Wo || !bo || !prior_alpha || !prior_beta || !prior_mu || !prior_nu ||
+        !post_alpha || !post_beta || !post_mu || !post_nu)
+        return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels_via: NULL pointer");
+    if ((center == nullptr) != (stats == nullptr))
+        return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels_via: center and stats go together");
+    if (K * D > kLanes) return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats_labels_via: K*D <= %d supported", kLanes);
+    NssArgs a = {};
+    a.x = x; a.zl = z_labels; a.LN = label_stride; a.Wg = Wg; a.bg = bg; a.Wo = Wo; a.bo = bo;
+    a.ra = prior_alpha; a.rb = prior_beta; a.rm = prior_mu; a.rn = prior_nu;
+    a.oa = post_alpha; a.ob = post_beta; a.om = post_mu; a.on = post_nu;
+    a.center = center; a.stats = stats;
+    a.z_anc = z_ancestors; a.c_anc = center_ancestors;
+    a.R = (long long)S * B; a.N = (int)N; a.B = (int)B;
+    cudaStream_t st = (cudaStream_t)stream;
+    APGS_KD_DISPATCH(K, D, launch_nss);
+    return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats_labels_via: (K=%lld, D=%lld) not instantiated", (long long)K,
                 (long long)D);
 }

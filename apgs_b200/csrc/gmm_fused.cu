@@ -56,6 +56,7 @@ struct ZFusedArgs {
     // ancestors (S,B) of a resampling step whose gather was deferred, or null: the particle's INPUT latents (tau, mu, old
     // assignments) are read from row (src_anc[s,b], b); outputs and random numbers belong to row (s,b)
     const int* src_anc;
+    const int* src_anc_z;          // the same for the old assignments when they went through other resampling steps (null: src_anc)
 };
 
 // ---- per-instance tables ------------------------------------------------------------------------------------------
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
     const bool valid = s0 + p < a.S;
     const long long r = (long long)(s0 + p) * a.B + b;
-    const long long rs = (valid && a.src_anc != nullptr) ? (long long)__ldg(a.src_anc + r) * a.B + b : r;   // row of the inputs
+    const long long rs = (valid && a.src_anc != nullptr) ? (long long)__ldg(a.src_anc + r) * a.B + b : r;   // row of tau, mu
+    const long long rz = (valid && a.src_anc_z != nullptr) ? (long long)__ldg(a.src_anc_z + r) * a.B + b : rs;  // row of z_old
     const int rows = min(P, a.S - s0);
     const unsigned int rb = (unsigned int)NK * 4u;
     // a row goes through the bulk-copy engine when its size keeps every row 16-byte aligned
@@ -394,12 +396,12 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
         if (valid) {
             if (bulk_in) {
                 if (j == 0) {
-                    if (old_tile) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + rs * NK, rb, &bar);
+                    if (old_tile) bulk_g2s(s_zo + (size_t)p * NK, a.z_old + rz * NK, rb, &bar);
                     if (forced) bulk_g2s(s_zn + (size_t)p * NK, a.z_forced + r * NK, rb, &bar);
                 }
             } else {
                 for (int i = j; i < NK; i += LANES) {
-                    if (old_tile) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + rs * NK + i);
+                    if (old_tile) s_zo[(size_t)p * NK + i] = __ldg(a.z_old + rz * NK + i);
                     if (forced) s_zn[(size_t)p * NK + i] = __ldg(a.z_forced + r * NK + i);
                 }
             }
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
         } else {
             for (int i = j; i < N; i += LANES) s_u[(size_t)p * NU + i] = __ldg(ur + i);
         }
-        const unsigned char* lr = a.zl_old + rs * a.LN;
+        const unsigned char* lr = a.zl_old + rz * a.LN;
         if ((a.LN & 15) == 0 && a.LN >= LS && aligned(a.zl_old, 16)) {
             for (int c = j; c < LS / 16; c += LANES)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_lb + (size_t)p * LS + c * 16)), "l"(lr + c * 16) : "memory");
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(P* LANES, (LEAN ? 4 : 3) * 32 / P) k_gmm_z_fus
     if (valid) {
         const float* zo = s_zo + (size_t)p * NK;
         float* zn = s_zn + (size_t)p * NK;
-        const unsigned char* zlo = a.zl_old + rs * a.LN;         // label rows of this particle (label mode)
+        const unsigned char* zlo = a.zl_old + rz * a.LN;         // label rows of this particle (label mode)
         unsigned char* zln = a.zl_new + r * a.LN;
         const float* tab = s_tab + (size_t)p * (K * TRS);
         const float b2l = b2 * 1.4426950408889634f;              // logits are carried in log2 units: l' = log2(e) logit
@@ -881,7 +883,7 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
                         int64_t label_stride, float* q_probs, const apgs_gmm_out_t* out, void* stream,
                         const float* const* heads = nullptr, const apgs_gmm_post_out_t* post_out = nullptr,
                         float* stats_out = nullptr, const uint64_t* philox_seed = nullptr, const float* tables = nullptr,
-                        const int32_t* src_ancestors = nullptr) {
+                        const int32_t* src_ancestors = nullptr, const int32_t* src_ancestors_z = nullptr) {
     if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024)
         return fail(APGS_E_SHAPE, "gmm_z_step_fused: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S, (long long)B,
                     (long long)N, (long long)H);
@@ -896,6 +898,7 @@ static int z_step_fused(const float* x, const float* tau, const float* mu, const
     a.seed = reinterpret_cast<const unsigned long long*>(philox_seed);
     a.tables = tables;
     a.src_anc = src_ancestors;
+    a.src_anc_z = src_ancestors_z;
     a.S = (int)S; a.B = (int)B; a.N = (int)N; a.H = (int)H;
     a.z_new = z_new; a.zl_new = z_new_lab; a.LN = label_stride; a.q_probs = q_probs;
     if (out) {
@@ -1036,7 +1039,7 @@ extern "C" int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, c
                                              int64_t label_stride, float* q_probs, const float* Wg, const float* bg,
                                              const float* Wo, const float* bo, const apgs_gmm_post_out_t* post_out,
                                              float* stats_out, const apgs_gmm_out_t* out, const float* tables,
-                                             const int32_t* src_ancestors, void* stream) {
+                                             const int32_t* src_ancestors, const int32_t* src_ancestors_z, void* stream) {
     if (!philox_seed) return fail(APGS_E_BADARG, "gmm_z_step_fused_tab: philox_seed is NULL");
     if (z_new_labels && label_stride < N) return fail(APGS_E_BADARG, "gmm_z_step_fused_tab: label_stride %lld < N", (long long)label_stride);
     if (post_out || stats_out) {
@@ -1048,7 +1051,7 @@ extern "C" int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, c
     const float* heads[4] = {Wg, bg, Wo, bo};
     return z_step_fused(x, tau, mu, W1, b1, W2, b2, H, prior, z_old_onehot, z_old_labels, nullptr, nullptr, S, B, N, K, D,
                         z_new_onehot, z_new_labels, z_new_labels ? label_stride : N, q_probs, out, stream,
-                        post_out ? heads : nullptr, post_out, stats_out, philox_seed, tables, src_ancestors);
+                        post_out ? heads : nullptr, post_out, stats_out, philox_seed, tables, src_ancestors, src_ancestors_z);
 }
 
 extern "C" int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, const float* mu, const float* W1,
@@ -1062,5 +1065,5 @@ extern "C" int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, c
     if (!philox_seed) return fail(APGS_E_BADARG, "gmm_z_step_fused_rng: philox_seed is NULL");
     return apgs_gmm_z_step_fused_tab_f32(x, tau, mu, W1, b1, W2, b2, H, prior, z_old_onehot, z_old_labels, philox_seed, S, B, N, K,
                                          D, z_new_onehot, z_new_labels, label_stride, q_probs, Wg, bg, Wo, bo, post_out,
-                                         stats_out, out, nullptr, nullptr, stream);
+                                         stats_out, out, nullptr, nullptr, nullptr, stream);
 }

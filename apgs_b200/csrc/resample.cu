@@ -687,6 +687,23 @@ extern "C" int apgs_gather_ancestors(const int32_t* anc32, const int64_t* anc64,
                          (cudaStream_t)stream);
 }
 
+__global__ void __launch_bounds__(256) k_compose_ancestors(const int* __restrict__ prev, const int* __restrict__ next,
+                                                           long long R, int B, int* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (r < R) out[r] = __ldg(prev + (long long)__ldg(next + r) * B + (r % B));
+}
+
+extern "C" int apgs_compose_ancestors(const int32_t* prev, const int32_t* next, int64_t S, int64_t B, int32_t* out,
+                                      void* stream) {
+    if (int e = check_sb(S, B, "compose_ancestors")) return e;
+    if (!prev || !next || !out) return fail(APGS_E_BADARG, "compose_ancestors: NULL pointer");
+    if (B >= (1ll << 31) || S * B >= (1ll << 38)) return fail(APGS_E_SHAPE, "compose_ancestors: S=%lld B=%lld too large", (long long)S, (long long)B);
+    const long long R = S * B;
+    k_compose_ancestors<<<(unsigned int)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prev, next, R, (int)B, out);
+    APGS_LAUNCH_OK("k_compose_ancestors launch");
+    return 0;
+}
+
 extern "C" int apgs_gather_ancestors_via(const int32_t* anc32, int64_t S, int64_t B, const apgs_latent_t* latents,
                                          const int32_t* const* first, int n_latents, void* stream) {
     if (int e = check_sb(S, B, "gather_ancestors_via")) return e;

@@ -174,9 +174,10 @@ def draw_logw_eta_stats(stats, center, post, prior, gamma_std, normal_std, tau_o
     return w, tau, mu
 
 
-def draw_logw_eta_stats_rng(stats, center, post, prior, seed, tau_old, mu_old, parts=False):
+def draw_logw_eta_stats_rng(stats, center, post, prior, seed, tau_old, mu_old, parts=False, old_ancestors=None):
     """draw_logw_eta_stats with the Gamma / Normal variates made inside the kernel (Philox + Marsaglia-Tsang + Box-Muller):
-    `seed` is an int64 CUDA tensor of two words drawn from torch's generator (philox_seed()).  Returns (Weights, tau, mu)."""
+    `seed` is an int64 CUDA tensor of two words drawn from torch's generator (philox_seed()).  Returns (Weights, tau, mu).
+    old_ancestors (S,B) int32: center / tau_old / mu_old of particle (s,b) are read from row (old_ancestors[s,b], b)."""
     lib = _lib.load()
     stats, center = _req(stats, "stats", ndim=4), _req(center, "center", ndim=4)
     tau_old, mu_old = _req(tau_old, "tau_old", ndim=4), _req(mu_old, "mu_old", ndim=4)
@@ -189,6 +190,15 @@ def draw_logw_eta_stats_rng(stats, center, post, prior, seed, tau_old, mu_old, p
     tau, mu = torch.empty_like(tau_old), torch.empty_like(tau_old)
     w, o = _outs(S, B, 1, tau_old.device, parts, False)
     with torch.cuda.device(tau_old.device), _call("gmm_logw_eta_stats", 1, 4 * S * B * (K * (1 + 2 * D) + 9 * K * D + 3)):
+        if old_ancestors is not None:
+            old_ancestors = _req(old_ancestors, "old_ancestors", dtype=torch.int32, ndim=2)
+            if tuple(old_ancestors.shape) != (S, B):
+                raise ValueError("old_ancestors must be (S, B) int32")
+            check(lib.apgs_gmm_draw_logw_eta_stats_rng_via_f32(ptr(stats), ptr(center), C.byref(ps), C.byref(rs), ptr(seed),
+                                                               ptr(tau), ptr(mu), ptr(tau_old), ptr(mu_old), ptr(old_ancestors),
+                                                               S, B, K, D, C.byref(o), _stream()),
+                  "apgs_gmm_draw_logw_eta_stats_rng_via_f32")
+            return w, tau, mu
         check(lib.apgs_gmm_draw_logw_eta_stats_rng_f32(ptr(stats), ptr(center), C.byref(ps), C.byref(rs), ptr(seed), ptr(tau),
                                                        ptr(mu), ptr(tau_old), ptr(mu_old), S, B, K, D, C.byref(o), _stream()),
               "apgs_gmm_draw_logw_eta_stats_rng_f32")
@@ -281,7 +291,7 @@ def z_tables(x, mlp, prior):
 
 def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=None, want_q=False,
                  parts=False, local=False, also_labels=0, want_onehot=True, eta_heads=None, seed=None, tables=None,
-                 src_ancestors=None):
+                 src_ancestors=None, src_ancestors_z=None):
     """N1+G3: Enc_apg_z MLP + softmax + categorical draw + z-step weights in one kernel.
     mlp = (W1 (H,3D), b1 (H), W2 (1,H) or (H), b2 (1)).  Returns (z_new, q_probs or None, Weights).
     z_old as uint8 labels (S,B,>=N) selects label mode (z_new comes back as labels of the same row stride).
@@ -297,14 +307,14 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
     every CTA; same results bit for bit.
     src_ancestors (S,B) int32 (with seed): tau, mu and z_old of particle (s,b) are read from row (src_ancestors[s,b], b) --
     the ancestors of a resampling step whose gather is deferred (ops.gather_ancestors(..., first=...)); same results as
-    gathering first."""
+    gathering first.  src_ancestors_z: the map for z_old alone when it differs (default: src_ancestors)."""
     lib = _lib.load()
     if seed is not None:
         if uniforms is not None or z_forced is not None:
             raise ValueError("seed replaces uniforms; it has no meaning with z_forced")
         return _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot,
-                                 eta_heads, seed, tables, src_ancestors)
-    if tables is not None or src_ancestors is not None:
+                                 eta_heads, seed, tables, src_ancestors, src_ancestors_z)
+    if tables is not None or src_ancestors is not None or src_ancestors_z is not None:
         raise ValueError("tables / src_ancestors ride on the seed entry (apgs_gmm_z_step_fused_tab_f32)")
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -389,7 +399,7 @@ def z_step_fused(x, tau, mu, mlp, prior, z_old=None, uniforms=None, z_forced=Non
 
 
 def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, also_labels, want_onehot, eta_heads, seed,
-                      tables=None, src_ancestors=None):
+                      tables=None, src_ancestors=None, src_ancestors_z=None):
     """z_step_fused with in-kernel uniforms: the same modes and return values, one entry point."""
     x = _x3(x)
     tau, mu = _req(tau, "tau", ndim=4), _req(mu, "mu", ndim=4)
@@ -409,6 +419,10 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
         src_ancestors = _req(src_ancestors, "src_ancestors", dtype=torch.int32, ndim=2)
         if tuple(src_ancestors.shape) != (S, B):
             raise ValueError("src_ancestors must be (S, B) int32")
+    if src_ancestors_z is not None:
+        src_ancestors_z = _req(src_ancestors_z, "src_ancestors_z", dtype=torch.int32, ndim=2)
+        if tuple(src_ancestors_z.shape) != (S, B):
+            raise ValueError("src_ancestors_z must be (S, B) int32")
     rs, rk = _prior_struct(prior)
     z_hot_old = z_lab_old = z_hot = z_lab = post = stats = po = None
     heads = [None] * 4
@@ -452,7 +466,8 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
                                                 C.byref(rs), ptr(z_hot_old), ptr(z_lab_old), ptr(seed), S, B, N, K, D,
                                                 ptr(z_hot), ptr(z_lab), LN, ptr(q), ptr(heads[0]), ptr(heads[1]),
                                                 ptr(heads[2]), ptr(heads[3]), C.byref(po) if po is not None else None,
-                                                ptr(stats), C.byref(o), ptr(tables), ptr(src_ancestors), _stream()),
+                                                ptr(stats), C.byref(o), ptr(tables), ptr(src_ancestors), ptr(src_ancestors_z),
+                                                _stream()),
               "apgs_gmm_z_step_fused_tab_f32")
     if also_labels:
         return (z_hot, z_lab), q, w
@@ -462,15 +477,19 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
     return z_new, q, w
 
 
-def eta_posterior_fused(x, z, heads, prior, center=None):
+def eta_posterior_fused(x, z, heads, prior, center=None, z_ancestors=None, center_ancestors=None):
     """N1b+G1: Linear heads of Enc_apg_eta (z given) / Enc_rws_eta (z None) + softmax + NSS posterior.
     heads = (Wg, bg, Wo, bo).  Returns alpha, beta, mu, nu of shape (S,B,K,D) ((1,B,K,D) when z is None).
     With `center` (S,B,K,D; the old mu) the same pass also returns the centred one-hot statistics of z,
-    (S,B,K,1+2D), as a fifth tensor -- the input of logw_eta_stats."""
+    (S,B,K,1+2D), as a fifth tensor -- the input of logw_eta_stats.
+    z_ancestors / center_ancestors (S,B) int32 (label mode): the label row / the centre of particle (s,b) are read from
+    row (map[s,b], b) -- ancestors of resampling steps whose gathers were deferred."""
     lib = _lib.load()
     x = _x3(x)
     B, N, D = x.shape
     Wg, bg, Wo, bo = [_req(v, "head weight") for v in heads]
+    if (z_ancestors is not None or center_ancestors is not None) and not (z is not None and z.dtype == torch.uint8):
+        raise ValueError("ancestor maps are taken in label mode only")
     K = Wg.shape[0]
     if z is not None and z.dtype == torch.uint8:
         # label mode: z (S,B,N) uint8
@@ -489,9 +508,18 @@ def eta_posterior_fused(x, z, heads, prior, center=None):
                 raise ValueError("center has shape %s, expected %s" % (tuple(center.shape), (S, B, K, D)))
             stats = torch.empty(S, B, K, 1 + 2 * D, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device), _call("gmm_eta_posterior_stats", 1, S * B * (N + 4 * (6 * K * D + K * (1 + 2 * D)))):
-            check(lib.apgs_gmm_eta_posterior_stats_labels_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
-                                                              *[ptr(v) for v in pr], *[ptr(v) for v in outs], ptr(center),
-                                                              ptr(stats), LN, _stream()), "apgs_gmm_eta_posterior_stats_labels_f32")
+            maps = [None if m is None else _req(m, "ancestor map", dtype=torch.int32, ndim=2) for m in (z_ancestors, center_ancestors)]
+            if any(m is not None and tuple(m.shape) != (S, B) for m in maps):
+                raise ValueError("ancestor maps must be (S, B) int32")
+            if maps[0] is not None or maps[1] is not None:
+                check(lib.apgs_gmm_eta_posterior_stats_labels_via_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N,
+                                                                      K, D, *[ptr(v) for v in pr], *[ptr(v) for v in outs],
+                                                                      ptr(center), ptr(stats), LN, ptr(maps[0]), ptr(maps[1]),
+                                                                      _stream()), "apgs_gmm_eta_posterior_stats_labels_via_f32")
+            else:
+                check(lib.apgs_gmm_eta_posterior_stats_labels_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
+                                                                  *[ptr(v) for v in pr], *[ptr(v) for v in outs], ptr(center),
+                                                                  ptr(stats), LN, _stream()), "apgs_gmm_eta_posterior_stats_labels_f32")
         return tuple(outs) + ((stats,) if stats is not None else ())
     if z is not None:
         z = _req(z, "z", ndim=4)

@@ -103,13 +103,41 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
                                                       label_stride=(N + 15) // 16 * 16, defer=True, tables=ztab)
     else:
         log_w, tau, mu, z, trace, _, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags, defer=True)
-    tau, mu, z = resample_and_book(tau, mu, z, log_w, log_q)
     compact = z.dtype == torch.uint8
+    # gatherless sweeps (evaluation flags, decomposed block, label mode, in-kernel draws): see the loop below
+    gatherless_now = bool(gatherless and compact and block == 'decomposed' and ztab is not None and not fuse_eta_stats
+                          and rng_in_kernels and _eta_fused(enc_apg_eta) and num_sweeps > 1)
+    z_map = eta_map = None
+    if gatherless_now:
+        if need_stats:
+            z_map, stats = resampler.ancestors32(log_w, want_stats=True, want_w=bool(result_flags['loss_required']))
+            _book_weights(trace, result_flags, log_q, stats)
+        else:
+            z_map = resampler.ancestors32(log_w)
+        eta_map = z_map                                  # the one-shot made (tau, mu, z) in the same order
+    else:
+        tau, mu, z = resample_and_book(tau, mu, z, log_w, log_q)
     pre = None         # (posterior parameters, centred statistics) of the current z, emitted by the previous z step
     for m in range(num_sweeps - 1):
         if block == 'decomposed':
             log_w_eta, tau, mu, trace, log_q_f = _update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags,
-                                                             defer=True, pre=pre)
+                                                             defer=True, pre=pre, z_map=z_map, eta_map=eta_map)
+            if gatherless_now:
+                # Gatherless sweep: no latent is moved.  Every block update reads its inputs through ancestor maps --
+                # (tau, mu) made by the eta step through A (this step's resampling), the labels made by the previous z step
+                # through its resampling C composed with A -- and writes its outputs in place order; a latent is at most two
+                # resampling steps old when it is read (ops.compose_ancestors).
+                if need_stats:
+                    A, stats = resampler.ancestors32(log_w_eta, want_stats=True, want_w=bool(result_flags['loss_required']))
+                    _book_weights(trace, result_flags, log_q_f, stats)
+                else:
+                    A = resampler.ancestors32(log_w_eta)
+                zA = ops.compose_ancestors(z_map, A) if z_map is not None else A
+                log_w_z, z, trace, _ = _update_z(enc_apg_z, generative, x, tau, mu, z, trace, result_flags, tables=ztab,
+                                                 src_ancestors=A, src_ancestors_z=zA)
+                z_map = resampler.ancestors32(log_w_z)                  # C: the new labels sit in the z step's order
+                eta_map = ops.compose_ancestors(A, z_map)               # (tau, mu) sit in the eta step's order: A then C
+                continue
             if compact and defer_gather and ztab is not None and not fuse_eta_stats:
                 # Deferred gather: the z step only READS (tau, mu, z) of the resampled particles, so it takes them through
                 # this resampling step's ancestors, and the gather after the z step composes the two index maps for the
@@ -210,6 +238,7 @@ lean_oneshot = True
 # statistics are ~1000 instructions per thread wherever they run, so the z step grows by 0.25 ms against 0.32 ms for the
 # standalone kernel, and the 156 extra bytes per particle cost the gather 0.07 ms -- no net gain, hence off by default.
 fuse_eta_stats = False
+gatherless = True              # evaluation sweeps: no gather at all -- every step reads through (composed) ancestor maps
 defer_gather = True            # evaluation sweeps: the z step reads through the eta step's ancestors (one gather per sweep)
 z_tables_per_objective = True  # evaluation sweeps: per-instance tables of the z step built once per apg_objective call
 
@@ -350,10 +379,16 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
     return _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags)[:4]
 
 
-def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False, pre=None):
+def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False, pre=None, z_map=None,
+                eta_map=None):
+    """z_map / eta_map (S,B) int32 (gatherless sweeps): z and (tau_old, mu_old) are still in the order of the steps that made
+    them; particle (s,b) reads them from rows (z_map[s,b], b) / (eta_map[s,b], b)."""
     if _eta_fused(enc_apg_eta):
         if pre is not None:
             post, stats = pre            # emitted by the z step that drew these labels, centred at its mu == mu_old
+        elif z_map is not None or eta_map is not None:
+            *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old, z_ancestors=z_map, center_ancestors=eta_map)
+            post = tuple(post)
         else:
             # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of
             *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old)
@@ -364,7 +399,7 @@ def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_fl
             # the variates themselves made in the kernel (Philox keyed by two words from torch's generator): no
             # _standard_gamma / randn launches, no variate tensors -- distribution-equal to the torch draws below
             w, tau, mu = kernels.draw_logw_eta_stats_rng(stats, mu_old, post, generative, kernels.philox_seed(mu_old.device),
-                                                         tau_old, mu_old)
+                                                         tau_old, mu_old, old_ancestors=eta_map)
         else:
             g_std = torch._standard_gamma(post[0])
             e_std = torch.randn_like(post[2])
@@ -391,7 +426,8 @@ def apg_update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags):
     return _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags)[:3]
 
 
-def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None, tables=None, src_ancestors=None):
+def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta_heads=None, tables=None, src_ancestors=None,
+              src_ancestors_z=None):
     """apg_update_z; with eta_heads (label mode, evaluation flags) the fused kernel also emits the next eta step's
     (posterior parameters, statistics) as the 4th value (else None)."""
     need_local = bool(result_flags['loss_required'])
@@ -419,7 +455,7 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
         z, q_probs, w = kernels.z_step_fused(x, tau, mu, enc_apg_z.mlp(), generative, z_old=z_old,
                                              want_q=bool(result_flags['mode_required']), local=need_local,
                                              seed=_zseed(tau.device), tables=tables if rng_in_kernels else None,
-                                             src_ancestors=src_ancestors)
+                                             src_ancestors=src_ancestors, src_ancestors_z=src_ancestors_z)
     else:
         q_probs = enc_apg_z.probs(x, tau, mu)
         z = cat(q_probs, validate_args=False).sample()

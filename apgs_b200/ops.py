@@ -232,6 +232,21 @@ def gather_ancestors(latents, anc, first=None):
     return outs
 
 
+def compose_ancestors(prev, nxt):
+    """out[s,b] = prev[nxt[s,b], b] (int32): the ancestor map of two consecutive resampling steps for a latent that was not
+    gathered in between (apgs_compose_ancestors)."""
+    lib = _lib.load()
+    prev = _req(prev, "prev", dtype=torch.int32, ndim=2)
+    nxt = _req(nxt, "next", dtype=torch.int32, ndim=2)
+    if prev.shape != nxt.shape:
+        raise ValueError("ancestor maps must have the same (S, B) shape")
+    S, B = nxt.shape
+    out = torch.empty_like(nxt)
+    with torch.cuda.device(nxt.device), _call("compose_ancestors", 1, S * B * 12):
+        check(lib.apgs_compose_ancestors(ptr(prev), ptr(nxt), S, B, ptr(out), _stream()), "apgs_compose_ancestors")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ R5
 def resample(latents, log_w=None, w_norm=None, strategy="systematic", uniforms=None,
              cdf_mode=_lib.CDF_AUTO, want_index=False, want_stats=False, want_w=True, uniform_layout=None):

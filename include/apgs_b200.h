@@ -121,6 +121,13 @@ APGS_API int apgs_gather_ancestors(const int32_t* anc32, const int64_t* anc64, i
 APGS_API int apgs_gather_ancestors_via(const int32_t* anc32, int64_t S, int64_t B, const apgs_latent_t* latents,
                               const int32_t* const* first, int n_latents, void* stream);
 
+/* Composition of two ancestor maps, out[s, b] = prev[next[s, b], b]: what two consecutive resampling steps do to a latent
+ *   that was never gathered in between.  With it a whole sweep runs WITHOUT gathers: every block update reads its inputs
+ *   through (composed) ancestor maps -- apgs_gmm_z_step_fused_tab_f32 (src_ancestors, src_ancestors_z),
+ *   apgs_gmm_eta_posterior_stats_labels_via_f32, apgs_gmm_draw_logw_eta_stats_rng_via_f32 -- and writes its outputs in place
+ *   order; a latent is at most two resampling steps old when it is read (apgs/gmm/objectives.py:37-45).             */
+APGS_API int apgs_compose_ancestors(const int32_t* prev, const int32_t* next, int64_t S, int64_t B, int32_t* out, void* stream);
+
 /* R5  fused resample = R2/R3 + R4.  replaces resample_variables,
  *     apgs/gmm/objectives.py:229-234, apgs/dmm/objectives.py:190-195, apgs/bmnist/objectives.py:5-9.
  *   workspace: apgs_resample_workspace_bytes(S,B) (holds the int32 ancestors + CDF scratch).  */
@@ -330,7 +337,8 @@ APGS_API int apgs_gmm_z_step_fused_rng_f32(const float* x, const float* tau, con
  *   rebuilding it.  tables = NULL: identical to apgs_gmm_z_step_fused_rng_f32.  Results are bit-identical either way.
  *   src_ancestors (S,B) int32 or NULL: the INPUT latents (tau, mu, z_old) of particle (s,b) are read from row
  *   (src_ancestors[s,b], b) -- the ancestors of a resampling step whose gather is deferred (apgs_gather_ancestors_via);
- *   outputs and the random stream are those of particle (s,b).  Bit-identical to gathering first.
+ *   outputs and the random stream are those of particle (s,b).  Bit-identical to gathering first.  src_ancestors_z: the map
+ *   for z_old alone when the assignments went through other resampling steps than (tau, mu) (NULL: src_ancestors).
  *   The tables depend on (x, W1, b1, W2, b2, prior->pi): rebuild them when any of these changes.                       */
 APGS_API size_t apgs_gmm_z_tables_bytes(int64_t B, int64_t N, int64_t H, int64_t K, int64_t D);
 APGS_API int apgs_gmm_z_tables_f32(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -343,11 +351,28 @@ APGS_API int apgs_gmm_z_step_fused_tab_f32(const float* x, const float* tau, con
                               float* z_new_onehot, uint8_t* z_new_labels, int64_t label_stride, float* q_probs,
                               const float* Wg, const float* bg, const float* Wo, const float* bo,
                               const apgs_gmm_post_out_t* post_out, float* stats_out,
-                              const apgs_gmm_out_t* out, const float* tables, const int32_t* src_ancestors, void* stream);
+                              const apgs_gmm_out_t* out, const float* tables, const int32_t* src_ancestors,
+                              const int32_t* src_ancestors_z, void* stream);
 /* Measurement only: the main loop of the fused z step alone (K = 3, H = 32; `ctas` CTAs of 32 particles x 8 lanes, `passes`
  *   passes of eight quads of hidden units each, synthetic tables) -- the ceiling of the step's MLP part on this GPU, timed
  *   by bench.py next to the step itself (roofline.mlp_loop_alone).  out: ctas * 256 floats (a checksum per thread).      */
 APGS_API int apgs_gmm_z_loop_probe_f32(int64_t ctas, int64_t passes, float* out, void* stream);
+/* The two eta-step entries with their INPUT latents read through ancestor maps (S,B) int32 (NULL = in place), see
+ *   apgs_compose_ancestors: labels from row (z_ancestors[s,b], b), centre from row (center_ancestors[s,b], b);
+ *   center / tau_old / mu_old from row (old_ancestors[s,b], b).  Outputs, statistics, posterior parameters and the random
+ *   stream belong to particle (s,b).  Bit-identical to gathering first.                                                 */
+APGS_API int apgs_gmm_eta_posterior_stats_labels_via_f32(const float* x, const uint8_t* z_labels,
+                                     const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                     int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                     const float* prior_alpha, const float* prior_beta,
+                                     const float* prior_mu, const float* prior_nu,
+                                     float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
+                                     const float* center, float* stats, int64_t label_stride,
+                                     const int32_t* z_ancestors, const int32_t* center_ancestors, void* stream);
+APGS_API int apgs_gmm_draw_logw_eta_stats_rng_via_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
+                                     const apgs_gmm_prior_t* prior, const uint64_t* philox_seed, float* tau, float* mu,
+                                     const float* tau_old, const float* mu_old, const int32_t* old_ancestors,
+                                     int64_t S, int64_t B, int64_t K, int64_t D, const apgs_gmm_out_t* out, void* stream);
 APGS_API int apgs_gmm_eta_posterior_stats_labels_f32(const float* x, const uint8_t* z_labels,
                                      const float* Wg, const float* bg, const float* Wo, const float* bo,
                                      int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,

@@ -738,12 +738,70 @@ def test_objective_with_deferred_gather_is_bit_identical(strategy):
     x = og.simulate(24, 60, 3, 2).to(DEV)
     out = {}
     for on in (True, False):
-        objectives.defer_gather = on
+        objectives.defer_gather, objectives.gatherless = on, False
         try:
             torch.manual_seed(3)
             with torch.no_grad():
                 out[on] = objectives.apg_objective(models, x, BENCH_FLAGS, 4, "decomposed", Resampler(strategy, 200, True, DEV))
         finally:
-            objectives.defer_gather = True
+            objectives.defer_gather, objectives.gatherless = True, True
     for k in ("ess", "density", "log_z"):
         assert torch.equal(out[True][k], out[False][k]), k
+
+
+def test_eta_step_kernels_through_ancestor_maps_equal_gather_first():
+    """apgs_gmm_eta_posterior_stats_labels_via_f32 / apgs_gmm_draw_logw_eta_stats_rng_via_f32 / apgs_compose_ancestors: reading the
+    labels, the centre and the old (tau, mu) through ancestor maps gives the numbers of gathering first, bit for bit."""
+    from apgs_b200 import ops
+    from apgs_b200.gmm import kernels
+    from apgs_b200.resampler import Resampler
+    S, B, N, K, D = 200, 6, 60, 3, 2
+    P, gen = og.make_params(), _Gen()
+    x, tau, mu, lab, _ = _latents(S, B, seed=41)
+    xg, tg, mg, lg = x.to(DEV), tau.to(DEV), mu.to(DEV), _pad_labels(lab.to(DEV))
+    torch.manual_seed(9)
+    rs = Resampler("systematic", S, True, DEV)
+    zmap = rs.ancestors32(torch.randn(S, B, device=DEV) * 2)
+    emap = rs.ancestors32(torch.randn(S, B, device=DEV) * 2)
+    comp = ops.compose_ancestors(zmap, emap)
+    assert torch.equal(comp.long(), torch.gather(zmap.long(), 0, emap.long()))
+    heads = _heads(P)
+    (lg1,) = ops.gather_ancestors([lg], zmap)
+    tg1, mg1 = ops.gather_ancestors([tg, mg], emap)
+    a = kernels.eta_posterior_fused(xg, lg1, heads, gen, center=mg1)
+    b = kernels.eta_posterior_fused(xg, lg, heads, gen, center=mg, z_ancestors=zmap, center_ancestors=emap)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    seed = torch.tensor([5, 6], dtype=torch.int64, device=DEV)
+    wa, ta, ma = kernels.draw_logw_eta_stats_rng(a[4], mg1, a[:4], gen, seed, tg1, mg1)
+    wb, tb, mb = kernels.draw_logw_eta_stats_rng(b[4], mg, b[:4], gen, seed, tg, mg, old_ancestors=emap)
+    assert torch.equal(ta, tb) and torch.equal(ma, mb)
+    for name in ("log_w", "log_q_f", "density"):
+        assert torch.equal(getattr(wa, name), getattr(wb, name)), name
+    # z step with separate maps for (tau, mu) and z_old
+    zs = torch.tensor([11, 0], dtype=torch.int64, device=DEV)
+    z1, _, w1 = kernels.z_step_fused(xg, tg1, mg1, _mlp(P), gen, z_old=lg1, seed=zs)
+    z2, _, w2 = kernels.z_step_fused(xg, tg, mg, _mlp(P), gen, z_old=lg, seed=zs, src_ancestors=emap, src_ancestors_z=zmap)
+    assert torch.equal(z1[..., :N], z2[..., :N]) and torch.equal(w1.log_w, w2.log_w) and torch.equal(w1.density, w2.density)
+
+
+@pytest.mark.parametrize("strategy", ["systematic", "multinomial"])
+def test_gatherless_objective_is_bit_identical(strategy):
+    """apg_objective (bench flags): the gatherless sweep, the one-gather-per-sweep sweep and the gather-everything sweep give
+    the same trace bit for bit under one seed."""
+    from apgs_b200.gmm import objectives
+    from apgs_b200.resampler import Resampler
+    models = _models_from_params(og.make_params())
+    x = og.simulate(24, 60, 3, 2).to(DEV)
+    out = {}
+    for mode in ("gatherless", "deferred", "plain"):
+        objectives.gatherless, objectives.defer_gather = mode == "gatherless", mode != "plain"
+        try:
+            torch.manual_seed(3)
+            with torch.no_grad():
+                out[mode] = objectives.apg_objective(models, x, BENCH_FLAGS, 5, "decomposed", Resampler(strategy, 200, True, DEV))
+        finally:
+            objectives.gatherless, objectives.defer_gather = True, True
+    for k in ("ess", "density", "log_z"):
+        assert torch.equal(out["gatherless"][k], out["plain"][k]), k
+        assert torch.equal(out["deferred"][k], out["plain"][k]), k
