@@ -88,7 +88,11 @@ def workload_config(args):
             "S": args.particles, "B_per_gpu": args.batch, "num_sweeps": args.sweeps, "block": "decomposed",
             "resample_strategy": "systematic", "flags": "ess+density (budget_analysis)",
             "encoder": args.encoder, "parallelism": "instances sharded over ranks (dp%d), metric all-reduce only" % args.gpus,
-            "cache": "inputs larger than L2 (per-rank latents + per-step scratch ~1 GB >> 126 MB L2); no flush",
+            "cache": "inputs larger than L2 (per-rank latents + per-step scratch ~0.4 GB >> 126 MB L2); no flush",
+            "resampling": "19 ancestor draws per objective as in the reference; inside the sweeps the block updates read their "
+                          "inputs through the (composed) ancestor maps instead of gathered copies -- bit-identical traces "
+                          "(tests/test_gmm_lean_gpu.py); the gather kernel itself is measured by roofline.hbm.all_distinct_probe "
+                          "and configs.C5_microbench",
             "ref_batch": args.ref_batch}
 
 
@@ -372,7 +376,8 @@ def gmm_roofline(prof, S, B, peak, peak_src, clocks, distinct_frac, probe, dev):
             "achieved": ach, "peak": peak_fma, "unit": "T lane-cycles/s of the fp32 FMA pipe (inner loop: 3.5 per tanh term)",
             "frac": ach / peak_fma, "traffic": None,
             "traffic_note": "DRAM bytes are not measurable inside the run; see ncu_capture (the committed ncu --set full capture "
-                            "of this command: k_gmm_z_fused moves 456 MB per launch = 396 GB/s, FMA pipe cycles active 66 %)",
+                            "of this command: k_gmm_z_fused moves ~0.2 GB per launch, FMA pipe cycles active 68 %, issue active 68 % with packed "
+                            "FFMA2 / FMUL2 counted once)",
             "share_of_step_kernel_time": round(zf["calls"] * zf["ms_avg"] / tot, 3), "avg_launch_ms": zf["ms_avg"],
             "launches_timed": zf["calls"], "sm_mhz": clk, "alg_GBs": zf["gbs"], "frac_hbm": zf["gbs"] / peak,
             "peak_source": "SMs x 128 lanes x sampled SM clock; hbm: " + peak_src}
