@@ -79,9 +79,11 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     # the part of Enc_apg_z that depends only on (x, weights) is the same for every particle and every sweep of this call:
     # tabulated once per instance, fetched by the z-step CTAs with one bulk copy (kernels.z_tables)
     ztab = None
-    if (z_tables_per_objective and rng_in_kernels and not result_flags['loss_required'] and getattr(enc_apg_z, 'fused', False)
-            and hasattr(enc_apg_z, 'mlp') and enc_apg_z.can_fuse(False)):
-        ztab = kernels.z_tables(x, enc_apg_z.mlp(), generative)
+    if (z_tables_per_objective and rng_in_kernels and getattr(enc_apg_z, 'fused', False) and hasattr(enc_apg_z, 'mlp')
+            and enc_apg_z.can_fuse(False)):
+        with torch.no_grad():                    # weights are constant within one objective call (training mode included)
+            ztab = kernels.z_tables(x, enc_apg_z.mlp(), generative)
+    evaluating = not result_flags['loss_required']
 
     def resample_and_book(tau, mu, z, log_w, log_q_f):
         """resample_variables + the W1 bookkeeping of the step from the SAME launch: the ancestor kernel's softmax over S
@@ -105,7 +107,7 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
         log_w, tau, mu, z, trace, _, log_q = _oneshot(enc_rws_eta, enc_apg_z, generative, x, trace, result_flags, defer=True)
     compact = z.dtype == torch.uint8
     # gatherless sweeps (evaluation flags, decomposed block, label mode, in-kernel draws): see the loop below
-    gatherless_now = bool(gatherless and compact and block == 'decomposed' and ztab is not None and not fuse_eta_stats
+    gatherless_now = bool(gatherless and evaluating and compact and block == 'decomposed' and ztab is not None and not fuse_eta_stats
                           and rng_in_kernels and _eta_fused(enc_apg_eta) and num_sweeps > 1)
     z_map = eta_map = None
     if gatherless_now:
@@ -138,7 +140,7 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
                 z_map = resampler.ancestors32(log_w_z)                  # C: the new labels sit in the z step's order
                 eta_map = ops.compose_ancestors(A, z_map)               # (tau, mu) sit in the eta step's order: A then C
                 continue
-            if compact and defer_gather and ztab is not None and not fuse_eta_stats:
+            if compact and defer_gather and evaluating and ztab is not None and not fuse_eta_stats:
                 # Deferred gather: the z step only READS (tau, mu, z) of the resampled particles, so it takes them through
                 # this resampling step's ancestors, and the gather after the z step composes the two index maps for the
                 # latents that are still in the old order (tau, mu) -- one gather launch per sweep instead of two.
@@ -265,11 +267,11 @@ def _train_z(enc_apg_z):
             and enc_apg_z.can_fuse(False))
 
 
-def _sample_z_train(enc_z, generative, x, tau, mu, label_stride=0):
+def _sample_z_train(enc_z, generative, x, tau, mu, label_stride=0, tables=None):
     """sample-only fused z step with a graph: z (one-hot), q_probs, log q(z) summed over the points (S,B), labels or None"""
     from .train import FusedZStep
     z, q_probs, _, _, _, log_q_local, z_hot = FusedZStep.apply(*enc_z.mlp(), kernels._x3(x), tau, mu, None, generative,
-                                                               int(label_stride), _zseed(tau.device))
+                                                               int(label_stride), _zseed(tau.device), tables)
     if label_stride:
         return z_hot, q_probs, log_q_local.sum(-1), z
     return z, q_probs, log_q_local.sum(-1), None
@@ -318,7 +320,7 @@ def _oneshot(enc_rws_eta, enc_rws_z, generative, x, trace, result_flags, label_s
         return log_w, tau, mu, None, trace, z_lab, log_q
     log_q_z = None
     if result_flags['loss_required'] and _train_z(enc_rws_z):
-        z, q_probs, log_q_z, z_lab = _sample_z_train(enc_rws_z, generative, x, tau, mu, label_stride)
+        z, q_probs, log_q_z, z_lab = _sample_z_train(enc_rws_z, generative, x, tau, mu, label_stride, tables=tables)
     elif label_stride:
         z, q_probs, z_lab = enc_rws_z.sample_fused(x, tau, mu, generative, label_stride=label_stride, seed=_zseed(tau.device))
     elif enc_rws_z.can_fuse(result_flags['loss_required']):
@@ -436,7 +438,7 @@ def _update_z(enc_apg_z, generative, x, tau, mu, z_old, trace, result_flags, eta
         # N2: the fused forward launch + a backward kernel for the MLP gradients (train.FusedZStep)
         from .train import FusedZStep
         z, q_probs, log_w, density, log_w_local, log_q_local, _ = FusedZStep.apply(*enc_apg_z.mlp(), kernels._x3(x), tau, mu,
-                                                                                  z_old, generative, 0, _zseed(tau.device))
+                                                                                  z_old, generative, 0, _zseed(tau.device), tables)
         w_local, _ = ops.local_weight_stats(log_w_local, want_w=True, want_sum=False)
         loss = (w_local * (-log_q_local)).sum(0).sum(-1).mean()
         trace['loss'][-1] = trace['loss'][-1] + loss.unsqueeze(0)

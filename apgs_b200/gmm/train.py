@@ -57,20 +57,21 @@ class FusedZStep(torch.autograd.Function):
     """z ~ q(z | x, tau, mu) and everything the z step needs from ONE forward launch; differentiable w.r.t. the MLP through
     log_q_local only (the weights are detached in the reference too, objectives.py:216-220).
 
-    apply(W1, b1, W2, b2, x, tau, mu, z_old, prior, label_stride, seed=None)
+    apply(W1, b1, W2, b2, x, tau, mu, z_old, prior, label_stride, seed=None, tables=None)
         -> z_new, q_probs, log_w, density, log_w_local, log_q_local, z_onehot
     z_old one-hot (S,B,N,K) or uint8 labels (S,B,LN) -> z_new in the same form.  z_old None: sample-only mode of the
     one-shot / joint step (log_w / log_w_local are then meaningless); with label_stride > 0 the draw comes back as labels
     (z_new) AND one-hot (z_onehot, what the one-shot's weight kernel reads), else z_onehot is z_new."""
 
     @staticmethod
-    def forward(ctx, W1, b1, W2, b2, x, tau, mu, z_old, prior, label_stride=0, seed=None):
+    def forward(ctx, W1, b1, W2, b2, x, tau, mu, z_old, prior, label_stride=0, seed=None, tables=None):
+        tables = tables if seed is not None else None       # kernels.z_tables of (x, weights): the forward launch fetches them
         if z_old is None and label_stride:
             (z_hot, z_new), q, w = kernels.z_step_fused(x, tau, mu, (W1, b1, W2, b2), prior, want_q=True, local=True,
-                                                        also_labels=label_stride, seed=seed)
+                                                        also_labels=label_stride, seed=seed, tables=tables)
         else:
             z_new, q, w = kernels.z_step_fused(x, tau, mu, (W1, b1, W2, b2), prior, z_old=z_old, want_q=True, local=True,
-                                               seed=seed)
+                                               seed=seed, tables=tables)
             z_hot = z_new
         ctx.save_for_backward(W1, b1, W2, b2, x, tau, mu, q, z_new)
         log_w_local = w.log_w_local if w.log_w_local is not None else w.log_q_local.new_zeros(())
@@ -82,9 +83,9 @@ class FusedZStep(torch.autograd.Function):
     def backward(ctx, gz, gq, glw, gd, glwl, glq, gzh):
         W1, b1, W2, b2, x, tau, mu, q, z_new = ctx.saved_tensors
         if glq is None:
-            return (None,) * 11
+            return (None,) * 12
         gW1, gb1, gW2, gb2 = z_logq_backward(x, tau, mu, (W1, b1, W2, b2), q, z_new, glq)
-        return gW1, gb1, gW2, gb2, None, None, None, None, None, None, None
+        return gW1, gb1, gW2, gb2, None, None, None, None, None, None, None, None
 
 
 def label_table_sum(table, z):
