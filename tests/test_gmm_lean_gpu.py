@@ -805,3 +805,94 @@ def test_gatherless_objective_is_bit_identical(strategy):
     for k in ("ess", "density", "log_z"):
         assert torch.equal(out["gatherless"][k], out["plain"][k]), k
         assert torch.equal(out["deferred"][k], out["plain"][k]), k
+
+
+def test_r2_entries_stay_inside_their_buffers_and_refuse_bad_arguments():
+    """raw C-ABI calls of the round-2 entries (z tables, tab step with ancestor maps, compose, eta `_via` entries) with every
+    output embedded in guard bands, ragged shapes (S not a multiple of the tiles, N = 41, H = 16)."""
+    import ctypes as C
+    from apgs_b200 import _lib
+    from apgs_b200._lib import ptr
+    from apgs_b200.gmm.kernels import _prior_struct, _post_struct
+    lib = _lib.load()
+    S, B, N, K, D, H, LN = 37, 5, 41, 3, 2, 16, 48
+    torch.manual_seed(13)
+    P = og.make_params(K, D, H)
+    G = 2048
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=DEV)
+        return buf, buf[G:G + n]
+
+    def intact(bufs):
+        torch.cuda.synchronize()
+        for name, (buf, view) in bufs.items():
+            fill = {torch.uint8: 0xEE, torch.int32: -77}.get(buf.dtype, -7.0)
+            assert bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all()), name
+    x, tau, mu, lab_old, _ = [t.to(DEV) for t in _latents(S, B, K, D, N, seed=19)]
+    lab = _pad_labels(lab_old, LN)
+    mlp = [t.contiguous() for t in _mlp(P)]
+    heads = [t.contiguous() for t in _heads(P)]
+    gen = _Gen(K, D)
+    rs, keep = _prior_struct(gen)
+    amap = torch.randint(0, S, (S, B), dtype=torch.int32, device=DEV)
+    bmap = torch.randint(0, S, (S, B), dtype=torch.int32, device=DEV)
+    # ---- tables
+    nb = lib.apgs_gmm_z_tables_bytes(B, N, H, K, D)
+    assert nb > 0 and nb % (16 * B) == 0 and lib.apgs_gmm_z_tables_bytes(0, N, H, K, D) == 0
+    bufs = {"tab": guarded(nb // 4, torch.float32, -7.0)}
+    assert lib.apgs_gmm_z_tables_f32(ptr(x), *[ptr(m) for m in mlp], H, C.byref(rs), B, N, K, D, ptr(bufs["tab"][1]), st) == 0
+    intact(bufs)
+    assert bool(torch.isfinite(bufs["tab"][1]).all())
+    assert lib.apgs_gmm_z_tables_f32(ptr(x), *[ptr(m) for m in mlp], H, C.byref(rs), B, N, K, D, None, st) < 0
+    assert lib.apgs_gmm_z_tables_f32(ptr(x), *[ptr(m) for m in mlp], H, C.byref(rs), B, N, 7, 5, ptr(bufs["tab"][1]), st) < 0
+    # ---- compose
+    cb = {"comp": guarded(S * B, torch.int32, -77)}
+    assert lib.apgs_compose_ancestors(ptr(amap), ptr(bmap), S, B, ptr(cb["comp"][1]), st) == 0
+    intact(cb)
+    assert torch.equal(cb["comp"][1].view(S, B).long(), torch.gather(amap.long(), 0, bmap.long()))
+    assert lib.apgs_compose_ancestors(None, ptr(bmap), S, B, ptr(cb["comp"][1]), st) < 0
+    # ---- the tab step with both maps, lean launch
+    zb = {"zl": guarded(S * B * LN, torch.uint8, 0xEE)}
+    for name in ("log_w", "log_q_f", "density"):
+        zb[name] = guarded(S * B, torch.float32, -7.0)
+    o = _lib.GmmOut()
+    for name in ("log_w", "log_q_f", "density"):
+        setattr(o, name, zb[name][1].data_ptr())
+    seed = torch.tensor([3, 4], dtype=torch.int64, device=DEV)
+    rc = lib.apgs_gmm_z_step_fused_tab_f32(ptr(x), ptr(tau), ptr(mu), *[ptr(m) for m in mlp], H, C.byref(rs), None, ptr(lab), ptr(seed),
+                                           S, B, N, K, D, None, ptr(zb["zl"][1]), LN, None, None, None, None, None, None, None,
+                                           C.byref(o), ptr(bufs["tab"][1]), ptr(amap), ptr(bmap), st)
+    assert rc == 0, lib.apgs_last_error()
+    intact(zb)
+    zl = zb["zl"][1].view(S, B, LN)
+    assert bool((zl[..., :N] < K).all()) and bool((zl[..., N:] == 0xEE).all())
+    assert bool(torch.isfinite(zb["log_w"][1]).all()) and not bool((zb["log_w"][1] == -7.0).any())
+    rc = lib.apgs_gmm_z_step_fused_tab_f32(ptr(x), ptr(tau), ptr(mu), *[ptr(m) for m in mlp], H, C.byref(rs), None, ptr(lab), None,
+                                           S, B, N, K, D, None, ptr(zb["zl"][1]), LN, None, None, None, None, None, None, None,
+                                           C.byref(o), ptr(bufs["tab"][1]), ptr(amap), ptr(bmap), st)
+    assert rc < 0                                                  # no seed
+    # ---- eta entries through maps
+    eb = {"stats": guarded(S * B * K * (1 + 2 * D), torch.float32, -7.0)}
+    for name in ("pa", "pb", "pm", "pn", "tau", "mu"):
+        eb[name] = guarded(S * B * K * D, torch.float32, -7.0)
+    for name in ("log_w", "log_q_f", "density"):
+        eb[name] = guarded(S * B, torch.float32, -7.0)
+    pr = [getattr(gen, "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
+    rc = lib.apgs_gmm_eta_posterior_stats_labels_via_f32(ptr(x), ptr(lab), *[ptr(h) for h in heads], S, B, N, K, D,
+                                                         *[ptr(v) for v in pr], *[ptr(eb[n][1]) for n in ("pa", "pb", "pm", "pn")],
+                                                         ptr(mu), ptr(eb["stats"][1]), LN, ptr(amap), ptr(bmap), st)
+    assert rc == 0, lib.apgs_last_error()
+    post = tuple(eb[n][1].view(S, B, K, D) for n in ("pa", "pb", "pm", "pn"))
+    ps, keep2 = _post_struct(post)
+    o2 = _lib.GmmOut()
+    for name in ("log_w", "log_q_f", "density"):
+        setattr(o2, name, eb[name][1].data_ptr())
+    rc = lib.apgs_gmm_draw_logw_eta_stats_rng_via_f32(ptr(eb["stats"][1]), ptr(mu), C.byref(ps), C.byref(rs), ptr(seed),
+                                                      ptr(eb["tau"][1]), ptr(eb["mu"][1]), ptr(tau), ptr(mu), ptr(bmap),
+                                                      S, B, K, D, C.byref(o2), st)
+    assert rc == 0, lib.apgs_last_error()
+    intact(eb)
+    for name in ("pa", "pb", "pm", "pn", "stats", "tau", "mu", "log_w", "log_q_f", "density"):
+        assert bool(torch.isfinite(eb[name][1]).all()) and not bool((eb[name][1] == -7.0).any()), name
