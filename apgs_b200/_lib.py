@@ -78,6 +78,7 @@ SIGNATURES = {
     "apgs_dmm_nss_pool_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_dmm_nss_pool_onehot_f32": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_dmm_local_encoder_fused_f32": (_int, [_p, _p, _DMLP, _DMLP, _DMLP, _i64, _p, _p, _p] + [_i64] * 5 + [_p] * 7),
+    "apgs_dmm_local_encoder_draw_f32": (_int, [_p, _p, _DMLP, _DMLP, _DMLP, _i64, _p, _p, _p, _p] + [_i64] * 5 + [_p] * 7 + [_DMLP, _i64, _p, _p]),
     "apgs_dmm_decoder_hidden2_f32": (_int, [_p, _DMLP, _i64, _i64, _i64, _p, _p]),
     "apgs_dmm_logw_mu_f32": (_int, [_p] * 7 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),
     "apgs_dmm_logw_local_f32": (_int, [_p] * 13 + [_DPR] + [_i64] * 5 + [_DOUT, _p]),

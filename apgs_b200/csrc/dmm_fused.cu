@@ -15,6 +15,7 @@
 // shared memory, weights in CTA-shared memory.  The first layers split as W (x - mu) + b = (W x + b) - W mu.
 // tanh(u) = 1 - 2 / (2^(2 log2(e) u) + 1) with the scale folded into the first-layer weights (gmm_common.cuh).
 #include "gmm_common.cuh"
+#include "rng.cuh"
 
 namespace apgs {
 
@@ -139,6 +140,14 @@ struct LocalEncArgs {
     float *con1_old, *con0_old;              // (R, N) out: concentrations at z_old (when z_old)
     long long R;
     int B, N, H;
+    // optional draws made in the kernel (Philox keyed by two host-drawn words, rng.cuh): the categorical draw's uniform when
+    // `u` is null, and beta ~ Beta(con1, con0) as torch draws it (two standard Gammas, normalised, clamped) -> beta_out (R, N)
+    const unsigned long long* seed;
+    float* beta_out;
+    // optional: the decoder's unit-normalised output of the drawn beta (Decoder.recon_mu, 1 -> HD -> tanh -> D) -> h2_out (R, N, D)
+    const float *dW0, *db0, *dW2, *db2;
+    float* h2_out;
+    int HD;
 };
 
 // sum_h w2[h] tanh(pre[h]) over one point, pre[h] = W'[h] . d + b'[h] already scaled by 2 log2(e):
@@ -180,7 +189,24 @@ __global__ void __launch_bounds__(kFW * 32) k_dmm_local_fused(LocalEncArgs a) {
     float* s_c0 = s_c1 + H * WS;
     float* s_mh = s_c0 + H * WS;                // [kFW][H][K]: W0_pi mu_k
     float* s_mu = s_mh + (size_t)kFW * H * K;   // [kFW][K][D]
+    float* s_dw = s_mu + (size_t)kFW * K * D;   // decoder (optional): [HD][2 + D]: w0', b0', -2 W2[d][h]
     __shared__ float s_sum[2];
+    __shared__ float s_db[D];
+    const bool dec = a.h2_out != nullptr;
+    if (dec) {
+        constexpr float TWO_PI = 6.283185307179586f;
+        for (int i = threadIdx.x; i < a.HD * (2 + D); i += blockDim.x) {
+            const int h = i / (2 + D), c = i % (2 + D);
+            s_dw[i] = c == 0 ? TANH_PRESCALE * TWO_PI * __ldg(a.dW0 + h)
+                             : (c == 1 ? TANH_PRESCALE * __ldg(a.db0 + h) : -2.f * __ldg(a.dW2 + (c - 2) * a.HD + h));
+        }
+        if (threadIdx.x >= 64 && threadIdx.x < 64 + D) {
+            const int d = threadIdx.x - 64;
+            float sacc = __ldg(a.db2 + d);
+            for (int h = 0; h < a.HD; ++h) sacc += __ldg(a.dW2 + d * a.HD + h);
+            s_db[d] = sacc;
+        }
+    }
     for (int i = threadIdx.x; i < H * WS; i += blockDim.x) {
         const int h = i / WS, c = i % WS;
         s_pi[i] = c < D ? __ldg(a.pW0 + h * D + c) : (c == D ? __ldg(a.pb0 + h) : __ldg(a.pW2 + h));
@@ -218,12 +244,28 @@ __global__ void __launch_bounds__(kFW * 32) k_dmm_local_fused(LocalEncArgs a) {
     const float pb2 = __ldg(a.pb2), sum1 = s_sum[0], sum0 = s_sum[1];
     const float* xb = a.x + (size_t)(r % a.B) * N * D;
     const bool forced = a.z_forced != nullptr, has_old = a.z_old != nullptr;
+    const bool draw = a.seed != nullptr;
+    uint2 key = make_uint2(0u, 0u);
+    unsigned int st_lo = 0u, st_hi = 0u;
+    if (draw) {
+        const unsigned long long sd = __ldg(a.seed), st = __ldg(a.seed + 1);
+        key = make_uint2((unsigned int)sd, (unsigned int)(sd >> 32));
+        st_lo = (unsigned int)st; st_hi = (unsigned int)(st >> 32);
+    }
     for (int n = lane; n < N; n += 32) {
         const long long pn = r * N + n;
         float xv[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) xv[d] = __ldg(xb + n * D + d);
-        const float un = forced ? 0.f : __ldg(a.u + pn);
+        // Philox words of this point: block 0 = {uniform of the categorical draw, two words -> two normals, uniform of the
+        // first Gamma}, block 1 = {uniform of the second Gamma, the two boost uniforms (alpha < 1)}
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+        const uint4 cbase = make_uint4((unsigned int)pn, (unsigned int)((unsigned long long)pn >> 32) ^ st_lo, st_hi, 0u);
+        if (draw) {
+            w0 = philox4x32_10(cbase, key);
+            w1 = philox4x32_10(make_uint4(cbase.x, cbase.y, cbase.z ^ 0x10000000u, 0u), key);
+        }
+        const float un = forced ? 0.f : (a.u != nullptr ? __ldg(a.u + pn) : (float)(w0.x >> 8) * 5.9604644775390625e-08f);
         // ---- pi logits: W2 . relu((W0 x + b0) - W0 mu_k) + b2   (models.py:78-79)
         float lg[K];
 #pragma unroll
@@ -266,16 +308,46 @@ __global__ void __launch_bounds__(kFW * 32) k_dmm_local_fused(LocalEncArgs a) {
         float dv[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) dv[d] = xv[d] - mu[lf * D + d];
-        a.con1[pn] = expf(tanh_net<D>(s_c1, H, dv, sum1));
-        a.con0[pn] = expf(tanh_net<D>(s_c0, H, dv, sum0));
+        const float c1v = expf(tanh_net<D>(s_c1, H, dv, sum1)), c0v = expf(tanh_net<D>(s_c0, H, dv, sum0));
+        a.con1[pn] = c1v;
+        a.con0[pn] = c0v;
+        if (draw && a.beta_out != nullptr) {
+            // Beta(con1, con0).sample() as torch draws it (Dirichlet on [con1, con0], apgs/dmm/models.py:90): two standard
+            // Gammas (Marsaglia-Tsang, clamped to the smallest normal like _standard_gamma), g1 / (g1 + g0), clamped to
+            // [tiny, 1 - eps].  Distribution-equal, not stream-equal, to torch's draw.
+            float n1, n0;
+            box_muller(w0.y, w0.z, n1, n0);
+            const float g1 = fmaxf(gamma_mt(c1v, n1, w0.w, w1.y, make_uint4(cbase.x, cbase.y, cbase.z ^ 0x20000000u, 0u), key), 1.17549435e-38f);
+            const float g0 = fmaxf(gamma_mt(c0v, n0, w1.x, w1.z, make_uint4(cbase.x, cbase.y, cbase.z ^ 0x30000000u, 0u), key), 1.17549435e-38f);
+            const float bt = fminf(fmaxf(__fdiv_rn(g1, __fadd_rn(g1, g0)), 1.17549435e-38f), 1.f - FLT_EPS_F);
+            a.beta_out[pn] = bt;
+            if (dec) {
+                // Decoder.recon_mu(2 pi beta), unit-normalised (apgs/dmm/models.py:202-203): k_dmm_decoder_hidden2's arithmetic
+                float o[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) o[d] = s_db[d];
+                for (int h = 0; h < a.HD; ++h) {
+                    const float* w = s_dw + h * (2 + D);
+                    const float rcp = rcp_ftz(ex2_ftz(fmaf(w[0], bt, w[1])) + 1.f);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) o[d] = fmaf(w[2 + d], rcp, o[d]);
+                }
+                float ss = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) ss = __fadd_rn(ss, __fmul_rn(o[d], o[d]));
+                const float nrm = __fsqrt_rn(ss);
+#pragma unroll
+                for (int d = 0; d < D; ++d) a.h2_out[pn * D + d] = __fdiv_rn(o[d], nrm);
+            }
+        }
         if (has_old) {                                                      // models.py:99-101 (backward kernel)
             int lb = 0;
             float best = __ldg(a.z_old + pn * K);
 #pragma unroll
             for (int k = 1; k < K; ++k) { const float v = __ldg(a.z_old + pn * K + k); if (v > best) { best = v; lb = k; } }
             if (lb == lf) {
-                a.con1_old[pn] = a.con1[pn];
-                a.con0_old[pn] = a.con0[pn];
+                a.con1_old[pn] = c1v;
+                a.con0_old[pn] = c0v;
             } else {
 #pragma unroll
                 for (int d = 0; d < D; ++d) dv[d] = xv[d] - mu[lb * D + d];
@@ -336,7 +408,8 @@ __global__ void __launch_bounds__(256) k_dmm_decoder_hidden2(DecArgs a) {
 
 template <int K, int D>
 static int launch_local(const LocalEncArgs& a, cudaStream_t st) {
-    const size_t smem = ((size_t)3 * a.H * (D + 2) + (size_t)kFW * a.H * K + (size_t)kFW * K * D) * 4;
+    const size_t smem = ((size_t)3 * a.H * (D + 2) + (size_t)kFW * a.H * K + (size_t)kFW * K * D +
+                         (a.h2_out != nullptr ? (size_t)a.HD * (2 + D) : 0)) * 4;
     if (smem > 200 * 1024) return fail(APGS_E_SHAPE, "dmm_local_encoder_fused: H=%d too large", a.H);
     auto kern = a.H == 32 ? k_dmm_local_fused<K, D, 32> : k_dmm_local_fused<K, D>;
     APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem), "smem attr");
@@ -374,12 +447,13 @@ extern "C" int apgs_dmm_nss_pool_onehot_f32(const float* tab1, const float* tab2
     return 0;
 }
 
-extern "C" int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu, const apgs_dmm_mlp_t* pi,
-                                                const apgs_dmm_mlp_t* con1_net, const apgs_dmm_mlp_t* con0_net,
-                                                int64_t H, const float* uniforms, const float* z_forced,
-                                                const float* z_old, int64_t S, int64_t B, int64_t N, int64_t K,
-                                                int64_t D, float* q_probs, float* z, float* con1, float* con0,
-                                                float* con1_old, float* con0_old, void* stream) {
+static int local_encoder(const float* x, const float* mu, const apgs_dmm_mlp_t* pi,
+                         const apgs_dmm_mlp_t* con1_net, const apgs_dmm_mlp_t* con0_net,
+                         int64_t H, const float* uniforms, const float* z_forced,
+                         const float* z_old, int64_t S, int64_t B, int64_t N, int64_t K,
+                         int64_t D, float* q_probs, float* z, float* con1, float* con0,
+                         float* con1_old, float* con0_old, void* stream, const uint64_t* seed, float* beta,
+                         const apgs_dmm_mlp_t* decoder, int64_t HD, float* hidden2) {
     if (S <= 0 || B <= 0 || N <= 0 || H <= 0 || H > 1024)
         return fail(APGS_E_SHAPE, "dmm_local_encoder_fused: bad sizes S=%lld B=%lld N=%lld H=%lld", (long long)S,
                     (long long)B, (long long)N, (long long)H);
@@ -390,7 +464,10 @@ extern "C" int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
     for (int i = 0; i < 3; ++i)
         if (!nets[i]->W0 || !nets[i]->b0 || !nets[i]->W2 || !nets[i]->b2)
             return fail(APGS_E_BADARG, "dmm_local_encoder_fused: NULL weight");
-    if (!uniforms && !z_forced) return fail(APGS_E_BADARG, "dmm_local_encoder_fused: uniforms (or z_forced) required");
+    if (!uniforms && !z_forced && !seed) return fail(APGS_E_BADARG, "dmm_local_encoder_fused: uniforms (or z_forced, or a seed) required");
+    if ((beta || hidden2) && !seed) return fail(APGS_E_BADARG, "dmm_local_encoder_draw: the Beta draw needs philox_seed");
+    if (hidden2 && (!beta || !decoder || !decoder->W0 || !decoder->b0 || !decoder->W2 || !decoder->b2 || HD <= 0 || HD > 4096))
+        return fail(APGS_E_BADARG, "dmm_local_encoder_draw: hidden2 needs beta, the decoder weights and its hidden width");
     if (z_old && (!con1_old || !con0_old))
         return fail(APGS_E_BADARG, "dmm_local_encoder_fused: con1_old/con0_old outputs required with z_old");
     LocalEncArgs a = {};
@@ -401,6 +478,8 @@ extern "C" int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
     a.u = uniforms; a.z_forced = z_forced; a.z_old = z_old;
     a.q_probs = q_probs; a.z = z; a.con1 = con1; a.con0 = con0; a.con1_old = con1_old; a.con0_old = con0_old;
     a.R = (long long)S * B; a.B = (int)B; a.N = (int)N; a.H = (int)H;
+    a.seed = reinterpret_cast<const unsigned long long*>(seed); a.beta_out = beta; a.h2_out = hidden2; a.HD = (int)HD;
+    if (hidden2) { a.dW0 = decoder->W0; a.db0 = decoder->b0; a.dW2 = decoder->W2; a.db2 = decoder->b2; }
     cudaStream_t st = (cudaStream_t)stream;
     if (K == 4 && D == 2) return launch_local<4, 2>(a, st);
     if (K == 3 && D == 2) return launch_local<3, 2>(a, st);
@@ -411,6 +490,29 @@ extern "C" int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
     if (K == 3 && D == 3) return launch_local<3, 3>(a, st);
     return fail(APGS_E_UNSUPPORTED, "dmm_local_encoder_fused: (K=%lld, D=%lld) not instantiated", (long long)K,
                 (long long)D);
+}
+
+extern "C" int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu, const apgs_dmm_mlp_t* pi,
+                                                const apgs_dmm_mlp_t* con1_net, const apgs_dmm_mlp_t* con0_net,
+                                                int64_t H, const float* uniforms, const float* z_forced,
+                                                const float* z_old, int64_t S, int64_t B, int64_t N, int64_t K,
+                                                int64_t D, float* q_probs, float* z, float* con1, float* con0,
+                                                float* con1_old, float* con0_old, void* stream) {
+    return local_encoder(x, mu, pi, con1_net, con0_net, H, uniforms, z_forced, z_old, S, B, N, K, D, q_probs, z, con1, con0,
+                         con1_old, con0_old, stream, nullptr, nullptr, nullptr, 0, nullptr);
+}
+
+extern "C" int apgs_dmm_local_encoder_draw_f32(const float* x, const float* mu, const apgs_dmm_mlp_t* pi,
+                                               const apgs_dmm_mlp_t* con1_net, const apgs_dmm_mlp_t* con0_net,
+                                               int64_t H, const float* uniforms, const float* z_forced,
+                                               const float* z_old, const uint64_t* philox_seed, int64_t S, int64_t B,
+                                               int64_t N, int64_t K, int64_t D, float* q_probs, float* z, float* con1,
+                                               float* con0, float* con1_old, float* con0_old, float* beta,
+                                               const apgs_dmm_mlp_t* decoder, int64_t decoder_hidden, float* hidden2,
+                                               void* stream) {
+    if (!philox_seed || !beta) return fail(APGS_E_BADARG, "dmm_local_encoder_draw: philox_seed and beta are required");
+    return local_encoder(x, mu, pi, con1_net, con0_net, H, uniforms, z_forced, z_old, S, B, N, K, D, q_probs, z, con1, con0,
+                         con1_old, con0_old, stream, philox_seed, beta, decoder, decoder_hidden, hidden2);
 }
 
 // bit 0: the fused local encoder is compiled for (K, D); bit 1: the decoder kernel for D.  The weight / pooling kernels

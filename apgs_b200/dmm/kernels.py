@@ -150,10 +150,13 @@ def nss_pool_onehot(tab1, tab2, z, prior_mu_mu, prior_mu_sigma):
     return out
 
 
-def local_encoder_fused(x, mu, enc, uniforms=None, z_forced=None, z_old=None):
+def local_encoder_fused(x, mu, enc, uniforms=None, z_forced=None, z_old=None, seed=None, decoder=None):
     """Enc_apg_local in one kernel (apgs/dmm/models.py:76-101).  enc: module with pi_log_prob, angle_log_con1,
     angle_log_con0.  Returns q_probs (S,B,N,K), z (S,B,N,K), con1, con0 (S,B,N,1) and, when z_old is given,
-    con1_old, con0_old (S,B,N,1) (else None, None)."""
+    con1_old, con0_old (S,B,N,1) (else None, None).
+    seed (two int64 words on the device, gmm.kernels.philox_seed): the draws are made in the kernel -- the categorical draw's
+    uniform (unless `uniforms` is given) and beta ~ Beta(con1, con0) -- and two more values come back: beta (S,B,N,1) and,
+    with decoder = Decoder.recon_mu, its unit-normalised output hidden2 (S,B,N,D) (else None)."""
     lib = _lib.load()
     x = _x3(x)
     mu = _req(mu, "mu", ndim=4)
@@ -167,7 +170,7 @@ def local_encoder_fused(x, mu, enc, uniforms=None, z_forced=None, z_old=None):
     if not (H == H1 == H0):
         raise ValueError("the three local MLPs must share num_hidden")
     dev = mu.device
-    if uniforms is None and z_forced is None:
+    if uniforms is None and z_forced is None and seed is None:
         uniforms = torch.rand(S, B, N, dtype=torch.float32, device=dev)
     for name, t, shp in (("uniforms", uniforms, (S, B, N)), ("z_forced", z_forced, (S, B, N, K)), ("z_old", z_old, (S, B, N, K))):
         if t is not None:
@@ -182,6 +185,25 @@ def local_encoder_fused(x, mu, enc, uniforms=None, z_forced=None, z_old=None):
                                 if z_old is not None else [])
     co = con + [None, None] if z_old is None else con
     nbytes = 4 * S * B * (N * (2 * K + 1 + len(con) + (K if z_old is not None else 0)) + K * D)
+    if seed is not None:
+        seed = _req(seed, "seed", dtype=torch.int64)
+        if seed.numel() < 2:
+            raise ValueError("seed must hold two int64 words")
+        beta = torch.empty(S, B, N, 1, dtype=torch.float32, device=dev)
+        h2 = dnet = None
+        HD = 0
+        if decoder is not None:
+            dnet, keepd, HD = _mlp_struct(decoder, "recon_mu")
+            if decoder[0].weight.shape[1] != 1 or decoder[2].weight.shape[0] != D:
+                raise ValueError("decoder must map 1 -> H -> D")
+            h2 = torch.empty(S, B, N, D, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _call("dmm_local_encoder_fused", 1, nbytes + 4 * S * B * N * (1 + (D if h2 is not None else 0))):
+            check(lib.apgs_dmm_local_encoder_draw_f32(ptr(x), ptr(mu), C.byref(pi), C.byref(c1), C.byref(c0), H, ptr(uniforms),
+                                                      ptr(z_forced), ptr(z_old), ptr(seed), S, B, N, K, D, ptr(q), ptr(z),
+                                                      ptr(co[0]), ptr(co[1]), ptr(co[2]), ptr(co[3]), ptr(beta),
+                                                      C.byref(dnet) if dnet is not None else None, HD, ptr(h2), _stream()),
+                  "apgs_dmm_local_encoder_draw_f32")
+        return q, z, co[0], co[1], co[2], co[3], beta, h2
     with torch.cuda.device(dev), _call("dmm_local_encoder_fused", 1, nbytes):
         check(lib.apgs_dmm_local_encoder_fused_f32(ptr(x), ptr(mu), C.byref(pi), C.byref(c1), C.byref(c0), H, ptr(uniforms),
                                                    ptr(z_forced), ptr(z_old), S, B, N, K, D, ptr(q), ptr(z), ptr(co[0]),

@@ -147,10 +147,12 @@ class Enc_apg_local(nn.Module):
         K, D = getattr(self, 'K', None), self.pi_log_prob[0].weight.shape[1]
         return K is None or bool(kernels.supported(K, D) & 1)
 
-    def sample_fused(self, ob, mu, z_old=None, uniforms=None, z_forced=None):
+    def sample_fused(self, ob, mu, z_old=None, uniforms=None, z_forced=None, seed=None, decoder=None):
         """probs + categorical draw + Beta concentrations (for z and, when given, for z_old) in one kernel:
-        q_probs, z, con1, con0, con1_old, con0_old."""
-        return kernels.local_encoder_fused(_x_inst(ob), mu, self, uniforms=uniforms, z_forced=z_forced, z_old=z_old)
+        q_probs, z, con1, con0, con1_old, con0_old; with seed also beta ~ Beta(con1, con0) drawn in the kernel and, with
+        decoder = Decoder.recon_mu, the decoder's hidden2 of it (kernels.local_encoder_fused)."""
+        return kernels.local_encoder_fused(_x_inst(ob), mu, self, uniforms=uniforms, z_forced=z_forced, z_old=z_old,
+                                           seed=seed, decoder=decoder)
 
     def probs(self, ob, mu, K):
         """q_probs (S,B,N,K): MLP on x_n - mu_k (models.py:78-79); W (x - mu) + b = (W x + b) - W mu."""

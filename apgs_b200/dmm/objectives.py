@@ -74,11 +74,25 @@ def apg_objective(models, x, K, result_flags, num_sweeps, resampler):
     return trace
 
 
-def _sample_local(enc_local, x, mu, K, z_old=None):
-    """q_probs, z, con1, con0, beta (+ the concentrations at z_old for the backward kernel when z_old is given)."""
+rng_in_kernels = True          # evaluation sweeps: the categorical draw's uniforms and beta ~ Beta(con1, con0) are made inside the
+                               # fused local-encoder kernel (else torch.rand / torch._standard_gamma), which then also evaluates
+                               # the decoder's hidden2 of the drawn beta
+
+
+def _sample_local(enc_local, x, mu, K, z_old=None, dec=None):
+    """q_probs, z, con1, con0, beta (+ the concentrations at z_old for the backward kernel when z_old is given).
+    dec (evaluation, fused encoder, in-kernel draws): the last value returned is the decoder's hidden2 of beta (else None)."""
     if enc_local.can_fuse():
-        q_probs, z, con1, con0, con1_b, con0_b = enc_local.sample_fused(x, mu, z_old=z_old)
-        beta = kernels.beta_sample(con1, con0)
+        h2 = None
+        if rng_in_kernels and dec is not None and getattr(dec, 'fused', False) and not torch.is_grad_enabled():
+            from ..gmm.kernels import philox_seed
+            q_probs, z, con1, con0, con1_b, con0_b, beta, h2 = enc_local.sample_fused(
+                x, mu, z_old=z_old, seed=philox_seed(mu.device), decoder=dec.recon_mu)
+        else:
+            q_probs, z, con1, con0, con1_b, con0_b = enc_local.sample_fused(x, mu, z_old=z_old)
+            beta = kernels.beta_sample(con1, con0)
+        if dec is not None:
+            return ((q_probs, z, con1, con0, beta) if z_old is None else (q_probs, z, con1, con0, beta, con1_b, con0_b)) + (h2,)
         return (q_probs, z, con1, con0, beta) if z_old is None else (q_probs, z, con1, con0, beta, con1_b, con0_b)
     if z_old is not None:
         out = _sample_local(enc_local, x, mu, K)
@@ -105,8 +119,12 @@ def _oneshot(enc_rws_mu, enc_rws_local, dec, x, K, trace, result_flags):
     """oneshot that also returns the decoder output h2 of the new beta."""
     q_mu, q_sigma = enc_rws_mu.params(x, K, (dec.prior_mu_mu, dec.prior_mu_sigma))
     mu = normal_sample(q_mu, q_sigma)
-    q_probs, z, con1, con0, beta = _sample_local(enc_rws_local, x, mu, K)
-    h2 = dec.hidden2(beta)
+    if enc_rws_local.can_fuse():
+        q_probs, z, con1, con0, beta, h2 = _sample_local(enc_rws_local, x, mu, K, dec=dec)
+    else:
+        (q_probs, z, con1, con0, beta), h2 = _sample_local(enc_rws_local, x, mu, K), None
+    if h2 is None:
+        h2 = dec.hidden2(beta)
     w = kernels.logw_oneshot(x, q_mu, q_sigma, mu, q_probs, z, beta, con1, con0, h2, dec)
     log_q, ll = w.log_q_f, w.ll_f
     if result_flags['loss_required']:
@@ -158,8 +176,12 @@ def apg_update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, resul
 
 def _update_local(enc_apg_local, dec, x, mu, z_old, beta_old, K, trace, result_flags, h2_old=None):
     """apg_update_local that takes the decoder output of beta_old when the caller holds it and returns the new one."""
-    q_probs, z, con1, con0, beta, con1_b, con0_b = _sample_local(enc_apg_local, x, mu, K, z_old=z_old)
-    h2 = dec.hidden2(beta)
+    if enc_apg_local.can_fuse():
+        q_probs, z, con1, con0, beta, con1_b, con0_b, h2 = _sample_local(enc_apg_local, x, mu, K, z_old=z_old, dec=dec)
+    else:
+        (q_probs, z, con1, con0, beta, con1_b, con0_b), h2 = _sample_local(enc_apg_local, x, mu, K, z_old=z_old), None
+    if h2 is None:
+        h2 = dec.hidden2(beta)
     if h2_old is None:
         h2_old = dec.hidden2(beta_old)
     need_local = bool(result_flags['loss_required'])

@@ -559,6 +559,20 @@ APGS_API int apgs_dmm_local_encoder_fused_f32(const float* x, const float* mu,
                                  float* q_probs, float* z, float* con1, float* con0,
                                  float* con1_old, float* con0_old, void* stream);
 
+/* The same kernel with the draws made inside it: beta ~ Beta(con1, con0) (`Beta(...).sample()`, apgs/dmm/models.py:90-91; as
+ *   torch draws it -- two standard Gammas by Marsaglia-Tsang, normalised, clamped to [tiny, 1 - eps] -- from Philox4x32-10
+ *   keyed by the two 64-bit words at philox_seed, which the host takes from its generator per launch) -> beta (S,B,N), and,
+ *   when `decoder` (recon_mu, 1 -> decoder_hidden -> tanh -> D) and hidden2 (S,B,N,D) are given, the decoder's unit-normalised
+ *   output of that beta (apgs/dmm/models.py:202-203; apgs_dmm_decoder_hidden2_f32's arithmetic).  uniforms may be NULL: the
+ *   categorical draw then takes its uniform from the same Philox stream.  Distribution-equal, not stream-equal, to torch.   */
+APGS_API int apgs_dmm_local_encoder_draw_f32(const float* x, const float* mu,
+                                 const apgs_dmm_mlp_t* pi, const apgs_dmm_mlp_t* con1_net, const apgs_dmm_mlp_t* con0_net,
+                                 int64_t H, const float* uniforms, const float* z_forced, const float* z_old,
+                                 const uint64_t* philox_seed, int64_t S, int64_t B, int64_t N, int64_t K, int64_t D,
+                                 float* q_probs, float* z, float* con1, float* con0, float* con1_old, float* con0_old,
+                                 float* beta, const apgs_dmm_mlp_t* decoder, int64_t decoder_hidden, float* hidden2,
+                                 void* stream);
+
 /* Decoder.recon_mu + unit normalisation (apgs/dmm/models.py:202-203): hidden2 (M,D) from beta (M), M = S*B*N;
  *   net = recon_mu (1->H->tanh->D).                                                                          */
 APGS_API int apgs_dmm_decoder_hidden2_f32(const float* beta, const apgs_dmm_mlp_t* net, int64_t H, int64_t D,

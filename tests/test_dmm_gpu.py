@@ -402,3 +402,88 @@ def test_N2_dmm_training_loop_runs_like_reference_train():
         opt.step()
     after = [p.detach() for m in models for p in m.parameters()]
     assert all(not torch.equal(a, b) for a, b in zip(before, after))
+
+
+def test_local_encoder_draws_in_the_kernel_beta_distribution_and_decoder():
+    """apgs_dmm_local_encoder_draw_f32: (i) with explicit uniforms the encoder outputs are those of the plain entry bit for
+    bit; (ii) beta ~ Beta(con1, con0): with (mu, z) replicated over S the draws of a point are iid over s -- mean / variance
+    against the closed forms within 4.5 standard errors, a Kolmogorov-Smirnov distance against torch's own Beta draws, no
+    correlation between neighbouring points or particles, different seeds differ; (iii) hidden2 == the decoder kernel on the
+    drawn beta, bit for bit; (iv) the in-kernel categorical uniform draws labels with the frequencies of q_probs."""
+    from apgs_b200.dmm import kernels
+    S, B, N, K, D, H = 768, 3, 64, 4, 2, 32
+    P, (_, enc_local, _, dec) = _mods(K, D, H, seed=5)
+    x = torch.randn(B, N, D) * 2
+    mu = (torch.randn(1, B, K, D) * 3).repeat(S, 1, 1, 1).contiguous()
+    z_f = torch.nn.functional.one_hot(torch.randint(0, K, (1, B, N)), K).float().repeat(S, 1, 1, 1).contiguous()
+    xg, mg, zg = x.to(DEV), mu.to(DEV), z_f.to(DEV)
+    s1 = torch.tensor([77, 1], dtype=torch.int64, device=DEV)
+    s2 = torch.tensor([78, 1], dtype=torch.int64, device=DEV)
+    u = torch.rand(S, B, N, device=DEV)
+    plain = kernels.local_encoder_fused(xg, mg, enc_local, uniforms=u, z_old=zg)
+    drawn = kernels.local_encoder_fused(xg, mg, enc_local, uniforms=u, z_old=zg, seed=s1, decoder=dec.recon_mu)
+    for a, b in zip(plain, drawn[:6]):
+        assert torch.equal(a, b)
+    # teacher-forced assignment: the concentrations of a point are the same for every particle
+    q, z, c1, c0, _, _, beta, h2 = kernels.local_encoder_fused(xg, mg, enc_local, z_forced=zg, seed=s1, decoder=dec.recon_mu)
+    again = kernels.local_encoder_fused(xg, mg, enc_local, z_forced=zg, seed=s1, decoder=dec.recon_mu)
+    other = kernels.local_encoder_fused(xg, mg, enc_local, z_forced=zg, seed=s2, decoder=dec.recon_mu)
+    assert torch.equal(beta, again[6]) and torch.equal(h2, again[7])
+    assert float((beta != other[6]).float().mean()) > 0.99
+    assert tuple(beta.shape) == (S, B, N, 1) and tuple(h2.shape) == (S, B, N, D)
+    fi = torch.finfo(torch.float32)
+    assert float(beta.min()) >= fi.tiny and float(beta.max()) <= 1.0 - fi.eps
+    assert torch.equal(h2, kernels.decoder_hidden2(beta, dec.recon_mu))
+    a, b = c1[0, :, :, 0].double(), c0[0, :, :, 0].double()
+    bt = beta[..., 0].double()
+    mean_ref, var_ref = a / (a + b), a * b / ((a + b) ** 2 * (a + b + 1))
+    zm = (bt.mean(0) - mean_ref).abs() / (var_ref / S).sqrt()
+    assert float(zm.max()) < 4.5, float(zm.max())
+    m4 = ((bt - mean_ref) ** 4).mean(0)
+    zv = (bt.var(0, unbiased=False) - var_ref).abs() / ((m4 - var_ref ** 2).clamp_min(1e-30) / S).sqrt()
+    assert float(zv.max()) < 5.0, float(zv.max())
+    # KS distance against torch's Beta for a few points (two-sample, n = m = S: D_crit(1e-4) ~ 2.2 / sqrt(S/2) ... use 0.12)
+    torch.manual_seed(0)
+    for (bb, nn) in ((0, 0), (1, 5), (2, 63)):
+        ref = torch.distributions.Beta(c1[0, bb, nn, 0], c0[0, bb, nn, 0]).sample((S,)).double().cpu().sort().values
+        got = bt[:, bb, nn].cpu().sort().values
+        allv = torch.cat((ref, got)).sort().values
+        d = (torch.searchsorted(ref, allv, right=True).double() / S - torch.searchsorted(got, allv, right=True).double() / S).abs().max()
+        assert float(d) < 0.12, (bb, nn, float(d))
+    resid = (bt - mean_ref) / var_ref.sqrt()
+    for dim in (0, 2):
+        p, q_ = resid.narrow(dim, 0, resid.shape[dim] - 1), resid.narrow(dim, 1, resid.shape[dim] - 1)
+        corr = float((p * q_).mean())
+        assert abs(corr) < 4.5 / p.numel() ** 0.5, (dim, corr)
+    # (iv) the categorical draw from the in-kernel uniform
+    qs, zs, *_ = kernels.local_encoder_fused(xg, mg, enc_local, seed=s1)
+    freq = zs.double().mean(0)
+    qn = (qs[0] / qs[0].sum(-1, keepdim=True)).double()
+    se = (qn * (1 - qn) / S).sqrt().clamp_min(1e-4)
+    assert float(((freq - qn).abs() / se).max()) < 4.5
+
+
+def test_dmm_objective_with_in_kernel_draws_matches_torch_draws_statistically():
+    """apg_objective with the draws made in the kernels vs torch draws: mean ESS / density / log Z agree within 5 standard errors."""
+    from apgs_b200.dmm import objectives, apg_objective, init_apg_models
+    from apgs_b200.resampler import Resampler
+    K, D, N, S, B, sweeps = 4, 2, 200, 50, 48, 4
+    torch.manual_seed(0)
+    models = init_apg_models(K, D, 32, 8, 32, 32, 0.5, True, DEV)
+    x = od.simulate(B, N, K, D).to(DEV)
+    flags = {'loss_required': False, 'ess_required': True, 'mode_required': False, 'density_required': True}
+    out = {}
+    for on in (True, False):
+        objectives.rng_in_kernels = on
+        try:
+            torch.manual_seed(1)
+            with torch.no_grad():
+                trs = [apg_objective(models, x, K, flags, sweeps, Resampler('systematic', S, True, DEV)) for _ in range(6)]
+        finally:
+            objectives.rng_in_kernels = True
+        out[on] = {k: torch.stack([t[k].double().reshape(sweeps, -1).mean(-1) for t in trs]) for k in ('ess', 'density', 'log_z')}
+    for k in ('ess', 'density', 'log_z'):
+        a, b = out[True][k], out[False][k]
+        se = (a.var(0) / a.shape[0] + b.var(0) / b.shape[0]).sqrt().clamp_min(1e-9)
+        zmax = float(((a.mean(0) - b.mean(0)).abs() / se).max())
+        assert zmax < 5.0, (k, zmax)
