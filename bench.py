@@ -167,7 +167,12 @@ def run_reference(args):
         # warm-up passes on a smaller batch (they only warm the thread pool, the allocator and the caches; CPU throughput is
         # flat in B), timed steps on the full sample: keeps the whole arm within a few minutes at --steps 20 --warmup 5
         if args.warmup > 0:
-            cpu_reference("gmm", S, max(1, min(B, 8)), sweeps, args.warmup, 0)
+            cpu_reference("gmm", S, max(1, min(B, 8)), sweeps, max(1, args.warmup - 1), 0)
+        # one calibration step at B = 8 sizes the timed sample so that the --steps run stays within --ref-seconds of CPU work
+        # (the contract's "bounded sample"): B = --ref-batch (64) when it fits, otherwise the largest multiple of 8
+        _, sec8, _ = cpu_reference("gmm", S, max(1, min(B, 8)), sweeps, 1, 0)
+        fit = int(args.ref_seconds / max(1e-6, args.steps * sec8 / max(1, min(B, 8))))
+        B = max(8, min(B, fit // 8 * 8)) if B > 8 else B
         v, sec, kind = cpu_reference("gmm", S, B, sweeps, args.steps, 0)
         cores = torch.get_num_threads()
         v1, sec1, _ = cpu_reference("gmm", S, 4, sweeps, 1, 0, threads=1)
@@ -179,7 +184,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "particle-sweeps/sec", "value": v, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args), "cpu_baseline": base,
+            "config": dict(workload_config(args), ref_batch=B), "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if not args.no_extras:
@@ -668,6 +673,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="instances per GPU")
     ap.add_argument("--sweeps", type=int, default=10)
     ap.add_argument("--ref-batch", type=int, default=64, help="instances per step of the CPU arm (SURVEY.md 8d)")
+    ap.add_argument("--ref-seconds", type=float, default=150.0,
+                    help="--impl reference: budget of CPU seconds for the timed steps; the sample is shrunk below --ref-batch to fit")
     ap.add_argument("--cpu-sweeps", type=int, default=10)
     ap.add_argument("--encoder", default="auto", choices=["auto", "torch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
