@@ -108,7 +108,9 @@ SIGNATURES = {
                                              _i64, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _PO, _p, _OUT, _p, _p, _p, _p]),
     "apgs_compose_ancestors": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "apgs_gmm_eta_posterior_stats_labels_via_f32": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64,
-                                                           _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p]),
+                                                           _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "apgs_gmm_eta_tables_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "apgs_gmm_eta_tables_f32": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_gmm_draw_logw_eta_stats_rng_via_f32": (_int, [_p, _p, _PO, _PR, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gather_ancestors_via": (_int, [_p, _i64, _i64, C.POINTER(Latent), C.POINTER(C.c_void_p), _int, _p]),
     "apgs_gmm_z_loop_probe_f32": (_int, [_i64, _i64, _p, _p]),

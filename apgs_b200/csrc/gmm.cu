@@ -41,6 +41,9 @@ struct NssArgs {
     // deferred gathers (k_gmm_nss_im, label mode): particle (s,b) reads its label row from row (z_anc[s,b], b) and its centre
     // from row (c_anc[s,b], b) -- ancestor maps (S,B) int32 of resampling steps that were never materialised -- or null
     const int *z_anc, *c_anc;
+    // per-instance head tables made once per objective by k_gmm_eta_tables ([N K][RS] factor rows + [N][D] points, padded to
+    // 4 floats per instance), or null: the CTA tabulates them itself
+    const float* tabs;
 };
 
 template <int K, int D, int P, int LANES, bool FUSED, bool HAS_Z, bool STATS = false>
@@ -282,7 +285,8 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     constexpr int RS = EtaTab<K, D>::RS;
     static_assert(RS <= TE, "the launcher sizes the table region as TE floats per row");
     float* s_tab = s_z + (zreg + 3) / 4 * 4;                            // [NK][RS] (region sized [NK][TE])
-    float* s_x = s_tab + (size_t)TE * NK;                               // [N][D]
+    float* s_x = s_tab + (size_t)RS * NK;                               // [N][D], right behind the rows (one block with them)
+    const unsigned int tab_bytes = a.tabs != nullptr ? (unsigned int)((RS * NK + N * D + 3) / 4 * 4) * 4u : 0u;
     const int b = (int)(blockIdx.x % (unsigned int)a.B);
     const int s0 = (int)(blockIdx.x / (unsigned int)a.B) * P;
     const int p = threadIdx.x / LANES, j = threadIdx.x % LANES;
@@ -299,7 +303,10 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     const bool lab_vec = labels && (a.LN & 15) == 0 && a.LN >= LS && aligned(a.zl, 16);   // caller pads its rows likewise
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, bulk_in ? rb * (unsigned int)rows : 0u);
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (bulk_in ? rb * (unsigned int)rows : 0u) + tab_bytes);
+        if (tab_bytes) bulk_g2s(s_tab, a.tabs + (size_t)b * (tab_bytes / 4), tab_bytes, &bar);    // the instance's tables: one copy
+    }
     if (valid) {
         if (labels) {
             if (lab_vec) {
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     }
     // ---- per-CTA table over (point, label), while the rows are in flight
     const float* xb = a.x + (size_t)b * N * D;
-    for (int idx = threadIdx.x; idx < NK; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < (a.tabs != nullptr ? 0 : NK); idx += blockDim.x) {
         const int n = idx / K, lab = idx % K;
         float xin[D];
 #pragma unroll
@@ -719,6 +726,42 @@ static int launch_eta_stats(const EtaStatsArgs& a, cudaStream_t st) {
     return 0;
 }
 
+// Enc_apg_eta's head factors over (point, label) and the points, per instance, in k_gmm_nss_im's shared-memory layout: built
+// once per objective (the heads and the data do not change inside it) and fetched by the CTAs with one bulk copy.
+template <int K, int D>
+__global__ void __launch_bounds__(256) k_gmm_eta_tables(const float* __restrict__ x, const float* Wg, const float* bg, const float* Wo,
+                                                        const float* bo, int N, float* __restrict__ tabs) {
+    constexpr int RS = EtaTab<K, D>::RS;
+    const int NK = N * K, b = (int)blockIdx.x;
+    const size_t stride = (size_t)(RS * NK + N * D + 3) / 4 * 4;
+    float* out = tabs + (size_t)b * stride;
+    const float* xb = x + (size_t)b * N * D;
+    for (int idx = threadIdx.x; idx < NK; idx += blockDim.x) {
+        const int n = idx / K, lab = idx % K;
+        float xin[D], row[RS];
+#pragma unroll
+        for (int i = 0; i < RS; ++i) row[i] = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) xin[d] = __ldg(xb + n * D + d);
+        if (lab == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) out[(size_t)RS * NK + n * D + d] = xin[d];
+        }
+        eta_head_factors<K, D>(Wg, bg, Wo, bo, xin, lab, row);
+#pragma unroll
+        for (int i = 0; i < RS; ++i) out[(size_t)idx * RS + i] = row[i];
+    }
+    for (size_t i = (size_t)RS * NK + (size_t)N * D + threadIdx.x; i < stride; i += blockDim.x) out[i] = 0.f;
+}
+
+template <int K, int D>
+static int launch_eta_tables(const float* x, const float* Wg, const float* bg, const float* Wo, const float* bo, int B, int N,
+                             float* tabs, cudaStream_t st) {
+    k_gmm_eta_tables<K, D><<<(unsigned int)B, 256, 0, st>>>(x, Wg, bg, Wo, bo, N, tabs);
+    APGS_LAUNCH_OK("k_gmm_eta_tables launch");
+    return 0;
+}
+
 // ----------------------------------------------------------------------------------- launchers
 
 // lanes per particle / particles per CTA of the instance-major statistics kernel.  4 lanes x 64 particles: the per-lane
@@ -1060,8 +1103,9 @@ extern "C" int apgs_gmm_eta_posterior_stats_labels_via_f32(const float* x, const
                                                        float* post_beta, float* post_mu, float* post_nu,
                                                        const float* center, float* stats, int64_t label_stride,
                                                        const int32_t* z_ancestors, const int32_t* center_ancestors,
-                                                       void* stream) {
+                                                       const float* tables, void* stream) {
     if (int e = check_gmm_dims(S, B, N, K, D, "gmm_eta_posterior_stats_labels_via")) return e;
+    if (tables && !aligned(tables, 16)) return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels_via: tables must be 16-byte aligned");
     if (label_stride < N) return fail(APGS_E_BADARG, "gmm_eta_posterior_stats_labels_via: label_stride %lld < N", (long long)label_stride);
     if (!x || !z_labels || !Wg || !bg || !Wo || !bo || !prior_alpha || !prior_beta || !prior_mu || !prior_nu ||
         !post_alpha || !post_beta || !post_mu || !post_nu)
@@ -1074,10 +1118,40 @@ extern "C" int apgs_gmm_eta_posterior_stats_labels_via_f32(const float* x, const
     a.ra = prior_alpha; a.rb = prior_beta; a.rm = prior_mu; a.rn = prior_nu;
     a.oa = post_alpha; a.ob = post_beta; a.om = post_mu; a.on = post_nu;
     a.center = center; a.stats = stats;
-    a.z_anc = z_ancestors; a.c_anc = center_ancestors;
+    a.z_anc = z_ancestors; a.c_anc = center_ancestors; a.tabs = tables;
     a.R = (long long)S * B; a.N = (int)N; a.B = (int)B;
     cudaStream_t st = (cudaStream_t)stream;
     APGS_KD_DISPATCH(K, D, launch_nss);
     return fail(APGS_E_UNSUPPORTED, "gmm_eta_posterior_stats_labels_via: (K=%lld, D=%lld) not instantiated", (long long)K,
                 (long long)D);
+}
+
+template <int K, int D>
+static size_t eta_tables_floats(int64_t N) { return (size_t)(EtaTab<K, D>::RS * N * K + N * D + 3) / 4 * 4; }
+
+// (K, D) of the instance-major statistics kernel (K D <= 8 and compiled): floats per instance, 0 if unsupported
+static size_t eta_tables_floats_kd(int64_t K, int64_t D, int64_t N) {
+    if (K == 3 && D == 2) return eta_tables_floats<3, 2>(N);
+    if (K == 2 && D == 2) return eta_tables_floats<2, 2>(N);
+    if (K == 4 && D == 2) return eta_tables_floats<4, 2>(N);
+    if (K == 3 && D == 1) return eta_tables_floats<3, 1>(N);
+    return 0;
+}
+
+extern "C" size_t apgs_gmm_eta_tables_bytes(int64_t B, int64_t N, int64_t K, int64_t D) {
+    if (B <= 0 || N <= 0) return 0;
+    return (size_t)B * eta_tables_floats_kd(K, D, N) * 4;
+}
+
+extern "C" int apgs_gmm_eta_tables_f32(const float* x, const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                       int64_t B, int64_t N, int64_t K, int64_t D, float* tables, void* stream) {
+    if (B <= 0 || N <= 0 || B > 0x7fffffffLL || N > (1 << 20)) return fail(APGS_E_SHAPE, "gmm_eta_tables: bad sizes");
+    if (!x || !Wg || !bg || !Wo || !bo || !tables) return fail(APGS_E_BADARG, "gmm_eta_tables: NULL pointer");
+    if (!aligned(tables, 16)) return fail(APGS_E_BADARG, "gmm_eta_tables: tables must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 3 && D == 2) return launch_eta_tables<3, 2>(x, Wg, bg, Wo, bo, (int)B, (int)N, tables, st);
+    if (K == 2 && D == 2) return launch_eta_tables<2, 2>(x, Wg, bg, Wo, bo, (int)B, (int)N, tables, st);
+    if (K == 4 && D == 2) return launch_eta_tables<4, 2>(x, Wg, bg, Wo, bo, (int)B, (int)N, tables, st);
+    if (K == 3 && D == 1) return launch_eta_tables<3, 1>(x, Wg, bg, Wo, bo, (int)B, (int)N, tables, st);
+    return fail(APGS_E_UNSUPPORTED, "gmm_eta_tables: (K=%lld, D=%lld) not instantiated", (long long)K, (long long)D);
 }

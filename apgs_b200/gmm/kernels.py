@@ -477,7 +477,28 @@ def _z_step_fused_rng(lib, x, tau, mu, mlp, prior, z_old, want_q, parts, local, 
     return z_new, q, w
 
 
-def eta_posterior_fused(x, z, heads, prior, center=None, z_ancestors=None, center_ancestors=None):
+def eta_tables(x, heads):
+    """Per-instance tables of the eta step (apgs_gmm_eta_tables_f32): Enc_apg_eta's head factors over (point, label) and the
+    points, built once per objective for eta_posterior_fused(..., tables=...) in label mode.  None when (K, D) is not
+    supported by the instance-major statistics kernel."""
+    lib = _lib.load()
+    x = _x3(x)
+    B, N, D = x.shape
+    Wg, bg, Wo, bo = [_req(v, "head weight") for v in heads]
+    K = Wg.shape[0]
+    if tuple(Wg.shape) != (K, D + K) or tuple(Wo.shape) != (D, D + K):
+        raise ValueError("unexpected head weight shapes %s %s" % (tuple(Wg.shape), tuple(Wo.shape)))
+    nbytes = lib.apgs_gmm_eta_tables_bytes(B, N, K, D)
+    if nbytes == 0:
+        return None
+    tables = torch.empty(B, nbytes // (4 * B), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _call("gmm_eta_tables", 1, nbytes):
+        check(lib.apgs_gmm_eta_tables_f32(ptr(x), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), B, N, K, D, ptr(tables), _stream()),
+              "apgs_gmm_eta_tables_f32")
+    return tables
+
+
+def eta_posterior_fused(x, z, heads, prior, center=None, z_ancestors=None, center_ancestors=None, tables=None):
     """N1b+G1: Linear heads of Enc_apg_eta (z given) / Enc_rws_eta (z None) + softmax + NSS posterior.
     heads = (Wg, bg, Wo, bo).  Returns alpha, beta, mu, nu of shape (S,B,K,D) ((1,B,K,D) when z is None).
     With `center` (S,B,K,D; the old mu) the same pass also returns the centred one-hot statistics of z,
@@ -488,8 +509,8 @@ def eta_posterior_fused(x, z, heads, prior, center=None, z_ancestors=None, cente
     x = _x3(x)
     B, N, D = x.shape
     Wg, bg, Wo, bo = [_req(v, "head weight") for v in heads]
-    if (z_ancestors is not None or center_ancestors is not None) and not (z is not None and z.dtype == torch.uint8):
-        raise ValueError("ancestor maps are taken in label mode only")
+    if (z_ancestors is not None or center_ancestors is not None or tables is not None) and not (z is not None and z.dtype == torch.uint8):
+        raise ValueError("ancestor maps / tables are taken in label mode only")
     K = Wg.shape[0]
     if z is not None and z.dtype == torch.uint8:
         # label mode: z (S,B,N) uint8
@@ -511,11 +532,16 @@ def eta_posterior_fused(x, z, heads, prior, center=None, z_ancestors=None, cente
             maps = [None if m is None else _req(m, "ancestor map", dtype=torch.int32, ndim=2) for m in (z_ancestors, center_ancestors)]
             if any(m is not None and tuple(m.shape) != (S, B) for m in maps):
                 raise ValueError("ancestor maps must be (S, B) int32")
-            if maps[0] is not None or maps[1] is not None:
+            if tables is not None:
+                tables = _req(tables, "tables", ndim=2)
+                if tables.shape[0] != B or tables.numel() * 4 != lib.apgs_gmm_eta_tables_bytes(B, N, K, D):
+                    raise ValueError("tables were built for another shape")
+            if maps[0] is not None or maps[1] is not None or tables is not None:
                 check(lib.apgs_gmm_eta_posterior_stats_labels_via_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N,
                                                                       K, D, *[ptr(v) for v in pr], *[ptr(v) for v in outs],
                                                                       ptr(center), ptr(stats), LN, ptr(maps[0]), ptr(maps[1]),
-                                                                      _stream()), "apgs_gmm_eta_posterior_stats_labels_via_f32")
+                                                                      ptr(tables), _stream()),
+                      "apgs_gmm_eta_posterior_stats_labels_via_f32")
             else:
                 check(lib.apgs_gmm_eta_posterior_stats_labels_f32(ptr(x), ptr(z), ptr(Wg), ptr(bg), ptr(Wo), ptr(bo), S, B, N, K, D,
                                                                   *[ptr(v) for v in pr], *[ptr(v) for v in outs], ptr(center),

@@ -155,14 +155,15 @@ class Enc_apg_eta(nn.Module):
         """(Wg, bg, Wo, bo) as the fused kernels take them."""
         return (self.gamma[0].weight, self.gamma[0].bias, self.ob[0].weight, self.ob[0].bias)
 
-    def params(self, ob, z, prior_ng, center=None, z_ancestors=None, center_ancestors=None):
+    def params(self, ob, z, prior_ng, center=None, z_ancestors=None, center_ancestors=None, tables=None):
         """posterior parameters (alpha, beta, mu, nu); with `center` (the old mu) the fused kernel's pass over z also
         returns the centred one-hot statistics of z as a fifth tensor (see kernels.logw_eta_stats).  z_ancestors /
         center_ancestors: read the labels / the centre through ancestor maps (kernels.eta_posterior_fused)."""
         if self.can_fuse():
             return kernels.eta_posterior_fused(ob, z, (self.gamma[0].weight, self.gamma[0].bias,
                                                        self.ob[0].weight, self.ob[0].bias), _PriorNG(prior_ng),
-                                               center=center, z_ancestors=z_ancestors, center_ancestors=center_ancestors)
+                                               center=center, z_ancestors=z_ancestors, center_ancestors=center_ancestors,
+                                               tables=tables)
         xp, gam = self.heads(ob, z)
         return kernels.nss_posterior(xp, gam, _PriorNG(prior_ng))
 

@@ -84,6 +84,10 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
         with torch.no_grad():                    # weights are constant within one objective call (training mode included)
             ztab = kernels.z_tables(x, enc_apg_z.mlp(), generative)
     evaluating = not result_flags['loss_required']
+    etab = None                                  # the same for Enc_apg_eta's head factors over (point, label): kernels.eta_tables
+    if z_tables_per_objective and evaluating and block == 'decomposed' and _eta_fused(enc_apg_eta) and num_sweeps > 1:
+        with torch.no_grad():
+            etab = kernels.eta_tables(x, enc_apg_eta.head_weights())
 
     def resample_and_book(tau, mu, z, log_w, log_q_f):
         """resample_variables + the W1 bookkeeping of the step from the SAME launch: the ancestor kernel's softmax over S
@@ -123,7 +127,8 @@ def apg_objective(models, x, result_flags, num_sweeps, block, resampler):
     for m in range(num_sweeps - 1):
         if block == 'decomposed':
             log_w_eta, tau, mu, trace, log_q_f = _update_eta(enc_apg_eta, generative, x, z, tau, mu, trace, result_flags,
-                                                             defer=True, pre=pre, z_map=z_map, eta_map=eta_map)
+                                                             defer=True, pre=pre, z_map=z_map, eta_map=eta_map,
+                                                             tables=etab if compact else None)
             if gatherless_now:
                 # Gatherless sweep: no latent is moved.  Every block update reads its inputs through ancestor maps --
                 # (tau, mu) made by the eta step through A (this step's resampling), the labels made by the previous z step
@@ -382,14 +387,15 @@ def apg_update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result
 
 
 def _update_eta(enc_apg_eta, generative, x, z, tau_old, mu_old, trace, result_flags, defer=False, pre=None, z_map=None,
-                eta_map=None):
+                eta_map=None, tables=None):
     """z_map / eta_map (S,B) int32 (gatherless sweeps): z and (tau_old, mu_old) are still in the order of the steps that made
     them; particle (s,b) reads them from rows (z_map[s,b], b) / (eta_map[s,b], b)."""
     if _eta_fused(enc_apg_eta):
         if pre is not None:
             post, stats = pre            # emitted by the z step that drew these labels, centred at its mu == mu_old
-        elif z_map is not None or eta_map is not None:
-            *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old, z_ancestors=z_map, center_ancestors=eta_map)
+        elif z_map is not None or eta_map is not None or tables is not None:
+            *post, stats = enc_apg_eta.params(x, z, generative.prior_ng, center=mu_old, z_ancestors=z_map, center_ancestors=eta_map,
+                                              tables=tables)
             post = tuple(post)
         else:
             # one pass over z: posterior parameters + the centred one-hot statistics both log-likelihoods are functions of

@@ -368,7 +368,17 @@ APGS_API int apgs_gmm_eta_posterior_stats_labels_via_f32(const float* x, const u
                                      const float* prior_mu, const float* prior_nu,
                                      float* post_alpha, float* post_beta, float* post_mu, float* post_nu,
                                      const float* center, float* stats, int64_t label_stride,
-                                     const int32_t* z_ancestors, const int32_t* center_ancestors, void* stream);
+                                     const int32_t* z_ancestors, const int32_t* center_ancestors, const float* tables,
+                                     void* stream);
+/* Per-instance tables of the eta step: Enc_apg_eta's two Linear heads on cat(x_n, e_label) (apgs/gmm/models.py:56-65) take
+ *   only K values per data point when z is one-hot; { x'_n, gamma_n } per (point, label) and the points themselves are the
+ *   same for every particle of an instance and every sweep of an objective.  apgs_gmm_eta_tables_f32 writes them once
+ *   (apgs_gmm_eta_tables_bytes(B, N, K, D) bytes, 16-byte aligned; 0: shape not supported) and
+ *   apgs_gmm_eta_posterior_stats_labels_via_f32(tables = ...) fetches an instance's block with one bulk copy per CTA instead
+ *   of tabulating it; tables = NULL: the CTA builds its own.  Bit-identical either way.  Depends on (x, Wg, bg, Wo, bo).  */
+APGS_API size_t apgs_gmm_eta_tables_bytes(int64_t B, int64_t N, int64_t K, int64_t D);
+APGS_API int apgs_gmm_eta_tables_f32(const float* x, const float* Wg, const float* bg, const float* Wo, const float* bo,
+                                     int64_t B, int64_t N, int64_t K, int64_t D, float* tables, void* stream);
 APGS_API int apgs_gmm_draw_logw_eta_stats_rng_via_f32(const float* stats, const float* center, const apgs_gmm_post_t* post,
                                      const apgs_gmm_prior_t* prior, const uint64_t* philox_seed, float* tau, float* mu,
                                      const float* tau_old, const float* mu_old, const int32_t* old_ancestors,

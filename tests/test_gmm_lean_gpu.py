@@ -880,9 +880,16 @@ def test_r2_entries_stay_inside_their_buffers_and_refuse_bad_arguments():
     for name in ("log_w", "log_q_f", "density"):
         eb[name] = guarded(S * B, torch.float32, -7.0)
     pr = [getattr(gen, "prior_" + n) for n in ("alpha", "beta", "mu", "nu")]
+    nbe = lib.apgs_gmm_eta_tables_bytes(B, N, K, D)
+    assert nbe > 0 and nbe % (16 * B) == 0 and lib.apgs_gmm_eta_tables_bytes(B, N, 7, 5) == 0
+    etab = guarded(nbe // 4, torch.float32, -7.0)
+    assert lib.apgs_gmm_eta_tables_f32(ptr(x), *[ptr(h) for h in heads], B, N, K, D, ptr(etab[1]), st) == 0
+    intact({"etab": etab})
+    assert bool(torch.isfinite(etab[1]).all())
+    assert lib.apgs_gmm_eta_tables_f32(ptr(x), *[ptr(h) for h in heads], B, N, K, D, None, st) < 0
     rc = lib.apgs_gmm_eta_posterior_stats_labels_via_f32(ptr(x), ptr(lab), *[ptr(h) for h in heads], S, B, N, K, D,
                                                          *[ptr(v) for v in pr], *[ptr(eb[n][1]) for n in ("pa", "pb", "pm", "pn")],
-                                                         ptr(mu), ptr(eb["stats"][1]), LN, ptr(amap), ptr(bmap), st)
+                                                         ptr(mu), ptr(eb["stats"][1]), LN, ptr(amap), ptr(bmap), ptr(etab[1]), st)
     assert rc == 0, lib.apgs_last_error()
     post = tuple(eb[n][1].view(S, B, K, D) for n in ("pa", "pb", "pm", "pn"))
     ps, keep2 = _post_struct(post)
@@ -896,3 +903,40 @@ def test_r2_entries_stay_inside_their_buffers_and_refuse_bad_arguments():
     intact(eb)
     for name in ("pa", "pb", "pm", "pn", "stats", "tau", "mu", "log_w", "log_q_f", "density"):
         assert bool(torch.isfinite(eb[name][1]).all()) and not bool((eb[name][1] == -7.0).any()), name
+
+
+@pytest.mark.parametrize("S,B,N,K,D", [(1000, 6, 60, 3, 2), (37, 5, 41, 3, 2), (70, 3, 17, 2, 2), (33, 4, 60, 4, 2), (21, 3, 30, 3, 1)])
+def test_eta_statistics_with_per_instance_tables_are_bit_identical(S, B, N, K, D):
+    """kernels.eta_tables: Enc_apg_eta's head factors over (point, label) tabulated once per instance and fetched by the CTAs of
+    the statistics kernel with one bulk copy -- same posterior parameters and statistics as the CTA tabulating them, bit for bit;
+    through apg_objective the traces are identical as well."""
+    from apgs_b200.gmm import kernels, objectives
+    from apgs_b200.resampler import Resampler
+    torch.manual_seed(S + N)
+    P, gen = og.make_params(K, D, 32), _Gen(K, D)
+    x, tau, mu, lab, _ = _latents(S, B, K, D, N, seed=51)
+    xg, mg = x.to(DEV), mu.to(DEV)
+    lg = _pad_labels(lab.to(DEV), LN=(N + 15) // 16 * 16)
+    heads = _heads(P)
+    tab = kernels.eta_tables(xg, heads)
+    assert tab is not None and tab.shape[0] == B
+    a = kernels.eta_posterior_fused(xg, lg, heads, gen, center=mg)
+    b = kernels.eta_posterior_fused(xg, lg, heads, gen, center=mg, tables=tab)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    with pytest.raises(ValueError):
+        kernels.eta_posterior_fused(xg, lg, heads, gen, center=mg, tables=tab[:, :-4].contiguous())
+    if (K, D) == (3, 2) and N == 60:
+        models = _models_from_params(P)
+        xo = og.simulate(16, 60, 3, 2).to(DEV)
+        out = {}
+        for on in (True, False):
+            objectives.z_tables_per_objective = on
+            try:
+                torch.manual_seed(3)
+                with torch.no_grad():
+                    out[on] = objectives.apg_objective(models, xo, BENCH_FLAGS, 4, "decomposed", Resampler("systematic", 100, True, DEV))
+            finally:
+                objectives.z_tables_per_objective = True
+        for k in ("ess", "density", "log_z"):
+            assert torch.equal(out[True][k], out[False][k]), k
