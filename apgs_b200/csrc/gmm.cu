@@ -234,13 +234,13 @@ __global__ void __launch_bounds__(P* LANES, STATS ? 4 : 1) k_gmm_nss_posterior(N
         const float a0 = __ldg(a.ra + e), b0 = __ldg(a.rb + e), m0 = __ldg(a.rm + e), n0 = __ldg(a.rn + e);
         const float cnt = (n1 == 0.f) ? 1.f : n1;                                   // Q1
         const float x_bar = __fdiv_rn(n2, cnt);
-        const float alpha = __fadd_rn(a0, __fdiv_rn(cnt, 2.f));
+        const float alpha = __fadd_rn(a0, __fmul_rn(cnt, 0.5f));
         const float nu = __fadd_rn(n0, cnt);
         const float cn = __fadd_rn(cnt, n0);
         const float mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), n2), cn);
-        const float u1 = __fdiv_rn(__fsub_rn(n3, __fdiv_rn(__fmul_rn(n2, n2), cnt)), 2.f);
+        const float u1 = __fmul_rn(__fsub_rn(n3, __fdiv_rn(__fmul_rn(n2, n2), cnt)), 0.5f);
         const float dx = __fsub_rn(x_bar, n0);                                       // Q2: prior_nu
-        const float u2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
+        const float u2 = __fmul_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 0.5f);
         const float beta = __fadd_rn(__fadd_rn(b0, u1), u2);
         const long long o = (r0 + p) * (K * D) + e;
         a.oa[o] = alpha; a.ob[o] = beta; a.om[o] = mu; a.on[o] = nu;
@@ -666,9 +666,11 @@ __global__ void __launch_bounds__(256) k_gmm_eta_weights_stats(EtaStatsArgs a) {
                 float x0, en;
                 box_muller(w.x, w.y, x0, en);
                 const float g = gamma_mt(qa, x0, w.z, w.w, ctr, key);
-                tf = fmaxf(__fdiv_rn(g, qb), 1.17549435e-38f);
-                const float sc = __fdiv_rn(1.f, __fsqrt_rn(__fmul_rn(qn, tf)));
-                mf = __fadd_rn(__fmul_rn(en, sc), qm);
+                // the stream is not torch's anyway: SFU quotient / reciprocal square root (~2 ulp) instead of the IEEE divide,
+                // square root and divide of the explicit-variate path (their slow-path branches cost ~10 % of this kernel)
+                tf = fmaxf(__fdividef(g, qb), 1.17549435e-38f);
+                const float sc = rsqrtf(__fmul_rn(qn, tf));
+                mf = fmaf(en, sc, qm);
                 a.tau_out[r * KD + e] = tf;
                 a.mu_out[r * KD + e] = mf;
             } else {

@@ -296,13 +296,13 @@ __device__ __forceinline__ void ng_posterior_elem(float f1, float f2, float f3, 
                                                   float& alpha, float& beta, float& mu, float& nu) {
     const float cnt = (f1 == 0.f) ? 1.f : f1;                                   // Q1
     const float x_bar = __fdiv_rn(f2, cnt);
-    alpha = __fadd_rn(a0, __fdiv_rn(cnt, 2.f));
+    alpha = __fadd_rn(a0, __fmul_rn(cnt, 0.5f));                                // x / 2 == x * 0.5 exactly (no IEEE-division slow path)
     nu = __fadd_rn(n0, cnt);
     const float cn = __fadd_rn(cnt, n0);
     mu = __fdiv_rn(__fadd_rn(__fmul_rn(m0, n0), f2), cn);
-    const float u1 = __fdiv_rn(__fsub_rn(f3, __fdiv_rn(__fmul_rn(f2, f2), cnt)), 2.f);
+    const float u1 = __fmul_rn(__fsub_rn(f3, __fdiv_rn(__fmul_rn(f2, f2), cnt)), 0.5f);
     const float dx = __fsub_rn(x_bar, n0);                                       // Q2: prior_nu
-    const float u2 = __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 2.f);
+    const float u2 = __fmul_rn(__fmul_rn(__fdiv_rn(__fmul_rn(cnt, n0), cn), __fmul_rn(dx, dx)), 0.5f);
     beta = __fadd_rn(__fadd_rn(b0, u1), u2);
 }
 
