@@ -377,7 +377,8 @@ def gmm_roofline(prof, S, B, peak, peak_src, clocks, distinct_frac, probe, dev):
     ach = fma_ops / (zf["ms_avg"] * 1e-3) / 1e12
     tot = max(1e-9, sum(q["calls"] * q["ms_avg"] for q in prof.values()))
     roof = {"kernel": "k_gmm_z_fused (fused Enc_apg_z MLP + softmax + draw + z-step weight): the step-dominant kernel",
-            "bound": "fp32 FMA pipe (compute; neither hbm nor tensor -- nothing on the path is a dense contraction)",
+            "bound": "fp32 FMA pipe / instruction issue (compute; neither hbm nor tensor -- nothing on the path is a dense "
+                     "contraction; packed FFMA2 / FMUL2 take two issue slots, see mlp_loop_alone)",
             "achieved": ach, "peak": peak_fma, "unit": "T lane-cycles/s of the fp32 FMA pipe (inner loop: 3.5 per tanh term)",
             "frac": ach / peak_fma, "traffic": None,
             "traffic_note": "DRAM bytes are not measurable inside the run; see ncu_capture (the committed ncu --set full capture "
