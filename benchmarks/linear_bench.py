@@ -1,0 +1,43 @@
+"""Enc_coor's Linear(4761 -> 400) + ReLU at the C4 shape (M = S*B = 640): the 3xTF32 tensor-core kernel against torch's fp32
+linear (cuBLAS SIMT sgemm): ms per call and the error against an fp64 product."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from apgs_b200.bmnist import kernels  # noqa: E402
+
+DEV = "cuda:0"
+M, K, N = (int(v) for v in (sys.argv[1:4] if len(sys.argv) >= 4 else (640, 4761, 400)))
+
+
+def timed(fn, iters=30, warm=5):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
+torch.manual_seed(0)
+x = torch.softmax(torch.randn(M, K, device=DEV) * 3, -1)
+w = torch.randn(N, K, device=DEV) / K ** 0.5
+b = torch.randn(N, device=DEV)
+ref = (x.double() @ w.double().t() + b.double()).clamp_min(0)
+mag = x.double().abs() @ w.double().abs().t() + b.double().abs()
+ours = kernels.linear_tf32x3(x, w, b, relu=True)
+th = torch.relu(torch.nn.functional.linear(x, w, b))
+row = {"M": M, "K": K, "N": N,
+       "tf32x3_ms": timed(lambda: kernels.linear_tf32x3(x, w, b, relu=True)),
+       "torch_fp32_ms": timed(lambda: torch.relu(torch.nn.functional.linear(x, w, b))),
+       "tf32x3_err": float(((ours.double() - ref).abs() / mag).max()), "torch_fp32_err": float(((th.double() - ref).abs() / mag).max())}
+row["TFLOPs_effective"] = 2.0 * M * K * N / row["tf32x3_ms"] / 1e9
+print(json.dumps(row))

@@ -597,6 +597,17 @@ APGS_API int apgs_bmnist_paste_subtract_f32(const float* frame, int64_t frame_st
                                    const float* z_where, const float* lin_fp,
                                    int64_t S, int64_t B, int64_t FP, int64_t DP, float* out, void* stream);
 
+/* out (M,N) = act(x (M,K) W (N,K)^T + bias (N)), act = ReLU when relu != 0: nn.Linear (+ nn.ReLU) for the one dense contraction
+ *   on the bouncing-MNIST path, Enc_coor.enc_hidden = Linear(4761 -> 400) + ReLU on the softmax of the template-match map
+ *   (apgs/bmnist/models.py:13-16,28; 150 calls per 5-sweep objective with M = S*B rows).  Tensor cores with fp32-level
+ *   accuracy: 3xTF32 error compensation (operands split into two TF32 halves in registers, three mma.sync.m16n8k8 per
+ *   product, fp32 accumulation) and deterministic split-K over the SMs (partial tiles in `workspace`,
+ *   apgs_linear_tf32x3_workspace_bytes(M, N, K) bytes, summed in a fixed order by a second launch).  Rows need only
+ *   4-byte alignment.  Results agree with an fp32 GEMM to ~1e-6 of sum_k |x_k w_k| (tests/test_bmnist_gpu.py).            */
+APGS_API size_t apgs_linear_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
+APGS_API int apgs_linear_tf32x3_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N,
+                                    int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* N3  bmnist template matching (apgs/bmnist/objectives.py:72-74):
  *     conv2d(frame_left (1, S*B, FP, FP), template_k (S*B, 1, DP, DP), groups = S*B) -> (S, B, CP*CP), CP = FP-DP+1,
  *     i.e. image (s,b) cross-correlated with ITS OWN template, optionally followed by the softmax over the CP*CP scores.

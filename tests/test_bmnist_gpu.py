@@ -424,3 +424,50 @@ def test_stn_bilinear_mode_vs_torch_grid_sample(S, B, T, K):
     torch.testing.assert_close(out, ref_crop, rtol=1e-5, atol=2e-6)
     # the default stays the reference's nearest mode
     assert Affine_Transformer(FP, DP, True, DEV).mode == "nearest"
+
+
+@pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (37, 4761, 400), (64, 100, 80), (130, 1029, 161), (1, 33, 7)])
+def test_linear_tf32x3_matches_fp64_like_an_fp32_gemm(M, K, N):
+    """apgs_linear_tf32x3_f32 (Enc_coor's Linear(4761 -> 400) + ReLU on the tensor cores): the error against an fp64 product is
+    of the order of an fp32 GEMM's own (<= 3e-6 of sum_k |x_k w_k| + |b|, and within 3x of torch's fp32 GEMM on the same inputs), for ragged M / N / K, with and without bias / ReLU;
+    deterministic from call to call."""
+    from apgs_b200.bmnist import kernels
+    torch.manual_seed(M + K)
+    x = torch.softmax(torch.randn(M, K) * 3, -1) if K > 1000 else torch.randn(M, K)
+    w = torch.randn(N, K) / K ** 0.5
+    b = torch.randn(N)
+    xg, wg, bg = x.to(DEV), w.to(DEV), b.to(DEV)
+    ref = x.double() @ w.double().t() + b.double()
+    mag = x.double().abs() @ w.double().abs().t() + b.double().abs()
+    out = kernels.linear_tf32x3(xg, wg, bg, relu=False)
+    assert tuple(out.shape) == (M, N)
+    err = ((out.cpu().double() - ref).abs() / mag).max()
+    f32 = ((torch.nn.functional.linear(xg, wg, bg).cpu().double() - ref).abs() / mag).max()
+    assert float(err) <= 3e-6 and float(err) <= 3 * float(f32) + 1e-7, (float(err), float(f32))
+    out_r = kernels.linear_tf32x3(xg, wg, bg, relu=True)
+    assert torch.equal(out_r, out.clamp_min(0)) and torch.equal(out_r, kernels.linear_tf32x3(xg, wg, bg, relu=True))
+    nb = kernels.linear_tf32x3(xg, wg, None)
+    assert float(((nb.cpu().double() - (ref - b.double())).abs() / mag).max()) <= 3e-6
+    # leading dimensions are kept
+    if M % 2 == 0:
+        assert torch.equal(kernels.linear_tf32x3(xg.view(2, M // 2, K), wg, bg), out.view(2, M // 2, N))
+
+
+def test_enc_coor_uses_the_tensor_core_layer_and_matches_the_torch_modules():
+    from apgs_b200.bmnist import models as M
+    torch.manual_seed(0)
+    enc = M.Enc_coor(4761, 400, 2).to(DEV)
+    conved = torch.softmax(torch.randn(10, 64, 4761, device=DEV) * 2, -1)
+    with torch.no_grad():
+        mean, std = enc.params(conved)
+        M.Enc_coor.fused = False
+        try:
+            mean_t, std_t = enc.params(conved)
+        finally:
+            M.Enc_coor.fused = True
+    assert float((mean - mean_t).abs().max()) <= 2e-6 and float(((std - std_t).abs() / std_t).max()) <= 1e-5
+    # training mode keeps the differentiable torch modules
+    for p in enc.parameters():
+        p.requires_grad_(True)
+    m2, _ = enc.params(conved)
+    assert m2.requires_grad
