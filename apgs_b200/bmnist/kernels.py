@@ -124,24 +124,28 @@ def _dense_images(t, name):
     return t.detach()
 
 
-def linear_tf32x3(x, weight, bias=None, relu=False):
-    """act(x W^T + b) on the tensor cores with fp32-level accuracy (apgs_linear_tf32x3_f32: 3xTF32 error compensation, split-K):
-    x (..., K), weight (N, K), bias (N) -> (..., N).  Forward values only (no autograd graph)."""
+def _linear(x, weight, bias, relu, which):
     lib = _lib.load()
     x = _req(x, "x")
     w = _req(weight, "weight", ndim=2)
     b = _req(bias, "bias", ndim=1) if bias is not None else None
     N, K = w.shape
     if x.shape[-1] != K or (b is not None and b.numel() != N):
-        raise ValueError("linear_tf32x3: x %s, weight %s, bias %s do not match" % (tuple(x.shape), tuple(w.shape), None if b is None else tuple(b.shape)))
+        raise ValueError("linear: x %s, weight %s, bias %s do not match" % (tuple(x.shape), tuple(w.shape), None if b is None else tuple(b.shape)))
     M = x.numel() // K
     out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
-    nws = lib.apgs_linear_tf32x3_workspace_bytes(M, N, K)
+    wsb, fn, name = lib.apgs_linear_tf32x3_workspace_bytes, lib.apgs_linear_tf32x3_f32, "apgs_linear_tf32x3_f32"
+    nws = wsb(M, N, K)
     ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device), _call("linear_tf32x3", 2, 4 * (M * K + N * K + M * N)):
-        check(lib.apgs_linear_tf32x3_f32(ptr(x), ptr(w), ptr(b), M, K, N, 1 if relu else 0, ptr(out), ptr(ws), nws, _stream()),
-              "apgs_linear_tf32x3_f32")
+    with torch.cuda.device(x.device), _call("linear_" + which, 2, 4 * (M * K + N * K + M * N)):
+        check(fn(ptr(x), ptr(w), ptr(b), M, K, N, 1 if relu else 0, ptr(out), ptr(ws), nws, _stream()), name)
     return out
+
+
+def linear_tf32x3(x, weight, bias=None, relu=False):
+    """act(x W^T + b) on the tensor cores with fp32-level accuracy (apgs_linear_tf32x3_f32: 3xTF32 error compensation, split-K):
+    x (..., K), weight (N, K), bias (N) -> (..., N).  Forward values only (no autograd graph)."""
+    return _linear(x, weight, bias, relu, "tf32x3")
 
 
 def template_match(frame, template, softmax=True):

@@ -426,7 +426,7 @@ def test_stn_bilinear_mode_vs_torch_grid_sample(S, B, T, K):
     assert Affine_Transformer(FP, DP, True, DEV).mode == "nearest"
 
 
-@pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (37, 4761, 400), (64, 100, 80), (130, 1029, 161), (1, 33, 7)])
+@pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (37, 4761, 400), (64, 100, 80), (130, 1029, 161), (1, 33, 7), (257, 513, 83)])
 def test_linear_tf32x3_matches_fp64_like_an_fp32_gemm(M, K, N):
     """apgs_linear_tf32x3_f32 (Enc_coor's Linear(4761 -> 400) + ReLU on the tensor cores): the error against an fp64 product is
     of the order of an fp32 GEMM's own (<= 3e-6 of sum_k |x_k w_k| + |b|, and within 3x of torch's fp32 GEMM on the same inputs), for ragged M / N / K, with and without bias / ReLU;
