@@ -34,6 +34,7 @@ KEYS = [("FFMA2/FMUL2/FADD2", lambda o: o.split(".")[0] in ("FFMA2", "FMUL2", "F
         ("LDGSTS (cp.async)", lambda o: o.startswith("LDGSTS")), ("UBLKCP (cp.async.bulk)", lambda o: o.startswith("UBLKCP")),
         ("LDS", lambda o: o.startswith("LDS")), ("STS", lambda o: o.startswith("STS")), ("SHFL", lambda o: o.startswith("SHFL")),
         ("ATOM/RED", lambda o: o.startswith("ATOM") or o.startswith("RED")), ("BAR/SYNCS", lambda o: o.startswith("BAR") or o.startswith("SYNCS")),
+        ("HMMA (mma.sync)", lambda o: o.startswith("HMMA") or o.startswith("IMMA") or o.startswith("DMMA")),
         ("UTMALDG/UTMASTG", lambda o: o.startswith("UTMALDG") or o.startswith("UTMASTG")), ("UTC*MMA/LDTM (tcgen05)", lambda o: o.startswith("UTC") or o.startswith("LDTM") or o.startswith("STTM"))]
 tot = collections.Counter()
 with open(os.path.join(ROOT, "profiles", "%s_sass_summary.md" % tag), "w") as f:
@@ -52,6 +53,7 @@ with open(os.path.join(ROOT, "profiles", "%s_sass_summary.md" % tag), "w") as f:
     f.write("Reading: the compute-bound kernels (`k_gmm_z_fused`, `k_gmm_nss_im`, the DMM encoders) run on packed fp32x2 (`FFMA2`/`FMUL2`) "
             "with `MUFU.RCP`/`EX2`/`LG2`; row staging uses the bulk-copy engine (`UBLKCP` = `cp.async.bulk.shared::cluster.global`) and "
             "`LDGSTS` (`cp.async`); the gather moves 16-byte vectors (`LDG.E.128` / `STG.E.128`).  There is no tensor-map TMA (`UTMALDG` / `UTMASTG`; the `UTMACMDFLUSH` that appears in a few kernels is the commit of `cp.async.bulk` stores) and no "
-            "tcgen05 (`UTC*MMA`, `LDTM`): nothing on the path is a dense contraction (north_star), and the row-granular TMA gather was measured "
-            "slower than LDG/STG (DESIGN.md section 4).  No atomics: every reduction is ordered (deterministic).\n")
+            "tcgen05 (`UTC*MMA`, `LDTM`): nothing on the section-8a path is a dense contraction (north_star), and the row-granular TMA gather was "
+            "measured slower than LDG/STG (DESIGN.md section 4).  The one tensor-core kernel is `k_linear_tf32x3` (bmnist's Enc_coor layer: "
+            "`HMMA.1688.F32.TF32` = `mma.sync.m16n8k8.tf32`, 3xTF32 error compensation).  No atomics: every reduction is ordered (deterministic).\n")
 print(open(os.path.join(ROOT, "profiles", "%s_sass_summary.md" % tag)).read()[-1500:])
