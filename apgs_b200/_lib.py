@@ -89,6 +89,8 @@ SIGNATURES = {
     "apgs_bmnist_paste_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_bmnist_paste_ll_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "apgs_bmnist_paste_subtract_f32": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _i64, _i64, _i64, _p, _p]),
+    "apgs_linear_tc5_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "apgs_linear_tc5_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "apgs_linear_tf32x3_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "apgs_linear_tf32x3_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "apgs_bmnist_template_match_f32": (_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _p]),

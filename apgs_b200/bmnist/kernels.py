@@ -134,7 +134,8 @@ def _linear(x, weight, bias, relu, which):
         raise ValueError("linear: x %s, weight %s, bias %s do not match" % (tuple(x.shape), tuple(w.shape), None if b is None else tuple(b.shape)))
     M = x.numel() // K
     out = torch.empty(tuple(x.shape[:-1]) + (N,), dtype=torch.float32, device=x.device)
-    wsb, fn, name = lib.apgs_linear_tf32x3_workspace_bytes, lib.apgs_linear_tf32x3_f32, "apgs_linear_tf32x3_f32"
+    wsb, fn, name = ((lib.apgs_linear_tc5_workspace_bytes, lib.apgs_linear_tc5_f32, "apgs_linear_tc5_f32") if which == "tc5" else
+                     (lib.apgs_linear_tf32x3_workspace_bytes, lib.apgs_linear_tf32x3_f32, "apgs_linear_tf32x3_f32"))
     nws = wsb(M, N, K)
     ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device), _call("linear_" + which, 2, 4 * (M * K + N * K + M * N)):
@@ -146,6 +147,12 @@ def linear_tf32x3(x, weight, bias=None, relu=False):
     """act(x W^T + b) on the tensor cores with fp32-level accuracy (apgs_linear_tf32x3_f32: 3xTF32 error compensation, split-K):
     x (..., K), weight (N, K), bias (N) -> (..., N).  Forward values only (no autograd graph)."""
     return _linear(x, weight, bias, relu, "tf32x3")
+
+
+def linear_tc5(x, weight, bias=None, relu=False):
+    """act(x W^T + b) as 3xTF32 through tcgen05 (apgs_linear_tc5_f32: tcgen05.mma kind::tf32 on shared-memory operand halves,
+    accumulator in tensor memory, deterministic split-K) -- the faster form on B200.  Forward values only."""
+    return _linear(x, weight, bias, relu, "tc5")
 
 
 def template_match(frame, template, softmax=True):

@@ -31,12 +31,14 @@ class Enc_coor(nn.Module):
                                            nn.Linear(int(0.5 * num_hidden), z_where_dim))
 
     fused = True          # evaluation path: the 4761 -> 400 layer on the tensor cores (3xTF32, csrc/linear_tf32x3.cu)
+    linear_kernel = "tc5"  # "tc5": tcgen05.mma kind::tf32, accumulator in tensor memory; "mma": warp-level mma.sync
 
     def params(self, conved):
         lin = self.enc_hidden[0]
         if self.fused and conved.is_cuda and not needs_grad(self) and conved.dtype == torch.float32 and lin.in_features >= 1024:
             from . import kernels
-            hidden = kernels.linear_tf32x3(conved, lin.weight, lin.bias, relu=True)      # Linear + ReLU, fp32-level accuracy
+            fn = kernels.linear_tc5 if self.linear_kernel == "tc5" else kernels.linear_tf32x3
+            hidden = fn(conved, lin.weight, lin.bias, relu=True)                          # Linear + ReLU, fp32-level accuracy
         else:
             hidden = self.enc_hidden(conved)
         return self.where_mean(hidden), self.where_log_std(hidden).exp()

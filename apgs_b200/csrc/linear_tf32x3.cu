@@ -204,3 +204,193 @@ extern "C" int apgs_linear_tf32x3_f32(const float* x, const float* W, const floa
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same 3xTF32 product on the 5th-generation tensor cores: tcgen05.mma kind::tf32 issued by one thread, operand halves as
+// separate shared-memory tiles (K-major, no swizzle: core matrices of 8 rows x 16 bytes, 128 bytes apart along K, 1 KB apart
+// along the rows), accumulator (128 x 80 fp32) in tensor memory, read back with tcgen05.ld for the split-K partial tile.
+// CTA tile 128 x 80, K chunks of 32 in two stages: all four warps stage a chunk (scalar loads -- rows are only 4-byte
+// aligned -- split into TF32 halves in registers, one 16-byte store per core-matrix row), fence to the async proxy, one
+// thread issues 12 MMAs and commits them to the stage's mbarrier, which releases the stage two chunks later.
+namespace apgs {
+
+#define APGS_TC5_CTAS 2
+constexpr int kTBM = 128, kTBN = 80, kTBK = 32, kTThreads = 128, kTCols = 128;
+constexpr int kTKH = kTBK / 16;                                                  // 16-k halves per chunk
+constexpr int kTRounds = (kTBM / 8 + kTBN / 8) * kTKH / 4;                       // staging rounds per warp and chunk
+constexpr int kTSBO = kTBK / 4 * 128;                                            // bytes between 8-row groups of an operand tile
+constexpr int kTABytes = kTBM * kTBK * 4, kTBBytes = kTBN * kTBK * 4;            // one half (hi or lo) of a stage
+constexpr int kTStage = 2 * kTABytes + 2 * kTBBytes;                             // A_hi | A_lo | B_hi | B_lo
+
+__device__ __forceinline__ unsigned long long umma_desc(unsigned int smem_addr) {
+    // K-major, SWIZZLE_NONE: leading (K) byte offset 128, stride (8-row group) byte offset 1024, descriptor version 1 (sm_100)
+    return (unsigned long long)((smem_addr >> 4) & 0x3FFFu) | (8ull << 16) | ((unsigned long long)(kTSBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(unsigned int tmem_d, unsigned long long a, unsigned long long b, unsigned int idesc, unsigned int acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+// bounded wait: a malformed descriptor must end in an error code, not in a hung GPU
+__device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned int parity) {
+    for (int it = 0; it < (1 << 22); ++it) {
+        unsigned int ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kTThreads) k_linear_tc5(const float* __restrict__ x, const float* __restrict__ W, int M, int N, int K,
+                                                          int k_per_split, float* __restrict__ partial, int* __restrict__ err) {
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    __shared__ unsigned long long bars[2];
+    __shared__ unsigned int tmem_slot;
+    const int n0 = (int)blockIdx.x * kTBN, m0 = (int)blockIdx.y * kTBM, split = (int)blockIdx.z;
+    const int kb = split * k_per_split, ke = min(K, kb + k_per_split);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kTCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned int tmem = tmem_slot;
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 80, M = 128
+    constexpr unsigned int idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned int)(kTBN >> 3) << 17) | ((unsigned int)(kTBM >> 4) << 24);
+
+    const int row8 = lane & 7, kg = lane >> 3;                      // a warp fills 8 rows x 16 k per round: one 16-byte store per lane
+    const int nchunks = (ke - kb + kTBK - 1) / kTBK;
+    bool ok = true;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int s = ch & 1, k0 = kb + ch * kTBK;
+        unsigned char* st = tsm + (size_t)s * kTStage;
+        // ---- global -> registers: rounds of (8 rows x 16 k): lane -> (row lane & 7, four consecutive k of group lane >> 3), so a
+        // lane owns one 16-byte row of a core matrix and stores it with one 16-byte store (a per-core-matrix mapping with
+        // 4-byte stores and four times fewer sectors per load measured slower: 0.098 vs 0.089 ms).  A: 16 row groups x 2 halves of
+        // the chunk, B: 10 x 2: 52 rounds, 13 per warp.
+        float v[kTRounds][4];
+#pragma unroll
+        for (int it = 0; it < kTRounds; ++it) {
+            const int rd = warp + 4 * it;                            // round index
+            const bool isA = rd < kTBM / 8 * kTKH;
+            const int q = isA ? rd : rd - kTBM / 8 * kTKH;
+            const int rg = q / kTKH, half = q % kTKH;                // row group, which 16 k of the chunk
+            const int r = rg * 8 + row8, kk = k0 + half * 16 + kg * 4;
+            const bool rok = isA ? (m0 + r < M) : (n0 + r < N);
+            const float* src = (isA ? x + (size_t)(m0 + r) * K : W + (size_t)(n0 + r) * K) + kk;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[it][i] = (rok && kk + i < ke) ? __ldg(src + i) : 0.f;
+        }
+        // ---- the stage must have been released by the MMAs of chunk ch - 2
+        if (ch >= 2) ok = ok && mbar_wait_bounded(&bars[s], (unsigned int)(((ch >> 1) - 1) & 1));
+#pragma unroll
+        for (int it = 0; it < kTRounds; ++it) {
+            const int rd = warp + 4 * it;
+            const bool isA = rd < kTBM / 8 * kTKH;
+            const int q = isA ? rd : rd - kTBM / 8 * kTKH;
+            const int rg = q / kTKH, half = q % kTKH;
+            unsigned int hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(v[it][i], hi[i], lo[i]);
+            unsigned char* base = st + (isA ? 0 : 2 * kTABytes);
+            const int half_bytes = isA ? kTABytes : kTBBytes;
+            const int off = rg * kTSBO + (half * 4 + kg) * 128 + row8 * 16;
+            *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(base + half_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned int a_hi = smem_u32(st), a_lo = a_hi + kTABytes, b_hi = a_hi + 2 * kTABytes, b_lo = b_hi + kTBBytes;
+#pragma unroll
+            for (int j = 0; j < kTBK / 8; ++j) {                            // one MMA covers 8 k = two core-matrix columns = 256 bytes
+                const unsigned int o = (unsigned int)j * 256u;
+                umma_tf32(tmem, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (ch > 0 || j > 0) ? 1u : 0u);
+                umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1u);
+                umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+        }
+    }
+    // ---- all MMAs done: the last commit arrives after every earlier one
+    if (nchunks > 0) {
+        const int last = nchunks - 1;
+        ok = ok && mbar_wait_bounded(&bars[last & 1], (unsigned int)((last >> 1) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok && tid == 0 && err != nullptr) atomicExch(err, 1);
+    // ---- accumulator rows 32 w .. 32 w + 31 belong to warp w: 80 fp32 columns, 16 at a time
+    float* out = partial + (size_t)split * M * N;
+    const int r = m0 + warp * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < kTBN; c0 += 16) {
+        unsigned int d[16];
+        if (nchunks > 0 && ok) {
+            const unsigned int taddr = tmem + ((unsigned int)(warp * 32) << 16) + (unsigned int)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+                           "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = 0u;
+        }
+        if (r < M) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (n0 + c0 + i < N) out[(size_t)r * N + n0 + c0 + i] = __uint_as_float(d[i]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTCols) : "memory");
+}
+
+static int linear_tc5_splits(long long M, long long N, long long K) {
+    const long long tiles = ((M + kTBM - 1) / kTBM) * ((N + kTBN - 1) / kTBN);
+    long long s = ((long long)APGS_TC5_CTAS * sm_count() + tiles - 1) / tiles;   // CTAs per SM the shared-memory stages allow
+    const long long smax = (K + 4 * kTBK - 1) / (4 * kTBK);
+    if (s > smax) s = smax;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    return (int)s;
+}
+
+}  // namespace apgs
+
+extern "C" size_t apgs_linear_tc5_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return (size_t)apgs::linear_tc5_splits(M, N, K) * (size_t)M * (size_t)N * sizeof(float) + 256;     // + the error word
+}
+
+extern "C" int apgs_linear_tc5_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N, int relu,
+                                   float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace apgs;
+    if (M <= 0 || N <= 0 || K <= 0 || M >= (1ll << 24) || N >= (1ll << 24) || K >= (1ll << 30))
+        return fail(APGS_E_SHAPE, "linear_tc5: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
+    if (!x || !W || !out) return fail(APGS_E_BADARG, "linear_tc5: NULL pointer");
+    const int splits = linear_tc5_splits(M, N, K);
+    const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float) + 256;
+    if (!workspace || workspace_bytes < need)
+        return fail(APGS_E_WORKSPACE, "linear_tc5: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+    int kps = (int)((K + splits - 1) / splits);
+    kps = (kps + kTBK - 1) / kTBK * kTBK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)2 * kTStage + 1024;
+    APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_linear_tc5), smem), "smem attr");
+    float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+    int* err = reinterpret_cast<int*>(workspace);
+    APGS_CUDA_OK(cudaMemsetAsync(err, 0, sizeof(int), st), "memset");
+    dim3 grid((unsigned int)((N + kTBN - 1) / kTBN), (unsigned int)((M + kTBM - 1) / kTBM), (unsigned int)splits);
+    k_linear_tc5<<<grid, kTThreads, smem, st>>>(x, W, (int)M, (int)N, (int)K, kps, part, err);
+    APGS_LAUNCH_OK("k_linear_tc5 launch");
+    const long long MN = (long long)M * N;
+    k_linear_reduce<<<(unsigned int)((MN + 255) / 256), 256, 0, st>>>(part, bias, MN, (int)N, splits, relu, out);
+    APGS_LAUNCH_OK("k_linear_reduce launch");
+    return 0;
+}

@@ -7,6 +7,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from apgs_b200 import _lib  # noqa: E402
+if os.environ.get("APGS_LIB"):
+    _lib.LIB_PATH = os.path.abspath(os.environ["APGS_LIB"])
 from apgs_b200.bmnist import kernels  # noqa: E402
 
 DEV = "cuda:0"
@@ -35,7 +38,10 @@ ref = (x.double() @ w.double().t() + b.double()).clamp_min(0)
 mag = x.double().abs() @ w.double().abs().t() + b.double().abs()
 ours = kernels.linear_tf32x3(x, w, b, relu=True)
 th = torch.relu(torch.nn.functional.linear(x, w, b))
-row = {"M": M, "K": K, "N": N,
+tc5 = kernels.linear_tc5(x, w, b, relu=True)
+torch.cuda.synchronize()
+row = {"M": M, "K": K, "N": N, "tc5_ms": timed(lambda: kernels.linear_tc5(x, w, b, relu=True)),
+       "tc5_err": float(((tc5.double() - ref).abs() / mag).max()),
        "tf32x3_ms": timed(lambda: kernels.linear_tf32x3(x, w, b, relu=True)),
        "torch_fp32_ms": timed(lambda: torch.relu(torch.nn.functional.linear(x, w, b))),
        "tf32x3_err": float(((ours.double() - ref).abs() / mag).max()), "torch_fp32_err": float(((th.double() - ref).abs() / mag).max())}

@@ -604,6 +604,13 @@ APGS_API int apgs_bmnist_paste_subtract_f32(const float* frame, int64_t frame_st
  *   product, fp32 accumulation) and deterministic split-K over the SMs (partial tiles in `workspace`,
  *   apgs_linear_tf32x3_workspace_bytes(M, N, K) bytes, summed in a fixed order by a second launch).  Rows need only
  *   4-byte alignment.  Results agree with an fp32 GEMM to ~1e-6 of sum_k |x_k w_k| (tests/test_bmnist_gpu.py).            */
+/* The same 3xTF32 product through tcgen05 (5th-generation tensor cores): tcgen05.mma kind::tf32 on shared-memory operand halves,
+ *   fp32 accumulator in tensor memory, split-K with the same deterministic reduction.  Workspace:
+ *   apgs_linear_tc5_workspace_bytes(M, N, K).  Returns through the same status codes; an MMA pipeline that does not
+ *   complete raises an error word in the workspace instead of hanging (checked by the host wrapper).                    */
+APGS_API size_t apgs_linear_tc5_workspace_bytes(int64_t M, int64_t N, int64_t K);
+APGS_API int apgs_linear_tc5_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N,
+                                 int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);
 APGS_API size_t apgs_linear_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 APGS_API int apgs_linear_tf32x3_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N,
                                     int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);

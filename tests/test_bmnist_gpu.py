@@ -427,6 +427,30 @@ def test_stn_bilinear_mode_vs_torch_grid_sample(S, B, T, K):
 
 
 @pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (37, 4761, 400), (64, 100, 80), (130, 1029, 161), (1, 33, 7), (257, 513, 83)])
+def test_linear_tcgen05_matches_fp64_like_an_fp32_gemm(M, K, N):
+    """apgs_linear_tc5_f32 (3xTF32 through tcgen05.mma, accumulator in tensor memory): fp32-GEMM accuracy against an fp64 product
+    for ragged M / N / K (tiles of 128 x 80, K slices of 32), with / without bias and ReLU, deterministic."""
+    from apgs_b200.bmnist import kernels
+    torch.manual_seed(M + K + 2)
+    x = torch.softmax(torch.randn(M, K) * 3, -1) if K > 1000 else torch.randn(M, K)
+    w = torch.randn(N, K) / K ** 0.5
+    b = torch.randn(N)
+    xg, wg, bg = x.to(DEV), w.to(DEV), b.to(DEV)
+    ref = x.double() @ w.double().t() + b.double()
+    mag = x.double().abs() @ w.double().abs().t() + b.double().abs()
+    out = kernels.linear_tc5(xg, wg, bg)
+    assert tuple(out.shape) == (M, N) and bool(torch.isfinite(out).all())
+    err = float(((out.cpu().double() - ref).abs() / mag).max())
+    f32 = float(((torch.nn.functional.linear(xg, wg, bg).cpu().double() - ref).abs() / mag).max())
+    assert err <= 4e-6 and err <= 4 * f32 + 5e-7, (err, f32)
+    assert torch.equal(kernels.linear_tc5(xg, wg, bg, relu=True), out.clamp_min(0))
+    assert torch.equal(kernels.linear_tc5(xg, wg, bg), out)
+    assert float(((kernels.linear_tc5(xg, wg, None).cpu().double() - (ref - b.double())).abs() / mag).max()) <= 4e-6
+    # agrees with the warp-level MMA form of the same 3xTF32 product
+    assert float(((out - kernels.linear_tf32x3(xg, wg, bg)).abs().cpu().double() / mag).max()) <= 4e-6
+
+
+@pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (37, 4761, 400), (64, 100, 80), (130, 1029, 161), (1, 33, 7), (257, 513, 83)])
 def test_linear_tf32x3_matches_fp64_like_an_fp32_gemm(M, K, N):
     """apgs_linear_tf32x3_f32 (Enc_coor's Linear(4761 -> 400) + ReLU on the tensor cores): the error against an fp64 product is
     of the order of an fp32 GEMM's own (<= 3e-6 of sum_k |x_k w_k| + |b|, and within 3x of torch's fp32 GEMM on the same inputs), for ragged M / N / K, with and without bias / ReLU;
@@ -465,7 +489,14 @@ def test_enc_coor_uses_the_tensor_core_layer_and_matches_the_torch_modules():
             mean_t, std_t = enc.params(conved)
         finally:
             M.Enc_coor.fused = True
-    assert float((mean - mean_t).abs().max()) <= 2e-6 and float(((std - std_t).abs() / std_t).max()) <= 1e-5
+    assert float((mean - mean_t).abs().max()) <= 3e-6 and float(((std - std_t).abs() / std_t).max()) <= 1e-5
+    M.Enc_coor.linear_kernel = "mma"
+    try:
+        with torch.no_grad():
+            mean_x, std_x = enc.params(conved)
+    finally:
+        M.Enc_coor.linear_kernel = "tc5"
+    assert float((mean_x - mean_t).abs().max()) <= 3e-6 and float(((std_x - std_t).abs() / std_t).max()) <= 1e-5
     # training mode keeps the differentiable torch modules
     for p in enc.parameters():
         p.requires_grad_(True)
