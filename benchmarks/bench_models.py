@@ -127,13 +127,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tasks", default="gmm,dmm,bmnist", help="comma-separated subset (the ncu captures of the C3 / C4 kernels)")
     a = ap.parse_args()
+    tasks = set(a.tasks.split(","))
     torch.cuda.set_device(DEV)
     if WORLD > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=DEV)
     rows = []
     for fn, args in ((gmm, (10, 20, 5, 20)), (gmm, (1000, 1024, 10, 16)), (dmm, (100, 256, 7, 8)), (bmnist, (10, 64, 5, 2))):
+        if fn.__name__ not in tasks:
+            continue
         torch.manual_seed(1000 + RANK)                       # every rank owns different instances
         r = fn(*args, a.no_cpu or WORLD > 1 or RANK != 0)
         if WORLD > 1:                                        # slowest rank, N times the work (weak scaling along B)

@@ -21,6 +21,14 @@ ncu -i "$out/${tag}_probe.ncu-rep" --page raw --csv > "$out/${tag}_raw_probe.csv
 python benchmarks/zbwd_bench.py > "$out/${tag}_zbwd.json" 2>&1 && \
 ncu --set full --clock-control none -k regex:'k_gmm_z_logq_bwd|k_label_table|k_gmm_z_fused' --launch-skip 8 --launch-count 4 -f -o "$out/${tag}_train" python benchmarks/zbwd_bench.py > "$out/${tag}_ncu_train.log" 2>&1
 ncu -i "$out/${tag}_train.ncu-rep" --page raw --csv > "$out/${tag}_raw_train.csv" 2>/dev/null
+# 5. the dominant kernels of the other two tasks (C3 DMM, C4 bmnist): launch list + one capture per kernel name
+for task in dmm bmnist; do
+  mcmd="python benchmarks/bench_models.py --no-cpu --tasks $task"
+  $mcmd > "$out/${tag}_${task}.json" 2>&1 || { echo "$task bench failed without ncu"; continue; }
+  ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 600 -c 1500 --csv --log-file "$out/${task}_launches.csv" $mcmd > "$out/${tag}_ncu_${task}_list.log" 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'k_dmm|k_template_match|k_linear_tc5|k_linear_reduce|k_stn|k_logw_wh' --launch-skip 100 --launch-count 30 -f -o "$out/${tag}_${task}" $mcmd > "$out/${tag}_ncu_${task}.log" 2>&1
+  ncu -i "$out/${tag}_${task}.ncu-rep" --page raw --csv > "$out/${tag}_raw_${task}.csv" 2>/dev/null
+done
 # the reports themselves exceed what gpurun copies back; the CSV exports are what is summarised
 rm -f "$out"/*.ncu-rep
 ls -la "$out"

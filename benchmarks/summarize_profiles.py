@@ -5,6 +5,7 @@ reads  gpurun_out/bench_launches.csv       ncu --metrics gpu__time_duration.sum 
        gpurun_out/<tag>_raw_bench.csv      `ncu -i prof.ncu-rep --page raw --csv` of the --set full capture inside bench.py
        gpurun_out/<tag>_raw_probe.csv      the same for benchmarks/probe_gather.py (all-distinct resample probe)
        gpurun_out/<tag>_raw_train.csv      the same for benchmarks/zbwd_bench.py (training-mode kernels), if present
+       gpurun_out/<tag>_raw_{dmm,bmnist}.csv  the same for benchmarks/bench_models.py --tasks dmm | bmnist (C3 / C4 kernels), if present
 (the .ncu-rep files are exported to CSV on the GPU box: they exceed what gpurun copies back)
 writes profiles/<tag>_launch_list.md, profiles/<tag>_ncu_kernels.md, profiles/ncu_bench_traffic.json
 """
@@ -73,7 +74,9 @@ with open(os.path.join(PR, "%s_ncu_kernels.md" % tag), "w") as f:
     for part, cmd in (("bench", "python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras  (GMM S=1000, B=1024, in-step kernels)"),
                       ("probe", "python benchmarks/probe_gather.py  (all-distinct resample probe: reference layout 1540 B per particle, "
                                 "near-uniform weights, L2 flushed)"),
-                      ("train", "python benchmarks/zbwd_bench.py  (training-mode kernels at S=1000, B=1024)")):
+                      ("train", "python benchmarks/zbwd_bench.py  (training-mode kernels at S=1000, B=1024)"),
+                      ("dmm", "python benchmarks/bench_models.py --no-cpu --tasks dmm  (C3 DMM S=100, B=256, 7 sweeps)"),
+                      ("bmnist", "python benchmarks/bench_models.py --no-cpu --tasks bmnist  (C4 bmnist S=10, B=64, T=10, 5 sweeps)")):
         path = os.path.join(GO, "%s_raw_%s.csv" % (tag, part))
         if not os.path.exists(path):
             continue
