@@ -155,10 +155,67 @@ def linear_tc5(x, weight, bias=None, relu=False):
     return _linear(x, weight, bias, relu, "tc5")
 
 
-def template_match(frame, template, softmax=True):
+class PackedRows:
+    """A (rows, K) fp32 matrix held as the packed TF32 hi / lo operand of apgs_linear_tc5_packed_f32 (include/apgs_b200.h,
+    csrc/tf32_pack.cuh): what template_match(..., packed=True) returns and linear_tc5_packed consumes.  `lead` is the leading
+    shape of the rows ((S, B) for the template-match map)."""
+
+    def __init__(self, buf, lead, K, which):
+        self.buf, self.lead, self.K, self.which = buf, tuple(lead), int(K), int(which)
+        self.rows = 1
+        for n in self.lead:
+            self.rows *= int(n)
+
+    def unpack(self):
+        """the matrix as an ordinary (..., K) fp32 tensor (hi + lo: exact to ~2^-22 relative) -- tests and fallbacks"""
+        TR = 128 if self.which == 0 else 80
+        nch = (self.K + 31) // 32
+        t = self.buf.view(-1, nch, 2, TR // 8, 8, 8, 4)                  # (row tile, chunk, half, 8-row group, k group, row, k)
+        full = (t[:, :, 0] + t[:, :, 1]).permute(0, 2, 4, 1, 3, 5).reshape(-1, nch * 32)
+        return full[:self.rows, :self.K].reshape(self.lead + (self.K,)).contiguous()
+
+
+def pack_rows(x, which):
+    """x (..., K) fp32 -> PackedRows (apgs_linear_tc5_pack_f32); which = 0: activations (128-row tiles), 1: weights (80-row tiles)."""
+    lib = _lib.load()
+    x = _req(x, "x")
+    K = x.shape[-1]
+    rows = x.numel() // K
+    nbytes = lib.apgs_linear_tc5_packed_bytes(rows, K, which)
+    buf = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _call("linear_tc5_pack", 1, 4 * rows * K + nbytes):
+        check(lib.apgs_linear_tc5_pack_f32(ptr(x), rows, K, K, which, ptr(buf), _stream()), "apgs_linear_tc5_pack_f32")
+    return PackedRows(buf, x.shape[:-1], K, which)
+
+
+def linear_tc5_packed(xp, wp, bias=None, relu=False):
+    """act(x W^T + b) from packed operands (PackedRows which=0 / which=1): apgs_linear_tc5_packed_f32 -- a stage of the GEMM is
+    two bulk copies, warp-specialised tcgen05 pipeline; bit-identical to linear_tc5 on the same matrices."""
+    lib = _lib.load()
+    if not (isinstance(xp, PackedRows) and isinstance(wp, PackedRows)) or xp.which != 0 or wp.which != 1 or xp.K != wp.K:
+        raise ValueError("linear_tc5_packed: PackedRows activations (which=0) and weights (which=1) of equal K required")
+    b = _req(bias, "bias", ndim=1) if bias is not None else None
+    M, N, K = xp.rows, wp.rows, xp.K
+    if b is not None and b.numel() != N:
+        raise ValueError("linear_tc5_packed: bias %s does not match N = %d" % (tuple(b.shape), N))
+    out = torch.empty(xp.lead + (N,), dtype=torch.float32, device=xp.buf.device)
+    nws = lib.apgs_linear_tc5_packed_workspace_bytes(M, N, K)
+    ws = torch.empty(nws, dtype=torch.uint8, device=xp.buf.device)
+    with torch.cuda.device(xp.buf.device), _call("linear_tc5_packed", 2, xp.buf.numel() * 4 + wp.buf.numel() * 4 + 4 * M * N):
+        check(lib.apgs_linear_tc5_packed_f32(ptr(xp.buf), ptr(wp.buf), ptr(b), M, K, N, 1 if relu else 0, ptr(out), ptr(ws), nws,
+                                             _stream()), "apgs_linear_tc5_packed_f32")
+    return out
+
+
+def template_match_supports_packed(FP, DP):
+    return FP == 96 and DP == 28
+
+
+def template_match(frame, template, softmax=True, packed=False):
     """N3: per-(s,b) cross-correlation of frame (S,B,FP,FP) with template (S,B,DP,DP) -> (S,B,CP*CP), CP = FP-DP+1,
     followed by the softmax over the scores (apgs/bmnist/objectives.py:72-74).  Strided views (frames[:, :, t],
-    template[:, :, k], S-expanded frames) are read in place."""
+    template[:, :, k], S-expanded frames) are read in place.  packed=True: the softmax map as PackedRows (the operand layout of
+    Enc_coor's tensor-core layer; FP = 96, DP = 28)."""
     lib = _lib.load()
     f, t = _dense_images(frame, "frame"), _dense_images(template, "template")
     S, B, FP, _ = f.shape
@@ -166,6 +223,16 @@ def template_match(frame, template, softmax=True):
     if tuple(t.shape) != (S, B, DP, DP) or f.shape[-2] != FP or DP > FP:
         raise ValueError("frame %s / template %s shapes do not match" % (tuple(f.shape), tuple(t.shape)))
     CP = FP - DP + 1
+    if packed:                                      # softmax written as the packed activation operand of linear_tc5_packed
+        if not softmax:
+            raise ValueError("template_match: packed output is the softmax map")
+        nbytes = lib.apgs_linear_tc5_packed_bytes(S * B, CP * CP, 0)
+        buf = torch.empty(nbytes // 4, dtype=torch.float32, device=f.device)
+        with torch.cuda.device(f.device), _call("bmnist_template_match", 1, 4 * S * B * (FP * FP + DP * DP) + nbytes):
+            check(lib.apgs_bmnist_template_match_packed_f32(ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),
+                                                            S, B, FP, DP, ptr(buf), _stream()),
+                  "apgs_bmnist_template_match_packed_f32")
+        return PackedRows(buf, (S, B), CP * CP, 0)
     out = torch.empty(S, B, CP * CP, dtype=torch.float32, device=f.device)
     with torch.cuda.device(f.device), _call("bmnist_template_match", 1, 4 * S * B * (FP * FP + DP * DP + CP * CP)):
         check(lib.apgs_bmnist_template_match_f32(ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),

@@ -31,13 +31,41 @@ class Enc_coor(nn.Module):
                                            nn.Linear(int(0.5 * num_hidden), z_where_dim))
 
     fused = True          # evaluation path: the 4761 -> 400 layer on the tensor cores (3xTF32, csrc/linear_tf32x3.cu)
-    linear_kernel = "tc5"  # "tc5": tcgen05.mma kind::tf32, accumulator in tensor memory; "mma": warp-level mma.sync
+    linear_kernel = "tc5pk"  # "tc5pk": tcgen05 from packed operands (weights packed once, activations written packed by the
+    #                          template-match kernel); "tc5": tcgen05, operands staged through registers; "mma": warp-level mma.sync
+
+    def _fusable(self):
+        return self.fused and not needs_grad(self) and self.enc_hidden[0].in_features >= 1024
+
+    def wants_packed(self, FP, DP):
+        """True when params() takes the template-match map as kernels.PackedRows (objectives._propose asks before matching)."""
+        from . import kernels
+        lin = self.enc_hidden[0]
+        return (self._fusable() and self.linear_kernel == "tc5pk" and lin.weight.is_cuda and lin.weight.dtype == torch.float32
+                and kernels.template_match_supports_packed(FP, DP) and lin.in_features == (FP - DP + 1) ** 2)
+
+    def packed_weight(self):
+        """the first layer's weight as the packed TF32 operand, rebuilt when the parameter changes (in-place updates bump
+        `_version`; a new storage changes `data_ptr`)"""
+        from . import kernels
+        w = self.enc_hidden[0].weight
+        key = (w.data_ptr(), w._version, w.device)
+        cache = getattr(self, "_wpack", None)
+        if cache is None or cache[0] != key:
+            cache = (key, kernels.pack_rows(w.detach(), 1))
+            self._wpack = cache
+        return cache[1]
 
     def params(self, conved):
+        from . import kernels
         lin = self.enc_hidden[0]
-        if self.fused and conved.is_cuda and not needs_grad(self) and conved.dtype == torch.float32 and lin.in_features >= 1024:
-            from . import kernels
-            fn = kernels.linear_tc5 if self.linear_kernel == "tc5" else kernels.linear_tf32x3
+        if isinstance(conved, kernels.PackedRows):
+            if self._fusable() and self.linear_kernel == "tc5pk":
+                hidden = kernels.linear_tc5_packed(conved, self.packed_weight(), lin.bias, relu=True)
+                return self.where_mean(hidden), self.where_log_std(hidden).exp()
+            conved = conved.unpack()
+        if self._fusable() and conved.is_cuda and conved.dtype == torch.float32:
+            fn = kernels.linear_tf32x3 if self.linear_kernel == "mma" else kernels.linear_tc5
             hidden = fn(conved, lin.weight, lin.bias, relu=True)                          # Linear + ReLU, fp32-level accuracy
         else:
             hidden = self.enc_hidden(conved)

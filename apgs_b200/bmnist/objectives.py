@@ -76,9 +76,11 @@ def _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t
     S, B, K, DP, _ = template.shape
     zs, means, stds = [], [], []
     frame_left = frame
+    packed = enc_coor.wants_packed(FP, DP)
     for k in range(K):
         template_k = template[:, :, k, :, :]
-        conved_k = kernels.template_match(frame_left, template_k)          # conv2d(groups=S*B) + softmax (:72-74)
+        # conv2d(groups=S*B) + softmax (:72-74); written as the packed operand of Enc_coor's tensor-core layer when it takes one
+        conved_k = kernels.template_match(frame_left, template_k, packed=packed)
         q_mean, q_std = enc_coor.params(conved_k)
         z_where_k = normal_sample(q_mean.detach(), q_std.detach())
         zs.append(z_where_k.unsqueeze(2)); means.append(q_mean.unsqueeze(2)); stds.append(q_std.unsqueeze(2))

@@ -17,6 +17,7 @@
 //     stall = math-pipe throttle: FFMA2 occupies the FMA pipe for two cycles, so the packed form moves the limit from
 //     issue to the pipe without raising throughput -- the scalar form is kept.
 #include "common.cuh"
+#include "tf32_pack.cuh"
 
 namespace apgs {
 
@@ -27,6 +28,7 @@ struct MatchArgs {
     long long ts, tb;
     float* out;                // (S*B, CP*CP)
     int S, B, FP, DP, softmax;
+    int packed;                // out is the packed TF32 hi / lo operand of k_linear_tc5pk (tf32_pack.cuh) instead of (S*B, CP*CP)
 };
 
 __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max) {
@@ -92,9 +94,34 @@ __global__ void __launch_bounds__(224, 5) k_template_match(MatchArgs a) {
             for (int c = 0; c < SEG; ++c) { acc[c] = expf(acc[c] - mx); se += acc[c]; }
         }
         se = block_reduce(se, s_red, false);
+        // The normalised row goes through shared memory (the image is no longer needed: both reductions have passed a CTA
+        // barrier behind the main loop), so that global memory sees whole lines instead of 23 scalar stores per thread at a
+        // lane stride of 69 floats (0.137 -> ... ms per call at the C4 shape).
+        constexpr int NCH = (CP * CP + 31) / 32;                        // 32-column chunks of the packed operand
+        static_assert(NCH * 32 <= FP * FS, "the row fits the image region");
+        float* s_row = s_f;
         if (live) {
+            const int k0 = i0 * CP + seg * SEG;                          // lanes: consecutive i0 -> stride 69 = 5 mod 32: no bank conflicts
 #pragma unroll
-            for (int c = 0; c < SEG; ++c) o[c] = __fdiv_rn(acc[c], se);
+            for (int c = 0; c < SEG; ++c) s_row[k0 + c] = __fdiv_rn(acc[c], se);
+        }
+        for (int k = CP * CP + (int)threadIdx.x; k < NCH * 32; k += blockDim.x) s_row[k] = 0.f;
+        __syncthreads();
+        if (!a.packed) {
+            float* orow = a.out + (size_t)img * CP * CP;
+            for (int k = threadIdx.x; k < CP * CP; k += blockDim.x) orow[k] = s_row[k];
+        } else {
+            // the next consumer is Enc_coor's Linear(CP*CP -> 400) on the tensor cores: the row already split into TF32 halves
+            // and in the MMA's shared-memory order (tf32_pack.cuh), so that the GEMM's stages are plain bulk copies.  One
+            // 16-byte store per (group of four columns, half); columns up to the chunk boundary are written as zeros.
+            for (int g = threadIdx.x; g < NCH * 8; g += blockDim.x) {
+                const float4 v = *reinterpret_cast<const float4*>(s_row + 4 * g);
+                unsigned int h0, h1, h2, h3, l0, l1, l2, l3;
+                split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
+                float* d = a.out + packed_index(kPackRowsX, img, 4 * g, NCH);
+                *reinterpret_cast<uint4*>(d) = make_uint4(h0, h1, h2, h3);
+                *reinterpret_cast<uint4*>(d + kPackRowsX * 32) = make_uint4(l0, l1, l2, l3);
+            }
         }
     } else if (live) {
 #pragma unroll
@@ -137,18 +164,20 @@ __global__ void __launch_bounds__(256) k_template_match_generic(MatchArgs a) {
 
 using namespace apgs;
 
-extern "C" int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
-                                              const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
-                                              int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax, float* out,
-                                              void* stream) {
+static int template_match_launch(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b, const float* tmpl,
+                                 int64_t tmpl_stride_s, int64_t tmpl_stride_b, int64_t S, int64_t B, int64_t FP, int64_t DP,
+                                 int softmax, int packed, float* out, void* stream) {
     if (S <= 0 || B <= 0 || FP <= 0 || DP <= 0 || DP > FP || S * B > 0x7fffffffLL)
-        return fail(APGS_E_SHAPE, "bmnist_template_match: bad sizes S=%lld B=%lld FP=%lld DP=%lld", (long long)S,
-                    (long long)B, (long long)FP, (long long)DP);
+        return fail(APGS_E_SHAPE, "bmnist_template_match: bad sizes S=%lld B=%lld FP=%lld DP=%lld", (long long)S, (long long)B,
+                    (long long)FP, (long long)DP);
     if (!frame || !tmpl || !out) return fail(APGS_E_BADARG, "bmnist_template_match: NULL pointer");
     if (frame_stride_s < 0 || frame_stride_b < 0 || tmpl_stride_s < 0 || tmpl_stride_b < 0)
         return fail(APGS_E_BADARG, "bmnist_template_match: negative stride");
+    if (packed && !(FP == 96 && DP == 28))
+        return fail(APGS_E_UNSUPPORTED, "bmnist_template_match_packed: compiled for FP=96, DP=28 only (got %lld, %lld)", (long long)FP,
+                    (long long)DP);
     MatchArgs a = {frame, (long long)frame_stride_s, (long long)frame_stride_b, tmpl, (long long)tmpl_stride_s,
-                   (long long)tmpl_stride_b, out, (int)S, (int)B, (int)FP, (int)DP, softmax};
+                   (long long)tmpl_stride_b, out, (int)S, (int)B, (int)FP, (int)DP, softmax, packed};
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned int grid = (unsigned int)(S * B);
     if (FP == 96 && DP == 28) {
@@ -163,4 +192,21 @@ extern "C" int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_
     }
     APGS_LAUNCH_OK("k_template_match launch");
     return 0;
+}
+
+extern "C" int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                              const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                              int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax, float* out,
+                                              void* stream) {
+    return template_match_launch(frame, frame_stride_s, frame_stride_b, tmpl, tmpl_stride_s, tmpl_stride_b, S, B, FP, DP, softmax, 0,
+                                 out, stream);
+}
+
+extern "C" int apgs_bmnist_template_match_packed_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                                     const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                                     int64_t S, int64_t B, int64_t FP, int64_t DP, float* out_packed,
+                                                     void* stream) {
+    if (out_packed && !aligned(out_packed, 16)) return fail(APGS_E_BADARG, "bmnist_template_match_packed: out must be 16-byte aligned");
+    return template_match_launch(frame, frame_stride_s, frame_stride_b, tmpl, tmpl_stride_s, tmpl_stride_b, S, B, FP, DP, 1, 1,
+                                 out_packed, stream);
 }

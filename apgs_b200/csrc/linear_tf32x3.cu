@@ -18,6 +18,7 @@
 // operand halves materialised as separate shared-memory tiles).
 #include <stdlib.h>
 #include "tile.cuh"
+#include "tf32_pack.cuh"
 
 namespace apgs {
 
@@ -26,15 +27,6 @@ constexpr int kLBM = 64, kLBN = 80, kLBK = 32, kLPad = 36, kLThreads = 128;
 #define APGS_LIN_CTAS_PER_SM 4
 #endif
 
-__device__ __forceinline__ unsigned int to_tf32(float v) {
-    unsigned int r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ void split_tf32(float v, unsigned int& hi, unsigned int& lo) {
-    hi = to_tf32(v);
-    lo = to_tf32(v - __uint_as_float(hi));
-}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned int (&a)[4], const unsigned int (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -150,9 +142,11 @@ __global__ void __launch_bounds__(kLThreads) k_linear_tf32x3(const float* __rest
 }
 
 __global__ void __launch_bounds__(256) k_linear_reduce(const float* __restrict__ partial, const float* __restrict__ bias, long long MN,
-                                                       int N, int splits, int relu, float* __restrict__ out) {
+                                                       int N, int splits, int relu, float* __restrict__ out,
+                                                       const int* __restrict__ err = nullptr) {
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= MN) return;
+    if (err != nullptr && *err != 0) { out[i] = __int_as_float(0x7fc00000); return; }   // an MMA pipeline timed out: NaN, loudly, without a host sync
     float v = bias != nullptr ? __ldg(bias + (int)(i % N)) : 0.f;
     for (int s = 0; s < splits; ++s) v += __ldg(partial + (size_t)s * MN + i);      // fixed order: deterministic
     out[i] = relu ? fmaxf(v, 0.f) : v;
@@ -351,9 +345,131 @@ __global__ void __launch_bounds__(kTThreads) k_linear_tc5(const float* __restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTCols) : "memory");
 }
 
-static int linear_tc5_splits(long long M, long long N, long long K) {
+// ---------------------------------------------------------------------------------------------------------------------------
+// Packed operands (r2): both operands arrive ALREADY split into TF32 halves and laid out tile by tile in the canonical
+// shared-memory order, so a stage is two bulk copies (cp.async.bulk, completion on the stage's mbarrier) and no register
+// ever touches an operand.  The weights are packed once per set of weights (k_pack_rows: they are constant over the 150 calls
+// of an objective), the activations are written in this layout by the kernel that produces them (k_template_match's
+// epilogue).  Layout of a packed matrix of R rows x K columns with TR rows per tile (TR = 128 for x, 80 for W):
+//   tile (rt, c) = rows rt*TR .. rt*TR+TR-1, columns 32c .. 32c+31, stored at float offset (rt * ceil(K/32) + c) * 2*TR*32 as
+//   { hi[TR x 32], lo[TR x 32] }, element (r, k) of a half at ((r % TR) / 8) * 256 + ((k % 32) / 4) * 32 + (r % 8) * 4 + k % 4
+//   (core matrices of 8 rows x 16 bytes, 128 bytes apart along K, 1 KB apart along the rows); rows >= R and columns >= K zero.
+// Warp-specialised: lane 0 of warp 0 issues the copies, lane 0 of warp 1 the MMAs (12 per 32-k chunk, same order as
+// k_linear_tc5: the two kernels give bit-identical results), all four warps read the accumulator out of tensor memory.
+static_assert(kPackRowsX == kTBM && kPackRowsW == kTBN, "packed tiles are the CTA tiles");
+// one thread per (row, group of four columns) of the padded matrix: 16 bytes of hi and 16 bytes of lo
+__global__ void __launch_bounds__(256) k_pack_rows(const float* __restrict__ src, long long R, long long K, long long ld, int TR,
+                                                   float* __restrict__ dst) {
+    const long long nchunks = (K + 31) / 32, kg = nchunks * 8, Rp = (R + TR - 1) / TR * TR;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Rp * kg) return;
+    const long long r = idx / kg, k = (idx % kg) * 4;
+    unsigned int hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32((r < R && k + i < K) ? __ldg(src + r * ld + k + i) : 0.f, hi[i], lo[i]);
+    float* d = dst + packed_index(TR, r, k, nchunks);
+    *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(d + (size_t)TR * 32) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int ST>
+__global__ void __launch_bounds__(kTThreads) k_linear_tc5pk(const float* __restrict__ Ap, const float* __restrict__ Wp, int M, int N,
+                                                            int nchunks_total, int chunks_per_split, float* __restrict__ partial,
+                                                            int* __restrict__ err) {
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    __shared__ unsigned long long full[ST], empty[ST];
+    __shared__ unsigned int tmem_slot;
+    const int n_tile = (int)blockIdx.x, m_tile = (int)blockIdx.y, split = (int)blockIdx.z;
+    const int n0 = n_tile * kTBN, m0 = m_tile * kTBM;
+    const int c0 = split * chunks_per_split;
+    const int nch = max(0, min(nchunks_total, c0 + chunks_per_split) - c0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(kTCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned int tmem = tmem_slot;
+    constexpr unsigned int idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned int)(kTBN >> 3) << 17) | ((unsigned int)(kTBM >> 4) << 24);
+    bool ok = true;
+    if (tid == 0) {                                                          // ---- producer: two bulk copies per stage
+        const float* a_src = Ap + ((size_t)m_tile * nchunks_total + c0) * (size_t)(2 * kTBM * kTBK);
+        const float* b_src = Wp + ((size_t)n_tile * nchunks_total + c0) * (size_t)(2 * kTBN * kTBK);
+        for (int ch = 0; ch < nch && ok; ++ch) {
+            const int s = ch % ST;
+            if (ch >= ST) ok = mbar_wait_bounded(&empty[s], (unsigned int)((ch / ST - 1) & 1));   // released by the MMAs of chunk ch - ST
+            if (!ok) break;
+            unsigned char* st = tsm + (size_t)s * kTStage;
+            mbar_expect_tx(&full[s], (unsigned int)kTStage);
+            bulk_g2s(st, a_src + (size_t)ch * (2 * kTBM * kTBK), 2 * kTABytes, &full[s]);
+            bulk_g2s(st + 2 * kTABytes, b_src + (size_t)ch * (2 * kTBN * kTBK), 2 * kTBBytes, &full[s]);
+        }
+    } else if (tid == 32) {                                                  // ---- MMA issuer
+        for (int ch = 0; ch < nch && ok; ++ch) {
+            const int s = ch % ST;
+            ok = mbar_wait_bounded(&full[s], (unsigned int)((ch / ST) & 1));
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned int a_hi = smem_u32(tsm + (size_t)s * kTStage), a_lo = a_hi + kTABytes, b_hi = a_hi + 2 * kTABytes, b_lo = b_hi + kTBBytes;
+#pragma unroll
+            for (int j = 0; j < kTBK / 8; ++j) {
+                const unsigned int o = (unsigned int)j * 256u;
+                umma_tf32(tmem, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (ch > 0 || j > 0) ? 1u : 0u);
+                umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1u);
+                umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+        }
+    }
+    // The other 126 threads sleep at this barrier until every copy and MMA has been ISSUED.  (A parity wait only distinguishes
+    // adjacent phases: a thread that skipped the loop must not poll the last commit's parity before the barrier has reached
+    // that phase -- it would pass on an earlier phase of the same parity.)
+    __syncwarp();
+    __syncthreads();
+    // ---- all MMAs done: the last commit arrives after every earlier one
+    if (nch > 0) {
+        const int last = nch - 1;
+        ok = mbar_wait_bounded(&empty[last % ST], (unsigned int)((last / ST) & 1)) && ok;
+    }
+    ok = __syncthreads_and(ok ? 1 : 0) != 0;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok && lane == 0 && err != nullptr) atomicExch(err, 1);
+    float* out = partial + (size_t)split * M * N;
+    const int r = m0 + warp * 32 + lane;
+#pragma unroll
+    for (int cc = 0; cc < kTBN; cc += 16) {
+        unsigned int d[16];
+        if (nch > 0 && ok) {
+            const unsigned int taddr = tmem + ((unsigned int)(warp * 32) << 16) + (unsigned int)cc;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+                           "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = 0u;
+        }
+        if (r < M) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (n0 + cc + i < N) out[(size_t)r * N + n0 + cc + i] = __uint_as_float(d[i]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTCols) : "memory");
+}
+
+static int linear_tc5_splits(long long M, long long N, long long K, int ctas_per_sm = APGS_TC5_CTAS) {
     const long long tiles = ((M + kTBM - 1) / kTBM) * ((N + kTBN - 1) / kTBN);
-    long long s = ((long long)APGS_TC5_CTAS * sm_count() + tiles - 1) / tiles;   // CTAs per SM the shared-memory stages allow
+    long long s = ((long long)ctas_per_sm * sm_count()) / tiles;                 // one wave of the CTAs the shared-memory stages allow
     const long long smax = (K + 4 * kTBK - 1) / (4 * kTBK);
     if (s > smax) s = smax;
     if (s < 1) s = 1;
@@ -390,7 +506,78 @@ extern "C" int apgs_linear_tc5_f32(const float* x, const float* W, const float* 
     k_linear_tc5<<<grid, kTThreads, smem, st>>>(x, W, (int)M, (int)N, (int)K, kps, part, err);
     APGS_LAUNCH_OK("k_linear_tc5 launch");
     const long long MN = (long long)M * N;
-    k_linear_reduce<<<(unsigned int)((MN + 255) / 256), 256, 0, st>>>(part, bias, MN, (int)N, splits, relu, out);
+    k_linear_reduce<<<(unsigned int)((MN + 255) / 256), 256, 0, st>>>(part, bias, MN, (int)N, splits, relu, out, err);
+    APGS_LAUNCH_OK("k_linear_reduce launch");
+    return 0;
+}
+
+
+// ---- packed operands (layout above k_pack_rows)
+// 2 stages x 2 CTAs per SM (default): the split-K of apgs_linear_tc5_f32, hence bit-identical to it (0.037 ms per call at the C4
+// shape).  APGS_TC5PK_STAGES=4: 4 stages x 1 CTA per SM, fewer and longer K slices -- 0.033 ms, but the longer fp32 accumulation
+// chains in tensor memory cost accuracy (4.4e-6 of sum|x w| against 2.1e-6), so it stays a measurement knob.
+static int tc5pk_stages() {
+    const char* e = getenv("APGS_TC5PK_STAGES");
+    return (e && atoi(e) == 4) ? 4 : 2;
+}
+
+extern "C" size_t apgs_linear_tc5_packed_bytes(int64_t rows, int64_t K, int which) {
+    if (rows <= 0 || K <= 0 || (which != 0 && which != 1)) return 0;
+    const int64_t TR = which == 0 ? apgs::kTBM : apgs::kTBN;
+    return (size_t)((rows + TR - 1) / TR) * (size_t)((K + 31) / 32) * (size_t)(2 * TR * 32) * sizeof(float);
+}
+
+extern "C" int apgs_linear_tc5_pack_f32(const float* src, int64_t rows, int64_t K, int64_t ld, int which, float* dst, void* stream) {
+    using namespace apgs;
+    if (rows <= 0 || K <= 0 || ld < K || rows >= (1ll << 24) || K >= (1ll << 30) || (which != 0 && which != 1))
+        return fail(APGS_E_SHAPE, "linear_tc5_pack: bad sizes rows=%lld K=%lld ld=%lld which=%d", (long long)rows, (long long)K,
+                    (long long)ld, which);
+    if (!src || !dst) return fail(APGS_E_BADARG, "linear_tc5_pack: NULL pointer");
+    if (!aligned(dst, 16)) return fail(APGS_E_BADARG, "linear_tc5_pack: dst must be 16-byte aligned");
+    const int TR = which == 0 ? kTBM : kTBN;
+    const long long n = (rows + TR - 1) / TR * TR * ((K + 31) / 32) * 8;
+    k_pack_rows<<<(unsigned int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, rows, K, ld, TR, dst);
+    APGS_LAUNCH_OK("k_pack_rows launch");
+    return 0;
+}
+
+extern "C" size_t apgs_linear_tc5_packed_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return (size_t)apgs::linear_tc5_splits(M, N, K, tc5pk_stages() == 4 ? 1 : 2) * (size_t)M * (size_t)N * sizeof(float) + 256;
+}
+
+extern "C" int apgs_linear_tc5_packed_f32(const float* x_packed, const float* w_packed, const float* bias, int64_t M, int64_t K,
+                                          int64_t N, int relu, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace apgs;
+    if (M <= 0 || N <= 0 || K <= 0 || M >= (1ll << 24) || N >= (1ll << 24) || K >= (1ll << 30))
+        return fail(APGS_E_SHAPE, "linear_tc5_packed: bad sizes M=%lld K=%lld N=%lld", (long long)M, (long long)K, (long long)N);
+    if (!x_packed || !w_packed || !out) return fail(APGS_E_BADARG, "linear_tc5_packed: NULL pointer");
+    if (!aligned(x_packed, 16) || !aligned(w_packed, 16))
+        return fail(APGS_E_BADARG, "linear_tc5_packed: packed operands must be 16-byte aligned");
+    const int stages = tc5pk_stages();
+    const int splits = linear_tc5_splits(M, N, K, stages == 4 ? 1 : 2);
+    const size_t need = (size_t)splits * (size_t)M * (size_t)N * sizeof(float) + 256;
+    if (!workspace || workspace_bytes < need)
+        return fail(APGS_E_WORKSPACE, "linear_tc5_packed: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+    int kps = (int)((K + splits - 1) / splits);
+    kps = (kps + kTBK - 1) / kTBK * kTBK;
+    const int nchunks = (int)((K + kTBK - 1) / kTBK);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)stages * kTStage + 1024;
+    float* part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+    int* err = reinterpret_cast<int*>(workspace);
+    APGS_CUDA_OK(cudaMemsetAsync(err, 0, sizeof(int), st), "memset");
+    dim3 grid((unsigned int)((N + kTBN - 1) / kTBN), (unsigned int)((M + kTBM - 1) / kTBM), (unsigned int)splits);
+    if (stages == 4) {
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_linear_tc5pk<4>), smem), "smem attr");
+        k_linear_tc5pk<4><<<grid, kTThreads, smem, st>>>(x_packed, w_packed, (int)M, (int)N, nchunks, kps / kTBK, part, err);
+    } else {
+        APGS_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(k_linear_tc5pk<2>), smem), "smem attr");
+        k_linear_tc5pk<2><<<grid, kTThreads, smem, st>>>(x_packed, w_packed, (int)M, (int)N, nchunks, kps / kTBK, part, err);
+    }
+    APGS_LAUNCH_OK("k_linear_tc5pk launch");
+    const long long MN = (long long)M * N;
+    k_linear_reduce<<<(unsigned int)((MN + 255) / 256), 256, 0, st>>>(part, bias, MN, (int)N, splits, relu, out, err);
     APGS_LAUNCH_OK("k_linear_reduce launch");
     return 0;
 }

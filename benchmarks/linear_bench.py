@@ -30,6 +30,31 @@ def timed(fn, iters=30, warm=5):
     return sorted(ts)[len(ts) // 2]
 
 
+def graph_timed(fn, calls=20, reps=10):
+    """ms per call on the device: `calls` calls captured into one CUDA graph (no host launch overhead in the timed region)"""
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(st)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / calls)
+    return sorted(ts)[len(ts) // 2]
+
+
 torch.manual_seed(0)
 x = torch.softmax(torch.randn(M, K, device=DEV) * 3, -1)
 w = torch.randn(N, K, device=DEV) / K ** 0.5
@@ -45,5 +70,15 @@ row = {"M": M, "K": K, "N": N, "tc5_ms": timed(lambda: kernels.linear_tc5(x, w, 
        "tf32x3_ms": timed(lambda: kernels.linear_tf32x3(x, w, b, relu=True)),
        "torch_fp32_ms": timed(lambda: torch.relu(torch.nn.functional.linear(x, w, b))),
        "tf32x3_err": float(((ours.double() - ref).abs() / mag).max()), "torch_fp32_err": float(((th.double() - ref).abs() / mag).max())}
+xp, wp = kernels.pack_rows(x, 0), kernels.pack_rows(w, 1)
+pk = kernels.linear_tc5_packed(xp, wp, b, relu=True)
+row["tc5_packed_ms"] = timed(lambda: kernels.linear_tc5_packed(xp, wp, b, relu=True))
+row["graph_ms"] = {"tc5": graph_timed(lambda: kernels.linear_tc5(x, w, b, relu=True)),
+                   "tc5_packed": graph_timed(lambda: kernels.linear_tc5_packed(xp, wp, b, relu=True)),
+                   "torch_fp32": graph_timed(lambda: torch.relu(torch.nn.functional.linear(x, w, b)))}
+row["tc5_packed_equals_tc5"] = bool(torch.equal(pk, tc5))
+row["pack_w_ms"] = timed(lambda: kernels.pack_rows(w, 1))
+row["pack_x_ms"] = timed(lambda: kernels.pack_rows(x, 0))
+row["tc5pk_stages"] = int(os.environ.get("APGS_TC5PK_STAGES", "2"))
 row["TFLOPs_effective"] = 2.0 * M * K * N / row["tf32x3_ms"] / 1e9
 print(json.dumps(row))

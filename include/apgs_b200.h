@@ -607,10 +607,26 @@ APGS_API int apgs_bmnist_paste_subtract_f32(const float* frame, int64_t frame_st
 /* The same 3xTF32 product through tcgen05 (5th-generation tensor cores): tcgen05.mma kind::tf32 on shared-memory operand halves,
  *   fp32 accumulator in tensor memory, split-K with the same deterministic reduction.  Workspace:
  *   apgs_linear_tc5_workspace_bytes(M, N, K).  Returns through the same status codes; an MMA pipeline that does not
- *   complete raises an error word in the workspace instead of hanging (checked by the host wrapper).                    */
+ *   complete raises an error word in the workspace instead of hanging, and the reduction launch then writes NaN to `out`. */
 APGS_API size_t apgs_linear_tc5_workspace_bytes(int64_t M, int64_t N, int64_t K);
 APGS_API int apgs_linear_tc5_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N,
                                  int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Packed operands for the tcgen05 form: both operands already split into their TF32 halves and laid out tile by tile in the
+ *   MMA's shared-memory order, so a pipeline stage of the GEMM is two bulk copies and no register touches an operand.
+ *   Layout (apgs_b200/csrc/tf32_pack.cuh): tiles of TR rows x 32 columns, TR = 128 for the activations (which = 0) and 80 for
+ *   the weights (which = 1); tile (rt, c) at float offset (rt * ceil(K/32) + c) * 2*TR*32 as { hi[TR x 32], lo[TR x 32] },
+ *   element (r, k) of a half at ((r % TR) / 8) * 256 + ((k % 32) / 4) * 32 + (r % 8) * 4 + k % 4; columns K .. 32 ceil(K/32) - 1
+ *   are zero.  apgs_linear_tc5_packed_bytes(rows, K, which) is the size of such a buffer (16-byte aligned).
+ *   apgs_linear_tc5_pack_f32 packs a row-major matrix (row stride ld >= K elements): once per set of weights -- Enc_coor's
+ *   weight is constant over the 150 calls of an objective (apgs/bmnist/models.py:13-16) -- while the activations are written in
+ *   this layout by apgs_bmnist_template_match_packed_f32.  apgs_linear_tc5_packed_f32 is then bit-identical to
+ *   apgs_linear_tc5_f32 on the same operands (same MMAs in the same order, same split-K; the measurement knob
+ *   APGS_TC5PK_STAGES=4 selects fewer, longer K slices).  Rows >= `rows` of the last activation tile may hold anything finite. */
+APGS_API size_t apgs_linear_tc5_packed_bytes(int64_t rows, int64_t K, int which);
+APGS_API int apgs_linear_tc5_pack_f32(const float* src, int64_t rows, int64_t K, int64_t ld, int which, float* dst, void* stream);
+APGS_API size_t apgs_linear_tc5_packed_workspace_bytes(int64_t M, int64_t N, int64_t K);
+APGS_API int apgs_linear_tc5_packed_f32(const float* x_packed, const float* w_packed, const float* bias, int64_t M, int64_t K,
+                                        int64_t N, int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);
 APGS_API size_t apgs_linear_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t K);
 APGS_API int apgs_linear_tf32x3_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N,
                                     int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);
@@ -624,6 +640,12 @@ APGS_API int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_st
                                    const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
                                    int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax,
                                    float* out, void* stream);
+/* The same with the softmax written as the packed activation operand of apgs_linear_tc5_packed_f32 (rows = S*B, K = CP*CP,
+ *   which = 0; apgs_linear_tc5_packed_bytes(S*B, CP*CP, 0) bytes): the map only feeds Enc_coor's first layer
+ *   (apgs/bmnist/objectives.py:74-75), so it never exists in fp32.  FP = 96, DP = 28 only (else APGS_E_UNSUPPORTED).        */
+APGS_API int apgs_bmnist_template_match_packed_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                   const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                   int64_t S, int64_t B, int64_t FP, int64_t DP, float* out_packed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -490,15 +490,194 @@ def test_enc_coor_uses_the_tensor_core_layer_and_matches_the_torch_modules():
         finally:
             M.Enc_coor.fused = True
     assert float((mean - mean_t).abs().max()) <= 3e-6 and float(((std - std_t).abs() / std_t).max()) <= 1e-5
-    M.Enc_coor.linear_kernel = "mma"
-    try:
-        with torch.no_grad():
-            mean_x, std_x = enc.params(conved)
-    finally:
-        M.Enc_coor.linear_kernel = "tc5"
-    assert float((mean_x - mean_t).abs().max()) <= 3e-6 and float(((std_x - std_t).abs() / std_t).max()) <= 1e-5
+    default = M.Enc_coor.linear_kernel
+    assert default == "tc5pk"
+    for which in ("mma", "tc5"):
+        M.Enc_coor.linear_kernel = which
+        try:
+            with torch.no_grad():
+                mean_x, std_x = enc.params(conved)
+        finally:
+            M.Enc_coor.linear_kernel = default
+        assert float((mean_x - mean_t).abs().max()) <= 3e-6 and float(((std_x - std_t).abs() / std_t).max()) <= 1e-5
+    # the default form takes the map as the packed operand (what the template-match kernel writes)
+    from apgs_b200.bmnist import kernels
+    with torch.no_grad():
+        mean_p, std_p = enc.params(kernels.pack_rows(conved, 0))
+    assert tuple(mean_p.shape) == tuple(mean_t.shape)
+    assert float((mean_p - mean_t).abs().max()) <= 3e-6 and float(((std_p - std_t).abs() / std_t).max()) <= 1e-5
     # training mode keeps the differentiable torch modules
     for p in enc.parameters():
         p.requires_grad_(True)
     m2, _ = enc.params(conved)
     assert m2.requires_grad
+
+
+def _packed_index(TR, r, k, nch):
+    """csrc/tf32_pack.cuh packed_index, restated"""
+    return ((r // TR) * nch + k // 32) * (2 * TR * 32) + ((r % TR) // 8) * 256 + ((k % 32) // 4) * 32 + (r % 8) * 4 + k % 4
+
+
+def _tf32_rna(v):
+    """cvt.rna.tf32.f32 on a float32 numpy array: round to 10 explicit mantissa bits, ties away from zero"""
+    import numpy as np
+    u = v.astype(np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("rows,K,which", [(200, 100, 0), (81, 33, 1), (640, 4761, 0), (400, 4761, 1)])
+def test_pack_rows_layout_halves_and_padding(rows, K, which):
+    """apgs_linear_tc5_pack_f32: every element sits where csrc/tf32_pack.cuh says, hi is the TF32 rounding of the value, lo the TF32
+    rounding of the exact remainder, padding rows / columns are zero, and PackedRows.unpack() inverts it."""
+    import numpy as np
+    from apgs_b200.bmnist import kernels
+    torch.manual_seed(rows + K)
+    x = torch.randn(rows, K)
+    pk = kernels.pack_rows(x.to(DEV), which)
+    TR, nch = (128, 80)[which], (K + 31) // 32
+    buf = pk.buf.cpu().numpy()
+    assert buf.size == ((rows + TR - 1) // TR) * nch * 2 * TR * 32
+    rng = np.random.default_rng(0)
+    rr = np.concatenate([rng.integers(0, rows, 300), [0, rows - 1]])
+    kk = np.concatenate([rng.integers(0, K, 300), [K - 1, 0]])
+    at = np.array([_packed_index(TR, int(r), int(k), nch) for r, k in zip(rr, kk)])
+    v = x.numpy()[rr, kk]
+    hi = _tf32_rna(v)
+    assert np.array_equal(buf[at], hi)
+    assert np.array_equal(buf[at + TR * 32], _tf32_rna(v - hi))
+    full = np.zeros(buf.size, dtype=bool)                        # every slot not addressed by a real element is zero
+    allr, allk = np.meshgrid(np.arange(rows), np.arange(K), indexing="ij")
+    ia = ((allr // TR) * nch + allk // 32) * (2 * TR * 32) + ((allr % TR) // 8) * 256 + ((allk % 32) // 4) * 32 + (allr % 8) * 4 + allk % 4
+    full[ia.ravel()] = True
+    full[ia.ravel() + TR * 32] = True
+    assert not buf[~full].any()
+    un = pk.unpack().cpu()
+    assert tuple(un.shape) == (rows, K) and float((un - x).abs().max()) <= 2.0 ** -21 * float(x.abs().max())
+
+
+@pytest.mark.parametrize("M,K,N", [(640, 4761, 400), (37, 4761, 400), (64, 100, 80), (130, 1029, 161), (1, 33, 7), (257, 513, 83)])
+def test_linear_tcgen05_from_packed_operands_is_bit_identical(M, K, N, monkeypatch):
+    """apgs_linear_tc5_packed_f32 (stages are bulk copies of pre-split, pre-laid-out tiles; warp-specialised producer / MMA issuer):
+    the same MMAs in the same order and the same split-K as apgs_linear_tc5_f32 -> equal bit for bit, at ragged shapes, with /
+    without bias and ReLU.  The 4-stage geometry (a measurement knob: fewer, longer K slices) is checked at its own accuracy."""
+    from apgs_b200.bmnist import kernels
+    monkeypatch.delenv("APGS_TC5PK_STAGES", raising=False)
+    torch.manual_seed(M + K + 3)
+    x = (torch.softmax(torch.randn(M, K) * 3, -1) if K > 1000 else torch.randn(M, K)).to(DEV)
+    w = (torch.randn(N, K) / K ** 0.5).to(DEV)
+    b = torch.randn(N).to(DEV)
+    xp, wp = kernels.pack_rows(x, 0), kernels.pack_rows(w, 1)
+    out = kernels.linear_tc5_packed(xp, wp, b)
+    assert tuple(out.shape) == (M, N) and bool(torch.isfinite(out).all())
+    assert torch.equal(out, kernels.linear_tc5(x, w, b))
+    assert torch.equal(kernels.linear_tc5_packed(xp, wp, b, relu=True), out.clamp_min(0))
+    assert torch.equal(kernels.linear_tc5_packed(xp, wp, None), kernels.linear_tc5(x, w, None))
+    ref = x.double() @ w.double().t() + b.double()
+    mag = x.double().abs() @ w.double().abs().t() + b.double().abs()
+    assert float(((out.double() - ref).abs() / mag).max()) <= 4e-6
+    xb = x.reshape(1, M, K).expand(2, M, K).contiguous()            # leading shape is kept
+    assert tuple(kernels.linear_tc5_packed(kernels.pack_rows(xb, 0), wp, b).shape) == (2, M, N)
+    # the other geometry: other slices of K, deterministic, accuracy of its longer accumulation chains
+    monkeypatch.setenv("APGS_TC5PK_STAGES", "4")
+    o4 = kernels.linear_tc5_packed(xp, wp, b)
+    assert float(((o4.double() - ref).abs() / mag).max()) <= 8e-6
+    assert torch.equal(o4, kernels.linear_tc5_packed(xp, wp, b))
+    assert torch.equal(kernels.linear_tc5_packed(xp, wp, b, relu=True), o4.clamp_min(0))
+
+
+@pytest.mark.parametrize("S,B", [(10, 64), (3, 5)])
+def test_template_match_writes_the_packed_operand(S, B, monkeypatch):
+    """apgs_bmnist_template_match_packed_f32: the softmax map as TF32 halves in the GEMM's layout equals the fp32 map to the
+    splitting error, padding columns are zero, and Enc_coor's layer on it equals the layer on the fp32 map bit for bit (the
+    register-staged kernel splits the same values the same way)."""
+    from apgs_b200.bmnist import kernels
+    from apgs_b200.bmnist.models import Enc_coor
+    monkeypatch.delenv("APGS_TC5PK_STAGES", raising=False)           # default geometry: the split-K of the register-staged kernel
+    torch.manual_seed(S * 100 + B)
+    FP, DP, T, K = 96, 28, 2, 2
+    frames = torch.rand(S, B, T, FP, FP, device=DEV)
+    tmpl = torch.rand(S, B, K, DP, DP, device=DEV)
+    fmap = kernels.template_match(frames[:, :, 1], tmpl[:, :, 1])                    # strided views
+    pk = kernels.template_match(frames[:, :, 1], tmpl[:, :, 1], packed=True)
+    assert isinstance(pk, kernels.PackedRows) and pk.rows == S * B and pk.K == 4761 and pk.lead == (S, B)
+    un = pk.unpack()
+    assert float((un - fmap).abs().max()) <= 2.0 ** -21 * float(fmap.abs().max())
+    nch = (4761 + 31) // 32
+    t = pk.buf.view(-1, nch, 2, 16, 8, 8, 4)
+    rows_live = torch.arange(t.shape[0] * 128, device=DEV).view(-1, 16, 8) < S * B           # (row tile, group, row)
+    pad = t[:, -1, :, :, 4761 % 32 // 4:, :, :]                                            # k groups holding columns >= 4761 of the last chunk
+    pad = pad[..., 1:] if 4761 % 4 else pad
+    assert not bool(pad.permute(0, 2, 4, 1, 3, 5)[rows_live].any())
+    torch.manual_seed(1)
+    enc = Enc_coor(4761, 400, 2).to(DEV)
+    with torch.no_grad():
+        assert enc.wants_packed(FP, DP)
+        m1, s1 = enc.params(pk)
+        enc.linear_kernel = "tc5"
+        assert not enc.wants_packed(FP, DP)
+        m0, s0 = enc.params(fmap)
+        m2, _ = enc.params(pk)                                                        # PackedRows on a non-packed path: unpacked
+    assert torch.equal(m1, m0) and torch.equal(s1, s0)
+    assert float((m2 - m0).abs().max()) <= 1e-5
+    # the weight cache follows in-place updates of the parameter
+    enc.linear_kernel = "tc5pk"
+    with torch.no_grad():
+        enc.enc_hidden[0].weight.mul_(0.5)
+        m3, _ = enc.params(pk)
+        enc.linear_kernel = "tc5"
+        m4, _ = enc.params(fmap)
+    assert torch.equal(m3, m4) and not torch.equal(m3, m1)
+
+
+def test_packed_operand_kernels_stay_inside_their_buffers():
+    """raw C-ABI calls of the packed-operand entries with every output embedded in sentinel guard bands (no compute-sanitizer
+    on this pool): the pack kernel, the template match writing the packed map from strided views, and the GEMM reading both
+    (ragged M / N / K: 15 rows of a 128-row tile, 7 of an 80-row tile, 25 columns of the last chunk)."""
+    from apgs_b200 import _lib
+    from apgs_b200._lib import ptr
+    lib = _lib.load()
+    S, B, T, K, FP, DP, N = 3, 5, 2, 3, 96, 28, 87
+    CP = FP - DP + 1
+    KK = CP * CP
+    G = 4096
+    torch.manual_seed(5)
+    frames = torch.rand(B, T, FP, FP, device=DEV)
+    tmpl = torch.rand(S, B, K, DP, DP, device=DEV)
+    W = torch.randn(N, KK + 3, device=DEV)[:, :KK] / 69.0                   # row stride ld = K + 3
+    bias = torch.randn(N, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(n, dtype=torch.float32, fill=-7.0):
+        buf = torch.full((n + 2 * G,), fill, device=DEV, dtype=dtype)
+        return buf, buf[G:G + n]
+    na, nw = lib.apgs_linear_tc5_packed_bytes(S * B, KK, 0) // 4, lib.apgs_linear_tc5_packed_bytes(N, KK, 1) // 4
+    assert na == 1 * 149 * 2 * 128 * 32 and nw == 2 * 149 * 2 * 80 * 32
+    ba, ap = guarded(na)
+    bw, wp = guarded(nw)
+    f_t, t_k = frames[:, 1], tmpl[:, :, 2]
+    rc = lib.apgs_bmnist_template_match_packed_f32(ptr(f_t), 0, f_t.stride(0), ptr(t_k), t_k.stride(0), t_k.stride(1), S, B, FP, DP,
+                                                   ptr(ap), st)
+    assert rc == 0, lib.apgs_last_error()
+    rc = lib.apgs_linear_tc5_pack_f32(ptr(W), N, KK, W.stride(0), 1, ptr(wp), st)
+    assert rc == 0, lib.apgs_last_error()
+    nws = lib.apgs_linear_tc5_packed_workspace_bytes(S * B, N, KK)
+    bws, ws = guarded(nws, torch.uint8, 0x5a)
+    bo, out = guarded(S * B * N)
+    # rows >= S*B of the activation tile keep the sentinel: they only reach accumulator rows that are never stored
+    rc = lib.apgs_linear_tc5_packed_f32(ptr(ap), ptr(wp), ptr(bias), S * B, KK, N, 1, ptr(out), ptr(ws), nws, st)
+    assert rc == 0, lib.apgs_last_error()
+    torch.cuda.synchronize()
+    for buf, fill in ((ba, -7.0), (bw, -7.0), (bo, -7.0), (bws, 0x5a)):
+        assert bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all())
+    fmap = torch.empty(S * B * KK, device=DEV)
+    rc = lib.apgs_bmnist_template_match_f32(ptr(f_t), 0, f_t.stride(0), ptr(t_k), t_k.stride(0), t_k.stride(1), S, B, FP, DP, 1,
+                                            ptr(fmap), st)
+    assert rc == 0, lib.apgs_last_error()
+    ref = torch.relu(fmap.view(S * B, KK).double() @ W.double().t() + bias.double())
+    np.testing.assert_allclose(out.view(S * B, N).cpu().numpy(), ref.cpu().numpy(), rtol=0, atol=2e-6)
+    # argument checks
+    assert lib.apgs_linear_tc5_packed_bytes(0, 10, 0) == 0 and lib.apgs_linear_tc5_packed_bytes(10, 10, 2) == 0
+    assert lib.apgs_linear_tc5_pack_f32(ptr(W), N, KK, KK - 1, 1, ptr(wp), st) < 0                       # ld < K
+    assert lib.apgs_linear_tc5_packed_f32(ptr(ap), ptr(wp), ptr(bias), S * B, KK, N, 1, ptr(out), ptr(ws), 16, st) < 0
+    assert lib.apgs_bmnist_template_match_packed_f32(ptr(f_t), 0, f_t.stride(0), ptr(t_k), t_k.stride(0), t_k.stride(1), S, B, 64, 28,
+                                                     ptr(ap), st) == -5                                    # APGS_E_UNSUPPORTED
