@@ -93,6 +93,7 @@ SIGNATURES = {
     "apgs_linear_tc5_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "apgs_linear_tf32x3_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "apgs_linear_tf32x3_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "apgs_bmnist_coor_heads_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "apgs_linear_tc5_packed_bytes": (_sz, [_i64, _i64, _int]),
     "apgs_linear_tc5_pack_f32": (_int, [_p, _i64, _i64, _i64, _int, _p, _p]),
     "apgs_linear_tc5_packed_workspace_bytes": (_sz, [_i64, _i64, _i64]),

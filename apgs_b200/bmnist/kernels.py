@@ -207,6 +207,36 @@ def linear_tc5_packed(xp, wp, bias=None, relu=False):
     return out
 
 
+def coor_heads_weights(w1_mean, b1_mean, w1_std, b1_std):
+    """the first layers of Enc_coor's two heads in apgs_bmnist_coor_heads_f32's layout: (w1t [ceil(H/4)][2 H2][4], b1 [2 H2])"""
+    w = torch.cat([w1_mean.detach(), w1_std.detach()], 0).float()               # (2 H2, H)
+    U, H = w.shape
+    K4 = (H + 3) // 4
+    if K4 * 4 != H:
+        w = torch.nn.functional.pad(w, (0, K4 * 4 - H))
+    return w.view(U, K4, 4).permute(1, 0, 2).contiguous(), torch.cat([b1_mean.detach(), b1_std.detach()], 0).float().contiguous()
+
+
+def coor_heads(hidden, w1t, b1, w2_mean, b2_mean, w2_std, b2_std):
+    """(q_mean, q_std) = (tanh(W2m relu(W1m h + b1m) + b2m), exp(W2s relu(W1s h + b1s) + b2s)) in one launch
+    (apgs_bmnist_coor_heads_f32; apgs/bmnist/models.py:31-32); w1t, b1 from coor_heads_weights.  Forward values only."""
+    lib = _lib.load()
+    h = _req(hidden, "hidden")
+    H = h.shape[-1]
+    M = h.numel() // H
+    w2m, b2m, w2s, b2s = (_req(t, n) for t, n in ((w2_mean, "w2_mean"), (b2_mean, "b2_mean"), (w2_std, "w2_std"), (b2_std, "b2_std")))
+    Z, H2 = w2m.shape
+    if tuple(w1t.shape) != ((H + 3) // 4, 2 * H2, 4) or tuple(b1.shape) != (2 * H2,) or tuple(w2s.shape) != (Z, H2) \
+            or b2m.numel() != Z or b2s.numel() != Z or not w1t.is_contiguous():
+        raise ValueError("coor_heads: weight shapes do not match hidden %s" % (tuple(h.shape),))
+    mean = torch.empty(tuple(h.shape[:-1]) + (Z,), dtype=torch.float32, device=h.device)
+    std = torch.empty_like(mean)
+    with torch.cuda.device(h.device), _call("bmnist_coor_heads", 1, 4 * (M * H + w1t.numel() + 2 * M * Z)):
+        check(lib.apgs_bmnist_coor_heads_f32(ptr(h), ptr(w1t), ptr(b1), ptr(w2m), ptr(b2m), ptr(w2s), ptr(b2s), M, H, H2, Z,
+                                             ptr(mean), ptr(std), _stream()), "apgs_bmnist_coor_heads_f32")
+    return mean, std
+
+
 def template_match_supports_packed(FP, DP):
     return FP == 96 and DP == 28
 

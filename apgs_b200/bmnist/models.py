@@ -56,20 +56,43 @@ class Enc_coor(nn.Module):
             self._wpack = cache
         return cache[1]
 
+    fused_heads = True    # evaluation path: where_mean / where_log_std (+ tanh / exp) in one launch (csrc/bmnist_heads.cu)
+
+    def _heads_fusable(self):
+        m, s = self.where_mean, self.where_log_std
+        return (self.fused_heads and len(m) == 4 and len(s) == 3 and isinstance(m[0], nn.Linear) and isinstance(m[2], nn.Linear)
+                and isinstance(s[0], nn.Linear) and isinstance(s[2], nn.Linear) and isinstance(m[3], nn.Tanh)
+                and m[0].weight.shape == s[0].weight.shape and m[2].weight.shape == s[2].weight.shape
+                and m[0].bias is not None and s[0].bias is not None and m[2].bias is not None and s[2].bias is not None)
+
+    def heads(self, hidden):
+        """(q_mean, q_std) from the hidden layer (models.py:31-32)"""
+        if self._fusable() and hidden.is_cuda and hidden.dtype == torch.float32 and self._heads_fusable():
+            from . import kernels
+            m, s = self.where_mean, self.where_log_std
+            ws = (m[0].weight, m[0].bias, s[0].weight, s[0].bias)
+            key = tuple((w.data_ptr(), w._version) for w in ws) + (m[0].weight.device,)
+            cache = getattr(self, "_hpack", None)
+            if cache is None or cache[0] != key:
+                cache = (key, kernels.coor_heads_weights(*ws))
+                self._hpack = cache
+            w1t, b1 = cache[1]
+            return kernels.coor_heads(hidden, w1t, b1, m[2].weight, m[2].bias, s[2].weight, s[2].bias)
+        return self.where_mean(hidden), self.where_log_std(hidden).exp()
+
     def params(self, conved):
         from . import kernels
         lin = self.enc_hidden[0]
         if isinstance(conved, kernels.PackedRows):
             if self._fusable() and self.linear_kernel == "tc5pk":
-                hidden = kernels.linear_tc5_packed(conved, self.packed_weight(), lin.bias, relu=True)
-                return self.where_mean(hidden), self.where_log_std(hidden).exp()
+                return self.heads(kernels.linear_tc5_packed(conved, self.packed_weight(), lin.bias, relu=True))
             conved = conved.unpack()
         if self._fusable() and conved.is_cuda and conved.dtype == torch.float32:
             fn = kernels.linear_tf32x3 if self.linear_kernel == "mma" else kernels.linear_tc5
             hidden = fn(conved, lin.weight, lin.bias, relu=True)                          # Linear + ReLU, fp32-level accuracy
         else:
             hidden = self.enc_hidden(conved)
-        return self.where_mean(hidden), self.where_log_std(hidden).exp()
+        return self.heads(hidden)
 
     def forward(self, conved, sampled=True, z_where_old=None):
         q = Trace()

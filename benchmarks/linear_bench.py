@@ -80,5 +80,13 @@ row["tc5_packed_equals_tc5"] = bool(torch.equal(pk, tc5))
 row["pack_w_ms"] = timed(lambda: kernels.pack_rows(w, 1))
 row["pack_x_ms"] = timed(lambda: kernels.pack_rows(x, 0))
 row["tc5pk_stages"] = int(os.environ.get("APGS_TC5PK_STAGES", "2"))
+# Enc_coor's two heads on the hidden layer (400 -> 200 -> 2, tanh / exp): one launch against the nn.Sequential modules
+import torch.nn as nn  # noqa: E402
+hm = nn.Sequential(nn.Linear(N, N // 2), nn.ReLU(), nn.Linear(N // 2, 2), nn.Tanh()).to(DEV)
+hs = nn.Sequential(nn.Linear(N, N // 2), nn.ReLU(), nn.Linear(N // 2, 2)).to(DEV)
+w1t, b1 = kernels.coor_heads_weights(hm[0].weight, hm[0].bias, hs[0].weight, hs[0].bias)
+with torch.no_grad():
+    row["graph_ms"]["heads_fused"] = graph_timed(lambda: kernels.coor_heads(tc5, w1t, b1, hm[2].weight, hm[2].bias, hs[2].weight, hs[2].bias))
+    row["graph_ms"]["heads_torch"] = graph_timed(lambda: (hm(tc5), hs(tc5).exp()))
 row["TFLOPs_effective"] = 2.0 * M * K * N / row["tf32x3_ms"] / 1e9
 print(json.dumps(row))

@@ -631,6 +631,16 @@ APGS_API size_t apgs_linear_tf32x3_workspace_bytes(int64_t M, int64_t N, int64_t
 APGS_API int apgs_linear_tf32x3_f32(const float* x, const float* W, const float* bias, int64_t M, int64_t K, int64_t N,
                                     int relu, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Enc_coor's two heads on the hidden layer in one launch (apgs/bmnist/models.py:16-26 definitions, :31-32 forward):
+ *     q_mean (M,Z) = tanh(W2m relu(W1m h + b1m) + b2m),   q_std (M,Z) = exp(W2s relu(W1s h + b1s) + b2s),   h = hidden (M,H)
+ *   w1t: the two first layers concatenated, transposed and 4-k interleaved, [ceil(H/4)][2*H2][4] floats with
+ *     w1t[k4][u][i] = W1cat[u][4*k4 + i], W1cat = [W1m (H2,H); W1s (H2,H)], zero for 4*k4 + i >= H (16-byte aligned; built once
+ *     per set of weights by the host); b1 (2*H2) = [b1m; b1s]; w2_mean / w2_std (Z,H2); b2_mean / b2_std (Z).
+ *   fp32, every sum in a fixed order: agrees with the nn.Sequential modules to the rounding of a different summation order.   */
+APGS_API int apgs_bmnist_coor_heads_f32(const float* hidden, const float* w1t, const float* b1, const float* w2_mean,
+                                        const float* b2_mean, const float* w2_std, const float* b2_std, int64_t M, int64_t H,
+                                        int64_t H2, int64_t Z, float* q_mean, float* q_std, void* stream);
+
 /* N3  bmnist template matching (apgs/bmnist/objectives.py:72-74):
  *     conv2d(frame_left (1, S*B, FP, FP), template_k (S*B, 1, DP, DP), groups = S*B) -> (S, B, CP*CP), CP = FP-DP+1,
  *     i.e. image (s,b) cross-correlated with ITS OWN template, optionally followed by the softmax over the CP*CP scores.

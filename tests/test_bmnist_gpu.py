@@ -681,3 +681,58 @@ def test_packed_operand_kernels_stay_inside_their_buffers():
     assert lib.apgs_linear_tc5_packed_f32(ptr(ap), ptr(wp), ptr(bias), S * B, KK, N, 1, ptr(out), ptr(ws), 16, st) < 0
     assert lib.apgs_bmnist_template_match_packed_f32(ptr(f_t), 0, f_t.stride(0), ptr(t_k), t_k.stride(0), t_k.stride(1), S, B, 64, 28,
                                                      ptr(ap), st) == -5                                    # APGS_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("M,H,H2,Z", [(640, 400, 200, 2), (13, 400, 200, 2), (1, 37, 9, 3), (77, 130, 65, 1)])
+def test_enc_coor_heads_in_one_launch_match_the_modules(M, H, H2, Z):
+    """apgs_bmnist_coor_heads_f32 against the reference's nn.Sequential heads (apgs/bmnist/models.py:16-26,31-32) in fp64 and in
+    torch fp32: tanh(W2 relu(W1 h + b1) + b2) and exp(...), ragged shapes (rows not a multiple of the 8-row tile, H not a multiple
+    of 4, H2 not a multiple of 32), outputs inside their buffers."""
+    import copy
+    import torch.nn as nn
+    from apgs_b200.bmnist import kernels
+    torch.manual_seed(M + H)
+    mean = nn.Sequential(nn.Linear(H, H2), nn.ReLU(), nn.Linear(H2, Z), nn.Tanh()).to(DEV)
+    lstd = nn.Sequential(nn.Linear(H, H2), nn.ReLU(), nn.Linear(H2, Z)).to(DEV)
+    hidden = torch.relu(torch.randn(M, H, device=DEV))
+    w1t, b1 = kernels.coor_heads_weights(mean[0].weight, mean[0].bias, lstd[0].weight, lstd[0].bias)
+    assert tuple(w1t.shape) == ((H + 3) // 4, 2 * H2, 4)
+    with torch.no_grad():
+        qm, qs = kernels.coor_heads(hidden, w1t, b1, mean[2].weight, mean[2].bias, lstd[2].weight, lstd[2].bias)
+        rm32, rs32 = mean(hidden), lstd(hidden).exp()
+        mean64, lstd64 = copy.deepcopy(mean).double(), copy.deepcopy(lstd).double()
+        rm, rs = mean64(hidden.double()), lstd64(hidden.double()).exp()
+    assert tuple(qm.shape) == (M, Z) and tuple(qs.shape) == (M, Z)
+    em, es = float((qm.double() - rm).abs().max()), float(((qs.double() - rs).abs() / rs).max())
+    em32, es32 = float((rm32.double() - rm).abs().max()), float(((rs32.double() - rs).abs() / rs).max())
+    assert em <= 2e-6 and es <= 2e-6, (em, es)
+    assert em <= 4 * em32 + 3e-7 and es <= 4 * es32 + 3e-7, (em, em32, es, es32)
+    # leading shape kept; deterministic
+    if M % 2 == 0:
+        q2, _ = kernels.coor_heads(hidden.view(2, M // 2, H), w1t, b1, mean[2].weight, mean[2].bias, lstd[2].weight, lstd[2].bias)
+        assert torch.equal(q2.view(M, Z), qm)
+
+
+def test_enc_coor_fused_heads_switch_and_weight_cache():
+    from apgs_b200.bmnist import models as M
+    torch.manual_seed(3)
+    enc = M.Enc_coor(4761, 400, 2).to(DEV)
+    conved = torch.softmax(torch.randn(10, 64, 4761, device=DEV) * 2, -1)
+    with torch.no_grad():
+        m1, s1 = enc.params(conved)
+        M.Enc_coor.fused_heads = False
+        try:
+            m0, s0 = enc.params(conved)
+        finally:
+            M.Enc_coor.fused_heads = True
+        assert float((m1 - m0).abs().max()) <= 2e-6 and float(((s1 - s0).abs() / s0).max()) <= 2e-6
+        enc.where_mean[0].weight.mul_(0.5)                              # the cached transposed weights follow the parameter
+        enc.where_log_std[0].bias.add_(0.1)
+        m2, s2 = enc.params(conved)
+        M.Enc_coor.fused_heads = False
+        try:
+            m3, s3 = enc.params(conved)
+        finally:
+            M.Enc_coor.fused_heads = True
+    assert float((m2 - m3).abs().max()) <= 2e-6 and float(((s2 - s3).abs() / s3).max()) <= 2e-6
+    assert not torch.equal(m2, m1)
