@@ -98,6 +98,8 @@ SIGNATURES = {
     "apgs_linear_tc5_pack_f32": (_int, [_p, _i64, _i64, _i64, _int, _p, _p]),
     "apgs_linear_tc5_packed_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "apgs_linear_tc5_packed_f32": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "apgs_bmnist_template_match_residual_f32": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _i64, _p, _p,
+                                                      _i64, _i64, _i64, _i64, _int, _int, _p, _p]),
     "apgs_bmnist_template_match_packed_f32": (_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_bmnist_template_match_f32": (_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _p]),
     "apgs_bmnist_logw_where_f32": (_int, [_p] * 11 + [_i64] * 4 + [_p] * 6),

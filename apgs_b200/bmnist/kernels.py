@@ -241,11 +241,17 @@ def template_match_supports_packed(FP, DP):
     return FP == 96 and DP == 28
 
 
-def template_match(frame, template, softmax=True, packed=False):
+def template_match_supports_residual(FP, DP):
+    return FP == 96 and DP == 28
+
+
+def template_match(frame, template, softmax=True, packed=False, prev=None, lin_fp=None):
     """N3: per-(s,b) cross-correlation of frame (S,B,FP,FP) with template (S,B,DP,DP) -> (S,B,CP*CP), CP = FP-DP+1,
     followed by the softmax over the scores (apgs/bmnist/objectives.py:72-74).  Strided views (frames[:, :, t],
     template[:, :, k], S-expanded frames) are read in place.  packed=True: the softmax map as PackedRows (the operand layout of
-    Enc_coor's tensor-core layer; FP = 96, DP = 28)."""
+    Enc_coor's tensor-core layer; FP = 96, DP = 28).  prev = [(digit (S,B,DP,DP), z_where (S,B,2)), ...] (at most two) with
+    lin_fp: the match runs on frame - paste(digit0) - paste(digit1), the residual frame of the sequential proposals (:87-89),
+    formed inside the kernel (bit-identical to paste_subtract followed by the match)."""
     lib = _lib.load()
     f, t = _dense_images(frame, "frame"), _dense_images(template, "template")
     S, B, FP, _ = f.shape
@@ -253,22 +259,45 @@ def template_match(frame, template, softmax=True, packed=False):
     if tuple(t.shape) != (S, B, DP, DP) or f.shape[-2] != FP or DP > FP:
         raise ValueError("frame %s / template %s shapes do not match" % (tuple(f.shape), tuple(t.shape)))
     CP = FP - DP + 1
+    if packed and not softmax:
+        raise ValueError("template_match: packed output is the softmax map")
+    prev = list(prev) if prev else []
+    if len(prev) > 2:
+        raise ValueError("template_match: at most two previous digits")
     if packed:                                      # softmax written as the packed activation operand of linear_tc5_packed
-        if not softmax:
-            raise ValueError("template_match: packed output is the softmax map")
         nbytes = lib.apgs_linear_tc5_packed_bytes(S * B, CP * CP, 0)
-        buf = torch.empty(nbytes // 4, dtype=torch.float32, device=f.device)
-        with torch.cuda.device(f.device), _call("bmnist_template_match", 1, 4 * S * B * (FP * FP + DP * DP) + nbytes):
+        out = torch.empty(nbytes // 4, dtype=torch.float32, device=f.device)
+    else:
+        nbytes = 4 * S * B * CP * CP
+        out = torch.empty(S, B, CP * CP, dtype=torch.float32, device=f.device)
+    pd, pz, lin = [], [], None
+    if prev:                                        # argument checks outside the timed call
+        if lin_fp is None:
+            raise ValueError("template_match: lin_fp is required with prev")
+        lin = _req(lin_fp, "lin_fp", ndim=1)
+        for d, z in prev:
+            d, z = _dense_images(d, "digit"), _req(z, "z_where", ndim=3)
+            if tuple(d.shape) != (S, B, DP, DP) or tuple(z.shape) != (S, B, 2) or lin.numel() != FP:
+                raise ValueError("template_match: prev digit %s / z_where %s do not match" % (tuple(d.shape), tuple(z.shape)))
+            pd.append(d), pz.append(z)
+    with torch.cuda.device(f.device), _call("bmnist_template_match", 1, 4 * S * B * (FP * FP + (1 + len(prev)) * DP * DP) + nbytes):
+        if prev:
+            d1, z1 = (pd[1], pz[1]) if len(pd) > 1 else (None, None)
+            check(lib.apgs_bmnist_template_match_residual_f32(
+                ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),
+                ptr(pd[0]), pd[0].stride(0), pd[0].stride(1), ptr(pz[0]),
+                ptr(d1), d1.stride(0) if d1 is not None else 0, d1.stride(1) if d1 is not None else 0, ptr(z1),
+                ptr(lin), S, B, FP, DP, 1 if softmax else 0, 1 if packed else 0, ptr(out), _stream()),
+                "apgs_bmnist_template_match_residual_f32")
+        elif packed:
             check(lib.apgs_bmnist_template_match_packed_f32(ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),
-                                                            S, B, FP, DP, ptr(buf), _stream()),
+                                                            S, B, FP, DP, ptr(out), _stream()),
                   "apgs_bmnist_template_match_packed_f32")
-        return PackedRows(buf, (S, B), CP * CP, 0)
-    out = torch.empty(S, B, CP * CP, dtype=torch.float32, device=f.device)
-    with torch.cuda.device(f.device), _call("bmnist_template_match", 1, 4 * S * B * (FP * FP + DP * DP + CP * CP)):
-        check(lib.apgs_bmnist_template_match_f32(ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),
-                                                 S, B, FP, DP, 1 if softmax else 0, ptr(out), _stream()),
-              "apgs_bmnist_template_match_f32")
-    return out
+        else:
+            check(lib.apgs_bmnist_template_match_f32(ptr(f), f.stride(0), f.stride(1), ptr(t), t.stride(0), t.stride(1),
+                                                     S, B, FP, DP, 1 if softmax else 0, ptr(out), _stream()),
+                  "apgs_bmnist_template_match_f32")
+    return PackedRows(out, (S, B), CP * CP, 0) if packed else out
 
 
 def paste_subtract(frame, digit, z_where, lin_fp):

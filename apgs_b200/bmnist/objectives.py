@@ -77,15 +77,24 @@ def _propose(enc_coor, dec_coor, AT, frame, template, z_where_t_1, z_where_old_t
     zs, means, stds = [], [], []
     frame_left = frame
     packed = enc_coor.wants_packed(FP, DP)
+    # the residual frame_left - digit_to_frame(template_k, z_where_k) (:87-89) is formed inside the next match (two digits deep;
+    # nearest-mode transformer at the compiled shape), otherwise by the paste-subtract kernel
+    in_match = getattr(AT, "mode", "nearest") == "nearest" and kernels.template_match_supports_residual(FP, DP)
+    prev = []
     for k in range(K):
         template_k = template[:, :, k, :, :]
         # conv2d(groups=S*B) + softmax (:72-74); written as the packed operand of Enc_coor's tensor-core layer when it takes one
-        conved_k = kernels.template_match(frame_left, template_k, packed=packed)
+        conved_k = kernels.template_match(frame_left, template_k, packed=packed, prev=prev, lin_fp=AT.lin_fp if prev else None)
         q_mean, q_std = enc_coor.params(conved_k)
         z_where_k = normal_sample(q_mean.detach(), q_std.detach())
         zs.append(z_where_k.unsqueeze(2)); means.append(q_mean.unsqueeze(2)); stds.append(q_std.unsqueeze(2))
         if k + 1 < K:                                        # frame_left - digit_to_frame(template_k, z_where_k) (:87-89)
-            frame_left = AT.subtract_digit(frame_left, template_k, z_where_k)
+            if in_match and len(prev) < 2:
+                prev = prev + [(template_k, z_where_k)]
+            else:
+                for d, z in prev + [(template_k, z_where_k)]:
+                    frame_left = AT.subtract_digit(frame_left, d, z)
+                prev = []
     z_where = torch.cat(zs, 2)
     q_mean, q_std = torch.cat(means, 2), torch.cat(stds, 2)
     log_q_graph = Normal(q_mean, q_std, validate_args=False).log_prob(z_where).sum(-1).sum(-1) if train else None

@@ -29,7 +29,23 @@ struct MatchArgs {
     float* out;                // (S*B, CP*CP)
     int S, B, FP, DP, softmax;
     int packed;                // out is the packed TF32 hi / lo operand of k_linear_tc5pk (tf32_pack.cuh) instead of (S*B, CP*CP)
+    // residual mode: the image is frame - paste(prev digit 0) - paste(prev digit 1), the frame_left of the sequential matches
+    // (apgs/bmnist/objectives.py:87-89), formed while the image is staged; digit p of (s,b) at prev[p] + s*ps[p] + b*pb[p]
+    // (DP*DP dense), its z_where at prev_z[p] + (s*B + b)*2, lin = affine_grid's base axis at the frame resolution
+    const float* prev[2];
+    long long ps[2], pb[2];
+    const float* prev_z[2];
+    const float* lin;
+    int n_prev;
 };
+
+// source index of Affine_Transformer.digit_to_frame along one axis (bmnist.cu stn_index; affine_transformer.py:41-52)
+__device__ __forceinline__ int match_stn_index(float lin, float scale, float t, int n_in) {
+    const float v = __fadd_rn(__fmul_rn(lin, scale), t);
+    const float u = __fmul_rn(__fadd_rn(v, 1.f), (float)(n_in - 1) * 0.5f);
+    const float r = rintf(u);
+    return (r >= 0.f && r <= (float)(n_in - 1)) ? (int)r : -1;
+}
 
 __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -54,7 +70,61 @@ __global__ void __launch_bounds__(224, 5) k_template_match(MatchArgs a) {
     const int img = blockIdx.x, s = img / a.B, b = img % a.B;
     const float* f = a.frame + s * a.fs + b * a.fb;
     const float* t = a.tmpl + s * a.ts + b * a.tb;
+    // frame_left = (frame - paste_0) - paste_1 (:87-89).  A pasted digit covers only the ~DP x DP pixels whose source index is
+    // in range (the transformer magnifies by FP / DP), and v - 0.f == v: only that footprint is touched, digit by digit in
+    // order -- bit-identical to k_stn_paste's residual mode.  The index vectors are built before the image is staged (their
+    // global loads overlap it) and a thread fetches all of its digit pixels before it subtracts any (independent loads).
+    __shared__ short s_pi[2][2][FP];                                      // [digit][rows / columns][frame coordinate] -> digit coordinate
+    __shared__ int s_lo[2][2], s_n[2][2];                                 // first in-range frame coordinate and how many follow
+    if (a.n_prev > 0) {
+        const float scale = (float)((double)FP / (double)DP), tr = (float)((double)(FP - DP) / (double)DP);
+        for (int i = threadIdx.x; i < a.n_prev * 2 * FP; i += blockDim.x) {
+            const int p = i / (2 * FP), ax = (i / FP) & 1, j = i % FP;
+            const float* zw = a.prev_z[p] + ((long long)s * a.B + b) * 2;
+            const float tt = ax == 0 ? __fmul_rn(__ldg(zw + 1), tr) : -__fmul_rn(__ldg(zw), tr);
+            s_pi[p][ax][j] = (short)match_stn_index(__ldg(a.lin + j), scale, tt, DP);
+        }
+    }
     for (int i = threadIdx.x; i < FP * FP; i += blockDim.x) s_f[(i / FP) * FS + (i % FP)] = __ldg(f + i);
+    if (a.n_prev > 0) {
+        __syncthreads();
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (w < a.n_prev * 2) {                                           // warp w: one (digit, axis); the in-range run is contiguous
+            static_assert(FP % 32 == 0, "lanes stride over the frame coordinates");
+            int lo = FP, hi = -1;
+#pragma unroll
+            for (int j = lane; j < FP; j += 32)
+                if (s_pi[w >> 1][w & 1][j] >= 0) { lo = min(lo, j); hi = max(hi, j); }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lane == 0) { s_lo[w >> 1][w & 1] = lo; s_n[w >> 1][w & 1] = hi >= lo ? hi - lo + 1 : 0; }
+        }
+        __syncthreads();
+        constexpr int PER = 5;                                            // footprint pixels per thread: (DP + 2)^2 <= 224 * 5
+        for (int p = 0; p < a.n_prev; ++p) {
+            const float* dg = a.prev[p] + s * a.ps[p] + b * a.pb[p];
+            const int nr = s_n[p][0], nc = s_n[p][1], r0 = s_lo[p][0], c0 = s_lo[p][1];
+            for (int base = 0; base < nr * nc; base += PER * (int)blockDim.x) {
+                float d[PER];
+                int at[PER];
+#pragma unroll
+                for (int q = 0; q < PER; ++q) {
+                    const int i = base + q * (int)blockDim.x + (int)threadIdx.x;
+                    at[q] = -1;
+                    d[q] = 0.f;
+                    if (i < nr * nc) {
+                        const int r = r0 + i / nc, c = c0 + i % nc;
+                        const int rr = s_pi[p][0][r], cc = s_pi[p][1][c];
+                        if (rr >= 0 && cc >= 0) { at[q] = r * FS + c; d[q] = __ldg(dg + rr * DP + cc); }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PER; ++q)
+                    if (at[q] >= 0) s_f[at[q]] = __fsub_rn(s_f[at[q]], d[q]);
+            }
+            __syncthreads();                                              // digit 1 subtracts from what digit 0 left
+        }
+    }
     for (int i = threadIdx.x; i < DP * DP; i += blockDim.x) s_t[i] = __ldg(t + i);
     __syncthreads();
     const bool live = threadIdx.x < CP * NSEG;
@@ -164,9 +234,17 @@ __global__ void __launch_bounds__(256) k_template_match_generic(MatchArgs a) {
 
 using namespace apgs;
 
+struct MatchPrev {
+    const float* digit[2];
+    int64_t ds[2], db[2];
+    const float* z[2];
+    const float* lin;
+    int n;
+};
+
 static int template_match_launch(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b, const float* tmpl,
                                  int64_t tmpl_stride_s, int64_t tmpl_stride_b, int64_t S, int64_t B, int64_t FP, int64_t DP,
-                                 int softmax, int packed, float* out, void* stream) {
+                                 int softmax, int packed, float* out, void* stream, const MatchPrev* prev = nullptr) {
     if (S <= 0 || B <= 0 || FP <= 0 || DP <= 0 || DP > FP || S * B > 0x7fffffffLL)
         return fail(APGS_E_SHAPE, "bmnist_template_match: bad sizes S=%lld B=%lld FP=%lld DP=%lld", (long long)S, (long long)B,
                     (long long)FP, (long long)DP);
@@ -177,7 +255,21 @@ static int template_match_launch(const float* frame, int64_t frame_stride_s, int
         return fail(APGS_E_UNSUPPORTED, "bmnist_template_match_packed: compiled for FP=96, DP=28 only (got %lld, %lld)", (long long)FP,
                     (long long)DP);
     MatchArgs a = {frame, (long long)frame_stride_s, (long long)frame_stride_b, tmpl, (long long)tmpl_stride_s,
-                   (long long)tmpl_stride_b, out, (int)S, (int)B, (int)FP, (int)DP, softmax, packed};
+                   (long long)tmpl_stride_b, out, (int)S, (int)B, (int)FP, (int)DP, softmax, packed,
+                   {nullptr, nullptr}, {0, 0}, {0, 0}, {nullptr, nullptr}, nullptr, 0};
+    if (prev != nullptr && prev->n > 0) {
+        if (!(FP == 96 && DP == 28))
+            return fail(APGS_E_UNSUPPORTED, "bmnist_template_match_residual: compiled for FP=96, DP=28 only (got %lld, %lld)",
+                        (long long)FP, (long long)DP);
+        if (prev->n > 2 || !prev->lin) return fail(APGS_E_BADARG, "bmnist_template_match_residual: at most two digits, lin required");
+        for (int p = 0; p < prev->n; ++p) {
+            if (!prev->digit[p] || !prev->z[p]) return fail(APGS_E_BADARG, "bmnist_template_match_residual: NULL digit / z_where");
+            if (prev->ds[p] < 0 || prev->db[p] < 0) return fail(APGS_E_BADARG, "bmnist_template_match_residual: negative stride");
+            a.prev[p] = prev->digit[p]; a.ps[p] = (long long)prev->ds[p]; a.pb[p] = (long long)prev->db[p]; a.prev_z[p] = prev->z[p];
+        }
+        a.lin = prev->lin;
+        a.n_prev = prev->n;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned int grid = (unsigned int)(S * B);
     if (FP == 96 && DP == 28) {
@@ -209,4 +301,20 @@ extern "C" int apgs_bmnist_template_match_packed_f32(const float* frame, int64_t
     if (out_packed && !aligned(out_packed, 16)) return fail(APGS_E_BADARG, "bmnist_template_match_packed: out must be 16-byte aligned");
     return template_match_launch(frame, frame_stride_s, frame_stride_b, tmpl, tmpl_stride_s, tmpl_stride_b, S, B, FP, DP, 1, 1,
                                  out_packed, stream);
+}
+
+extern "C" int apgs_bmnist_template_match_residual_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                                       const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                                       const float* digit0, int64_t digit0_stride_s, int64_t digit0_stride_b,
+                                                       const float* z_where0, const float* digit1, int64_t digit1_stride_s,
+                                                       int64_t digit1_stride_b, const float* z_where1, const float* lin_fp,
+                                                       int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax, int packed,
+                                                       float* out, void* stream) {
+    if (packed && out && !aligned(out, 16)) return fail(APGS_E_BADARG, "bmnist_template_match_residual: packed out must be 16-byte aligned");
+    if (packed && !softmax) return fail(APGS_E_BADARG, "bmnist_template_match_residual: the packed output is the softmax map");
+    MatchPrev pv = {{digit0, digit1}, {digit0_stride_s, digit1_stride_s}, {digit0_stride_b, digit1_stride_b}, {z_where0, z_where1},
+                    lin_fp, digit0 ? (digit1 ? 2 : 1) : 0};
+    if (!digit0 && digit1) return fail(APGS_E_BADARG, "bmnist_template_match_residual: digit1 without digit0");
+    return template_match_launch(frame, frame_stride_s, frame_stride_b, tmpl, tmpl_stride_s, tmpl_stride_b, S, B, FP, DP, softmax,
+                                 packed, out, stream, &pv);
 }

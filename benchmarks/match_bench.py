@@ -1,0 +1,59 @@
+"""bmnist template matching at the C4 shape (S*B = 640 images of 96x96, 28x28 templates), device time per call from CUDA-graph
+replays: fp32 map, packed TF32 operand, the match on the residual frame (one / two previous digits subtracted while the image
+is staged) against paste_subtract + match."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from apgs_b200.bmnist import kernels, Affine_Transformer  # noqa: E402
+
+DEV = "cuda:0"
+S, B, FP, DP, K = 10, 64, 96, 28, 3
+
+
+def graph_timed(fn, calls=20, reps=10):
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(st)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b) / calls)
+    return sorted(ts)[len(ts) // 2]
+
+
+torch.manual_seed(0)
+AT = Affine_Transformer(FP, DP, True, DEV)
+f = torch.rand(B, FP, FP, device=DEV).unsqueeze(0).expand(S, -1, -1, -1)
+t = torch.rand(S, B, K, DP, DP, device=DEV)
+z = torch.rand(S, B, K, 2, device=DEV) * 1.6 - 0.8
+p1 = [(t[:, :, 0], z[:, :, 0].contiguous())]
+p2 = p1 + [(t[:, :, 1], z[:, :, 1].contiguous())]
+left = AT.subtract_digit(f, *p1[0])
+left2 = AT.subtract_digit(left, *p2[1])
+row = {"S": S, "B": B,
+       "match_fp32_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2])),
+       "match_packed_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True)),
+       "match_packed_prev1_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True, prev=p1, lin_fp=AT.lin_fp)),
+       "match_packed_prev2_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True, prev=p2, lin_fp=AT.lin_fp)),
+       "match_packed_on_materialised_residual_ms": graph_timed(lambda: kernels.template_match(left2, t[:, :, 2], packed=True)),
+       "paste_subtract_ms": graph_timed(lambda: AT.subtract_digit(left, *p2[1]))}
+fma = S * B * (FP - DP + 1) ** 2 * DP * DP
+row["TFMA_s_packed"] = fma / row["match_packed_ms"] / 1e9
+print(json.dumps(row))

@@ -656,6 +656,19 @@ APGS_API int apgs_bmnist_template_match_f32(const float* frame, int64_t frame_st
 APGS_API int apgs_bmnist_template_match_packed_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
                                    const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
                                    int64_t S, int64_t B, int64_t FP, int64_t DP, float* out_packed, void* stream);
+/* The match on the RESIDUAL frame of the sequential proposals (apgs/bmnist/objectives.py:72-89): the image of (s,b) is
+ *     (frame - digit_to_frame(digit0, z_where0)) - digit_to_frame(digit1, z_where1)         (digit1 / digit0 may be NULL)
+ *   formed pixel by pixel, in that order, while the image is staged in shared memory -- bit-identical to matching the output
+ *   of apgs_bmnist_paste_subtract_f32, without the frame_left tensors ever existing.  digit p of (s,b) at
+ *   digit_p + s*stride_s + b*stride_b (DP*DP dense), z_where_p (S,B,2) contiguous, lin_fp = affine_grid's base axis at the
+ *   frame resolution (FP floats; Affine_Transformer's nearest mode, affine_transformer.py:41-52).  packed != 0 writes the
+ *   softmax as the packed operand (as apgs_bmnist_template_match_packed_f32).  FP = 96, DP = 28 when a digit is given.        */
+APGS_API int apgs_bmnist_template_match_residual_f32(const float* frame, int64_t frame_stride_s, int64_t frame_stride_b,
+                                   const float* tmpl, int64_t tmpl_stride_s, int64_t tmpl_stride_b,
+                                   const float* digit0, int64_t digit0_stride_s, int64_t digit0_stride_b, const float* z_where0,
+                                   const float* digit1, int64_t digit1_stride_s, int64_t digit1_stride_b, const float* z_where1,
+                                   const float* lin_fp, int64_t S, int64_t B, int64_t FP, int64_t DP, int softmax, int packed,
+                                   float* out, void* stream);
 
 #ifdef __cplusplus
 }

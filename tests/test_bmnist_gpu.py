@@ -736,3 +736,36 @@ def test_enc_coor_fused_heads_switch_and_weight_cache():
             M.Enc_coor.fused_heads = True
     assert float((m2 - m3).abs().max()) <= 2e-6 and float(((s2 - s3).abs() / s3).max()) <= 2e-6
     assert not torch.equal(m2, m1)
+
+
+@pytest.mark.parametrize("S,B", [(10, 64), (2, 3)])
+def test_template_match_on_the_residual_frame_is_bit_identical(S, B):
+    """apgs_bmnist_template_match_residual_f32: forming frame - paste(digit0) - paste(digit1) while the image is staged gives the
+    bits of paste_subtract (k_stn_paste's residual mode) followed by the match (apgs/bmnist/objectives.py:72-89), for one and
+    two previous digits, S-shared frames (stride 0), strided template views, fp32 and packed outputs; digits partly outside the
+    frame included."""
+    from apgs_b200.bmnist import kernels, Affine_Transformer
+    torch.manual_seed(S + 7 * B)
+    FP, DP, T, K = 96, 28, 3, 3
+    AT = Affine_Transformer(FP, DP, True, DEV)
+    frames = torch.rand(B, T, FP, FP, device=DEV).unsqueeze(0).expand(S, -1, -1, -1, -1)     # stride-0 particle axis
+    tmpl = torch.rand(S, B, K, DP, DP, device=DEV)
+    z = (torch.rand(S, B, K, 2, device=DEV) * 2.4 - 1.2)                                    # some digits stick out of the frame
+    f_t = frames[:, :, 1]
+    left1 = AT.subtract_digit(f_t, tmpl[:, :, 0], z[:, :, 0].contiguous())
+    left2 = AT.subtract_digit(left1, tmpl[:, :, 1], z[:, :, 1].contiguous())
+    p1 = [(tmpl[:, :, 0], z[:, :, 0].contiguous())]
+    p2 = p1 + [(tmpl[:, :, 1], z[:, :, 1].contiguous())]
+    for sm in (True, False):
+        assert torch.equal(kernels.template_match(f_t, tmpl[:, :, 1], softmax=sm, prev=p1, lin_fp=AT.lin_fp),
+                           kernels.template_match(left1, tmpl[:, :, 1], softmax=sm))
+        assert torch.equal(kernels.template_match(f_t, tmpl[:, :, 2], softmax=sm, prev=p2, lin_fp=AT.lin_fp),
+                           kernels.template_match(left2, tmpl[:, :, 2], softmax=sm))
+    a = kernels.template_match(f_t, tmpl[:, :, 2], packed=True, prev=p2, lin_fp=AT.lin_fp)
+    b = kernels.template_match(left2, tmpl[:, :, 2], packed=True)
+    assert torch.equal(a.unpack(), b.unpack())
+    assert not torch.equal(kernels.template_match(f_t, tmpl[:, :, 2]), kernels.template_match(left2, tmpl[:, :, 2]))
+    with pytest.raises(ValueError):
+        kernels.template_match(f_t, tmpl[:, :, 2], prev=p2 + p1, lin_fp=AT.lin_fp)
+    with pytest.raises(ValueError):
+        kernels.template_match(f_t, tmpl[:, :, 2], prev=p1)
