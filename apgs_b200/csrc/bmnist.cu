@@ -107,8 +107,14 @@ __global__ void __launch_bounds__(256) k_stn_paste(StnArgs a) {
     float* rec = a.dst != nullptr ? a.dst + (long long)sbt * FP * FP : nullptr;
     const float EPS = 1e-9f;
     float acc = 0.f, comp = 0.f;                                      // Kahan partial of this thread
+    // Background pixels (no digit pasted: recon == 0, ~3/4 of a frame) take their two logarithms from registers: the same
+    // logf of the same arguments, evaluated once per thread instead of once per pixel -- bit-identical.
+    float zero;                                                       // opaque to the compiler: the run-time logf, not a folded constant
+    asm volatile("mov.f32 %0, 0f00000000;" : "=f"(zero));
+    const float log_eps = logf(__fadd_rn(zero, EPS)), log_one = logf(__fadd_rn(__fsub_rn(1.f, zero), EPS));
+    const int step_i = (int)blockDim.x / FP, step_j = (int)blockDim.x % FP;
+    int i = (int)threadIdx.x / FP, j = (int)threadIdx.x % FP;          // (row, column) of pixel o, advanced without divisions
     for (int o = threadIdx.x; o < FP * FP; o += blockDim.x) {
-        const int i = o / FP, j = o % FP;
         float v = 0.f;
         for (int k = 0; k < K; ++k) {                                 // .sum(-3): k = 0, 1, 2 in order
             const int r = s_idx[(k * 2 + 0) * FP + i], c = s_idx[(k * 2 + 1) * FP + j];
@@ -118,8 +124,15 @@ __global__ void __launch_bounds__(256) k_stn_paste(StnArgs a) {
         if (rec != nullptr) __stcs(rec + o, v);
         const float x = __ldg(fr + o);
         // log(x_mean + EPS) * x + log(1 - x_mean + EPS) * (1 - x)      (models.py:161-162)
-        const float term = __fadd_rn(__fmul_rn(logf(__fadd_rn(v, EPS)), x),
-                                     __fmul_rn(logf(__fadd_rn(__fsub_rn(1.f, v), EPS)), __fsub_rn(1.f, x)));
+        float l0 = log_eps, l1 = log_one;
+        if (v != 0.f) {
+            l0 = logf(__fadd_rn(v, EPS));
+            l1 = logf(__fadd_rn(__fsub_rn(1.f, v), EPS));
+        }
+        const float term = __fadd_rn(__fmul_rn(l0, x), __fmul_rn(l1, __fsub_rn(1.f, x)));
+        i += step_i;
+        j += step_j;
+        if (j >= FP) { j -= FP; ++i; }
         const float y = __fsub_rn(term, comp);
         const float tsum = __fadd_rn(acc, y);
         comp = __fsub_rn(__fsub_rn(tsum, acc), y);
