@@ -75,6 +75,7 @@ SIGNATURES = {
     "apgs_gmm_logw_z_f32": (_int, [_p, _p, _p, _p, _PR, _p, _p, _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
     "apgs_gmm_logw_joint_f32": (_int, [_p, _PO, _PR, _p, _p, _p, _p, _p, _p, _p,
                                        _i64, _i64, _i64, _i64, _i64, _OUT, _p]),
+    "apgs_dmm_mu_heads_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "apgs_dmm_nss_pool_f32": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_dmm_nss_pool_onehot_f32": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "apgs_dmm_local_encoder_fused_f32": (_int, [_p, _p, _DMLP, _DMLP, _DMLP, _i64, _p, _p, _p] + [_i64] * 5 + [_p] * 7),

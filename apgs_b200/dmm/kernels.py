@@ -64,6 +64,35 @@ def nss_pool(nss1, nss2, prior_mu_mu, prior_mu_sigma):
     return out
 
 
+def mu_heads_supported(mean_seq, sigma_seq):
+    """True when (mean_mu, mean_log_sigma) are Linear + Tanh + Linear of equal shapes that apgs_dmm_mu_heads_f32 takes."""
+    import torch.nn as nn
+    ok = all(len(q) == 3 and isinstance(q[0], nn.Linear) and isinstance(q[1], nn.Tanh) and isinstance(q[2], nn.Linear)
+             and q[0].bias is not None and q[2].bias is not None for q in (mean_seq, sigma_seq))
+    return (ok and mean_seq[0].weight.shape == sigma_seq[0].weight.shape and mean_seq[2].weight.shape == sigma_seq[2].weight.shape
+            and mean_seq[0].in_features <= 32 and mean_seq[2].out_features <= 4 and mean_seq[0].out_features <= 1024)
+
+
+def mu_heads(v, mean_seq, sigma_seq):
+    """(q_mu, q_sigma) = (mean_mu(v), mean_log_sigma(v).exp()) in one launch (apgs_dmm_mu_heads_f32; apgs/dmm/models.py:43-44).
+    Forward values only."""
+    lib = _lib.load()
+    v = _req(v, "nss_prior")
+    H = v.shape[-1]
+    M = v.numel() // H
+    ws = [_req(t, "weight") for t in (mean_seq[0].weight, mean_seq[0].bias, mean_seq[2].weight, mean_seq[2].bias,
+                                      sigma_seq[0].weight, sigma_seq[0].bias, sigma_seq[2].weight, sigma_seq[2].bias)]
+    H2, Z = ws[0].shape[0], ws[2].shape[0]
+    if ws[0].shape[1] != H:
+        raise ValueError("mu_heads: input width %d does not match the first layer %s" % (H, tuple(ws[0].shape)))
+    mean = torch.empty(tuple(v.shape[:-1]) + (Z,), dtype=torch.float32, device=v.device)
+    std = torch.empty_like(mean)
+    with torch.cuda.device(v.device), _call("dmm_mu_heads", 1, 4 * M * (H + 2 * Z)):
+        check(lib.apgs_dmm_mu_heads_f32(ptr(v), *[ptr(w) for w in ws], M, H, H2, Z, ptr(mean), ptr(std), _stream()),
+              "apgs_dmm_mu_heads_f32")
+    return mean, std
+
+
 def _flat(t, name):
     """(S,B,N,1) or (S,B,N) -> contiguous tensor read as (S,B,N)."""
     t = _req(t, name)

@@ -39,9 +39,19 @@ class _EncMu(nn.Module):
         self.mean_mu = nn.Sequential(nn.Linear(num_nss + 2 * D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, D))
         self.mean_log_sigma = nn.Sequential(nn.Linear(num_nss + 2 * D, num_hidden), nn.Tanh(), nn.Linear(num_hidden, D))
 
+    fused_heads = True    # evaluation path: mean_mu / mean_log_sigma (+ exp) in one launch (csrc/dmm_heads.cu)
+
+    def _mu_heads(self, nss_prior):
+        """(q_mu, q_sigma) from cat(nss, priors) (models.py:43-44)"""
+        if (self.fused_heads and nss_prior.is_cuda and nss_prior.dtype == torch.float32 and not needs_grad(self)
+                and not (torch.is_grad_enabled() and nss_prior.requires_grad)
+                and kernels.mu_heads_supported(self.mean_mu, self.mean_log_sigma)):
+            return kernels.mu_heads(nss_prior, self.mean_mu, self.mean_log_sigma)
+        return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
+
     def _heads(self, nss1, nss2, priors):
         nss_prior = kernels.nss_pool(nss1, nss2, priors[0], priors[1])          # D1
-        return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
+        return self._mu_heads(nss_prior)
 
     def _heads_torch(self, nss1, nss2, priors, EPS=1e-8):
         """D1 + heads with PyTorch ops only (autograd graph for training; models.py:134-139)."""
@@ -112,7 +122,7 @@ class Enc_apg_mu(_EncMu):
             with torch.no_grad():
                 tab1, tab2 = self.label_tables(x) if tables is None else tables
                 nss_prior = kernels.nss_pool_onehot(tab1, tab2, z, priors[0], priors[1])
-                return self.mean_mu(nss_prior), self.mean_log_sigma(nss_prior).exp()
+                return self._mu_heads(nss_prior)
         h1 = torch.tanh(_split_linear(self.nss1[0], x, z))
         h2 = torch.tanh(_split_linear(self.nss2[0], x, z))
         return self._heads(self.nss1[2](h1), F.softmax(self.nss2[2](h2), -1), priors)

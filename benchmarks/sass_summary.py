@@ -54,7 +54,7 @@ with open(os.path.join(ROOT, "profiles", "%s_sass_summary.md" % tag), "w") as f:
             "with `MUFU.RCP`/`EX2`/`LG2`; row staging uses the bulk-copy engine (`UBLKCP` = `cp.async.bulk.shared::cluster.global`) and "
             "`LDGSTS` (`cp.async`); the gather moves 16-byte vectors (`LDG.E.128` / `STG.E.128`).  There is no tensor-map TMA (`UTMALDG` / `UTMASTG`; the `UTMACMDFLUSH` that appears in a few kernels is the commit of `cp.async.bulk` stores) and no "
             "tcgen05 (`UTC*MMA`, `LDTM`): nothing on the section-8a path is a dense contraction (north_star), and the row-granular TMA gather was "
-            "measured slower than LDG/STG (DESIGN.md section 4).  The tensor-core kernels are bmnist's Enc_coor layer as 3xTF32: `k_linear_tc5` "
+            "measured slower than LDG/STG (DESIGN.md section 4).  The tensor-core kernels are bmnist's Enc_coor layer as 3xTF32: `k_linear_tc5pk` (the evaluation path: `UBLKCP` bulk copies of pre-packed operand tiles feeding `UTCHMMA`, no operand ever in a register) and `k_linear_tc5` "
             "(`UTCHMMA` = `tcgen05.mma kind::tf32`, `LDTM` = `tcgen05.ld`, `UTCBAR` = `tcgen05.commit`) and `k_linear_tf32x3` "
             "(`HMMA.1688.F32.TF32` = `mma.sync.m16n8k8.tf32`).  No atomics: every reduction is ordered (deterministic).\n")
 print(open(os.path.join(ROOT, "profiles", "%s_sass_summary.md" % tag)).read()[-1500:])

@@ -583,6 +583,16 @@ APGS_API int apgs_dmm_local_encoder_draw_f32(const float* x, const float* mu,
                                  float* beta, const apgs_dmm_mlp_t* decoder, int64_t decoder_hidden, float* hidden2,
                                  void* stream);
 
+/* The two heads of Enc_rws_mu / Enc_apg_mu on the pooled statistics in one launch (apgs/dmm/models.py: mean_mu,
+ *   mean_log_sigma -- Linear(num_nss + 2 D, H2) + Tanh + Linear(H2, D); forward :43-44, :88-89):
+ *     q_mu (M,Z) = W2m tanh(W1m v + b1m) + b2m,   q_sigma (M,Z) = exp(W2s tanh(W1s v + b1s) + b2s),   v (M,H), M = S*B*K rows
+ *   weights as nn.Linear holds them: w1_* (H2,H), b1_* (H2), w2_* (Z,H2), b2_* (Z).  A thread owns a row; fp32, sums in
+ *   ascending k.  H <= 32, Z <= 4 (else APGS_E_UNSUPPORTED: the host keeps the nn.Sequential modules).                      */
+APGS_API int apgs_dmm_mu_heads_f32(const float* v, const float* w1_mean, const float* b1_mean, const float* w2_mean,
+                                   const float* b2_mean, const float* w1_sigma, const float* b1_sigma, const float* w2_sigma,
+                                   const float* b2_sigma, int64_t M, int64_t H, int64_t H2, int64_t Z, float* q_mu,
+                                   float* q_sigma, void* stream);
+
 /* Decoder.recon_mu + unit normalisation (apgs/dmm/models.py:202-203): hidden2 (M,D) from beta (M), M = S*B*N;
  *   net = recon_mu (1->H->tanh->D).                                                                          */
 APGS_API int apgs_dmm_decoder_hidden2_f32(const float* beta, const apgs_dmm_mlp_t* net, int64_t H, int64_t D,

@@ -487,3 +487,50 @@ def test_dmm_objective_with_in_kernel_draws_matches_torch_draws_statistically():
         se = (a.var(0) / a.shape[0] + b.var(0) / b.shape[0]).sqrt().clamp_min(1e-9)
         zmax = float(((a.mean(0) - b.mean(0)).abs() / se).max())
         assert zmax < 5.0, (k, zmax)
+
+
+@pytest.mark.parametrize("M_shape,H,H2,Z", [((100, 256, 4), 12, 32, 2), ((3, 5, 4), 14, 32, 3), ((7,), 5, 9, 1), ((2, 300), 32, 40, 4)])
+def test_mu_heads_in_one_launch_match_the_modules(M_shape, H, H2, Z):
+    """apgs_dmm_mu_heads_f32 against the reference's nn.Sequential heads (apgs/dmm/models.py: mean_mu / mean_log_sigma,
+    forward :43-44) in fp64 and torch fp32: W2 tanh(W1 v + b1) + b2 and exp(...), widths that are not multiples of 4, row counts
+    that are not multiples of the CTA."""
+    import copy
+    import torch.nn as nn
+    from apgs_b200.dmm import kernels
+    torch.manual_seed(H + H2)
+    mean = nn.Sequential(nn.Linear(H, H2), nn.Tanh(), nn.Linear(H2, Z)).to(DEV)
+    lsig = nn.Sequential(nn.Linear(H, H2), nn.Tanh(), nn.Linear(H2, Z)).to(DEV)
+    v = torch.randn(*M_shape, H, device=DEV) * 2
+    assert kernels.mu_heads_supported(mean, lsig)
+    with torch.no_grad():
+        qm, qs = kernels.mu_heads(v, mean, lsig)
+        rm32, rs32 = mean(v), lsig(v).exp()
+        rm, rs = copy.deepcopy(mean).double()(v.double()), copy.deepcopy(lsig).double()(v.double()).exp()
+    assert tuple(qm.shape) == tuple(M_shape) + (Z,) and tuple(qs.shape) == tuple(qm.shape)
+    em, es = float((qm.double() - rm).abs().max()), float(((qs.double() - rs).abs() / rs).max())
+    em32, es32 = float((rm32.double() - rm).abs().max()), float(((rs32.double() - rs).abs() / rs).max())
+    assert em <= 2e-6 and es <= 2e-6, (em, es)
+    assert em <= 4 * em32 + 3e-7 and es <= 4 * es32 + 3e-7, (em, em32, es, es32)
+    assert not kernels.mu_heads_supported(nn.Sequential(nn.Linear(40, H2), nn.Tanh(), nn.Linear(H2, Z)),
+                                          nn.Sequential(nn.Linear(40, H2), nn.Tanh(), nn.Linear(H2, Z)))
+
+
+def test_enc_mu_fused_heads_switch():
+    """Enc_rws_mu / Enc_apg_mu with and without the one-launch heads (module switch `fused_heads`); training mode keeps the
+    differentiable modules."""
+    from apgs_b200.dmm import models as M
+    torch.manual_seed(4)
+    K, D, N, S, B = 4, 2, 50, 6, 5
+    enc = M.Enc_rws_mu(K, D, 32, 8).to(DEV)
+    x = torch.randn(S, B, N, D, device=DEV)
+    priors = (torch.zeros(D, device=DEV), torch.ones(D, device=DEV) * 4)
+    with torch.no_grad():
+        m1, s1 = enc.params(x, K, priors)
+        M._EncMu.fused_heads = False
+        try:
+            m0, s0 = enc.params(x, K, priors)
+        finally:
+            M._EncMu.fused_heads = True
+    assert float((m1 - m0).abs().max()) <= 2e-6 and float(((s1 - s0).abs() / s0).max()) <= 2e-6
+    q = enc(x, K, priors)                                            # parameters require grad: the graph survives
+    assert q['means'].log_prob.requires_grad
