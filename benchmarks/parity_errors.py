@@ -82,6 +82,35 @@ c1r, c0r = od.enc_local_cons(Pd["enc_apg_local"], xs, mu, zf)
 rows.append(("DMM `q_probs` (fused Enc_apg_local)", "2e-5 rel", "%.2e rel" % rel(q, q_ref, 1e-7)))
 rows.append(("DMM Beta concentrations", "2e-5 rel", "%.2e rel" % max(rel(c1, c1r), rel(c0, c0r))))
 rows.append(("DMM decoder `hidden2` (unit vector)", "1e-5 abs", "%.2e abs" % absmax(h2, od.dec_hidden2(Pd["dec"], beta))))
+# ------------------------------------------------------------------ one-launch heads and the packed-operand tensor-core layer
+import copy  # noqa: E402
+import torch.nn as nn  # noqa: E402
+from apgs_b200.bmnist import kernels as bk  # noqa: E402
+torch.manual_seed(2)
+with torch.no_grad():
+    v = torch.randn(100, 256, 4, 12, device=DEV) * 2
+    hm = nn.Sequential(nn.Linear(12, 32), nn.Tanh(), nn.Linear(32, 2)).to(DEV)
+    hs = nn.Sequential(nn.Linear(12, 32), nn.Tanh(), nn.Linear(32, 2)).to(DEV)
+    qm, qs = dk.mu_heads(v, hm, hs)
+    rm, rs = copy.deepcopy(hm).double()(v.double()), copy.deepcopy(hs).double()(v.double()).exp()
+    rows.append(("DMM `q_mu` / `q_sigma` (one-launch heads) vs fp64 modules", "2e-6 abs / rel",
+                 "%.2e abs / %.2e rel (torch fp32 modules: %.2e / %.2e)" % (absmax(qm, rm), rel(qs, rs), absmax(hm(v), rm), rel(hs(v).exp(), rs))))
+    xc = torch.softmax(torch.randn(640, 4761, device=DEV) * 3, -1)
+    wc, bc = torch.randn(400, 4761, device=DEV) / 69.0, torch.randn(400, device=DEV)
+    ref = xc.double() @ wc.double().t() + bc.double()
+    mag = xc.double().abs() @ wc.double().abs().t() + bc.double().abs()
+    o = bk.linear_tc5_packed(bk.pack_rows(xc, 0), bk.pack_rows(wc, 1), bc)
+    rows.append(("bmnist Enc_coor layer 4761 -> 400 (3xTF32 `tcgen05` from packed operands) / sum |x w|", "4e-6",
+                 "%.2e (torch fp32 GEMM: %.2e)" % (float(((o.double() - ref).abs() / mag).max()),
+                                                    float(((torch.nn.functional.linear(xc, wc, bc).double() - ref).abs() / mag).max()))))
+    hid = torch.relu(o)
+    cm = nn.Sequential(nn.Linear(400, 200), nn.ReLU(), nn.Linear(200, 2), nn.Tanh()).to(DEV)
+    cs = nn.Sequential(nn.Linear(400, 200), nn.ReLU(), nn.Linear(200, 2)).to(DEV)
+    w1t, b1 = bk.coor_heads_weights(cm[0].weight, cm[0].bias, cs[0].weight, cs[0].bias)
+    qm, qs = bk.coor_heads(hid, w1t, b1, cm[2].weight, cm[2].bias, cs[2].weight, cs[2].bias)
+    rm, rs = copy.deepcopy(cm).double()(hid.double()), copy.deepcopy(cs).double()(hid.double()).exp()
+    rows.append(("bmnist `q_mean` / `q_std` of z_where (one-launch heads) vs fp64 modules", "2e-6 abs / rel",
+                 "%.2e abs / %.2e rel (torch fp32 modules: %.2e / %.2e)" % (absmax(qm, rm), rel(qs, rs), absmax(cm(hid), rm), rel(cs(hid).exp(), rs))))
 print("# r2: maximum observed errors against the oracle (`python benchmarks/parity_errors.py` on a B200)\n")
 print("Every log-WEIGHT is tested to the north_star's 1e-5 of the magnitudes summed (SURVEY.md H2); the intermediates below have wider test "
       "tolerances because they go through the SFU approximations (`ex2.approx`, `rcp.approx`, `lg2.approx`, ~2^-22 each) of the fused MLPs.  "
