@@ -47,12 +47,18 @@ p1 = [(t[:, :, 0], z[:, :, 0].contiguous())]
 p2 = p1 + [(t[:, :, 1], z[:, :, 1].contiguous())]
 left = AT.subtract_digit(f, *p1[0])
 left2 = AT.subtract_digit(left, *p2[1])
+pout = [(t[:, :, 0], torch.full((S, B, 2), 5.0, device=DEV))]                          # empty footprint: only the index prologue runs
+fsigned = (torch.rand(B, FP, FP, device=DEV) * 2 - 1).unsqueeze(0).expand(S, -1, -1, -1)           # S-shared like f, signed values
+fsparse = (torch.rand(B, FP, FP, device=DEV) * (torch.rand(B, FP, FP, device=DEV) < 0.25)).unsqueeze(0).expand(S, -1, -1, -1)   # 3/4 black
 row = {"S": S, "B": B,
        "match_fp32_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2])),
        "match_packed_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True)),
        "match_packed_prev1_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True, prev=p1, lin_fp=AT.lin_fp)),
        "match_packed_prev2_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True, prev=p2, lin_fp=AT.lin_fp)),
        "match_packed_on_materialised_residual_ms": graph_timed(lambda: kernels.template_match(left2, t[:, :, 2], packed=True)),
+       "match_packed_signed_random_input_ms": graph_timed(lambda: kernels.template_match(fsigned, t[:, :, 2], packed=True)),
+       "match_packed_zero_background_input_ms": graph_timed(lambda: kernels.template_match(fsparse, t[:, :, 2], packed=True)),
+       "match_packed_prev1_digit_outside_frame_ms": graph_timed(lambda: kernels.template_match(f, t[:, :, 2], packed=True, prev=pout, lin_fp=AT.lin_fp)),
        "paste_subtract_ms": graph_timed(lambda: AT.subtract_digit(left, *p2[1]))}
 fma = S * B * (FP - DP + 1) ** 2 * DP * DP
 row["TFMA_s_packed"] = fma / row["match_packed_ms"] / 1e9
