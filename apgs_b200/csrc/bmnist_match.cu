@@ -58,6 +58,14 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
     return r;
 }
 
+// e / sum of the softmax.  1 <= sum <= CP*CP (the maximum contributes exp(0)), so for e >= 2^-113 numerator and quotient are
+// normal numbers and div.rn stays on its fast path; below that (probabilities under 1e-34 -- a peaked map over 4761 positions
+// has many, and as denormal numerators they sent most warps through the division's slow path: 0.134 -> 0.151 ms per call on
+// residual frames) the quotient is e * (1 / sum), full speed on denormals and within one ulp of the division.
+__device__ __forceinline__ float softmax_quotient(float e, float sum, float inv_sum) {
+    return e >= 0x1p-113f ? __fdiv_rn(e, sum) : __fmul_rn(e, inv_sum);
+}
+
 template <int FP, int DP, int SEG>
 __global__ void __launch_bounds__(224, 5) k_template_match(MatchArgs a) {
     constexpr int CP = FP - DP + 1, NSEG = CP / SEG, FS = FP + 1, WIN = SEG + DP - 1;
@@ -170,10 +178,11 @@ __global__ void __launch_bounds__(224, 5) k_template_match(MatchArgs a) {
         constexpr int NCH = (CP * CP + 31) / 32;                        // 32-column chunks of the packed operand
         static_assert(NCH * 32 <= FP * FS, "the row fits the image region");
         float* s_row = s_f;
+        const float inv_se = __frcp_rn(se);
         if (live) {
             const int k0 = i0 * CP + seg * SEG;                          // lanes: consecutive i0 -> stride 69 = 5 mod 32: no bank conflicts
 #pragma unroll
-            for (int c = 0; c < SEG; ++c) s_row[k0 + c] = __fdiv_rn(acc[c], se);
+            for (int c = 0; c < SEG; ++c) s_row[k0 + c] = softmax_quotient(acc[c], se, inv_se);
         }
         for (int k = CP * CP + (int)threadIdx.x; k < NCH * 32; k += blockDim.x) s_row[k] = 0.f;
         __syncthreads();
