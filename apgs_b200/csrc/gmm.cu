@@ -275,7 +275,10 @@ __global__ void __launch_bounds__(P* LANES, 4) k_gmm_nss_im(NssArgs a, int S) {
     constexpr int RW = EtaTab<K, D>::RW;                                // reduction row (odd stride: no bank conflicts)
     const int N = NC ? NC : a.N, NK = N * K;
     const int ZS = nss_im_zstride(NK);
-    const size_t zreg = max((size_t)P * ZS, (size_t)P * LANES * RW);    // z rows, later the cross-lane reduction buffer
+    // z rows, later the cross-lane reduction buffer.  Label mode stages 1-byte labels instead of one-hot rows (P * LS bytes), so
+    // the region is the reduction buffer alone: 27 instead of 58 KB per CTA at the reference shape -- 4 CTAs per SM, not 3.
+    const size_t zreg = a.zl != nullptr ? max(((size_t)P * ((N + 15) & ~15) + 3) / 4, (size_t)P * LANES * RW)
+                                        : max((size_t)P * ZS, (size_t)P * LANES * RW);
     float* s_z = reinterpret_cast<float*>(smem);
     // The table holds the FACTORS, one short row per (point, label): { x'_0..x'_{D-1}, gamma_0..gamma_{K-1} }, and the
     // products gamma_k x'_d, gamma_k x'_d^2 are formed by the FMAs that accumulate them (FMA pipe has headroom, the
@@ -776,11 +779,13 @@ static int launch_nss_im(const NssArgs& a, cudaStream_t st) {
     constexpr int NS = K * (1 + 2 * D), TE = K + 2 * K * D;
     constexpr int RW = (TE > NS ? TE : NS) | 1;
     const long long S = a.R / a.B;
-    const size_t zreg = (max((size_t)kImP * nss_im_zstride(a.N * K), (size_t)kImP * kImLanes * RW) + 3) / 4 * 4;
+    const size_t zrows = a.zl != nullptr ? ((size_t)kImP * ((a.N + 15) & ~15) + 3) / 4 : (size_t)kImP * nss_im_zstride(a.N * K);
+    const size_t zreg = (max(zrows, (size_t)kImP * kImLanes * RW) + 3) / 4 * 4;
     const size_t smem = (zreg + (size_t)a.N * K * TE + (size_t)a.N * D) * 4;
     if (smem > 200 * 1024) {
         // the one-hot rows of 64 particles do not fit: 32 particles x 8 lanes
-        const size_t zreg8 = (max((size_t)kP * nss_im_zstride(a.N * K), (size_t)kP * kLanes * RW) + 3) / 4 * 4;
+        const size_t zrows8 = a.zl != nullptr ? ((size_t)kP * ((a.N + 15) & ~15) + 3) / 4 : (size_t)kP * nss_im_zstride(a.N * K);
+        const size_t zreg8 = (max(zrows8, (size_t)kP * kLanes * RW) + 3) / 4 * 4;
         const size_t smem8 = (zreg8 + (size_t)a.N * K * TE + (size_t)a.N * D) * 4;
         if (smem8 > 200 * 1024) return fail(APGS_E_SHAPE, "gmm_eta_posterior: N=%d too large for one tile", a.N);
         void (*kern8)(NssArgs, int) = a.stats != nullptr ? k_gmm_nss_im<K, D, kP, kLanes, true> : k_gmm_nss_im<K, D, kP, kLanes, false>;
